@@ -1,0 +1,259 @@
+"""Host-side mirror of the reference's hot-path routines, on top of the C ABI.
+
+The method names and argument meaning follow the Fortran module procedures they stand in for
+(buildH0 / buildS: dftb/nonscc.F90; unpackHS / packHS: dftb/sparse2dense.F90; getDensityMatrix /
+getEDensityMatrix: dftb/densitymatrix.F90; mulliken: dftb/populations.F90; derivative_shift:
+dftb/forces.F90; diagDenseMtx: dftbplus/eigenvects.F90), so the parity tests read like calls
+into the reference.  Arrays: numpy (host; copied by the library) or torch CUDA tensors (device;
+used in place).  Layout conventions are those of include/dftbp_b200.h: memory is the Fortran
+layout, numpy/torch see it C-ordered with reversed dimensions; dense matrices are column-major
+(numpy order='F', torch tensors with strides (1, ld) -- see `new_dense`).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+class DftbB200Error(RuntimeError):
+    """Non-zero status from libdftbp_b200 (the Fortran shim raises TStatus / calls error())."""
+
+    def __init__(self, code, msg):
+        super().__init__("libdftbp_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if _is_torch(x):
+        return ctypes.c_void_p(x.data_ptr())
+    return ctypes.c_void_p(x.ctypes.data)
+
+
+def _ld(mat):
+    """leading dimension of a column-major dense matrix (numpy F-order or torch strides (1, ld))."""
+    if _is_torch(mat):
+        assert mat.dim() == 2 and (mat.stride(0) == 1 or mat.shape[0] == 1), "dense matrix must be column-major"
+        return max(int(mat.stride(1)), int(mat.shape[0])) if mat.shape[1] > 1 else int(mat.shape[0])
+    assert mat.flags.f_contiguous, "dense matrix must be order='F'"
+    return mat.shape[0]
+
+
+def new_dense(n, dtype=None, device=None):
+    """Column-major n x n torch matrix on the GPU, indexed [row, col]."""
+    import torch
+    return torch.zeros((n, n), dtype=dtype or torch.float64, device=device or "cuda").t()
+
+
+def _f64(a):
+    return a if _is_torch(a) else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return a if _is_torch(a) else np.ascontiguousarray(a, dtype=np.int32)
+
+
+class HotPath:
+    """One library context (= one TDftbPlus instance on one GPU)."""
+
+    def __init__(self, device=0, rank=0, nranks=1):
+        self._L = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self._L.dftbp_b200_create(ctypes.byref(h), device, rank, nranks)
+        self._h = h
+        if rc != 0:
+            msg = self._L.dftbp_b200_last_error(h).decode() if h else "create failed"
+            if h:
+                self._L.dftbp_b200_destroy(h)
+            self._h = None
+            raise DftbB200Error(rc, msg)
+        self.device, self.rank, self.nranks = device, rank, nranks
+        self.geo = None
+        self.mOrb = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.dftbp_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise DftbB200Error(rc, self._L.dftbp_b200_last_error(self._h).decode())
+
+    # ---- plumbing ------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self._L.dftbp_b200_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self._ck(self._L.dftbp_b200_synchronize(self._h))
+
+    @property
+    def kernel_launches(self):
+        return int(self._L.dftbp_b200_kernel_launches(self._h))
+
+    @property
+    def num_pairs(self):
+        return int(self._L.dftbp_b200_num_pairs(self._h))
+
+    # ---- once per run ---------------------------------------------------------------------
+    def set_orbitals(self, ang_shells):
+        """TOrbitals: ang_shells[iSp] = list of shell angular momenta of species iSp+1."""
+        nsp = len(ang_shells)
+        msh = max(len(a) for a in ang_shells)
+        n_shell = np.array([len(a) for a in ang_shells], dtype=np.int32)
+        ang = np.zeros((nsp, msh), dtype=np.int32)
+        for i, a in enumerate(ang_shells):
+            ang[i, :len(a)] = a
+        self._ck(self._L.dftbp_b200_set_orbitals(self._h, nsp, msh, _ptr(n_shell), _ptr(ang)))
+        self.ang_shells = [list(a) for a in ang_shells]
+        self.nOrbSpecies = np.array([sum(2 * l + 1 for l in a) for a in ang_shells], dtype=np.int32)
+        self.mOrb = int(self.nOrbSpecies.max())
+        self.mShell = msh
+
+    def set_sk_table(self, which, sp1, sp2, dist, tab, method=2):
+        """SlakoCont addTable: tab[nGrid, nInteg] (order='F'), which 0 = H, 1 = S."""
+        tab = np.asfortranarray(tab, dtype=np.float64)
+        self._ck(self._L.dftbp_b200_set_sk_table(self._h, which, sp1, sp2, tab.shape[0], tab.shape[1],
+                                                 float(dist), _ptr(tab), method))
+
+    def sk_cutoff(self):
+        c = ctypes.c_double()
+        self._ck(self._L.dftbp_b200_get_sk_cutoff(self._h, ctypes.byref(c)))
+        return c.value
+
+    # ---- once per geometry ------------------------------------------------------------------
+    def set_geometry(self, geo):
+        """geo: dict with the arrays of SURVEY.md section 8.0 (see dftbplus_b200.geometry)."""
+        g = geo
+        self._ck(self._L.dftbp_b200_set_geometry(
+            self._h, g["nAtom"], g["nAllAtom"], g["mNeigh"], _ptr(_f64(g["coords"])), _ptr(_i32(g["species"])),
+            _ptr(_i32(g["img2CentCell"])), _ptr(_i32(g["iCellVec"])), g["cellVec"].shape[0],
+            _ptr(_f64(g["cellVec"])), _ptr(_i32(g["nNeighbourSK"])), _ptr(_i32(g["iNeighbour"])),
+            _ptr(_i32(g["iPair"])), _ptr(_i32(g["iAtomStart"])), g["sparseSize"]))
+        self.geo = g
+
+    def update_coords(self, coords):
+        self._ck(self._L.dftbp_b200_update_coords(self._h, _ptr(_f64(coords))))
+
+    # ---- K1 ---------------------------------------------------------------------------------
+    def _selfegy(self, selfegy):
+        se = np.zeros((len(self.ang_shells), self.mShell))
+        for i, row in enumerate(selfegy):
+            se[i, :len(row)] = row
+        return se
+
+    def _sparse_out(self, out):
+        return np.zeros(self.geo["sparseSize"]) if out is None else out
+
+    def buildH0(self, selfegy, ham=None):
+        ham = self._sparse_out(ham)
+        se = self._selfegy(selfegy)
+        self._ck(self._L.dftbp_b200_build_h0(self._h, _ptr(se), _ptr(ham)))
+        return ham
+
+    def buildS(self, over=None):
+        over = self._sparse_out(over)
+        self._ck(self._L.dftbp_b200_build_s(self._h, _ptr(over)))
+        return over
+
+    def buildH0S(self, selfegy, ham=None, over=None):
+        ham, over = self._sparse_out(ham), self._sparse_out(over)
+        se = self._selfegy(selfegy)
+        self._ck(self._L.dftbp_b200_build_h0_s(self._h, _ptr(se), _ptr(ham), _ptr(over)))
+        return ham, over
+
+    # ---- K2 ---------------------------------------------------------------------------------
+    def unpackHS(self, orig, kpoint=None, square=None):
+        n = self.geo["nOrb"]
+        if kpoint is None:
+            if square is None:
+                square = np.zeros((n, n), order="F")
+            self._ck(self._L.dftbp_b200_unpack_hs_real(self._h, _ptr(_f64(orig)), _ptr(square), _ld(square)))
+        else:
+            if square is None:
+                square = np.zeros((n, n), order="F", dtype=np.complex128)
+            kp = (ctypes.c_double * 3)(*[float(x) for x in kpoint])
+            self._ck(self._L.dftbp_b200_unpack_hs_cplx(self._h, _ptr(_f64(orig)), kp, _ptr(square), _ld(square)))
+        return square
+
+    def packHS(self, primitive, square, kpoint=None, kweight=1.0):
+        """Accumulates into primitive (in place) like the reference."""
+        if kpoint is None:
+            self._ck(self._L.dftbp_b200_pack_hs_real(self._h, _ptr(primitive), _ptr(square), _ld(square)))
+        else:
+            kp = (ctypes.c_double * 3)(*[float(x) for x in kpoint])
+            self._ck(self._L.dftbp_b200_pack_hs_cplx(self._h, _ptr(primitive), _ptr(square), _ld(square), kp,
+                                                     float(kweight)))
+        return primitive
+
+    # ---- K3 ---------------------------------------------------------------------------------
+    def _dm(self, eigvecs, filling, weights, dm):
+        cplx = (str(eigvecs.dtype).endswith("complex128"))
+        n = eigvecs.shape[0]
+        if dm is None:
+            if _is_torch(eigvecs):
+                dm = new_dense(n, dtype=eigvecs.dtype, device=eigvecs.device)
+            else:
+                dm = np.zeros((n, n), order="F", dtype=eigvecs.dtype)
+        fn = self._L.dftbp_b200_density_matrix_cplx if cplx else self._L.dftbp_b200_density_matrix_real
+        self._ck(fn(self._h, _ptr(dm), _ptr(eigvecs), n, _ld(eigvecs), _ptr(_f64(filling)),
+                    _ptr(None if weights is None else _f64(weights))))
+        return dm
+
+    def getDensityMatrix(self, eigvecs, filling, dm=None):
+        """TDensityMatrix%getDensityMatrix (full, real or complex by dtype)."""
+        return self._dm(eigvecs, filling, None, dm)
+
+    def getEDensityMatrix(self, eigvecs, filling, eigen, dm=None):
+        """TDensityMatrix%getEDensityMatrix: weights filling*eigen, nLevels from filling."""
+        w = filling * eigen
+        return self._dm(eigvecs, filling, w, dm)
+
+    # ---- K4 ---------------------------------------------------------------------------------
+    def mulliken(self, over, rho, qq=None, block=False):
+        nA = self.geo["nAtom"]
+        if qq is None:
+            qq = np.zeros((nA, self.mOrb, self.mOrb) if block else (nA, self.mOrb))
+        fn = self._L.dftbp_b200_mulliken_block if block else self._L.dftbp_b200_mulliken_orbital
+        self._ck(fn(self._h, _ptr(qq), _ptr(_f64(over)), _ptr(_f64(rho))))
+        return qq
+
+    # ---- K5 ---------------------------------------------------------------------------------
+    def derivative_shift(self, dm, edm, shift=None, diff_type=1, delta=0.0, deriv=None):
+        """dm[nSpin, sparseSize] (or 1-D), edm[sparseSize], shift[nSpin, nAtom, mOrb, mOrb] or None."""
+        if not _is_torch(dm):
+            dm = np.ascontiguousarray(np.atleast_2d(dm), dtype=np.float64)
+        n_spin = dm.shape[0] if dm.ndim == 2 else 1
+        if deriv is None:
+            deriv = np.zeros((self.geo["nAtom"], 3))
+        self._ck(self._L.dftbp_b200_derivative_shift(
+            self._h, _ptr(deriv), _ptr(dm), n_spin, _ptr(_f64(edm)),
+            _ptr(None if shift is None else _f64(shift)), diff_type, float(delta)))
+        return deriv
+
+    # ---- cuSOLVER ---------------------------------------------------------------------------
+    def diagDenseMtx(self, H, S, eigen=None, jobz="V"):
+        """hegvd: H, S column-major, overwritten (H <- eigenvectors); returns eigenvalues."""
+        n = H.shape[0]
+        cplx = str(H.dtype).endswith("complex128")
+        if eigen is None:
+            if _is_torch(H):
+                import torch
+                eigen = torch.zeros(n, dtype=torch.float64, device=H.device)
+            else:
+                eigen = np.zeros(n)
+        fn = self._L.dftbp_b200_hegv_cplx if cplx else self._L.dftbp_b200_hegv_real
+        self._ck(fn(self._h, _ptr(H), _ptr(S), _ptr(eigen), n, _ld(H), jobz.encode()[0:1]))
+        return eigen

@@ -1,0 +1,247 @@
+// common.cuh -- context, error handling and host/device pointer plumbing of libdftbp_b200.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dftbp_b200.h"
+
+namespace dftbp_b200 {
+
+constexpr int kMaxOrb = 16;   // s+p+d+f
+constexpr int kMaxInteg = 32; // >= integrals per species pair (spdf-spdf = 30)
+constexpr int kWarpsPerCta = 8;
+
+// One equidistant SK table on the device (TSlakoEqGrid, dftb/slakoeqgrid.F90:25-33).
+struct SkTableDev {
+  const double *tab;   // (nGrid, nInteg) column-major
+  const double *tail;  // (3, nInteg): y1, y1p, y1pp of the 5th-order tail (slakoeqgrid.F90:228-240)
+  double dist, invDist, rMax;
+  int nGrid, nInteg, method, pad;
+};
+
+// A_k = sum_mu t[mu] * V[vBase + mu]   (tools/gen_sk_gaunt.py)
+struct ADesc {
+  double t[4];
+  int vBase, cnt, pad0, pad1;  // 48 bytes: keeps 16-byte alignment for vector loads
+};
+
+struct DevTerm {
+  double coef;
+  int y, aslot;
+};
+
+// Everything the pair kernels need for one ordered species pair (sp1 = atom, sp2 = neighbour).
+struct SpPairProg {
+  SkTableDev H, S;
+  int nOrb1, nOrb2, nInteg, nY;
+  int aOff;     // first ADesc
+  int elemOff;  // first entry of elemStart (nOrb1*nOrb2 + 1 entries, absolute term indices)
+  int pad0, pad1;
+};
+
+struct Geometry {
+  int nAtom = 0, nAllAtom = 0, mNeigh = 0, nCellVec = 0, sparseSize = 0, nOrb = 0;
+  double *coords = nullptr;      // (3, nAllAtom)
+  int *species = nullptr;        // (nAllAtom)
+  int *img2CentCell = nullptr;   // (nAllAtom)
+  int *iCellVec = nullptr;       // (nAllAtom)
+  double *cellVec = nullptr;     // (3, nCellVec)
+  int *nNeighbourSK = nullptr;   // (nAtom)
+  int *iNeighbour = nullptr;     // (mNeigh+1, nAtom)
+  int *iPair = nullptr;          // (mNeigh+1, nAtom)
+  int *iAtomStart = nullptr;     // (nAtom+1)
+  int *workAll = nullptr;        // flat (iNeigh + ld*iAtom0) of every block (iNeigh >= 0), all atoms
+  int *workMine = nullptr;       // same, this rank's contiguous atom chunk (build_*)
+  int *workLoad = nullptr;       // same, this rank's workload-balanced atoms (mulliken, forces)
+  long long nWorkAll = 0, nWorkMine = 0, nWorkLoad = 0, nPairsMine = 0;
+  bool hasDuplicates = false;    // two blocks of one atom fold onto the same dense block
+};
+
+struct Staging {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+};
+
+struct PendingCopy {
+  void *host;
+  const void *dev;
+  size_t bytes;
+};
+
+}  // namespace dftbp_b200
+
+struct dftbp_b200_ctx {
+  int device = 0, rank = 0, nRanks = 1;
+  cudaStream_t stream = nullptr;
+  bool ownStream = true;
+  std::string err;
+  long long launches = 0;
+  int smCount = 148;
+
+  // orbitals
+  int nSpecies = 0, mShell = 0, mOrb = 0;
+  std::vector<int> nShell, angShell, nOrbSpecies;
+  int *dNOrbSpecies = nullptr;
+  int *dOrbShell = nullptr;  // (mOrb, nSpecies): shell index of each orbital
+  // SK programs
+  std::vector<dftbp_b200::SpPairProg> progs;  // [sp1 + nSpecies*sp2]
+  dftbp_b200::SpPairProg *dProgs = nullptr;
+  dftbp_b200::ADesc *dADesc = nullptr;
+  int *dElemStart = nullptr;
+  dftbp_b200::DevTerm *dTerms = nullptr;
+  void *dYDesc = nullptr;
+  bool progsDirty = true;
+  std::vector<void *> tableAllocs;
+  double cutoff = 0.0;
+
+  dftbp_b200::Geometry geo;
+  std::vector<dftbp_b200::Staging> staging;
+  std::vector<dftbp_b200::PendingCopy> pending;
+  double *dSelfE = nullptr;  // (mOrb, nSpecies) on-site energy per orbital
+  void *solverHandle = nullptr;
+  void *solverWork = nullptr;
+  size_t solverWorkBytes = 0;
+  int *dInfo = nullptr;
+};
+
+namespace dftbp_b200 {
+
+inline int fail(dftbp_b200_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+#define DFTBP_CUDA(ctx, call)                                                                   \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      return dftbp_b200::fail(ctx, DFTBP_B200_ECUDA, "%s failed: %s (%s:%d)", #call,            \
+                              cudaGetErrorString(e_), __FILE__, __LINE__);                      \
+  } while (0)
+
+#define DFTBP_CHECK(ctx, cond, msg)                                                             \
+  do {                                                                                          \
+    if (!(cond)) return dftbp_b200::fail(ctx, DFTBP_B200_EINVAL, "%s (%s:%d)", msg, __FILE__, __LINE__); \
+  } while (0)
+
+#define DFTBP_TRY(call)                 \
+  do {                                  \
+    int rc_ = (call);                   \
+    if (rc_ != 0) return rc_;           \
+  } while (0)
+
+inline bool isDevicePtr(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Staging slots (grow-only device buffers for host-pointer callers).
+enum Slot { kSlotA = 0, kSlotB, kSlotC, kSlotD, kSlotE, kSlotF, kSlotCount };
+
+inline int stagingGet(dftbp_b200_ctx *ctx, int slot, size_t bytes, void **out) {
+  if ((int)ctx->staging.size() < kSlotCount) ctx->staging.resize(kSlotCount);
+  Staging &s = ctx->staging[slot];
+  if (s.bytes < bytes) {
+    if (s.ptr) DFTBP_CUDA(ctx, cudaFree(s.ptr));
+    s.ptr = nullptr;
+    s.bytes = 0;
+    cudaError_t e = cudaMalloc(&s.ptr, bytes);
+    if (e != cudaSuccess)
+      return fail(ctx, DFTBP_B200_ENOMEM, "cudaMalloc of %zu staging bytes failed: %s", bytes,
+                  cudaGetErrorString(e));
+    s.bytes = bytes;
+  }
+  *out = s.ptr;
+  return 0;
+}
+
+// Device view of an input array (copies H2D when the caller passed a host pointer).
+template <class T>
+inline int devIn(dftbp_b200_ctx *ctx, int slot, const T *p, size_t count, const T **out) {
+  if (p == nullptr) return fail(ctx, DFTBP_B200_EINVAL, "null input pointer");
+  if (isDevicePtr(p)) {
+    *out = p;
+    return 0;
+  }
+  void *d;
+  DFTBP_TRY(stagingGet(ctx, slot, count * sizeof(T), &d));
+  DFTBP_CUDA(ctx, cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  *out = static_cast<const T *>(d);
+  return 0;
+}
+
+// Device view of an output (or in/out) array; host pointers get a staging buffer whose content
+// is copied back by finish().
+template <class T>
+inline int devOut(dftbp_b200_ctx *ctx, int slot, T *p, size_t count, bool copyIn, T **out) {
+  if (p == nullptr) return fail(ctx, DFTBP_B200_EINVAL, "null output pointer");
+  if (isDevicePtr(p)) {
+    *out = p;
+    return 0;
+  }
+  void *d;
+  DFTBP_TRY(stagingGet(ctx, slot, count * sizeof(T), &d));
+  if (copyIn)
+    DFTBP_CUDA(ctx, cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->pending.push_back({p, d, count * sizeof(T)});
+  *out = static_cast<T *>(d);
+  return 0;
+}
+
+// Copy staged outputs back and make host results visible; no-op (and no sync) for device callers.
+inline int finish(dftbp_b200_ctx *ctx) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    ctx->pending.clear();
+    return fail(ctx, DFTBP_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  }
+  if (ctx->pending.empty()) return 0;
+  for (const PendingCopy &c : ctx->pending)
+    DFTBP_CUDA(ctx, cudaMemcpyAsync(c.host, c.dev, c.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->pending.clear();
+  DFTBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+template <class T>
+inline int uploadNew(dftbp_b200_ctx *ctx, T **dst, const T *src, size_t count) {
+  if (*dst) cudaFree(*dst);
+  *dst = nullptr;
+  if (count == 0) return 0;
+  cudaError_t e = cudaMalloc((void **)dst, count * sizeof(T));
+  if (e != cudaSuccess)
+    return fail(ctx, DFTBP_B200_ENOMEM, "cudaMalloc(%zu) failed: %s", count * sizeof(T),
+                cudaGetErrorString(e));
+  cudaMemcpyKind kind = isDevicePtr(src) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  DFTBP_CUDA(ctx, cudaMemcpyAsync(*dst, src, count * sizeof(T), kind, ctx->stream));
+  // the source may be a temporary host vector: make the copy complete before returning
+  DFTBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+inline int gridFor(const dftbp_b200_ctx *ctx, long long nWarpItems, int warpsPerCta, int ctasPerSm) {
+  long long need = (nWarpItems + warpsPerCta - 1) / warpsPerCta;
+  long long cap = (long long)ctx->smCount * ctasPerSm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// implemented in context.cu / solver.cu
+int syncPrograms(dftbp_b200_ctx *ctx);
+void solverDestroy(dftbp_b200_ctx *ctx);
+
+}  // namespace dftbp_b200

@@ -1,0 +1,407 @@
+// context.cu -- lifecycle, TOrbitals / TSlakoCont upload, geometry upload.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+#include "sk_gaunt_tables.h"
+
+using namespace dftbp_b200;
+
+namespace {
+
+constexpr double kDistFudge = 1.0;      // common/accuracy.F90:44
+constexpr double kDistFudgeOld = 0.3;   // common/accuracy.F90:48
+constexpr double kDeltaR = 1e-5;        // dftb/slakoeqgrid.F90:89
+
+// 8-point Neville tableau on a uniform grid, same operation order as polyInterU2
+// (math/interpolation.F90:182-239) so that the tail coefficients below carry the reference's
+// own rounding (their second derivative amplifies rounding by 1/deltaR^2, SURVEY.md hard part 1).
+double nevilleUniform8(const double *xp, const double *yp, double xx) {
+  const int nn = 8;
+  double cc[8], dd[8], delta[7];
+  for (int ii = 1; ii <= nn - 1; ++ii) delta[ii - 1] = 1.0 / (xp[ii] - xp[0]);
+  for (int ii = 0; ii < nn; ++ii) cc[ii] = dd[ii] = yp[ii];
+  int iCl = (int)std::ceil((xx - xp[0]) * delta[0]);
+  iCl = std::min(std::max(iCl, 1), nn);
+  double yy = yp[iCl - 1];
+  iCl -= 1;
+  for (int mm = 1; mm <= nn - 1; ++mm) {
+    for (int ii = 1; ii <= nn - mm; ++ii) {
+      double r2 = (dd[ii - 1] - cc[ii]) * delta[mm - 1];
+      cc[ii - 1] = (xp[ii - 1] - xx) * r2;
+      dd[ii - 1] = (xp[ii + mm - 1] - xx) * r2;
+    }
+    double dyy;
+    if (2 * iCl < nn - mm) {
+      dyy = cc[iCl];
+    } else {
+      dyy = dd[iCl - 1];
+      iCl -= 1;
+    }
+    yy = yy + dyy;
+  }
+  return yy;
+}
+
+// y1, y1p, y1pp at the last grid point (SlakoEqGrid_interNew_, slakoeqgrid.F90:224-240)
+void tailCoefficients(int nGrid, int nInteg, double dist, const double *tab, std::vector<double> &out) {
+  out.assign(3 * (size_t)nInteg, 0.0);
+  if (nGrid < 9) return;
+  double xa[8], ya[8];
+  for (int ii = 1; ii <= 8; ++ii) xa[ii - 1] = (double)(nGrid - 8 + ii) * dist;
+  for (int c = 0; c < nInteg; ++c) {
+    for (int ii = 0; ii < 8; ++ii) ya[ii] = tab[(size_t)(nGrid - 8 + ii) + (size_t)nGrid * c];
+    double y0 = nevilleUniform8(xa, ya, xa[7] - kDeltaR);
+    double y2 = nevilleUniform8(xa, ya, xa[7] + kDeltaR);
+    double y1 = ya[7];
+    out[3 * c + 0] = y1;
+    out[3 * c + 1] = (y2 - y0) / (2.0 * kDeltaR);
+    out[3 * c + 2] = (y2 + y0 - 2.0 * y1) / (kDeltaR * kDeltaR);
+  }
+}
+
+void freeGeometry(Geometry &g) {
+  cudaFree(g.coords); cudaFree(g.species); cudaFree(g.img2CentCell); cudaFree(g.iCellVec);
+  cudaFree(g.cellVec); cudaFree(g.nNeighbourSK); cudaFree(g.iNeighbour); cudaFree(g.iPair);
+  cudaFree(g.iAtomStart);
+  if (g.workMine != g.workAll) cudaFree(g.workMine);
+  if (g.workLoad != g.workAll) cudaFree(g.workLoad);
+  cudaFree(g.workAll);
+  g = Geometry();
+}
+
+template <class T>
+std::vector<T> toHost(const T *p, size_t n) {
+  std::vector<T> v(n);
+  if (n == 0) return v;
+  if (isDevicePtr(p)) cudaMemcpy(v.data(), p, n * sizeof(T), cudaMemcpyDeviceToHost);
+  else std::memcpy(v.data(), p, n * sizeof(T));
+  return v;
+}
+
+}  // namespace
+
+// getChunkRanges, common/schedule.F90:230-263 (0-based rank, 1-based inclusive range)
+static void chunkRange(int groupSize, int myRank, int first, int last, int *lf, int *ll) {
+  int len = last - first + 1, nLocal = len / groupSize, rem = len % groupSize;
+  if (myRank < rem) {
+    nLocal += 1;
+    *lf = first + myRank * nLocal;
+  } else {
+    *lf = first + rem * (nLocal + 1) + (myRank - rem) * nLocal;
+  }
+  *ll = std::min(*lf + nLocal - 1, last);
+}
+
+extern "C" {
+
+const char *dftbp_b200_version(void) { return "dftbp_b200 0.1.0 (sm_100a)"; }
+
+int dftbp_b200_create(dftbp_b200_ctx **out, int device, int rank, int nRanks) {
+  if (!out) return DFTBP_B200_EINVAL;
+  *out = nullptr;
+  int nDev = 0;
+  cudaError_t e = cudaGetDeviceCount(&nDev);
+  dftbp_b200_ctx *ctx = new dftbp_b200_ctx();
+  *out = ctx;  // returned even on failure so that last_error is readable
+  if (e != cudaSuccess || nDev == 0)
+    return fail(ctx, DFTBP_B200_ENODEVICE,
+                "no CUDA device available (%s); libdftbp_b200 has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= nDev)
+    return fail(ctx, DFTBP_B200_EINVAL, "device %d out of range (0..%d)", device, nDev - 1);
+  if (nRanks < 1 || rank < 0 || rank >= nRanks)
+    return fail(ctx, DFTBP_B200_EINVAL, "bad rank %d of %d", rank, nRanks);
+  ctx->device = device; ctx->rank = rank; ctx->nRanks = nRanks;
+  DFTBP_CUDA(ctx, cudaSetDevice(device));
+  DFTBP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  cudaDeviceProp prop;
+  DFTBP_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+  ctx->smCount = prop.multiProcessorCount;
+  DFTBP_CUDA(ctx, cudaMalloc((void **)&ctx->dInfo, sizeof(int)));
+  return 0;
+}
+
+int dftbp_b200_destroy(dftbp_b200_ctx *ctx) {
+  if (!ctx) return 0;
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  freeGeometry(ctx->geo);
+  for (void *p : ctx->tableAllocs) cudaFree(p);
+  for (Staging &s : ctx->staging) cudaFree(s.ptr);
+  cudaFree(ctx->dNOrbSpecies); cudaFree(ctx->dOrbShell); cudaFree(ctx->dProgs); cudaFree(ctx->dADesc);
+  cudaFree(ctx->dElemStart); cudaFree(ctx->dTerms); cudaFree(ctx->dYDesc); cudaFree(ctx->dSelfE);
+  cudaFree(ctx->solverWork); cudaFree(ctx->dInfo);
+  solverDestroy(ctx);
+  if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+
+const char *dftbp_b200_last_error(const dftbp_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int dftbp_b200_set_stream(dftbp_b200_ctx *ctx, void *s) {
+  if (!ctx) return DFTBP_B200_EINVAL;
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (s == nullptr) {
+    if (!ctx->ownStream) {
+      DFTBP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+      ctx->ownStream = true;
+    }
+    return 0;
+  }
+  if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)s;
+  ctx->ownStream = false;
+  return 0;
+}
+
+void *dftbp_b200_get_stream(dftbp_b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int dftbp_b200_synchronize(dftbp_b200_ctx *ctx) {
+  if (!ctx) return DFTBP_B200_EINVAL;
+  DFTBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+long long dftbp_b200_kernel_launches(const dftbp_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+long long dftbp_b200_num_pairs(const dftbp_b200_ctx *ctx) { return ctx ? ctx->geo.nPairsMine : 0; }
+
+int dftbp_b200_set_orbitals(dftbp_b200_ctx *ctx, int nSpecies, int mShell, const int *nShell,
+                            const int *angShell) {
+  if (!ctx) return DFTBP_B200_EINVAL;
+  DFTBP_CHECK(ctx, nSpecies > 0 && mShell > 0 && nShell && angShell, "set_orbitals: bad arguments");
+  ctx->nSpecies = nSpecies;
+  ctx->mShell = mShell;
+  ctx->nShell.assign(nShell, nShell + nSpecies);
+  ctx->angShell.assign(angShell, angShell + (size_t)mShell * nSpecies);
+  ctx->nOrbSpecies.assign(nSpecies, 0);
+  ctx->mOrb = 0;
+  for (int sp = 0; sp < nSpecies; ++sp) {
+    DFTBP_CHECK(ctx, nShell[sp] >= 1 && nShell[sp] <= mShell, "set_orbitals: nShell out of range");
+    for (int sh = 0; sh < nShell[sp]; ++sh) {
+      int l = angShell[sh + mShell * sp];
+      DFTBP_CHECK(ctx, l >= 0 && l <= skg::kLMax, "set_orbitals: angular momentum must be 0..3");
+      ctx->nOrbSpecies[sp] += 2 * l + 1;
+    }
+    ctx->mOrb = std::max(ctx->mOrb, ctx->nOrbSpecies[sp]);
+  }
+  DFTBP_CHECK(ctx, ctx->mOrb <= kMaxOrb, "set_orbitals: more than 16 orbitals per atom");
+  // shell index of each orbital (iShellOrb, type/orbitals.F90:33-35), 0-based
+  std::vector<int> orbShell((size_t)ctx->mOrb * nSpecies, 0);
+  for (int sp = 0; sp < nSpecies; ++sp) {
+    int o = 0;
+    for (int sh = 0; sh < nShell[sp]; ++sh)
+      for (int k = 0; k < 2 * angShell[sh + mShell * sp] + 1; ++k) orbShell[o++ + ctx->mOrb * sp] = sh;
+  }
+  DFTBP_TRY(uploadNew(ctx, &ctx->dNOrbSpecies, ctx->nOrbSpecies.data(), nSpecies));
+  DFTBP_TRY(uploadNew(ctx, &ctx->dOrbShell, orbShell.data(), orbShell.size()));
+  DFTBP_TRY(uploadNew(ctx, (skg::YDesc **)&ctx->dYDesc, skg::kYDesc, skg::kNY));
+
+  // Build the per-species-pair programs from the generic Gaunt tables.
+  std::vector<ADesc> aDesc;
+  std::vector<int> elemStart;
+  std::vector<DevTerm> terms;
+  ctx->progs.assign((size_t)nSpecies * nSpecies, SpPairProg());
+  for (int sp2 = 0; sp2 < nSpecies; ++sp2)
+    for (int sp1 = 0; sp1 < nSpecies; ++sp1) {
+      SpPairProg &pg = ctx->progs[sp1 + nSpecies * sp2];
+      std::memset(&pg, 0, sizeof(pg));
+      pg.nOrb1 = ctx->nOrbSpecies[sp1];
+      pg.nOrb2 = ctx->nOrbSpecies[sp2];
+      pg.aOff = (int)aDesc.size();
+      pg.elemOff = (int)elemStart.size();
+      std::vector<std::vector<DevTerm>> perElem((size_t)pg.nOrb1 * pg.nOrb2);
+      int ind = 0, iCol = 0, lmax1 = 0, lmax2 = 0;
+      for (int sh1 = 0; sh1 < nShell[sp1]; ++sh1) {
+        int l1 = angShell[sh1 + mShell * sp1];
+        lmax1 = std::max(lmax1, l1);
+        int iRow = 0;
+        for (int sh2 = 0; sh2 < nShell[sp2]; ++sh2) {
+          int l2 = angShell[sh2 + mShell * sp2], lmin = std::min(l1, l2);
+          lmax2 = std::max(lmax2, l2);
+          for (int k = 0; k <= lmin; ++k) {
+            ADesc d;
+            for (int mu = 0; mu < 4; ++mu) d.t[mu] = mu <= lmin ? skg::kT[l1][l2][k][mu] : 0.0;
+            d.vBase = ind;
+            d.cnt = lmin + 1;
+            d.pad0 = d.pad1 = 0;
+            aDesc.push_back(d);
+          }
+          for (int a = 0; a < 2 * l1 + 1; ++a)
+            for (int b = 0; b < 2 * l2 + 1; ++b) {
+              int e = (iRow + b) + pg.nOrb2 * (iCol + a);
+              int t0 = skg::kElemStart[l1][l2][a * (2 * l2 + 1) + b];
+              int t1 = skg::kElemStart[l1][l2][a * (2 * l2 + 1) + b + 1];
+              for (int t = t0; t < t1; ++t)
+                perElem[e].push_back({skg::kTerms[t].coef, skg::kTerms[t].y, ind + skg::kTerms[t].k});
+            }
+          ind += lmin + 1;
+          iRow += 2 * l2 + 1;
+        }
+        iCol += 2 * l1 + 1;
+      }
+      pg.nInteg = ind;
+      DFTBP_CHECK(ctx, ind <= kMaxInteg, "set_orbitals: too many integrals per species pair");
+      pg.nY = (lmax1 + lmax2 + 1) * (lmax1 + lmax2 + 1);
+      for (auto &v : perElem) {
+        elemStart.push_back((int)terms.size());
+        terms.insert(terms.end(), v.begin(), v.end());
+      }
+      elemStart.push_back((int)terms.size());
+    }
+  DFTBP_TRY(uploadNew(ctx, &ctx->dADesc, aDesc.data(), aDesc.size()));
+  DFTBP_TRY(uploadNew(ctx, &ctx->dElemStart, elemStart.data(), elemStart.size()));
+  DFTBP_TRY(uploadNew(ctx, &ctx->dTerms, terms.data(), terms.size()));
+  cudaFree(ctx->dSelfE);
+  ctx->dSelfE = nullptr;
+  DFTBP_CUDA(ctx, cudaMalloc((void **)&ctx->dSelfE, sizeof(double) * ctx->mOrb * nSpecies));
+  ctx->progsDirty = true;
+  return 0;
+}
+
+int dftbp_b200_set_sk_table(dftbp_b200_ctx *ctx, int which, int sp1, int sp2, int nGrid,
+                            int nInteg, double dist, const double *skTab, int method) {
+  if (!ctx) return DFTBP_B200_EINVAL;
+  DFTBP_CHECK(ctx, ctx->nSpecies > 0, "set_sk_table: call set_orbitals first");
+  DFTBP_CHECK(ctx, which == 0 || which == 1, "set_sk_table: which must be 0 (H) or 1 (S)");
+  DFTBP_CHECK(ctx, sp1 >= 1 && sp1 <= ctx->nSpecies && sp2 >= 1 && sp2 <= ctx->nSpecies,
+              "set_sk_table: species out of range");
+  DFTBP_CHECK(ctx, skTab && dist > 0.0, "set_sk_table: bad table");
+  SpPairProg &pg = ctx->progs[(sp1 - 1) + ctx->nSpecies * (sp2 - 1)];
+  if (nInteg != pg.nInteg)
+    return fail(ctx, DFTBP_B200_EINVAL, "set_sk_table: species pair (%d,%d) needs %d integrals, got %d",
+                sp1, sp2, pg.nInteg, nInteg);
+  if (method == DFTBP_B200_SK_EQGRID_OLD)
+    return fail(ctx, DFTBP_B200_ENOTIMPL,
+                "OldSKInterpolation (skEqGridOld, slakoeqgrid.F90:248-317) is not built yet");
+  DFTBP_CHECK(ctx, method == DFTBP_B200_SK_EQGRID_NEW, "set_sk_table: unknown interpolation method");
+  // SlakoEqGrid_interNew_ aborts for tables shorter than nInterNew_+1 (slakoeqgrid.F90:207-210)
+  if (nGrid < 9)
+    return fail(ctx, DFTBP_B200_EINVAL, "SlakoEqGrid: Not enough points in the SK-table for interpolation!");
+  std::vector<double> host = toHost(skTab, (size_t)nGrid * nInteg), tail;
+  tailCoefficients(nGrid, nInteg, dist, host.data(), tail);
+  double *dTab = nullptr, *dTail = nullptr;
+  DFTBP_TRY(uploadNew(ctx, &dTab, host.data(), host.size()));
+  DFTBP_TRY(uploadNew(ctx, &dTail, tail.data(), tail.size()));
+  ctx->tableAllocs.push_back(dTab);
+  ctx->tableAllocs.push_back(dTail);
+  SkTableDev &t = which == 0 ? pg.H : pg.S;
+  t.tab = dTab; t.tail = dTail; t.dist = dist; t.invDist = 1.0 / dist;
+  t.nGrid = nGrid; t.nInteg = nInteg; t.method = method;
+  t.rMax = (double)nGrid * dist + kDistFudge;
+  ctx->cutoff = std::max(ctx->cutoff, (double)nGrid * dist + (method == 1 ? kDistFudgeOld : kDistFudge));
+  ctx->progsDirty = true;
+  return 0;
+}
+
+int dftbp_b200_get_sk_cutoff(dftbp_b200_ctx *ctx, double *cutoff) {
+  if (!ctx || !cutoff) return DFTBP_B200_EINVAL;
+  *cutoff = ctx->cutoff;
+  return 0;
+}
+
+int dftbp_b200_set_geometry(dftbp_b200_ctx *ctx, int nAtom, int nAllAtom, int mNeigh,
+                            const double *coords, const int *species, const int *img2CentCell,
+                            const int *iCellVec, int nCellVec, const double *cellVec,
+                            const int *nNeighbourSK, const int *iNeighbour, const int *iPair,
+                            const int *iAtomStart, int sparseSize) {
+  if (!ctx) return DFTBP_B200_EINVAL;
+  DFTBP_CHECK(ctx, ctx->nSpecies > 0, "set_geometry: call set_orbitals first");
+  DFTBP_CHECK(ctx, nAtom > 0 && nAllAtom >= nAtom && mNeigh >= 0 && nCellVec >= 1 && sparseSize > 0,
+              "set_geometry: bad sizes");
+  DFTBP_CHECK(ctx, coords && species && img2CentCell && iCellVec && cellVec && nNeighbourSK &&
+                       iNeighbour && iPair && iAtomStart, "set_geometry: null array");
+  const int ld = mNeigh + 1;
+  std::vector<int> hN = toHost(nNeighbourSK, nAtom), hNb = toHost(iNeighbour, (size_t)ld * nAtom);
+  std::vector<int> hImg = toHost(img2CentCell, nAllAtom), hSp = toHost(species, nAllAtom);
+  std::vector<int> hStart = toHost(iAtomStart, nAtom + 1);
+  for (int i = 0; i < nAtom; ++i) {
+    DFTBP_CHECK(ctx, hN[i] >= 0 && hN[i] <= mNeigh, "set_geometry: nNeighbourSK exceeds mNeigh");
+    DFTBP_CHECK(ctx, hSp[i] >= 1 && hSp[i] <= ctx->nSpecies, "set_geometry: species out of range");
+    DFTBP_CHECK(ctx, hStart[i + 1] - hStart[i] == ctx->nOrbSpecies[hSp[i] - 1],
+                "set_geometry: iAtomStart inconsistent with the orbitals of the species");
+    for (int k = 0; k <= hN[i]; ++k) {
+      int a2 = hNb[k + (size_t)ld * i];
+      DFTBP_CHECK(ctx, a2 >= 1 && a2 <= nAllAtom, "set_geometry: iNeighbour entry out of range");
+    }
+  }
+  Geometry g;
+  freeGeometry(ctx->geo);
+  g.nAtom = nAtom; g.nAllAtom = nAllAtom; g.mNeigh = mNeigh; g.nCellVec = nCellVec;
+  g.sparseSize = sparseSize; g.nOrb = hStart[nAtom] - 1;
+  DFTBP_TRY(uploadNew(ctx, &g.coords, coords, (size_t)3 * nAllAtom));
+  DFTBP_TRY(uploadNew(ctx, &g.species, species, nAllAtom));
+  DFTBP_TRY(uploadNew(ctx, &g.img2CentCell, img2CentCell, nAllAtom));
+  DFTBP_TRY(uploadNew(ctx, &g.iCellVec, iCellVec, nAllAtom));
+  DFTBP_TRY(uploadNew(ctx, &g.cellVec, cellVec, (size_t)3 * nCellVec));
+  DFTBP_TRY(uploadNew(ctx, &g.nNeighbourSK, nNeighbourSK, nAtom));
+  DFTBP_TRY(uploadNew(ctx, &g.iNeighbour, iNeighbour, (size_t)ld * nAtom));
+  DFTBP_TRY(uploadNew(ctx, &g.iPair, iPair, (size_t)ld * nAtom));
+  DFTBP_TRY(uploadNew(ctx, &g.iAtomStart, iAtomStart, nAtom + 1));
+
+  // Work lists: one entry per sparse block.
+  std::vector<int> all, mine, load;
+  std::vector<int> stamp(nAtom + 1, -1);
+  for (int i = 0; i < nAtom; ++i) {
+    for (int k = 0; k <= hN[i]; ++k) all.push_back(k + ld * i);
+    stamp[i + 1] = i;  // the on-site block
+    for (int k = 1; k <= hN[i]; ++k) {
+      int f = hImg[hNb[k + (size_t)ld * i] - 1];
+      if (stamp[f] == i) g.hasDuplicates = true;
+      stamp[f] = i;
+    }
+  }
+  DFTBP_TRY(uploadNew(ctx, &g.workAll, all.data(), all.size()));
+  g.nWorkAll = (long long)all.size();
+  if (ctx->nRanks == 1) {
+    g.workMine = g.workLoad = g.workAll;
+    g.nWorkMine = g.nWorkLoad = g.nWorkAll;
+    g.nPairsMine = g.nWorkAll - nAtom;
+  } else {
+    int first, last;
+    chunkRange(ctx->nRanks, ctx->rank, 1, nAtom, &first, &last);  // distributeRangeInChunks
+    for (int i = first - 1; i <= last - 1; ++i)
+      for (int k = 0; k <= hN[i]; ++k) mine.push_back(k + ld * i);
+    // getIndicesWithWorkload, common/schedule.F90:267-307
+    std::vector<long long> rankLoad(ctx->nRanks, 0);
+    for (int i = 0; i < nAtom; ++i) {
+      int r = (int)(std::min_element(rankLoad.begin(), rankLoad.end()) - rankLoad.begin());
+      rankLoad[r] += std::max(1, hN[i]);
+      if (r == ctx->rank)
+        for (int k = 0; k <= hN[i]; ++k) load.push_back(k + ld * i);
+    }
+    DFTBP_TRY(uploadNew(ctx, &g.workMine, mine.data(), mine.size()));
+    DFTBP_TRY(uploadNew(ctx, &g.workLoad, load.data(), load.size()));
+    g.nWorkMine = (long long)mine.size();
+    g.nWorkLoad = (long long)load.size();
+    g.nPairsMine = g.nWorkMine - std::max(0, last - first + 1);
+  }
+  ctx->geo = g;
+  return 0;
+}
+
+int dftbp_b200_update_coords(dftbp_b200_ctx *ctx, const double *coords) {
+  if (!ctx) return DFTBP_B200_EINVAL;
+  DFTBP_CHECK(ctx, ctx->geo.nAllAtom > 0 && coords, "update_coords: no geometry set");
+  cudaMemcpyKind kind = isDevicePtr(coords) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  DFTBP_CUDA(ctx, cudaMemcpyAsync(ctx->geo.coords, coords, sizeof(double) * 3 * ctx->geo.nAllAtom, kind,
+                                  ctx->stream));
+  if (kind == cudaMemcpyHostToDevice) DFTBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+}  // extern "C"
+
+namespace dftbp_b200 {
+// (re-)upload the species-pair programs after tables changed
+int syncPrograms(dftbp_b200_ctx *ctx) {
+  if (!ctx->progsDirty) return 0;
+  for (const SpPairProg &pg : ctx->progs)
+    if (pg.H.tab == nullptr || pg.S.tab == nullptr)
+      return fail(ctx, DFTBP_B200_EINVAL,
+                  "SK tables missing: set_sk_table must be called for H and S of every species pair");
+  DFTBP_TRY(uploadNew(ctx, &ctx->dProgs, ctx->progs.data(), ctx->progs.size()));
+  ctx->progsDirty = false;
+  return 0;
+}
+}  // namespace dftbp_b200

@@ -1,0 +1,373 @@
+// k3_density_matrix.cu -- fullDensityMatrix_{real,cmplx} / fullEnergyDensityMatrix_{real,cmplx}
+// (dftb/densitymatrix.F90:530-806): dm = lower( C(:,1:nLevels) diag(w) C(:,1:nLevels)^H ).
+//
+// The reference scales the eigenvector columns by sqrt(f), calls BLAS xSYRK/xHERK and un-scales
+// (or uses a shifted two-pass form when a weight is <= 0).  Here the weight is folded into the B
+// operand while it is loaded from shared memory, so weights of any sign need one pass, the
+// eigenvectors are never modified and no sqrt is taken.
+//
+// FP64 tensor-core contraction: DMMA (mma.sync.m8n8k4.f64; the only FP64 MMA shape sm_100a has
+// in hardware -- m16n8k16 etc. lower to the same DMMA.8x8x4 SASS).  Persistent CTAs walk the
+// lower-triangular tile list in super-blocks so concurrently running CTAs share row panels in L2;
+// operands stream global -> shared through a 4-stage cp.async pipeline; the eigenvectors are
+// column-major, i.e. "MN-major" for both operands, and the shared tiles use a pitch = 4 (mod 16)
+// doubles so the (k = lane%4, mn = lane/4) fragment loads are bank-conflict free.
+//
+// Roofline: FP64 tensor pipe; flops = n^2 * nLevels (one triangle, FMA = 2), x4 for complex.
+#include "common.cuh"
+
+using namespace dftbp_b200;
+
+namespace {
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cpAsync(void *smem, const void *gmem, int bytes, int srcBytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  if (bytes == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(srcBytes));
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(srcBytes));
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// i-th lower-triangular tile in super-block order: super-blocks of G x G tiles, row-major over the
+// lower triangle of super-blocks, row-major inside.  Returns false when (ti, tj) is above the diagonal.
+struct TileOrder {
+  int nT, G, nSB;
+};
+
+__device__ __forceinline__ bool tileAt(const TileOrder &o, long long idx, int *ti, int *tj) {
+  // idx enumerates ALL positions of all lower super-blocks (including padding); callers skip misses
+  const int per = o.G * o.G;
+  const long long sb = idx / per;
+  const int in = (int)(idx - sb * per);
+  // sb -> (si, sj), si >= sj
+  int si = (int)((sqrt(8.0 * (double)sb + 1.0) - 1.0) * 0.5);
+  while ((long long)(si + 1) * (si + 2) / 2 <= sb) ++si;
+  while ((long long)si * (si + 1) / 2 > sb) --si;
+  const int sj = (int)(sb - (long long)si * (si + 1) / 2);
+  *ti = si * o.G + in / o.G;
+  *tj = sj * o.G + in % o.G;
+  return *ti < o.nT && *tj <= *ti;
+}
+
+// ------------------------------------------------------------------------------------------------
+// real:  dm(i,j) = sum_k w_k C(i,k) C(j,k),  i >= j
+// ------------------------------------------------------------------------------------------------
+template <int BM, int BK, int STAGES, int WARPS_M, int WARPS_N, int VEC>
+__global__ void __launch_bounds__(32 * WARPS_M * WARPS_N)
+k3_dm_real(const double *__restrict__ C, int ldc, const double *__restrict__ wgt, int n,
+           const int *__restrict__ nLevels, double *__restrict__ dm, int ldd, TileOrder order) {
+  const int K = *nLevels;
+  constexpr int NT = 32 * WARPS_M * WARPS_N;
+  constexpr int PITCH = BM + 4;
+  constexpr int WM = BM / WARPS_M, WN = BM / WARPS_N;  // warp tile
+  constexpr int MI = WM / 8, NI = WN / 8;
+  extern __shared__ __align__(16) double smem[];
+  double *As = smem;                             // [STAGES][BK][PITCH]
+  double *Bs = As + STAGES * BK * PITCH;         // [STAGES][BK][PITCH]
+  double *Ws = Bs + STAGES * BK * PITCH;         // [STAGES][BK]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp % WARPS_M, wn = warp / WARPS_M;
+  const int fk = lane & 3, fmn = lane >> 2;
+  const int nK = (K + BK - 1) / BK;
+  const long long nIdx = (long long)order.nSB * (order.nSB + 1) / 2 * order.G * order.G;
+
+  for (long long idx = blockIdx.x; idx < nIdx; idx += gridDim.x) {
+    int ti, tj;
+    if (!tileAt(order, idx, &ti, &tj)) continue;
+    const int i0 = ti * BM, j0 = tj * BM;
+
+    auto loadStage = [&](int stage, int kt) {
+      const int k0 = kt * BK;
+      constexpr int CH = BM / VEC;  // chunks per k column
+      for (int c = tid; c < CH * BK; c += NT) {
+        const int col = c / CH, ch = c - col * CH;
+        const int k = k0 + col;
+        {
+          const int i = i0 + ch * VEC;
+          int valid = (k < K) ? min(max(n - i, 0), VEC) : 0;
+          const double *src = valid > 0 ? C + (size_t)i + (size_t)ldc * k : C;
+          cpAsync(As + (stage * BK + col) * PITCH + ch * VEC, src, VEC * 8, valid * 8);
+        }
+        {
+          const int j = j0 + ch * VEC;
+          int valid = (k < K) ? min(max(n - j, 0), VEC) : 0;
+          const double *src = valid > 0 ? C + (size_t)j + (size_t)ldc * k : C;
+          cpAsync(Bs + (stage * BK + col) * PITCH + ch * VEC, src, VEC * 8, valid * 8);
+        }
+      }
+      if (tid < BK) {
+        const int k = k0 + tid;
+        cpAsync(Ws + stage * BK + tid, k < K ? wgt + k : wgt, 8, k < K ? 8 : 0);
+      }
+    };
+
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+      if (s < nK) loadStage(s, s);
+      cpAsyncCommit();
+    }
+    for (int kt = 0; kt < nK; ++kt) {
+      cpAsyncWait<STAGES - 2>();
+      __syncthreads();
+      if (kt + STAGES - 1 < nK) loadStage((kt + STAGES - 1) % STAGES, kt + STAGES - 1);
+      cpAsyncCommit();
+      const int st = kt % STAGES;
+      const double *a_s = As + st * BK * PITCH + wm * WM + fmn;
+      const double *b_s = Bs + st * BK * PITCH + wn * WN + fmn;
+      const double *w_s = Ws + st * BK;
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) {
+        const int kr = kk * 4 + fk;
+        const double wk = w_s[kr];
+        double a[MI], b[NI];
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) a[mi] = a_s[kr * PITCH + mi * 8];
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) b[ni] = b_s[kr * PITCH + ni * 8] * wk;
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+      }
+    }
+    cpAsyncWait<0>();
+    __syncthreads();
+
+    // epilogue: lane holds D(row = fmn, col = 2*fk + {0,1}) of each 8x8 tile
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni) {
+        const int i = i0 + wm * WM + mi * 8 + fmn;
+        const int j = j0 + wn * WN + ni * 8 + 2 * fk;
+        if (i < n) {
+          if (j < n && i >= j) dm[(size_t)i + (size_t)ldd * j] = acc[mi][ni][0];
+          if (j + 1 < n && i >= j + 1) dm[(size_t)i + (size_t)ldd * (j + 1)] = acc[mi][ni][1];
+        }
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// complex:  dm(i,j) = sum_k w_k C(i,k) conj(C(j,k)),  i >= j, imag(diag) = 0 (as xHERK)
+//   re += ar*(w br) + ai*(w bi);  im += ai*(w br) + ar*(-w bi)
+// ------------------------------------------------------------------------------------------------
+template <int BM, int BK, int STAGES, int WARPS_M, int WARPS_N>
+__global__ void __launch_bounds__(32 * WARPS_M * WARPS_N)
+k3_dm_cplx(const double2 *__restrict__ C, int ldc, const double *__restrict__ wgt, int n,
+           const int *__restrict__ nLevels, double2 *__restrict__ dm, int ldd, TileOrder order) {
+  const int K = *nLevels;
+  constexpr int NT = 32 * WARPS_M * WARPS_N;
+  constexpr int PITCH = BM + 2;  // in complex (16-byte) units: = 2 (mod 8) for conflict-free LDS.128
+  constexpr int WM = BM / WARPS_M, WN = BM / WARPS_N;
+  constexpr int MI = WM / 8, NI = WN / 8;
+  extern __shared__ __align__(16) double smem[];
+  double2 *As = reinterpret_cast<double2 *>(smem);
+  double2 *Bs = As + STAGES * BK * PITCH;
+  double *Ws = reinterpret_cast<double *>(Bs + STAGES * BK * PITCH);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp % WARPS_M, wn = warp / WARPS_M;
+  const int fk = lane & 3, fmn = lane >> 2;
+  const int nK = (K + BK - 1) / BK;
+  const long long nIdx = (long long)order.nSB * (order.nSB + 1) / 2 * order.G * order.G;
+
+  for (long long idx = blockIdx.x; idx < nIdx; idx += gridDim.x) {
+    int ti, tj;
+    if (!tileAt(order, idx, &ti, &tj)) continue;
+    const int i0 = ti * BM, j0 = tj * BM;
+
+    auto loadStage = [&](int stage, int kt) {
+      const int k0 = kt * BK;
+      for (int c = tid; c < BM * BK; c += NT) {
+        const int col = c / BM, ch = c - col * BM;
+        const int k = k0 + col;
+        const int i = i0 + ch, j = j0 + ch;
+        const bool va = k < K && i < n, vb = k < K && j < n;
+        cpAsync(As + (stage * BK + col) * PITCH + ch, va ? C + (size_t)i + (size_t)ldc * k : C, 16, va ? 16 : 0);
+        cpAsync(Bs + (stage * BK + col) * PITCH + ch, vb ? C + (size_t)j + (size_t)ldc * k : C, 16, vb ? 16 : 0);
+      }
+      if (tid < BK) {
+        const int k = k0 + tid;
+        cpAsync(Ws + stage * BK + tid, k < K ? wgt + k : wgt, 8, k < K ? 8 : 0);
+      }
+    };
+
+    double re[MI][NI][2], im[MI][NI][2];
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni) re[mi][ni][0] = re[mi][ni][1] = im[mi][ni][0] = im[mi][ni][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+      if (s < nK) loadStage(s, s);
+      cpAsyncCommit();
+    }
+    for (int kt = 0; kt < nK; ++kt) {
+      cpAsyncWait<STAGES - 2>();
+      __syncthreads();
+      if (kt + STAGES - 1 < nK) loadStage((kt + STAGES - 1) % STAGES, kt + STAGES - 1);
+      cpAsyncCommit();
+      const int st = kt % STAGES;
+      const double2 *a_s = As + st * BK * PITCH + wm * WM + fmn;
+      const double2 *b_s = Bs + st * BK * PITCH + wn * WN + fmn;
+      const double *w_s = Ws + st * BK;
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) {
+        const int kr = kk * 4 + fk;
+        const double wk = w_s[kr];
+        double2 a[MI], b[NI];
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) a[mi] = a_s[kr * PITCH + mi * 8];
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) {
+          const double2 v = b_s[kr * PITCH + ni * 8];
+          b[ni] = make_double2(v.x * wk, v.y * wk);
+        }
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < NI; ++ni) {
+            dmma884(re[mi][ni][0], re[mi][ni][1], a[mi].x, b[ni].x);
+            dmma884(re[mi][ni][0], re[mi][ni][1], a[mi].y, b[ni].y);
+            dmma884(im[mi][ni][0], im[mi][ni][1], a[mi].y, b[ni].x);
+            dmma884(im[mi][ni][0], im[mi][ni][1], a[mi].x, -b[ni].y);
+          }
+      }
+    }
+    cpAsyncWait<0>();
+    __syncthreads();
+
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni) {
+        const int i = i0 + wm * WM + mi * 8 + fmn;
+        const int j = j0 + wn * WN + ni * 8 + 2 * fk;
+        if (i < n) {
+          if (j < n && i >= j)
+            dm[(size_t)i + (size_t)ldd * j] = make_double2(re[mi][ni][0], i == j ? 0.0 : im[mi][ni][0]);
+          if (j + 1 < n && i >= j + 1)
+            dm[(size_t)i + (size_t)ldd * (j + 1)] = make_double2(re[mi][ni][1], i == j + 1 ? 0.0 : im[mi][ni][1]);
+        }
+      }
+  }
+}
+
+// nLevels = index of the last |filling| >= epsilon (densitymatrix.F90:549-554); computed on the
+// device so that device-resident fillings need no host round trip.  Result in *out (>= 1).
+__global__ void k3_count_levels(const double *filling, int n, int *out) {
+  __shared__ int best;
+  if (threadIdx.x == 0) best = 1;
+  __syncthreads();
+  int mine = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (fabs(filling[i]) >= 2.220446049250313e-16) mine = max(mine, i + 1);
+  atomicMax(&best, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) *out = best;
+}
+
+TileOrder makeOrder(int n, int BM) {
+  TileOrder o;
+  o.nT = (n + BM - 1) / BM;
+  o.G = 12;
+  o.nSB = (o.nT + o.G - 1) / o.G;
+  return o;
+}
+
+template <class Kern>
+int setSmem(dftbp_b200_ctx *ctx, Kern k, size_t bytes) {
+  DFTBP_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+int densityImpl(dftbp_b200_ctx *ctx, void *dm, const void *eigvecs, int n, int ld, const double *filling,
+                const double *weights, bool cplx) {
+  if (!ctx) return DFTBP_B200_EINVAL;
+  DFTBP_CHECK(ctx, dm && eigvecs && filling && n > 0 && ld >= n, "density_matrix: bad arguments");
+  const size_t el = cplx ? 2 : 1;
+  const double *dC, *dF, *dW;
+  double *dDm;
+  DFTBP_TRY(devIn(ctx, kSlotA, (const double *)eigvecs, (size_t)ld * n * el, &dC));
+  DFTBP_TRY(devIn(ctx, kSlotC, filling, (size_t)n, &dF));
+  dW = dF;
+  if (weights) DFTBP_TRY(devIn(ctx, kSlotD, weights, (size_t)n, &dW));
+  DFTBP_TRY(devOut(ctx, kSlotB, (double *)dm, (size_t)ld * n * el, false, &dDm));
+  // dm(:,:) = 0 (densitymatrix.F90:547); the kernel then fills the lower triangle
+  DFTBP_CUDA(ctx, cudaMemsetAsync(dDm, 0, sizeof(double) * ld * n * el, ctx->stream));
+  k3_count_levels<<<1, 256, 0, ctx->stream>>>(dF, n, ctx->dInfo);
+  ctx->launches += 2;
+  const int *K = ctx->dInfo;  // stays on the device: no host round trip inside the SCC loop
+  if (!cplx) {
+    const bool big = n >= 1024;
+    const bool aligned = (ld % 2 == 0) && ((reinterpret_cast<size_t>(dC) & 15) == 0);
+    if (big) {
+      constexpr int BM = 128, BK = 16, ST = 4;
+      const size_t smemB = sizeof(double) * (2 * ST * BK * (BM + 4) + ST * BK);
+      const TileOrder o = makeOrder(n, BM);
+      const long long nTiles = (long long)o.nT * (o.nT + 1) / 2;
+      const int grid = (int)std::min<long long>(nTiles, ctx->smCount);
+      if (aligned) {
+        auto kern = k3_dm_real<BM, BK, ST, 2, 4, 2>;
+        DFTBP_TRY(setSmem(ctx, kern, smemB));
+        kern<<<grid, 256, smemB, ctx->stream>>>(dC, ld, dW, n, K, dDm, ld, o);
+      } else {
+        auto kern = k3_dm_real<BM, BK, ST, 2, 4, 1>;
+        DFTBP_TRY(setSmem(ctx, kern, smemB));
+        kern<<<grid, 256, smemB, ctx->stream>>>(dC, ld, dW, n, K, dDm, ld, o);
+      }
+    } else {
+      constexpr int BM = 64, BK = 16, ST = 3;
+      const size_t smemB = sizeof(double) * (2 * ST * BK * (BM + 4) + ST * BK);
+      const TileOrder o = makeOrder(n, BM);
+      const long long nTiles = (long long)o.nT * (o.nT + 1) / 2;
+      const int grid = (int)std::min<long long>(nTiles, 2LL * ctx->smCount);
+      auto kern = k3_dm_real<BM, BK, ST, 2, 2, 1>;
+      DFTBP_TRY(setSmem(ctx, kern, smemB));
+      kern<<<grid, 128, smemB, ctx->stream>>>(dC, ld, dW, n, K, dDm, ld, o);
+    }
+  } else {
+    constexpr int BM = 64, BK = 8, ST = 4;
+    const size_t smemB = sizeof(double2) * (2 * ST * BK * (BM + 2)) + sizeof(double) * ST * BK;
+    const TileOrder o = makeOrder(n, BM);
+    const long long nTiles = (long long)o.nT * (o.nT + 1) / 2;
+    const int grid = (int)std::min<long long>(nTiles, 2LL * ctx->smCount);
+    auto kern = k3_dm_cplx<BM, BK, ST, 2, 2>;
+    DFTBP_TRY(setSmem(ctx, kern, smemB));
+    kern<<<grid, 128, smemB, ctx->stream>>>((const double2 *)dC, ld, dW, n, K, (double2 *)dDm, ld, o);
+  }
+  ctx->launches++;
+  return finish(ctx);
+}
+
+}  // namespace
+
+extern "C" {
+
+int dftbp_b200_density_matrix_real(dftbp_b200_ctx *ctx, double *dm, const double *eigvecs, int n, int ld,
+                                   const double *filling, const double *weights) {
+  return densityImpl(ctx, dm, eigvecs, n, ld, filling, weights, false);
+}
+
+int dftbp_b200_density_matrix_cplx(dftbp_b200_ctx *ctx, void *dm, const void *eigvecs, int n, int ld,
+                                   const double *filling, const double *weights) {
+  return densityImpl(ctx, dm, eigvecs, n, ld, filling, weights, true);
+}
+
+}  // extern "C"

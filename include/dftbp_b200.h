@@ -1,0 +1,190 @@
+/*
+ * dftbp_b200.h -- C ABI of libdftbp_b200.so: the B200 (sm_100a) implementation of DFTB+'s
+ * per-SCC-step data-parallel hot path.
+ *
+ * This is the drop-in boundary.  Each entry point replaces the body of one Fortran module
+ * procedure of the reference (cited below, paths relative to /root/reference/src/dftbp/);
+ * INTEGRATION.md shows the ISO_C_BINDING interface block a DFTB+ maintainer adds on the
+ * Fortran side.  Plain pointers and sizes only -- no torch / C++ types cross this boundary.
+ *
+ * Conventions (identical to the reference):
+ *   - all reals are IEEE double, complex = interleaved (re, im) doubles (complex(dp));
+ *   - arrays are passed exactly as the Fortran caller holds them: column-major, atom and
+ *     species VALUES 1-based, iPair (= iSparseStart) offsets 0-based;
+ *   - iNeighbour(0:mNeigh, nAtom) and iPair(0:mNeigh, nAtom) arrive as raw (mNeigh+1) x nAtom
+ *     int arrays, element [iNeigh + (mNeigh+1)*(iAtom-1)];
+ *   - a sparse block is nOrb2 x nOrb1 column-major, rows = orbitals of the NEIGHBOUR.
+ *
+ * Pointers: every array argument may be a host pointer or a device pointer (detected with
+ * cudaPointerGetAttributes).  Host inputs are copied H2D, host outputs D2H, and the call is
+ * synchronous for them.  Device pointers are used in place on the context's stream with no
+ * synchronisation, so a device-resident driver can chain calls with no PCIe traffic.
+ *
+ * Errors: every function returns 0 on success, otherwise a DFTBP_B200_E* code; the message is
+ * available from dftbp_b200_last_error().  (Reference convention: TStatus + @:RAISE_ERROR,
+ * include/error.fypp:87-105, or error() abort, io/message.F90:74-84; the Fortran shim maps a
+ * non-zero return onto those.)  There is NO CPU fallback: without a CUDA device
+ * dftbp_b200_create fails with DFTBP_B200_ENODEVICE.
+ *
+ * Threading: a context is used by one host thread at a time (the reference calls these
+ * routines from the serial part of the driver); distinct contexts are independent
+ * (cf. INSTANCE_SAFE_BUILD, config.cmake:62).
+ */
+#ifndef DFTBP_B200_H
+#define DFTBP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dftbp_b200_ctx dftbp_b200_ctx;
+
+enum {
+  DFTBP_B200_OK = 0,
+  DFTBP_B200_EINVAL = 1,     /* bad argument / call order */
+  DFTBP_B200_ENODEVICE = 2,  /* no CUDA device: there is no CPU fallback */
+  DFTBP_B200_ECUDA = 3,      /* CUDA runtime / cuSOLVER error */
+  DFTBP_B200_ENOTIMPL = 4,   /* valid reference option that is not built yet */
+  DFTBP_B200_ENOMEM = 5
+};
+
+/* skIntMethod, dftb/slakoeqgrid.F90:62-65 */
+enum { DFTBP_B200_SK_EQGRID_OLD = 1, DFTBP_B200_SK_EQGRID_NEW = 2 };
+/* diffTypes, dftb/nonscc.F90:27-38 */
+enum { DFTBP_B200_DIFF_FINITE = 1, DFTBP_B200_DIFF_RICHARDSON = 2 };
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+
+/* One context per TDftbPlus instance / per GPU.  rank / nRanks restate env%mpi%groupComm
+ * (common/schedule.F90:51-76): with nRanks > 1 the pair-parallel routines (build_*, mulliken_*,
+ * derivative_shift) only process this rank's share of the atoms and leave the rest of the
+ * output zero, exactly like the reference before assembleChunks (schedule.F90:170-182); the
+ * caller sums over ranks (MPI_Allreduce in the reference, NCCL in the host layer here). */
+int dftbp_b200_create(dftbp_b200_ctx **ctx, int device, int rank, int nRanks);
+int dftbp_b200_destroy(dftbp_b200_ctx *ctx);
+const char *dftbp_b200_last_error(const dftbp_b200_ctx *ctx);
+const char *dftbp_b200_version(void);
+
+/* Use an existing CUDA stream (cudaStream_t passed as void*); NULL = the context's own.
+ * dftbp_b200_synchronize blocks until all work queued by this context has finished. */
+int dftbp_b200_set_stream(dftbp_b200_ctx *ctx, void *cuda_stream);
+void *dftbp_b200_get_stream(dftbp_b200_ctx *ctx);
+int dftbp_b200_synchronize(dftbp_b200_ctx *ctx);
+
+/* ---- once per run: flattened TOrbitals and TSlakoCont ----------------------------------- */
+
+/* TOrbitals, type/orbitals.F90:20-51.  angShell is (mShell, nSpecies) column-major; angular
+ * momenta 0..3 (mAngRot_, dftb/sk.F90:28).  nOrbSpecies is derived. */
+int dftbp_b200_set_orbitals(dftbp_b200_ctx *ctx, int nSpecies, int mShell, const int *nShell,
+                            const int *angShell);
+
+/* SlakoCont_addTableEqGrid + SlakoEqGrid_init, dftb/slakocont.F90:97-111 and
+ * dftb/slakoeqgrid.F90:95-121.  which: 0 = Hamiltonian container, 1 = overlap container.
+ * (sp1, sp2) (1-based) is the pair the reference later fetches with
+ * getSKIntegrals(skCont, sk, dist, sp1, sp2), sp1 = species of the atom, sp2 = species of its
+ * neighbour (slakocont.F90:156-176).  skTab is (nGrid, nInteg) column-major, row j <-> r = j*dist;
+ * nInteg must equal sum over shell pairs (sp1 outer, sp2 inner) of min(l1,l2)+1
+ * (dftbplus/parser.F90:4061-4130). */
+int dftbp_b200_set_sk_table(dftbp_b200_ctx *ctx, int which, int sp1, int sp2, int nGrid,
+                            int nInteg, double dist, const double *skTab, int skIntMethod);
+
+/* SlakoCont_getCutoff, slakocont.F90:139-150 (max over tables of nGrid*dist + distFudge) */
+int dftbp_b200_get_sk_cutoff(dftbp_b200_ctx *ctx, double *cutoff);
+
+/* ---- once per geometry (handleCoordinateChange, dftbplus/main.F90:2413-2577) ------------- */
+
+/* coords(3, nAllAtom), species(nAllAtom), img2CentCell(nAllAtom), iCellVec(nAllAtom),
+ * cellVec(3, nCellVec), nNeighbourSK(nAtom), iNeighbour(0:mNeigh, nAtom), iPair(0:mNeigh, nAtom),
+ * iAtomStart(nAtom+1).  All are copied to the device. */
+int dftbp_b200_set_geometry(dftbp_b200_ctx *ctx, int nAtom, int nAllAtom, int mNeigh,
+                            const double *coords, const int *species, const int *img2CentCell,
+                            const int *iCellVec, int nCellVec, const double *cellVec,
+                            const int *nNeighbourSK, const int *iNeighbour, const int *iPair,
+                            const int *iAtomStart, int sparseSize);
+
+/* Coordinates only (same neighbour map): geometry steps that keep the list, and finite
+ * differences.  coords(3, nAllAtom). */
+int dftbp_b200_update_coords(dftbp_b200_ctx *ctx, const double *coords);
+
+/* ---- K1: Slater-Koster pair build -------------------------------------------------------- */
+
+/* buildH0, dftb/nonscc.F90:66-124.  selfegy(mShell, nSpecies); ham(sparseSize) out. */
+int dftbp_b200_build_h0(dftbp_b200_ctx *ctx, const double *selfegy, double *ham);
+/* buildS, dftb/nonscc.F90:128-181.  over(sparseSize) out. */
+int dftbp_b200_build_s(dftbp_b200_ctx *ctx, double *over);
+/* both in one launch (the reference calls them back to back, dftbplus/main.F90:1219-1221) */
+int dftbp_b200_build_h0_s(dftbp_b200_ctx *ctx, const double *selfegy, double *ham, double *over);
+
+/* ---- K2: sparse <-> dense ----------------------------------------------------------------- */
+
+/* unpackHS_real, dftb/sparse2dense.F90:266-321.  square(ld, nOrb), ld >= nOrb; zeroed, then
+ * off-site blocks go to the lower triangle. */
+int dftbp_b200_unpack_hs_real(dftbp_b200_ctx *ctx, const double *orig, double *square, int ld);
+/* unpackHS_cmplx_kpts, dftb/sparse2dense.F90:185-260.  kPoint in relative coordinates. */
+int dftbp_b200_unpack_hs_cplx(dftbp_b200_ctx *ctx, const double *orig, const double kPoint[3],
+                              void *square_c128, int ld);
+/* packHS_real, dftb/sparse2dense.F90:1024-1096.  primitive(sparseSize) ACCUMULATES. */
+int dftbp_b200_pack_hs_real(dftbp_b200_ctx *ctx, double *primitive, const double *square, int ld);
+/* packHS_cmplx_kpts, dftb/sparse2dense.F90:820-918. */
+int dftbp_b200_pack_hs_cplx(dftbp_b200_ctx *ctx, double *primitive, const void *square_c128,
+                            int ld, const double kPoint[3], double kWeight);
+
+/* ---- K3: density matrix -------------------------------------------------------------------- */
+
+/* TDensityMatrix%getDensityMatrix / getEDensityMatrix -> fullDensityMatrix_real and
+ * fullEnergyDensityMatrix_real, dftb/densitymatrix.F90:123-233,530-591,664-733:
+ *   dm = lower triangle of  C(:,1:nLevels) diag(w(1:nLevels)) C(:,1:nLevels)^T,
+ * nLevels = index of the last |filling| >= epsilon(1.0).  filling(n) decides nLevels;
+ * weights(n) are the weights (== filling for the density matrix, filling*eigen for the
+ * energy-weighted one); pass weights = NULL to use filling.  Weights of either sign are handled
+ * directly (the reference's sqrt / shift-by-arbitraryConstant reformulations exist only because
+ * BLAS xSYRK needs a positive-definite form).  dm(ld, n): the strict upper triangle is zeroed,
+ * eigvecs(ld, n) is not modified. */
+int dftbp_b200_density_matrix_real(dftbp_b200_ctx *ctx, double *dm, const double *eigvecs, int n,
+                                   int ld, const double *filling, const double *weights);
+/* fullDensityMatrix_cmplx / fullEnergyDensityMatrix_cmplx, densitymatrix.F90:597-658,739-806:
+ * dm = lower triangle of C diag(w) C^H. */
+int dftbp_b200_density_matrix_cplx(dftbp_b200_ctx *ctx, void *dm_c128, const void *eigvecs_c128,
+                                   int n, int ld, const double *filling, const double *weights);
+
+/* ---- K4: Mulliken populations -------------------------------------------------------------- */
+
+/* mullikenPerOrbital, dftb/populations.F90:120-187.  qq(mOrb, nAtom) ACCUMULATES. */
+int dftbp_b200_mulliken_orbital(dftbp_b200_ctx *ctx, double *qq, const double *over,
+                                const double *rho);
+/* mullikenPerBlock, dftb/populations.F90:306-375.  qq(mOrb, mOrb, nAtom) ACCUMULATES. */
+int dftbp_b200_mulliken_block(dftbp_b200_ctx *ctx, double *qq, const double *over,
+                              const double *rho);
+
+/* ---- K5: force contraction ----------------------------------------------------------------- */
+
+/* derivative_shift generic, dftb/forces.F90:27-38: shift == NULL -> derivativeNonSccEuclidian
+ * (:119-217), else derivative_blockEuclidean (:548-669).  DM(sparseSize, nSpin),
+ * EDM(sparseSize), shift(mOrb, mOrb, nAtom, nSpin), deriv(3, nAtom) is overwritten.
+ * diffType / delta restate TNonSccDiff (dftb/nonscc.F90:39-60); delta <= 0 selects the
+ * reference default epsilon(1.0)**0.25. */
+int dftbp_b200_derivative_shift(dftbp_b200_ctx *ctx, double *deriv, const double *DM, int nSpin,
+                                const double *EDM, const double *shift, int diffType,
+                                double delta);
+
+/* ---- not rewritten: dense generalized eigensolve via cuSOLVER ------------------------------- */
+
+/* diagDenseMtx, dftbplus/eigenvects.F90:85-100 (hegvd branch): H C = S C diag(eigen), lower
+ * triangles referenced; on exit H holds the eigenvectors, S its Cholesky factor.  jobz 'V'/'N'.
+ * H, S (ld, n) and eigen(n) may be host or device pointers. */
+int dftbp_b200_hegv_real(dftbp_b200_ctx *ctx, double *H, double *S, double *eigen, int n, int ld,
+                         char jobz);
+int dftbp_b200_hegv_cplx(dftbp_b200_ctx *ctx, void *H_c128, void *S_c128, double *eigen, int n,
+                         int ld, char jobz);
+
+/* ---- introspection (bench / tests) --------------------------------------------------------- */
+
+/* number of kernels this context has launched since creation */
+long long dftbp_b200_kernel_launches(const dftbp_b200_ctx *ctx);
+/* number of (iAtom, iNeigh >= 1) pairs in this rank's share of the current geometry */
+long long dftbp_b200_num_pairs(const dftbp_b200_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFTBP_B200_H */
