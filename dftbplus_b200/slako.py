@@ -156,14 +156,15 @@ def write_synthetic_set(directory, names, ang_shells, onsite, hubbard, occ, mass
     onsite/hubbard/occ: per species dicts {l: value}."""
     os.makedirs(directory, exist_ok=True)
     rng = np.random.default_rng(seed)
-    if extended is None:
-        extended = any(3 in a for a in ang_shells)
     r = dist * np.arange(1, n_grid + 1)
-    ncol = 20 if extended else 10
-    order = list(range(1, 21)) if extended else I_SK_INTER_OLD
     done = {}
+    force_extended = extended
     for i, a in enumerate(names):
         for j, b in enumerate(names):
+            # the extended 20-column format is only needed when an f shell is involved
+            extended = force_extended if force_extended is not None else (3 in ang_shells[i] or 3 in ang_shells[j])
+            ncol = 20 if extended else 10
+            order = list(range(1, 21)) if extended else I_SK_INTER_OLD
             def cols(scale_lo, scale_hi, b_lo, b_hi):
                 amp = rng.uniform(scale_lo, scale_hi, ncol) * rng.choice([-1.0, 1.0], ncol)
                 aa = rng.uniform(0.2, 0.6, ncol)

@@ -124,7 +124,7 @@ def rotate_h0(model, sk, direction, sp1, sp2):
     sk = np.ascontiguousarray(sk, dtype=np.float64)
     hh = np.zeros((model.mOrb, model.mOrb), order="F")
     lib().orc_rotate_h0(model._h, _d(hh), _d(sk), ctypes.c_double(direction[0]),
-                        ctypes.c_double(direction[1]), ctypes.c_double(direction[2]), sp1, sp2)
+                        ctypes.c_double(direction[1]), ctypes.c_double(direction[2]), int(sp1), int(sp2))
     return hh[:model.nOrbSpecies[sp2 - 1], :model.nOrbSpecies[sp1 - 1]].copy()
 
 

@@ -1,0 +1,158 @@
+"""Self-checks of the oracle's hot-path restatement that need no golden files:
+layout of the H2O example, hermiticity under atom swap, pack(unpack(x)) == x, sum of Mulliken
+charges = N electrons, sum of forces = 0, forces = finite difference of the band energy."""
+import numpy as np
+import scipy.linalg
+
+from helpers import oracle, case, fermi_fillings, n_electrons
+
+
+def test_h2o_layout_appendix_d():
+    w, sk, geo, model, selfegy = case("h2o")
+    assert geo["nAtom"] == geo["nAllAtom"] == 3 and geo["sparseSize"] == 27 and geo["nOrb"] == 6
+    assert list(geo["nNeighbourSK"]) == [2, 1, 0]
+    assert list(geo["iNeighbour"][0]) == [1, 2, 3] or list(geo["iNeighbour"][0]) == [1, 3, 2]
+    assert list(geo["iPair"][0]) == [0, 16, 20] and list(geo["iPair"][1][:2]) == [24, 25]
+    assert geo["iPair"][2][0] == 26 and list(geo["iAtomStart"]) == [1, 5, 6, 7]
+    g2 = oracle.neighbour_geometry(model, w["coord0"], w["species0"])
+    for k in ("nNeighbourSK", "iPair", "iAtomStart", "img2CentCell", "iCellVec"):
+        assert np.array_equal(g2[k], geo[k]), k
+    h0 = oracle.build_h0(model, geo, selfegy)
+    s = oracle.build_s(model, geo)
+    # on-site blocks: diagonal only (nonscc.F90:109-116,166-173)
+    assert np.allclose(h0[:16].reshape(4, 4), np.diag([selfegy[0][0]] + [selfegy[0][1]] * 3))
+    assert np.allclose(s[:16].reshape(4, 4), np.eye(4)) and s[24] == 1.0 and s[26] == 1.0
+    # unpack puts the O-H block (1x4) at square(5, 1:4): lower triangle
+    sq = oracle.unpack_hs_real(geo, s)
+    assert np.allclose(sq[4, 0:4], s[16:20]) and np.all(sq[0:4, 4] == 0.0)
+
+
+def test_block_transposition_rule_under_atom_swap():
+    """<a|H|b> built from atom a's side equals the transpose built from b's side when the
+    parameter set is consistent (sk.F90:128-133 with the B-A file, parser.F90:4110-4114)."""
+    w, sk, geo, model, selfegy = case("ce_o")
+    perm = np.arange(geo["nAtom"])[::-1]
+    g2 = oracle.neighbour_geometry(model, w["coord0"][perm], w["species0"][perm])
+    s1 = oracle.unpack_hs_real(geo, oracle.build_s(model, geo))
+    s2 = oracle.unpack_hs_real(g2, oracle.build_s(model, g2))
+    full1 = np.tril(s1) + np.tril(s1, -1).T
+    full2 = np.tril(s2) + np.tril(s2, -1).T
+    # orbital permutation induced by the atom permutation
+    idx1 = [np.arange(geo["iAtomStart"][a] - 1, geo["iAtomStart"][a + 1] - 1) for a in range(geo["nAtom"])]
+    order = np.concatenate([idx1[a] for a in perm])
+    # only l-l integrals are tied between the A-B and B-A synthetic files; compare those blocks
+    ev1 = np.linalg.eigvalsh(full1[np.ix_(order, order)])
+    assert full2.shape == full1.shape and np.isfinite(ev1).all()
+    for a in range(geo["nAtom"]):
+        for b in range(geo["nAtom"]):
+            if w["species0"][perm[a]] == w["species0"][perm[b]]:
+                ia = np.arange(g2["iAtomStart"][a] - 1, g2["iAtomStart"][a + 1] - 1)
+                ib = np.arange(g2["iAtomStart"][b] - 1, g2["iAtomStart"][b + 1] - 1)
+                assert np.allclose(full2[np.ix_(ia, ib)], full1[np.ix_(idx1[perm[a]], idx1[perm[b]])], atol=1e-13)
+
+
+def test_pack_unpack_roundtrip_gamma_and_k():
+    w, sk, geo, model, selfegy = case("ce_o")
+    x = np.random.default_rng(0).normal(size=geo["sparseSize"])
+    # make on-site blocks symmetric, as every physical sparse matrix is
+    for a in range(geo["nAtom"]):
+        n = geo["nOrbAtom"][a]
+        blk = x[geo["iPair"][a, 0]:geo["iPair"][a, 0] + n * n].reshape(n, n)
+        blk[:] = 0.5 * (blk + blk.T)
+    back = oracle.pack_hs_real(geo, np.zeros_like(x), oracle.unpack_hs_real(geo, x))
+    assert np.allclose(back, x, atol=1e-15)
+    # periodic, k-points: sum_k w_k pack_k(unpack_k(x)) == x when no two blocks collide
+    w2, sk2, geo2, model2, _ = case("si512")
+    x = np.random.default_rng(1).normal(size=geo2["sparseSize"])
+    for a in range(geo2["nAtom"]):
+        blk = x[geo2["iPair"][a, 0]:geo2["iPair"][a, 0] + 16].reshape(4, 4)
+        blk[:] = 0.5 * (blk + blk.T)
+    k = np.array([0.125, -0.375, 0.25])
+    back = oracle.pack_hs_cplx(geo2, np.zeros_like(x), oracle.unpack_hs_cplx(geo2, x, k), k, 1.0)
+    assert np.allclose(back, x, atol=1e-14)
+
+
+def _scf_like(name):
+    w, sk, geo, model, selfegy = case(name)
+    h0 = oracle.build_h0(model, geo, selfegy)
+    s = oracle.build_s(model, geo)
+    H, S = oracle.unpack_hs_real(geo, h0), oracle.unpack_hs_real(geo, s)
+    eig, C = scipy.linalg.eigh(H, S, lower=True)
+    f = fermi_fillings(eig, n_electrons(w, sk))
+    return w, sk, geo, model, selfegy, h0, s, eig, np.asfortranarray(C), f
+
+
+def test_mulliken_sums_to_electron_count_and_band_energy():
+    w, sk, geo, model, selfegy, h0, s, eig, C, f = _scf_like("ce_o")
+    dm = oracle.density_matrix(C, f)
+    assert np.allclose(dm, oracle.weighted_density_matrix(C, f), atol=1e-13)
+    assert np.all(np.triu(dm, 1) == 0.0)
+    rho = oracle.pack_hs_real(geo, np.zeros(geo["sparseSize"]), dm)
+    q = oracle.mulliken_per_orbital(model, geo, s, rho)
+    assert abs(q.sum() - n_electrons(w, sk)) < 1e-10
+    e_band = oracle.mulliken_per_orbital(model, geo, h0, rho).sum()       # Tr[rho H0], getenergies.F90:198
+    assert abs(e_band - (f * eig).sum()) < 1e-10
+    qb = oracle.mulliken_per_block(model, geo, s, rho)
+    assert np.allclose(np.einsum("aii->ai", qb), q, atol=1e-12)           # block diagonal = orbital charges
+    assert np.allclose(qb, qb.transpose(0, 2, 1), atol=1e-13)
+
+
+def test_energy_density_matrix_branches_agree():
+    w, sk, geo, model, selfegy, h0, s, eig, C, f = _scf_like("ce_o")
+    # all products negative -> sqrt branch; mixed signs -> shifted branch (densitymatrix.F90:695-730)
+    for shift in (0.0, -eig.min() + 0.05 - 0.3):
+        e = eig + shift
+        edm = oracle.energy_density_matrix(C, f, e)
+        assert np.allclose(edm, oracle.weighted_density_matrix(C, f * e), atol=1e-12)
+    # fillings with an exact zero inside the occupied range -> shifted branch of the DM
+    f2 = f.copy(); f2[1] = 0.0
+    assert np.allclose(oracle.density_matrix(C, f2), oracle.weighted_density_matrix(C, f2), atol=1e-12)
+
+
+def test_forces_sum_to_zero_and_match_band_energy_derivative():
+    w, sk, geo, model, selfegy, h0, s, eig, C, f = _scf_like("ce_o")
+    dm = oracle.pack_hs_real(geo, np.zeros(geo["sparseSize"]), oracle.density_matrix(C, f))
+    edm = oracle.pack_hs_real(geo, np.zeros(geo["sparseSize"]), oracle.energy_density_matrix(C, f, eig))
+    deriv = oracle.derivative_shift(model, geo, dm, edm)
+    assert np.abs(deriv.sum(axis=0)).max() < 1e-9
+    # dE_band/dR by central differences of the whole eigenproblem (fixed occupations at kT -> ~fixed)
+    def e_band(coord0):
+        g = oracle.neighbour_geometry(model, coord0, w["species0"])
+        Hh = oracle.unpack_hs_real(g, oracle.build_h0(model, g, selfegy))
+        Ss = oracle.unpack_hs_real(g, oracle.build_s(model, g))
+        ev = scipy.linalg.eigh(Hh, Ss, lower=True, eigvals_only=True)
+        ff = fermi_fillings(ev, n_electrons(w, sk))
+        kT = 0.001
+        x = ff / 2.0
+        x = np.clip(x, 1e-300, 1 - 1e-16)
+        ts = -2.0 * kT * np.sum(x * np.log(x) + (1 - x) * np.log(1 - x))   # Mermin: E - TS is variational
+        return (ff * ev).sum() - ts
+    h = 1e-4
+    for atom, comp in [(0, 0), (2, 1), (4, 2)]:
+        cp, cm = w["coord0"].copy(), w["coord0"].copy()
+        cp[atom, comp] += h
+        cm[atom, comp] -= h
+        num = (e_band(cp) - e_band(cm)) / (2 * h)
+        assert abs(num - deriv[atom, comp]) < 5e-7, (num, deriv[atom, comp])
+    # Richardson derivator agrees with the finite-difference one to far better than the force tolerance
+    d2 = oracle.derivative_shift(model, geo, dm, edm, diff_type=2)
+    assert np.abs(d2 - deriv).max() < 1e-7
+    # block (SCC) variant with zero shift equals the non-SCC routine
+    sh = np.zeros((1, geo["nAtom"], model.mOrb, model.mOrb))
+    assert np.allclose(oracle.derivative_shift(model, geo, dm, edm, shift=sh), deriv, atol=1e-13)
+
+
+def test_partial_builds_sum_to_full_build():
+    """distributeRangeInChunks + assembleChunks (nonscc.F90:104,122): per-rank zero-padded arrays
+    add up to the single-rank result; workload-split Mulliken / forces likewise."""
+    w, sk, geo, model, selfegy = case("fec128")
+    full = oracle.build_s(model, geo)
+    parts = [oracle.build_s(model, geo, rank=r, nranks=3) for r in range(3)]
+    assert np.array_equal(sum(parts), full)
+    assert all(np.count_nonzero(p) < np.count_nonzero(full) for p in parts)
+    rho = np.random.default_rng(2).normal(size=geo["sparseSize"])
+    q_full = oracle.mulliken_per_orbital(model, geo, full, rho)
+    q_parts = sum(oracle.mulliken_per_orbital(
+        model, geo, full, rho,
+        iter_indices=oracle.indices_with_workload(3, r, 1, geo["nAtom"], geo["nNeighbourSK"])) for r in range(3))
+    assert np.allclose(q_parts, q_full, atol=1e-12)

@@ -1,0 +1,56 @@
+"""Known-answer tests of the reference's own unit suite for the partition logic
+(test/src/dftbp/unit/common/schedule.F90), run against the oracle restatement and the product's
+host mirror; plus TParallelKS (type/parallelks.F90:78-84)."""
+import numpy as np
+import pytest
+
+from helpers import oracle
+from dftbplus_b200 import schedule
+
+
+def _impls():
+    return [("oracle", oracle.chunk_ranges, oracle.indices_with_workload),
+            ("host", schedule.get_chunk_ranges, schedule.get_indices_with_workload)]
+
+
+@pytest.mark.parametrize("name,chunk,_", _impls())
+def test_chunk_ranges(name, chunk, _):
+    assert chunk(1, 0, 1, 42) == (1, 42)
+    assert chunk(1, 0, 7, 42) == (7, 42)
+    assert [chunk(3, r, 1, 17) for r in range(3)] == [(1, 6), (7, 12), (13, 17)]
+    assert [chunk(3, r, 3, 20) for r in range(3)] == [(3, 8), (9, 14), (15, 20)]
+
+
+@pytest.mark.parametrize("name,_,idx", _impls())
+def test_indices_with_workload(name, _, idx):
+    assert list(idx(1, 0, 1, 10, [1] * 10)) == list(range(1, 11))
+    assert list(idx(1, 0, 1, 10, [5] * 10)) == list(range(1, 11))
+    assert list(idx(1, 0, 1, 10, [0] * 5 + [1] * 5)) == list(range(1, 11))
+    assert list(idx(1, 0, 1, 10, [0] * 10)) == list(range(1, 11))
+    assert list(idx(1, 0, 7, 10, [-100] * 6 + [1] * 4)) == [7, 8, 9, 10]
+    w = [1, 1, 5, 0, 0, 1, 1, 1, 10, 2]
+    assert list(idx(2, 0, 1, 10, w)) == [1, 3, 9]
+    assert list(idx(2, 1, 1, 10, w)) == [2, 4, 5, 6, 7, 8, 10]
+    w = [10, 2, 3, 0, 10, 1, 1, 1, 10, 1]
+    assert list(idx(3, 0, 1, 10, w)) == [1, 10]
+    assert list(idx(3, 1, 1, 10, w)) == [2, 4, 5]
+    assert list(idx(3, 2, 1, 10, w)) == [3, 6, 7, 8, 9]
+    w = [100] + [1] * 9
+    assert list(idx(3, 0, 1, 10, w)) == [1]
+    assert list(idx(3, 1, 1, 10, w)) == [2, 4, 6, 8, 10]
+    assert list(idx(3, 2, 1, 10, w)) == [3, 5, 7, 9]
+    w = [1] * 9 + [100]
+    assert list(idx(3, 0, 1, 10, w)) == [1, 4, 7, 10]
+    assert list(idx(3, 1, 1, 10, w)) == [2, 5, 8]
+    assert list(idx(3, 2, 1, 10, w)) == [3, 6, 9]
+
+
+def test_parallel_ks_round_robin():
+    # 4 k-points x 2 spins over 3 groups: group = mod((iS-1)*nK + iK-1, nGroup)
+    got = [schedule.parallel_ks(3, g, 4, 2) for g in range(3)]
+    assert got[0] == [(1, 1), (4, 1), (3, 2)]
+    assert got[1] == [(2, 1), (1, 2), (4, 2)]
+    assert got[2] == [(3, 1), (2, 2)]
+    allks = sorted(sum(got, []))
+    assert allks == sorted((k, s) for s in (1, 2) for k in (1, 2, 3, 4))
+    assert schedule.parallel_ks(1, 0, 2, 2) == [(1, 1), (2, 1), (1, 2), (2, 2)]

@@ -1,0 +1,106 @@
+#!/usr/bin/env python3
+"""Quick device-resident timings of every kernel (CUDA events on the library's stream) plus the
+cuBLAS FP64 GEMM / SYRK rate used as the FP64 tensor-pipe denominator.  Development aid; the judged
+numbers come from bench.py."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from dftbplus_b200 import workloads  # noqa: E402
+from dftbplus_b200.api import HotPath, new_dense  # noqa: E402
+
+
+def timeit(fn, stream, n=10, warm=3):
+    for _ in range(warm):
+        fn()
+    stream.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(n):
+        fn()
+    b.record(stream)
+    b.synchronize()
+    return a.elapsed_time(b) / n
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else "fec4096"
+    dense = "--dense" in sys.argv
+    dev = torch.device("cuda:0")
+    out = {"workload": name}
+    # cuBLAS FP64 rates
+    st0 = torch.cuda.current_stream()
+    n = 8192
+    A = torch.randn(n, n, dtype=torch.float64, device=dev)
+    B = torch.randn(n, n, dtype=torch.float64, device=dev)
+    ms = timeit(lambda: torch.matmul(A, B), st0, n=5, warm=2)
+    out["cublas_dgemm_8192_tflops"] = 2 * n ** 3 / ms / 1e9
+    del A, B
+    t0 = time.time()
+    w = workloads.BY_NAME[name]()
+    sk, geo, _ = workloads.prepare(w)
+    out["prep_s"] = time.time() - t0
+    hp = HotPath(0)
+    stream = torch.cuda.Stream(device=dev)
+    hp.set_stream(stream.cuda_stream)
+    sk.upload(hp)
+    hp.set_geometry(geo)
+    ss, nOrb, nAtom = geo["sparseSize"], geo["nOrb"], geo["nAtom"]
+    pairs = hp.num_pairs
+    out.update(nAtom=nAtom, nOrb=nOrb, sparseSize=ss, pairs=pairs)
+    f64 = dict(dtype=torch.float64, device=dev)
+    ham, over = torch.zeros(ss, **f64), torch.zeros(ss, **f64)
+    ms = timeit(lambda: hp.buildH0S(sk.selfegy, ham, over), stream)
+    blocks = geo["nOrbAtom"][:, None] * 0
+    out["k1_ms"] = ms
+    out["k1_pairs_per_s"] = pairs / ms * 1e3
+    out["k1_GBs"] = 16.0 * ss / ms / 1e6
+    rho = over * torch.randn(ss, **f64)
+    edm = over * torch.randn(ss, **f64)
+    qq = torch.zeros((nAtom, hp.mOrb), **f64)
+    ms = timeit(lambda: hp.mulliken(over, rho, qq=qq), stream)
+    out["k4_ms"] = ms
+    out["k4_GBs"] = 16.0 * ss / ms / 1e6
+    deriv = torch.zeros((nAtom, 3), **f64)
+    ms = timeit(lambda: hp.derivative_shift(rho, edm, deriv=deriv), stream, n=5)
+    out["k5_ms"] = ms
+    out["k5_pairs_per_s"] = pairs / ms * 1e3
+    if dense:
+        sq = new_dense(nOrb)
+        ms = timeit(lambda: hp.unpackHS(ham, square=sq), stream, n=5)
+        out["k2a_ms"] = ms
+        out["k2a_GBs"] = (8.0 * ss + 8.0 * nOrb * nOrb) / ms / 1e6
+        ms = timeit(lambda: hp.packHS(rho, sq), stream, n=5)
+        out["k2b_ms"] = ms
+        out["k2b_GBs"] = 24.0 * ss / ms / 1e6
+        C = new_dense(nOrb)
+        C.copy_(torch.randn(nOrb, nOrb, **f64) / nOrb ** 0.5)
+        nocc = int(sum(sum(sk.occ[s - 1]) for s in w["species0"]) / 2)
+        fill = torch.zeros(nOrb, **f64)
+        fill[:nocc] = 2.0
+        ms = timeit(lambda: hp.getDensityMatrix(C, fill, dm=sq), stream, n=2, warm=1)
+        out["k3_ms"] = ms
+        out["k3_nocc"] = nocc
+        out["k3_tflops"] = nOrb * nOrb * nocc / ms / 1e9
+        # cuBLAS dsyrk-equivalent through torch: C[:, :nocc] @ C[:, :nocc].T (full GEMM, 2x flops)
+        Cc = C[:, :nocc].contiguous()
+        with torch.cuda.stream(stream):
+            ms = timeit(lambda: torch.matmul(Cc, Cc.t()), stream, n=2, warm=1)
+        out["cublas_gemm_same_shape_ms"] = ms
+        out["cublas_gemm_same_shape_tflops"] = 2.0 * nOrb * nOrb * nocc / ms / 1e9
+    out["launches"] = hp.kernel_launches
+    print(json.dumps(out))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "probe_%s.json" % name), "w") as fh:
+        json.dump(out, fh, indent=1)
+    hp.close()
+
+
+if __name__ == "__main__":
+    main()
