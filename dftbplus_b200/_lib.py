@@ -41,6 +41,8 @@ SIGNATURES = {
     "dftbp_b200_derivative_shift": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_double]),
     "dftbp_b200_hegv_real": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_char]),
     "dftbp_b200_hegv_cplx": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_char]),
+    "dftbp_b200_timer_enable": (c_int, [c_void_p, c_int]),
+    "dftbp_b200_timer_read": (c_int, [c_void_p, c_int, P(c_double), P(ctypes.c_longlong)]),
     "dftbp_b200_kernel_launches": (ctypes.c_longlong, [c_void_p]),
     "dftbp_b200_num_pairs": (ctypes.c_longlong, [c_void_p]),
 }

@@ -96,6 +96,28 @@ class HotPath:
     def set_stream(self, cuda_stream_ptr):
         self._ck(self._L.dftbp_b200_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr)))
 
+    def use_torch_stream(self):
+        """Enqueue on torch's current stream (needed whenever torch tensors are passed as device
+        pointers: the producer/consumer kernels of those tensors live on that stream)."""
+        import torch
+        s = torch.cuda.current_stream().cuda_stream
+        self.set_stream(s if s != 0 else 1)      # 0 = legacy default stream -> cudaStreamLegacy
+
+    TIMERS = ("sparseH0S", "sparseToDense", "denseToSparse", "densityMatrix", "mulliken", "forceCalc",
+              "diagonalization")
+
+    def timer_enable(self, on=True):
+        self._ck(self._L.dftbp_b200_timer_enable(self._h, 1 if on else 0))
+
+    def timer_read(self):
+        """{name: (total device ms, calls)} with the reference's timer names (environment.F90:96-134)."""
+        out = {}
+        for i, name in enumerate(self.TIMERS):
+            ms, n = ctypes.c_double(), ctypes.c_longlong()
+            self._ck(self._L.dftbp_b200_timer_read(self._h, i, ctypes.byref(ms), ctypes.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
+
     def synchronize(self):
         self._ck(self._L.dftbp_b200_synchronize(self._h))
 

@@ -73,6 +73,24 @@ struct PendingCopy {
   size_t bytes;
 };
 
+// Device-time accounting per routine, named after the reference's global timers
+// (common/environment.F90:96-134) so CPU-vs-GPU tables line up.
+enum TimerSlot {
+  kTimerSparseH0S = 0,    // "Sparse H0 and S build"          K1
+  kTimerSparseToDense,    // "Sparse to dense"                K2a (zero-fill + scatter)
+  kTimerDenseToSparse,    // "Dense to sparse"                K2b
+  kTimerDensityMatrix,    // "Density matrix creation"        K3
+  kTimerMulliken,         // Mulliken (part of "SCC")         K4
+  kTimerForceCalc,        // "Force calculation"              K5
+  kTimerDiagonalization,  // "Diagonalisation"                cuSOLVER
+  kTimerCount
+};
+
+struct TimedSpan {
+  cudaEvent_t a, b;
+  int slot;
+};
+
 }  // namespace dftbp_b200
 
 struct dftbp_b200_ctx {
@@ -103,6 +121,11 @@ struct dftbp_b200_ctx {
   std::vector<dftbp_b200::Staging> staging;
   std::vector<dftbp_b200::PendingCopy> pending;
   double *dSelfE = nullptr;  // (mOrb, nSpecies) on-site energy per orbital
+  bool timing = false;
+  std::vector<dftbp_b200::TimedSpan> spans;
+  std::vector<cudaEvent_t> eventPool;
+  double timerMs[dftbp_b200::kTimerCount] = {0};
+  long long timerCalls[dftbp_b200::kTimerCount] = {0};
   void *solverHandle = nullptr;
   void *solverWork = nullptr;
   size_t solverWorkBytes = 0;
@@ -239,6 +262,35 @@ inline int gridFor(const dftbp_b200_ctx *ctx, long long nWarpItems, int warpsPer
   if (need < 1) need = 1;
   return (int)(need < cap ? need : cap);
 }
+
+// RAII span: records an event pair around the launches of one routine when timing is enabled.
+struct ScopedTimer {
+  dftbp_b200_ctx *ctx;
+  TimedSpan span;
+  bool on;
+  ScopedTimer(dftbp_b200_ctx *c, int slot) : ctx(c), on(c->timing) {
+    if (!on) return;
+    auto get = [&]() {
+      cudaEvent_t e;
+      if (!ctx->eventPool.empty()) {
+        e = ctx->eventPool.back();
+        ctx->eventPool.pop_back();
+      } else {
+        cudaEventCreate(&e);
+      }
+      return e;
+    };
+    span.a = get();
+    span.b = get();
+    span.slot = slot;
+    cudaEventRecord(span.a, ctx->stream);
+  }
+  ~ScopedTimer() {
+    if (!on) return;
+    cudaEventRecord(span.b, ctx->stream);
+    ctx->spans.push_back(span);
+  }
+};
 
 // implemented in context.cu / solver.cu
 int syncPrograms(dftbp_b200_ctx *ctx);

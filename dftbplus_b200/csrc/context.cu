@@ -132,6 +132,8 @@ int dftbp_b200_destroy(dftbp_b200_ctx *ctx) {
   cudaFree(ctx->dElemStart); cudaFree(ctx->dTerms); cudaFree(ctx->dYDesc); cudaFree(ctx->dSelfE);
   cudaFree(ctx->solverWork); cudaFree(ctx->dInfo);
   solverDestroy(ctx);
+  for (TimedSpan &sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
   if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;
@@ -150,8 +152,43 @@ int dftbp_b200_set_stream(dftbp_b200_ctx *ctx, void *s) {
     return 0;
   }
   if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
-  ctx->stream = (cudaStream_t)s;
+  ctx->stream = (s == (void *)1) ? cudaStreamLegacy : (cudaStream_t)s;
   ctx->ownStream = false;
+  return 0;
+}
+
+int dftbp_b200_timer_enable(dftbp_b200_ctx *ctx, int on) {
+  if (!ctx) return DFTBP_B200_EINVAL;
+  DFTBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (TimedSpan &sp : ctx->spans) {
+    ctx->eventPool.push_back(sp.a);
+    ctx->eventPool.push_back(sp.b);
+  }
+  ctx->spans.clear();
+  for (int i = 0; i < kTimerCount; ++i) {
+    ctx->timerMs[i] = 0.0;
+    ctx->timerCalls[i] = 0;
+  }
+  ctx->timing = on != 0;
+  return 0;
+}
+
+int dftbp_b200_timer_read(dftbp_b200_ctx *ctx, int slot, double *ms, long long *calls) {
+  if (!ctx) return DFTBP_B200_EINVAL;
+  DFTBP_CHECK(ctx, slot >= 0 && slot < kTimerCount && ms && calls, "timer_read: bad arguments");
+  DFTBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (TimedSpan &sp : ctx->spans) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) {
+      ctx->timerMs[sp.slot] += t;
+      ctx->timerCalls[sp.slot] += 1;
+    }
+    ctx->eventPool.push_back(sp.a);
+    ctx->eventPool.push_back(sp.b);
+  }
+  ctx->spans.clear();
+  *ms = ctx->timerMs[slot];
+  *calls = ctx->timerCalls[slot];
   return 0;
 }
 

@@ -103,6 +103,7 @@ int launchBuild(dftbp_b200_ctx *ctx, const double *selfegy, double *ham, double 
     if (partial) DFTBP_CUDA(ctx, cudaMemsetAsync(p.over, 0, sizeof(double) * g.sparseSize, ctx->stream));
   }
   if (p.nWork > 0) {
+    ScopedTimer timer(ctx, kTimerSparseH0S);
     const int grid = gridFor(ctx, p.nWork, kWarpsPerCta, 8 * 4);
     if (ham && over) k1_pair_build<true, true><<<grid, 32 * kWarpsPerCta, 0, ctx->stream>>>(p);
     else if (ham) k1_pair_build<true, false><<<grid, 32 * kWarpsPerCta, 0, ctx->stream>>>(p);

@@ -130,6 +130,8 @@ int unpackImpl(dftbp_b200_ctx *ctx, const double *orig, const double *kPoint, vo
   double *dSq;
   DFTBP_TRY(devIn(ctx, kSlotA, orig, (size_t)g.sparseSize, &dOrig));
   DFTBP_TRY(devOut(ctx, kSlotB, (double *)square, nSq, false, &dSq));
+  {
+  ScopedTimer timer(ctx, kTimerSparseToDense);
   DFTBP_CUDA(ctx, cudaMemsetAsync(dSq, 0, nSq * sizeof(double), ctx->stream));
   const K2Params p = makeParams(ctx, ld, kPoint, 1.0);
   const int grid = gridFor(ctx, p.nWork, 8, 8);
@@ -140,7 +142,8 @@ int unpackImpl(dftbp_b200_ctx *ctx, const double *orig, const double *kPoint, vo
     if (g.hasDuplicates) k2_unpack<false, true><<<grid, 256, 0, ctx->stream>>>(p, dOrig, dSq);
     else k2_unpack<false, false><<<grid, 256, 0, ctx->stream>>>(p, dOrig, dSq);
   }
-  ctx->launches += 2;  // memset + scatter
+  ctx->launches += 1;  // the scatter kernel (the zero-fill is a cudaMemsetAsync)
+  }
   return finish(ctx);
 }
 
@@ -155,11 +158,14 @@ int packImpl(dftbp_b200_ctx *ctx, double *primitive, const void *square, int ld,
   const double *dSq;
   DFTBP_TRY(devOut(ctx, kSlotA, primitive, (size_t)g.sparseSize, true, &dPrim));
   DFTBP_TRY(devIn(ctx, kSlotB, (const double *)square, nSq, &dSq));
-  const K2Params p = makeParams(ctx, ld, kPoint, kWeight);
-  const int grid = gridFor(ctx, p.nWork, 8, 8);
-  if (cplx) k2_pack<true><<<grid, 256, 0, ctx->stream>>>(p, dPrim, dSq);
-  else k2_pack<false><<<grid, 256, 0, ctx->stream>>>(p, dPrim, dSq);
-  ctx->launches++;
+  {
+    ScopedTimer timer(ctx, kTimerDenseToSparse);
+    const K2Params p = makeParams(ctx, ld, kPoint, kWeight);
+    const int grid = gridFor(ctx, p.nWork, 8, 8);
+    if (cplx) k2_pack<true><<<grid, 256, 0, ctx->stream>>>(p, dPrim, dSq);
+    else k2_pack<false><<<grid, 256, 0, ctx->stream>>>(p, dPrim, dSq);
+    ctx->launches++;
+  }
   return finish(ctx);
 }
 

@@ -309,10 +309,12 @@ int densityImpl(dftbp_b200_ctx *ctx, void *dm, const void *eigvecs, int n, int l
   dW = dF;
   if (weights) DFTBP_TRY(devIn(ctx, kSlotD, weights, (size_t)n, &dW));
   DFTBP_TRY(devOut(ctx, kSlotB, (double *)dm, (size_t)ld * n * el, false, &dDm));
+  {
+  ScopedTimer timer(ctx, kTimerDensityMatrix);
   // dm(:,:) = 0 (densitymatrix.F90:547); the kernel then fills the lower triangle
   DFTBP_CUDA(ctx, cudaMemsetAsync(dDm, 0, sizeof(double) * ld * n * el, ctx->stream));
   k3_count_levels<<<1, 256, 0, ctx->stream>>>(dF, n, ctx->dInfo);
-  ctx->launches += 2;
+  ctx->launches += 1;  // k3_count_levels
   const int *K = ctx->dInfo;  // stays on the device: no host round trip inside the SCC loop
   if (!cplx) {
     const bool big = n >= 1024;
@@ -353,6 +355,7 @@ int densityImpl(dftbp_b200_ctx *ctx, void *dm, const void *eigvecs, int n, int l
     kern<<<grid, 128, smemB, ctx->stream>>>((const double2 *)dC, ld, dW, n, K, (double2 *)dDm, ld, o);
   }
   ctx->launches++;
+  }
   return finish(ctx);
 }
 

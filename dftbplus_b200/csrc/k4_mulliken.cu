@@ -106,6 +106,7 @@ int mullikenImpl(dftbp_b200_ctx *ctx, double *qq, const double *over, const doub
   p.iNeighbour = g.iNeighbour; p.iPair = g.iPair; p.img2CentCell = g.img2CentCell;
   p.iAtomStart = g.iAtomStart;
   if (p.nWork > 0) {
+    ScopedTimer timer(ctx, kTimerMulliken);
     const int grid = gridFor(ctx, p.nWork, 8, 8);
     if (block) k4_mulliken_block<<<grid, 256, 0, ctx->stream>>>(p, dOver, dRho, dQ);
     else k4_mulliken_orbital<<<grid, 256, 0, ctx->stream>>>(p, dOver, dRho, dQ);

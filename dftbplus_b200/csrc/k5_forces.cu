@@ -149,8 +149,8 @@ extern "C" int dftbp_b200_derivative_shift(dftbp_b200_ctx *ctx, double *deriv, c
     DFTBP_TRY(devIn(ctx, kSlotC, shift, (size_t)ctx->mOrb * ctx->mOrb * g.nAtom * nSpin, &p.shift));
   DFTBP_TRY(devOut(ctx, kSlotD, deriv, (size_t)3 * g.nAtom, false, &p.deriv));
   DFTBP_CUDA(ctx, cudaMemsetAsync(p.deriv, 0, sizeof(double) * 3 * g.nAtom, ctx->stream));
-  ctx->launches++;
   if (p.nWork > 0) {
+    ScopedTimer timer(ctx, kTimerForceCalc);
     const int grid = gridFor(ctx, p.nWork, kWarpsPerCta, 8 * 4);
     const int ne = (ctx->mOrb * ctx->mOrb + 31) / 32;
     if (ne <= 1) k5_derivative_shift<1><<<grid, 32 * kWarpsPerCta, 0, ctx->stream>>>(p);

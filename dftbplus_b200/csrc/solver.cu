@@ -61,12 +61,15 @@ int hegvImpl(dftbp_b200_ctx *ctx, void *H, void *S, double *eigen, int n, int ld
     return fail(ctx, DFTBP_B200_ECUDA, "cusolver hegvd bufferSize failed (%d)", (int)st);
   }
   DFTBP_TRY(ensureWork(ctx, (size_t)lwork * sizeof(double) * el));
+  {
+  ScopedTimer timer(ctx, kTimerDiagonalization);
   if (cplx)
     st = cusolverDnZhegvd(h, CUSOLVER_EIG_TYPE_1, mode, CUBLAS_FILL_MODE_LOWER, n, (cuDoubleComplex *)dH, ld,
                           (cuDoubleComplex *)dS, ld, dE, (cuDoubleComplex *)ctx->solverWork, lwork, ctx->dInfo);
   else
     st = cusolverDnDsygvd(h, CUSOLVER_EIG_TYPE_1, mode, CUBLAS_FILL_MODE_LOWER, n, dH, ld, dS, ld, dE,
                           (double *)ctx->solverWork, lwork, ctx->dInfo);
+  }
   if (st != CUSOLVER_STATUS_SUCCESS) {
     ctx->pending.clear();
     return fail(ctx, DFTBP_B200_ECUDA, "cusolver hegvd failed (%d)", (int)st);

@@ -65,8 +65,11 @@ int dftbp_b200_destroy(dftbp_b200_ctx *ctx);
 const char *dftbp_b200_last_error(const dftbp_b200_ctx *ctx);
 const char *dftbp_b200_version(void);
 
-/* Use an existing CUDA stream (cudaStream_t passed as void*); NULL = the context's own.
- * dftbp_b200_synchronize blocks until all work queued by this context has finished. */
+/* Use an existing CUDA stream (cudaStream_t passed as void*); NULL = the context's own
+ * (non-blocking) stream; (void*)1 = cudaStreamLegacy, the default stream most host frameworks
+ * (PyTorch included) enqueue on.  Device-pointer callers must put the library on the stream that
+ * produces / consumes their buffers.  dftbp_b200_synchronize blocks until all work queued by this
+ * context has finished. */
 int dftbp_b200_set_stream(dftbp_b200_ctx *ctx, void *cuda_stream);
 void *dftbp_b200_get_stream(dftbp_b200_ctx *ctx);
 int dftbp_b200_synchronize(dftbp_b200_ctx *ctx);
@@ -178,6 +181,22 @@ int dftbp_b200_hegv_cplx(dftbp_b200_ctx *ctx, void *H_c128, void *S_c128, double
                          int ld, char jobz);
 
 /* ---- introspection (bench / tests) --------------------------------------------------------- */
+
+/* Device-time accounting per routine with CUDA events on the context's stream; slots are named
+ * after the reference's timers (common/environment.F90:96-134). */
+enum {
+  DFTBP_B200_TIMER_SPARSE_H0S = 0,     /* "Sparse H0 and S build"   */
+  DFTBP_B200_TIMER_SPARSE_TO_DENSE,    /* "Sparse to dense"         */
+  DFTBP_B200_TIMER_DENSE_TO_SPARSE,    /* "Dense to sparse"         */
+  DFTBP_B200_TIMER_DENSITY_MATRIX,     /* "Density matrix creation" */
+  DFTBP_B200_TIMER_MULLIKEN,
+  DFTBP_B200_TIMER_FORCE_CALC,         /* "Force calculation"       */
+  DFTBP_B200_TIMER_DIAGONALIZATION,    /* "Diagonalisation"         */
+  DFTBP_B200_TIMER_COUNT
+};
+int dftbp_b200_timer_enable(dftbp_b200_ctx *ctx, int on);   /* also resets the accumulators */
+/* synchronises the stream; total device milliseconds and number of calls of one slot */
+int dftbp_b200_timer_read(dftbp_b200_ctx *ctx, int slot, double *ms, long long *calls);
 
 /* number of kernels this context has launched since creation */
 long long dftbp_b200_kernel_launches(const dftbp_b200_ctx *ctx);

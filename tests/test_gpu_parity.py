@@ -221,7 +221,11 @@ def test_device_resident_scc_step(hp_cache):
     build -> unpack -> hegvd -> DM -> pack -> Mulliken -> E-DM -> forces; against the oracle chain."""
     import torch
     w, sk, geo, model, selfegy, H, S, eig, C, f = _eig_case("fec128")
-    hp = hp_cache("fec128")
+    from dftbplus_b200.api import HotPath
+    hp = HotPath(0)
+    hp.use_torch_stream()          # torch tensors as device pointers: share torch's stream
+    sk.upload(hp)
+    hp.set_geometry(geo)
     dev = torch.device("cuda:0")
     n, ss = geo["nOrb"], geo["sparseSize"]
     ham = torch.zeros(ss, dtype=torch.float64, device=dev)
@@ -298,6 +302,7 @@ def test_full_size_properties_fec4096():
         n = geo["nOrbAtom"][a]
         blk = x[geo["iPair"][a, 0]:geo["iPair"][a, 0] + n * n].reshape(n, n)
         blk[:] = 0.5 * (blk + blk.T)
+    hp.use_torch_stream()
     xd = torch.from_numpy(x).cuda()
     sq = new_dense(geo["nOrb"])
     hp.unpackHS(xd, square=sq)

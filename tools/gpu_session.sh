@@ -1,0 +1,14 @@
+#!/bin/bash
+# One GPU-box session: parity tests, bench, ncu evidence.  Usage: tools/gpu_session.sh [tag]
+TAG=${1:-r01}
+mkdir -p gpurun_out
+echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee gpurun_out/pytest_$TAG.log
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke_$TAG.log
+echo "== bench"; timeout 900 python bench.py 2>&1 | tail -3 | tee gpurun_out/bench_$TAG.log
+echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -2 | tee gpurun_out/bench_ref_$TAG.log
+echo "== ncu launch list (bench, pair path only)"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 1 --no-dense > gpurun_out/ncu_launch_$TAG.log 2>&1
+echo "== ncu full: K1, K5, K4, K2, K3, cuBLAS dgemm"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k1_pair_build|k5_derivative|k4_mulliken|k2_unpack|k2_pack' -c 8 -o gpurun_out/prof_pairs_$TAG python tools/gpu_probe.py fec4096 --dense > gpurun_out/ncu_pairs_$TAG.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k3_dm_real|gemm|dgemm' -c 4 -o gpurun_out/prof_dm_$TAG python tools/gpu_probe.py fec1024 --dense > gpurun_out/ncu_dm_$TAG.log 2>&1
+ls -la gpurun_out | tail -20
