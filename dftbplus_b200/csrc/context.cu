@@ -118,7 +118,7 @@ int dftbp_b200_create(dftbp_b200_ctx **out, int device, int rank, int nRanks) {
   cudaDeviceProp prop;
   DFTBP_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
   ctx->smCount = prop.multiProcessorCount;
-  DFTBP_CUDA(ctx, cudaMalloc((void **)&ctx->dInfo, sizeof(int)));
+  DFTBP_CUDA(ctx, cudaMalloc((void **)&ctx->dInfo, 4 * sizeof(int)));  // [0] info / nLevels, [2..3] tile counter
   return 0;
 }
 

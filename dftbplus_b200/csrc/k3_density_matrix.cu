@@ -14,6 +14,8 @@
 // doubles so the (k = lane%4, mn = lane/4) fragment loads are bank-conflict free.
 //
 // Roofline: FP64 tensor pipe; flops = n^2 * nLevels (one triangle, FMA = 2), x4 for complex.
+#include <cstdlib>
+
 #include "common.cuh"
 
 using namespace dftbp_b200;
@@ -64,7 +66,8 @@ __device__ __forceinline__ bool tileAt(const TileOrder &o, long long idx, int *t
 template <int BM, int BK, int STAGES, int WARPS_M, int WARPS_N, int VEC>
 __global__ void __launch_bounds__(32 * WARPS_M * WARPS_N)
 k3_dm_real(const double *__restrict__ C, int ldc, const double *__restrict__ wgt, int n,
-           const int *__restrict__ nLevels, double *__restrict__ dm, int ldd, TileOrder order) {
+           const int *__restrict__ nLevels, double *__restrict__ dm, int ldd, TileOrder order,
+           unsigned long long *tileCounter) {
   const int K = *nLevels;
   constexpr int NT = 32 * WARPS_M * WARPS_N;
   constexpr int PITCH = BM + 4;
@@ -80,7 +83,15 @@ k3_dm_real(const double *__restrict__ C, int ldc, const double *__restrict__ wgt
   const int nK = (K + BK - 1) / BK;
   const long long nIdx = (long long)order.nSB * (order.nSB + 1) / 2 * order.G * order.G;
 
-  for (long long idx = blockIdx.x; idx < nIdx; idx += gridDim.x) {
+  __shared__ long long nextSlot;
+  for (;;) {
+    // dynamic tile scheduler: one atomic per tile keeps all SMs busy to the end (diagonal
+    // super-blocks are half empty, so a static round-robin leaves SMs idle for ~30% of the time)
+    __syncthreads();
+    if (tid == 0) nextSlot = atomicAdd(tileCounter, 1ULL);
+    __syncthreads();
+    const long long idx = nextSlot;
+    if (idx >= nIdx) break;
     int ti, tj;
     if (!tileAt(order, idx, &ti, &tj)) continue;
     const int i0 = ti * BM, j0 = tj * BM;
@@ -170,7 +181,8 @@ k3_dm_real(const double *__restrict__ C, int ldc, const double *__restrict__ wgt
 template <int BM, int BK, int STAGES, int WARPS_M, int WARPS_N>
 __global__ void __launch_bounds__(32 * WARPS_M * WARPS_N)
 k3_dm_cplx(const double2 *__restrict__ C, int ldc, const double *__restrict__ wgt, int n,
-           const int *__restrict__ nLevels, double2 *__restrict__ dm, int ldd, TileOrder order) {
+           const int *__restrict__ nLevels, double2 *__restrict__ dm, int ldd, TileOrder order,
+           unsigned long long *tileCounter) {
   const int K = *nLevels;
   constexpr int NT = 32 * WARPS_M * WARPS_N;
   constexpr int PITCH = BM + 2;  // in complex (16-byte) units: = 2 (mod 8) for conflict-free LDS.128
@@ -186,7 +198,15 @@ k3_dm_cplx(const double2 *__restrict__ C, int ldc, const double *__restrict__ wg
   const int nK = (K + BK - 1) / BK;
   const long long nIdx = (long long)order.nSB * (order.nSB + 1) / 2 * order.G * order.G;
 
-  for (long long idx = blockIdx.x; idx < nIdx; idx += gridDim.x) {
+  __shared__ long long nextSlot;
+  for (;;) {
+    // dynamic tile scheduler: one atomic per tile keeps all SMs busy to the end (diagonal
+    // super-blocks are half empty, so a static round-robin leaves SMs idle for ~30% of the time)
+    __syncthreads();
+    if (tid == 0) nextSlot = atomicAdd(tileCounter, 1ULL);
+    __syncthreads();
+    const long long idx = nextSlot;
+    if (idx >= nIdx) break;
     int ti, tj;
     if (!tileAt(order, idx, &ti, &tj)) continue;
     const int i0 = ti * BM, j0 = tj * BM;
@@ -297,6 +317,19 @@ int setSmem(dftbp_b200_ctx *ctx, Kern k, size_t bytes) {
   return 0;
 }
 
+template <int BM, int BK, int ST, int WMn, int WNn, int VEC>
+int launchReal(dftbp_b200_ctx *ctx, int ctasPerSm, const double *dC, int ld, const double *dW, int n,
+               const int *K, double *dDm, unsigned long long *counter) {
+  const size_t smemB = sizeof(double) * (2 * ST * BK * (BM + 4) + ST * BK);
+  const TileOrder o = makeOrder(n, BM);
+  const long long nTiles = (long long)o.nT * (o.nT + 1) / 2;
+  const int grid = (int)std::min<long long>(nTiles, (long long)ctasPerSm * ctx->smCount);
+  auto kern = k3_dm_real<BM, BK, ST, WMn, WNn, VEC>;
+  DFTBP_TRY(setSmem(ctx, kern, smemB));
+  kern<<<grid, 32 * WMn * WNn, smemB, ctx->stream>>>(dC, ld, dW, n, K, dDm, ld, o, counter);
+  return 0;
+}
+
 int densityImpl(dftbp_b200_ctx *ctx, void *dm, const void *eigvecs, int n, int ld, const double *filling,
                 const double *weights, bool cplx) {
   if (!ctx) return DFTBP_B200_EINVAL;
@@ -316,33 +349,37 @@ int densityImpl(dftbp_b200_ctx *ctx, void *dm, const void *eigvecs, int n, int l
   k3_count_levels<<<1, 256, 0, ctx->stream>>>(dF, n, ctx->dInfo);
   ctx->launches += 1;  // k3_count_levels
   const int *K = ctx->dInfo;  // stays on the device: no host round trip inside the SCC loop
+  unsigned long long *counter = reinterpret_cast<unsigned long long *>(ctx->dInfo + 2);
+  DFTBP_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
   if (!cplx) {
-    const bool big = n >= 1024;
     const bool aligned = (ld % 2 == 0) && ((reinterpret_cast<size_t>(dC) & 15) == 0);
-    if (big) {
-      constexpr int BM = 128, BK = 16, ST = 4;
-      const size_t smemB = sizeof(double) * (2 * ST * BK * (BM + 4) + ST * BK);
-      const TileOrder o = makeOrder(n, BM);
-      const long long nTiles = (long long)o.nT * (o.nT + 1) / 2;
-      const int grid = (int)std::min<long long>(nTiles, ctx->smCount);
-      if (aligned) {
-        auto kern = k3_dm_real<BM, BK, ST, 2, 4, 2>;
-        DFTBP_TRY(setSmem(ctx, kern, smemB));
-        kern<<<grid, 256, smemB, ctx->stream>>>(dC, ld, dW, n, K, dDm, ld, o);
-      } else {
-        auto kern = k3_dm_real<BM, BK, ST, 2, 4, 1>;
-        DFTBP_TRY(setSmem(ctx, kern, smemB));
-        kern<<<grid, 256, smemB, ctx->stream>>>(dC, ld, dW, n, K, dDm, ld, o);
-      }
+    // tuning hook (development only): DFTBP_B200_K3_VARIANT selects a tile configuration
+    const char *env = getenv("DFTBP_B200_K3_VARIANT");
+    const int variant = env ? atoi(env) : 0;
+    if (n < 1024) {
+      DFTBP_TRY((launchReal<64, 16, 3, 2, 2, 1>(ctx, 2, dC, ld, dW, n, K, dDm, counter)));
+    } else if (!aligned) {
+      DFTBP_TRY((launchReal<128, 16, 4, 2, 4, 1>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
+    } else if (variant == 1) {
+      DFTBP_TRY((launchReal<128, 16, 4, 4, 4, 2>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
+    } else if (variant == 2) {
+      DFTBP_TRY((launchReal<128, 32, 3, 2, 4, 2>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
+    } else if (variant == 3) {
+      DFTBP_TRY((launchReal<128, 16, 4, 2, 4, 2>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
+    } else if (variant == 6) {
+      DFTBP_TRY((launchReal<64, 16, 3, 2, 2, 2>(ctx, 4, dC, ld, dW, n, K, dDm, counter)));
+    } else if (variant == 7) {
+      DFTBP_TRY((launchReal<64, 16, 4, 2, 2, 2>(ctx, 2, dC, ld, dW, n, K, dDm, counter)));
+    } else if (variant == 8) {
+      DFTBP_TRY((launchReal<64, 32, 3, 2, 2, 2>(ctx, 2, dC, ld, dW, n, K, dDm, counter)));
+    } else if (variant == 9) {
+      DFTBP_TRY((launchReal<64, 16, 4, 4, 2, 2>(ctx, 3, dC, ld, dW, n, K, dDm, counter)));
+    } else if (variant == 10) {
+      DFTBP_TRY((launchReal<64, 8, 6, 2, 2, 2>(ctx, 4, dC, ld, dW, n, K, dDm, counter)));
     } else {
-      constexpr int BM = 64, BK = 16, ST = 3;
-      const size_t smemB = sizeof(double) * (2 * ST * BK * (BM + 4) + ST * BK);
-      const TileOrder o = makeOrder(n, BM);
-      const long long nTiles = (long long)o.nT * (o.nT + 1) / 2;
-      const int grid = (int)std::min<long long>(nTiles, 2LL * ctx->smCount);
-      auto kern = k3_dm_real<BM, BK, ST, 2, 2, 1>;
-      DFTBP_TRY(setSmem(ctx, kern, smemB));
-      kern<<<grid, 128, smemB, ctx->stream>>>(dC, ld, dW, n, K, dDm, ld, o);
+      // 64x64 tiles, 4 warps of 32x32, three CTAs per SM: independent barrier domains hide the
+      // per-k-tile __syncthreads better than one 128x128 CTA (measured 30.3 vs 26.3 TFLOP/s)
+      DFTBP_TRY((launchReal<64, 16, 4, 2, 2, 2>(ctx, 3, dC, ld, dW, n, K, dDm, counter)));
     }
   } else {
     constexpr int BM = 64, BK = 8, ST = 4;
@@ -352,7 +389,7 @@ int densityImpl(dftbp_b200_ctx *ctx, void *dm, const void *eigvecs, int n, int l
     const int grid = (int)std::min<long long>(nTiles, 2LL * ctx->smCount);
     auto kern = k3_dm_cplx<BM, BK, ST, 2, 2>;
     DFTBP_TRY(setSmem(ctx, kern, smemB));
-    kern<<<grid, 128, smemB, ctx->stream>>>((const double2 *)dC, ld, dW, n, K, (double2 *)dDm, ld, o);
+    kern<<<grid, 128, smemB, ctx->stream>>>((const double2 *)dC, ld, dW, n, K, (double2 *)dDm, ld, o, counter);
   }
   ctx->launches++;
   }

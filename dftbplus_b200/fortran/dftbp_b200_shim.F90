@@ -1,0 +1,283 @@
+!> ISO_C_BINDING shim: lets the DFTB+ host call libdftbp_b200.so behind its own routine signatures.
+!>
+!> Delivered as source only -- this image has no Fortran compiler, so the file has been reviewed
+!> against the reference signatures but not compiled.  The wrapper routines take exactly the dummy
+!> arguments of the reference routines they replace (cited per routine), minus the derived types
+!> that the one-off set_* calls have already flattened into the context.
+module dftbp_b200_shim
+  use, intrinsic :: iso_c_binding
+  implicit none
+  private
+
+  public :: TB200Ctx, b200_init, b200_setGeometry
+  public :: b200_buildH0, b200_buildS, b200_unpackHS_real, b200_unpackHS_cmplx
+  public :: b200_packHS_real, b200_packHS_cmplx, b200_getDensityMatrix_real
+  public :: b200_mullikenPerOrbital, b200_derivative_shift
+
+  integer, parameter :: dp = c_double
+
+  type :: TB200Ctx
+    type(c_ptr) :: h = c_null_ptr
+  end type TB200Ctx
+
+  interface
+    integer(c_int) function dftbp_b200_create(ctx, device, rank, nRanks) bind(C)
+      import :: c_ptr, c_int
+      type(c_ptr), intent(out) :: ctx
+      integer(c_int), value :: device, rank, nRanks
+    end function
+    function dftbp_b200_last_error(ctx) bind(C) result(msg)
+      import :: c_ptr
+      type(c_ptr), value :: ctx
+      type(c_ptr) :: msg
+    end function
+    integer(c_int) function dftbp_b200_set_orbitals(ctx, nSpecies, mShell, nShell, angShell) bind(C)
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nSpecies, mShell
+      integer(c_int), intent(in) :: nShell(*), angShell(*)
+    end function
+    integer(c_int) function dftbp_b200_set_sk_table(ctx, which, sp1, sp2, nGrid, nInteg, dist, skTab,&
+        & skIntMethod) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: which, sp1, sp2, nGrid, nInteg, skIntMethod
+      real(c_double), value :: dist
+      real(c_double), intent(in) :: skTab(*)
+    end function
+    integer(c_int) function dftbp_b200_set_geometry(ctx, nAtom, nAllAtom, mNeigh, coords, species,&
+        & img2CentCell, iCellVec, nCellVec, cellVec, nNeighbourSK, iNeighbour, iPair, iAtomStart,&
+        & sparseSize) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nAtom, nAllAtom, mNeigh, nCellVec, sparseSize
+      real(c_double), intent(in) :: coords(*), cellVec(*)
+      integer(c_int), intent(in) :: species(*), img2CentCell(*), iCellVec(*), nNeighbourSK(*)
+      integer(c_int), intent(in) :: iNeighbour(*), iPair(*), iAtomStart(*)
+    end function
+    integer(c_int) function dftbp_b200_build_h0(ctx, selfegy, ham) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(in) :: selfegy(*)
+      real(c_double), intent(out) :: ham(*)
+    end function
+    integer(c_int) function dftbp_b200_build_s(ctx, over) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(out) :: over(*)
+    end function
+    integer(c_int) function dftbp_b200_unpack_hs_real(ctx, orig, square, ld) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(in) :: orig(*)
+      real(c_double), intent(out) :: square(*)
+      integer(c_int), value :: ld
+    end function
+    integer(c_int) function dftbp_b200_unpack_hs_cplx(ctx, orig, kPoint, square, ld) bind(C)
+      import :: c_ptr, c_int, c_double, c_double_complex
+      type(c_ptr), value :: ctx
+      real(c_double), intent(in) :: orig(*), kPoint(3)
+      complex(c_double_complex), intent(out) :: square(*)
+      integer(c_int), value :: ld
+    end function
+    integer(c_int) function dftbp_b200_pack_hs_real(ctx, primitive, square, ld) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(inout) :: primitive(*)
+      real(c_double), intent(in) :: square(*)
+      integer(c_int), value :: ld
+    end function
+    integer(c_int) function dftbp_b200_pack_hs_cplx(ctx, primitive, square, ld, kPoint, kWeight) bind(C)
+      import :: c_ptr, c_int, c_double, c_double_complex
+      type(c_ptr), value :: ctx
+      real(c_double), intent(inout) :: primitive(*)
+      complex(c_double_complex), intent(in) :: square(*)
+      integer(c_int), value :: ld
+      real(c_double), intent(in) :: kPoint(3)
+      real(c_double), value :: kWeight
+    end function
+    integer(c_int) function dftbp_b200_density_matrix_real(ctx, dm, eigvecs, n, ld, filling, weights)&
+        & bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(out) :: dm(*)
+      real(c_double), intent(in) :: eigvecs(*), filling(*)
+      integer(c_int), value :: n, ld
+      type(c_ptr), value :: weights
+    end function
+    integer(c_int) function dftbp_b200_mulliken_orbital(ctx, qq, over, rho) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(inout) :: qq(*)
+      real(c_double), intent(in) :: over(*), rho(*)
+    end function
+    integer(c_int) function dftbp_b200_derivative_shift(ctx, deriv, DM, nSpin, EDM, shift, diffType,&
+        & delta) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(out) :: deriv(*)
+      real(c_double), intent(in) :: DM(*), EDM(*)
+      integer(c_int), value :: nSpin, diffType
+      type(c_ptr), value :: shift
+      real(c_double), value :: delta
+    end function
+  end interface
+
+contains
+
+  !> Non-zero status -> the reference's abort path (io/message.F90:74-84).  Routines that carry a
+  !> TStatus (getDensityMatrix) would use @:RAISE_ERROR(errStatus, rc, msg) instead.
+  subroutine check(ctx, rc)
+    use dftbp_io_message, only : error
+    type(TB200Ctx), intent(in) :: ctx
+    integer(c_int), intent(in) :: rc
+    character(kind=c_char), pointer :: cmsg(:)
+    character(len=512) :: msg
+    integer :: ii
+    if (rc == 0) return
+    call c_f_pointer(dftbp_b200_last_error(ctx%h), cmsg, [512])
+    msg = ""
+    do ii = 1, 512
+      if (cmsg(ii) == c_null_char) exit
+      msg(ii:ii) = cmsg(ii)
+    end do
+    call error("libdftbp_b200: " // trim(msg))
+  end subroutine check
+
+  !> Once per run, after readSKFiles (dftbplus/parser.F90:3668): flattens TOrbitals + TSlakoCont.
+  !> skHam/skOver(iSp1,iSp2) hold the arrays that were passed to SlakoEqGrid_init.
+  subroutine b200_init(ctx, device, rank, nRanks, orb, nGrid, dist, skHam, skOver, skIntMethod)
+    use dftbp_type_orbitals, only : TOrbitals
+    type(TB200Ctx), intent(out) :: ctx
+    integer, intent(in) :: device, rank, nRanks
+    type(TOrbitals), intent(in) :: orb
+    integer, intent(in) :: nGrid(:,:), skIntMethod
+    real(dp), intent(in) :: dist(:,:)
+    real(dp), intent(in) :: skHam(:,:,:,:), skOver(:,:,:,:)   ! (nGridMax, nIntegMax, iSp1, iSp2)
+    integer :: iSp1, iSp2, nSp, nInt
+    nSp = size(orb%nShell)
+    call check(ctx, dftbp_b200_create(ctx%h, int(device, c_int), int(rank, c_int), int(nRanks, c_int)))
+    call check(ctx, dftbp_b200_set_orbitals(ctx%h, int(nSp, c_int), int(orb%mShell, c_int), orb%nShell,&
+        & orb%angShell))
+    do iSp1 = 1, nSp
+      do iSp2 = 1, nSp
+        nInt = nIntegrals(orb, iSp1, iSp2)
+        call check(ctx, dftbp_b200_set_sk_table(ctx%h, 0_c_int, iSp1, iSp2, nGrid(iSp1,iSp2), nInt,&
+            & dist(iSp1,iSp2), skHam(1:nGrid(iSp1,iSp2), 1:nInt, iSp1, iSp2), skIntMethod))
+        call check(ctx, dftbp_b200_set_sk_table(ctx%h, 1_c_int, iSp1, iSp2, nGrid(iSp1,iSp2), nInt,&
+            & dist(iSp1,iSp2), skOver(1:nGrid(iSp1,iSp2), 1:nInt, iSp1, iSp2), skIntMethod))
+      end do
+    end do
+  contains
+    integer function nIntegrals(orb, iSp1, iSp2)
+      type(TOrbitals), intent(in) :: orb
+      integer, intent(in) :: iSp1, iSp2
+      integer :: iSh1, iSh2
+      nIntegrals = 0
+      do iSh1 = 1, orb%nShell(iSp1)
+        do iSh2 = 1, orb%nShell(iSp2)
+          nIntegrals = nIntegrals + min(orb%angShell(iSh1, iSp1), orb%angShell(iSh2, iSp2)) + 1
+        end do
+      end do
+    end function nIntegrals
+  end subroutine b200_init
+
+  !> Once per geometry, at the end of handleCoordinateChange (dftbplus/main.F90:2413-2577).
+  subroutine b200_setGeometry(ctx, coords, species, img2CentCell, iCellVec, cellVec, nNeighbourSK,&
+      & iNeighbour, iSparseStart, iAtomStart, sparseSize)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(in) :: coords(:,:), cellVec(:,:)
+    integer, intent(in) :: species(:), img2CentCell(:), iCellVec(:), nNeighbourSK(:)
+    integer, intent(in) :: iNeighbour(0:,:), iSparseStart(0:,:), iAtomStart(:), sparseSize
+    integer :: nAtom, nAllAtom, mNeigh
+    nAtom = size(nNeighbourSK)
+    nAllAtom = size(coords, dim=2)
+    mNeigh = ubound(iNeighbour, dim=1)
+    ! iSparseStart may be allocated wider than iNeighbour; pass matching (0:mNeigh, nAtom) sections
+    call check(ctx, dftbp_b200_set_geometry(ctx%h, nAtom, nAllAtom, mNeigh, coords, species,&
+        & img2CentCell, iCellVec, size(cellVec, dim=2), cellVec, nNeighbourSK, iNeighbour,&
+        & iSparseStart(0:mNeigh, :), iAtomStart, sparseSize))
+  end subroutine b200_setGeometry
+
+  !> buildH0, dftb/nonscc.F90:66 (env, skHamCont, coords, ... are held by the context)
+  subroutine b200_buildH0(ctx, ham, selfegy)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(out) :: ham(:)
+    real(dp), intent(in) :: selfegy(:,:)
+    call check(ctx, dftbp_b200_build_h0(ctx%h, selfegy, ham))
+  end subroutine b200_buildH0
+
+  !> buildS, dftb/nonscc.F90:128
+  subroutine b200_buildS(ctx, over)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(out) :: over(:)
+    call check(ctx, dftbp_b200_build_s(ctx%h, over))
+  end subroutine b200_buildS
+
+  !> unpackHS_real, dftb/sparse2dense.F90:266
+  subroutine b200_unpackHS_real(ctx, square, orig)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(out) :: square(:,:)
+    real(dp), intent(in) :: orig(:)
+    call check(ctx, dftbp_b200_unpack_hs_real(ctx%h, orig, square, size(square, dim=1)))
+  end subroutine b200_unpackHS_real
+
+  !> unpackHS_cmplx_kpts, dftb/sparse2dense.F90:185
+  subroutine b200_unpackHS_cmplx(ctx, square, orig, kPoint)
+    type(TB200Ctx), intent(in) :: ctx
+    complex(dp), intent(out) :: square(:,:)
+    real(dp), intent(in) :: orig(:), kPoint(:)
+    call check(ctx, dftbp_b200_unpack_hs_cplx(ctx%h, orig, kPoint, square, size(square, dim=1)))
+  end subroutine b200_unpackHS_cmplx
+
+  !> packHS_real, dftb/sparse2dense.F90:1024
+  subroutine b200_packHS_real(ctx, primitive, square)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(inout) :: primitive(:)
+    real(dp), intent(in) :: square(:,:)
+    call check(ctx, dftbp_b200_pack_hs_real(ctx%h, primitive, square, size(square, dim=1)))
+  end subroutine b200_packHS_real
+
+  !> packHS_cmplx_kpts, dftb/sparse2dense.F90:820
+  subroutine b200_packHS_cmplx(ctx, primitive, square, kPoint, kWeight)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(inout) :: primitive(:)
+    complex(dp), intent(in) :: square(:,:)
+    real(dp), intent(in) :: kPoint(:), kWeight
+    call check(ctx, dftbp_b200_pack_hs_cplx(ctx%h, primitive, square, size(square, dim=1), kPoint, kWeight))
+  end subroutine b200_packHS_cmplx
+
+  !> fullDensityMatrix_real, dftb/densitymatrix.F90:530 (eigenvecs is left untouched)
+  subroutine b200_getDensityMatrix_real(ctx, dm, eigenvecs, filling)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(out) :: dm(:,:)
+    real(dp), intent(in) :: eigenvecs(:,:), filling(:)
+    call check(ctx, dftbp_b200_density_matrix_real(ctx%h, dm, eigenvecs, size(dm, dim=2),&
+        & size(dm, dim=1), filling, c_null_ptr))
+  end subroutine b200_getDensityMatrix_real
+
+  !> mullikenPerOrbital, dftb/populations.F90:120
+  subroutine b200_mullikenPerOrbital(ctx, qq, over, rho)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(inout) :: qq(:,:)
+    real(dp), intent(in) :: over(:), rho(:)
+    call check(ctx, dftbp_b200_mulliken_orbital(ctx%h, qq, over, rho))
+  end subroutine b200_mullikenPerOrbital
+
+  !> derivative_shift, dftb/forces.F90:27-38 (block variant when shift is present)
+  subroutine b200_derivative_shift(ctx, deriv, DM, EDM, shift, diffType, deltaXDiff)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(out) :: deriv(:,:)
+    real(dp), intent(in), target :: DM(:,:)
+    real(dp), intent(in) :: EDM(:)
+    real(dp), intent(in), target, optional :: shift(:,:,:,:)
+    integer, intent(in) :: diffType
+    real(dp), intent(in) :: deltaXDiff
+    type(c_ptr) :: pShift
+    pShift = c_null_ptr
+    if (present(shift)) pShift = c_loc(shift)
+    call check(ctx, dftbp_b200_derivative_shift(ctx%h, deriv, DM, size(DM, dim=2), EDM, pShift,&
+        & int(diffType, c_int), deltaXDiff))
+  end subroutine b200_derivative_shift
+
+end module dftbp_b200_shim
