@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -41,7 +42,20 @@ struct SpPairProg {
   int nOrb1, nOrb2, nInteg, nY;
   int aOff;     // first ADesc
   int elemOff;  // first entry of elemStart (nOrb1*nOrb2 + 1 entries, absolute term indices)
+  int nSh1, nSh2;                     // shells of the atom / of the neighbour
+  unsigned long long shells1, shells2;  // angular momentum per shell, 4 bits each (shell 0 lowest)
+  int canon1, canon2;  // lmax if the species' shells are exactly l = 0..lmax in order (s, sp, spd, spdf), else -1
   int pad0, pad1;
+};
+
+// Device-built schedule of the lane-per-pair kernels (pair_sort.cu): the off-site pairs of one work
+// list, counting-sorted by (species pair, distance bin) and padded with -1 so that every aligned
+// group of 32 entries (= one warp) holds one species pair and neighbouring table rows.
+struct SortedPairs {
+  int *items = nullptr;   // flat ids iNeigh + ld*iAtom0, -1 = padding
+  int *total = nullptr;   // device scalar: padded length (multiple of 32)
+  long long capacity = 0; // allocated entries of items
+  bool valid = false;     // false after set_geometry / update_coords
 };
 
 struct Geometry {
@@ -60,6 +74,7 @@ struct Geometry {
   int *workLoad = nullptr;       // same, this rank's workload-balanced atoms (mulliken, forces)
   long long nWorkAll = 0, nWorkMine = 0, nWorkLoad = 0, nPairsMine = 0;
   bool hasDuplicates = false;    // two blocks of one atom fold onto the same dense block
+  int firstAtomMine = 0, lastAtomMine = -1;  // 0-based inclusive atom chunk of workMine
 };
 
 struct Staging {
@@ -100,6 +115,9 @@ struct dftbp_b200_ctx {
   std::string err;
   long long launches = 0;
   int smCount = 148;
+  size_t smemOptin = 232448;  // max dynamic shared memory per CTA
+  size_t smemPerSm = 233472;
+  int lMaxAll = 0;            // highest angular momentum of any species
 
   // orbitals
   int nSpecies = 0, mShell = 0, mOrb = 0;
@@ -118,6 +136,11 @@ struct dftbp_b200_ctx {
   double cutoff = 0.0;
 
   dftbp_b200::Geometry geo;
+  // lane-per-pair schedules (pair_sort.cu); buffers are grow-only and survive set_geometry
+  dftbp_b200::SortedPairs sortMine, sortLoad;  // of geo.workMine / geo.workLoad
+  int *sortKeys = nullptr;                     // scratch: bin of every work item
+  int *sortBins = nullptr;                     // scratch: histogram / cursors
+  long long sortKeysCap = 0, sortBinsCap = 0;
   std::vector<dftbp_b200::Staging> staging;
   std::vector<dftbp_b200::PendingCopy> pending;
   double *dSelfE = nullptr;  // (mOrb, nSpecies) on-site energy per orbital
@@ -292,8 +315,11 @@ struct ScopedTimer {
   }
 };
 
-// implemented in context.cu / solver.cu
+// implemented in context.cu / solver.cu / pair_sort.cu
 int syncPrograms(dftbp_b200_ctx *ctx);
+// (re)build the sorted pair schedule of workMine (forLoad = false) or workLoad (true) if stale
+int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out);
+void freeSortedPairs(dftbp_b200_ctx *ctx);
 void solverDestroy(dftbp_b200_ctx *ctx);
 
 }  // namespace dftbp_b200

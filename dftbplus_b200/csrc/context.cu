@@ -118,6 +118,8 @@ int dftbp_b200_create(dftbp_b200_ctx **out, int device, int rank, int nRanks) {
   cudaDeviceProp prop;
   DFTBP_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
   ctx->smCount = prop.multiProcessorCount;
+  ctx->smemOptin = prop.sharedMemPerBlockOptin;
+  ctx->smemPerSm = prop.sharedMemPerMultiprocessor;
   DFTBP_CUDA(ctx, cudaMalloc((void **)&ctx->dInfo, 4 * sizeof(int)));  // [0] info / nLevels, [2..3] tile counter
   return 0;
 }
@@ -126,6 +128,7 @@ int dftbp_b200_destroy(dftbp_b200_ctx *ctx) {
   if (!ctx) return 0;
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   freeGeometry(ctx->geo);
+  freeSortedPairs(ctx);
   for (void *p : ctx->tableAllocs) cudaFree(p);
   for (Staging &s : ctx->staging) cudaFree(s.ptr);
   cudaFree(ctx->dNOrbSpecies); cudaFree(ctx->dOrbShell); cudaFree(ctx->dProgs); cudaFree(ctx->dADesc);
@@ -213,12 +216,14 @@ int dftbp_b200_set_orbitals(dftbp_b200_ctx *ctx, int nSpecies, int mShell, const
   ctx->angShell.assign(angShell, angShell + (size_t)mShell * nSpecies);
   ctx->nOrbSpecies.assign(nSpecies, 0);
   ctx->mOrb = 0;
+  ctx->lMaxAll = 0;
   for (int sp = 0; sp < nSpecies; ++sp) {
     DFTBP_CHECK(ctx, nShell[sp] >= 1 && nShell[sp] <= mShell, "set_orbitals: nShell out of range");
     for (int sh = 0; sh < nShell[sp]; ++sh) {
       int l = angShell[sh + mShell * sp];
       DFTBP_CHECK(ctx, l >= 0 && l <= skg::kLMax, "set_orbitals: angular momentum must be 0..3");
       ctx->nOrbSpecies[sp] += 2 * l + 1;
+      ctx->lMaxAll = std::max(ctx->lMaxAll, l);
     }
     ctx->mOrb = std::max(ctx->mOrb, ctx->nOrbSpecies[sp]);
   }
@@ -279,6 +284,19 @@ int dftbp_b200_set_orbitals(dftbp_b200_ctx *ctx, int nSpecies, int mShell, const
       }
       pg.nInteg = ind;
       DFTBP_CHECK(ctx, ind <= kMaxInteg, "set_orbitals: too many integrals per species pair");
+      pg.nSh1 = nShell[sp1];
+      pg.nSh2 = nShell[sp2];
+      auto canon = [&](int sp) {
+        for (int sh = 0; sh < nShell[sp]; ++sh)
+          if (angShell[sh + mShell * sp] != sh) return -1;
+        return nShell[sp] - 1;
+      };
+      pg.canon1 = canon(sp1);
+      pg.canon2 = canon(sp2);
+      for (int sh = 0; sh < nShell[sp1]; ++sh)
+        pg.shells1 |= (unsigned long long)angShell[sh + mShell * sp1] << (4 * sh);
+      for (int sh = 0; sh < nShell[sp2]; ++sh)
+        pg.shells2 |= (unsigned long long)angShell[sh + mShell * sp2] << (4 * sh);
       pg.nY = (lmax1 + lmax2 + 1) * (lmax1 + lmax2 + 1);
       for (auto &v : perElem) {
         elemStart.push_back((int)terms.size());
@@ -394,6 +412,8 @@ int dftbp_b200_set_geometry(dftbp_b200_ctx *ctx, int nAtom, int nAllAtom, int mN
     g.workMine = g.workLoad = g.workAll;
     g.nWorkMine = g.nWorkLoad = g.nWorkAll;
     g.nPairsMine = g.nWorkAll - nAtom;
+    g.firstAtomMine = 0;
+    g.lastAtomMine = nAtom - 1;
   } else {
     int first, last;
     chunkRange(ctx->nRanks, ctx->rank, 1, nAtom, &first, &last);  // distributeRangeInChunks
@@ -412,8 +432,11 @@ int dftbp_b200_set_geometry(dftbp_b200_ctx *ctx, int nAtom, int nAllAtom, int mN
     g.nWorkMine = (long long)mine.size();
     g.nWorkLoad = (long long)load.size();
     g.nPairsMine = g.nWorkMine - std::max(0, last - first + 1);
+    g.firstAtomMine = first - 1;
+    g.lastAtomMine = last - 1;
   }
   ctx->geo = g;
+  ctx->sortMine.valid = ctx->sortLoad.valid = false;
   return 0;
 }
 
@@ -424,6 +447,7 @@ int dftbp_b200_update_coords(dftbp_b200_ctx *ctx, const double *coords) {
   DFTBP_CUDA(ctx, cudaMemcpyAsync(ctx->geo.coords, coords, sizeof(double) * 3 * ctx->geo.nAllAtom, kind,
                                   ctx->stream));
   if (kind == cudaMemcpyHostToDevice) DFTBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->sortMine.valid = ctx->sortLoad.valid = false;  // distance bins changed
   return 0;
 }
 

@@ -1,0 +1,222 @@
+// sk_lane_eval.cuh -- lane-per-pair evaluation of one diatomic H0 / S block.
+//
+// Replaces, for one neighbour pair, the body of buildDiatomicBlocks (dftb/nonscc.F90:406-421):
+// getSKIntegrals (dftb/slakoeqgrid.F90:183-244: 8-point polynomial on the equidistant grid, 5th
+// order tail) followed by rotateH0 (dftb/sk.F90:35-140).  Every THREAD owns one pair; the 32 pairs
+// of a warp share the ordered species pair (pair_sort.cu), so the shell loops of rotateH0 and the
+// dispatch on the shell-pair type are warp-uniform and the rotation is the generated straight-line
+// code of sk_gaunt_code.cuh (coefficients as immediates, harmonics in registers).  Compared with
+// the warp-per-pair evaluator (sk_eval.cuh) this removes the table-driven term loops whose
+// integer / branch overhead made K1 issue bound (profiles/r01_ncu_k1_warp_per_pair.txt).
+//
+// The interpolation is the Lagrange form of the polynomial the reference builds with Neville
+// (math/interpolation.F90:182-239): the eight weights depend on the distance only, so they are
+// formed once per pair and table and every integral is 8 loads + 8 FMAs.
+#pragma once
+#include <type_traits>
+
+#include "common.cuh"
+#include "sk_gaunt_code.cuh"
+
+namespace dftbp_b200 {
+
+struct LaneInterp {
+  double w[8];  // Lagrange weights of rows j0 .. j0+7          (mode 0)
+  double xr;    // rMax - r                                     (mode 1)
+  int j0;       // first row (0-based) of the window
+  int mode;     // 0 = polynomial, 1 = 5th order tail, 2 = beyond rMax -> 0
+};
+
+// SlakoEqGrid_interNew_, slakoeqgrid.F90:183-244, the part that depends on r only
+__device__ __forceinline__ void laneInterpSetup(const SkTableDev &t, double r, LaneInterp &li) {
+  li.j0 = 0;
+  li.xr = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) li.w[j] = 0.0;
+  if (r >= t.rMax) {
+    li.mode = 2;
+    return;
+  }
+  const int ind = (int)floor(r / t.dist);
+  if (ind < t.nGrid) {
+    li.mode = 0;
+    int iLast = min(t.nGrid, ind + 4);
+    iLast = max(iLast, 8);
+    const int j0 = iLast - 8;  // row j sits at (j+1)*dist
+    li.j0 = j0;
+    const double u = (r - (double)(j0 + 1) * t.dist) * t.invDist;
+    const double d0 = u, d1 = u - 1.0, d2 = u - 2.0, d3 = u - 3.0, d4 = u - 4.0, d5 = u - 5.0,
+                 d6 = u - 6.0, d7 = u - 7.0;
+    const double p1 = d0, p2 = p1 * d1, p3 = p2 * d2, p4 = p3 * d3, p5 = p4 * d4, p6 = p5 * d5,
+                 p7 = p6 * d6;
+    const double s6 = d7, s5 = s6 * d6, s4 = s5 * d5, s3 = s4 * d4, s2 = s3 * d3, s1 = s2 * d2,
+                 s0 = s1 * d1;
+    li.w[0] = (-1.0 / 5040.0) * s0;
+    li.w[1] = (1.0 / 720.0) * (p1 * s1);
+    li.w[2] = (-1.0 / 240.0) * (p2 * s2);
+    li.w[3] = (1.0 / 144.0) * (p3 * s3);
+    li.w[4] = (-1.0 / 144.0) * (p4 * s4);
+    li.w[5] = (1.0 / 240.0) * (p5 * s5);
+    li.w[6] = (-1.0 / 720.0) * (p6 * s6);
+    li.w[7] = (1.0 / 5040.0) * p7;
+  } else {
+    li.mode = 1;
+    li.xr = -(r - t.rMax);
+  }
+}
+
+// value of integral column `col` (uniform across the warp)
+__device__ __forceinline__ double laneInterp(const SkTableDev &t, const LaneInterp &li, int col) {
+  if (li.mode == 0) {
+    const double *__restrict__ y = t.tab + (size_t)col * t.nGrid + li.j0;
+    double acc = li.w[0] * __ldg(y);
+#pragma unroll
+    for (int j = 1; j < 8; ++j) acc = fma(li.w[j], __ldg(y + j), acc);
+    return acc;
+  }
+  if (li.mode == 1) {
+    // poly5ToZero (math/interpolation.F90:31-67) with dx = -1, invdx = -1; y1, y1', y1'' prepared
+    // on the host in the reference's operation order (context.cu: tailCoefficients)
+    const double y1 = __ldg(t.tail + 3 * col), y1p = __ldg(t.tail + 3 * col + 1),
+                 y1pp = __ldg(t.tail + 3 * col + 2);
+    const double dx1 = -y1p, dx2 = y1pp;
+    const double dd = 10.0 * y1 - 4.0 * dx1 + 0.5 * dx2;
+    const double ee = -15.0 * y1 + 7.0 * dx1 - dx2;
+    const double ff = 6.0 * y1 - 3.0 * dx1 + 0.5 * dx2;
+    const double xr = li.xr;
+    return ((ff * xr + ee) * xr + dd) * xr * xr * xr;
+  }
+  return 0.0;
+}
+
+// all NI integrals of one table at once: the mode branch is taken once, the 8*NI loads of the common
+// polynomial branch are independent and get issued back to back
+template <int NI>
+__device__ __forceinline__ void laneInterpAll(const SkTableDev &t, const LaneInterp &li, double (&v)[NI]) {
+  if (li.mode == 0) {
+    const double *__restrict__ y = t.tab + li.j0;
+    const size_t nGrid = (size_t)t.nGrid;
+#pragma unroll
+    for (int c = 0; c < NI; ++c) {
+      const double *__restrict__ yc = y + c * nGrid;
+      double acc = li.w[0] * __ldg(yc);
+#pragma unroll
+      for (int j = 1; j < 8; ++j) acc = fma(li.w[j], __ldg(yc + j), acc);
+      v[c] = acc;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < NI; ++c) v[c] = laneInterp(t, li, c);
+  }
+}
+
+// Evaluate the block of the (warp-uniform) species-pair program pg for this lane's pair at
+// distance r along the unit vector (dx, dy, dz).  emit(row, col, h, s) is called once per element
+// of the nOrb2 x nOrb1 block in shell-pair order (atom-1 shells outer, like rotateH0);
+// endGroup(firstCol, nCols) after the last row of every atom-1 shell, i.e. when the columns
+// firstCol .. firstCol+nCols-1 of the block are complete.
+template <bool DO_H, bool DO_S, int LMAX, class Emit, class EndGroup>
+__device__ __forceinline__ void skLaneEval(const SpPairProg &pg, double r, double dx, double dy, double dz,
+                                           Emit &&emit, EndGroup &&endGroup) {
+  LaneInterp liH, liS;
+  if (DO_H) laneInterpSetup(pg.H, r, liH);
+  if (DO_S) laneInterpSetup(pg.S, r, liS);
+  double Y[(2 * LMAX + 1) * (2 * LMAX + 1)];
+  skg::harmonics<2 * LMAX>(dx, dy, dz, Y);
+  int ind = 0, iCol = 0;
+  const int nSh1 = pg.nSh1, nSh2 = pg.nSh2;
+  const unsigned long long sh1s = pg.shells1, sh2s = pg.shells2;
+  for (int sh1 = 0; sh1 < nSh1; ++sh1) {
+    const int l1 = (int)((sh1s >> (4 * sh1)) & 0xF);
+    int iRow = 0;
+    for (int sh2 = 0; sh2 < nSh2; ++sh2) {
+      const int l2 = (int)((sh2s >> (4 * sh2)) & 0xF);
+      const int lmin = min(l1, l2);
+      double vH[4], vS[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        vH[k] = 0.0;
+        vS[k] = 0.0;
+        if (k <= LMAX && k <= lmin) {
+          if (DO_H) vH[k] = laneInterp(pg.H, liH, ind + k);
+          if (DO_S) vS[k] = laneInterp(pg.S, liS, ind + k);
+        }
+      }
+      skg::blockDispatch<DO_H, DO_S, LMAX>(l1, l2, Y, vH, vS, [&](int a, int b, double h, double s) {
+        emit(iRow + b, iCol + a, h, s);
+      });
+      ind += lmin + 1;
+      iRow += 2 * l2 + 1;
+    }
+    endGroup(iCol, 2 * l1 + 1);
+    iCol += 2 * l1 + 1;
+  }
+}
+
+// ---- canonical species pairs: shells 0..LM1 on the atom, 0..LM2 on the neighbour (s, sp, spd, spdf) ---
+// Everything about the shell structure is a compile-time constant, so the loops of rotateH0 unroll
+// completely: the integrals live in registers with static indices, the element offsets become
+// immediates, and phase A (all table loads of the pair, issued back to back -> one memory round
+// trip) is separated from phase B (pure FP64 + stores), which is what keeps the staging rows of
+// the callers short-lived.
+
+template <int N, class F>
+__device__ __forceinline__ void staticFor(F &&f) {
+  if constexpr (N > 0) {
+    staticFor<N - 1>(f);
+    f(std::integral_constant<int, N - 1>{});
+  }
+}
+
+__host__ __device__ constexpr int canonMin(int a, int b) { return a < b ? a : b; }
+// first integral of shell pair (l1, l2) when the neighbour has shells 0..LM2 (getFullTable order,
+// dftbplus/parser.F90:4096-4127: atom-1 shells outer)
+__host__ __device__ constexpr int canonIntegStart(int l1, int l2, int LM2) {
+  int n = 0;
+  for (int a = 0; a < l1; ++a)
+    for (int b = 0; b <= LM2; ++b) n += canonMin(a, b) + 1;
+  for (int b = 0; b < l2; ++b) n += canonMin(l1, b) + 1;
+  return n;
+}
+
+template <bool DO_H, bool DO_S, int LM1, int LM2, class Emit>
+__device__ __forceinline__ void skLaneEvalCanon(const SpPairProg &pg, double r, double dx, double dy, double dz,
+                                                Emit &&emit) {
+  constexpr int NI = canonIntegStart(LM1 + 1, 0, LM2);
+  constexpr int LY = LM1 + LM2;
+  constexpr int N2 = (LM2 + 1) * (LM2 + 1);
+  double vH[NI], vS[NI];
+  // phase A: every integral of the pair
+  if (DO_H) {
+    LaneInterp li;
+    laneInterpSetup(pg.H, r, li);
+    laneInterpAll<NI>(pg.H, li, vH);
+  }
+  if (DO_S) {
+    LaneInterp li;
+    laneInterpSetup(pg.S, r, li);
+    laneInterpAll<NI>(pg.S, li, vS);
+  }
+  double Y[(LY + 1) * (LY + 1)];
+  skg::harmonics<LY>(dx, dy, dz, Y);
+  // phase B: rotation, shell pair by shell pair
+  staticFor<LM1 + 1>([&](auto l1c) {
+    constexpr int l1 = decltype(l1c)::value;
+    staticFor<LM2 + 1>([&](auto l2c) {
+      constexpr int l2 = decltype(l2c)::value;
+      constexpr int lmin = canonMin(l1, l2);
+      constexpr int ind = canonIntegStart(l1, l2, LM2);
+      double h4[4] = {0.0, 0.0, 0.0, 0.0}, s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k <= lmin; ++k) {
+        if (DO_H) h4[k] = vH[ind + k];
+        if (DO_S) s4[k] = vS[ind + k];
+      }
+      skg::blockT<l1, l2, DO_H, DO_S>(Y, h4, s4, [&](int a, int b, double h, double s) {
+        emit(l2 * l2 + b + N2 * (l1 * l1 + a), h, s);  // e = (iRow + b) + nOrb2 * (iCol + a)
+      });
+    });
+  });
+}
+
+}  // namespace dftbp_b200

@@ -205,8 +205,147 @@ def emit(tables):
     return len(terms_all)
 
 
+OUT_CODE = os.path.join(HERE, "..", "dftbplus_b200", "csrc", "sk_gaunt_code.cuh")
+
+
+def emit_code(tables):
+    """Straight-line device code for the lane-per-pair kernels (K1/K5 v2): every thread owns one
+    neighbour pair, all 32 lanes of a warp run the same shell-pair type, so the Gaunt sums are
+    emitted as unrolled FMAs with the coefficients as immediates -- no tables, no branches."""
+    L = []
+    ap = L.append
+    pool = []
+    pool_index = {}
+
+    def C(v):
+        """reference to a coefficient in the __constant__ pool: DFMA / DMUL take constant-bank
+        operands directly, whereas a 64-bit immediate costs two UMOVs per use"""
+        key = float(v).hex()
+        if key not in pool_index:
+            pool_index[key] = len(pool)
+            pool.append(float(v))
+        return "skgC[%d]" % pool_index[key]
+
+    ap("// GENERATED by tools/gen_sk_gaunt.py (emit_code) -- do not edit.")
+    ap("// Straight-line Slater-Koster rotation: harmonics of the bond direction and one function per")
+    ap("// ordered shell-pair type (l1 = shell of the atom, l2 = shell of the neighbour).")
+    ap("// emit(a, b, h, s): a = m1 index (column inside the shell of atom 1), b = m2 index (row).")
+    ap("#pragma once")
+    ap("namespace dftbp_b200 { namespace skg {")
+    # ---- harmonics
+    ap("template <int LY>")
+    ap("__device__ __forceinline__ void harmonics(double x, double y, double z, double (&Y)[(LY + 1) * (LY + 1)]) {")
+    ap("  const double z2 = z * z;")
+    ap("  const double c1 = x, s1 = y;")
+    for m in range(2, LY + 1):
+        ap("  [[maybe_unused]] const double c%d = c%d * x - s%d * y, s%d = c%d * y + s%d * x;" % (m, m - 1, m - 1, m, m - 1, m - 1))
+    ap("  Y[0] = 1.0;")
+    for Lq in range(1, LY + 1):
+        ap("  if constexpr (LY >= %d) {" % Lq)
+        for m in range(0, Lq + 1):
+            c = legendre_deriv_coeffs(Lq, m)
+            par = (Lq - m) & 1
+            ev = list(c[par::2])
+            # Horner in z2
+            expr = "%.17e" % ev[-1]
+            for ck in reversed(ev[:-1]):
+                expr = "fma(z2, %s, %.17e)" % (expr, ck)
+            if par:
+                expr = "(%s) * z" % expr
+            if m == 0:
+                ap("    Y[%d] = %s;" % (Lq * Lq + Lq, expr))
+            else:
+                ap("    { const double p = %s; Y[%d] = p * c%d; Y[%d] = p * s%d; }" %
+                   (expr, Lq * Lq + Lq + m, m, Lq * Lq + Lq - m, m))
+        ap("  }")
+    ap("}")
+    # ---- shell-pair blocks
+    for l1 in range(LMAX + 1):
+        for l2 in range(LMAX + 1):
+            Ls, G, T = tables[(l1, l2)]
+            lmin = min(l1, l2)
+            nk = lmin + 1
+            ap("// (l1, l2) = (%d, %d): L = %s" % (l1, l2, Ls))
+            ap("template <bool DO_H, bool DO_S, int NY, class Emit>")
+            ap("__device__ __forceinline__ void block_%d_%d(const double (&Y)[NY], const double (&vH)[4], const double (&vS)[4], Emit &&emit) {" % (l1, l2))
+            ap("  static_assert(NY >= %d, \"harmonics up to L = %d needed\");" % ((l1 + l2 + 1) ** 2, l1 + l2))
+            for which in ("H", "S"):
+                for k in range(nk):
+                    terms = []
+                    for mu in range(nk):
+                        if T[k, mu] != 0.0:
+                            terms.append("%s * v%s[%d]" % (C(T[k, mu]), which, mu))
+                    expr = terms[0]
+                    for t in terms[1:]:
+                        c, v = t.split(" * ")
+                        expr = "fma(%s, %s, %s)" % (c, v, expr)
+                    ap("  [[maybe_unused]] const double a%s%d = DO_%s ? %s : 0.0;" % (which, k, which, expr))
+            for a in range(2 * l1 + 1):
+                for b in range(2 * l2 + 1):
+                    ap("  {")
+                    used = []
+                    for k, Lq in enumerate(Ls):
+                        terms = [(G[k][a, b, M + Lq], Lq * Lq + Lq + M) for M in range(-Lq, Lq + 1)
+                                 if G[k][a, b, M + Lq] != 0.0]
+                        if not terms:
+                            continue
+                        expr = "%s * Y[%d]" % (C(terms[0][0]), terms[0][1])
+                        for g, yi in terms[1:]:
+                            expr = "fma(%s, Y[%d], %s)" % (C(g), yi, expr)
+                        ap("    const double t%d = %s;" % (k, expr))
+                        used.append(k)
+                    if used:
+                        for which in ("H", "S"):
+                            expr = "a%s%d * t%d" % (which, used[0], used[0])
+                            for k in used[1:]:
+                                expr = "fma(a%s%d, t%d, %s)" % (which, k, k, expr)
+                            ap("    const double %s = DO_%s ? %s : 0.0;" % (which.lower(), which, expr))
+                        ap("    emit(%d, %d, h, s);" % (a, b))
+                    else:
+                        ap("    emit(%d, %d, 0.0, 0.0);" % (a, b))
+                    ap("  }")
+            ap("}")
+    # ---- dispatch
+    ap("// Uniform (per warp) dispatch on the shell-pair type; LMAX = highest l of any species.")
+    ap("template <bool DO_H, bool DO_S, int LMAX, class Emit>")
+    ap("__device__ __forceinline__ void blockDispatch(int l1, int l2, const double (&Y)[(2 * LMAX + 1) * (2 * LMAX + 1)],")
+    ap("                                              const double (&vH)[4], const double (&vS)[4], Emit &&emit) {")
+    ap("  switch (l1 * 4 + l2) {")
+    for l1 in range(LMAX + 1):
+        for l2 in range(LMAX + 1):
+            ap("    case %d: if constexpr (LMAX >= %d) block_%d_%d<DO_H, DO_S>(Y, vH, vS, emit); break;" %
+               (l1 * 4 + l2, max(l1, l2), l1, l2))
+    ap("    default: break;")
+    ap("  }")
+    ap("}")
+    ap("// compile-time dispatch (canonical s/sp/spd/spdf species: the shell loops unroll completely)")
+    ap("template <int L1, int L2, bool DO_H, bool DO_S, int NY, class Emit>")
+    ap("__device__ __forceinline__ void blockT(const double (&Y)[NY], const double (&vH)[4], const double (&vS)[4], Emit &&emit) {")
+    first = True
+    for l1 in range(LMAX + 1):
+        for l2 in range(LMAX + 1):
+            ap("  %sif constexpr (L1 == %d && L2 == %d) block_%d_%d<DO_H, DO_S>(Y, vH, vS, emit);" %
+               ("" if first else "else ", l1, l2, l1, l2))
+            first = False
+    ap("}")
+    ap("}}  // namespace")
+    # the pool goes in front of the first use
+    at = L.index("namespace dftbp_b200 { namespace skg {") + 1
+    decl = ["// coefficient pool (Gaunt coefficients and V -> A_L maps)",
+            "static __constant__ double skgC[%d] = {" % len(pool)]
+    for i in range(0, len(pool), 4):
+        decl.append("  " + ", ".join("%.17e" % v for v in pool[i:i + 4]) + ",")
+    decl.append("};")
+    L[at:at] = decl
+    with open(OUT_CODE, "w") as fh:
+        fh.write("\n".join(L) + "\n")
+    return len(L)
+
+
 if __name__ == "__main__":
     tb = build()
     err = self_check(tb)
     n = emit(tb)
+    nl = emit_code(tb)
+    print("straight-line code: %d lines -> %s" % (nl, os.path.normpath(OUT_CODE)))
     print("self-check max err %.2e; %d Gaunt terms -> %s" % (err, n, os.path.normpath(OUT)))
