@@ -35,88 +35,101 @@ struct K1Params {
   double *over;
 };
 
-// TMA bulk copy shared -> global (cp.async.bulk, SASS UBLKCP): both addresses 16-byte aligned,
-// size a multiple of 16.
-__device__ __forceinline__ void bulkStore(double *gdst, const double *ssrc, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
-               : "memory");
-}
-
-// Stage row of one lane and one matrix: element e of the block lives at row[e + par], par = the
-// parity (in doubles) of the block's global address, so that shared and global element addresses
-// agree modulo 16 and the 16-byte aligned interior of the block can leave as ONE bulk copy; the
-// at most one leading and one trailing element go out as plain stores.
-__device__ __forceinline__ void flushRow(double *gdst, const double *row, int par, int nElem) {
-  const int nBulk = (nElem - par) & ~1;
-  if (nBulk > 0) bulkStore(gdst + par, row + 2 * par, 8u * (unsigned)nBulk);
-  if (par) gdst[0] = row[1];
-  if (par + nBulk < nElem) gdst[nElem - 1] = row[nElem - 1 + par];
-}
-
-template <int LMAX, bool DO_H, bool DO_S>
-__global__ void __launch_bounds__(256) k1_pair_build(const K1Params p) {
-  extern __shared__ __align__(16) double smem[];
+// One work item = (chunk of 32 sorted pairs, matrix): H0 and S of a chunk are separate items; the
+// kernel is latency bound, not FP64 bound, so the harmonics recomputed for the second matrix are
+// free, while the smaller register and shared-memory footprint doubles the resident warps.
+//
+// Write-out, one atom-1 shell ("column group") at a time: the (2 l1 + 1) * nOrb2 elements of a group
+// are contiguous in the column-major block.  Lane q stages its group in row q of the warp's
+// [32][pitch] tile (odd pitch: the lanes' writes of one element hit 32 different banks); then the
+// warp streams the 32 runs out with consecutive lanes on consecutive elements -- flat index
+// idx = lane + 32 k over the 32 * count staged elements, (row, element) = (idx / count, idx % count)
+// by a multiply-shift -- so all 32 lanes store in every step and every store instruction covers at
+// most two contiguous runs of the sparse array.  (A TMA bulk copy per block was tried: UBLKCP takes
+// uniform-register operands, so the 32 copies of a warp serialise in a vote loop -- slower.)
+//
+// The index loads of an item (schedule entry -> iNeighbour / iPair -> coordinates, species) are a
+// chain of dependent global loads; they are software-pipelined two items ahead.
+template <int LMAX>
+__global__ void __launch_bounds__(256, 2) k1_pair_build(const K1Params p) {
+  extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wIn = threadIdx.x >> 5, nW = blockDim.x >> 5;
-  // this lane's staging rows: H at rowH, S at rowS (each 16-byte aligned, p.pitch doubles apart)
-  double *rowH = smem + ((size_t)wIn * 32 + lane) * ((DO_H && DO_S) ? 2 : 1) * p.pitch;
-  double *rowS = rowH + ((DO_H && DO_S) ? p.pitch : 0);
+  double *stage = smem + (size_t)wIn * 32 * p.pitch;
+  double *row = stage + (size_t)lane * p.pitch;
   const int nChunks = __ldg(p.total) >> 5;
-  for (int chunk = blockIdx.x * nW + wIn; chunk < nChunks; chunk += gridDim.x * nW) {
-    int flat = __ldg(p.items + 32 * chunk + lane);
-    const bool valid = flat >= 0;
-    const int flat0 = __shfl_sync(0xffffffffu, flat, 0);  // lane 0 of a chunk is never padding
-    if (!valid) flat = flat0;
-    const int iAt1 = flat / p.ld;
-    const int iAt2 = __ldg(p.iNeighbour + flat) - 1;
-    const int sp1 = __shfl_sync(0xffffffffu, __ldg(p.species + iAt1), 0) - 1;
-    const int sp2 = __shfl_sync(0xffffffffu, __ldg(p.species + iAt2), 0) - 1;
-    const int ind = __ldg(p.iPair + flat);
-    const SpPairProg pg = p.progs[sp1 + p.nSpecies * sp2];
-    const int n2 = pg.nOrb2, nElem = pg.nOrb1 * n2;
-    double *gH = DO_H ? p.ham + ind : nullptr;
-    double *gS = DO_S ? p.over + ind : nullptr;
-    const int parH = (int)((reinterpret_cast<size_t>(gH) >> 3) & 1);
-    const int parS = (int)((reinterpret_cast<size_t>(gS) >> 3) & 1);
+  const int nMat = (p.ham && p.over) ? 2 : 1;
+  const int nItems = nChunks * nMat;
+  const int stride = gridDim.x * nW;
+  auto loadFlat = [&](int it) -> int {
+    if (it >= nItems) return -1;
+    int f = __ldg(p.items + 32 * (nMat == 2 ? it >> 1 : it) + lane);
+    const int f0 = __shfl_sync(0xffffffffu, f, 0);  // lane 0 of a chunk is never padding
+    return f >= 0 ? f : -2 - f0;                    // padding lanes shadow lane 0's pair: encoded < -1
+  };
+  auto flatOf = [](int f) { return f >= 0 ? f : -2 - f; };
+  int item = blockIdx.x * nW + wIn;
+  // pipeline registers: C = current item, N = next, NN = the one after
+  int fC = loadFlat(item), fN = loadFlat(item + stride);
+  int indC = 0;
+  double c1x = 0, c1y = 0, c1z = 0, c2x = 0, c2y = 0, c2z = 0;
+  int s1C = 1, s2C = 1;
+  if (fC != -1) {
+    const int f = flatOf(fC), iAt1 = f / p.ld;
+    const int iAt2 = __ldg(p.iNeighbour + f) - 1;
+    indC = __ldg(p.iPair + f);
+    c1x = __ldg(p.coords + 3 * iAt1); c1y = __ldg(p.coords + 3 * iAt1 + 1); c1z = __ldg(p.coords + 3 * iAt1 + 2);
+    c2x = __ldg(p.coords + 3 * iAt2); c2y = __ldg(p.coords + 3 * iAt2 + 1); c2z = __ldg(p.coords + 3 * iAt2 + 2);
+    s1C = __ldg(p.species + iAt1);
+    s2C = __ldg(p.species + iAt2);
+  }
+  for (; item < nItems; item += stride) {
+    // stage 1 of item + 2 strides, stage 2 of item + stride
+    const int fNN = loadFlat(item + 2 * stride);
+    int iAt2N = 0, indN = 0, iAt1N = 0;
+    if (fN != -1) {
+      const int f = flatOf(fN);
+      iAt1N = f / p.ld;
+      iAt2N = __ldg(p.iNeighbour + f) - 1;
+      indN = __ldg(p.iPair + f);
+    }
+    // ---- current item
+    const bool isS = nMat == 2 ? (item & 1) : (p.ham == nullptr);
+    const bool valid = fC >= 0;
+    const int sp1 = __shfl_sync(0xffffffffu, s1C, 0) - 1, sp2 = __shfl_sync(0xffffffffu, s2C, 0) - 1;
+    const SpPairProg &pg = p.progs[sp1 + p.nSpecies * sp2];
+    const SkTableDev tab = isS ? pg.S : pg.H;
+    const int nElem = pg.nOrb1 * pg.nOrb2;
+    double *__restrict__ outBase = isS ? p.over : p.ham;
     // vect = coords(:,iAt2) - coords(:,iAt1); dist = sqrt(sum(vect**2)); vect = vect/dist
-    const double vx = __ldg(p.coords + 3 * iAt2) - __ldg(p.coords + 3 * iAt1);
-    const double vy = __ldg(p.coords + 3 * iAt2 + 1) - __ldg(p.coords + 3 * iAt1 + 1);
-    const double vz = __ldg(p.coords + 3 * iAt2 + 2) - __ldg(p.coords + 3 * iAt1 + 2);
+    const double vx = c2x - c1x, vy = c2y - c1y, vz = c2z - c1z;
     const double dist = sqrt(vx * vx + vy * vy + vz * vz);
     const double rinv = 1.0 / dist;
-    // the previous chunk's bulk copies must have read their rows before they are overwritten
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    double *wH = rowH + parH, *wS = rowS + parS;
-    const double ux = vx * rinv, uy = vy * rinv, uz = vz * rinv;
-    auto put = [&](int e, double h, double s) {
-      if (DO_H) wH[e] = h;
-      if (DO_S) wS[e] = s;
-    };
-    // canonical species pairs (s / sp / spd): fully unrolled evaluator; anything else: generic loops
-    const int canon = (pg.canon1 >= 0 && pg.canon2 >= 0 && pg.canon1 <= 2 && pg.canon2 <= 2)
-                          ? pg.canon1 * 3 + pg.canon2 : -1;
-    switch (canon) {
-      case 0: skLaneEvalCanon<DO_H, DO_S, 0, 0>(pg, dist, ux, uy, uz, put); break;
-      case 1: if constexpr (LMAX >= 1) skLaneEvalCanon<DO_H, DO_S, 0, 1>(pg, dist, ux, uy, uz, put); break;
-      case 2: if constexpr (LMAX >= 2) skLaneEvalCanon<DO_H, DO_S, 0, 2>(pg, dist, ux, uy, uz, put); break;
-      case 3: if constexpr (LMAX >= 1) skLaneEvalCanon<DO_H, DO_S, 1, 0>(pg, dist, ux, uy, uz, put); break;
-      case 4: if constexpr (LMAX >= 1) skLaneEvalCanon<DO_H, DO_S, 1, 1>(pg, dist, ux, uy, uz, put); break;
-      case 5: if constexpr (LMAX >= 2) skLaneEvalCanon<DO_H, DO_S, 1, 2>(pg, dist, ux, uy, uz, put); break;
-      case 6: if constexpr (LMAX >= 2) skLaneEvalCanon<DO_H, DO_S, 2, 0>(pg, dist, ux, uy, uz, put); break;
-      case 7: if constexpr (LMAX >= 2) skLaneEvalCanon<DO_H, DO_S, 2, 1>(pg, dist, ux, uy, uz, put); break;
-      case 8: if constexpr (LMAX >= 2) skLaneEvalCanon<DO_H, DO_S, 2, 2>(pg, dist, ux, uy, uz, put); break;
-      default:
-        skLaneEval<DO_H, DO_S, LMAX>(
-            pg, dist, ux, uy, uz, [&](int row, int col, double h, double s) { put(row + n2 * col, h, s); },
-            [](int, int) {});
+    const int desc = valid ? indC : -1;
+    skLaneEvalAny<LMAX>(
+        pg, tab, dist, vx * rinv, vy * rinv, vz * rinv, [&](int e, double v) { row[e] = v; },
+        [&](int first, int count) {
+          __syncwarp();
+          const unsigned M = (1048576u + (unsigned)count - 1u) / (unsigned)count;  // idx / count = idx * M >> 20
+          double *__restrict__ dst = outBase + first;
+#pragma unroll 4
+          for (int k = 0; k < count; ++k) {
+            const unsigned idx = (unsigned)(lane + 32 * k);
+            const unsigned q = (idx * M) >> 20;
+            const unsigned e = idx - q * (unsigned)count;
+            const int base = __shfl_sync(0xffffffffu, desc, (int)q);
+            const double v = stage[q * p.pitch + e];
+            if (base >= 0) dst[base + e] = v;
+          }
+          __syncwarp();
+        });
+    // stage 3 of item + stride, then rotate the pipeline
+    if (fN != -1) {
+      c1x = __ldg(p.coords + 3 * iAt1N); c1y = __ldg(p.coords + 3 * iAt1N + 1); c1z = __ldg(p.coords + 3 * iAt1N + 2);
+      c2x = __ldg(p.coords + 3 * iAt2N); c2y = __ldg(p.coords + 3 * iAt2N + 1); c2z = __ldg(p.coords + 3 * iAt2N + 2);
+      s1C = __ldg(p.species + iAt1N);
+      s2C = __ldg(p.species + iAt2N);
     }
-    // generic-proxy writes of this thread -> visible to the async proxy, then one bulk copy per matrix
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (valid) {
-      if (DO_H) flushRow(gH, rowH, parH, nElem);
-      if (DO_S) flushRow(gS, rowS, parS, nElem);
-    }
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    fC = fN; fN = fNN; indC = indN;
   }
   // on-site blocks
   for (int iAt = p.firstAtom + blockIdx.x * nW + wIn; iAt <= p.lastAtom; iAt += gridDim.x * nW) {
@@ -125,11 +138,10 @@ __global__ void __launch_bounds__(256) k1_pair_build(const K1Params p) {
     const int ind = __ldg(p.iPair + (size_t)p.ld * iAt);
     for (int e = lane; e < nElem; e += 32) {
       const int a = e / n, b = e - a * n;
-      if (DO_H) p.ham[ind + e] = (a == b) ? __ldg(p.selfE + a + p.mOrb * sp) : 0.0;
-      if (DO_S) p.over[ind + e] = (a == b) ? 1.0 : 0.0;
+      if (p.ham) p.ham[ind + e] = (a == b) ? __ldg(p.selfE + a + p.mOrb * sp) : 0.0;
+      if (p.over) p.over[ind + e] = (a == b) ? 1.0 : 0.0;
     }
   }
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // selfegy(mShell, nSpecies) -> per-orbital on-site energies (mOrb, nSpecies)
@@ -142,15 +154,11 @@ __global__ void k1_expand_selfegy(const double *selfegy, const int *orbShell, co
 }
 
 template <int LMAX>
-int launchTyped(dftbp_b200_ctx *ctx, const K1Params &p, int grid, int warps, size_t smemBytes, bool h, bool s) {
-  auto go = [&](auto kern) -> int {
-    DFTBP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-    kern<<<grid, 32 * warps, smemBytes, ctx->stream>>>(p);
-    return 0;
-  };
-  if (h && s) return go(k1_pair_build<LMAX, true, true>);
-  if (h) return go(k1_pair_build<LMAX, true, false>);
-  return go(k1_pair_build<LMAX, false, true>);
+int launchTyped(dftbp_b200_ctx *ctx, const K1Params &p, int grid, int warps, size_t smemBytes) {
+  DFTBP_CUDA(ctx, cudaFuncSetAttribute(k1_pair_build<LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smemBytes));
+  k1_pair_build<LMAX><<<grid, 32 * warps, smemBytes, ctx->stream>>>(p);
+  return 0;
 }
 
 int launchBuild(dftbp_b200_ctx *ctx, const double *selfegy, double *ham, double *over) {
@@ -185,22 +193,21 @@ int launchBuild(dftbp_b200_ctx *ctx, const double *selfegy, double *ham, double 
   }
   if (g.nWorkMine > 0) {
     ScopedTimer timer(ctx, kTimerSparseH0S);
-    // staging rows: per lane and matrix mOrb^2 elements + 1 (parity shift), 16-byte aligned rows whose
-    // stride in 16-byte units is odd (spreads the lanes' same-element writes over the banks)
-    p.pitch = (ctx->mOrb * ctx->mOrb + 2) & ~1;
-    if (((p.pitch >> 1) & 1) == 0) p.pitch += 2;
-    const size_t perWarp = sizeof(double) * 32 * (size_t)p.pitch * ((ham && over) ? 2 : 1);
-    int warps = (int)std::min<size_t>(8, ctx->smemOptin / perWarp);
+    // staging row per lane: the largest column group, (2 lmax + 1) * mOrb elements, odd pitch
+    p.pitch = ((2 * ctx->lMaxAll + 1) * ctx->mOrb) | 1;
+    const size_t perWarp = sizeof(double) * 32 * (size_t)p.pitch;
+    // 8 warps per CTA, 2 CTAs per SM: 16 warps x 128 registers fill the register file
+    int warps = (int)std::min<size_t>(8, (ctx->smemOptin - 2048) / perWarp);
     DFTBP_CHECK(ctx, warps >= 1, "build: staging tile does not fit into shared memory");
     const size_t smemBytes = perWarp * warps;
-    const int ctasPerSm = std::max<int>(1, (int)std::min<size_t>(ctx->smemPerSm / (smemBytes + 1024), 2048 / (32 * warps)));
-    const long long chunks = (g.nWorkMine + 31) / 32 + ctx->nSpecies * ctx->nSpecies;
-    const int grid = (int)std::max<long long>(1, std::min<long long>((chunks + warps - 1) / warps,
+    const int ctasPerSm = std::max<int>(1, (int)std::min<size_t>(ctx->smemPerSm / (smemBytes + 1024), 2));
+    const long long items = ((g.nWorkMine + 31) / 32 + ctx->nSpecies * ctx->nSpecies) * ((ham && over) ? 2 : 1);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((items + warps - 1) / warps,
                                                                      (long long)ctx->smCount * ctasPerSm));
     int rc;
-    if (ctx->lMaxAll <= 1) rc = launchTyped<1>(ctx, p, grid, warps, smemBytes, ham != nullptr, over != nullptr);
-    else if (ctx->lMaxAll == 2) rc = launchTyped<2>(ctx, p, grid, warps, smemBytes, ham != nullptr, over != nullptr);
-    else rc = launchTyped<3>(ctx, p, grid, warps, smemBytes, ham != nullptr, over != nullptr);
+    if (ctx->lMaxAll <= 1) rc = launchTyped<1>(ctx, p, grid, warps, smemBytes);
+    else if (ctx->lMaxAll == 2) rc = launchTyped<2>(ctx, p, grid, warps, smemBytes);
+    else rc = launchTyped<3>(ctx, p, grid, warps, smemBytes);
     if (rc) return rc;
     ctx->launches++;
   }

@@ -89,42 +89,22 @@ __device__ __forceinline__ double laneInterp(const SkTableDev &t, const LaneInte
   return 0.0;
 }
 
-// all NI integrals of one table at once: the mode branch is taken once, the 8*NI loads of the common
-// polynomial branch are independent and get issued back to back
-template <int NI>
-__device__ __forceinline__ void laneInterpAll(const SkTableDev &t, const LaneInterp &li, double (&v)[NI]) {
-  if (li.mode == 0) {
-    const double *__restrict__ y = t.tab + li.j0;
-    const size_t nGrid = (size_t)t.nGrid;
-#pragma unroll
-    for (int c = 0; c < NI; ++c) {
-      const double *__restrict__ yc = y + c * nGrid;
-      double acc = li.w[0] * __ldg(yc);
-#pragma unroll
-      for (int j = 1; j < 8; ++j) acc = fma(li.w[j], __ldg(yc + j), acc);
-      v[c] = acc;
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < NI; ++c) v[c] = laneInterp(t, li, c);
-  }
-}
-
-// Evaluate the block of the (warp-uniform) species-pair program pg for this lane's pair at
-// distance r along the unit vector (dx, dy, dz).  emit(row, col, h, s) is called once per element
-// of the nOrb2 x nOrb1 block in shell-pair order (atom-1 shells outer, like rotateH0);
-// endGroup(firstCol, nCols) after the last row of every atom-1 shell, i.e. when the columns
-// firstCol .. firstCol+nCols-1 of the block are complete.
-template <bool DO_H, bool DO_S, int LMAX, class Emit, class EndGroup>
-__device__ __forceinline__ void skLaneEval(const SpPairProg &pg, double r, double dx, double dy, double dz,
-                                           Emit &&emit, EndGroup &&endGroup) {
-  LaneInterp liH, liS;
-  if (DO_H) laneInterpSetup(pg.H, r, liH);
-  if (DO_S) laneInterpSetup(pg.S, r, liS);
+// Evaluate one matrix (table t = the H or the S table of the warp-uniform species-pair program pg)
+// of this lane's pair at distance r along the unit vector (dx, dy, dz), one atom-1 shell ("column
+// group") after the other, like the outer loop of rotateH0 (sk.F90:72-137).  The columns of one
+// atom-1 shell are a contiguous run of (2 l1 + 1) * nOrb2 elements of the column-major block:
+//   emit(eLocal, value)        element eLocal = row + nOrb2 * (col - firstCol) of the current group
+//   endGroup(first, count)     the group is complete; it covers elements [first, first + count)
+// Generic shell structure: run-time loops, warp-uniform dispatch on the shell-pair type.
+template <int LMAX, class Emit, class EndGroup>
+__device__ __forceinline__ void skLaneEval(const SpPairProg &pg, const SkTableDev &t, double r, double dx,
+                                           double dy, double dz, Emit &&emit, EndGroup &&endGroup) {
+  LaneInterp li;
+  laneInterpSetup(t, r, li);
   double Y[(2 * LMAX + 1) * (2 * LMAX + 1)];
   skg::harmonics<2 * LMAX>(dx, dy, dz, Y);
   int ind = 0, iCol = 0;
-  const int nSh1 = pg.nSh1, nSh2 = pg.nSh2;
+  const int nSh1 = pg.nSh1, nSh2 = pg.nSh2, n2 = pg.nOrb2;
   const unsigned long long sh1s = pg.shells1, sh2s = pg.shells2;
   for (int sh1 = 0; sh1 < nSh1; ++sh1) {
     const int l1 = (int)((sh1s >> (4 * sh1)) & 0xF);
@@ -132,33 +112,26 @@ __device__ __forceinline__ void skLaneEval(const SpPairProg &pg, double r, doubl
     for (int sh2 = 0; sh2 < nSh2; ++sh2) {
       const int l2 = (int)((sh2s >> (4 * sh2)) & 0xF);
       const int lmin = min(l1, l2);
-      double vH[4], vS[4];
+      double v[4];
+      const double zero[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        vH[k] = 0.0;
-        vS[k] = 0.0;
-        if (k <= LMAX && k <= lmin) {
-          if (DO_H) vH[k] = laneInterp(pg.H, liH, ind + k);
-          if (DO_S) vS[k] = laneInterp(pg.S, liS, ind + k);
-        }
-      }
-      skg::blockDispatch<DO_H, DO_S, LMAX>(l1, l2, Y, vH, vS, [&](int a, int b, double h, double s) {
-        emit(iRow + b, iCol + a, h, s);
+      for (int k = 0; k < 4; ++k) v[k] = (k <= LMAX && k <= lmin) ? laneInterp(t, li, ind + k) : 0.0;
+      skg::blockDispatch<true, false, LMAX>(l1, l2, Y, v, zero, [&](int a, int b, double h, double) {
+        emit(iRow + b + n2 * a, h);
       });
       ind += lmin + 1;
       iRow += 2 * l2 + 1;
     }
-    endGroup(iCol, 2 * l1 + 1);
+    endGroup(n2 * iCol, n2 * (2 * l1 + 1));
     iCol += 2 * l1 + 1;
   }
 }
 
 // ---- canonical species pairs: shells 0..LM1 on the atom, 0..LM2 on the neighbour (s, sp, spd, spdf) ---
 // Everything about the shell structure is a compile-time constant, so the loops of rotateH0 unroll
-// completely: the integrals live in registers with static indices, the element offsets become
-// immediates, and phase A (all table loads of the pair, issued back to back -> one memory round
-// trip) is separated from phase B (pure FP64 + stores), which is what keeps the staging rows of
-// the callers short-lived.
+// completely: the integrals live in registers with static indices and the element offsets become
+// immediates.  The table loads of group g+1 are issued before endGroup(g) runs (the caller's
+// write-out), so their latency hides behind it.
 
 template <int N, class F>
 __device__ __forceinline__ void staticFor(F &&f) {
@@ -179,44 +152,85 @@ __host__ __device__ constexpr int canonIntegStart(int l1, int l2, int LM2) {
   return n;
 }
 
-template <bool DO_H, bool DO_S, int LM1, int LM2, class Emit>
-__device__ __forceinline__ void skLaneEvalCanon(const SpPairProg &pg, double r, double dx, double dy, double dz,
-                                                Emit &&emit) {
-  constexpr int NI = canonIntegStart(LM1 + 1, 0, LM2);
+// integrals [START, START + N) of table t (polynomial branch taken once; 8 N independent loads)
+template <int START, int N, int NV>
+__device__ __forceinline__ void laneInterpRange(const SkTableDev &t, const LaneInterp &li, double (&v)[NV]) {
+  static_assert(N <= NV, "group buffer too small");
+  if (li.mode == 0) {
+    const double *__restrict__ y = t.tab + li.j0 + (size_t)START * t.nGrid;
+    const size_t nGrid = (size_t)t.nGrid;
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+      const double *__restrict__ yc = y + c * nGrid;
+      double acc = li.w[0] * __ldg(yc);
+#pragma unroll
+      for (int j = 1; j < 8; ++j) acc = fma(li.w[j], __ldg(yc + j), acc);
+      v[c] = acc;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < N; ++c) v[c] = laneInterp(t, li, START + c);
+  }
+}
+
+template <int LM1, int LM2, class Emit, class EndGroup>
+__device__ __forceinline__ void skLaneEvalCanon(const SkTableDev &t, double r, double dx, double dy, double dz,
+                                                Emit &&emit, EndGroup &&endGroup) {
   constexpr int LY = LM1 + LM2;
   constexpr int N2 = (LM2 + 1) * (LM2 + 1);
-  double vH[NI], vS[NI];
-  // phase A: every integral of the pair
-  if (DO_H) {
-    LaneInterp li;
-    laneInterpSetup(pg.H, r, li);
-    laneInterpAll<NI>(pg.H, li, vH);
-  }
-  if (DO_S) {
-    LaneInterp li;
-    laneInterpSetup(pg.S, r, li);
-    laneInterpAll<NI>(pg.S, li, vS);
-  }
+  // integrals of the largest group (atom-1 shell LM1)
+  constexpr int NG = canonIntegStart(LM1 + 1, 0, LM2) - canonIntegStart(LM1, 0, LM2);
+  LaneInterp li;
+  laneInterpSetup(t, r, li);
   double Y[(LY + 1) * (LY + 1)];
   skg::harmonics<LY>(dx, dy, dz, Y);
-  // phase B: rotation, shell pair by shell pair
+  double vCur[NG], vNext[NG];
+  laneInterpRange<0, canonIntegStart(1, 0, LM2), NG>(t, li, vCur);
   staticFor<LM1 + 1>([&](auto l1c) {
     constexpr int l1 = decltype(l1c)::value;
+    constexpr int g0 = canonIntegStart(l1, 0, LM2);
+    if constexpr (l1 < LM1)  // prefetch the next group's integrals
+      laneInterpRange<canonIntegStart(l1 + 1, 0, LM2), canonIntegStart(l1 + 2, 0, LM2) - canonIntegStart(l1 + 1, 0, LM2), NG>(
+          t, li, vNext);
     staticFor<LM2 + 1>([&](auto l2c) {
       constexpr int l2 = decltype(l2c)::value;
       constexpr int lmin = canonMin(l1, l2);
-      constexpr int ind = canonIntegStart(l1, l2, LM2);
-      double h4[4] = {0.0, 0.0, 0.0, 0.0}, s4[4] = {0.0, 0.0, 0.0, 0.0};
+      constexpr int ind = canonIntegStart(l1, l2, LM2) - g0;
+      double v4[4] = {0.0, 0.0, 0.0, 0.0};
+      const double zero[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-      for (int k = 0; k <= lmin; ++k) {
-        if (DO_H) h4[k] = vH[ind + k];
-        if (DO_S) s4[k] = vS[ind + k];
-      }
-      skg::blockT<l1, l2, DO_H, DO_S>(Y, h4, s4, [&](int a, int b, double h, double s) {
-        emit(l2 * l2 + b + N2 * (l1 * l1 + a), h, s);  // e = (iRow + b) + nOrb2 * (iCol + a)
+      for (int k = 0; k <= lmin; ++k) v4[k] = vCur[ind + k];
+      skg::blockT<l1, l2, true, false>(Y, v4, zero, [&](int a, int b, double h, double) {
+        emit(l2 * l2 + b + N2 * a, h);  // (iRow + b) + nOrb2 * (column inside the group)
       });
     });
+    endGroup(N2 * l1 * l1, N2 * (2 * l1 + 1));
+    if constexpr (l1 < LM1) {
+#pragma unroll
+      for (int c = 0; c < NG; ++c) vCur[c] = vNext[c];
+    }
   });
+}
+
+// Warp-uniform dispatch: canonical species pairs up to spd go to the unrolled evaluator, anything
+// else (f shells, repeated or unordered shells) to the generic loops.
+template <int LMAX, class Emit, class EndGroup>
+__device__ __forceinline__ void skLaneEvalAny(const SpPairProg &pg, const SkTableDev &t, double r, double dx,
+                                              double dy, double dz, Emit &&emit, EndGroup &&endGroup) {
+  const int canon = (pg.canon1 >= 0 && pg.canon2 >= 0 && pg.canon1 <= 2 && pg.canon2 <= 2)
+                        ? pg.canon1 * 3 + pg.canon2 : -1;
+  switch (canon) {
+    case 0: skLaneEvalCanon<0, 0>(t, r, dx, dy, dz, emit, endGroup); break;
+    case 1: if constexpr (LMAX >= 1) skLaneEvalCanon<0, 1>(t, r, dx, dy, dz, emit, endGroup); break;
+    case 2: if constexpr (LMAX >= 2) skLaneEvalCanon<0, 2>(t, r, dx, dy, dz, emit, endGroup); break;
+    case 3: if constexpr (LMAX >= 1) skLaneEvalCanon<1, 0>(t, r, dx, dy, dz, emit, endGroup); break;
+    case 4: if constexpr (LMAX >= 1) skLaneEvalCanon<1, 1>(t, r, dx, dy, dz, emit, endGroup); break;
+    case 5: if constexpr (LMAX >= 2) skLaneEvalCanon<1, 2>(t, r, dx, dy, dz, emit, endGroup); break;
+    case 6: if constexpr (LMAX >= 2) skLaneEvalCanon<2, 0>(t, r, dx, dy, dz, emit, endGroup); break;
+    case 7: if constexpr (LMAX >= 2) skLaneEvalCanon<2, 1>(t, r, dx, dy, dz, emit, endGroup); break;
+    case 8: if constexpr (LMAX >= 2) skLaneEvalCanon<2, 2>(t, r, dx, dy, dz, emit, endGroup); break;
+    default: skLaneEval<LMAX>(pg, t, r, dx, dy, dz, emit, endGroup);
+  }
 }
 
 }  // namespace dftbp_b200
