@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256, 2) k1_pair_build(const K1Params p) {
     const double rinv = 1.0 / dist;
     const int desc = valid ? indC : -1;
     skLaneEvalAny<LMAX>(
-        pg, tab, dist, vx * rinv, vy * rinv, vz * rinv, [&](int e, double v) { row[e] = v; },
+        pg, tab, dist, vx * rinv, vy * rinv, vz * rinv, [&](int, int e, double v) { row[e] = v; },
         [&](int first, int count) {
           __syncwarp();
           const unsigned M = (1048576u + (unsigned)count - 1u) / (unsigned)count;  // idx / count = idx * M >> 20

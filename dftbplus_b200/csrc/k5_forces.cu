@@ -1,120 +1,213 @@
 // k5_forces.cu -- derivative_shift (dftb/forces.F90:27-38, 119-217, 548-669) with the reference's
 // finite-difference derivator (getFirstDerivFiniteDiff, dftb/nonscc.F90:428-484).
 //
-// One warp per off-site pair (iAtom1 /= iAtom2f).  The reference materialises H' and S'
-// (mOrb x mOrb x 3 each, 12 full SK evaluations per pair) and then contracts them; here the six
-// displaced blocks are contracted on the fly in registers -- no dH/dR ever exists in memory:
+// The reference materialises H' and S' (mOrb x mOrb x 3 each, 12 full SK evaluations per pair)
+// and then contracts them; here the six displaced blocks are contracted on the fly in registers --
+// no dH/dR ever exists in memory:
 //
 //   g(j) = 2 [ sum rho.H'_j - sum Erho.S'_j + sum_spin sum rho_s . 1/2 (S'_j V1_s + V2_s S'_j) ]
 //        = 2 sum_e [ wH_e H'_j,e + wS_e S'_j,e ],
 //   wH = rho_1,  wS = -Erho + sum_spin 1/2 (rho_s V1_s^T + V2_s^T rho_s)        (independent of j)
 //   X'_j = (X(v - delta e_j) - X(v + delta e_j)) / (2 delta)                      (nonscc.F90:471-481)
 //
-// so g(j) = (1/delta) sum_e [ wH_e (H_e(-) - H_e(+)) + wS_e (S_e(-) - S_e(+)) ], one warp
-// reduction per Cartesian direction, then deriv(:,iAtom1) += g, deriv(:,iAtom2f) -= g.
-// FP64 CUDA-core bound (about 6 block evaluations of sk_eval.cuh per pair), not HBM bound.
-#include "sk_eval.cuh"
+// so g(j) = (1/delta) sum_e [ wH_e (H_e(-) - H_e(+)) + wS_e (S_e(-) - S_e(+)) ];
+// deriv(:,iAtom1) += g, deriv(:,iAtom2f) -= g.
+//
+// Lane-per-pair, like K1: every thread owns one neighbour pair of the sorted schedule
+// (pair_sort.cu) and runs the straight-line evaluator of sk_lane_eval.cuh six times per matrix.
+// One work item = (chunk of 32 pairs, matrix): the H part (weights rho_1) and the S part (weights
+// wS) are independent sums, so they are separate items and a warp stages ONE weight array:
+//   1. the warp loads the 32 weight blocks cooperatively (lanes on consecutive elements: coalesced)
+//      into its [32][pitch] shared tile, forming wS on the way;
+//   2. every lane contracts its six displaced blocks against its own row of the tile;
+//   3. six atomic adds per lane.
+// FP64 CUDA-core bound (6 block evaluations per pair and matrix), not HBM bound.
+#include "sk_lane_eval.cuh"
 
 using namespace dftbp_b200;
 
 namespace {
 
-constexpr int kMaxElemPerLane = (kMaxOrb * kMaxOrb + 31) / 32;  // 8
-
 struct K5Params {
-  SkDeviceTables tb;
-  const int *work;
-  long long nWork;
-  int ld, nSpecies, mOrb, nAtom, nSpin, sparseSize;
+  const SpPairProg *progs;
+  const int *items;
+  const int *total;
+  int ld, nSpecies, mOrb, nAtom, nSpin, sparseSize, pitch;
   const double *coords;
   const int *species, *iNeighbour, *iPair, *img2CentCell;
   const double *DM, *EDM, *shift;
+  const int *shiftFull;  // device flag: some shift block has an off-diagonal element
   double delta;
   double *deriv;
 };
 
-template <int NE>  // elements per lane: ceil(mOrb^2 / 32)
-__global__ void __launch_bounds__(32 * kWarpsPerCta)
-k5_derivative_shift(const K5Params p) {
-  __shared__ WarpScratch scratch[kWarpsPerCta];
-  const int lane = threadIdx.x & 31, wIn = threadIdx.x >> 5;
-  WarpScratch &ws = scratch[wIn];
-  const long long nWarps = (long long)gridDim.x * kWarpsPerCta;
-  for (long long w = (long long)blockIdx.x * kWarpsPerCta + wIn; w < p.nWork; w += nWarps) {
-    const int flat = __ldg(p.work + w);
-    const int iAt1 = flat / p.ld, iNeigh = flat - iAt1 * p.ld;
-    if (iNeigh == 0) continue;  // loop from 1 as no contribution from the atom itself
+// flag = 1 if any off-diagonal element of any shift block is non-zero
+__global__ void k5_shift_structure(const double *__restrict__ shift, int mOrb, long long nBlocks, int *flag) {
+  const long long n = nBlocks * mOrb * mOrb;
+  bool any = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int inBlock = (int)(i % (mOrb * mOrb));
+    const int a = inBlock / mOrb, b = inBlock - a * mOrb;
+    if (a != b && shift[i] != 0.0) any = true;
+  }
+  if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+template <int LMAX>
+__global__ void __launch_bounds__(256, 1) k5_derivative_shift(const K5Params p) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wIn = threadIdx.x >> 5, nW = blockDim.x >> 5;
+  double *stage = smem + (size_t)wIn * 32 * p.pitch;
+  const double *row = stage + (size_t)lane * p.pitch;
+  const int nChunks = __ldg(p.total) >> 5;
+  const int nItems = 2 * nChunks;
+  const bool shiftFull = p.shift != nullptr && __ldg(p.shiftFull) != 0;
+  const int mo2 = p.mOrb * p.mOrb;
+  for (int item = blockIdx.x * nW + wIn; item < nItems; item += gridDim.x * nW) {
+    const int chunk = item >> 1;
+    const bool isS = item & 1;
+    int flat = __ldg(p.items + 32 * chunk + lane);
+    const bool valid = flat >= 0;
+    const int flat0 = __shfl_sync(0xffffffffu, flat, 0);  // lane 0 of a chunk is never padding
+    if (!valid) flat = flat0;
+    const int iAt1 = flat / p.ld;
     const int iAt2 = __ldg(p.iNeighbour + flat) - 1;
     const int iAt2f = __ldg(p.img2CentCell + iAt2) - 1;
-    if (iAt1 == iAt2f) continue;
-    const int sp1 = __ldg(p.species + iAt1) - 1, sp2 = __ldg(p.species + iAt2) - 1;
+    // pairs whose neighbour folds onto the atom itself do not contribute (forces.F90:186, :631)
+    const bool live = valid && iAt1 != iAt2f;
+    const int sp1 = __shfl_sync(0xffffffffu, __ldg(p.species + iAt1), 0) - 1;
+    const int sp2 = __shfl_sync(0xffffffffu, __ldg(p.species + iAt2), 0) - 1;
     const int ind = __ldg(p.iPair + flat);
-    const SpPairProg &pg = p.tb.progs[sp1 + p.nSpecies * sp2];
+    const SpPairProg &pg = p.progs[sp1 + p.nSpecies * sp2];
+    const SkTableDev tab = isS ? pg.S : pg.H;
     const int n1 = pg.nOrb1, n2 = pg.nOrb2, nElem = n1 * n2;
 
-    // contraction weights of this lane's elements
-    double wH[NE], wS[NE];
+    // ---- 1. stage the contraction weights of the 32 pairs: flat index idx = lane + 32 k over the
+    // 32 * nElem elements, (pair, element) = (idx / nElem, idx % nElem) by multiply-shift.  Batches
+    // of U elements per lane, written branch-free so that all loads of a batch are in flight
+    // together (the weights stream from HBM: one latency per batch instead of one per element).
+    {
+      constexpr int U = 8;
+      const int desc = live ? ind : -1;
+      const unsigned M = (1048576u + (unsigned)nElem - 1u) / (unsigned)nElem;
+      const unsigned M2 = (1048576u + (unsigned)n2 - 1u) / (unsigned)n2;
+      const bool scc = isS && p.shift != nullptr;
+      const double *__restrict__ src = isS ? p.EDM : p.DM;
+      const double sign = isS ? -1.0 : 1.0;
+      for (int k0 = 0; k0 < nElem; k0 += U) {
+        unsigned qq[U], ee[U];
+        int base[U], a1Q[U], a2Q[U];
+        double w[U];
 #pragma unroll
-    for (int i = 0; i < NE; ++i) {
-      const int e = lane + 32 * i;
-      wH[i] = 0.0;
-      wS[i] = 0.0;
-      if (e < nElem) {
-        wH[i] = __ldg(p.DM + ind + e);
-        double s = -__ldg(p.EDM + ind + e);
-        if (p.shift) {
-          const int a = e / n2, b = e - a * n2;  // element (row b, col a) of the n2 x n1 block
-          const int mo2 = p.mOrb * p.mOrb;
-          for (int iSpin = 0; iSpin < p.nSpin; ++iSpin) {
-            const double *__restrict__ rho = p.DM + (size_t)p.sparseSize * iSpin + ind;
-            const double *__restrict__ V1 = p.shift + (size_t)mo2 * (iAt1 + (size_t)p.nAtom * iSpin);
-            const double *__restrict__ V2 = p.shift + (size_t)mo2 * (iAt2f + (size_t)p.nAtom * iSpin);
-            double x = 0.0;
-            // (rho V1^T)(b,a) = sum_c rho(b,c) V1(a,c);  (V2^T rho)(b,a) = sum_c V2(c,b) rho(c,a)
-            for (int c = 0; c < n1; ++c) x = fma(__ldg(rho + b + n2 * c), __ldg(V1 + a + p.mOrb * c), x);
-            for (int c = 0; c < n2; ++c) x = fma(__ldg(V2 + c + p.mOrb * b), __ldg(rho + c + n2 * a), x);
-            s = fma(0.5, x, s);
+        for (int u = 0; u < U; ++u) {
+          const unsigned idx = (unsigned)(lane + 32 * (k0 + u));
+          const unsigned q = min((idx * M) >> 20, 31u);
+          qq[u] = q;
+          ee[u] = idx - q * (unsigned)nElem;
+          const int bq = __shfl_sync(0xffffffffu, desc, (int)q);
+          base[u] = (k0 + u < nElem) ? bq : -1;  // dead pairs never read their row
+          if (scc) {
+            a1Q[u] = __shfl_sync(0xffffffffu, iAt1, (int)q);
+            a2Q[u] = __shfl_sync(0xffffffffu, iAt2f, (int)q);
           }
         }
-        wS[i] = s;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          // unconditional loads (dead slots read element 0): independent, so they all issue up front
+          const size_t off = base[u] >= 0 ? (size_t)base[u] + ee[u] : 0;
+          w[u] = __ldg(src + off);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) w[u] *= sign;
+        if (scc && !shiftFull) {
+          // diagonal shift blocks (plain SCC / collinear spin):
+          // (rho V1^T + V2^T rho)(b,a) = rho(b,a) (V1(a,a) + V2(b,b)), element (row b, col a) of the n2 x n1 block
+          for (int iSpin = 0; iSpin < p.nSpin; ++iSpin) {
+            const double *__restrict__ rho = p.DM + (size_t)p.sparseSize * iSpin;
+            const double *__restrict__ V = p.shift + (size_t)mo2 * p.nAtom * iSpin;
+            double r[U], x1[U], x2[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const unsigned a = (ee[u] * M2) >> 20, b = ee[u] - a * (unsigned)n2;
+              const bool on = base[u] >= 0;
+              r[u] = __ldg(rho + (on ? (size_t)base[u] + ee[u] : 0));
+              x1[u] = __ldg(V + (on ? (size_t)mo2 * a1Q[u] + a * (p.mOrb + 1) : 0));
+              x2[u] = __ldg(V + (on ? (size_t)mo2 * a2Q[u] + b * (p.mOrb + 1) : 0));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) w[u] = fma(0.5, r[u] * (x1[u] + x2[u]), w[u]);
+          }
+        } else if (scc) {
+          // full shift blocks: (rho V1^T)(b,a) = sum_c rho(b,c) V1(a,c);  (V2^T rho)(b,a) = sum_c V2(c,b) rho(c,a)
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (base[u] < 0) continue;
+            const unsigned a = (ee[u] * M2) >> 20, b = ee[u] - a * (unsigned)n2;
+            for (int iSpin = 0; iSpin < p.nSpin; ++iSpin) {
+              const double *__restrict__ rho = p.DM + (size_t)p.sparseSize * iSpin + base[u];
+              const double *__restrict__ V1 = p.shift + (size_t)mo2 * (a1Q[u] + (size_t)p.nAtom * iSpin);
+              const double *__restrict__ V2 = p.shift + (size_t)mo2 * (a2Q[u] + (size_t)p.nAtom * iSpin);
+              double x = 0.0;
+              for (int c = 0; c < n1; ++c) x = fma(__ldg(rho + b + n2 * c), __ldg(V1 + a + p.mOrb * c), x);
+              for (int c = 0; c < n2; ++c) x = fma(__ldg(V2 + c + p.mOrb * b), __ldg(rho + c + n2 * a), x);
+              w[u] = fma(0.5, x, w[u]);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (base[u] >= 0) stage[qq[u] * p.pitch + ee[u]] = w[u];
       }
     }
+    __syncwarp();
 
+    // ---- 2. six displaced evaluations, contracted on the fly
     const double v0 = __ldg(p.coords + 3 * iAt2) - __ldg(p.coords + 3 * iAt1);
     const double v1 = __ldg(p.coords + 3 * iAt2 + 1) - __ldg(p.coords + 3 * iAt1 + 1);
     const double v2 = __ldg(p.coords + 3 * iAt2 + 2) - __ldg(p.coords + 3 * iAt1 + 2);
-    double g[3];
-#pragma unroll
-    for (int jj = 0; jj < 3; ++jj) {
-      double acc = 0.0;
-#pragma unroll
-      for (int ii = 1; ii <= 2; ++ii) {
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+    if (__any_sync(0xffffffffu, live)) {
+#pragma unroll 1
+      for (int k = 0; k < 6; ++k) {
+        const int jj = k >> 1;
         // vect(jj) = vect(jj) - real(2*ii-3) * deltaXDiff : ii=1 -> +delta, ii=2 -> -delta
-        const double sgn = (ii == 1) ? 1.0 : -1.0;
-        double d0 = v0, d1 = v1, d2 = v2;
-        if (jj == 0) d0 = v0 + sgn * p.delta;
-        if (jj == 1) d1 = v1 + sgn * p.delta;
-        if (jj == 2) d2 = v2 + sgn * p.delta;
+        const double sgn = (k & 1) ? -1.0 : 1.0;
+        const double d0 = jj == 0 ? v0 + sgn * p.delta : v0;
+        const double d1 = jj == 1 ? v1 + sgn * p.delta : v1;
+        const double d2 = jj == 2 ? v2 + sgn * p.delta : v2;
         const double dist = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
-        const double wgt = (ii == 1) ? -1.0 : 1.0;  // (tmp(ii=2) - tmp(ii=1))
-        skEvalBlock<true, true>(p.tb, pg, dist, d0 / dist, d1 / dist, d2 / dist, ws, lane,
-                                [&](int e, double h, double s) {
-                                  const int i = e >> 5;
-#pragma unroll
-                                  for (int k = 0; k < NE; ++k)
-                                    if (k == i) acc = fma(wgt, fma(wH[k], h, wS[k] * s), acc);
-                                });
+        const double rinv = 1.0 / dist;
+        double acc = 0.0;
+        skLaneEvalAny<LMAX>(
+            pg, tab, dist, d0 * rinv, d1 * rinv, d2 * rinv,
+            [&](int first, int e, double x) { acc = fma(row[first + e], x, acc); }, [](int, int) {});
+        acc *= -sgn;  // (tmp(ii=2) - tmp(ii=1))
+        if (jj == 0) g0 += acc;
+        if (jj == 1) g1 += acc;
+        if (jj == 2) g2 += acc;
       }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-      g[jj] = acc / p.delta;
     }
-    if (lane < 3) {
-      const double gv = lane == 0 ? g[0] : (lane == 1 ? g[1] : g[2]);
-      atomicAdd(p.deriv + lane + 3 * iAt1, gv);
-      atomicAdd(p.deriv + lane + 3 * iAt2f, -gv);
+    // ---- 3. deriv(:,iAtom1) += g, deriv(:,iAtom2f) -= g
+    if (live) {
+      const double inv = 1.0 / p.delta;
+      g0 *= inv; g1 *= inv; g2 *= inv;
+      atomicAdd(p.deriv + 3 * iAt1, g0);
+      atomicAdd(p.deriv + 3 * iAt1 + 1, g1);
+      atomicAdd(p.deriv + 3 * iAt1 + 2, g2);
+      atomicAdd(p.deriv + 3 * iAt2f, -g0);
+      atomicAdd(p.deriv + 3 * iAt2f + 1, -g1);
+      atomicAdd(p.deriv + 3 * iAt2f + 2, -g2);
     }
+    __syncwarp();  // the tile is restaged by the next item
   }
+}
+
+template <int LMAX>
+int launchTyped(dftbp_b200_ctx *ctx, const K5Params &p, int grid, int warps, size_t smemBytes) {
+  DFTBP_CUDA(ctx, cudaFuncSetAttribute(k5_derivative_shift<LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smemBytes));
+  k5_derivative_shift<LMAX><<<grid, 32 * warps, smemBytes, ctx->stream>>>(p);
+  return 0;
 }
 
 }  // namespace
@@ -132,9 +225,11 @@ extern "C" int dftbp_b200_derivative_shift(dftbp_b200_ctx *ctx, double *deriv, c
                 "Differentiation = Richardson (nonscc.F90:488-600) is not built yet; use FiniteDiff");
   DFTBP_CHECK(ctx, diffType == DFTBP_B200_DIFF_FINITE, "derivative_shift: invalid differentiator type");
   DFTBP_TRY(syncPrograms(ctx));
+  const SortedPairs *sched;
+  DFTBP_TRY(ensureSortedPairs(ctx, true, &sched));
   K5Params p;
-  p.tb = {ctx->dProgs, ctx->dADesc, ctx->dElemStart, ctx->dTerms, (const YDescDev *)ctx->dYDesc};
-  p.work = g.workLoad; p.nWork = g.nWorkLoad; p.ld = g.mNeigh + 1; p.nSpecies = ctx->nSpecies;
+  p.progs = ctx->dProgs; p.items = sched->items; p.total = sched->total;
+  p.ld = g.mNeigh + 1; p.nSpecies = ctx->nSpecies;
   p.mOrb = ctx->mOrb; p.nAtom = g.nAtom; p.nSpin = nSpin; p.sparseSize = g.sparseSize;
   p.coords = g.coords; p.species = g.species; p.iNeighbour = g.iNeighbour; p.iPair = g.iPair;
   p.img2CentCell = g.img2CentCell;
@@ -145,17 +240,32 @@ extern "C" int dftbp_b200_derivative_shift(dftbp_b200_ctx *ctx, double *deriv, c
   DFTBP_TRY(devIn(ctx, kSlotA, DM, (size_t)g.sparseSize * nDm, &p.DM));
   DFTBP_TRY(devIn(ctx, kSlotB, EDM, (size_t)g.sparseSize, &p.EDM));
   p.shift = nullptr;
+  p.shiftFull = ctx->dInfo + 1;
   if (shift)
     DFTBP_TRY(devIn(ctx, kSlotC, shift, (size_t)ctx->mOrb * ctx->mOrb * g.nAtom * nSpin, &p.shift));
   DFTBP_TRY(devOut(ctx, kSlotD, deriv, (size_t)3 * g.nAtom, false, &p.deriv));
   DFTBP_CUDA(ctx, cudaMemsetAsync(p.deriv, 0, sizeof(double) * 3 * g.nAtom, ctx->stream));
-  if (p.nWork > 0) {
+  if (g.nWorkLoad > 0) {
     ScopedTimer timer(ctx, kTimerForceCalc);
-    const int grid = gridFor(ctx, p.nWork, kWarpsPerCta, 8 * 4);
-    const int ne = (ctx->mOrb * ctx->mOrb + 31) / 32;
-    if (ne <= 1) k5_derivative_shift<1><<<grid, 32 * kWarpsPerCta, 0, ctx->stream>>>(p);
-    else if (ne <= 3) k5_derivative_shift<3><<<grid, 32 * kWarpsPerCta, 0, ctx->stream>>>(p);
-    else k5_derivative_shift<kMaxElemPerLane><<<grid, 32 * kWarpsPerCta, 0, ctx->stream>>>(p);
+    if (shift) {
+      // plain SCC / collinear spin shifts are diagonal blocks: detect it and skip the per-pair matrix products
+      DFTBP_CUDA(ctx, cudaMemsetAsync(ctx->dInfo + 1, 0, sizeof(int), ctx->stream));
+      k5_shift_structure<<<ctx->smCount, 256, 0, ctx->stream>>>(p.shift, ctx->mOrb, (long long)g.nAtom * nSpin,
+                                                                  ctx->dInfo + 1);
+      ctx->launches++;
+    }
+    p.pitch = (ctx->mOrb * ctx->mOrb) | 1;
+    const size_t perWarp = sizeof(double) * 32 * (size_t)p.pitch;
+    int warps = (int)std::min<size_t>(8, (ctx->smemOptin - 2048) / perWarp);
+    DFTBP_CHECK(ctx, warps >= 1, "derivative_shift: weight tile does not fit into shared memory");
+    const size_t smemBytes = perWarp * warps;
+    const long long items = 2 * ((g.nWorkLoad + 31) / 32 + ctx->nSpecies * ctx->nSpecies);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((items + warps - 1) / warps, ctx->smCount));
+    int rc;
+    if (ctx->lMaxAll <= 1) rc = launchTyped<1>(ctx, p, grid, warps, smemBytes);
+    else if (ctx->lMaxAll == 2) rc = launchTyped<2>(ctx, p, grid, warps, smemBytes);
+    else rc = launchTyped<3>(ctx, p, grid, warps, smemBytes);
+    if (rc) return rc;
     ctx->launches++;
   }
   return finish(ctx);

@@ -93,8 +93,9 @@ __device__ __forceinline__ double laneInterp(const SkTableDev &t, const LaneInte
 // of this lane's pair at distance r along the unit vector (dx, dy, dz), one atom-1 shell ("column
 // group") after the other, like the outer loop of rotateH0 (sk.F90:72-137).  The columns of one
 // atom-1 shell are a contiguous run of (2 l1 + 1) * nOrb2 elements of the column-major block:
-//   emit(eLocal, value)        element eLocal = row + nOrb2 * (col - firstCol) of the current group
-//   endGroup(first, count)     the group is complete; it covers elements [first, first + count)
+//   emit(first, eLocal, value)  element first + eLocal of the block, eLocal = row + nOrb2 * (col - firstCol)
+//                               inside the current group, first = nOrb2 * firstCol
+//   endGroup(first, count)      the group is complete; it covers elements [first, first + count)
 // Generic shell structure: run-time loops, warp-uniform dispatch on the shell-pair type.
 template <int LMAX, class Emit, class EndGroup>
 __device__ __forceinline__ void skLaneEval(const SpPairProg &pg, const SkTableDev &t, double r, double dx,
@@ -117,7 +118,7 @@ __device__ __forceinline__ void skLaneEval(const SpPairProg &pg, const SkTableDe
 #pragma unroll
       for (int k = 0; k < 4; ++k) v[k] = (k <= LMAX && k <= lmin) ? laneInterp(t, li, ind + k) : 0.0;
       skg::blockDispatch<true, false, LMAX>(l1, l2, Y, v, zero, [&](int a, int b, double h, double) {
-        emit(iRow + b + n2 * a, h);
+        emit(n2 * iCol, iRow + b + n2 * a, h);
       });
       ind += lmin + 1;
       iRow += 2 * l2 + 1;
@@ -201,7 +202,7 @@ __device__ __forceinline__ void skLaneEvalCanon(const SkTableDev &t, double r, d
 #pragma unroll
       for (int k = 0; k <= lmin; ++k) v4[k] = vCur[ind + k];
       skg::blockT<l1, l2, true, false>(Y, v4, zero, [&](int a, int b, double h, double) {
-        emit(l2 * l2 + b + N2 * a, h);  // (iRow + b) + nOrb2 * (column inside the group)
+        emit(N2 * l1 * l1, l2 * l2 + b + N2 * a, h);  // (iRow + b) + nOrb2 * (column inside the group)
       });
     });
     endGroup(N2 * l1 * l1, N2 * (2 * l1 + 1));

@@ -71,6 +71,17 @@ def main():
     ms = timeit(lambda: hp.derivative_shift(rho, edm, deriv=deriv), stream, n=5)
     out["k5_ms"] = ms
     out["k5_pairs_per_s"] = pairs / ms * 1e3
+    # SCC form, 2 spins: diagonal shift blocks (plain SCC / collinear spin) and full blocks (DFTB+U-like)
+    rho2 = torch.stack([rho, over * torch.randn(ss, **f64)])
+    mo = hp.mOrb
+    shd = torch.zeros((2, nAtom, mo, mo), **f64)
+    shd[:, :, torch.arange(mo), torch.arange(mo)] = 0.1 * torch.randn((2, nAtom, mo), **f64)
+    ms = timeit(lambda: hp.derivative_shift(rho2, edm, shift=shd, deriv=deriv), stream, n=5)
+    out["k5_scc_diag_ms"] = ms
+    shf = 0.1 * torch.randn((2, nAtom, mo, mo), **f64)
+    shf = 0.5 * (shf + shf.transpose(2, 3)).contiguous()
+    ms = timeit(lambda: hp.derivative_shift(rho2, edm, shift=shf, deriv=deriv), stream, n=5)
+    out["k5_scc_full_ms"] = ms
     if dense:
         sq = new_dense(nOrb)
         ms = timeit(lambda: hp.unpackHS(ham, square=sq), stream, n=5)
