@@ -35,8 +35,8 @@ struct K5Params {
   int ld, nSpecies, mOrb, nAtom, nSpin, sparseSize, pitch;
   const double *coords;
   const int *species, *iNeighbour, *iPair, *img2CentCell;
-  const double *DM, *EDM, *shift;
-  const int *shiftFull;  // device flag: some shift block has an off-diagonal element
+  const double *DM;     // rho, first spin channel = wH
+  const double *negWS;  // -wS: Erho (no SCC) or the array prepared by k5_force_weights
   double delta;
   double *deriv;
 };
@@ -53,6 +53,58 @@ __global__ void k5_shift_structure(const double *__restrict__ shift, int mOrb, l
   if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
+// -wS = Erho - sum_spin 1/2 (rho_s V1_s^T + V2_s^T rho_s) for every off-site block of this rank's
+// work list (the SCC part of derivative_blockEuclidean, forces.F90:640-656, independent of the
+// Cartesian direction).  One warp per block, lanes on consecutive elements: a streaming kernel.
+// Plain SCC and collinear-spin shifts are diagonal blocks (the device flag says so); then
+// (rho V1^T + V2^T rho)(b,a) = rho(b,a) (V1(a,a) + V2(b,b)) and no matrix product is needed.
+struct K5WeightParams {
+  const int *work;
+  long long nWork;
+  int ld, mOrb, nAtom, nSpin, sparseSize;
+  const int *iNeighbour, *iPair, *img2CentCell, *iAtomStart;
+  const double *DM, *EDM, *shift;
+  const int *shiftFull;
+  double *negWS;
+};
+
+__global__ void __launch_bounds__(256) k5_force_weights(const K5WeightParams p) {
+  const int lane = threadIdx.x & 31;
+  const bool full = __ldg(p.shiftFull) != 0;
+  const int mo2 = p.mOrb * p.mOrb;
+  const long long nWarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < p.nWork; w += nWarps) {
+    const int flat = __ldg(p.work + w);
+    const int iAt1 = flat / p.ld;
+    if (flat - iAt1 * p.ld == 0) continue;
+    const int iAt2f = __ldg(p.img2CentCell + __ldg(p.iNeighbour + flat) - 1) - 1;
+    if (iAt1 == iAt2f) continue;
+    const int n1 = __ldg(p.iAtomStart + iAt1 + 1) - __ldg(p.iAtomStart + iAt1);
+    const int n2 = __ldg(p.iAtomStart + iAt2f + 1) - __ldg(p.iAtomStart + iAt2f);
+    const int ind = __ldg(p.iPair + flat);
+    for (int e = lane; e < n1 * n2; e += 32) {
+      const int a = e / n2, b = e - a * n2;  // element (row b, col a) of the n2 x n1 block
+      double s = __ldg(p.EDM + ind + e);
+      for (int iSpin = 0; iSpin < p.nSpin; ++iSpin) {
+        const double *__restrict__ rho = p.DM + (size_t)p.sparseSize * iSpin + ind;
+        const double *__restrict__ V1 = p.shift + (size_t)mo2 * (iAt1 + (size_t)p.nAtom * iSpin);
+        const double *__restrict__ V2 = p.shift + (size_t)mo2 * (iAt2f + (size_t)p.nAtom * iSpin);
+        double x;
+        if (!full) {
+          x = __ldg(rho + e) * (__ldg(V1 + a + p.mOrb * a) + __ldg(V2 + b + p.mOrb * b));
+        } else {
+          // (rho V1^T)(b,a) = sum_c rho(b,c) V1(a,c);  (V2^T rho)(b,a) = sum_c V2(c,b) rho(c,a)
+          x = 0.0;
+          for (int c = 0; c < n1; ++c) x = fma(__ldg(rho + b + n2 * c), __ldg(V1 + a + p.mOrb * c), x);
+          for (int c = 0; c < n2; ++c) x = fma(__ldg(V2 + c + p.mOrb * b), __ldg(rho + c + n2 * a), x);
+        }
+        s = fma(-0.5, x, s);
+      }
+      p.negWS[ind + e] = s;
+    }
+  }
+}
+
 template <int LMAX>
 __global__ void __launch_bounds__(256, 1) k5_derivative_shift(const K5Params p) {
   extern __shared__ double smem[];
@@ -61,8 +113,6 @@ __global__ void __launch_bounds__(256, 1) k5_derivative_shift(const K5Params p) 
   const double *row = stage + (size_t)lane * p.pitch;
   const int nChunks = __ldg(p.total) >> 5;
   const int nItems = 2 * nChunks;
-  const bool shiftFull = p.shift != nullptr && __ldg(p.shiftFull) != 0;
-  const int mo2 = p.mOrb * p.mOrb;
   for (int item = blockIdx.x * nW + wIn; item < nItems; item += gridDim.x * nW) {
     const int chunk = item >> 1;
     const bool isS = item & 1;
@@ -80,85 +130,33 @@ __global__ void __launch_bounds__(256, 1) k5_derivative_shift(const K5Params p) 
     const int ind = __ldg(p.iPair + flat);
     const SpPairProg &pg = p.progs[sp1 + p.nSpecies * sp2];
     const SkTableDev tab = isS ? pg.S : pg.H;
-    const int n1 = pg.nOrb1, n2 = pg.nOrb2, nElem = n1 * n2;
+    const int nElem = pg.nOrb1 * pg.nOrb2;
 
-    // ---- 1. stage the contraction weights of the 32 pairs: flat index idx = lane + 32 k over the
-    // 32 * nElem elements, (pair, element) = (idx / nElem, idx % nElem) by multiply-shift.  Batches
-    // of U elements per lane, written branch-free so that all loads of a batch are in flight
-    // together (the weights stream from HBM: one latency per batch instead of one per element).
+    // ---- 1. stage the contraction weights of the 32 pairs: rho_1 blocks for the H part, -wS blocks
+    // (Erho without SCC, the array prepared by k5_force_weights with SCC) for the S part.  Flat
+    // index idx = lane + 32 k over the 32 * nElem elements, (pair, element) = (idx / nElem,
+    // idx % nElem) by multiply-shift; cp.async (LDGSTS) moves the 8-byte elements global -> shared
+    // without passing through registers, so the whole tile is in flight at once: one HBM latency
+    // per item.
     {
-      constexpr int U = 8;
       const int desc = live ? ind : -1;
       const unsigned M = (1048576u + (unsigned)nElem - 1u) / (unsigned)nElem;
-      const unsigned M2 = (1048576u + (unsigned)n2 - 1u) / (unsigned)n2;
-      const bool scc = isS && p.shift != nullptr;
-      const double *__restrict__ src = isS ? p.EDM : p.DM;
-      const double sign = isS ? -1.0 : 1.0;
-      for (int k0 = 0; k0 < nElem; k0 += U) {
-        unsigned qq[U], ee[U];
-        int base[U], a1Q[U], a2Q[U];
-        double w[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const unsigned idx = (unsigned)(lane + 32 * (k0 + u));
-          const unsigned q = min((idx * M) >> 20, 31u);
-          qq[u] = q;
-          ee[u] = idx - q * (unsigned)nElem;
-          const int bq = __shfl_sync(0xffffffffu, desc, (int)q);
-          base[u] = (k0 + u < nElem) ? bq : -1;  // dead pairs never read their row
-          if (scc) {
-            a1Q[u] = __shfl_sync(0xffffffffu, iAt1, (int)q);
-            a2Q[u] = __shfl_sync(0xffffffffu, iAt2f, (int)q);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          // unconditional loads (dead slots read element 0): independent, so they all issue up front
-          const size_t off = base[u] >= 0 ? (size_t)base[u] + ee[u] : 0;
-          w[u] = __ldg(src + off);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) w[u] *= sign;
-        if (scc && !shiftFull) {
-          // diagonal shift blocks (plain SCC / collinear spin):
-          // (rho V1^T + V2^T rho)(b,a) = rho(b,a) (V1(a,a) + V2(b,b)), element (row b, col a) of the n2 x n1 block
-          for (int iSpin = 0; iSpin < p.nSpin; ++iSpin) {
-            const double *__restrict__ rho = p.DM + (size_t)p.sparseSize * iSpin;
-            const double *__restrict__ V = p.shift + (size_t)mo2 * p.nAtom * iSpin;
-            double r[U], x1[U], x2[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const unsigned a = (ee[u] * M2) >> 20, b = ee[u] - a * (unsigned)n2;
-              const bool on = base[u] >= 0;
-              r[u] = __ldg(rho + (on ? (size_t)base[u] + ee[u] : 0));
-              x1[u] = __ldg(V + (on ? (size_t)mo2 * a1Q[u] + a * (p.mOrb + 1) : 0));
-              x2[u] = __ldg(V + (on ? (size_t)mo2 * a2Q[u] + b * (p.mOrb + 1) : 0));
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) w[u] = fma(0.5, r[u] * (x1[u] + x2[u]), w[u]);
-          }
-        } else if (scc) {
-          // full shift blocks: (rho V1^T)(b,a) = sum_c rho(b,c) V1(a,c);  (V2^T rho)(b,a) = sum_c V2(c,b) rho(c,a)
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            if (base[u] < 0) continue;
-            const unsigned a = (ee[u] * M2) >> 20, b = ee[u] - a * (unsigned)n2;
-            for (int iSpin = 0; iSpin < p.nSpin; ++iSpin) {
-              const double *__restrict__ rho = p.DM + (size_t)p.sparseSize * iSpin + base[u];
-              const double *__restrict__ V1 = p.shift + (size_t)mo2 * (a1Q[u] + (size_t)p.nAtom * iSpin);
-              const double *__restrict__ V2 = p.shift + (size_t)mo2 * (a2Q[u] + (size_t)p.nAtom * iSpin);
-              double x = 0.0;
-              for (int c = 0; c < n1; ++c) x = fma(__ldg(rho + b + n2 * c), __ldg(V1 + a + p.mOrb * c), x);
-              for (int c = 0; c < n2; ++c) x = fma(__ldg(V2 + c + p.mOrb * b), __ldg(rho + c + n2 * a), x);
-              w[u] = fma(0.5, x, w[u]);
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          if (base[u] >= 0) stage[qq[u] * p.pitch + ee[u]] = w[u];
+      const double *__restrict__ src = isS ? p.negWS : p.DM;
+      const unsigned stageS = (unsigned)__cvta_generic_to_shared(stage);
+#pragma unroll 4
+      for (int k = 0; k < nElem; ++k) {
+        const unsigned idx = (unsigned)(lane + 32 * k);
+        const unsigned q = (idx * M) >> 20;
+        const unsigned e = idx - q * (unsigned)nElem;
+        const int bq = __shfl_sync(0xffffffffu, desc, (int)q);
+        if (bq >= 0)  // dead pairs never read their row
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(stageS + 8u * (q * (unsigned)p.pitch + e)),
+                       "l"(src + bq + e)
+                       : "memory");
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
 
     // ---- 2. six displaced evaluations, contracted on the fly
@@ -181,7 +179,7 @@ __global__ void __launch_bounds__(256, 1) k5_derivative_shift(const K5Params p) 
         skLaneEvalAny<LMAX>(
             pg, tab, dist, d0 * rinv, d1 * rinv, d2 * rinv,
             [&](int first, int e, double x) { acc = fma(row[first + e], x, acc); }, [](int, int) {});
-        acc *= -sgn;  // (tmp(ii=2) - tmp(ii=1))
+        acc *= isS ? sgn : -sgn;  // (tmp(ii=2) - tmp(ii=1)); the S tile holds -wS
         if (jj == 0) g0 += acc;
         if (jj == 1) g1 += acc;
         if (jj == 2) g2 += acc;
@@ -238,21 +236,29 @@ extern "C" int dftbp_b200_derivative_shift(dftbp_b200_ctx *ctx, double *deriv, c
   // the non-SCC routine takes DM(:) only; the block routine DM(:, nSpin)
   const int nDm = shift ? nSpin : 1;
   DFTBP_TRY(devIn(ctx, kSlotA, DM, (size_t)g.sparseSize * nDm, &p.DM));
-  DFTBP_TRY(devIn(ctx, kSlotB, EDM, (size_t)g.sparseSize, &p.EDM));
-  p.shift = nullptr;
-  p.shiftFull = ctx->dInfo + 1;
+  DFTBP_TRY(devIn(ctx, kSlotB, EDM, (size_t)g.sparseSize, &p.negWS));
+  const double *dEDM = p.negWS, *dShift = nullptr;
   if (shift)
-    DFTBP_TRY(devIn(ctx, kSlotC, shift, (size_t)ctx->mOrb * ctx->mOrb * g.nAtom * nSpin, &p.shift));
+    DFTBP_TRY(devIn(ctx, kSlotC, shift, (size_t)ctx->mOrb * ctx->mOrb * g.nAtom * nSpin, &dShift));
   DFTBP_TRY(devOut(ctx, kSlotD, deriv, (size_t)3 * g.nAtom, false, &p.deriv));
   DFTBP_CUDA(ctx, cudaMemsetAsync(p.deriv, 0, sizeof(double) * 3 * g.nAtom, ctx->stream));
   if (g.nWorkLoad > 0) {
     ScopedTimer timer(ctx, kTimerForceCalc);
     if (shift) {
-      // plain SCC / collinear spin shifts are diagonal blocks: detect it and skip the per-pair matrix products
-      DFTBP_CUDA(ctx, cudaMemsetAsync(ctx->dInfo + 1, 0, sizeof(int), ctx->stream));
-      k5_shift_structure<<<ctx->smCount, 256, 0, ctx->stream>>>(p.shift, ctx->mOrb, (long long)g.nAtom * nSpin,
-                                                                  ctx->dInfo + 1);
-      ctx->launches++;
+      // plain SCC / collinear spin shifts are diagonal blocks: detect it, then form -wS once per block
+      int *flag = ctx->dInfo + 1;
+      DFTBP_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+      k5_shift_structure<<<ctx->smCount, 256, 0, ctx->stream>>>(dShift, ctx->mOrb, (long long)g.nAtom * nSpin, flag);
+      void *scratch;
+      DFTBP_TRY(stagingGet(ctx, kSlotE, sizeof(double) * (size_t)g.sparseSize, &scratch));
+      K5WeightParams wp;
+      wp.work = g.workLoad; wp.nWork = g.nWorkLoad; wp.ld = g.mNeigh + 1; wp.mOrb = ctx->mOrb;
+      wp.nAtom = g.nAtom; wp.nSpin = nSpin; wp.sparseSize = g.sparseSize; wp.iNeighbour = g.iNeighbour;
+      wp.iPair = g.iPair; wp.img2CentCell = g.img2CentCell; wp.iAtomStart = g.iAtomStart;
+      wp.DM = p.DM; wp.EDM = dEDM; wp.shift = dShift; wp.shiftFull = flag; wp.negWS = (double *)scratch;
+      k5_force_weights<<<gridFor(ctx, wp.nWork, 8, 8), 256, 0, ctx->stream>>>(wp);
+      p.negWS = (const double *)scratch;
+      ctx->launches += 2;
     }
     p.pitch = (ctx->mOrb * ctx->mOrb) | 1;
     const size_t perWarp = sizeof(double) * 32 * (size_t)p.pitch;
