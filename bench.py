@@ -101,6 +101,16 @@ def algorithmic_bytes_k1(geo):
     return 16.0 * geo["sparseSize"] + 8.0 * float(geo["nNeighbourSK"].sum())
 
 
+def scc_shift(rng, n_spin, n_atom, m_orb):
+    """Block shift of a collinear-spin SCC run without DFTB+U / on-site corrections (BASELINE config
+    4): diagonal mOrb x mOrb blocks, one value per orbital (hamiltonian.F90:148-293 -> shift.F90:232-309
+    expand atom / shell potentials onto the block diagonal)."""
+    sh = np.zeros((n_spin, n_atom, m_orb, m_orb))
+    idx = np.arange(m_orb)
+    sh[:, :, idx, idx] = 0.05 * rng.normal(size=(n_spin, n_atom, m_orb))
+    return sh
+
+
 def reference_arm(a, rank, world):
     """The reference's CPU path (oracle restatement, C + OpenMP, all host threads): same step."""
     if rank != 0:
@@ -112,7 +122,7 @@ def reference_arm(a, rank, world):
     s = oracle.build_s(model, geo)
     dm = s * rng.normal(size=(2, geo["sparseSize"]))
     edm = s * rng.normal(size=geo["sparseSize"])
-    shift = 0.05 * rng.normal(size=(2, geo["nAtom"], model.mOrb, model.mOrb))
+    shift = scc_shift(rng, 2, geo["nAtom"], model.mOrb)
     pairs = int(geo["nNeighbourSK"].sum())
 
     def step():
@@ -199,12 +209,19 @@ def main():
         dm = over.unsqueeze(0) * torch.from_numpy(rng.normal(size=(n_spin, ss))).to(dev)
         dm = dm.contiguous()
         edm = over * torch.from_numpy(rng.normal(size=ss)).to(dev)
-        shift = torch.from_numpy(0.05 * rng.normal(size=(n_spin, nAtom, hp.mOrb, hp.mOrb))).to(dev)
+        shift = torch.from_numpy(scc_shift(rng, n_spin, nAtom, hp.mOrb)).to(dev)
+        shift_full = torch.from_numpy(0.05 * rng.normal(size=(n_spin, nAtom, hp.mOrb, hp.mOrb))).to(dev)
+        coords_dev = torch.from_numpy(np.ascontiguousarray(geo["coords"])).to(dev)
         deriv = torch.zeros((nAtom, 3), **f64)
         flush = torch.empty(256 * 1024 * 1024 // 8, **f64)          # > 126 MB L2
     stream.synchronize()
 
     def step_device():
+        # a new geometry every step: the coordinates are refreshed, so the device-side pair
+        # schedule (pair_sort.cu: histogram, scan, scatter) is rebuilt inside the timed region
+        hp.update_coords(coords_dev)
+        if hpw is not hp:
+            hpw.update_coords(coords_dev)
         hp.buildH0S(sk.selfegy, ham, over)                               # K1 (all pairs)
         hpw.derivative_shift(dm, edm, shift=shift, deriv=deriv)          # K5 (this rank's atoms)
         if world > 1:
@@ -252,7 +269,17 @@ def main():
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
                 "ms_per_launch": k1_ms, "l2": "flushed between steps (256 MB memset)"}
     kernels = {"sparseH0S": {"ms": k1_ms, "pairs_per_s": pairs / k1_ms * 1e3},
-               "forceCalc": {"ms": k5_ms, "pairs_per_s_this_rank": hpw.num_pairs / k5_ms * 1e3}}
+               "forceCalc": {"ms": k5_ms, "pairs_per_s_this_rank": hpw.num_pairs / k5_ms * 1e3,
+                             "shift": "diagonal blocks (collinear-spin SCC)"}}
+    # the same force call with full (DFTB+U-like) shift blocks: per-pair matrix products in the weights kernel
+    hpw.timer_enable(True)
+    for i in range(3):
+        hpw.derivative_shift(dm, edm, shift=shift_full, deriv=deriv)
+    tf = hpw.timer_read()
+    kernels["forceCalc_full_shift_blocks"] = {"ms": tf["forceCalc"][0] / max(1, tf["forceCalc"][1])}
+    hp.timer_enable(True)
+    if hpw is not hp:
+        hpw.timer_enable(True)
 
     # ---- e2e: the C-ABI call with HOST buffers (pinned), copies inside the timed region ----------
     def pinned(shape):

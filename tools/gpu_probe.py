@@ -90,6 +90,7 @@ def main():
         ms = timeit(lambda: hp.packHS(rho, sq), stream, n=5)
         out["k2b_ms"] = ms
         out["k2b_GBs"] = 24.0 * ss / ms / 1e6
+    if dense and "--no-k3" not in sys.argv:
         C = new_dense(nOrb)
         C.copy_(torch.randn(nOrb, nOrb, **f64) / nOrb ** 0.5)
         nocc = int(sum(sum(sk.occ[s - 1]) for s in w["species0"]) / 2)

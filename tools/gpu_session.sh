@@ -8,7 +8,9 @@ echo "== bench"; timeout 900 python bench.py 2>&1 | tail -3 | tee gpurun_out/ben
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -2 | tee gpurun_out/bench_ref_$TAG.log
 echo "== ncu launch list (bench, pair path only)"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 1 --no-dense > gpurun_out/ncu_launch_$TAG.log 2>&1
-echo "== ncu full: K1, K5, K4, K2, K3, cuBLAS dgemm"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k1_pair_build|k5_derivative|k4_mulliken|k2_unpack|k2_pack' -c 8 -o gpurun_out/prof_pairs_$TAG python tools/gpu_probe.py fec4096 --dense > gpurun_out/ncu_pairs_$TAG.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k3_dm_real|gemm|dgemm' -c 4 -o gpurun_out/prof_dm_$TAG python tools/gpu_probe.py fec1024 --dense > gpurun_out/ncu_dm_$TAG.log 2>&1
-ls -la gpurun_out | tail -20
+echo "== ncu full, one launch per kernel"
+for K in k1_pair_build k5_derivative_shift k5_force_weights k4_mulliken_orbital k2_unpack k2_pack ps_keys ps_scan ps_scatter; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 2 -c 1 -o gpurun_out/prof_${K}_$TAG python tools/gpu_probe.py fec4096 --dense --no-k3 > gpurun_out/ncu_${K}_$TAG.log 2>&1
+done
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k3_dm_real' -c 2 -o gpurun_out/prof_k3_dm_real_$TAG python tools/gpu_probe.py fec1024 --dense > gpurun_out/ncu_dm_$TAG.log 2>&1
+ls -la gpurun_out | tail -30
