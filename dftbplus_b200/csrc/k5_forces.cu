@@ -41,16 +41,19 @@ struct K5Params {
   double *deriv;
 };
 
-// flag = 1 if any off-diagonal element of any shift block is non-zero
-__global__ void k5_shift_structure(const double *__restrict__ shift, int mOrb, long long nBlocks, int *flag) {
-  const long long n = nBlocks * mOrb * mOrb;
+// flag = 1 if any off-diagonal element of any shift block is non-zero (one warp per block)
+__global__ void __launch_bounds__(256) k5_shift_structure(const double *__restrict__ shift, int mOrb, int nBlocks,
+                                                          int *flag) {
+  const int lane = threadIdx.x & 31, mo2 = mOrb * mOrb;
   bool any = false;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int inBlock = (int)(i % (mOrb * mOrb));
-    const int a = inBlock / mOrb, b = inBlock - a * mOrb;
-    if (a != b && shift[i] != 0.0) any = true;
+  for (int blk = blockIdx.x * 8 + (threadIdx.x >> 5); blk < nBlocks; blk += gridDim.x * 8) {
+    const double *__restrict__ v = shift + (size_t)mo2 * blk;
+    for (int e = lane; e < mo2; e += 32) {
+      const int a = e / mOrb, b = e - a * mOrb;
+      if (a != b && __ldg(v + e) != 0.0) any = true;
+    }
   }
-  if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+  if (__any_sync(0xffffffffu, any) && lane == 0) atomicOr(flag, 1);
 }
 
 // -wS = Erho - sum_spin 1/2 (rho_s V1_s^T + V2_s^T rho_s) for every off-site block of this rank's
@@ -68,9 +71,10 @@ struct K5WeightParams {
   double *negWS;
 };
 
-__global__ void __launch_bounds__(256) k5_force_weights(const K5WeightParams p) {
+template <bool FULL>
+__global__ void __launch_bounds__(256, 4) k5_force_weights(const K5WeightParams p) {
+  if ((__ldg(p.shiftFull) != 0) != FULL) return;  // the other instantiation handles this shift structure
   const int lane = threadIdx.x & 31;
-  const bool full = __ldg(p.shiftFull) != 0;
   const int mo2 = p.mOrb * p.mOrb;
   const long long nWarps = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < p.nWork; w += nWarps) {
@@ -82,25 +86,52 @@ __global__ void __launch_bounds__(256) k5_force_weights(const K5WeightParams p) 
     const int n1 = __ldg(p.iAtomStart + iAt1 + 1) - __ldg(p.iAtomStart + iAt1);
     const int n2 = __ldg(p.iAtomStart + iAt2f + 1) - __ldg(p.iAtomStart + iAt2f);
     const int ind = __ldg(p.iPair + flat);
-    for (int e = lane; e < n1 * n2; e += 32) {
-      const int a = e / n2, b = e - a * n2;  // element (row b, col a) of the n2 x n1 block
-      double s = __ldg(p.EDM + ind + e);
+    const int nElem = n1 * n2;
+    const unsigned M2 = (1048576u + (unsigned)n2 - 1u) / (unsigned)n2;  // e / n2 = e * M2 >> 20 (e < 256)
+    const double *__restrict__ edm = p.EDM + ind;
+    double *__restrict__ out = p.negWS + ind;
+    for (int e0 = lane; e0 < nElem; e0 += 96) {
+      // three elements per lane and pass, all loads independent
+      int e[3], a[3], b[3];
+      bool on[3];
+      double s[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        e[k] = e0 + 32 * k;
+        on[k] = e[k] < nElem;
+        if (!on[k]) e[k] = 0;
+        a[k] = (int)(((unsigned)e[k] * M2) >> 20);  // element (row b, col a) of the n2 x n1 block
+        b[k] = e[k] - a[k] * n2;
+        s[k] = __ldg(edm + e[k]);
+      }
       for (int iSpin = 0; iSpin < p.nSpin; ++iSpin) {
         const double *__restrict__ rho = p.DM + (size_t)p.sparseSize * iSpin + ind;
         const double *__restrict__ V1 = p.shift + (size_t)mo2 * (iAt1 + (size_t)p.nAtom * iSpin);
         const double *__restrict__ V2 = p.shift + (size_t)mo2 * (iAt2f + (size_t)p.nAtom * iSpin);
-        double x;
-        if (!full) {
-          x = __ldg(rho + e) * (__ldg(V1 + a + p.mOrb * a) + __ldg(V2 + b + p.mOrb * b));
+        if (!FULL) {
+          double r[3], x1[3], x2[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            r[k] = __ldg(rho + e[k]);
+            x1[k] = __ldg(V1 + a[k] * (p.mOrb + 1));
+            x2[k] = __ldg(V2 + b[k] * (p.mOrb + 1));
+          }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) s[k] = fma(-0.5 * r[k], x1[k] + x2[k], s[k]);
         } else {
           // (rho V1^T)(b,a) = sum_c rho(b,c) V1(a,c);  (V2^T rho)(b,a) = sum_c V2(c,b) rho(c,a)
-          x = 0.0;
-          for (int c = 0; c < n1; ++c) x = fma(__ldg(rho + b + n2 * c), __ldg(V1 + a + p.mOrb * c), x);
-          for (int c = 0; c < n2; ++c) x = fma(__ldg(V2 + c + p.mOrb * b), __ldg(rho + c + n2 * a), x);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            double x = 0.0;
+            for (int c = 0; c < n1; ++c) x = fma(__ldg(rho + b[k] + n2 * c), __ldg(V1 + a[k] + p.mOrb * c), x);
+            for (int c = 0; c < n2; ++c) x = fma(__ldg(V2 + c + p.mOrb * b[k]), __ldg(rho + c + n2 * a[k]), x);
+            s[k] = fma(-0.5, x, s[k]);
+          }
         }
-        s = fma(-0.5, x, s);
       }
-      p.negWS[ind + e] = s;
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (on[k]) out[e[k]] = s[k];
     }
   }
 }
@@ -248,7 +279,8 @@ extern "C" int dftbp_b200_derivative_shift(dftbp_b200_ctx *ctx, double *deriv, c
       // plain SCC / collinear spin shifts are diagonal blocks: detect it, then form -wS once per block
       int *flag = ctx->dInfo + 1;
       DFTBP_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
-      k5_shift_structure<<<ctx->smCount, 256, 0, ctx->stream>>>(dShift, ctx->mOrb, (long long)g.nAtom * nSpin, flag);
+      k5_shift_structure<<<std::min(ctx->smCount * 8, (g.nAtom * nSpin + 7) / 8), 256, 0, ctx->stream>>>(
+          dShift, ctx->mOrb, g.nAtom * nSpin, flag);
       void *scratch;
       DFTBP_TRY(stagingGet(ctx, kSlotE, sizeof(double) * (size_t)g.sparseSize, &scratch));
       K5WeightParams wp;
@@ -256,9 +288,11 @@ extern "C" int dftbp_b200_derivative_shift(dftbp_b200_ctx *ctx, double *deriv, c
       wp.nAtom = g.nAtom; wp.nSpin = nSpin; wp.sparseSize = g.sparseSize; wp.iNeighbour = g.iNeighbour;
       wp.iPair = g.iPair; wp.img2CentCell = g.img2CentCell; wp.iAtomStart = g.iAtomStart;
       wp.DM = p.DM; wp.EDM = dEDM; wp.shift = dShift; wp.shiftFull = flag; wp.negWS = (double *)scratch;
-      k5_force_weights<<<gridFor(ctx, wp.nWork, 8, 8), 256, 0, ctx->stream>>>(wp);
+      // both instantiations are launched; the one that does not match the device flag returns at once
+      k5_force_weights<false><<<gridFor(ctx, wp.nWork, 8, 4), 256, 0, ctx->stream>>>(wp);
+      k5_force_weights<true><<<gridFor(ctx, wp.nWork, 8, 4), 256, 0, ctx->stream>>>(wp);
       p.negWS = (const double *)scratch;
-      ctx->launches += 2;
+      ctx->launches += 3;
     }
     p.pitch = (ctx->mOrb * ctx->mOrb) | 1;
     const size_t perWarp = sizeof(double) * 32 * (size_t)p.pitch;

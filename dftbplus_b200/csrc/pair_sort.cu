@@ -6,7 +6,8 @@
 // and (b) sit at neighbouring distances, so that the 8-row windows of the SK tables they
 // interpolate from fall into the same one or two cache lines (broadcast loads instead of gathers).
 // A counting sort by key = (species pair, distance bin) gives both; it runs on the device in three
-// small launches (histogram, single-CTA scan with per-bucket padding to a multiple of 32, scatter)
+// small launches (histogram, single-CTA scan with per-bucket padding to a multiple of 32, scatter;
+// histogram and scatter aggregate in shared memory, one global atomic per CTA and occupied bin)
 // and is redone whenever the coordinates change.  The order inside a bin is arbitrary (atomic
 // cursors): every pair is evaluated independently and written to its own iPair offset, so the
 // results do not depend on it.
@@ -16,42 +17,64 @@ using namespace dftbp_b200;
 
 namespace {
 
-constexpr int kSortBins = 1024;  // distance bins per species pair over [0, SK cutoff]
+constexpr int kSortThreads = 1024;  // one big CTA aggregates many items per histogram bin in shared memory
 
-__global__ void __launch_bounds__(256) ps_keys(const int *__restrict__ work, long long nWork, int ld,
-                                               int nSpecies, const double *__restrict__ coords,
-                                               const int *__restrict__ species,
-                                               const int *__restrict__ iNeighbour, double binScale,
-                                               int *__restrict__ keys, int *__restrict__ hist) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nWork) return;
-  const int flat = __ldg(work + i);
+// distance bins per species pair over [0, SK cutoff]: as fine as the shared-memory histogram allows
+// (1024 bins = 0.011 bohr at an 11 bohr cutoff, half a table row; 64 bins still keep a warp within
+// a few rows)
+int binsFor(int nBuckets) { return nBuckets <= 8 ? 1024 : nBuckets <= 32 ? 256 : nBuckets <= 128 ? 64 : 16; }
+
+__device__ __forceinline__ int pairKey(int flat, int ld, int nSpecies, int nBins, double binScale,
+                                       const double *__restrict__ coords, const int *__restrict__ species,
+                                       const int *__restrict__ iNeighbour) {
   const int iAt1 = flat / ld, iNeigh = flat - iAt1 * ld;
-  if (iNeigh == 0) {  // on-site blocks are not pairs
-    keys[i] = -1;
-    return;
-  }
+  if (iNeigh == 0) return -1;  // on-site blocks are not pairs
   const int iAt2 = __ldg(iNeighbour + flat) - 1;
   const int sp1 = __ldg(species + iAt1) - 1, sp2 = __ldg(species + iAt2) - 1;
   const double vx = __ldg(coords + 3 * iAt2) - __ldg(coords + 3 * iAt1);
   const double vy = __ldg(coords + 3 * iAt2 + 1) - __ldg(coords + 3 * iAt1 + 1);
   const double vz = __ldg(coords + 3 * iAt2 + 2) - __ldg(coords + 3 * iAt1 + 2);
   const double r = sqrt(vx * vx + vy * vy + vz * vz);
-  const int bin = min(kSortBins - 1, max(0, (int)(r * binScale)));
-  const int key = (sp1 + nSpecies * sp2) * kSortBins + bin;
-  keys[i] = key;
-  atomicAdd(hist + key, 1);
+  const int bin = min(nBins - 1, max(0, (int)(r * binScale)));
+  return (sp1 + nSpecies * sp2) * nBins + bin;
 }
 
-// one CTA of kSortBins threads: exclusive scan bucket by bucket, every bucket starts on a multiple of 32
-__global__ void __launch_bounds__(kSortBins) ps_scan(int *__restrict__ hist, int nBuckets, int *__restrict__ total) {
+// pass 1: key of every work item + histogram.  Each CTA owns a contiguous slab of the work list and
+// counts in shared memory first, so only one global atomic per (CTA, occupied bin) remains --
+// crystalline systems put thousands of pairs into the same few bins.
+__global__ void __launch_bounds__(kSortThreads) ps_keys(const int *__restrict__ work, long long nWork, int ld,
+                                                        int nSpecies, int nBins, int nKeys,
+                                                        const double *__restrict__ coords,
+                                                        const int *__restrict__ species,
+                                                        const int *__restrict__ iNeighbour, double binScale,
+                                                        int *__restrict__ keys, int *__restrict__ hist) {
+  extern __shared__ int sh[];
+  for (int k = threadIdx.x; k < nKeys; k += kSortThreads) sh[k] = 0;
+  __syncthreads();
+  const long long per = (nWork + gridDim.x - 1) / gridDim.x;
+  const long long lo = per * blockIdx.x, hi = min(nWork, lo + per);
+  for (long long i = lo + threadIdx.x; i < hi; i += kSortThreads) {
+    const int key = pairKey(__ldg(work + i), ld, nSpecies, nBins, binScale, coords, species, iNeighbour);
+    keys[i] = key;
+    if (key >= 0) atomicAdd(sh + key, 1);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nKeys; k += kSortThreads) {
+    const int c = sh[k];
+    if (c) atomicAdd(hist + k, c);
+  }
+}
+
+// one CTA: exclusive scan bucket by bucket (nBins entries each), every bucket starts on a multiple of 32
+__global__ void __launch_bounds__(1024) ps_scan(int *__restrict__ hist, int nBuckets, int nBins,
+                                                int *__restrict__ total) {
   __shared__ int warpSum[32];
   __shared__ int baseSh;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   if (t == 0) baseSh = 0;
   __syncthreads();
   for (int b = 0; b < nBuckets; ++b) {
-    const int v = hist[b * kSortBins + t];
+    const int v = t < nBins ? hist[b * nBins + t] : 0;
     int x = v;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -72,23 +95,38 @@ __global__ void __launch_bounds__(kSortBins) ps_scan(int *__restrict__ hist, int
     __syncthreads();
     const int base = baseSh;
     const int incl = x + (w > 0 ? warpSum[w - 1] : 0);
-    hist[b * kSortBins + t] = base + incl - v;
+    if (t < nBins) hist[b * nBins + t] = base + incl - v;
     __syncthreads();
-    if (t == kSortBins - 1) baseSh = (base + incl + 31) & ~31;
+    if (t == 1023) baseSh = (base + incl + 31) & ~31;
     __syncthreads();
   }
   if (t == 0) *total = baseSh;
 }
 
-__global__ void __launch_bounds__(256) ps_scatter(const int *__restrict__ work, long long nWork,
-                                                  const int *__restrict__ keys, int *__restrict__ cursors,
-                                                  int *__restrict__ items) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nWork) return;
-  const int key = keys[i];
-  if (key < 0) return;
-  const int pos = atomicAdd(cursors + key, 1);
-  items[pos] = __ldg(work + i);
+// pass 2: every CTA counts its slab again (from the stored keys), reserves one contiguous range
+// per occupied bin with a single global atomic, and places its items with shared-memory atomics
+__global__ void __launch_bounds__(kSortThreads) ps_scatter(const int *__restrict__ work, long long nWork,
+                                                           int nKeys, const int *__restrict__ keys,
+                                                           int *__restrict__ cursors, int *__restrict__ items) {
+  extern __shared__ int sh[];
+  for (int k = threadIdx.x; k < nKeys; k += kSortThreads) sh[k] = 0;
+  __syncthreads();
+  const long long per = (nWork + gridDim.x - 1) / gridDim.x;
+  const long long lo = per * blockIdx.x, hi = min(nWork, lo + per);
+  for (long long i = lo + threadIdx.x; i < hi; i += kSortThreads) {
+    const int key = keys[i];
+    if (key >= 0) atomicAdd(sh + key, 1);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nKeys; k += kSortThreads) {
+    const int c = sh[k];
+    if (c) sh[k] = atomicAdd(cursors + k, c);  // count -> first position of this CTA's range
+  }
+  __syncthreads();
+  for (long long i = lo + threadIdx.x; i < hi; i += kSortThreads) {
+    const int key = keys[i];
+    if (key >= 0) items[atomicAdd(sh + key, 1)] = __ldg(work + i);
+  }
 }
 
 template <class T>
@@ -130,7 +168,10 @@ int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out
   const int *work = (forLoad && !shared) ? g.workLoad : g.workMine;
   const long long nWork = (forLoad && !shared) ? g.nWorkLoad : g.nWorkMine;
   const int nBuckets = ctx->nSpecies * ctx->nSpecies;
-  const long long nBins = (long long)nBuckets * kSortBins;
+  const int nBins = binsFor(nBuckets);
+  const long long nBins64 = (long long)nBuckets * nBins;
+  DFTBP_CHECK(ctx, nBins64 * sizeof(int) <= ctx->smemOptin - 1024, "too many species pairs for the pair schedule");
+  const int nKeys = (int)nBins64;
   const long long cap = ((nWork + 31) & ~31LL) + 32LL * nBuckets + 32;
   if (sp.capacity < cap) {
     if (sp.items) cudaFree(sp.items);
@@ -141,16 +182,22 @@ int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out
   }
   if (!sp.total) DFTBP_CUDA(ctx, cudaMalloc((void **)&sp.total, sizeof(int)));
   DFTBP_TRY(growTo(ctx, &ctx->sortKeys, &ctx->sortKeysCap, std::max(nWork, 1LL)));
-  DFTBP_TRY(growTo(ctx, &ctx->sortBins, &ctx->sortBinsCap, nBins));
-  DFTBP_CUDA(ctx, cudaMemsetAsync(ctx->sortBins, 0, sizeof(int) * nBins, ctx->stream));
+  DFTBP_TRY(growTo(ctx, &ctx->sortBins, &ctx->sortBinsCap, nBins64));
+  DFTBP_CUDA(ctx, cudaMemsetAsync(ctx->sortBins, 0, sizeof(int) * nBins64, ctx->stream));
   DFTBP_CUDA(ctx, cudaMemsetAsync(sp.items, 0xFF, sizeof(int) * sp.capacity, ctx->stream));
-  const double binScale = (double)kSortBins / (ctx->cutoff > 0.0 ? ctx->cutoff : 1.0);
+  const double binScale = (double)nBins / (ctx->cutoff > 0.0 ? ctx->cutoff : 1.0);
   if (nWork > 0) {
-    const int grid = (int)((nWork + 255) / 256);
-    ps_keys<<<grid, 256, 0, ctx->stream>>>(work, nWork, g.mNeigh + 1, ctx->nSpecies, g.coords, g.species,
-                                           g.iNeighbour, binScale, ctx->sortKeys, ctx->sortBins);
-    ps_scan<<<1, kSortBins, 0, ctx->stream>>>(ctx->sortBins, nBuckets, sp.total);
-    ps_scatter<<<grid, 256, 0, ctx->stream>>>(work, nWork, ctx->sortKeys, ctx->sortBins, sp.items);
+    // slabs of at least 2048 items per CTA (aggregation), at most one CTA per SM
+    const int grid = (int)std::max<long long>(1, std::min<long long>(ctx->smCount, (nWork + 2047) / 2048));
+    const size_t smemBytes = sizeof(int) * (size_t)nKeys;
+    DFTBP_CUDA(ctx, cudaFuncSetAttribute(ps_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+    DFTBP_CUDA(ctx, cudaFuncSetAttribute(ps_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+    ps_keys<<<grid, kSortThreads, smemBytes, ctx->stream>>>(work, nWork, g.mNeigh + 1, ctx->nSpecies, nBins, nKeys,
+                                                           g.coords, g.species, g.iNeighbour, binScale,
+                                                           ctx->sortKeys, ctx->sortBins);
+    ps_scan<<<1, 1024, 0, ctx->stream>>>(ctx->sortBins, nBuckets, nBins, sp.total);
+    ps_scatter<<<grid, kSortThreads, smemBytes, ctx->stream>>>(work, nWork, nKeys, ctx->sortKeys, ctx->sortBins,
+                                                              sp.items);
     ctx->launches += 3;
   } else {
     DFTBP_CUDA(ctx, cudaMemsetAsync(sp.total, 0, sizeof(int), ctx->stream));
