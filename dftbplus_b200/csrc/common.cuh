@@ -58,6 +58,8 @@ struct SortedPairs {
   bool valid = false;     // false after set_geometry / update_coords
 };
 
+struct BlockDesc;  // block_desc.cuh
+
 struct Geometry {
   int nAtom = 0, nAllAtom = 0, mNeigh = 0, nCellVec = 0, sparseSize = 0, nOrb = 0;
   double *coords = nullptr;      // (3, nAllAtom)
@@ -72,6 +74,8 @@ struct Geometry {
   int *workAll = nullptr;        // flat (iNeigh + ld*iAtom0) of every block (iNeigh >= 0), all atoms
   int *workMine = nullptr;       // same, this rank's contiguous atom chunk (build_*)
   int *workLoad = nullptr;       // same, this rank's workload-balanced atoms (mulliken, forces)
+  BlockDesc *descAll = nullptr;  // resolved index chain of every entry of workAll (block_desc.cuh)
+  BlockDesc *descLoad = nullptr; // same for workLoad (== descAll on one rank)
   long long nWorkAll = 0, nWorkMine = 0, nWorkLoad = 0, nPairsMine = 0;
   bool hasDuplicates = false;    // two blocks of one atom fold onto the same dense block
   int firstAtomMine = 0, lastAtomMine = -1;  // 0-based inclusive atom chunk of workMine

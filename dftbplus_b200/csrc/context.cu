@@ -2,7 +2,7 @@
 #include <algorithm>
 #include <cmath>
 
-#include "common.cuh"
+#include "block_desc.cuh"
 #include "sk_gaunt_tables.h"
 
 using namespace dftbp_b200;
@@ -67,6 +67,8 @@ void freeGeometry(Geometry &g) {
   if (g.workMine != g.workAll) cudaFree(g.workMine);
   if (g.workLoad != g.workAll) cudaFree(g.workLoad);
   cudaFree(g.workAll);
+  if (g.descLoad != g.descAll) cudaFree(g.descLoad);
+  cudaFree(g.descAll);
   g = Geometry();
 }
 
@@ -369,7 +371,8 @@ int dftbp_b200_set_geometry(dftbp_b200_ctx *ctx, int nAtom, int nAllAtom, int mN
   const int ld = mNeigh + 1;
   std::vector<int> hN = toHost(nNeighbourSK, nAtom), hNb = toHost(iNeighbour, (size_t)ld * nAtom);
   std::vector<int> hImg = toHost(img2CentCell, nAllAtom), hSp = toHost(species, nAllAtom);
-  std::vector<int> hStart = toHost(iAtomStart, nAtom + 1);
+  std::vector<int> hStart = toHost(iAtomStart, nAtom + 1), hPair = toHost(iPair, (size_t)ld * nAtom);
+  std::vector<int> hVec = toHost(iCellVec, nAllAtom);
   for (int i = 0; i < nAtom; ++i) {
     DFTBP_CHECK(ctx, hN[i] >= 0 && hN[i] <= mNeigh, "set_geometry: nNeighbourSK exceeds mNeigh");
     DFTBP_CHECK(ctx, hSp[i] >= 1 && hSp[i] <= ctx->nSpecies, "set_geometry: species out of range");
@@ -378,6 +381,8 @@ int dftbp_b200_set_geometry(dftbp_b200_ctx *ctx, int nAtom, int nAllAtom, int mN
     for (int k = 0; k <= hN[i]; ++k) {
       int a2 = hNb[k + (size_t)ld * i];
       DFTBP_CHECK(ctx, a2 >= 1 && a2 <= nAllAtom, "set_geometry: iNeighbour entry out of range");
+      DFTBP_CHECK(ctx, hImg[a2 - 1] >= 1 && hImg[a2 - 1] <= nAtom, "set_geometry: img2CentCell entry out of range");
+      DFTBP_CHECK(ctx, hVec[a2 - 1] >= 1 && hVec[a2 - 1] <= nCellVec, "set_geometry: iCellVec entry out of range");
     }
   }
   Geometry g;
@@ -408,8 +413,31 @@ int dftbp_b200_set_geometry(dftbp_b200_ctx *ctx, int nAtom, int nAllAtom, int mN
   }
   DFTBP_TRY(uploadNew(ctx, &g.workAll, all.data(), all.size()));
   g.nWorkAll = (long long)all.size();
+  // resolve iNeighbour -> img2CentCell -> iAtomStart / iCellVec / iPair once per geometry (block_desc.cuh)
+  auto describe = [&](const std::vector<int> &work) {
+    std::vector<BlockDesc> d(work.size());
+    for (size_t w = 0; w < work.size(); ++w) {
+      const int flat = work[w], i = flat / ld, k = flat - i * ld;
+      const int a2 = hNb[flat] - 1, f = hImg[a2] - 1;
+      BlockDesc &b = d[w];
+      b.ind = hPair[flat];
+      b.ii = hStart[i] - 1;
+      b.jj = hStart[f] - 1;
+      b.n12 = (hStart[i + 1] - hStart[i]) | ((hStart[f + 1] - hStart[f]) << 8);
+      b.iAt1 = i;
+      b.iAt2f = f;
+      b.iVec = hVec[a2] - 1;
+      b.iNeigh = k;
+    }
+    return d;
+  };
+  {
+    std::vector<BlockDesc> d = describe(all);
+    DFTBP_TRY(uploadNew(ctx, &g.descAll, d.data(), d.size()));
+  }
   if (ctx->nRanks == 1) {
     g.workMine = g.workLoad = g.workAll;
+    g.descLoad = g.descAll;
     g.nWorkMine = g.nWorkLoad = g.nWorkAll;
     g.nPairsMine = g.nWorkAll - nAtom;
     g.firstAtomMine = 0;
@@ -429,6 +457,10 @@ int dftbp_b200_set_geometry(dftbp_b200_ctx *ctx, int nAtom, int nAllAtom, int mN
     }
     DFTBP_TRY(uploadNew(ctx, &g.workMine, mine.data(), mine.size()));
     DFTBP_TRY(uploadNew(ctx, &g.workLoad, load.data(), load.size()));
+    {
+      std::vector<BlockDesc> d = describe(load);
+      DFTBP_TRY(uploadNew(ctx, &g.descLoad, d.data(), d.size()));
+    }
     g.nWorkMine = (long long)mine.size();
     g.nWorkLoad = (long long)load.size();
     g.nPairsMine = g.nWorkMine - std::max(0, last - first + 1);

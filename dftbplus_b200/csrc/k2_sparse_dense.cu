@@ -1,8 +1,11 @@
 // k2_sparse_dense.cu -- unpackHS / packHS (dftb/sparse2dense.F90:185-321, 820-918, 1024-1096).
 //
-// HBM-streaming kernels, one warp per sparse block, lane e <-> element e of the column-major
-// block: the sparse side is read / written as contiguous runs, the dense side as nOrb2-long
-// column segments.  The Bloch phase exp(+-i 2 pi k.cellVec) is one sincospi per block.
+// HBM-streaming kernels.  A warp walks through a chunk of consecutive sparse blocks (block_desc.cuh: the
+// iNeighbour -> img2CentCell -> iAtomStart chain is resolved once per geometry, so no dependent
+// index loads sit in front of the data), lane e <-> element e of the column-major block: the sparse
+// side is read / written as contiguous runs, the dense side as nOrb2-long column segments.  The
+// loads of a block are issued together before the first use.  The Bloch phase
+// exp(+-i 2 pi k.cellVec) is one sincospi per block.
 //
 // unpack: the dense matrix is zero-filled first (the reference does square(:,:) = 0).  Blocks of
 // one atom that fold onto the same dense block (several periodic images of one neighbour, or a
@@ -10,39 +13,21 @@
 // only then are the adds atomic, otherwise they are plain stores.
 // pack: pure gather + read-modify-write of the sparse array (it ACCUMULATES, like the reference);
 // the on-site block is symmetrised / hermitised from its lower triangle (:1084-1088, :906-910).
-#include "common.cuh"
+#include "block_desc.cuh"
 
 using namespace dftbp_b200;
 
 namespace {
 
 struct K2Params {
-  const int *work;
+  const BlockDesc *desc;
   long long nWork;
-  int ld, ldSq;
-  const int *iNeighbour, *iPair, *img2CentCell, *iAtomStart, *iCellVec;
+  int ldSq;
   const double *cellVec;
   double k0, k1, k2, kWeight;
 };
 
-struct BlockInfo {
-  int iAt1, iAt2f, ii, jj, n1, n2, ind, iVec;
-};
-
-__device__ __forceinline__ BlockInfo blockInfo(const K2Params &p, long long w) {
-  BlockInfo b;
-  const int flat = __ldg(p.work + w);
-  b.iAt1 = flat / p.ld;
-  const int iAt2 = __ldg(p.iNeighbour + flat) - 1;
-  b.iAt2f = __ldg(p.img2CentCell + iAt2) - 1;
-  b.ii = __ldg(p.iAtomStart + b.iAt1) - 1;
-  b.n1 = __ldg(p.iAtomStart + b.iAt1 + 1) - 1 - b.ii;
-  b.jj = __ldg(p.iAtomStart + b.iAt2f) - 1;
-  b.n2 = __ldg(p.iAtomStart + b.iAt2f + 1) - 1 - b.jj;
-  b.ind = __ldg(p.iPair + flat);
-  b.iVec = __ldg(p.iCellVec + iAt2) - 1;
-  return b;
-}
+constexpr int kUnroll = 3;  // 96 elements per pass: one pass for anything up to spd-spd (81)
 
 // exp(i * sign * 2 pi k . cellVec)
 __device__ __forceinline__ void blochPhase(const K2Params &p, int iVec, double sign, double *re, double *im) {
@@ -55,69 +40,100 @@ template <bool CPLX, bool ATOMIC>
 __global__ void __launch_bounds__(256) k2_unpack(const K2Params p, const double *__restrict__ orig,
                                                  double *__restrict__ square) {
   const int lane = threadIdx.x & 31;
-  const long long nWarps = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < p.nWork; w += nWarps) {
-    const BlockInfo b = blockInfo(p, w);
-    double pr = 1.0, pi = 0.0;
-    if (CPLX) blochPhase(p, b.iVec, 1.0, &pr, &pi);
-    const int nElem = b.n1 * b.n2;
-    for (int e = lane; e < nElem; e += 32) {
-      const int a = e / b.n2, r = e - a * b.n2;
-      const double v = __ldg(orig + b.ind + e);
-      const size_t pos = (size_t)(b.jj + r) + (size_t)p.ldSq * (b.ii + a);
-      if (CPLX) {
-        if (ATOMIC) {
-          atomicAdd(square + 2 * pos, pr * v);
-          atomicAdd(square + 2 * pos + 1, pi * v);
-        } else {
-          reinterpret_cast<double2 *>(square)[pos] = make_double2(pr * v, pi * v);
+  forEachBlock(
+      p.desc, p.nWork, [] {},
+      [&](const BlockDesc &b) {
+        double pr = 1.0, pi = 0.0;
+        if (CPLX) blochPhase(p, b.iVec, 1.0, &pr, &pi);
+        const int n2 = b.n12 >> 8, nElem = (b.n12 & 0xFF) * n2;
+        const unsigned M2 = (1048576u + (unsigned)n2 - 1u) / (unsigned)n2;  // e / n2 = e * M2 >> 20 (e < 256)
+        for (int e0 = lane; e0 < nElem; e0 += 32 * kUnroll) {
+          double v[kUnroll];
+#pragma unroll
+          for (int k = 0; k < kUnroll; ++k) {
+            const int e = e0 + 32 * k;
+            v[k] = e < nElem ? __ldg(orig + b.ind + e) : 0.0;
+          }
+#pragma unroll
+          for (int k = 0; k < kUnroll; ++k) {
+            const int e = e0 + 32 * k;
+            if (e >= nElem) break;
+            const int a = (int)(((unsigned)e * M2) >> 20), r = e - a * n2;
+            const size_t pos = (size_t)(b.jj + r) + (size_t)p.ldSq * (b.ii + a);
+            if (CPLX) {
+              if (ATOMIC) {
+                atomicAdd(square + 2 * pos, pr * v[k]);
+                atomicAdd(square + 2 * pos + 1, pi * v[k]);
+              } else {
+                reinterpret_cast<double2 *>(square)[pos] = make_double2(pr * v[k], pi * v[k]);
+              }
+            } else {
+              if (ATOMIC) atomicAdd(square + pos, v[k]);
+              else square[pos] = v[k];
+            }
+          }
         }
-      } else {
-        if (ATOMIC) atomicAdd(square + pos, v);
-        else square[pos] = v;
-      }
-    }
-  }
+      },
+      [] {});
 }
 
 template <bool CPLX>
 __global__ void __launch_bounds__(256) k2_pack(const K2Params p, double *__restrict__ primitive,
                                                const double *__restrict__ square) {
   const int lane = threadIdx.x & 31;
-  const long long nWarps = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < p.nWork; w += nWarps) {
-    const BlockInfo b = blockInfo(p, w);
-    double pr = 1.0, pi = 0.0;
-    if (CPLX) blochPhase(p, b.iVec, -1.0, &pr, &pi);
-    const bool onsite = b.iAt1 == b.iAt2f;
-    const int nElem = b.n1 * b.n2;
-    for (int e = lane; e < nElem; e += 32) {
-      const int a = e / b.n2, r = e - a * b.n2;
-      // on-site: element above the diagonal (row < col) is taken from the lower triangle
-      const bool mirror = onsite && r < a;
-      const size_t pos = mirror ? (size_t)(b.jj + a) + (size_t)p.ldSq * (b.ii + r)
-                                : (size_t)(b.jj + r) + (size_t)p.ldSq * (b.ii + a);
-      double val;
-      if (CPLX) {
-        const double2 z = __ldg(reinterpret_cast<const double2 *>(square) + pos);
-        const double zi = mirror ? -z.y : z.y;
-        val = p.kWeight * (pr * z.x - pi * zi);
-      } else {
-        val = __ldg(square + pos);
-      }
-      primitive[b.ind + e] += val;
-    }
-  }
+  forEachBlock(
+      p.desc, p.nWork, [] {},
+      [&](const BlockDesc &b) {
+        double pr = 1.0, pi = 0.0;
+        if (CPLX) blochPhase(p, b.iVec, -1.0, &pr, &pi);
+        const bool onsite = b.iAt1 == b.iAt2f;
+        const int n2 = b.n12 >> 8, nElem = (b.n12 & 0xFF) * n2;
+        const unsigned M2 = (1048576u + (unsigned)n2 - 1u) / (unsigned)n2;
+        double *__restrict__ prim = primitive + b.ind;
+        for (int e0 = lane; e0 < nElem; e0 += 32 * kUnroll) {
+          double val[kUnroll], old[kUnroll];
+#pragma unroll
+          for (int k = 0; k < kUnroll; ++k) {
+            const int e = e0 + 32 * k;
+            val[k] = 0.0;
+            old[k] = 0.0;
+            if (e < nElem) {
+              const int a = (int)(((unsigned)e * M2) >> 20), r = e - a * n2;
+              // on-site: element above the diagonal (row < col) is taken from the lower triangle
+              const bool mirror = onsite && r < a;
+              const size_t pos = mirror ? (size_t)(b.jj + a) + (size_t)p.ldSq * (b.ii + r)
+                                        : (size_t)(b.jj + r) + (size_t)p.ldSq * (b.ii + a);
+              if (CPLX) {
+                const double2 z = __ldg(reinterpret_cast<const double2 *>(square) + pos);
+                const double zi = mirror ? -z.y : z.y;
+                val[k] = p.kWeight * (pr * z.x - pi * zi);
+              } else {
+                val[k] = __ldg(square + pos);
+              }
+              old[k] = prim[e];
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < kUnroll; ++k) {
+            const int e = e0 + 32 * k;
+            if (e < nElem) prim[e] = old[k] + val[k];
+          }
+        }
+      },
+      [] {});
 }
 
 K2Params makeParams(dftbp_b200_ctx *ctx, int ldSq, const double *k, double kWeight) {
   const Geometry &g = ctx->geo;
   K2Params p;
-  p.work = g.workAll; p.nWork = g.nWorkAll; p.ld = g.mNeigh + 1; p.ldSq = ldSq;
-  p.iNeighbour = g.iNeighbour; p.iPair = g.iPair; p.img2CentCell = g.img2CentCell;
-  p.iAtomStart = g.iAtomStart; p.iCellVec = g.iCellVec; p.cellVec = g.cellVec;
+  p.desc = g.descAll; p.nWork = g.nWorkAll; p.ldSq = ldSq; p.cellVec = g.cellVec;
   p.k0 = k ? k[0] : 0.0; p.k1 = k ? k[1] : 0.0; p.k2 = k ? k[2] : 0.0; p.kWeight = kWeight;
   return p;
+}
+
+// one chunk of blocks per warp and pass; enough CTAs to fill the machine, 8 resident per SM
+int gridForChunks(const dftbp_b200_ctx *ctx, long long nBlocks) {
+  return gridFor(ctx, (nBlocks + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, 8);
 }
 
 int unpackImpl(dftbp_b200_ctx *ctx, const double *orig, const double *kPoint, void *square, int ld, bool cplx) {
@@ -134,7 +150,7 @@ int unpackImpl(dftbp_b200_ctx *ctx, const double *orig, const double *kPoint, vo
   ScopedTimer timer(ctx, kTimerSparseToDense);
   DFTBP_CUDA(ctx, cudaMemsetAsync(dSq, 0, nSq * sizeof(double), ctx->stream));
   const K2Params p = makeParams(ctx, ld, kPoint, 1.0);
-  const int grid = gridFor(ctx, p.nWork, 8, 8);
+  const int grid = gridForChunks(ctx, p.nWork);
   if (cplx) {
     if (g.hasDuplicates) k2_unpack<true, true><<<grid, 256, 0, ctx->stream>>>(p, dOrig, dSq);
     else k2_unpack<true, false><<<grid, 256, 0, ctx->stream>>>(p, dOrig, dSq);
@@ -161,7 +177,7 @@ int packImpl(dftbp_b200_ctx *ctx, double *primitive, const void *square, int ld,
   {
     ScopedTimer timer(ctx, kTimerDenseToSparse);
     const K2Params p = makeParams(ctx, ld, kPoint, kWeight);
-    const int grid = gridFor(ctx, p.nWork, 8, 8);
+    const int grid = gridForChunks(ctx, p.nWork);
     if (cplx) k2_pack<true><<<grid, 256, 0, ctx->stream>>>(p, dPrim, dSq);
     else k2_pack<false><<<grid, 256, 0, ctx->stream>>>(p, dPrim, dSq);
     ctx->launches++;

@@ -22,6 +22,7 @@
 //   2. every lane contracts its six displaced blocks against its own row of the tile;
 //   3. six atomic adds per lane.
 // FP64 CUDA-core bound (6 block evaluations per pair and matrix), not HBM bound.
+#include "block_desc.cuh"
 #include "sk_lane_eval.cuh"
 
 using namespace dftbp_b200;
@@ -62,10 +63,9 @@ __global__ void __launch_bounds__(256) k5_shift_structure(const double *__restri
 // Plain SCC and collinear-spin shifts are diagonal blocks (the device flag says so); then
 // (rho V1^T + V2^T rho)(b,a) = rho(b,a) (V1(a,a) + V2(b,b)) and no matrix product is needed.
 struct K5WeightParams {
-  const int *work;
+  const BlockDesc *desc;
   long long nWork;
-  int ld, mOrb, nAtom, nSpin, sparseSize;
-  const int *iNeighbour, *iPair, *img2CentCell, *iAtomStart;
+  int mOrb, nAtom, nSpin, sparseSize;
   const double *DM, *EDM, *shift;
   const int *shiftFull;
   double *negWS;
@@ -76,72 +76,68 @@ __global__ void __launch_bounds__(256, 4) k5_force_weights(const K5WeightParams 
   if ((__ldg(p.shiftFull) != 0) != FULL) return;  // the other instantiation handles this shift structure
   const int lane = threadIdx.x & 31;
   const int mo2 = p.mOrb * p.mOrb;
-  const long long nWarps = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < p.nWork; w += nWarps) {
-    const int flat = __ldg(p.work + w);
-    const int iAt1 = flat / p.ld;
-    if (flat - iAt1 * p.ld == 0) continue;
-    const int iAt2f = __ldg(p.img2CentCell + __ldg(p.iNeighbour + flat) - 1) - 1;
-    if (iAt1 == iAt2f) continue;
-    const int n1 = __ldg(p.iAtomStart + iAt1 + 1) - __ldg(p.iAtomStart + iAt1);
-    const int n2 = __ldg(p.iAtomStart + iAt2f + 1) - __ldg(p.iAtomStart + iAt2f);
-    const int ind = __ldg(p.iPair + flat);
-    const int nElem = n1 * n2;
-    const unsigned M2 = (1048576u + (unsigned)n2 - 1u) / (unsigned)n2;  // e / n2 = e * M2 >> 20 (e < 256)
-    const double *__restrict__ edm = p.EDM + ind;
-    double *__restrict__ out = p.negWS + ind;
-    for (int e0 = lane; e0 < nElem; e0 += 96) {
-      // three elements per lane and pass, all loads independent
-      int e[3], a[3], b[3];
-      bool on[3];
-      double s[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        e[k] = e0 + 32 * k;
-        on[k] = e[k] < nElem;
-        if (!on[k]) e[k] = 0;
-        a[k] = (int)(((unsigned)e[k] * M2) >> 20);  // element (row b, col a) of the n2 x n1 block
-        b[k] = e[k] - a[k] * n2;
-        s[k] = __ldg(edm + e[k]);
-      }
-      for (int iSpin = 0; iSpin < p.nSpin; ++iSpin) {
-        const double *__restrict__ rho = p.DM + (size_t)p.sparseSize * iSpin + ind;
-        const double *__restrict__ V1 = p.shift + (size_t)mo2 * (iAt1 + (size_t)p.nAtom * iSpin);
-        const double *__restrict__ V2 = p.shift + (size_t)mo2 * (iAt2f + (size_t)p.nAtom * iSpin);
-        if (!FULL) {
-          double r[3], x1[3], x2[3];
+  forEachBlock(
+      p.desc, p.nWork, [] {},
+      [&](const BlockDesc &blk) {
+        if (blk.iNeigh == 0 || blk.iAt1 == blk.iAt2f) return;
+        const int n1 = blk.n12 & 0xFF, n2 = blk.n12 >> 8, ind = blk.ind;
+        const int nElem = n1 * n2;
+        const unsigned M2 = (1048576u + (unsigned)n2 - 1u) / (unsigned)n2;  // e / n2 = e * M2 >> 20 (e < 256)
+        const double *__restrict__ edm = p.EDM + ind;
+        double *__restrict__ out = p.negWS + ind;
+        for (int e0 = lane; e0 < nElem; e0 += 96) {
+          // three elements per lane and pass, all loads independent
+          int e[3], a[3], b[3];
+          bool on[3];
+          double s[3];
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
-            r[k] = __ldg(rho + e[k]);
-            x1[k] = __ldg(V1 + a[k] * (p.mOrb + 1));
-            x2[k] = __ldg(V2 + b[k] * (p.mOrb + 1));
+            e[k] = e0 + 32 * k;
+            on[k] = e[k] < nElem;
+            if (!on[k]) e[k] = 0;
+            a[k] = (int)(((unsigned)e[k] * M2) >> 20);  // element (row b, col a) of the n2 x n1 block
+            b[k] = e[k] - a[k] * n2;
+            s[k] = __ldg(edm + e[k]);
+          }
+          for (int iSpin = 0; iSpin < p.nSpin; ++iSpin) {
+            const double *__restrict__ rho = p.DM + (size_t)p.sparseSize * iSpin + ind;
+            const double *__restrict__ V1 = p.shift + (size_t)mo2 * (blk.iAt1 + (size_t)p.nAtom * iSpin);
+            const double *__restrict__ V2 = p.shift + (size_t)mo2 * (blk.iAt2f + (size_t)p.nAtom * iSpin);
+            if (!FULL) {
+              double r[3], x1[3], x2[3];
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                r[k] = __ldg(rho + e[k]);
+                x1[k] = __ldg(V1 + a[k] * (p.mOrb + 1));
+                x2[k] = __ldg(V2 + b[k] * (p.mOrb + 1));
+              }
+#pragma unroll
+              for (int k = 0; k < 3; ++k) s[k] = fma(-0.5 * r[k], x1[k] + x2[k], s[k]);
+            } else {
+              // (rho V1^T)(b,a) = sum_c rho(b,c) V1(a,c);  (V2^T rho)(b,a) = sum_c V2(c,b) rho(c,a)
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                double x = 0.0;
+                for (int c = 0; c < n1; ++c) x = fma(__ldg(rho + b[k] + n2 * c), __ldg(V1 + a[k] + p.mOrb * c), x);
+                for (int c = 0; c < n2; ++c) x = fma(__ldg(V2 + c + p.mOrb * b[k]), __ldg(rho + c + n2 * a[k]), x);
+                s[k] = fma(-0.5, x, s[k]);
+              }
+            }
           }
 #pragma unroll
-          for (int k = 0; k < 3; ++k) s[k] = fma(-0.5 * r[k], x1[k] + x2[k], s[k]);
-        } else {
-          // (rho V1^T)(b,a) = sum_c rho(b,c) V1(a,c);  (V2^T rho)(b,a) = sum_c V2(c,b) rho(c,a)
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            double x = 0.0;
-            for (int c = 0; c < n1; ++c) x = fma(__ldg(rho + b[k] + n2 * c), __ldg(V1 + a[k] + p.mOrb * c), x);
-            for (int c = 0; c < n2; ++c) x = fma(__ldg(V2 + c + p.mOrb * b[k]), __ldg(rho + c + n2 * a[k]), x);
-            s[k] = fma(-0.5, x, s[k]);
-          }
+          for (int k = 0; k < 3; ++k)
+            if (on[k]) out[e[k]] = s[k];
         }
-      }
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        if (on[k]) out[e[k]] = s[k];
-    }
-  }
+      },
+      [] {});
 }
 
 template <int LMAX>
-__global__ void __launch_bounds__(256, 1) k5_derivative_shift(const K5Params p) {
+__global__ void __launch_bounds__(320, 1) k5_derivative_shift(const K5Params p) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wIn = threadIdx.x >> 5, nW = blockDim.x >> 5;
   double *stage = smem + (size_t)wIn * 32 * p.pitch;
-  const double *row = stage + (size_t)lane * p.pitch;
+  double *row = stage + (size_t)lane * p.pitch;
   const int nChunks = __ldg(p.total) >> 5;
   const int nItems = 2 * nChunks;
   for (int item = blockIdx.x * nW + wIn; item < nItems; item += gridDim.x * nW) {
@@ -190,12 +186,14 @@ __global__ void __launch_bounds__(256, 1) k5_derivative_shift(const K5Params p) 
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
 
-    // ---- 2. six displaced evaluations, contracted on the fly
+    // ---- 2. fold the weights of this lane's pair into W (independent of the bond vector), then six
+    // displaced evaluations, each an interpolation + harmonics + short dot product (sk_lane_eval.cuh)
     const double v0 = __ldg(p.coords + 3 * iAt2) - __ldg(p.coords + 3 * iAt1);
     const double v1 = __ldg(p.coords + 3 * iAt2 + 1) - __ldg(p.coords + 3 * iAt1 + 1);
     const double v2 = __ldg(p.coords + 3 * iAt2 + 2) - __ldg(p.coords + 3 * iAt1 + 2);
     double g0 = 0.0, g1 = 0.0, g2 = 0.0;
     if (__any_sync(0xffffffffu, live)) {
+      if (live) skLaneWBuildAny<LMAX>(pg, row);
 #pragma unroll 1
       for (int k = 0; k < 6; ++k) {
         const int jj = k >> 1;
@@ -206,10 +204,7 @@ __global__ void __launch_bounds__(256, 1) k5_derivative_shift(const K5Params p) 
         const double d2 = jj == 2 ? v2 + sgn * p.delta : v2;
         const double dist = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
         const double rinv = 1.0 / dist;
-        double acc = 0.0;
-        skLaneEvalAny<LMAX>(
-            pg, tab, dist, d0 * rinv, d1 * rinv, d2 * rinv,
-            [&](int first, int e, double x) { acc = fma(row[first + e], x, acc); }, [](int, int) {});
+        double acc = live ? skLaneWDotAny<LMAX>(pg, tab, dist, d0 * rinv, d1 * rinv, d2 * rinv, row) : 0.0;
         acc *= isS ? sgn : -sgn;  // (tmp(ii=2) - tmp(ii=1)); the S tile holds -wS
         if (jj == 0) g0 += acc;
         if (jj == 1) g1 += acc;
@@ -232,9 +227,14 @@ __global__ void __launch_bounds__(256, 1) k5_derivative_shift(const K5Params p) 
 }
 
 template <int LMAX>
-int launchTyped(dftbp_b200_ctx *ctx, const K5Params &p, int grid, int warps, size_t smemBytes) {
+int launchTyped(dftbp_b200_ctx *ctx, const K5Params &p, long long items, int warps, size_t smemBytes) {
   DFTBP_CUDA(ctx, cudaFuncSetAttribute(k5_derivative_shift<LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smemBytes));
+  int perSm = 1;  // resident CTAs per SM (registers and the weight tile decide)
+  DFTBP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k5_derivative_shift<LMAX>, 32 * warps,
+                                                                smemBytes));
+  const int grid = (int)std::max<long long>(
+      1, std::min<long long>((items + warps - 1) / warps, (long long)ctx->smCount * std::max(perSm, 1)));
   k5_derivative_shift<LMAX><<<grid, 32 * warps, smemBytes, ctx->stream>>>(p);
   return 0;
 }
@@ -284,27 +284,27 @@ extern "C" int dftbp_b200_derivative_shift(dftbp_b200_ctx *ctx, double *deriv, c
       void *scratch;
       DFTBP_TRY(stagingGet(ctx, kSlotE, sizeof(double) * (size_t)g.sparseSize, &scratch));
       K5WeightParams wp;
-      wp.work = g.workLoad; wp.nWork = g.nWorkLoad; wp.ld = g.mNeigh + 1; wp.mOrb = ctx->mOrb;
-      wp.nAtom = g.nAtom; wp.nSpin = nSpin; wp.sparseSize = g.sparseSize; wp.iNeighbour = g.iNeighbour;
-      wp.iPair = g.iPair; wp.img2CentCell = g.img2CentCell; wp.iAtomStart = g.iAtomStart;
+      wp.desc = g.descLoad; wp.nWork = g.nWorkLoad; wp.mOrb = ctx->mOrb;
+      wp.nAtom = g.nAtom; wp.nSpin = nSpin; wp.sparseSize = g.sparseSize;
       wp.DM = p.DM; wp.EDM = dEDM; wp.shift = dShift; wp.shiftFull = flag; wp.negWS = (double *)scratch;
+      const int wGrid = gridFor(ctx, (wp.nWork + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, 4);
       // both instantiations are launched; the one that does not match the device flag returns at once
-      k5_force_weights<false><<<gridFor(ctx, wp.nWork, 8, 4), 256, 0, ctx->stream>>>(wp);
-      k5_force_weights<true><<<gridFor(ctx, wp.nWork, 8, 4), 256, 0, ctx->stream>>>(wp);
+      k5_force_weights<false><<<wGrid, 256, 0, ctx->stream>>>(wp);
+      k5_force_weights<true><<<wGrid, 256, 0, ctx->stream>>>(wp);
       p.negWS = (const double *)scratch;
       ctx->launches += 3;
     }
     p.pitch = (ctx->mOrb * ctx->mOrb) | 1;
     const size_t perWarp = sizeof(double) * 32 * (size_t)p.pitch;
-    int warps = (int)std::min<size_t>(8, (ctx->smemOptin - 2048) / perWarp);
+    // 10 warps x <= 204 registers fill the register file; the weight tile usually limits first
+    int warps = (int)std::min<size_t>(10, (ctx->smemOptin - 2048) / perWarp);
     DFTBP_CHECK(ctx, warps >= 1, "derivative_shift: weight tile does not fit into shared memory");
     const size_t smemBytes = perWarp * warps;
     const long long items = 2 * ((g.nWorkLoad + 31) / 32 + ctx->nSpecies * ctx->nSpecies);
-    const int grid = (int)std::max<long long>(1, std::min<long long>((items + warps - 1) / warps, ctx->smCount));
     int rc;
-    if (ctx->lMaxAll <= 1) rc = launchTyped<1>(ctx, p, grid, warps, smemBytes);
-    else if (ctx->lMaxAll == 2) rc = launchTyped<2>(ctx, p, grid, warps, smemBytes);
-    else rc = launchTyped<3>(ctx, p, grid, warps, smemBytes);
+    if (ctx->lMaxAll <= 1) rc = launchTyped<1>(ctx, p, items, warps, smemBytes);
+    else if (ctx->lMaxAll == 2) rc = launchTyped<2>(ctx, p, items, warps, smemBytes);
+    else rc = launchTyped<3>(ctx, p, items, warps, smemBytes);
     if (rc) return rc;
     ctx->launches++;
   }

@@ -234,4 +234,143 @@ __device__ __forceinline__ void skLaneEvalAny(const SpPairProg &pg, const SkTabl
   }
 }
 
+
+// ---- weight-contracted form (K5) ---------------------------------------------------------------------
+// A contraction sum_e w_e E_e(d) of the block with fixed weights w (rho, E-rho, ...) is
+//   sum over shell pairs, k:  A_k(r) * sum_M W_(k,M) S_(L_k M)(d),   W_(k,M) = sum_(a,b) G_k(a,b;M) w(a,b),
+// and W does not depend on the bond vector.  The force kernel evaluates the block at six displaced
+// bond vectors per pair (getFirstDerivFiniteDiff, dftb/nonscc.F90:428-484): it folds the weights
+// into W once (skLaneWBuild, in place in the lane's row: W of a shell pair is never longer than
+// the sub-block it replaces) and every displaced evaluation is then interpolation + harmonics + a
+// (lmin + 1)(2 lmax + 1)-term dot product per shell pair instead of a full rotation.
+
+// row[e] = weight of block element e (column-major nOrb2 x nOrb1) -> W, in place; generic shells
+template <int LMAX>
+__device__ __forceinline__ void skLaneWBuild(const SpPairProg &pg, double *row) {
+  int iCol = 0;
+  const int nSh1 = pg.nSh1, nSh2 = pg.nSh2, n2 = pg.nOrb2;
+  const unsigned long long sh1s = pg.shells1, sh2s = pg.shells2;
+  for (int sh1 = 0; sh1 < nSh1; ++sh1) {
+    const int l1 = (int)((sh1s >> (4 * sh1)) & 0xF);
+    int iRow = 0;
+    for (int sh2 = 0; sh2 < nSh2; ++sh2) {
+      const int l2 = (int)((sh2s >> (4 * sh2)) & 0xF);
+      double *sub = row + iRow + n2 * iCol;
+      skg::wbuildDispatch<LMAX>(
+          l1, l2, [&](int a, int b) { return sub[b + n2 * a]; }, [&](int a, int b, double v) { sub[b + n2 * a] = v; });
+      iRow += 2 * l2 + 1;
+    }
+    iCol += 2 * l1 + 1;
+  }
+}
+
+// sum_e w_e E_e for table t at distance r along (dx, dy, dz); row holds W (skLaneWBuild)
+template <int LMAX>
+__device__ __forceinline__ double skLaneWDot(const SpPairProg &pg, const SkTableDev &t, double r, double dx,
+                                             double dy, double dz, const double *row) {
+  LaneInterp li;
+  laneInterpSetup(t, r, li);
+  double Y[(2 * LMAX + 1) * (2 * LMAX + 1)];
+  skg::harmonics<2 * LMAX>(dx, dy, dz, Y);
+  int ind = 0, iCol = 0;
+  const int nSh1 = pg.nSh1, nSh2 = pg.nSh2, n2 = pg.nOrb2;
+  const unsigned long long sh1s = pg.shells1, sh2s = pg.shells2;
+  double acc = 0.0;
+  for (int sh1 = 0; sh1 < nSh1; ++sh1) {
+    const int l1 = (int)((sh1s >> (4 * sh1)) & 0xF);
+    int iRow = 0;
+    for (int sh2 = 0; sh2 < nSh2; ++sh2) {
+      const int l2 = (int)((sh2s >> (4 * sh2)) & 0xF);
+      const int lmin = min(l1, l2);
+      double v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = (k <= LMAX && k <= lmin) ? laneInterp(t, li, ind + k) : 0.0;
+      const double *sub = row + iRow + n2 * iCol;
+      acc += skg::wdotDispatch<LMAX>(l1, l2, Y, v, [&](int a, int b) { return sub[b + n2 * a]; });
+      ind += lmin + 1;
+      iRow += 2 * l2 + 1;
+    }
+    iCol += 2 * l1 + 1;
+  }
+  return acc;
+}
+
+template <int LM1, int LM2>
+__device__ __forceinline__ void skLaneWBuildCanon(double *row) {
+  constexpr int N2 = (LM2 + 1) * (LM2 + 1);
+  staticFor<LM1 + 1>([&](auto l1c) {
+    constexpr int l1 = decltype(l1c)::value;
+    staticFor<LM2 + 1>([&](auto l2c) {
+      constexpr int l2 = decltype(l2c)::value;
+      double *sub = row + l2 * l2 + N2 * l1 * l1;
+      skg::wbuildT<l1, l2>([&](int a, int b) { return sub[b + N2 * a]; },
+                           [&](int a, int b, double v) { sub[b + N2 * a] = v; });
+    });
+  });
+}
+
+template <int LM1, int LM2>
+__device__ __forceinline__ double skLaneWDotCanon(const SkTableDev &t, double r, double dx, double dy, double dz,
+                                                  const double *row) {
+  constexpr int LY = LM1 + LM2;
+  constexpr int N2 = (LM2 + 1) * (LM2 + 1);
+  constexpr int NI = canonIntegStart(LM1 + 1, 0, LM2);  // all integrals of the species pair
+  LaneInterp li;
+  laneInterpSetup(t, r, li);
+  double v[NI];
+  laneInterpRange<0, NI, NI>(t, li, v);
+  double Y[(LY + 1) * (LY + 1)];
+  skg::harmonics<LY>(dx, dy, dz, Y);
+  double acc = 0.0;
+  staticFor<LM1 + 1>([&](auto l1c) {
+    constexpr int l1 = decltype(l1c)::value;
+    staticFor<LM2 + 1>([&](auto l2c) {
+      constexpr int l2 = decltype(l2c)::value;
+      double a[4];
+      skg::acoefT<l1, l2>(v + canonIntegStart(l1, l2, LM2), a);
+      const double *sub = row + l2 * l2 + N2 * l1 * l1;
+      acc += skg::wdotT<l1, l2>(Y, a, [&](int aa, int b) { return sub[b + N2 * aa]; });
+    });
+  });
+  return acc;
+}
+
+__device__ __forceinline__ int canonCase(const SpPairProg &pg) {
+  return (pg.canon1 >= 0 && pg.canon2 >= 0 && pg.canon1 <= 2 && pg.canon2 <= 2) ? pg.canon1 * 3 + pg.canon2 : -1;
+}
+
+template <int LMAX>
+__device__ __forceinline__ void skLaneWBuildAny(const SpPairProg &pg, double *row) {
+  switch (canonCase(pg)) {
+    case 0: skLaneWBuildCanon<0, 0>(row); break;
+    case 1: if constexpr (LMAX >= 1) skLaneWBuildCanon<0, 1>(row); break;
+    case 2: if constexpr (LMAX >= 2) skLaneWBuildCanon<0, 2>(row); break;
+    case 3: if constexpr (LMAX >= 1) skLaneWBuildCanon<1, 0>(row); break;
+    case 4: if constexpr (LMAX >= 1) skLaneWBuildCanon<1, 1>(row); break;
+    case 5: if constexpr (LMAX >= 2) skLaneWBuildCanon<1, 2>(row); break;
+    case 6: if constexpr (LMAX >= 2) skLaneWBuildCanon<2, 0>(row); break;
+    case 7: if constexpr (LMAX >= 2) skLaneWBuildCanon<2, 1>(row); break;
+    case 8: if constexpr (LMAX >= 2) skLaneWBuildCanon<2, 2>(row); break;
+    default: skLaneWBuild<LMAX>(pg, row);
+  }
+}
+
+template <int LMAX>
+__device__ __forceinline__ double skLaneWDotAny(const SpPairProg &pg, const SkTableDev &t, double r, double dx,
+                                                double dy, double dz, const double *row) {
+  switch (canonCase(pg)) {
+    case 0: return skLaneWDotCanon<0, 0>(t, r, dx, dy, dz, row);
+    case 1: if constexpr (LMAX >= 1) return skLaneWDotCanon<0, 1>(t, r, dx, dy, dz, row); break;
+    case 2: if constexpr (LMAX >= 2) return skLaneWDotCanon<0, 2>(t, r, dx, dy, dz, row); break;
+    case 3: if constexpr (LMAX >= 1) return skLaneWDotCanon<1, 0>(t, r, dx, dy, dz, row); break;
+    case 4: if constexpr (LMAX >= 1) return skLaneWDotCanon<1, 1>(t, r, dx, dy, dz, row); break;
+    case 5: if constexpr (LMAX >= 2) return skLaneWDotCanon<1, 2>(t, r, dx, dy, dz, row); break;
+    case 6: if constexpr (LMAX >= 2) return skLaneWDotCanon<2, 0>(t, r, dx, dy, dz, row); break;
+    case 7: if constexpr (LMAX >= 2) return skLaneWDotCanon<2, 1>(t, r, dx, dy, dz, row); break;
+    case 8: if constexpr (LMAX >= 2) return skLaneWDotCanon<2, 2>(t, r, dx, dy, dz, row); break;
+    default: break;
+  }
+  return skLaneWDot<LMAX>(pg, t, r, dx, dy, dz, row);
+}
+
 }  // namespace dftbp_b200

@@ -305,6 +305,152 @@ def emit_code(tables):
                         ap("    emit(%d, %d, 0.0, 0.0);" % (a, b))
                     ap("  }")
             ap("}")
+    # ---- column-wise forward rotation (K1) and weight-contracted forms (K5), per shell-pair type
+    def wcount(l1, l2):
+        return (min(l1, l2) + 1) * (2 * max(l1, l2) + 1)
+
+    for l1 in range(LMAX + 1):
+        for l2 in range(LMAX + 1):
+            Ls, G, T = tables[(l1, l2)]
+            lmin = min(l1, l2)
+            nk = lmin + 1
+            # A_k = sum_mu T[k, mu] V_mu
+            ap("// (l1, l2) = (%d, %d): expansion coefficients, one column, weight contraction" % (l1, l2))
+            ap("__device__ __forceinline__ void acoef_%d_%d(const double *v, double *a) {" % (l1, l2))
+            for k in range(nk):
+                terms = [(T[k, mu], mu) for mu in range(nk) if T[k, mu] != 0.0]
+                expr = "%s * v[%d]" % (C(terms[0][0]), terms[0][1])
+                for c, mu in terms[1:]:
+                    expr = "fma(%s, v[%d], %s)" % (C(c), mu, expr)
+                ap("  a[%d] = %s;" % (k, expr))
+            ap("}")
+            # column A of the block: emit(b, h, s), b = m2 index (row inside the shell of atom 2)
+            ap("template <int A, bool DO_H, bool DO_S, int NY, class Emit>")
+            ap("__device__ __forceinline__ void col_%d_%d(const double (&Y)[NY], const double *aH, const double *aS, Emit &&emit) {" % (l1, l2))
+            ap("  static_assert(NY >= %d, \"harmonics up to L = %d needed\");" % ((l1 + l2 + 1) ** 2, l1 + l2))
+            for a in range(2 * l1 + 1):
+                ap("  %sif constexpr (A == %d) {" % ("" if a == 0 else "else ", a))
+                for b in range(2 * l2 + 1):
+                    ap("    {")
+                    used = []
+                    for k, Lq in enumerate(Ls):
+                        terms = [(G[k][a, b, M + Lq], Lq * Lq + Lq + M) for M in range(-Lq, Lq + 1)
+                                 if G[k][a, b, M + Lq] != 0.0]
+                        if not terms:
+                            continue
+                        expr = "%s * Y[%d]" % (C(terms[0][0]), terms[0][1])
+                        for g, yi in terms[1:]:
+                            expr = "fma(%s, Y[%d], %s)" % (C(g), yi, expr)
+                        ap("      const double t%d = %s;" % (k, expr))
+                        used.append(k)
+                    if used:
+                        for which in ("H", "S"):
+                            expr = "a%s[%d] * t%d" % (which, used[0], used[0])
+                            for k in used[1:]:
+                                expr = "fma(a%s[%d], t%d, %s)" % (which, k, k, expr)
+                            ap("      const double %s = DO_%s ? %s : 0.0;" % (which.lower(), which, expr))
+                        ap("      emit(%d, h, s);" % b)
+                    else:
+                        ap("      emit(%d, 0.0, 0.0);" % b)
+                    ap("    }")
+                ap("  }")
+            ap("}")
+            # W_j = sum_(a,b) G[k][a,b,M] w(a,b), j = (k, M) flattened; %d values
+            ap("template <class GetW, class PutW>")
+            ap("__device__ __forceinline__ void wbuild_%d_%d(GetW &&getw, PutW &&putW) {" % (l1, l2))
+            for a in range(2 * l1 + 1):
+                for b in range(2 * l2 + 1):
+                    ap("  const double w_%d_%d = getw(%d, %d);" % (a, b, a, b))
+            j = 0
+            for k, Lq in enumerate(Ls):
+                for M in range(-Lq, Lq + 1):
+                    terms = [(G[k][a, b, M + Lq], a, b) for a in range(2 * l1 + 1) for b in range(2 * l2 + 1)
+                             if G[k][a, b, M + Lq] != 0.0]
+                    if terms:
+                        expr = "%s * w_%d_%d" % (C(terms[0][0]), terms[0][1], terms[0][2])
+                        for g, a, b in terms[1:]:
+                            expr = "fma(%s, w_%d_%d, %s)" % (C(g), a, b, expr)
+                    else:
+                        expr = "0.0"
+                    ap("  const double W%d = %s;" % (j, expr))
+                    j += 1
+            assert j == wcount(l1, l2)
+            for jj in range(j):  # W_j is parked in the slot of the j-th element (a, b) of the sub-block
+                ap("  putW(%d, %d, W%d);" % (jj // (2 * l2 + 1), jj % (2 * l2 + 1), jj))
+            ap("}")
+            # sum_k a_k sum_M W_(k,M) S_(L_k M)
+            ap("template <int NY, class GetW>")
+            ap("__device__ __forceinline__ double wdot_%d_%d(const double (&Y)[NY], const double *a, GetW &&getW) {" % (l1, l2))
+            ap("  static_assert(NY >= %d, \"harmonics up to L = %d needed\");" % ((l1 + l2 + 1) ** 2, l1 + l2))
+            j = 0
+            for k, Lq in enumerate(Ls):
+                expr = None
+                for M in range(-Lq, Lq + 1):
+                    yi = Lq * Lq + Lq + M
+                    slot = "%d, %d" % (j // (2 * l2 + 1), j % (2 * l2 + 1))
+                    expr = ("getW(%s) * Y[%d]" % (slot, yi)) if expr is None else ("fma(getW(%s), Y[%d], %s)" % (slot, yi, expr))
+                    j += 1
+                ap("  const double u%d = %s;" % (k, expr))
+            expr = "a[0] * u0"
+            for k in range(1, nk):
+                expr = "fma(a[%d], u%d, %s)" % (k, k, expr)
+            ap("  return %s;" % expr)
+            ap("}")
+    # compile-time and warp-uniform run-time selectors of the new forms
+    ap("template <int L1, int L2>")
+    ap("__device__ __forceinline__ void acoefT(const double *v, double *a) {")
+    first = True
+    for l1 in range(LMAX + 1):
+        for l2 in range(LMAX + 1):
+            ap("  %sif constexpr (L1 == %d && L2 == %d) acoef_%d_%d(v, a);" % ("" if first else "else ", l1, l2, l1, l2))
+            first = False
+    ap("}")
+    ap("template <int L1, int L2, int A, bool DO_H, bool DO_S, int NY, class Emit>")
+    ap("__device__ __forceinline__ void colT(const double (&Y)[NY], const double *aH, const double *aS, Emit &&emit) {")
+    first = True
+    for l1 in range(LMAX + 1):
+        for l2 in range(LMAX + 1):
+            ap("  %sif constexpr (L1 == %d && L2 == %d) col_%d_%d<A, DO_H, DO_S>(Y, aH, aS, emit);" %
+               ("" if first else "else ", l1, l2, l1, l2))
+            first = False
+    ap("}")
+    ap("template <int L1, int L2, class GetW, class PutW>")
+    ap("__device__ __forceinline__ void wbuildT(GetW &&getw, PutW &&putW) {")
+    first = True
+    for l1 in range(LMAX + 1):
+        for l2 in range(LMAX + 1):
+            ap("  %sif constexpr (L1 == %d && L2 == %d) wbuild_%d_%d(getw, putW);" % ("" if first else "else ", l1, l2, l1, l2))
+            first = False
+    ap("}")
+    ap("template <int L1, int L2, int NY, class GetW>")
+    ap("__device__ __forceinline__ double wdotT(const double (&Y)[NY], const double *a, GetW &&getW) {")
+    for l1 in range(LMAX + 1):
+        for l2 in range(LMAX + 1):
+            ap("  if constexpr (L1 == %d && L2 == %d) return wdot_%d_%d(Y, a, getW);" % (l1, l2, l1, l2))
+    ap("  return 0.0;")
+    ap("}")
+    ap("template <int LMAX, class GetW, class PutW>")
+    ap("__device__ __forceinline__ void wbuildDispatch(int l1, int l2, GetW &&getw, PutW &&putW) {")
+    ap("  switch (l1 * 4 + l2) {")
+    for l1 in range(LMAX + 1):
+        for l2 in range(LMAX + 1):
+            ap("    case %d: if constexpr (LMAX >= %d) wbuild_%d_%d(getw, putW); break;" % (l1 * 4 + l2, max(l1, l2), l1, l2))
+    ap("    default: break;")
+    ap("  }")
+    ap("}")
+    ap("template <int LMAX, class GetW>")
+    ap("__device__ __forceinline__ double wdotDispatch(int l1, int l2, const double (&Y)[(2 * LMAX + 1) * (2 * LMAX + 1)],")
+    ap("                                                const double *v, GetW &&getW) {")
+    ap("  double a[4];")
+    ap("  switch (l1 * 4 + l2) {")
+    for l1 in range(LMAX + 1):
+        for l2 in range(LMAX + 1):
+            ap("    case %d: if constexpr (LMAX >= %d) { acoef_%d_%d(v, a); return wdot_%d_%d(Y, a, getW); } break;" %
+               (l1 * 4 + l2, max(l1, l2), l1, l2, l1, l2))
+    ap("    default: break;")
+    ap("  }")
+    ap("  return 0.0;")
+    ap("}")
     # ---- dispatch
     ap("// Uniform (per warp) dispatch on the shell-pair type; LMAX = highest l of any species.")
     ap("template <bool DO_H, bool DO_S, int LMAX, class Emit>")
