@@ -235,6 +235,52 @@ __device__ __forceinline__ void skLaneEvalAny(const SpPairProg &pg, const SkTabl
 }
 
 
+// ---- column-wise canonical evaluator (K1) --------------------------------------------------------------
+// H0 and S of one pair in a single pass, one block column (nOrb2 contiguous elements) at a time:
+//   emit(e, h, s)   element e (0 .. N2-1) of the current column, H0 and S value
+//   endCol(col)     column col (0-based, atom-1 orbital) is complete
+// The harmonics, the Lagrange weights (both tables share the grid: checked on the host) and the
+// Gaunt sums t_k(a, b) are shared between the two matrices; only the A_k differ.  The caller
+// stages ONE column per lane, so the staging tile is 32 x N2 doubles per matrix instead of
+// 32 x (largest column group).
+template <int LM1, int LM2, bool DO_H, bool DO_S, class Emit, class EndCol>
+__device__ __forceinline__ void skLaneEvalCanonCols(const SkTableDev &tH, const SkTableDev &tS, double r, double dx,
+                                                    double dy, double dz, Emit &&emit, EndCol &&endCol) {
+  constexpr int LY = LM1 + LM2;
+  constexpr int NG = canonIntegStart(LM1 + 1, 0, LM2) - canonIntegStart(LM1, 0, LM2);  // largest group
+  LaneInterp li;
+  laneInterpSetup(DO_H ? tH : tS, r, li);
+  double Y[(LY + 1) * (LY + 1)];
+  skg::harmonics<LY>(dx, dy, dz, Y);
+  staticFor<LM1 + 1>([&](auto l1c) {
+    constexpr int l1 = decltype(l1c)::value;
+    constexpr int g0 = canonIntegStart(l1, 0, LM2);
+    constexpr int ng = canonIntegStart(l1 + 1, 0, LM2) - g0;
+    double aH[NG], aS[NG];
+    {
+      double vH[NG], vS[NG];
+      if constexpr (DO_H) laneInterpRange<g0, ng, NG>(tH, li, vH);
+      if constexpr (DO_S) laneInterpRange<g0, ng, NG>(tS, li, vS);
+      staticFor<LM2 + 1>([&](auto l2c) {
+        constexpr int l2 = decltype(l2c)::value;
+        constexpr int off = canonIntegStart(l1, l2, LM2) - g0;
+        if constexpr (DO_H) skg::acoefT<l1, l2>(vH + off, aH + off);
+        if constexpr (DO_S) skg::acoefT<l1, l2>(vS + off, aS + off);
+      });
+    }
+    staticFor<2 * l1 + 1>([&](auto ac) {
+      constexpr int a = decltype(ac)::value;
+      staticFor<LM2 + 1>([&](auto l2c) {
+        constexpr int l2 = decltype(l2c)::value;
+        constexpr int off = canonIntegStart(l1, l2, LM2) - g0;
+        skg::colT<l1, l2, a, DO_H, DO_S>(Y, aH + off, aS + off,
+                                         [&](int b, double h, double sv) { emit(l2 * l2 + b, h, sv); });
+      });
+      endCol(l1 * l1 + a);
+    });
+  });
+}
+
 // ---- weight-contracted form (K5) ---------------------------------------------------------------------
 // A contraction sum_e w_e E_e(d) of the block with fixed weights w (rho, E-rho, ...) is
 //   sum over shell pairs, k:  A_k(r) * sum_M W_(k,M) S_(L_k M)(d),   W_(k,M) = sum_(a,b) G_k(a,b;M) w(a,b),

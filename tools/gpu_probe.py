@@ -16,7 +16,12 @@ from dftbplus_b200 import workloads  # noqa: E402
 from dftbplus_b200.api import HotPath, new_dense  # noqa: E402
 
 
+ONCE = "--once" in sys.argv  # one warm-up + one timed call per kernel: the ncu capture run
+
+
 def timeit(fn, stream, n=10, warm=3):
+    if ONCE:
+        n, warm = 1, 1
     for _ in range(warm):
         fn()
     stream.synchronize()
