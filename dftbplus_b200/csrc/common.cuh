@@ -20,9 +20,12 @@ constexpr int kWarpsPerCta = 8;
 // One equidistant SK table on the device (TSlakoEqGrid, dftb/slakoeqgrid.F90:25-33).
 struct SkTableDev {
   const double *tab;   // (nGrid, nInteg) column-major
-  const double *tail;  // (3, nInteg): y1, y1p, y1pp of the 5th-order tail (slakoeqgrid.F90:228-240)
+  const double *tail;  // (3, nInteg): coefficients dd, ee, ff of the 5th-order tail (poly5ToZero,
+                       // math/interpolation.F90:31-67; slakoeqgrid.F90:228-240 / :295-307)
   double dist, invDist, rMax;
-  int nGrid, nInteg, method, pad;
+  double tailX0, tailInvDx;  // tail abscissa xr = (r - tailX0) * tailInvDx
+  int nGrid, nInteg, method;
+  int mIndM1;  // skEqGridOld: mInd - 1, the first grid interval beyond the tail (slakoeqgrid.F90:268,295)
 };
 
 // A_k = sum_mu t[mu] * V[vBase + mu]   (tools/gen_sk_gaunt.py)
@@ -51,11 +54,22 @@ struct SpPairProg {
 // Device-built schedule of the lane-per-pair kernels (pair_sort.cu): the off-site pairs of one work
 // list, counting-sorted by (species pair, distance bin) and padded with -1 so that every aligned
 // group of 32 entries (= one warp) holds one species pair and neighbouring table rows.
+// One record per schedule slot, written by the sort: everything a lane needs to start on its pair
+// without the dependent chain schedule -> iNeighbour -> img2CentCell / iPair / species -> coords.
+struct __align__(16) PairRec {
+  double vx, vy, vz;  // coords(:,iAtom2) - coords(:,iAtom1)   (nonscc.F90:413)
+  int ind;            // iPair(iNeigh, iAtom1); -1 = padding slot
+  int sp;             // sp1 + nSpecies * sp2 (0-based): index of the species-pair program
+};
+static_assert(sizeof(PairRec) == 32, "PairRec must be two 16-byte words");
+
 struct SortedPairs {
-  int *items = nullptr;   // flat ids iNeigh + ld*iAtom0, -1 = padding
-  int *total = nullptr;   // device scalar: padded length (multiple of 32)
-  long long capacity = 0; // allocated entries of items
-  bool valid = false;     // false after set_geometry / update_coords
+  int *items = nullptr;    // flat ids iNeigh + ld*iAtom0, -1 = padding
+  PairRec *recs = nullptr; // per slot, same order as items
+  int2 *atoms = nullptr;   // per slot: (iAtom1, iAtom2f), 0-based (K5: where the gradient goes)
+  int *total = nullptr;    // device scalar: padded length (multiple of 32)
+  long long capacity = 0;  // allocated entries of items / recs / atoms
+  bool valid = false;      // false after set_geometry / update_coords
 };
 
 struct BlockDesc;  // block_desc.cuh

@@ -44,6 +44,16 @@ double nevilleUniform8(const double *xp, const double *yp, double xx) {
 }
 
 // y1, y1p, y1pp at the last grid point (SlakoEqGrid_interNew_, slakoeqgrid.F90:224-240)
+// poly5ToZero, math/interpolation.F90:31-67: coefficients of xr^3, xr^4, xr^5 in the reference's order
+void poly5Coefficients(double y0, double y0p, double y0pp, double dx, double *out) {
+  const double dx1 = y0p * dx;
+  const double dx2 = y0pp * dx * dx;
+  out[0] = 10.0 * y0 - 4.0 * dx1 + 0.5 * dx2;
+  out[1] = -15.0 * y0 + 7.0 * dx1 - 1.0 * dx2;
+  out[2] = 6.0 * y0 - 3.0 * dx1 + 0.5 * dx2;
+}
+
+// skEqGridNew tail, slakoeqgrid.F90:222-241
 void tailCoefficients(int nGrid, int nInteg, double dist, const double *tab, std::vector<double> &out) {
   out.assign(3 * (size_t)nInteg, 0.0);
   if (nGrid < 9) return;
@@ -54,9 +64,26 @@ void tailCoefficients(int nGrid, int nInteg, double dist, const double *tab, std
     double y0 = nevilleUniform8(xa, ya, xa[7] - kDeltaR);
     double y2 = nevilleUniform8(xa, ya, xa[7] + kDeltaR);
     double y1 = ya[7];
-    out[3 * c + 0] = y1;
-    out[3 * c + 1] = (y2 - y0) / (2.0 * kDeltaR);
-    out[3 * c + 2] = (y2 + y0 - 2.0 * y1) / (kDeltaR * kDeltaR);
+    poly5Coefficients(y1, (y2 - y0) / (2.0 * kDeltaR), (y2 + y0 - 2.0 * y1) / (kDeltaR * kDeltaR),
+                      -1.0 * kDistFudge, &out[3 * c]);
+  }
+}
+
+// skEqGridOld extrapolation, slakoeqgrid.F90:295-307: slope and curvature of the free cubic spline
+// (math/interpolation.F90:74-120) at the last grid point start the 5th-order tail
+void tailCoefficientsOld(int nGrid, int nInteg, double dist, const double *tab, double tailDx,
+                         std::vector<double> &out) {
+  out.assign(3 * (size_t)nInteg, 0.0);
+  for (int c = 0; c < nInteg; ++c) {
+    const double *col = tab + (size_t)nGrid * c;
+    const double y0 = col[nGrid - 3], y1 = col[nGrid - 2], y2 = col[nGrid - 1];
+    const double r1 = (y2 - y0) / (2.0 * dist);
+    const double r2 = (y2 + y0 - 2.0 * y1) / (dist * dist);
+    const double cc = 0.5 * r2, dx1 = 1.0 / dist;
+    const double dd = (((y2 - y1) * dx1 - r1) * dx1 - 0.5 * r2) * dx1;
+    const double y1p = (3.0 * dd * dist + 2.0 * cc) * dist + r1;
+    const double y1pp = 6.0 * dd * dist + 2.0 * cc;
+    poly5Coefficients(y2, y1p, y1pp, tailDx, &out[3 * c]);
   }
 }
 
@@ -122,7 +149,9 @@ int dftbp_b200_create(dftbp_b200_ctx **out, int device, int rank, int nRanks) {
   ctx->smCount = prop.multiProcessorCount;
   ctx->smemOptin = prop.sharedMemPerBlockOptin;
   ctx->smemPerSm = prop.sharedMemPerMultiprocessor;
-  DFTBP_CUDA(ctx, cudaMalloc((void **)&ctx->dInfo, 4 * sizeof(int)));  // [0] info / nLevels, [2..3] tile counter
+  DFTBP_CUDA(ctx, cudaMalloc((void **)&ctx->dInfo, 16 * sizeof(int)));
+  // [0] info / nLevels, [1] shift flag, [2..3] K3 tile counter, [4..5] K1 / [6..7] K5 / [8..9] K4 item schedulers
+  DFTBP_CUDA(ctx, cudaMemset(ctx->dInfo, 0, 16 * sizeof(int)));
   return 0;
 }
 
@@ -328,25 +357,42 @@ int dftbp_b200_set_sk_table(dftbp_b200_ctx *ctx, int which, int sp1, int sp2, in
   if (nInteg != pg.nInteg)
     return fail(ctx, DFTBP_B200_EINVAL, "set_sk_table: species pair (%d,%d) needs %d integrals, got %d",
                 sp1, sp2, pg.nInteg, nInteg);
-  if (method == DFTBP_B200_SK_EQGRID_OLD)
-    return fail(ctx, DFTBP_B200_ENOTIMPL,
-                "OldSKInterpolation (skEqGridOld, slakoeqgrid.F90:248-317) is not built yet");
-  DFTBP_CHECK(ctx, method == DFTBP_B200_SK_EQGRID_NEW, "set_sk_table: unknown interpolation method");
-  // SlakoEqGrid_interNew_ aborts for tables shorter than nInterNew_+1 (slakoeqgrid.F90:207-210)
-  if (nGrid < 9)
+  DFTBP_CHECK(ctx, method == DFTBP_B200_SK_EQGRID_NEW || method == DFTBP_B200_SK_EQGRID_OLD,
+              "set_sk_table: unknown interpolation method");
+  const bool old = method == DFTBP_B200_SK_EQGRID_OLD;
+  // SlakoEqGrid_interNew_ / _interOld_ abort for tables shorter than nInter + 1 points
+  // (slakoeqgrid.F90:207-210, :271-273)
+  if (nGrid < (old ? 4 : 9))
     return fail(ctx, DFTBP_B200_EINVAL, "SlakoEqGrid: Not enough points in the SK-table for interpolation!");
   std::vector<double> host = toHost(skTab, (size_t)nGrid * nInteg), tail;
-  tailCoefficients(nGrid, nInteg, dist, host.data(), tail);
+  SkTableDev &t = which == 0 ? pg.H : pg.S;
+  t.dist = dist; t.invDist = 1.0 / dist;
+  t.nGrid = nGrid; t.nInteg = nInteg; t.method = method;
+  if (old) {
+    // mInd = leng + floor(distFudgeOld / incr); the tail runs over (mInd - leng - 1) * incr
+    const int mInd = nGrid + (int)std::floor(kDistFudgeOld / dist);
+    const double span = (double)(mInd - nGrid - 1) * dist;
+    t.mIndM1 = mInd - 1;
+    t.tailX0 = (double)(mInd - 1) * dist;
+    t.tailInvDx = -1.0 / span;
+    t.rMax = (double)(mInd - 1) * dist;  // first distance that certainly yields zero
+    tailCoefficientsOld(nGrid, nInteg, dist, host.data(), -1.0 * span, tail);
+  } else {
+    t.rMax = (double)nGrid * dist + kDistFudge;
+    t.mIndM1 = 0;
+    t.tailX0 = t.rMax;
+    t.tailInvDx = -1.0 / kDistFudge;
+    tailCoefficients(nGrid, nInteg, dist, host.data(), tail);
+  }
+  host.resize(host.size() + 8, 0.0);  // the 8-row window of a short skEqGridOld table may pass the last column
   double *dTab = nullptr, *dTail = nullptr;
   DFTBP_TRY(uploadNew(ctx, &dTab, host.data(), host.size()));
   DFTBP_TRY(uploadNew(ctx, &dTail, tail.data(), tail.size()));
   ctx->tableAllocs.push_back(dTab);
   ctx->tableAllocs.push_back(dTail);
-  SkTableDev &t = which == 0 ? pg.H : pg.S;
-  t.tab = dTab; t.tail = dTail; t.dist = dist; t.invDist = 1.0 / dist;
-  t.nGrid = nGrid; t.nInteg = nInteg; t.method = method;
-  t.rMax = (double)nGrid * dist + kDistFudge;
-  ctx->cutoff = std::max(ctx->cutoff, (double)nGrid * dist + (method == 1 ? kDistFudgeOld : kDistFudge));
+  t.tab = dTab; t.tail = dTail;
+  // SlakoEqGrid_getCutoff, slakoeqgrid.F90:162-179
+  ctx->cutoff = std::max(ctx->cutoff, (double)nGrid * dist + (old ? kDistFudgeOld : kDistFudge));
   ctx->progsDirty = true;
   return 0;
 }

@@ -2,14 +2,14 @@
 //
 // Lane-per-pair: every thread evaluates the diatomic block of one neighbour pair with the
 // straight-line evaluator of sk_lane_eval.cuh; the 32 pairs of a warp come from the device-built
-// schedule of pair_sort.cu (one species pair, neighbouring distances).  A thread's block is
-// scattered over 648-byte strides in the sparse array, so the warp transposes through shared
-// memory: each lane writes its elements into its own row of a [32][pitch] staging tile (odd
-// pitch: conflict free), then the warp streams the 32 blocks out one after the other with lanes
-// running over the contiguous elements -- every store instruction covers one 256-byte run.  H0
-// and S of a pair share a row (H at [0, nElem), S at [nElem, 2 nElem)) so small blocks (sp-sp: 16
-// elements) still fill the warp.  On-site blocks (iNeigh = 0; diagonal = on-site energies or 1,
-// nonscc.F90:109-116 / :166-173) are written by a second grid-stride loop, one warp per atom.
+// schedule of pair_sort.cu (one species pair, neighbouring distances), which also leaves one
+// 32-byte record per pair (bond vector, sparse offset, species-pair program): a lane starts from
+// ONE coalesced load instead of the chain schedule -> iNeighbour -> iPair / species -> coords.
+// A thread's block is scattered over 648-byte strides in the sparse array, so the warp transposes
+// through shared memory: each lane writes its elements into its own row of a [32][pitch] staging
+// tile (odd pitch: conflict free), then the warp streams the 32 runs out one pair after the other
+// with lanes on consecutive elements.  On-site blocks (iNeigh = 0; diagonal = on-site energies or
+// 1, nonscc.F90:109-116 / :166-173) are written by a second grid-stride loop, one warp per atom.
 // Every element of this rank's segment is written exactly once: no memset, no atomics.
 //
 // Roofline: HBM-write bound for d-block systems, 16*n1*n2 + 8 algorithmic bytes per pair
@@ -24,13 +24,11 @@ namespace {
 
 struct K1Params {
   const SpPairProg *progs;
-  const int *items;   // sorted pair schedule (pair_sort.cu)
-  const int *total;   // its padded length
-  int ld, nSpecies, mOrb, pitch;
+  const PairRec *recs;  // sorted pair schedule with per-pair records (pair_sort.cu)
+  const int *total;     // its padded length
+  int ld, nSpecies, mOrb;
   int firstAtom, lastAtom;  // on-site blocks of this rank
-  const double *coords;
   const int *species;
-  const int *iNeighbour;
   const int *iPair;
   const double *selfE;  // (mOrb, nSpecies)
   double *ham;
@@ -44,94 +42,84 @@ struct K1Params {
 // Write-out, one atom-1 shell ("column group") at a time: the (2 l1 + 1) * nOrb2 elements of a group
 // are contiguous in the column-major block.  Lane q stages its group in row q of the warp's
 // [32][pitch] tile (odd pitch: the lanes' writes of one element hit 32 different banks); then the
-// warp streams the 32 runs out with consecutive lanes on consecutive elements -- flat index
-// idx = lane + 32 k over the 32 * count staged elements, (row, element) = (idx / count, idx % count)
-// by a multiply-shift -- so all 32 lanes store in every step and every store instruction covers at
-// most two contiguous runs of the sparse array.  (A TMA bulk copy per block was tried: UBLKCP takes
-// uniform-register operands, so the 32 copies of a warp serialise in a vote loop -- slower.)
-//
-// The index loads of an item (schedule entry -> iNeighbour / iPair -> coordinates, species) are a
-// chain of dependent global loads; they are software-pipelined two items ahead.
-template <int LMAX>
-__global__ void __launch_bounds__(256, 2) k1_pair_build(const K1Params p) {
+// warp walks over the 32 rows and copies each run with lanes on consecutive elements (one or two
+// store instructions per run for s/p/d).  The base offset of a run is warp-uniform, so a run costs
+// one shuffle and an LDS/STG pair per 32 elements.  (The earlier flat mapping idx = lane + 32 k ->
+// (row, element) kept all 32 lanes busy in every store but paid a multiply-shift division, a
+// shuffle and a predicate per ELEMENT: 44 % of the kernel's instructions,
+// profiles/r01e_ncu_k1_source_hotspots.txt.  A TMA bulk copy per run is not possible: the runs start
+// at arbitrary 8-byte offsets, cp.async.bulk needs 16.)
+template <int LMAX, int WARPS, int CTAS>
+__global__ void __launch_bounds__(32 * WARPS, CTAS) k1_pair_build(const K1Params p) {
   extern __shared__ double smem[];
+  // staging row per lane: the largest column group, (2 lmax + 1) * mOrb elements, odd pitch
+  constexpr int PITCH = ((2 * LMAX + 1) * (LMAX + 1) * (LMAX + 1)) | 1;
   const int lane = threadIdx.x & 31, wIn = threadIdx.x >> 5, nW = blockDim.x >> 5;
-  double *stage = smem + (size_t)wIn * 32 * p.pitch;
-  double *row = stage + (size_t)lane * p.pitch;
+  double *stage = smem + (size_t)wIn * 32 * PITCH;
+  double *row = stage + (size_t)lane * PITCH;
   const int nChunks = __ldg(p.total) >> 5;
   const int nMat = (p.ham && p.over) ? 2 : 1;
   const int nItems = nChunks * nMat;
   const int stride = gridDim.x * nW;
-  auto loadFlat = [&](int it) -> int {
-    if (it >= nItems) return -1;
-    int f = __ldg(p.items + 32 * (nMat == 2 ? it >> 1 : it) + lane);
-    const int f0 = __shfl_sync(0xffffffffu, f, 0);  // lane 0 of a chunk is never padding
-    return f >= 0 ? f : -2 - f0;                    // padding lanes shadow lane 0's pair: encoded < -1
+  // record of this lane's pair in item `it`: two 16-byte loads, coalesced across the warp
+  auto loadRec = [&](int it, double2 &xy, double &z, int &ind, int &sp) {
+    if (it >= nItems) return;
+    const PairRec *r = p.recs + 32 * (size_t)(nMat == 2 ? it >> 1 : it) + lane;
+    xy = __ldg(reinterpret_cast<const double2 *>(r));
+    const int4 w = __ldg(reinterpret_cast<const int4 *>(r) + 1);
+    z = __hiloint2double(w.y, w.x);
+    ind = w.z;
+    sp = w.w;
   };
-  auto flatOf = [](int f) { return f >= 0 ? f : -2 - f; };
   int item = blockIdx.x * nW + wIn;
-  // pipeline registers: C = current item, N = next, NN = the one after
-  int fC = loadFlat(item), fN = loadFlat(item + stride);
-  int indC = 0;
-  double c1x = 0, c1y = 0, c1z = 0, c2x = 0, c2y = 0, c2z = 0;
-  int s1C = 1, s2C = 1;
-  if (fC != -1) {
-    const int f = flatOf(fC), iAt1 = f / p.ld;
-    const int iAt2 = __ldg(p.iNeighbour + f) - 1;
-    indC = __ldg(p.iPair + f);
-    c1x = __ldg(p.coords + 3 * iAt1); c1y = __ldg(p.coords + 3 * iAt1 + 1); c1z = __ldg(p.coords + 3 * iAt1 + 2);
-    c2x = __ldg(p.coords + 3 * iAt2); c2y = __ldg(p.coords + 3 * iAt2 + 1); c2z = __ldg(p.coords + 3 * iAt2 + 2);
-    s1C = __ldg(p.species + iAt1);
-    s2C = __ldg(p.species + iAt2);
-  }
+  double2 xyN = make_double2(0.0, 0.0);
+  double zN = 1.0;
+  int indN = -1, spN = 0;
+  loadRec(item, xyN, zN, indN, spN);
   for (; item < nItems; item += stride) {
-    // stage 1 of item + 2 strides, stage 2 of item + stride
-    const int fNN = loadFlat(item + 2 * stride);
-    int iAt2N = 0, indN = 0, iAt1N = 0;
-    if (fN != -1) {
-      const int f = flatOf(fN);
-      iAt1N = f / p.ld;
-      iAt2N = __ldg(p.iNeighbour + f) - 1;
-      indN = __ldg(p.iPair + f);
+    double vx = xyN.x, vy = xyN.y, vz = zN;
+    const int ind = indN;
+    const int sp = __shfl_sync(0xffffffffu, spN, 0);  // lane 0 of a chunk is never padding
+    loadRec(item + stride, xyN, zN, indN, spN);        // the next item's record is in flight during this one
+    {
+      // padding lanes shadow lane 0's pair (they evaluate a valid geometry and store nothing)
+      const double x0 = __shfl_sync(0xffffffffu, vx, 0), y0 = __shfl_sync(0xffffffffu, vy, 0),
+                   z0 = __shfl_sync(0xffffffffu, vz, 0);
+      if (ind < 0) { vx = x0; vy = y0; vz = z0; }
     }
-    // ---- current item
     const bool isS = nMat == 2 ? (item & 1) : (p.ham == nullptr);
-    const bool valid = fC >= 0;
-    const int sp1 = __shfl_sync(0xffffffffu, s1C, 0) - 1, sp2 = __shfl_sync(0xffffffffu, s2C, 0) - 1;
-    const SpPairProg &pg = p.progs[sp1 + p.nSpecies * sp2];
+    const SpPairProg &pg = p.progs[sp];
     const SkTableDev tab = isS ? pg.S : pg.H;
-    const int nElem = pg.nOrb1 * pg.nOrb2;
-    double *__restrict__ outBase = isS ? p.over : p.ham;
-    // vect = coords(:,iAt2) - coords(:,iAt1); dist = sqrt(sum(vect**2)); vect = vect/dist
-    const double vx = c2x - c1x, vy = c2y - c1y, vz = c2z - c1z;
+    double *__restrict__ outLane = (isS ? p.over : p.ham) + lane;
+    // dist = sqrt(sum(vect**2)); vect = vect/dist
     const double dist = sqrt(vx * vx + vy * vy + vz * vz);
     const double rinv = 1.0 / dist;
-    const int desc = valid ? indC : -1;
     skLaneEvalAny<LMAX>(
         pg, tab, dist, vx * rinv, vy * rinv, vz * rinv, [&](int, int e, double v) { row[e] = v; },
         [&](int first, int count) {
           __syncwarp();
-          const unsigned M = (1048576u + (unsigned)count - 1u) / (unsigned)count;  // idx / count = idx * M >> 20
-          double *__restrict__ dst = outBase + first;
-#pragma unroll 4
-          for (int k = 0; k < count; ++k) {
-            const unsigned idx = (unsigned)(lane + 32 * k);
-            const unsigned q = (idx * M) >> 20;
-            const unsigned e = idx - q * (unsigned)count;
-            const int base = __shfl_sync(0xffffffffu, desc, (int)q);
-            const double v = stage[q * p.pitch + e];
-            if (base >= 0) dst[base + e] = v;
+          // run q: `count` staged elements of row q -> out[ind_q + first ..); lanes on consecutive
+          // elements.  One shuffle (the run's base, warp-uniform), predicated LDS / STG pairs.
+          const double *__restrict__ src = stage + lane;
+          const bool m0 = lane < count, m1 = lane + 32 < count;
+#pragma unroll 8
+          for (int q = 0; q < 32; ++q) {
+            const int base = __shfl_sync(0xffffffffu, ind, q);
+            const bool on = base >= 0;
+            double *__restrict__ d = outLane + (first + base);
+            const double *__restrict__ s = src + q * PITCH;
+            double v0 = 0.0, v1 = 0.0;
+            if (m0) v0 = s[0];
+            if (m1) v1 = s[32];
+            if (on && m0) d[0] = v0;
+            if (on && m1) d[32] = v1;
+            if constexpr (LMAX >= 3) {  // f shells: runs of up to 7 * 16 elements
+              for (int e = lane + 64; e < count; e += 32)
+                if (on) d[e - lane] = s[e - lane];
+            }
           }
           __syncwarp();
         });
-    // stage 3 of item + stride, then rotate the pipeline
-    if (fN != -1) {
-      c1x = __ldg(p.coords + 3 * iAt1N); c1y = __ldg(p.coords + 3 * iAt1N + 1); c1z = __ldg(p.coords + 3 * iAt1N + 2);
-      c2x = __ldg(p.coords + 3 * iAt2N); c2y = __ldg(p.coords + 3 * iAt2N + 1); c2z = __ldg(p.coords + 3 * iAt2N + 2);
-      s1C = __ldg(p.species + iAt1N);
-      s2C = __ldg(p.species + iAt2N);
-    }
-    fC = fN; fN = fNN; indC = indN;
   }
   // on-site blocks
   for (int iAt = p.firstAtom + blockIdx.x * nW + wIn; iAt <= p.lastAtom; iAt += gridDim.x * nW) {
@@ -146,129 +134,6 @@ __global__ void __launch_bounds__(256, 2) k1_pair_build(const K1Params p) {
   }
 }
 
-// ---- column-staged variant: H0 and S in one pass (canonical s / sp / spd species, one grid per pair) ----
-// One work item = one chunk of 32 sorted pairs, both matrices.  Every lane evaluates its pair column
-// by column (skLaneEvalCanonCols) and parks one column (nOrb2 contiguous elements) per matrix in its
-// row of the warp's [32][PITCH] tiles; the warp then streams the 32 columns out with the flat index
-// idx = lane + 32 k over the 32 * nOrb2 staged elements, (pair, element) = (idx / nOrb2, idx % nOrb2)
-// with nOrb2 a compile-time constant.  Compared with k1_pair_build: the harmonics, interpolation
-// weights and Gaunt sums are shared by H0 and S, the index arithmetic of the write-out is paid once
-// for both matrices, and the tile shrinks from 32 x 45 to 2 x 32 x 9 doubles per warp, which leaves
-// the SK tables an L1 of > 150 KB per SM.
-constexpr int kNoPair = -(1 << 30);
-
-template <int LM1, int LM2, bool DO_H, bool DO_S>
-__device__ __forceinline__ void k1ColsItem(const SpPairProg &pg, double r, double dx, double dy, double dz, int lane,
-                                           int desc, double *__restrict__ stageH, double *__restrict__ stageS,
-                                           double *__restrict__ ham, double *__restrict__ over) {
-  constexpr int N2 = (LM2 + 1) * (LM2 + 1);
-  constexpr int PITCH = N2 | 1;  // odd: the lanes' writes of one element hit 32 different banks
-  double *rowH = stageH + lane * PITCH, *rowS = stageS + lane * PITCH;
-  // element (pair q, e) goes to base_q + N2 * col + e = (base_q - q * N2) + idx + N2 * col
-  const int dq = desc >= 0 ? desc - lane * N2 : kNoPair;
-  skLaneEvalCanonCols<LM1, LM2, DO_H, DO_S>(
-      pg.H, pg.S, r, dx, dy, dz,
-      [&](int e, double h, double sv) {
-        if (DO_H) rowH[e] = h;
-        if (DO_S) rowS[e] = sv;
-      },
-      [&](int col) {
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < N2; ++k) {
-          const int idx = lane + 32 * k;
-          const int q = idx / N2;
-          const int dv = __shfl_sync(0xffffffffu, dq, q);
-          const int sIdx = idx + q * (PITCH - N2);
-          if (dv > kNoPair / 2) {
-            if (DO_H) ham[dv + idx + N2 * col] = stageH[sIdx];
-            if (DO_S) over[dv + idx + N2 * col] = stageS[sIdx];
-          }
-        }
-        __syncwarp();
-      });
-}
-
-template <int LMAX, bool DO_H, bool DO_S>
-__global__ void __launch_bounds__(256, 2) k1_pair_build_cols(const K1Params p) {
-  extern __shared__ double smem[];
-  constexpr int PMAX = ((LMAX + 1) * (LMAX + 1)) | 1;
-  const int lane = threadIdx.x & 31, wIn = threadIdx.x >> 5, nW = blockDim.x >> 5;
-  double *stageH = smem + (size_t)wIn * 64 * PMAX;
-  double *stageS = stageH + 32 * PMAX;
-  const int nItems = __ldg(p.total) >> 5;
-  const int stride = gridDim.x * nW;
-  auto loadFlat = [&](int it) -> int {
-    if (it >= nItems) return -1;
-    int f = __ldg(p.items + 32 * it + lane);
-    const int f0 = __shfl_sync(0xffffffffu, f, 0);  // lane 0 of a chunk is never padding
-    return f >= 0 ? f : -2 - f0;                    // padding lanes shadow lane 0's pair: encoded < -1
-  };
-  auto flatOf = [](int f) { return f >= 0 ? f : -2 - f; };
-  int item = blockIdx.x * nW + wIn;
-  int fC = loadFlat(item), fN = loadFlat(item + stride);
-  int indC = 0;
-  double c1x = 0, c1y = 0, c1z = 0, c2x = 0, c2y = 0, c2z = 0;
-  int s1C = 1, s2C = 1;
-  if (fC != -1) {
-    const int f = flatOf(fC), iAt1 = f / p.ld;
-    const int iAt2 = __ldg(p.iNeighbour + f) - 1;
-    indC = __ldg(p.iPair + f);
-    c1x = __ldg(p.coords + 3 * iAt1); c1y = __ldg(p.coords + 3 * iAt1 + 1); c1z = __ldg(p.coords + 3 * iAt1 + 2);
-    c2x = __ldg(p.coords + 3 * iAt2); c2y = __ldg(p.coords + 3 * iAt2 + 1); c2z = __ldg(p.coords + 3 * iAt2 + 2);
-    s1C = __ldg(p.species + iAt1);
-    s2C = __ldg(p.species + iAt2);
-  }
-  for (; item < nItems; item += stride) {
-    const int fNN = loadFlat(item + 2 * stride);
-    int iAt2N = 0, indN = 0, iAt1N = 0;
-    if (fN != -1) {
-      const int f = flatOf(fN);
-      iAt1N = f / p.ld;
-      iAt2N = __ldg(p.iNeighbour + f) - 1;
-      indN = __ldg(p.iPair + f);
-    }
-    const int sp1 = __shfl_sync(0xffffffffu, s1C, 0) - 1, sp2 = __shfl_sync(0xffffffffu, s2C, 0) - 1;
-    const SpPairProg &pg = p.progs[sp1 + p.nSpecies * sp2];
-    // vect = coords(:,iAt2) - coords(:,iAt1); dist = sqrt(sum(vect**2)); vect = vect/dist
-    const double vx = c2x - c1x, vy = c2y - c1y, vz = c2z - c1z;
-    const double dist = sqrt(vx * vx + vy * vy + vz * vz);
-    const double rinv = 1.0 / dist;
-    const double dx = vx * rinv, dy = vy * rinv, dz = vz * rinv;
-    const int desc = fC >= 0 ? indC : -1;
-    switch (pg.canon1 * 3 + pg.canon2) {
-      case 0: k1ColsItem<0, 0, DO_H, DO_S>(pg, dist, dx, dy, dz, lane, desc, stageH, stageS, p.ham, p.over); break;
-      case 1: if constexpr (LMAX >= 1) k1ColsItem<0, 1, DO_H, DO_S>(pg, dist, dx, dy, dz, lane, desc, stageH, stageS, p.ham, p.over); break;
-      case 2: if constexpr (LMAX >= 2) k1ColsItem<0, 2, DO_H, DO_S>(pg, dist, dx, dy, dz, lane, desc, stageH, stageS, p.ham, p.over); break;
-      case 3: if constexpr (LMAX >= 1) k1ColsItem<1, 0, DO_H, DO_S>(pg, dist, dx, dy, dz, lane, desc, stageH, stageS, p.ham, p.over); break;
-      case 4: if constexpr (LMAX >= 1) k1ColsItem<1, 1, DO_H, DO_S>(pg, dist, dx, dy, dz, lane, desc, stageH, stageS, p.ham, p.over); break;
-      case 5: if constexpr (LMAX >= 2) k1ColsItem<1, 2, DO_H, DO_S>(pg, dist, dx, dy, dz, lane, desc, stageH, stageS, p.ham, p.over); break;
-      case 6: if constexpr (LMAX >= 2) k1ColsItem<2, 0, DO_H, DO_S>(pg, dist, dx, dy, dz, lane, desc, stageH, stageS, p.ham, p.over); break;
-      case 7: if constexpr (LMAX >= 2) k1ColsItem<2, 1, DO_H, DO_S>(pg, dist, dx, dy, dz, lane, desc, stageH, stageS, p.ham, p.over); break;
-      case 8: if constexpr (LMAX >= 2) k1ColsItem<2, 2, DO_H, DO_S>(pg, dist, dx, dy, dz, lane, desc, stageH, stageS, p.ham, p.over); break;
-      default: break;
-    }
-    if (fN != -1) {
-      c1x = __ldg(p.coords + 3 * iAt1N); c1y = __ldg(p.coords + 3 * iAt1N + 1); c1z = __ldg(p.coords + 3 * iAt1N + 2);
-      c2x = __ldg(p.coords + 3 * iAt2N); c2y = __ldg(p.coords + 3 * iAt2N + 1); c2z = __ldg(p.coords + 3 * iAt2N + 2);
-      s1C = __ldg(p.species + iAt1N);
-      s2C = __ldg(p.species + iAt2N);
-    }
-    fC = fN; fN = fNN; indC = indN;
-  }
-  // on-site blocks
-  for (int iAt = p.firstAtom + blockIdx.x * nW + wIn; iAt <= p.lastAtom; iAt += gridDim.x * nW) {
-    const int sp = __ldg(p.species + iAt) - 1;
-    const int n = p.progs[sp + p.nSpecies * sp].nOrb1, nElem = n * n;
-    const int ind = __ldg(p.iPair + (size_t)p.ld * iAt);
-    for (int e = lane; e < nElem; e += 32) {
-      const int a = e / n, b = e - a * n;
-      if (DO_H) p.ham[ind + e] = (a == b) ? __ldg(p.selfE + a + p.mOrb * sp) : 0.0;
-      if (DO_S) p.over[ind + e] = (a == b) ? 1.0 : 0.0;
-    }
-  }
-}
-
 // selfegy(mShell, nSpecies) -> per-orbital on-site energies (mOrb, nSpecies)
 __global__ void k1_expand_selfegy(const double *selfegy, const int *orbShell, const int *nOrbSpecies,
                                   int mShell, int mOrb, int nSpecies, double *selfE) {
@@ -278,45 +143,31 @@ __global__ void k1_expand_selfegy(const double *selfegy, const int *orbShell, co
   selfE[i] = o < nOrbSpecies[sp] ? selfegy[orbShell[i] + mShell * sp] : 0.0;
 }
 
-template <int LMAX>
-int launchTyped(dftbp_b200_ctx *ctx, const K1Params &p, int grid, int warps, size_t smemBytes) {
-  DFTBP_CUDA(ctx, cudaFuncSetAttribute(k1_pair_build<LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smemBytes));
-  k1_pair_build<LMAX><<<grid, 32 * warps, smemBytes, ctx->stream>>>(p);
-  return 0;
-}
-
-template <int LMAX, bool DO_H, bool DO_S>
-int launchCols(dftbp_b200_ctx *ctx, const K1Params &p, long long items) {
-  constexpr int PMAX = ((LMAX + 1) * (LMAX + 1)) | 1;
-  const int warps = 8;
-  const size_t smemBytes = sizeof(double) * 64 * PMAX * warps;
+template <int LMAX, int WARPS, int CTAS>
+int launchTyped(dftbp_b200_ctx *ctx, const K1Params &p, long long items) {
+  constexpr int PITCH = ((2 * LMAX + 1) * (LMAX + 1) * (LMAX + 1)) | 1;
+  const size_t smemBytes = sizeof(double) * 32 * (size_t)PITCH * WARPS;
+  DFTBP_CHECK(ctx, smemBytes <= ctx->smemOptin, "build: staging tile does not fit into shared memory");
+  DFTBP_CUDA(ctx, cudaFuncSetAttribute(k1_pair_build<LMAX, WARPS, CTAS>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
   int perSm = 1;
-  DFTBP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k1_pair_build_cols<LMAX, DO_H, DO_S>,
-                                                                32 * warps, smemBytes));
+  DFTBP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k1_pair_build<LMAX, WARPS, CTAS>,
+                                                                32 * WARPS, smemBytes));
   const int grid = (int)std::max<long long>(
-      1, std::min<long long>((items + warps - 1) / warps, (long long)ctx->smCount * std::max(perSm, 1)));
-  k1_pair_build_cols<LMAX, DO_H, DO_S><<<grid, 32 * warps, smemBytes, ctx->stream>>>(p);
+      1, std::min<long long>((items + WARPS - 1) / WARPS, (long long)ctx->smCount * std::max(perSm, 1)));
+  k1_pair_build<LMAX, WARPS, CTAS><<<grid, 32 * WARPS, smemBytes, ctx->stream>>>(p);
   return 0;
 }
 
+// resident warps per SM: 8 x 2 (128 registers) or 6 x 3 (112 registers); the staging tiles
+// (11.5 KB per warp for spd) allow at most 19
 template <int LMAX>
-int launchColsAny(dftbp_b200_ctx *ctx, const K1Params &p, long long items) {
-  if (p.ham && p.over) return launchCols<LMAX, true, true>(ctx, p, items);
-  if (p.ham) return launchCols<LMAX, true, false>(ctx, p, items);
-  return launchCols<LMAX, false, true>(ctx, p, items);
-}
-
-// the column-staged kernel needs canonical s / sp / spd species and one grid per species pair
-bool colsEligible(const dftbp_b200_ctx *ctx) {
-  if (ctx->lMaxAll > 2) return false;
-  const char *env = getenv("DFTBP_B200_K1");
-  if (env && !strcmp(env, "groups")) return false;  // A/B switch for tools/gpu_probe.py
-  for (const SpPairProg &pg : ctx->progs) {
-    if (pg.canon1 < 0 || pg.canon2 < 0 || pg.canon1 > 2 || pg.canon2 > 2) return false;
-    if (pg.H.nGrid != pg.S.nGrid || pg.H.dist != pg.S.dist || pg.H.rMax != pg.S.rMax) return false;
-  }
-  return true;
+int launchTypedAny(dftbp_b200_ctx *ctx, const K1Params &p, long long items) {
+  const char *env = getenv("DFTBP_B200_K1_CFG");  // tuning switch (tools/gpu_probe.py)
+  const int cfg = env ? atoi(env) : 82;
+  if (cfg == 63) return launchTyped<LMAX, 6, 3>(ctx, p, items);
+  if (cfg == 44) return launchTyped<LMAX, 4, 4>(ctx, p, items);
+  return launchTyped<LMAX, 8, 2>(ctx, p, items);
 }
 
 int launchBuild(dftbp_b200_ctx *ctx, const double *selfegy, double *ham, double *over) {
@@ -327,10 +178,10 @@ int launchBuild(dftbp_b200_ctx *ctx, const double *selfegy, double *ham, double 
   const SortedPairs *sched;
   DFTBP_TRY(ensureSortedPairs(ctx, false, &sched));
   K1Params p;
-  p.progs = ctx->dProgs; p.items = sched->items; p.total = sched->total;
+  p.progs = ctx->dProgs; p.recs = sched->recs; p.total = sched->total;
   p.ld = g.mNeigh + 1; p.nSpecies = ctx->nSpecies; p.mOrb = ctx->mOrb;
   p.firstAtom = g.firstAtomMine; p.lastAtom = g.lastAtomMine;
-  p.coords = g.coords; p.species = g.species; p.iNeighbour = g.iNeighbour;
+  p.species = g.species;
   p.iPair = g.iPair; p.selfE = ctx->dSelfE; p.ham = nullptr; p.over = nullptr;
   const bool partial = ctx->nRanks > 1;  // other ranks' segments stay zero (assembleChunks sums)
   if (ham) {
@@ -351,26 +202,11 @@ int launchBuild(dftbp_b200_ctx *ctx, const double *selfegy, double *ham, double 
   }
   if (g.nWorkMine > 0) {
     ScopedTimer timer(ctx, kTimerSparseH0S);
-    // staging row per lane: the largest column group, (2 lmax + 1) * mOrb elements, odd pitch
-    p.pitch = ((2 * ctx->lMaxAll + 1) * ctx->mOrb) | 1;
-    const size_t perWarp = sizeof(double) * 32 * (size_t)p.pitch;
-    // 8 warps per CTA, 2 CTAs per SM: 16 warps x 128 registers fill the register file
-    int warps = (int)std::min<size_t>(8, (ctx->smemOptin - 2048) / perWarp);
-    DFTBP_CHECK(ctx, warps >= 1, "build: staging tile does not fit into shared memory");
-    const size_t smemBytes = perWarp * warps;
-    const int ctasPerSm = std::max<int>(1, (int)std::min<size_t>(ctx->smemPerSm / (smemBytes + 1024), 2));
     const long long items = ((g.nWorkMine + 31) / 32 + ctx->nSpecies * ctx->nSpecies) * ((ham && over) ? 2 : 1);
-    const int grid = (int)std::max<long long>(1, std::min<long long>((items + warps - 1) / warps,
-                                                                     (long long)ctx->smCount * ctasPerSm));
     int rc;
-    if (colsEligible(ctx)) {
-      const long long chunks = (g.nWorkMine + 31) / 32 + ctx->nSpecies * ctx->nSpecies;
-      if (ctx->lMaxAll == 0) rc = launchColsAny<0>(ctx, p, chunks);
-      else if (ctx->lMaxAll == 1) rc = launchColsAny<1>(ctx, p, chunks);
-      else rc = launchColsAny<2>(ctx, p, chunks);
-    } else if (ctx->lMaxAll <= 1) rc = launchTyped<1>(ctx, p, grid, warps, smemBytes);
-    else if (ctx->lMaxAll == 2) rc = launchTyped<2>(ctx, p, grid, warps, smemBytes);
-    else rc = launchTyped<3>(ctx, p, grid, warps, smemBytes);
+    if (ctx->lMaxAll <= 1) rc = launchTypedAny<1>(ctx, p, items);
+    else if (ctx->lMaxAll == 2) rc = launchTypedAny<2>(ctx, p, items);
+    else rc = launchTyped<3, 6, 1>(ctx, p, items);
     if (rc) return rc;
     ctx->launches++;
   }

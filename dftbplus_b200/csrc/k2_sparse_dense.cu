@@ -13,6 +13,8 @@
 // only then are the adds atomic, otherwise they are plain stores.
 // pack: pure gather + read-modify-write of the sparse array (it ACCUMULATES, like the reference);
 // the on-site block is symmetrised / hermitised from its lower triangle (:1084-1088, :906-910).
+#include <cstdlib>
+
 #include "block_desc.cuh"
 
 using namespace dftbp_b200;
@@ -77,50 +79,63 @@ __global__ void __launch_bounds__(256) k2_unpack(const K2Params p, const double 
       [] {});
 }
 
-template <bool CPLX>
+// kPackBatch blocks per pass: the dense gather and the sparse read of all of them are in flight
+// before the first store -- one block alone is only six loads per lane (profiles/
+// r01d_ncu_all_kernels.txt: 14 long-scoreboard stall cycles per issue), but the registers of a
+// large batch cost more occupancy than the batch wins (4 blocks: 100 registers, 2x slower).
+template <bool CPLX, int kPackBatch>
 __global__ void __launch_bounds__(256) k2_pack(const K2Params p, double *__restrict__ primitive,
                                                const double *__restrict__ square) {
   const int lane = threadIdx.x & 31;
-  forEachBlock(
-      p.desc, p.nWork, [] {},
-      [&](const BlockDesc &b) {
+  forEachBlockBatch<kPackBatch>(p.desc, p.nWork, [&](const BlockDesc(&b)[kPackBatch], int count) {
+    int maxElem = 0;
+#pragma unroll
+    for (int q = 0; q < kPackBatch; ++q)
+      if (q < count) maxElem = max(maxElem, (b[q].n12 & 0xFF) * (b[q].n12 >> 8));
+    for (int e0 = lane; e0 < maxElem; e0 += 32 * kUnroll) {
+      double val[kPackBatch][kUnroll], old[kPackBatch][kUnroll];
+#pragma unroll
+      for (int q = 0; q < kPackBatch; ++q) {
+        const bool onsite = b[q].iAt1 == b[q].iAt2f;
+        const int n2 = b[q].n12 >> 8, nElem = q < count ? (b[q].n12 & 0xFF) * n2 : 0;
+        const unsigned M2 = (1048576u + (unsigned)n2 - 1u) / (unsigned)n2;  // e / n2 = e * M2 >> 20 (e < 256)
         double pr = 1.0, pi = 0.0;
-        if (CPLX) blochPhase(p, b.iVec, -1.0, &pr, &pi);
-        const bool onsite = b.iAt1 == b.iAt2f;
-        const int n2 = b.n12 >> 8, nElem = (b.n12 & 0xFF) * n2;
-        const unsigned M2 = (1048576u + (unsigned)n2 - 1u) / (unsigned)n2;
-        double *__restrict__ prim = primitive + b.ind;
-        for (int e0 = lane; e0 < nElem; e0 += 32 * kUnroll) {
-          double val[kUnroll], old[kUnroll];
+        if (CPLX) blochPhase(p, b[q].iVec, -1.0, &pr, &pi);
+        const double *__restrict__ prim = primitive + b[q].ind;
 #pragma unroll
-          for (int k = 0; k < kUnroll; ++k) {
-            const int e = e0 + 32 * k;
-            val[k] = 0.0;
-            old[k] = 0.0;
-            if (e < nElem) {
-              const int a = (int)(((unsigned)e * M2) >> 20), r = e - a * n2;
-              // on-site: element above the diagonal (row < col) is taken from the lower triangle
-              const bool mirror = onsite && r < a;
-              const size_t pos = mirror ? (size_t)(b.jj + a) + (size_t)p.ldSq * (b.ii + r)
-                                        : (size_t)(b.jj + r) + (size_t)p.ldSq * (b.ii + a);
-              if (CPLX) {
-                const double2 z = __ldg(reinterpret_cast<const double2 *>(square) + pos);
-                const double zi = mirror ? -z.y : z.y;
-                val[k] = p.kWeight * (pr * z.x - pi * zi);
-              } else {
-                val[k] = __ldg(square + pos);
-              }
-              old[k] = prim[e];
+        for (int k = 0; k < kUnroll; ++k) {
+          const int e = e0 + 32 * k;
+          val[q][k] = 0.0;
+          old[q][k] = 0.0;
+          if (e < nElem) {
+            const int a = (int)(((unsigned)e * M2) >> 20), r = e - a * n2;
+            // on-site: element above the diagonal (row < col) is taken from the lower triangle
+            const bool mirror = onsite && r < a;
+            const size_t pos = mirror ? (size_t)(b[q].jj + a) + (size_t)p.ldSq * (b[q].ii + r)
+                                      : (size_t)(b[q].jj + r) + (size_t)p.ldSq * (b[q].ii + a);
+            if (CPLX) {
+              const double2 z = __ldg(reinterpret_cast<const double2 *>(square) + pos);
+              const double zi = mirror ? -z.y : z.y;
+              val[q][k] = p.kWeight * (pr * z.x - pi * zi);
+            } else {
+              val[q][k] = __ldg(square + pos);
             }
-          }
-#pragma unroll
-          for (int k = 0; k < kUnroll; ++k) {
-            const int e = e0 + 32 * k;
-            if (e < nElem) prim[e] = old[k] + val[k];
+            old[q][k] = prim[e];
           }
         }
-      },
-      [] {});
+      }
+#pragma unroll
+      for (int q = 0; q < kPackBatch; ++q) {
+        const int nElem = q < count ? (b[q].n12 & 0xFF) * (b[q].n12 >> 8) : 0;
+        double *__restrict__ prim = primitive + b[q].ind;
+#pragma unroll
+        for (int k = 0; k < kUnroll; ++k) {
+          const int e = e0 + 32 * k;
+          if (e < nElem) prim[e] = old[q][k] + val[q][k];
+        }
+      }
+    }
+  });
 }
 
 K2Params makeParams(dftbp_b200_ctx *ctx, int ldSq, const double *k, double kWeight) {
@@ -178,8 +193,16 @@ int packImpl(dftbp_b200_ctx *ctx, double *primitive, const void *square, int ld,
     ScopedTimer timer(ctx, kTimerDenseToSparse);
     const K2Params p = makeParams(ctx, ld, kPoint, kWeight);
     const int grid = gridForChunks(ctx, p.nWork);
-    if (cplx) k2_pack<true><<<grid, 256, 0, ctx->stream>>>(p, dPrim, dSq);
-    else k2_pack<false><<<grid, 256, 0, ctx->stream>>>(p, dPrim, dSq);
+    const char *env = getenv("DFTBP_B200_K2_BATCH");  // tuning switch (tools/gpu_probe.py)
+    const int batch = env ? atoi(env) : 2;
+    if (cplx) {
+      if (batch == 1) k2_pack<true, 1><<<grid, 256, 0, ctx->stream>>>(p, dPrim, dSq);
+      else k2_pack<true, 2><<<grid, 256, 0, ctx->stream>>>(p, dPrim, dSq);
+    } else {
+      if (batch == 1) k2_pack<false, 1><<<grid, 256, 0, ctx->stream>>>(p, dPrim, dSq);
+      else if (batch == 4) k2_pack<false, 4><<<grid, 256, 0, ctx->stream>>>(p, dPrim, dSq);
+      else k2_pack<false, 2><<<grid, 256, 0, ctx->stream>>>(p, dPrim, dSq);
+    }
     ctx->launches++;
   }
   return finish(ctx);

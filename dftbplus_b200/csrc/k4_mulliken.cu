@@ -8,6 +8,8 @@
 // blocks belong to the same iAtom1 (the sparse array is atom-major), so the column sums stay in a
 // register across the chunk and leave the warp only when the atom changes: about n2 global
 // reductions per block instead of 2*n1*n2.  qq ACCUMULATES like the reference.
+#include <cstdlib>
+
 #include "block_desc.cuh"
 
 using namespace dftbp_b200;
@@ -20,56 +22,66 @@ struct K4Params {
   int mOrb;
 };
 
+// EPL = elements per lane and block (3: blocks up to 96 elements, s/p/d; 8: f shells), BATCH = blocks
+// whose loads are issued together (BATCH * EPL * 2 independent loads per lane in flight)
+template <int EPL, int BATCH>
 __global__ void __launch_bounds__(256) k4_mulliken_orbital(const K4Params p, const double *__restrict__ over,
                                                            const double *__restrict__ rho,
                                                            double *__restrict__ qq) {
-  __shared__ double tile[8][kMaxOrb * kMaxOrb];
+  extern __shared__ double smem[];
+  constexpr int kTile = 32 * EPL;  // doubles per staged block
   const int lane = threadIdx.x & 31, wIn = threadIdx.x >> 5;
-  double *t = tile[wIn];
+  double *tile = smem + (size_t)wIn * BATCH * kTile;
   double colAcc = 0.0;  // lane a: sum(sqrTmp, dim=1)(a) accumulated over the blocks of curAtom
   int curAtom = -1, curN1 = 0;
   auto flush = [&]() {
     if (curAtom >= 0 && lane < curN1) atomicAdd(qq + lane + p.mOrb * curAtom, colAcc);
     colAcc = 0.0;
   };
-  forEachBlock(
-      p.desc, p.nWork, [&] { curAtom = -1; colAcc = 0.0; },
-      [&](const BlockDesc &b) {
-        const int n1 = b.n12 & 0xFF, n2 = b.n12 >> 8, nElem = n1 * n2;
-        if (b.iAt1 != curAtom) {
-          flush();
-          curAtom = b.iAt1;
-          curN1 = n1;
-        }
-        {
-          double o[8], r[8];
+  forEachBlockBatch<BATCH>(p.desc, p.nWork, [&](const BlockDesc(&b)[BATCH], int count) {
+    // ---- element products of all blocks of the batch -> shared tile (coalesced, all loads in flight)
+    {
+      double o[BATCH][EPL], r[BATCH][EPL];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {  // all loads of the block in flight at once
-            const int e = lane + 32 * k;
-            o[k] = e < nElem ? __ldg(over + b.ind + e) : 0.0;
-            r[k] = e < nElem ? __ldg(rho + b.ind + e) : 0.0;
-          }
+      for (int q = 0; q < BATCH; ++q) {
+        const int nElem = q < count ? (b[q].n12 & 0xFF) * (b[q].n12 >> 8) : 0;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int e = lane + 32 * k;
-            if (e < nElem) t[e] = o[k] * r[k];
-          }
+        for (int k = 0; k < EPL; ++k) {
+          const int e = lane + 32 * k;
+          o[q][k] = e < nElem ? __ldg(over + b[q].ind + e) : 0.0;
+          r[q][k] = e < nElem ? __ldg(rho + b[q].ind + e) : 0.0;
         }
-        __syncwarp();
-        if (lane < n1) {  // sum(sqrTmp, dim=1) -> qq(1:nOrb1, iAtom1)
-          double s = 0.0;
-          for (int r = 0; r < n2; ++r) s += t[r + n2 * lane];
-          colAcc += s;
-        }
-        if (b.iAt1 != b.iAt2f && lane >= 16 && lane - 16 < n2) {  // sum(sqrTmp, dim=2) -> qq(1:nOrb2, iAtom2f)
-          const int r = lane - 16;
-          double s = 0.0;
-          for (int a = 0; a < n1; ++a) s += t[r + n2 * a];
-          atomicAdd(qq + r + p.mOrb * b.iAt2f, s);
-        }
-        __syncwarp();
-      },
-      [&] { flush(); curAtom = -1; });
+      }
+#pragma unroll
+      for (int q = 0; q < BATCH; ++q)
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) tile[q * kTile + lane + 32 * k] = o[q][k] * r[q][k];
+    }
+    __syncwarp();
+    // ---- segmented sums, block by block: lane a -> column a, lane 16 + b -> row b
+    for (int q = 0; q < count; ++q) {
+      const int n1 = b[q].n12 & 0xFF, n2 = b[q].n12 >> 8;
+      const double *t = tile + q * kTile;
+      if (b[q].iAt1 != curAtom) {
+        flush();
+        curAtom = b[q].iAt1;
+        curN1 = n1;
+      }
+      if (lane < n1) {  // sum(sqrTmp, dim=1) -> qq(1:nOrb1, iAtom1)
+        double s = 0.0;
+        for (int rr = 0; rr < n2; ++rr) s += t[rr + n2 * lane];
+        colAcc += s;
+      }
+      if (b[q].iAt1 != b[q].iAt2f && lane >= 16 && lane - 16 < n2) {  // sum(sqrTmp, dim=2) -> qq(1:nOrb2, iAtom2f)
+        const int rr = lane - 16;
+        double s = 0.0;
+        for (int a = 0; a < n1; ++a) s += t[rr + n2 * a];
+        atomicAdd(qq + rr + p.mOrb * b[q].iAt2f, s);
+      }
+    }
+    __syncwarp();
+  });
+  flush();
 }
 
 // qq(:,:,iAtom1) += 0.5*(rho^T S + S^T rho);  qq(:,:,iAtom2f) += 0.5*(rho S^T + S rho^T)
@@ -125,8 +137,18 @@ int mullikenImpl(dftbp_b200_ctx *ctx, double *qq, const double *over, const doub
   if (p.nWork > 0) {
     ScopedTimer timer(ctx, kTimerMulliken);
     const int grid = gridFor(ctx, (p.nWork + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, 8);
-    if (block) k4_mulliken_block<<<grid, 256, 0, ctx->stream>>>(p, dOver, dRho, dQ);
-    else k4_mulliken_orbital<<<grid, 256, 0, ctx->stream>>>(p, dOver, dRho, dQ);
+    if (block) {
+      k4_mulliken_block<<<grid, 256, 0, ctx->stream>>>(p, dOver, dRho, dQ);
+    } else if (ctx->mOrb <= 9) {  // 8 warps x BATCH blocks x 96 doubles
+      const char *env = getenv("DFTBP_B200_K4_BATCH");  // tuning switch (tools/gpu_probe.py)
+      const int batch = env ? atoi(env) : 2;
+      if (batch == 1) k4_mulliken_orbital<3, 1><<<grid, 256, sizeof(double) * 8 * 1 * 96, ctx->stream>>>(p, dOver, dRho, dQ);
+      else if (batch == 4) k4_mulliken_orbital<3, 4><<<grid, 256, sizeof(double) * 8 * 4 * 96, ctx->stream>>>(p, dOver, dRho, dQ);
+      else k4_mulliken_orbital<3, 2><<<grid, 256, sizeof(double) * 8 * 2 * 96, ctx->stream>>>(p, dOver, dRho, dQ);
+    } else {
+      const size_t smemBytes = sizeof(double) * 8 * 2 * 256;
+      k4_mulliken_orbital<8, 2><<<grid, 256, smemBytes, ctx->stream>>>(p, dOver, dRho, dQ);
+    }
     ctx->launches++;
   }
   return finish(ctx);

@@ -31,16 +31,42 @@ namespace {
 
 struct K5Params {
   const SpPairProg *progs;
-  const int *items;
+  const PairRec *recs;  // sorted pair schedule with per-pair records (pair_sort.cu)
+  const int2 *atoms;    // (iAtom1, iAtom2f) per slot
   const int *total;
   int ld, nSpecies, mOrb, nAtom, nSpin, sparseSize, pitch;
-  const double *coords;
-  const int *species, *iNeighbour, *iPair, *img2CentCell;
   const double *DM;     // rho, first spin channel = wH
   const double *negWS;  // -wS: Erho (no SCC) or the array prepared by k5_force_weights
   double delta;
   double *deriv;
 };
+
+// this lane's pair of chunk `chunk`: bond vector, sparse offset, the two atoms, species-pair
+// program (warp-uniform).  Padding lanes shadow lane 0's pair and are not live; pairs whose
+// neighbour folds onto the atom itself do not contribute (forces.F90:186, :631).
+struct K5Pair {
+  double v0, v1, v2;
+  int ind, iAt1, iAt2f, sp;
+  bool live;
+};
+
+__device__ __forceinline__ K5Pair k5LoadPair(const K5Params &p, int chunk, int lane) {
+  const PairRec *r = p.recs + 32 * (size_t)chunk + lane;
+  const double2 xy = __ldg(reinterpret_cast<const double2 *>(r));
+  const int4 w = __ldg(reinterpret_cast<const int4 *>(r) + 1);
+  const int2 at = __ldg(p.atoms + 32 * (size_t)chunk + lane);
+  K5Pair k;
+  k.v0 = xy.x; k.v1 = xy.y; k.v2 = __hiloint2double(w.y, w.x);
+  k.ind = w.z;
+  k.sp = __shfl_sync(0xffffffffu, w.w, 0);  // lane 0 of a chunk is never padding
+  const double x0 = __shfl_sync(0xffffffffu, k.v0, 0), y0 = __shfl_sync(0xffffffffu, k.v1, 0),
+               z0 = __shfl_sync(0xffffffffu, k.v2, 0);
+  const bool valid = k.ind >= 0;
+  if (!valid) { k.v0 = x0; k.v1 = y0; k.v2 = z0; }
+  k.iAt1 = at.x; k.iAt2f = at.y;
+  k.live = valid && at.x != at.y;
+  return k;
+}
 
 // flag = 1 if any off-diagonal element of any shift block is non-zero (one warp per block)
 __global__ void __launch_bounds__(256) k5_shift_structure(const double *__restrict__ shift, int mOrb, int nBlocks,
@@ -143,19 +169,10 @@ __global__ void __launch_bounds__(320, 1) k5_derivative_shift(const K5Params p) 
   for (int item = blockIdx.x * nW + wIn; item < nItems; item += gridDim.x * nW) {
     const int chunk = item >> 1;
     const bool isS = item & 1;
-    int flat = __ldg(p.items + 32 * chunk + lane);
-    const bool valid = flat >= 0;
-    const int flat0 = __shfl_sync(0xffffffffu, flat, 0);  // lane 0 of a chunk is never padding
-    if (!valid) flat = flat0;
-    const int iAt1 = flat / p.ld;
-    const int iAt2 = __ldg(p.iNeighbour + flat) - 1;
-    const int iAt2f = __ldg(p.img2CentCell + iAt2) - 1;
-    // pairs whose neighbour folds onto the atom itself do not contribute (forces.F90:186, :631)
-    const bool live = valid && iAt1 != iAt2f;
-    const int sp1 = __shfl_sync(0xffffffffu, __ldg(p.species + iAt1), 0) - 1;
-    const int sp2 = __shfl_sync(0xffffffffu, __ldg(p.species + iAt2), 0) - 1;
-    const int ind = __ldg(p.iPair + flat);
-    const SpPairProg &pg = p.progs[sp1 + p.nSpecies * sp2];
+    const K5Pair pr = k5LoadPair(p, chunk, lane);
+    const bool live = pr.live;
+    const int ind = pr.ind, iAt1 = pr.iAt1, iAt2f = pr.iAt2f;
+    const SpPairProg &pg = p.progs[pr.sp];
     const SkTableDev tab = isS ? pg.S : pg.H;
     const int nElem = pg.nOrb1 * pg.nOrb2;
 
@@ -188,9 +205,7 @@ __global__ void __launch_bounds__(320, 1) k5_derivative_shift(const K5Params p) 
 
     // ---- 2. fold the weights of this lane's pair into W (independent of the bond vector), then six
     // displaced evaluations, each an interpolation + harmonics + short dot product (sk_lane_eval.cuh)
-    const double v0 = __ldg(p.coords + 3 * iAt2) - __ldg(p.coords + 3 * iAt1);
-    const double v1 = __ldg(p.coords + 3 * iAt2 + 1) - __ldg(p.coords + 3 * iAt1 + 1);
-    const double v2 = __ldg(p.coords + 3 * iAt2 + 2) - __ldg(p.coords + 3 * iAt1 + 2);
+    const double v0 = pr.v0, v1 = pr.v1, v2 = pr.v2;
     double g0 = 0.0, g1 = 0.0, g2 = 0.0;
     if (__any_sync(0xffffffffu, live)) {
       if (live) skLaneWBuildAny<LMAX>(pg, row);
@@ -226,6 +241,124 @@ __global__ void __launch_bounds__(320, 1) k5_derivative_shift(const K5Params p) 
   }
 }
 
+// ---- Differentiation = Richardson (getFirstDerivRichardson, dftb/nonscc.F90:488-600) -----------------
+// The reference extrapolates every matrix element of H' and S' separately: central differences
+// with h = 1/8, 1/16, ... (powers of two, exactly representable), a Richardson table of at most
+// three extrapolation columns, element-wise convergence test |dd(mm-1) - dd(mm)| <= 1e-11 * dd(mm)
+// (no absolute value on the right-hand side: elements with a negative derivative never pass it and
+// run until h reaches epsilon^(1/4), row 9), converged elements are frozen.  The table of a block
+// stops growing when all its elements have converged, but a frozen element does not change any
+// more and an unconverged one only exists when the table ran to the last row, so the result of an
+// element does not depend on the other elements of the block.  That is data dependent per element
+// and cannot be folded into the weights like the finite-difference form: every lane walks through
+// its pair's block in slices of kSlice elements, keeps the last two table rows of the slice in
+// local memory, re-evaluates the block for every slice and row (the evaluator is cheap compared
+// with the bookkeeping) and contracts the converged derivatives with the weights.
+// Rarely used (the default derivator is FiniteDiff); written for parity, not for speed.
+template <int LMAX>
+__global__ void __launch_bounds__(64) k5_derivative_shift_richardson(const K5Params p) {
+  constexpr int kSlice = 32, kMaxRows = 20, kMaxCols = 3;
+  constexpr double kTol = 1.0e-11;
+  const int lane = threadIdx.x & 31, wIn = threadIdx.x >> 5, nW = blockDim.x >> 5;
+  const int nChunks = __ldg(p.total) >> 5;
+  double tmp[kSlice];                    // tmp(:,:,1), then the central difference of the new row
+  double rowA[(kMaxCols + 1) * kSlice];  // dd(:,:,0:3,ii-1) and dd(:,:,0:3,ii), swapped every row
+  double rowB[(kMaxCols + 1) * kSlice];
+  double done[kSlice];                   // converged value per element
+  bool conv[kSlice];
+  for (int chunk = blockIdx.x * nW + wIn; chunk < nChunks; chunk += gridDim.x * nW) {
+    const K5Pair pr = k5LoadPair(p, chunk, lane);
+    if (!pr.live) continue;  // the evaluator has no warp-level synchronisation: lanes may diverge
+    const int ind = pr.ind, iAt1 = pr.iAt1, iAt2f = pr.iAt2f;
+    const SpPairProg &pg = p.progs[pr.sp];
+    const int nElem = pg.nOrb1 * pg.nOrb2;
+    const double v0 = pr.v0, v1 = pr.v1, v2 = pr.v2;
+    double g[3] = {0.0, 0.0, 0.0};
+    for (int which = 0; which < 2; ++which) {
+      const SkTableDev tab = which ? pg.S : pg.H;
+      // g = 2 (sum rho_1 . H' - sum (-wS) . S'); the S weights arrive negated (negWS)
+      const double *__restrict__ wgt = (which ? p.negWS : p.DM) + ind;
+      const double wSign = which ? -2.0 : 2.0;
+      for (int iCart = 0; iCart < 3; ++iCart) {
+        for (int e0 = 0; e0 < nElem; e0 += kSlice) {
+          const int nS = min(kSlice, nElem - e0);
+          // central difference (tmp(:,:,2) - tmp(:,:,1)) / (2 hh) of elements [e0, e0 + nS) -> tmp
+          auto centralDiff = [&](double hh) {
+            for (int kk = 1; kk <= 2; ++kk) {
+              const double sh = -(double)(2 * kk - 3) * hh;  // kk = 1: +hh, kk = 2: -hh (nonscc.F90:539)
+              const double d0 = iCart == 0 ? v0 + sh : v0, d1 = iCart == 1 ? v1 + sh : v1,
+                           d2 = iCart == 2 ? v2 + sh : v2;
+              const double dist = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+              const double ux = d0 / dist, uy = d1 / dist, uz = d2 / dist;
+              skLaneEvalAny<LMAX>(
+                  pg, tab, dist, ux, uy, uz,
+                  [&](int first, int e, double v) {
+                    const unsigned k = (unsigned)(first + e - e0);
+                    if (k < (unsigned)kSlice) tmp[k] = kk == 1 ? v : (v - tmp[k]) / (2.0 * hh);
+                  },
+                  [](int, int) {});
+            }
+          };
+          double hh = 0.125;
+          double *prev = rowA, *cur = rowB;
+          centralDiff(hh);
+          for (int k = 0; k < nS; ++k) {
+            cur[k] = tmp[k];
+            for (int c = 1; c <= kMaxCols; ++c) cur[c * kSlice + k] = 0.0;
+            conv[k] = false;
+            done[k] = 0.0;
+          }
+          int ii = 0, mm = 0;
+          bool all = false;
+          while (ii < kMaxRows && !all) {
+            hh = hh / 2.0;
+            if (hh <= 1.220703125e-4) break;  // epsilon(1.0_dp)**0.25_dp = 2^-13
+            ii += 1;
+            double *t = prev; prev = cur; cur = t;
+            centralDiff(hh);
+            mm = min(ii, kMaxCols);
+            all = true;
+            for (int k = 0; k < nS; ++k) {
+              if (conv[k]) continue;
+              cur[k] = tmp[k];
+              for (int kk = 1; kk <= mm; ++kk) {
+                const double pw = (double)(1 << (2 * kk));
+                cur[kk * kSlice + k] = (pw * cur[(kk - 1) * kSlice + k] - prev[(kk - 1) * kSlice + k]) / (pw - 1.0);
+              }
+              const double hi = cur[mm * kSlice + k];
+              const double diff = fabs(cur[(mm - 1) * kSlice + k] - hi);
+              if (diff <= kTol * hi) {
+                conv[k] = true;
+                done[k] = hi;
+              } else {
+                all = false;
+              }
+            }
+          }
+          // deriv(:,:,iCart) = dd(:,:,mm,ii)
+          double acc = 0.0;
+          for (int k = 0; k < nS; ++k)
+            acc = fma(__ldg(wgt + e0 + k), conv[k] ? done[k] : cur[mm * kSlice + k], acc);
+          g[iCart] = fma(wSign, acc, g[iCart]);
+        }
+      }
+    }
+    atomicAdd(p.deriv + 3 * iAt1, g[0]);
+    atomicAdd(p.deriv + 3 * iAt1 + 1, g[1]);
+    atomicAdd(p.deriv + 3 * iAt1 + 2, g[2]);
+    atomicAdd(p.deriv + 3 * iAt2f, -g[0]);
+    atomicAdd(p.deriv + 3 * iAt2f + 1, -g[1]);
+    atomicAdd(p.deriv + 3 * iAt2f + 2, -g[2]);
+  }
+}
+
+template <int LMAX>
+int launchRichardson(dftbp_b200_ctx *ctx, const K5Params &p, long long chunks) {
+  const int grid = (int)std::max<long long>(1, std::min<long long>((chunks + 1) / 2, (long long)ctx->smCount * 8));
+  k5_derivative_shift_richardson<LMAX><<<grid, 64, 0, ctx->stream>>>(p);
+  return 0;
+}
+
 template <int LMAX>
 int launchTyped(dftbp_b200_ctx *ctx, const K5Params &p, long long items, int warps, size_t smemBytes) {
   DFTBP_CUDA(ctx, cudaFuncSetAttribute(k5_derivative_shift<LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -249,19 +382,15 @@ extern "C" int dftbp_b200_derivative_shift(dftbp_b200_ctx *ctx, double *deriv, c
   DFTBP_CHECK(ctx, g.nAtom > 0, "derivative_shift: no geometry set");
   DFTBP_CHECK(ctx, deriv && DM && EDM, "derivative_shift: null argument");
   DFTBP_CHECK(ctx, nSpin == 1 || nSpin == 2 || nSpin == 4, "derivative_shift: nSpin must be 1, 2 or 4");
-  if (diffType == DFTBP_B200_DIFF_RICHARDSON)
-    return fail(ctx, DFTBP_B200_ENOTIMPL,
-                "Differentiation = Richardson (nonscc.F90:488-600) is not built yet; use FiniteDiff");
-  DFTBP_CHECK(ctx, diffType == DFTBP_B200_DIFF_FINITE, "derivative_shift: invalid differentiator type");
+  DFTBP_CHECK(ctx, diffType == DFTBP_B200_DIFF_FINITE || diffType == DFTBP_B200_DIFF_RICHARDSON,
+              "derivative_shift: invalid differentiator type");
   DFTBP_TRY(syncPrograms(ctx));
   const SortedPairs *sched;
   DFTBP_TRY(ensureSortedPairs(ctx, true, &sched));
   K5Params p;
-  p.progs = ctx->dProgs; p.items = sched->items; p.total = sched->total;
+  p.progs = ctx->dProgs; p.recs = sched->recs; p.atoms = sched->atoms; p.total = sched->total;
   p.ld = g.mNeigh + 1; p.nSpecies = ctx->nSpecies;
   p.mOrb = ctx->mOrb; p.nAtom = g.nAtom; p.nSpin = nSpin; p.sparseSize = g.sparseSize;
-  p.coords = g.coords; p.species = g.species; p.iNeighbour = g.iNeighbour; p.iPair = g.iPair;
-  p.img2CentCell = g.img2CentCell;
   // nonscc.F90:43: deltaXDiff = epsilon(1.0_dp)**0.25_dp
   p.delta = delta > 0.0 ? delta : 1.220703125e-4;
   // the non-SCC routine takes DM(:) only; the block routine DM(:, nSpin)
@@ -302,7 +431,12 @@ extern "C" int dftbp_b200_derivative_shift(dftbp_b200_ctx *ctx, double *deriv, c
     const size_t smemBytes = perWarp * warps;
     const long long items = 2 * ((g.nWorkLoad + 31) / 32 + ctx->nSpecies * ctx->nSpecies);
     int rc;
-    if (ctx->lMaxAll <= 1) rc = launchTyped<1>(ctx, p, items, warps, smemBytes);
+    if (diffType == DFTBP_B200_DIFF_RICHARDSON) {
+      const long long chunks = items / 2;
+      if (ctx->lMaxAll <= 1) rc = launchRichardson<1>(ctx, p, chunks);
+      else if (ctx->lMaxAll == 2) rc = launchRichardson<2>(ctx, p, chunks);
+      else rc = launchRichardson<3>(ctx, p, chunks);
+    } else if (ctx->lMaxAll <= 1) rc = launchTyped<1>(ctx, p, items, warps, smemBytes);
     else if (ctx->lMaxAll == 2) rc = launchTyped<2>(ctx, p, items, warps, smemBytes);
     else rc = launchTyped<3>(ctx, p, items, warps, smemBytes);
     if (rc) return rc;

@@ -104,10 +104,19 @@ __global__ void __launch_bounds__(1024) ps_scan(int *__restrict__ hist, int nBuc
 }
 
 // pass 2: every CTA counts its slab again (from the stored keys), reserves one contiguous range
-// per occupied bin with a single global atomic, and places its items with shared-memory atomics
+// per occupied bin with a single global atomic, and places its items with shared-memory atomics.
+// Together with the flat id it writes the pair's record (bond vector, sparse offset, species-pair
+// program, the two atoms): the consumers read one coalesced 32-byte record per lane instead of
+// walking the index chain.
 __global__ void __launch_bounds__(kSortThreads) ps_scatter(const int *__restrict__ work, long long nWork,
                                                            int nKeys, const int *__restrict__ keys,
-                                                           int *__restrict__ cursors, int *__restrict__ items) {
+                                                           int *__restrict__ cursors, int *__restrict__ items,
+                                                           PairRec *__restrict__ recs, int2 *__restrict__ atoms,
+                                                           int ld, int nSpecies, const double *__restrict__ coords,
+                                                           const int *__restrict__ species,
+                                                           const int *__restrict__ iNeighbour,
+                                                           const int *__restrict__ iPair,
+                                                           const int *__restrict__ img2CentCell) {
   extern __shared__ int sh[];
   for (int k = threadIdx.x; k < nKeys; k += kSortThreads) sh[k] = 0;
   __syncthreads();
@@ -125,7 +134,21 @@ __global__ void __launch_bounds__(kSortThreads) ps_scatter(const int *__restrict
   __syncthreads();
   for (long long i = lo + threadIdx.x; i < hi; i += kSortThreads) {
     const int key = keys[i];
-    if (key >= 0) items[atomicAdd(sh + key, 1)] = __ldg(work + i);
+    if (key < 0) continue;
+    const int flat = __ldg(work + i);
+    const int iAt1 = flat / ld;
+    const int iAt2 = __ldg(iNeighbour + flat) - 1;
+    PairRec r;
+    // vect(:) = coords(:,iAt2) - coords(:,iAt1), nonscc.F90:413
+    r.vx = __ldg(coords + 3 * iAt2) - __ldg(coords + 3 * iAt1);
+    r.vy = __ldg(coords + 3 * iAt2 + 1) - __ldg(coords + 3 * iAt1 + 1);
+    r.vz = __ldg(coords + 3 * iAt2 + 2) - __ldg(coords + 3 * iAt1 + 2);
+    r.ind = __ldg(iPair + flat);
+    r.sp = (__ldg(species + iAt1) - 1) + nSpecies * (__ldg(species + iAt2) - 1);
+    const int pos = atomicAdd(sh + key, 1);
+    items[pos] = flat;
+    recs[pos] = r;
+    atoms[pos] = make_int2(iAt1, __ldg(img2CentCell + iAt2) - 1);
   }
 }
 
@@ -148,10 +171,12 @@ int growTo(dftbp_b200_ctx *ctx, T **p, long long *cap, long long need) {
 namespace dftbp_b200 {
 
 void freeSortedPairs(dftbp_b200_ctx *g) {
-  cudaFree(g->sortLoad.items);
-  cudaFree(g->sortLoad.total);
-  cudaFree(g->sortMine.items);
-  cudaFree(g->sortMine.total);
+  for (SortedPairs *sp : {&g->sortLoad, &g->sortMine}) {
+    cudaFree(sp->items);
+    cudaFree(sp->recs);
+    cudaFree(sp->atoms);
+    cudaFree(sp->total);
+  }
   cudaFree(g->sortKeys);
   cudaFree(g->sortBins);
   g->sortMine = g->sortLoad = SortedPairs();
@@ -174,10 +199,13 @@ int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out
   const int nKeys = (int)nBins64;
   const long long cap = ((nWork + 31) & ~31LL) + 32LL * nBuckets + 32;
   if (sp.capacity < cap) {
-    if (sp.items) cudaFree(sp.items);
-    sp.items = nullptr;
-    long long c = 0;
+    cudaFree(sp.items); cudaFree(sp.recs); cudaFree(sp.atoms);
+    sp.items = nullptr; sp.recs = nullptr; sp.atoms = nullptr;
+    sp.capacity = 0;
+    long long c = 0, c2 = 0, c3 = 0;
     DFTBP_TRY(growTo(ctx, &sp.items, &c, cap));
+    DFTBP_TRY(growTo(ctx, &sp.recs, &c2, cap));
+    DFTBP_TRY(growTo(ctx, &sp.atoms, &c3, cap));
     sp.capacity = c;
   }
   if (!sp.total) DFTBP_CUDA(ctx, cudaMalloc((void **)&sp.total, sizeof(int)));
@@ -185,6 +213,8 @@ int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out
   DFTBP_TRY(growTo(ctx, &ctx->sortBins, &ctx->sortBinsCap, nBins64));
   DFTBP_CUDA(ctx, cudaMemsetAsync(ctx->sortBins, 0, sizeof(int) * nBins64, ctx->stream));
   DFTBP_CUDA(ctx, cudaMemsetAsync(sp.items, 0xFF, sizeof(int) * sp.capacity, ctx->stream));
+  // padding slots: ind = -1 (the consumers then shadow lane 0 of the chunk)
+  DFTBP_CUDA(ctx, cudaMemsetAsync(sp.recs, 0xFF, sizeof(PairRec) * sp.capacity, ctx->stream));
   const double binScale = (double)nBins / (ctx->cutoff > 0.0 ? ctx->cutoff : 1.0);
   if (nWork > 0) {
     // slabs of at least 2048 items per CTA (aggregation), at most one CTA per SM
@@ -197,7 +227,9 @@ int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out
                                                            ctx->sortKeys, ctx->sortBins);
     ps_scan<<<1, 1024, 0, ctx->stream>>>(ctx->sortBins, nBuckets, nBins, sp.total);
     ps_scatter<<<grid, kSortThreads, smemBytes, ctx->stream>>>(work, nWork, nKeys, ctx->sortKeys, ctx->sortBins,
-                                                              sp.items);
+                                                              sp.items, sp.recs, sp.atoms, g.mNeigh + 1,
+                                                              ctx->nSpecies, g.coords, g.species, g.iNeighbour,
+                                                              g.iPair, g.img2CentCell);
     ctx->launches += 3;
   } else {
     DFTBP_CUDA(ctx, cudaMemsetAsync(sp.total, 0, sizeof(int), ctx->stream));

@@ -21,11 +21,42 @@
 namespace dftbp_b200 {
 
 struct LaneInterp {
-  double w[8];  // Lagrange weights of rows j0 .. j0+7          (mode 0)
-  double xr;    // rMax - r                                     (mode 1)
+  double w[8];  // Lagrange weights of rows j0 .. j0+7               (mode 0)
+  double xr;    // tail abscissa / offset into the spline interval    (mode 1, 3)
   int j0;       // first row (0-based) of the window
-  int mode;     // 0 = polynomial, 1 = 5th order tail, 2 = beyond rMax -> 0
+  int mode;     // 0 = polynomial, 1 = 5th order tail, 2 = beyond the cutoff -> 0,
+                // 3 = free cubic spline over the last grid interval (skEqGridOld only)
 };
+
+// SlakoEqGrid_interOld_ (OldSKInterpolation = Yes), slakoeqgrid.F90:248-317, the part that depends
+// on r only.  The 3-point polynomial is expressed in the same 8-row window form as the 8-point one
+// (five zero weights; the window is shifted so that it never leaves the column), so the integral
+// loops below are shared by the two methods.
+__device__ __forceinline__ void laneInterpSetupOld(const SkTableDev &t, double r, LaneInterp &li) {
+  const int leng = t.nGrid;
+  const int ind = (int)floor(r / t.dist);
+  if (ind < leng - 1) {
+    li.mode = 0;
+    int iLast = min(leng, ind + 2);
+    iLast = max(iLast, 3);
+    const int jf = iLast - 3;                   // first row of the 3-point window, row j sits at (j+1)*dist
+    const int jw = max(0, min(jf, leng - 8));   // 8-row window that contains it
+    const int off = jf - jw;
+    const double u = (r - (double)(jf + 1) * t.dist) * t.invDist;
+    const double w0 = 0.5 * ((u - 1.0) * (u - 2.0)), w1 = -(u * (u - 2.0)), w2 = 0.5 * (u * (u - 1.0));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) li.w[k] = k == off ? w0 : (k == off + 1 ? w1 : (k == off + 2 ? w2 : 0.0));
+    li.j0 = jw;
+  } else if (ind < leng) {
+    li.mode = 3;  // between the penultimate and the last grid point
+    li.xr = r - (double)(leng - 1) * t.dist;
+  } else if (ind < t.mIndM1) {
+    li.mode = 1;  // dr = rr - (mInd - 1) * incr; xr = dr * invdistFudge
+    li.xr = (r - t.tailX0) * t.tailInvDx;
+  } else {
+    li.mode = 2;
+  }
+}
 
 // SlakoEqGrid_interNew_, slakoeqgrid.F90:183-244, the part that depends on r only
 __device__ __forceinline__ void laneInterpSetup(const SkTableDev &t, double r, LaneInterp &li) {
@@ -33,6 +64,10 @@ __device__ __forceinline__ void laneInterpSetup(const SkTableDev &t, double r, L
   li.xr = 0.0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) li.w[j] = 0.0;
+  if (t.method == DFTBP_B200_SK_EQGRID_OLD) {  // uniform per table
+    laneInterpSetupOld(t, r, li);
+    return;
+  }
   if (r >= t.rMax) {
     li.mode = 2;
     return;
@@ -60,8 +95,8 @@ __device__ __forceinline__ void laneInterpSetup(const SkTableDev &t, double r, L
     li.w[6] = (-1.0 / 720.0) * (p6 * s6);
     li.w[7] = (1.0 / 5040.0) * p7;
   } else {
-    li.mode = 1;
-    li.xr = -(r - t.rMax);
+    li.mode = 1;  // xr = (rr - rMax) * invdx, invdx = -1 / distFudge
+    li.xr = (r - t.tailX0) * t.tailInvDx;
   }
 }
 
@@ -75,16 +110,26 @@ __device__ __forceinline__ double laneInterp(const SkTableDev &t, const LaneInte
     return acc;
   }
   if (li.mode == 1) {
-    // poly5ToZero (math/interpolation.F90:31-67) with dx = -1, invdx = -1; y1, y1', y1'' prepared
-    // on the host in the reference's operation order (context.cu: tailCoefficients)
-    const double y1 = __ldg(t.tail + 3 * col), y1p = __ldg(t.tail + 3 * col + 1),
-                 y1pp = __ldg(t.tail + 3 * col + 2);
-    const double dx1 = -y1p, dx2 = y1pp;
-    const double dd = 10.0 * y1 - 4.0 * dx1 + 0.5 * dx2;
-    const double ee = -15.0 * y1 + 7.0 * dx1 - dx2;
-    const double ff = 6.0 * y1 - 3.0 * dx1 + 0.5 * dx2;
+    // poly5ToZero (math/interpolation.F90:31-67): the coefficients dd, ee, ff of the three highest
+    // powers were formed on the host from (y, y', y'') at the start of the tail, in the reference's
+    // operation order (context.cu: tailCoefficients / tailCoefficientsOld)
+    const double dd = __ldg(t.tail + 3 * col), ee = __ldg(t.tail + 3 * col + 1), ff = __ldg(t.tail + 3 * col + 2);
     const double xr = li.xr;
     return ((ff * xr + ee) * xr + dd) * xr * xr * xr;
+  }
+  if (li.mode == 3) {
+    // free cubic spline through the last three grid points (slakoeqgrid.F90:285-294,
+    // freeCubicSpline math/interpolation.F90:74-120)
+    const double *__restrict__ c = t.tab + (size_t)col * t.nGrid + (t.nGrid - 3);
+    const double y0 = __ldg(c), y1 = __ldg(c + 1), y2 = __ldg(c + 2);
+    const double incr = t.dist;
+    const double y1p = (y2 - y0) / (2.0 * incr);
+    const double y1pp = (y2 + y0 - 2.0 * y1) / (incr * incr);
+    const double dx1 = 1.0 / incr;
+    const double cc = 0.5 * y1pp;
+    const double d3 = (((y2 - y1) * dx1 - y1p) * dx1 - 0.5 * y1pp) * dx1;
+    const double xx = li.xr;
+    return ((d3 * xx + cc) * xx + y1p) * xx + y1;
   }
   return 0.0;
 }
@@ -234,52 +279,6 @@ __device__ __forceinline__ void skLaneEvalAny(const SpPairProg &pg, const SkTabl
   }
 }
 
-
-// ---- column-wise canonical evaluator (K1) --------------------------------------------------------------
-// H0 and S of one pair in a single pass, one block column (nOrb2 contiguous elements) at a time:
-//   emit(e, h, s)   element e (0 .. N2-1) of the current column, H0 and S value
-//   endCol(col)     column col (0-based, atom-1 orbital) is complete
-// The harmonics, the Lagrange weights (both tables share the grid: checked on the host) and the
-// Gaunt sums t_k(a, b) are shared between the two matrices; only the A_k differ.  The caller
-// stages ONE column per lane, so the staging tile is 32 x N2 doubles per matrix instead of
-// 32 x (largest column group).
-template <int LM1, int LM2, bool DO_H, bool DO_S, class Emit, class EndCol>
-__device__ __forceinline__ void skLaneEvalCanonCols(const SkTableDev &tH, const SkTableDev &tS, double r, double dx,
-                                                    double dy, double dz, Emit &&emit, EndCol &&endCol) {
-  constexpr int LY = LM1 + LM2;
-  constexpr int NG = canonIntegStart(LM1 + 1, 0, LM2) - canonIntegStart(LM1, 0, LM2);  // largest group
-  LaneInterp li;
-  laneInterpSetup(DO_H ? tH : tS, r, li);
-  double Y[(LY + 1) * (LY + 1)];
-  skg::harmonics<LY>(dx, dy, dz, Y);
-  staticFor<LM1 + 1>([&](auto l1c) {
-    constexpr int l1 = decltype(l1c)::value;
-    constexpr int g0 = canonIntegStart(l1, 0, LM2);
-    constexpr int ng = canonIntegStart(l1 + 1, 0, LM2) - g0;
-    double aH[NG], aS[NG];
-    {
-      double vH[NG], vS[NG];
-      if constexpr (DO_H) laneInterpRange<g0, ng, NG>(tH, li, vH);
-      if constexpr (DO_S) laneInterpRange<g0, ng, NG>(tS, li, vS);
-      staticFor<LM2 + 1>([&](auto l2c) {
-        constexpr int l2 = decltype(l2c)::value;
-        constexpr int off = canonIntegStart(l1, l2, LM2) - g0;
-        if constexpr (DO_H) skg::acoefT<l1, l2>(vH + off, aH + off);
-        if constexpr (DO_S) skg::acoefT<l1, l2>(vS + off, aS + off);
-      });
-    }
-    staticFor<2 * l1 + 1>([&](auto ac) {
-      constexpr int a = decltype(ac)::value;
-      staticFor<LM2 + 1>([&](auto l2c) {
-        constexpr int l2 = decltype(l2c)::value;
-        constexpr int off = canonIntegStart(l1, l2, LM2) - g0;
-        skg::colT<l1, l2, a, DO_H, DO_S>(Y, aH + off, aS + off,
-                                         [&](int b, double h, double sv) { emit(l2 * l2 + b, h, sv); });
-      });
-      endCol(l1 * l1 + a);
-    });
-  });
-}
 
 // ---- weight-contracted form (K5) ---------------------------------------------------------------------
 // A contraction sum_e w_e E_e(d) of the block with fixed weights w (rho, E-rho, ...) is

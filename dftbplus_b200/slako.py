@@ -110,7 +110,9 @@ class SlakoSet:
     """All tables of a parameter set for the given species: what readSKFiles leaves in
     TSlakoCont (H and S), plus on-site energies, Hubbard U and reference occupations."""
 
-    def __init__(self, directory, names, ang_shells, truncation_cutoff=None):
+    def __init__(self, directory, names, ang_shells, truncation_cutoff=None, method=2):
+        # method: 2 = skEqGridNew (default), 1 = skEqGridOld (OldSKInterpolation = Yes), slakoeqgrid.F90:62-65
+        self.method = method
         self.names, self.ang_shells = list(names), [list(a) for a in ang_shells]
         nsp = len(names)
         files = {}
@@ -133,15 +135,16 @@ class SlakoSet:
         self.n_orb_species = np.array([sum(2 * l + 1 for l in a) for a in self.ang_shells], dtype=np.int32)
 
     def cutoff(self):
-        return max(t[1].shape[0] * t[0] + 1.0 for t in self.tables.values())  # + distFudge
+        fudge = 0.3 if self.method == 1 else 1.0     # distFudgeOld / distFudge, slakoeqgrid.F90:162-179
+        return max(t[1].shape[0] * t[0] + fudge for t in self.tables.values())
 
     def upload(self, hot):
         """set_orbitals + set_sk_table for every ordered pair on a HotPath (or an oracle Model-like
         object with the same two methods)."""
         hot.set_orbitals(self.ang_shells)
         for (i, j), (dist, ham, over) in self.tables.items():
-            hot.set_sk_table(0, i, j, dist, ham)
-            hot.set_sk_table(1, i, j, dist, over)
+            hot.set_sk_table(0, i, j, dist, ham, self.method)
+            hot.set_sk_table(1, i, j, dist, over, self.method)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -27,7 +27,7 @@ SPECIES = {
 }
 
 
-def make_slako_set(names, directory=None, n_grid=500, dist=0.02, seed=20250101):
+def make_slako_set(names, directory=None, n_grid=500, dist=0.02, seed=20250101, method=2):
     """Write (once) and read a synthetic parameter set for the named species."""
     if directory is None:
         directory = os.path.join(tempfile.gettempdir(), "dftbp_b200_slakos",
@@ -39,7 +39,7 @@ def make_slako_set(names, directory=None, n_grid=500, dist=0.02, seed=20250101):
                                   [SPECIES[n][2] for n in names], [SPECIES[n][3] for n in names],
                                   [SPECIES[n][4] for n in names], dist=dist, n_grid=n_grid, seed=seed)
         open(marker, "w").close()
-    return slako.SlakoSet(directory, names, shells), directory
+    return slako.SlakoSet(directory, names, shells, method=method), directory
 
 
 def _water_molecule():
@@ -105,9 +105,9 @@ def fe_c(cells=(16, 16, 8), c_fraction=0.25, seed=2):
                 latvec=np.diag(np.array(cells, dtype=np.float64) * a), kpoints=None, n_spin=2)
 
 
-def prepare(workload, n_grid=500, dist=0.02, seed=20250101, slako_dir=None):
+def prepare(workload, n_grid=500, dist=0.02, seed=20250101, slako_dir=None, method=2):
     """geometry arrays + SlakoSet for a workload dict."""
-    sk, directory = make_slako_set(workload["names"], slako_dir, n_grid=n_grid, dist=dist, seed=seed)
+    sk, directory = make_slako_set(workload["names"], slako_dir, n_grid=n_grid, dist=dist, seed=seed, method=method)
     cutoff = sk.cutoff()
     geo = geometry.build_geometry(workload["coord0"], workload["species0"], sk.n_orb_species,
                                   workload["latvec"], cutoff)

@@ -84,7 +84,7 @@ def get_full_table(sk12, sk21, ang_shells1, ang_shells2):
     return sk_ham, sk_over
 
 
-def load_model(directory, names, ang_shells):
+def load_model(directory, names, ang_shells, method=2):
     """readSKFiles (parser.F90:3668-3886) into an oracle Model; returns (model, selfegy)."""
     import os
     from . import oracle
@@ -94,7 +94,7 @@ def load_model(directory, names, ang_shells):
     for i in range(len(names)):
         for j in range(len(names)):
             ham, over = get_full_table(files[(i, j)], files[(j, i)], ang_shells[i], ang_shells[j])
-            model.set_table(0, i + 1, j + 1, files[(i, j)]["dist"], ham)
-            model.set_table(1, i + 1, j + 1, files[(i, j)]["dist"], over)
+            model.set_table(0, i + 1, j + 1, files[(i, j)]["dist"], ham, method)
+            model.set_table(1, i + 1, j + 1, files[(i, j)]["dist"], over, method)
     selfegy = [[files[(i, i)]["skSelf"][l] for l in ang_shells[i]] for i in range(len(names))]
     return model, selfegy

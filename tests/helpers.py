@@ -40,16 +40,29 @@ def extra_workloads():
                latvec=0.5 * a * np.array([[0.0, 1, 1], [1, 0, 1], [1, 1, 0]]),
                kpoints=np.array([[0.0, 0, 0], [0.5, 0, 0], [0.25, 0.25, 0.25], [0.1, -0.3, 0.45]]),
                kweights=np.array([0.125, 0.125, 0.5, 0.25]), n_spin=1)
-    return {"ce_o": ce, "si2": si2}
+    # one Fe atom at the origin and neighbours at chosen distances: every branch of both SK
+    # interpolation methods (grid 0.02 x 500: polynomial, last-interval cubic spline of the old
+    # method, 5th-order tails 10.0-10.28 (old) / 10.0-11.0 (new), beyond the cutoff)
+    rs = [1.37, 2.5, 4.013, 7.7, 9.93, 9.965, 9.9850001, 9.995, 10.0000001, 10.013, 10.1, 10.27,
+          10.2799, 10.2801, 10.29, 10.5, 10.9, 10.9999, 11.0001]
+    pts = [np.zeros(3)]
+    for k, r in enumerate(rs):
+        u = rng.normal(size=3)
+        pts.append(r * u / np.linalg.norm(u))
+    scan = dict(name="scan", names=["Fe", "C"], coord0=np.array(pts),
+                species0=np.array([1] + [1 + (k % 2) for k in range(len(rs))]), latvec=None, kpoints=None,
+                n_spin=1)
+    return {"ce_o": ce, "si2": si2, "scan": scan}
 
 
 @functools.lru_cache(maxsize=None)
-def case(name):
-    """(workload, SlakoSet, geometry dict, oracle Model, selfegy) for a named workload."""
+def case(name, method=2):
+    """(workload, SlakoSet, geometry dict, oracle Model, selfegy) for a named workload.
+    method: 2 = skEqGridNew, 1 = skEqGridOld (OldSKInterpolation = Yes)."""
     ex = extra_workloads()
     w = ex[name] if name in ex else workloads.BY_NAME[name]()
-    sk, geo, directory = workloads.prepare(w)
-    model, selfegy = oldskdata.load_model(directory, w["names"], sk.ang_shells)
+    sk, geo, directory = workloads.prepare(w, method=method)
+    model, selfegy = oldskdata.load_model(directory, w["names"], sk.ang_shells, method=method)
     return w, sk, geo, model, selfegy
 
 

@@ -18,10 +18,10 @@ def hp_cache():
     from dftbplus_b200.api import HotPath
     cache = {}
 
-    def get(name, rank=0, nranks=1):
-        key = (name, rank, nranks)
+    def get(name, rank=0, nranks=1, method=2):
+        key = (name, rank, nranks, method)
         if key not in cache:
-            w, sk, geo, model, selfegy = case(name)
+            w, sk, geo, model, selfegy = case(name, method)
             hp = HotPath(0, rank, nranks)
             sk.upload(hp)
             hp.set_geometry(geo)
@@ -57,6 +57,33 @@ def test_k1_tail_region_and_cutoff(hp_cache):
         blk, ref = s[geo["iPair"][i, k]:geo["iPair"][i, k] + n], s_ref[geo["iPair"][i, k]:geo["iPair"][i, k] + n]
         assert np.abs(blk - ref).max() <= 1e-12 * np.abs(s_ref).max()
         assert np.allclose(blk, ref, rtol=1e-9, atol=1e-16)        # small tail values keep relative accuracy
+
+
+@pytest.mark.parametrize("name", ["scan", "h2o", "ce_o", "fec128"])
+@pytest.mark.parametrize("method", [1, 2])
+def test_k1_interpolation_methods(name, method, hp_cache):
+    """OldSKInterpolation = Yes (skEqGridOld, slakoeqgrid.F90:248-317) and the default method on a
+    distance scan that visits every branch: polynomial, cubic spline, tail, beyond the cutoff."""
+    w, sk, geo, model, selfegy = case(name, method)
+    hp = hp_cache(name, method=method)
+    assert abs(hp.sk_cutoff() - model.cutoff()) < 1e-12 and abs(sk.cutoff() - model.cutoff()) < 1e-12
+    h, s = hp.buildH0S(sk.selfegy)
+    h_ref, s_ref = oracle.build_h0(model, geo, selfegy), oracle.build_s(model, geo)
+    assert_sparse_close(h, h_ref, what="H0 %s method %d" % (name, method))
+    assert_sparse_close(s, s_ref, what="S %s method %d" % (name, method))
+    if name == "scan":
+        # block by block, relative to the block's own size: the tail values are tiny
+        r = np.sqrt(geo["neighDist2"])
+        seen = set()
+        for k in range(1, geo["nNeighbourSK"][0] + 1):
+            j = geo["iNeighbour"][0, k] - 1
+            n = geo["nOrbAtom"][0] * geo["nOrbAtom"][geo["img2CentCell"][j] - 1]
+            a = geo["iPair"][0, k]
+            for got, ref in ((h[a:a + n], h_ref[a:a + n]), (s[a:a + n], s_ref[a:a + n])):
+                assert np.abs(got - ref).max() <= 1e-11 * np.abs(ref).max() + 1e-18, (method, r[0, k])
+            seen.add(bool(np.abs(s_ref[a:a + n]).max() > 0))
+        assert seen == {True} or seen == {True, False}
+        assert geo["nNeighbourSK"][0] >= (14 if method == 1 else 18)
 
 
 def test_k1_partial_ranks_sum_to_full(hp_cache):
@@ -203,6 +230,28 @@ def test_k5_derivative_shift(name, hp_cache):
         got = hp.derivative_shift(dm[:n_spin], edm, shift=sh)
         assert np.abs(got - ref).max() < TOL_FORCE, (n_spin, np.abs(got - ref).max())
         assert np.abs(got - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("name,method", [("h2o", 2), ("ce_o", 2), ("fec128", 2), ("scan", 1), ("fec128", 1)])
+def test_k5_richardson_and_old_interpolation(name, method, hp_cache):
+    """Differentiation = Richardson (nonscc.F90:488-600) and forces with OldSKInterpolation."""
+    w, sk, geo, model, selfegy = case(name, method)
+    hp = hp_cache(name, method=method)
+    rng = np.random.default_rng(15)
+    s = oracle.build_s(model, geo)
+    dm = s * rng.normal(size=(2, geo["sparseSize"]))
+    edm = s * rng.normal(size=geo["sparseSize"])
+    sh = 0.1 * rng.normal(size=(2, geo["nAtom"], model.mOrb, model.mOrb))
+    sh = 0.5 * (sh + sh.transpose(0, 1, 3, 2))
+    for diff_type in (1, 2):
+        ref = oracle.derivative_shift(model, geo, dm[0], edm, diff_type=diff_type)
+        got = hp.derivative_shift(dm[0], edm, diff_type=diff_type)
+        assert np.abs(got - ref).max() < TOL_FORCE, (diff_type, np.abs(got - ref).max())
+        assert np.abs(got - ref).max() < 1e-8 * max(1.0, np.abs(ref).max())
+        ref = oracle.derivative_shift(model, geo, dm, edm, shift=sh, diff_type=diff_type)
+        got = hp.derivative_shift(dm, edm, shift=sh, diff_type=diff_type)
+        assert np.abs(got - ref).max() < TOL_FORCE, (diff_type, np.abs(got - ref).max())
+        assert np.abs(got - ref).max() < 1e-8 * max(1.0, np.abs(ref).max())
 
 
 def test_hegv_cusolver(hp_cache):

@@ -109,3 +109,29 @@ def test_old_interpolation_branches():
     assert np.isfinite(a).all() and abs(a[0] - (1 + 2 * (r_last - 0.5 * dist) + 3 * (r_last - 0.5 * dist) ** 2)) < 1e-2
     assert np.all(oracle.sk_eval(quad, dist, r_last + 0.31, method=1) == 0.0)
     assert np.all(oracle.sk_eval(quad, dist, r_last + 0.1, method=1) != 0.0)
+
+
+def test_old_interpolation_branches():
+    """SlakoEqGrid_interOld_ (slakoeqgrid.F90:248-317): the 3-point polynomial reproduces a
+    quadratic exactly, the free cubic spline of the last interval passes through the last two grid
+    points, the 5th-order tail starts at the last grid value and ends at zero at (mInd - 1) * dist,
+    and the interaction vanishes beyond; getCutoff adds distFudgeOld = 0.3."""
+    dist, n = 0.02, 500
+    r = dist * np.arange(1, n + 1)
+    quad = np.asfortranarray(np.stack([0.3 - 0.2 * r + 0.05 * r * r, np.exp(-0.3 * r)], axis=1))
+    for x in (0.031, 0.5, 3.333, 9.9, 9.9799):
+        got = oracle.sk_eval(quad, dist, x, method=1)
+        assert abs(got[0] - (0.3 - 0.2 * x + 0.05 * x * x)) < 1e-13
+        assert abs(got[1] - np.exp(-0.3 * x)) < 1e-6
+    assert np.allclose(oracle.sk_eval(quad, dist, 9.98, method=1), quad[-2], rtol=1e-13)
+    assert np.allclose(oracle.sk_eval(quad, dist, 10.0 - 1e-12, method=1), quad[-1], rtol=1e-9)
+    assert np.allclose(oracle.sk_eval(quad, dist, 10.0, method=1), quad[-1], rtol=1e-12)
+    m_ind = n + int(np.floor(0.3 / dist))
+    end = (m_ind - 1) * dist
+    assert np.abs(oracle.sk_eval(quad, dist, end - 1e-9, method=1)).max() < 1e-20
+    assert np.all(oracle.sk_eval(quad, dist, end + 1e-9, method=1) == 0.0)
+    assert np.all(oracle.sk_eval(quad, dist, 10.29, method=1) == 0.0)
+    # monotone decay through the tail for a monotone table
+    tail = np.array([oracle.sk_eval(quad, dist, x, method=1)[1] for x in np.linspace(10.0, end, 15)])
+    assert np.all(np.diff(tail) < 0) and tail[-1] >= 0
+    assert abs(oracle.lib().orc_sk_cutoff(n, ctypes.c_double(dist), 1) - (n * dist + 0.3)) < 1e-14
