@@ -194,7 +194,7 @@ int packImpl(dftbp_b200_ctx *ctx, double *primitive, const void *square, int ld,
     const K2Params p = makeParams(ctx, ld, kPoint, kWeight);
     const int grid = gridForChunks(ctx, p.nWork);
     const char *env = getenv("DFTBP_B200_K2_BATCH");  // tuning switch (tools/gpu_probe.py)
-    const int batch = env ? atoi(env) : 2;
+    const int batch = env ? atoi(env) : 1;
     if (cplx) {
       if (batch == 1) k2_pack<true, 1><<<grid, 256, 0, ctx->stream>>>(p, dPrim, dSq);
       else k2_pack<true, 2><<<grid, 256, 0, ctx->stream>>>(p, dPrim, dSq);

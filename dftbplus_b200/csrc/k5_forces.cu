@@ -22,6 +22,8 @@
 //   2. every lane contracts its six displaced blocks against its own row of the tile;
 //   3. six atomic adds per lane.
 // FP64 CUDA-core bound (6 block evaluations per pair and matrix), not HBM bound.
+#include <cstdlib>
+
 #include "block_desc.cuh"
 #include "sk_lane_eval.cuh"
 
@@ -156,6 +158,69 @@ __global__ void __launch_bounds__(256, 4) k5_force_weights(const K5WeightParams 
         }
       },
       [] {});
+}
+
+// Diagonal shift blocks (the common case), streaming form: the spin loop is unrolled so that all
+// loads of a pass -- (1 + 3 NSPIN) per element, three elements per lane and block -- are issued
+// before the first use (the generic kernel above: 35 % of the HBM roofline, latency bound,
+// profiles/r01d_ncu_all_kernels.txt).  BATCH > 1 blocks per pass costs more occupancy than it wins.
+template <int BATCH, int NSPIN>
+__global__ void __launch_bounds__(256) k5_force_weights_diag(const K5WeightParams p) {
+  if (__ldg(p.shiftFull) != 0) return;  // full blocks: k5_force_weights<true>
+  const int lane = threadIdx.x & 31;
+  const int mo2 = p.mOrb * p.mOrb, dstep = p.mOrb + 1;
+  forEachBlockBatch<BATCH>(p.desc, p.nWork, [&](const BlockDesc(&b)[BATCH], int count) {
+    int maxElem = 0;
+#pragma unroll
+    for (int q = 0; q < BATCH; ++q) {
+      const bool off = q < count && b[q].iNeigh != 0 && b[q].iAt1 != b[q].iAt2f;
+      if (off) maxElem = max(maxElem, (b[q].n12 & 0xFF) * (b[q].n12 >> 8));
+    }
+    for (int e0 = lane; e0 < maxElem; e0 += 96) {
+      double s[BATCH][3], r[BATCH][3][NSPIN], x1[BATCH][3][NSPIN], x2[BATCH][3][NSPIN];
+#pragma unroll
+      for (int q = 0; q < BATCH; ++q) {
+        const bool off = q < count && b[q].iNeigh != 0 && b[q].iAt1 != b[q].iAt2f;
+        const int n2 = b[q].n12 >> 8, nElem = off ? (b[q].n12 & 0xFF) * n2 : 0;
+        const unsigned M2 = (1048576u + (unsigned)n2 - 1u) / (unsigned)n2;  // e / n2 = e * M2 >> 20 (e < 256)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int e = e0 + 32 * k;
+          const bool on = e < nElem;
+          const int ee = on ? e : 0;
+          const int a = (int)(((unsigned)ee * M2) >> 20), bb = ee - a * n2;  // element (row bb, col a)
+          s[q][k] = on ? __ldg(p.EDM + b[q].ind + ee) : 0.0;
+#pragma unroll
+          for (int iSpin = 0; iSpin < NSPIN; ++iSpin) {
+            r[q][k][iSpin] = on ? __ldg(p.DM + (size_t)p.sparseSize * iSpin + b[q].ind + ee) : 0.0;
+            x1[q][k][iSpin] = on ? __ldg(p.shift + (size_t)mo2 * (b[q].iAt1 + (size_t)p.nAtom * iSpin) + a * dstep) : 0.0;
+            x2[q][k][iSpin] = on ? __ldg(p.shift + (size_t)mo2 * (b[q].iAt2f + (size_t)p.nAtom * iSpin) + bb * dstep) : 0.0;
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < BATCH; ++q) {
+        const bool off = q < count && b[q].iNeigh != 0 && b[q].iAt1 != b[q].iAt2f;
+        const int nElem = off ? (b[q].n12 & 0xFF) * (b[q].n12 >> 8) : 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int e = e0 + 32 * k;
+          double v = s[q][k];
+#pragma unroll
+          for (int iSpin = 0; iSpin < NSPIN; ++iSpin)
+            v = fma(-0.5 * r[q][k][iSpin], x1[q][k][iSpin] + x2[q][k][iSpin], v);
+          if (e < nElem) p.negWS[b[q].ind + e] = v;
+        }
+      }
+    }
+  });
+}
+
+template <int BATCH>
+void launchWeightsDiag(const K5WeightParams &wp, int nSpin, int grid, cudaStream_t stream) {
+  if (nSpin == 1) k5_force_weights_diag<BATCH, 1><<<grid, 256, 0, stream>>>(wp);
+  else if (nSpin == 2) k5_force_weights_diag<BATCH, 2><<<grid, 256, 0, stream>>>(wp);
+  else k5_force_weights_diag<BATCH, 4><<<grid, 256, 0, stream>>>(wp);
 }
 
 template <int LMAX>
@@ -418,7 +483,13 @@ extern "C" int dftbp_b200_derivative_shift(dftbp_b200_ctx *ctx, double *deriv, c
       wp.DM = p.DM; wp.EDM = dEDM; wp.shift = dShift; wp.shiftFull = flag; wp.negWS = (double *)scratch;
       const int wGrid = gridFor(ctx, (wp.nWork + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, 4);
       // both instantiations are launched; the one that does not match the device flag returns at once
-      k5_force_weights<false><<<wGrid, 256, 0, ctx->stream>>>(wp);
+      {
+        const char *env = getenv("DFTBP_B200_K5W_BATCH");  // tuning switch (tools/gpu_probe.py)
+        const int batch = env ? atoi(env) : 1;  // measured: 1 block per pass 98 us, 2 blocks 160 us, generic kernel 135 us
+        if (batch == 0) k5_force_weights<false><<<wGrid, 256, 0, ctx->stream>>>(wp);
+        else if (batch == 1) launchWeightsDiag<1>(wp, nSpin, wGrid, ctx->stream);
+        else launchWeightsDiag<2>(wp, nSpin, wGrid, ctx->stream);
+      }
       k5_force_weights<true><<<wGrid, 256, 0, ctx->stream>>>(wp);
       p.negWS = (const double *)scratch;
       ctx->launches += 3;

@@ -6,8 +6,8 @@ echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 |
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke_$TAG.log
 echo "== probe (all kernels, device resident)"
 timeout 600 python tools/gpu_probe.py fec4096 --dense --no-k3 2>&1 | tail -1 | tee gpurun_out/probe_$TAG.log
-echo "== probe, K1 = column-group kernel (A/B)"
-DFTBP_B200_K1=groups timeout 600 python tools/gpu_probe.py fec4096 2>&1 | tail -1 | tee gpurun_out/probe_k1groups_$TAG.log
+echo "== probe, K1 6 warps x 3 CTAs (A/B)"
+DFTBP_B200_K1_CFG=63 timeout 600 python tools/gpu_probe.py fec4096 2>&1 | tail -1 | tee gpurun_out/probe_k1groups_$TAG.log
 echo "== bench"; timeout 900 python bench.py 2>&1 | tail -3 | tee gpurun_out/bench_$TAG.log
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -2 | tee gpurun_out/bench_ref_$TAG.log
 echo "== ncu launch list (bench, pair path only)"
