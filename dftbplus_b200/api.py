@@ -104,7 +104,7 @@ class HotPath:
         self.set_stream(s if s != 0 else 1)      # 0 = legacy default stream -> cudaStreamLegacy
 
     TIMERS = ("sparseH0S", "sparseToDense", "denseToSparse", "densityMatrix", "mulliken", "forceCalc",
-              "diagonalization")
+              "diagonalization", "addShift")
 
     def timer_enable(self, on=True):
         self._ck(self._L.dftbp_b200_timer_enable(self._h, 1 if on else 0))
@@ -251,6 +251,16 @@ class HotPath:
         fn = self._L.dftbp_b200_mulliken_block if block else self._L.dftbp_b200_mulliken_orbital
         self._ck(fn(self._h, _ptr(qq), _ptr(_f64(over)), _ptr(_f64(rho))))
         return qq
+
+    # ---- K6 ---------------------------------------------------------------------------------
+    def addShift(self, ham, over, shift, is_input_zero=False):
+        """addShift (dftb/shift.F90:41-228), in place on ham[nSpin, sparseSize] (or 1-D for one spin):
+        shift[nSpin, nAtom] -> addShift_atom, shift[nSpin, nAtom, mOrb, mOrb] -> addShift_block."""
+        n_spin = ham.shape[0] if ham.ndim == 2 else 1
+        block = shift.ndim == 4
+        fn = self._L.dftbp_b200_add_shift_block if block else self._L.dftbp_b200_add_shift_atom
+        self._ck(fn(self._h, _ptr(ham), _ptr(_f64(over)), _ptr(_f64(shift)), n_spin, 1 if is_input_zero else 0))
+        return ham
 
     # ---- K5 ---------------------------------------------------------------------------------
     def derivative_shift(self, dm, edm, shift=None, diff_type=1, delta=0.0, deriv=None):

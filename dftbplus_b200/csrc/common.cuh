@@ -116,6 +116,7 @@ enum TimerSlot {
   kTimerMulliken,         // Mulliken (part of "SCC")         K4
   kTimerForceCalc,        // "Force calculation"              K5
   kTimerDiagonalization,  // "Diagonalisation"                cuSOLVER
+  kTimerAddShift,         // addShift (part of "SCC")         K6
   kTimerCount
 };
 

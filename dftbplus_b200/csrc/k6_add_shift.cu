@@ -1,0 +1,162 @@
+// k6_add_shift.cu -- addShift_atom / addShift_block (dftb/shift.F90:41-127, 132-228): the SCC
+// contribution to the sparse Hamiltonian, every SCC iteration right before unpackHS
+// (getSccHamiltonian, dftbplus/main.F90:1449):
+//
+//   ham(block, iSpin) += 1/2 * over(block) * (shift(iAt1, iSpin) + shift(iAt2f, iSpin))      (atom)
+//   ham(block, iSpin) += 1/2 * (S . V(:,:,iAt1,iSpin) + V(:,:,iAt2f,iSpin) . S)               (block)
+//
+// HBM-streaming, same shape as the Mulliken kernel: a warp walks through chunks of consecutive
+// sparse blocks (block_desc.cuh), lane <-> element, 8 (1 + 2 nSpin) algorithmic bytes per element
+// (over read once, ham read-modify-write per spin).  Block shifts of plain SCC / collinear spin are
+// diagonal (hamiltonian.F90 expands atom and shell potentials onto the block diagonal,
+// shift.F90:232-306): a device-side flag selects the element-wise form
+// 1/2 S(b,a) (V1(a,a) + V2(b,b)) or the per-block matrix products, without a host round trip.
+// isInputZero: the reference zeroes ham and loops over this rank's workload-balanced atoms
+// (distributeRangeWithWorkload; assembleChunks sums the ranks); otherwise every rank does all atoms.
+#include "block_desc.cuh"
+
+using namespace dftbp_b200;
+
+namespace {
+
+struct K6Params {
+  const BlockDesc *desc;
+  long long nWork;
+  int mOrb, nAtom, nSpin, sparseSize;
+  const double *over, *shift;
+  const int *shiftFull;  // device flag (block variant): 1 = some block has off-diagonal elements
+  double *ham;
+};
+
+// flag = 1 if any off-diagonal element of any shift block is non-zero (one warp per block)
+__global__ void __launch_bounds__(256) k6_shift_structure(const double *__restrict__ shift, int mOrb, int nBlocks,
+                                                          int *flag) {
+  const int lane = threadIdx.x & 31, mo2 = mOrb * mOrb;
+  bool any = false;
+  for (int blk = blockIdx.x * 8 + (threadIdx.x >> 5); blk < nBlocks; blk += gridDim.x * 8) {
+    const double *__restrict__ v = shift + (size_t)mo2 * blk;
+    for (int e = lane; e < mo2; e += 32) {
+      const int a = e / mOrb, b = e - a * mOrb;
+      if (a != b && __ldg(v + e) != 0.0) any = true;
+    }
+  }
+  if (__any_sync(0xffffffffu, any) && lane == 0) atomicOr(flag, 1);
+}
+
+// MODE 0: atom shifts shift(nAtom, nSpin); 1: diagonal block shifts; 2: full block shifts
+template <int MODE, int NSPIN>
+__global__ void __launch_bounds__(256) k6_add_shift(const K6Params p) {
+  if (MODE == 1 && __ldg(p.shiftFull) != 0) return;  // the MODE 2 launch handles it
+  if (MODE == 2 && __ldg(p.shiftFull) == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int mo2 = p.mOrb * p.mOrb, dstep = p.mOrb + 1;
+  forEachBlock(
+      p.desc, p.nWork, [] {},
+      [&](const BlockDesc &blk) {
+        const int n1 = blk.n12 & 0xFF, n2 = blk.n12 >> 8, nElem = n1 * n2, ind = blk.ind;
+        const unsigned M2 = (1048576u + (unsigned)n2 - 1u) / (unsigned)n2;  // e / n2 = e * M2 >> 20 (e < 256)
+        const double *__restrict__ S = p.over + ind;
+        for (int e0 = lane; e0 < nElem; e0 += 96) {
+          double s[3], h[3][NSPIN], x[3][NSPIN];
+          int e[3];
+          bool on[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {  // three elements per lane and pass, all loads independent
+            e[k] = e0 + 32 * k;
+            on[k] = e[k] < nElem;
+            if (!on[k]) e[k] = 0;
+            const int a = (int)(((unsigned)e[k] * M2) >> 20), b = e[k] - a * n2;  // element (row b, col a)
+            s[k] = __ldg(S + e[k]);
+#pragma unroll
+            for (int iSpin = 0; iSpin < NSPIN; ++iSpin) {
+              h[k][iSpin] = p.ham[(size_t)p.sparseSize * iSpin + ind + e[k]];
+              if (MODE == 0) {
+                x[k][iSpin] = s[k] * 0.5 * (__ldg(p.shift + blk.iAt1 + (size_t)p.nAtom * iSpin) +
+                                            __ldg(p.shift + blk.iAt2f + (size_t)p.nAtom * iSpin));
+              } else {
+                const double *__restrict__ V1 = p.shift + (size_t)mo2 * (blk.iAt1 + (size_t)p.nAtom * iSpin);
+                const double *__restrict__ V2 = p.shift + (size_t)mo2 * (blk.iAt2f + (size_t)p.nAtom * iSpin);
+                if (MODE == 1) {
+                  x[k][iSpin] = 0.5 * (s[k] * (__ldg(V1 + a * dstep) + __ldg(V2 + b * dstep)));
+                } else {
+                  // (S V1)(b,a) = sum_c S(b,c) V1(c,a);  (V2 S)(b,a) = sum_c V2(b,c) S(c,a)
+                  double u = 0.0, v = 0.0;
+                  for (int c = 0; c < n1; ++c) u = fma(__ldg(S + b + n2 * c), __ldg(V1 + c + p.mOrb * a), u);
+                  for (int c = 0; c < n2; ++c) v = fma(__ldg(V2 + b + p.mOrb * c), __ldg(S + c + n2 * a), v);
+                  x[k][iSpin] = 0.5 * (u + v);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int iSpin = 0; iSpin < NSPIN; ++iSpin)
+              if (on[k]) p.ham[(size_t)p.sparseSize * iSpin + ind + e[k]] = h[k][iSpin] + x[k][iSpin];
+        }
+      },
+      [] {});
+}
+
+template <int MODE>
+void launchMode(const K6Params &p, int grid, cudaStream_t st) {
+  if (p.nSpin == 1) k6_add_shift<MODE, 1><<<grid, 256, 0, st>>>(p);
+  else if (p.nSpin == 2) k6_add_shift<MODE, 2><<<grid, 256, 0, st>>>(p);
+  else k6_add_shift<MODE, 4><<<grid, 256, 0, st>>>(p);
+}
+
+int addShiftImpl(dftbp_b200_ctx *ctx, double *ham, const double *over, const double *shift, int nSpin,
+                 int isInputZero, bool block) {
+  if (!ctx) return DFTBP_B200_EINVAL;
+  const Geometry &g = ctx->geo;
+  DFTBP_CHECK(ctx, g.nAtom > 0, "add_shift: no geometry set");
+  DFTBP_CHECK(ctx, ham && over && shift, "add_shift: null argument");
+  DFTBP_CHECK(ctx, nSpin == 1 || nSpin == 2 || nSpin == 4, "add_shift: nSpin must be 1, 2 or 4");
+  K6Params p;
+  p.mOrb = ctx->mOrb; p.nAtom = g.nAtom; p.nSpin = nSpin; p.sparseSize = g.sparseSize;
+  const size_t nShift = (block ? (size_t)ctx->mOrb * ctx->mOrb : 1) * g.nAtom * nSpin;
+  DFTBP_TRY(devOut(ctx, kSlotA, ham, (size_t)g.sparseSize * nSpin, !isInputZero, &p.ham));
+  DFTBP_TRY(devIn(ctx, kSlotB, over, (size_t)g.sparseSize, &p.over));
+  DFTBP_TRY(devIn(ctx, kSlotC, shift, nShift, &p.shift));
+  if (isInputZero) {
+    DFTBP_CUDA(ctx, cudaMemsetAsync(p.ham, 0, sizeof(double) * (size_t)g.sparseSize * nSpin, ctx->stream));
+    p.desc = g.descLoad; p.nWork = g.nWorkLoad;
+  } else {
+    p.desc = g.descAll; p.nWork = g.nWorkAll;
+  }
+  p.shiftFull = ctx->dInfo + 1;
+  if (p.nWork > 0) {
+    ScopedTimer timer(ctx, kTimerAddShift);
+    const int grid = gridFor(ctx, (p.nWork + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, 4);
+    if (!block) {
+      launchMode<0>(p, grid, ctx->stream);
+      ctx->launches++;
+    } else {
+      int *flag = ctx->dInfo + 1;
+      DFTBP_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+      k6_shift_structure<<<std::min(ctx->smCount * 8, (g.nAtom * nSpin + 7) / 8), 256, 0, ctx->stream>>>(
+          p.shift, ctx->mOrb, g.nAtom * nSpin, flag);
+      // both forms are launched; the one that does not match the device flag returns at once
+      launchMode<1>(p, grid, ctx->stream);
+      launchMode<2>(p, grid, ctx->stream);
+      ctx->launches += 3;
+    }
+  }
+  return finish(ctx);
+}
+
+}  // namespace
+
+extern "C" {
+
+int dftbp_b200_add_shift_atom(dftbp_b200_ctx *ctx, double *ham, const double *over, const double *shift, int nSpin,
+                              int isInputZero) {
+  return addShiftImpl(ctx, ham, over, shift, nSpin, isInputZero, false);
+}
+
+int dftbp_b200_add_shift_block(dftbp_b200_ctx *ctx, double *ham, const double *over, const double *shift, int nSpin,
+                               int isInputZero) {
+  return addShiftImpl(ctx, ham, over, shift, nSpin, isInputZero, true);
+}
+
+}  // extern "C"

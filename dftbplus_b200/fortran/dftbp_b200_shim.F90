@@ -12,7 +12,7 @@ module dftbp_b200_shim
   public :: TB200Ctx, b200_init, b200_setGeometry
   public :: b200_buildH0, b200_buildS, b200_unpackHS_real, b200_unpackHS_cmplx
   public :: b200_packHS_real, b200_packHS_cmplx, b200_getDensityMatrix_real
-  public :: b200_mullikenPerOrbital, b200_derivative_shift
+  public :: b200_mullikenPerOrbital, b200_derivative_shift, b200_addShift_block, b200_addShift_atom
 
   integer, parameter :: dp = c_double
 
@@ -110,6 +110,20 @@ module dftbp_b200_shim
       type(c_ptr), value :: ctx
       real(c_double), intent(inout) :: qq(*)
       real(c_double), intent(in) :: over(*), rho(*)
+    end function
+    integer(c_int) function dftbp_b200_add_shift_atom(ctx, ham, over, shift, nSpin, isInputZero) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(inout) :: ham(*)
+      real(c_double), intent(in) :: over(*), shift(*)
+      integer(c_int), value :: nSpin, isInputZero
+    end function
+    integer(c_int) function dftbp_b200_add_shift_block(ctx, ham, over, shift, nSpin, isInputZero) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(inout) :: ham(*)
+      real(c_double), intent(in) :: over(*), shift(*)
+      integer(c_int), value :: nSpin, isInputZero
     end function
     integer(c_int) function dftbp_b200_derivative_shift(ctx, deriv, DM, nSpin, EDM, shift, diffType,&
         & delta) bind(C)
@@ -263,6 +277,26 @@ contains
     real(dp), intent(in) :: over(:), rho(:)
     call check(ctx, dftbp_b200_mulliken_orbital(ctx%h, qq, over, rho))
   end subroutine b200_mullikenPerOrbital
+
+  !> addShift_atom, dftb/shift.F90:41 -- shift(nAtom, nSpin)
+  subroutine b200_addShift_atom(ctx, ham, over, shift, isInputZero)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(inout) :: ham(:,:)
+    real(dp), intent(in) :: over(:), shift(:,:)
+    logical, intent(in) :: isInputZero
+    call check(ctx, dftbp_b200_add_shift_atom(ctx%h, ham, over, shift, size(ham, dim=2),&
+        & merge(1_c_int, 0_c_int, isInputZero)))
+  end subroutine b200_addShift_atom
+
+  !> addShift_block, dftb/shift.F90:132 -- shift(mOrb, mOrb, nAtom, nSpin)
+  subroutine b200_addShift_block(ctx, ham, over, shift, isInputZero)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(inout) :: ham(:,:)
+    real(dp), intent(in) :: over(:), shift(:,:,:,:)
+    logical, intent(in) :: isInputZero
+    call check(ctx, dftbp_b200_add_shift_block(ctx%h, ham, over, shift, size(ham, dim=2),&
+        & merge(1_c_int, 0_c_int, isInputZero)))
+  end subroutine b200_addShift_block
 
   !> derivative_shift, dftb/forces.F90:27-38 (block variant when shift is present)
   subroutine b200_derivative_shift(ctx, deriv, DM, EDM, shift, diffType, deltaXDiff)

@@ -159,6 +159,20 @@ int dftbp_b200_mulliken_orbital(dftbp_b200_ctx *ctx, double *qq, const double *o
 int dftbp_b200_mulliken_block(dftbp_b200_ctx *ctx, double *qq, const double *over,
                               const double *rho);
 
+/* ---- K6: SCC contribution to the sparse Hamiltonian ------------------------ */
+
+/* addShift_atom, dftb/shift.F90:41-127 (caller: getSccHamiltonian, dftbplus/main.F90:1449):
+ * ham(:, iSpin) += over * 0.5 * (shift(iAt1, iSpin) + shift(iAt2f, iSpin)) for every sparse block.
+ * ham(sparseSize, nSpin) in/out, over(sparseSize), shift(nAtom, nSpin), all column-major.
+ * isInputZero != 0: ham is zeroed first and only this rank's workload-balanced atoms are added
+ * (the caller sums the ranks, assembleChunks); == 0: every rank adds all atoms, like the reference. */
+int dftbp_b200_add_shift_atom(dftbp_b200_ctx *ctx, double *ham, const double *over,
+                              const double *shift, int nSpin, int isInputZero);
+/* addShift_block, dftb/shift.F90:132-228: ham(block, iSpin) += 0.5 * (S . shift(:,:,iAt1,iSpin) +
+ * shift(:,:,iAt2f,iSpin) . S); shift(mOrb, mOrb, nAtom, nSpin). */
+int dftbp_b200_add_shift_block(dftbp_b200_ctx *ctx, double *ham, const double *over,
+                               const double *shift, int nSpin, int isInputZero);
+
 /* ---- K5: force contraction ----------------------------------------------------------------- */
 
 /* derivative_shift generic, dftb/forces.F90:27-38: shift == NULL -> derivativeNonSccEuclidian
@@ -192,6 +206,7 @@ enum {
   DFTBP_B200_TIMER_MULLIKEN,
   DFTBP_B200_TIMER_FORCE_CALC,         /* "Force calculation"       */
   DFTBP_B200_TIMER_DIAGONALIZATION,    /* "Diagonalisation"         */
+  DFTBP_B200_TIMER_ADD_SHIFT,          /* addShift (inside "SCC")   */
   DFTBP_B200_TIMER_COUNT
 };
 int dftbp_b200_timer_enable(dftbp_b200_ctx *ctx, int on);   /* also resets the accumulators */

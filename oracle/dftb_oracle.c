@@ -941,6 +941,68 @@ void orc_pack_hs_cplx(double *primitive, const double *square, int nOrb, const d
  * dftb/populations.F90 : Mulliken
  * ---------------------------------------------------------------------------------------- */
 
+/* addShift_atom, dftb/shift.F90:41-127.  ham(sparseSize, nSpin) column-major, shift(nAtom, nSpin).
+ * isInputZero: ham is zeroed first (then the reference distributes the atoms by workload and
+ * sums the ranks' arrays: iterIndices restates that; NULL = all atoms). */
+void orc_add_shift_atom(double *ham, const double *over, int sparseSize, int nSpin, int nAtom,
+                        const int *nOrbAtom, const int *iNeighbour, int mNeigh,
+                        const int *nNeighbourSK, const int *img2CentCell, const int *iPair,
+                        const double *shift, int isInputZero, const int *iterIndices, int nIter)
+{
+  const int ld = mNeigh + 1;
+  int iSpin, iIter, iNeigh, k;
+  if (isInputZero) memset(ham, 0, sizeof(double) * (size_t)sparseSize * nSpin);
+  if (!iterIndices) nIter = nAtom;
+  for (iSpin = 0; iSpin < nSpin; ++iSpin)
+    for (iIter = 0; iIter < nIter; ++iIter) {
+      int iAt1 = iterIndices ? iterIndices[iIter] : iIter + 1;
+      int nOrb1 = nOrbAtom[iAt1 - 1];
+      for (iNeigh = 0; iNeigh <= nNeighbourSK[iAt1 - 1]; ++iNeigh) {
+        int iAt2f = img2CentCell[iNeighbour[iNeigh + ld * (iAt1 - 1)] - 1];
+        int nOrb2 = nOrbAtom[iAt2f - 1];
+        int iOrig = iPair[iNeigh + ld * (iAt1 - 1)];
+        double *h = ham + (size_t)sparseSize * iSpin + iOrig;
+        for (k = 0; k < nOrb2 * nOrb1; ++k)
+          h[k] = h[k] + over[iOrig + k] * 0.5 *
+                            (shift[(iAt1 - 1) + nAtom * iSpin] + shift[(iAt2f - 1) + nAtom * iSpin]);
+      }
+    }
+}
+
+/* addShift_block, dftb/shift.F90:132-228.  shift(mOrb, mOrb, nAtom, nSpin). */
+void orc_add_shift_block(double *ham, const double *over, int sparseSize, int nSpin, int nAtom,
+                         int mOrb, const int *nOrbAtom, const int *iNeighbour, int mNeigh,
+                         const int *nNeighbourSK, const int *img2CentCell, const int *iPair,
+                         const double *shift, int isInputZero, const int *iterIndices, int nIter)
+{
+  const int ld = mNeigh + 1;
+  int iSpin, iIter, iNeigh, a, b, c;
+  if (isInputZero) memset(ham, 0, sizeof(double) * (size_t)sparseSize * nSpin);
+  if (!iterIndices) nIter = nAtom;
+  for (iSpin = 0; iSpin < nSpin; ++iSpin)
+    for (iIter = 0; iIter < nIter; ++iIter) {
+      int iAt1 = iterIndices ? iterIndices[iIter] : iIter + 1;
+      int nOrb1 = nOrbAtom[iAt1 - 1];
+      const double *V1 = shift + (size_t)mOrb * mOrb * ((iAt1 - 1) + (size_t)nAtom * iSpin);
+      for (iNeigh = 0; iNeigh <= nNeighbourSK[iAt1 - 1]; ++iNeigh) {
+        int iAt2f = img2CentCell[iNeighbour[iNeigh + ld * (iAt1 - 1)] - 1];
+        int nOrb2 = nOrbAtom[iAt2f - 1];
+        int iOrig = iPair[iNeigh + ld * (iAt1 - 1)];
+        const double *V2 = shift + (size_t)mOrb * mOrb * ((iAt2f - 1) + (size_t)nAtom * iSpin);
+        const double *S = over + iOrig;
+        double *h = ham + (size_t)sparseSize * iSpin + iOrig;
+        /* tmpH = 0.5 * (matmul(tmpS, shift(:,:,iAt1)) + matmul(shift(:,:,iAt2f), tmpS)) */
+        for (a = 0; a < nOrb1; ++a)
+          for (b = 0; b < nOrb2; ++b) {
+            double x = 0.0, y = 0.0;
+            for (c = 0; c < nOrb1; ++c) x += S[b + nOrb2 * c] * V1[c + mOrb * a];
+            for (c = 0; c < nOrb2; ++c) y += V2[b + mOrb * c] * S[c + nOrb2 * a];
+            h[b + nOrb2 * a] = h[b + nOrb2 * a] + 0.5 * (x + y);
+          }
+      }
+    }
+}
+
 /* mullikenPerOrbital, populations.F90:120-187.  qq(mOrb, nAtom) accumulates.  iterIndices /
  * nIter restate distributeRangeWithWorkload (schedule.F90:137-164); NULL = all atoms. */
 void orc_mulliken_per_orbital(double *qq, int mOrb, const double *over, const double *rho,

@@ -311,6 +311,29 @@ def weighted_density_matrix(eigvecs, weights):
     return np.tril((c * np.asarray(weights[:n_lev])[None, :]) @ c.conj().T)
 
 
+def add_shift(model, geo, ham, over, shift, is_input_zero=False, iter_indices=None):
+    """addShift (dftb/shift.F90:41-228): ham[nSpin, sparseSize] += 1/2 (S V_i + V_j S).
+    shift[nSpin, nAtom] -> addShift_atom, shift[nSpin, nAtom, mOrb, mOrb] -> addShift_block.
+    Returns the updated ham (a copy)."""
+    ham = np.array(np.atleast_2d(ham), dtype=np.float64, order="C")
+    n_spin = ham.shape[0]
+    over = np.ascontiguousarray(over, dtype=np.float64)
+    shift = np.ascontiguousarray(shift, dtype=np.float64)
+    it = None if iter_indices is None else np.ascontiguousarray(iter_indices, dtype=np.int32)
+    n_it = 0 if it is None else len(it)
+    if shift.ndim == 2:
+        lib().orc_add_shift_atom(_d(ham), _d(over), geo["sparseSize"], n_spin, geo["nAtom"], _i(geo["nOrbAtom"]),
+                                 _i(geo["iNeighbour"]), geo["mNeigh"], _i(geo["nNeighbourSK"]),
+                                 _i(geo["img2CentCell"]), _i(geo["iPair"]), _d(shift), int(is_input_zero),
+                                 _i(it), n_it)
+    else:
+        lib().orc_add_shift_block(_d(ham), _d(over), geo["sparseSize"], n_spin, geo["nAtom"], model.mOrb,
+                                  _i(geo["nOrbAtom"]), _i(geo["iNeighbour"]), geo["mNeigh"],
+                                  _i(geo["nNeighbourSK"]), _i(geo["img2CentCell"]), _i(geo["iPair"]), _d(shift),
+                                  int(is_input_zero), _i(it), n_it)
+    return ham
+
+
 def mulliken_per_orbital(model, geo, over, rho, qq=None, iter_indices=None):
     if qq is None:
         qq = np.zeros((geo["nAtom"], model.mOrb))

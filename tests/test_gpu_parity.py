@@ -254,6 +254,35 @@ def test_k5_richardson_and_old_interpolation(name, method, hp_cache):
         assert np.abs(got - ref).max() < 1e-8 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("name", ["h2o", "ce_o", "si2", "fec128"])
+def test_k6_add_shift(name, hp_cache):
+    """addShift_atom / addShift_block (dftb/shift.F90:41-228): diagonal and full block shifts,
+    1 and 2 spin channels, accumulate and isInputZero forms, partial (per-rank) sums."""
+    w, sk, geo, model, selfegy = case(name)
+    hp = hp_cache(name)
+    rng = np.random.default_rng(16)
+    s = oracle.build_s(model, geo)
+    h0 = oracle.build_h0(model, geo, selfegy)
+    n_atom, mo = geo["nAtom"], model.mOrb
+    for n_spin in (1, 2):
+        ham = np.stack([h0] + [0.3 * h0] * (n_spin - 1))
+        v_atom = 0.1 * rng.normal(size=(n_spin, n_atom))
+        v_diag = np.zeros((n_spin, n_atom, mo, mo))
+        idx = np.arange(mo)
+        v_diag[:, :, idx, idx] = 0.1 * rng.normal(size=(n_spin, n_atom, mo))
+        v_full = 0.1 * rng.normal(size=(n_spin, n_atom, mo, mo))
+        v_full = 0.5 * (v_full + v_full.transpose(0, 1, 3, 2))
+        for shift in (v_atom, v_diag, v_full):
+            for zero in (False, True):
+                ref = oracle.add_shift(model, geo, ham, s, shift, is_input_zero=zero)
+                got = hp.addShift(ham.copy(), s, shift, is_input_zero=zero)
+                assert_sparse_close(got, ref, what="addShift %s nSpin %d ndim %d zero %s" % (name, n_spin, shift.ndim, zero))
+    if name == "fec128":
+        ham = np.stack([h0, h0])
+        parts = sum(hp_cache(name, r, 3).addShift(ham.copy(), s, v_full, is_input_zero=True) for r in range(3))
+        assert_sparse_close(parts, oracle.add_shift(model, geo, ham, s, v_full, is_input_zero=True), what="addShift ranks")
+
+
 def test_hegv_cusolver(hp_cache):
     w, sk, geo, model, selfegy, H, S, eig, C, f = _eig_case("ce_o")
     hp = hp_cache("ce_o")
