@@ -43,8 +43,10 @@ __global__ void __launch_bounds__(256) k6_shift_structure(const double *__restri
   if (__any_sync(0xffffffffu, any) && lane == 0) atomicOr(flag, 1);
 }
 
-// MODE 0: atom shifts shift(nAtom, nSpin); 1: diagonal block shifts; 2: full block shifts
-template <int MODE, int NSPIN>
+// MODE 0: atom shifts shift(nAtom, nSpin); 1: diagonal block shifts; 2: full block shifts.
+// ZERO: isInputZero -- ham is written, not accumulated: no read of ham and (on one rank, where the
+// work list covers every block) no zero fill either.
+template <int MODE, int NSPIN, bool ZERO>
 __global__ void __launch_bounds__(256) k6_add_shift(const K6Params p) {
   if (MODE == 1 && __ldg(p.shiftFull) != 0) return;  // the MODE 2 launch handles it
   if (MODE == 2 && __ldg(p.shiftFull) == 0) return;
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(256) k6_add_shift(const K6Params p) {
             s[k] = __ldg(S + e[k]);
 #pragma unroll
             for (int iSpin = 0; iSpin < NSPIN; ++iSpin) {
-              h[k][iSpin] = p.ham[(size_t)p.sparseSize * iSpin + ind + e[k]];
+              h[k][iSpin] = ZERO ? 0.0 : p.ham[(size_t)p.sparseSize * iSpin + ind + e[k]];
               if (MODE == 0) {
                 x[k][iSpin] = s[k] * 0.5 * (__ldg(p.shift + blk.iAt1 + (size_t)p.nAtom * iSpin) +
                                             __ldg(p.shift + blk.iAt2f + (size_t)p.nAtom * iSpin));
@@ -98,11 +100,17 @@ __global__ void __launch_bounds__(256) k6_add_shift(const K6Params p) {
       [] {});
 }
 
+template <int MODE, bool ZERO>
+void launchModeZ(const K6Params &p, int grid, cudaStream_t st) {
+  if (p.nSpin == 1) k6_add_shift<MODE, 1, ZERO><<<grid, 256, 0, st>>>(p);
+  else if (p.nSpin == 2) k6_add_shift<MODE, 2, ZERO><<<grid, 256, 0, st>>>(p);
+  else k6_add_shift<MODE, 4, ZERO><<<grid, 256, 0, st>>>(p);
+}
+
 template <int MODE>
-void launchMode(const K6Params &p, int grid, cudaStream_t st) {
-  if (p.nSpin == 1) k6_add_shift<MODE, 1><<<grid, 256, 0, st>>>(p);
-  else if (p.nSpin == 2) k6_add_shift<MODE, 2><<<grid, 256, 0, st>>>(p);
-  else k6_add_shift<MODE, 4><<<grid, 256, 0, st>>>(p);
+void launchMode(const K6Params &p, bool zero, int grid, cudaStream_t st) {
+  if (zero) launchModeZ<MODE, true>(p, grid, st);
+  else launchModeZ<MODE, false>(p, grid, st);
 }
 
 int addShiftImpl(dftbp_b200_ctx *ctx, double *ham, const double *over, const double *shift, int nSpin,
@@ -119,7 +127,9 @@ int addShiftImpl(dftbp_b200_ctx *ctx, double *ham, const double *over, const dou
   DFTBP_TRY(devIn(ctx, kSlotB, over, (size_t)g.sparseSize, &p.over));
   DFTBP_TRY(devIn(ctx, kSlotC, shift, nShift, &p.shift));
   if (isInputZero) {
-    DFTBP_CUDA(ctx, cudaMemsetAsync(p.ham, 0, sizeof(double) * (size_t)g.sparseSize * nSpin, ctx->stream));
+    // several ranks: the blocks of the other ranks' atoms stay zero (assembleChunks sums the arrays)
+    if (ctx->nRanks > 1)
+      DFTBP_CUDA(ctx, cudaMemsetAsync(p.ham, 0, sizeof(double) * (size_t)g.sparseSize * nSpin, ctx->stream));
     p.desc = g.descLoad; p.nWork = g.nWorkLoad;
   } else {
     p.desc = g.descAll; p.nWork = g.nWorkAll;
@@ -129,7 +139,7 @@ int addShiftImpl(dftbp_b200_ctx *ctx, double *ham, const double *over, const dou
     ScopedTimer timer(ctx, kTimerAddShift);
     const int grid = gridFor(ctx, (p.nWork + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, 4);
     if (!block) {
-      launchMode<0>(p, grid, ctx->stream);
+      launchMode<0>(p, isInputZero != 0, grid, ctx->stream);
       ctx->launches++;
     } else {
       int *flag = ctx->dInfo + 1;
@@ -137,8 +147,8 @@ int addShiftImpl(dftbp_b200_ctx *ctx, double *ham, const double *over, const dou
       k6_shift_structure<<<std::min(ctx->smCount * 8, (g.nAtom * nSpin + 7) / 8), 256, 0, ctx->stream>>>(
           p.shift, ctx->mOrb, g.nAtom * nSpin, flag);
       // both forms are launched; the one that does not match the device flag returns at once
-      launchMode<1>(p, grid, ctx->stream);
-      launchMode<2>(p, grid, ctx->stream);
+      launchMode<1>(p, isInputZero != 0, grid, ctx->stream);
+      launchMode<2>(p, isInputZero != 0, grid, ctx->stream);
       ctx->launches += 3;
     }
   }

@@ -87,6 +87,12 @@ def main():
     shf = 0.5 * (shf + shf.transpose(2, 3)).contiguous()
     ms = timeit(lambda: hp.derivative_shift(rho2, edm, shift=shf, deriv=deriv), stream, n=5)
     out["k5_scc_full_ms"] = ms
+    ham2 = torch.zeros((2, ss), **f64)
+    ms = timeit(lambda: hp.addShift(ham2, over, shd, is_input_zero=True), stream)
+    out["k6_addshift_diag_ms"] = ms
+    out["k6_GBs"] = 8.0 * ss * 5 / ms / 1e6
+    ms = timeit(lambda: hp.addShift(ham2, over, shf, is_input_zero=True), stream, n=5)
+    out["k6_addshift_full_ms"] = ms
     if dense:
         sq = new_dense(nOrb)
         ms = timeit(lambda: hp.unpackHS(ham, square=sq), stream, n=5)
