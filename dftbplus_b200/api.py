@@ -275,6 +275,19 @@ class HotPath:
             _ptr(None if shift is None else _f64(shift)), diff_type, float(delta)))
         return deriv
 
+    def stress(self, dm, edm, cell_vol, shift=None, diff_type=1, delta=0.0, st=None):
+        """getNonSCCStress / getBlockStress (dftb/stress.F90:70-326); returns st[3, 3] with
+        st[ii, jj] = reference st(jj, ii)."""
+        if not _is_torch(dm):
+            dm = np.ascontiguousarray(np.atleast_2d(dm), dtype=np.float64)
+        n_spin = dm.shape[0] if dm.ndim == 2 else 1
+        if st is None:
+            st = np.zeros((3, 3))
+        self._ck(self._L.dftbp_b200_stress(
+            self._h, _ptr(st), _ptr(dm), n_spin, _ptr(_f64(edm)),
+            _ptr(None if shift is None else _f64(shift)), diff_type, float(delta), float(cell_vol)))
+        return st
+
     # ---- cuSOLVER ---------------------------------------------------------------------------
     def diagDenseMtx(self, H, S, eigen=None, jobz="V"):
         """hegvd: H, S column-major, overwritten (H <- eigenvectors); returns eigenvalues."""

@@ -215,7 +215,7 @@ inline bool isDevicePtr(const void *p) {
 }
 
 // Staging slots (grow-only device buffers for host-pointer callers).
-enum Slot { kSlotA = 0, kSlotB, kSlotC, kSlotD, kSlotE, kSlotF, kSlotCount };
+enum Slot { kSlotA = 0, kSlotB, kSlotC, kSlotD, kSlotE, kSlotF, kSlotG, kSlotCount };
 
 inline int stagingGet(dftbp_b200_ctx *ctx, int slot, size_t bytes, void **out) {
   if ((int)ctx->staging.size() < kSlotCount) ctx->staging.resize(kSlotCount);

@@ -40,12 +40,14 @@ struct K5Params {
   const double *DM;     // rho, first spin channel = wH
   const double *negWS;  // -wS: Erho (no SCC) or the array prepared by k5_force_weights
   double delta;
-  double *deriv;
+  double *deriv;   // (3, nAtom) or nullptr (stress only)
+  double *stress;  // 9 raw accumulators sum fac * intermed(jj) * vect(ii) at [jj + 3 ii], or nullptr
 };
 
 // this lane's pair of chunk `chunk`: bond vector, sparse offset, the two atoms, species-pair
 // program (warp-uniform).  Padding lanes shadow lane 0's pair and are not live; pairs whose
-// neighbour folds onto the atom itself do not contribute (forces.F90:186, :631).
+// neighbour folds onto the atom itself do not contribute to the forces (forces.F90:186, :631) but
+// do contribute to the stress (stress.F90:164-176).
 struct K5Pair {
   double v0, v1, v2;
   int ind, iAt1, iAt2f, sp;
@@ -66,7 +68,7 @@ __device__ __forceinline__ K5Pair k5LoadPair(const K5Params &p, int chunk, int l
   const bool valid = k.ind >= 0;
   if (!valid) { k.v0 = x0; k.v1 = y0; k.v2 = z0; }
   k.iAt1 = at.x; k.iAt2f = at.y;
-  k.live = valid && at.x != at.y;
+  k.live = valid && (at.x != at.y || p.stress != nullptr);
   return k;
 }
 
@@ -97,6 +99,7 @@ struct K5WeightParams {
   const double *DM, *EDM, *shift;
   const int *shiftFull;
   double *negWS;
+  int selfImages;  // 1: also blocks between an atom and its own periodic image (stress)
 };
 
 template <bool FULL>
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(256, 4) k5_force_weights(const K5WeightParams 
   forEachBlock(
       p.desc, p.nWork, [] {},
       [&](const BlockDesc &blk) {
-        if (blk.iNeigh == 0 || blk.iAt1 == blk.iAt2f) return;
+        if (blk.iNeigh == 0 || (blk.iAt1 == blk.iAt2f && !p.selfImages)) return;
         const int n1 = blk.n12 & 0xFF, n2 = blk.n12 >> 8, ind = blk.ind;
         const int nElem = n1 * n2;
         const unsigned M2 = (1048576u + (unsigned)n2 - 1u) / (unsigned)n2;  // e / n2 = e * M2 >> 20 (e < 256)
@@ -173,14 +176,14 @@ __global__ void __launch_bounds__(256) k5_force_weights_diag(const K5WeightParam
     int maxElem = 0;
 #pragma unroll
     for (int q = 0; q < BATCH; ++q) {
-      const bool off = q < count && b[q].iNeigh != 0 && b[q].iAt1 != b[q].iAt2f;
+      const bool off = q < count && b[q].iNeigh != 0 && (b[q].iAt1 != b[q].iAt2f || p.selfImages);
       if (off) maxElem = max(maxElem, (b[q].n12 & 0xFF) * (b[q].n12 >> 8));
     }
     for (int e0 = lane; e0 < maxElem; e0 += 96) {
       double s[BATCH][3], r[BATCH][3][NSPIN], x1[BATCH][3][NSPIN], x2[BATCH][3][NSPIN];
 #pragma unroll
       for (int q = 0; q < BATCH; ++q) {
-        const bool off = q < count && b[q].iNeigh != 0 && b[q].iAt1 != b[q].iAt2f;
+        const bool off = q < count && b[q].iNeigh != 0 && (b[q].iAt1 != b[q].iAt2f || p.selfImages);
         const int n2 = b[q].n12 >> 8, nElem = off ? (b[q].n12 & 0xFF) * n2 : 0;
         const unsigned M2 = (1048576u + (unsigned)n2 - 1u) / (unsigned)n2;  // e / n2 = e * M2 >> 20 (e < 256)
 #pragma unroll
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(256) k5_force_weights_diag(const K5WeightParam
       }
 #pragma unroll
       for (int q = 0; q < BATCH; ++q) {
-        const bool off = q < count && b[q].iNeigh != 0 && b[q].iAt1 != b[q].iAt2f;
+        const bool off = q < count && b[q].iNeigh != 0 && (b[q].iAt1 != b[q].iAt2f || p.selfImages);
         const int nElem = off ? (b[q].n12 & 0xFF) * (b[q].n12 >> 8) : 0;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -223,9 +226,10 @@ void launchWeightsDiag(const K5WeightParams &wp, int nSpin, int grid, cudaStream
   else k5_force_weights_diag<BATCH, 4><<<grid, 256, 0, stream>>>(wp);
 }
 
-template <int LMAX>
+template <int LMAX, bool STRESS>
 __global__ void __launch_bounds__(320, 1) k5_derivative_shift(const K5Params p) {
   extern __shared__ double smem[];
+  double st[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // STRESS: this lane's share of st(jj,ii)
   const int lane = threadIdx.x & 31, wIn = threadIdx.x >> 5, nW = blockDim.x >> 5;
   double *stage = smem + (size_t)wIn * 32 * p.pitch;
   double *row = stage + (size_t)lane * p.pitch;
@@ -295,15 +299,41 @@ __global__ void __launch_bounds__(320, 1) k5_derivative_shift(const K5Params p) 
     if (live) {
       const double inv = 1.0 / p.delta;
       g0 *= inv; g1 *= inv; g2 *= inv;
-      atomicAdd(p.deriv + 3 * iAt1, g0);
-      atomicAdd(p.deriv + 3 * iAt1 + 1, g1);
-      atomicAdd(p.deriv + 3 * iAt1 + 2, g2);
-      atomicAdd(p.deriv + 3 * iAt2f, -g0);
-      atomicAdd(p.deriv + 3 * iAt2f + 1, -g1);
-      atomicAdd(p.deriv + 3 * iAt2f + 2, -g2);
+      if (p.deriv && iAt1 != iAt2f) {
+        atomicAdd(p.deriv + 3 * iAt1, g0);
+        atomicAdd(p.deriv + 3 * iAt1 + 1, g1);
+        atomicAdd(p.deriv + 3 * iAt1 + 2, g2);
+        atomicAdd(p.deriv + 3 * iAt2f, -g0);
+        atomicAdd(p.deriv + 3 * iAt2f + 1, -g1);
+        atomicAdd(p.deriv + 3 * iAt2f + 2, -g2);
+      }
+      if (STRESS) {
+        // st(jj,ii) += fac * intermed(jj) * vect(ii), vect = coords(:,iAtom1) - coords(:,iAtom2) = -v,
+        // fac = 2 unless the neighbour is a periodic image of the atom itself (stress.F90:158-176)
+        const double fac = iAt1 != iAt2f ? -2.0 : -1.0;
+        const double g[3] = {fac * g0, fac * g1, fac * g2}, v[3] = {v0, v1, v2};
+#pragma unroll
+        for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+          for (int jj = 0; jj < 3; ++jj) st[jj + 3 * ii] = fma(g[jj], v[ii], st[jj + 3 * ii]);
+      }
     }
     __syncwarp();  // the tile is restaged by the next item
   }
+  if (STRESS) {  // one reduction per warp and kernel: 9 atomics per warp
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      double x = st[k];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+      if (lane == 0) atomicAdd(p.stress + k, x);
+    }
+  }
+}
+
+// st = -0.5 * st / cellVol (stress.F90:182)
+__global__ void k5_stress_scale(const double *__restrict__ acc, double cellVol, double *__restrict__ st) {
+  if (threadIdx.x < 9) st[threadIdx.x] = -0.5 * acc[threadIdx.x] / cellVol;
 }
 
 // ---- Differentiation = Richardson (getFirstDerivRichardson, dftb/nonscc.F90:488-600) -----------------
@@ -408,12 +438,20 @@ __global__ void __launch_bounds__(64) k5_derivative_shift_richardson(const K5Par
         }
       }
     }
-    atomicAdd(p.deriv + 3 * iAt1, g[0]);
-    atomicAdd(p.deriv + 3 * iAt1 + 1, g[1]);
-    atomicAdd(p.deriv + 3 * iAt1 + 2, g[2]);
-    atomicAdd(p.deriv + 3 * iAt2f, -g[0]);
-    atomicAdd(p.deriv + 3 * iAt2f + 1, -g[1]);
-    atomicAdd(p.deriv + 3 * iAt2f + 2, -g[2]);
+    if (p.deriv && iAt1 != iAt2f) {
+      atomicAdd(p.deriv + 3 * iAt1, g[0]);
+      atomicAdd(p.deriv + 3 * iAt1 + 1, g[1]);
+      atomicAdd(p.deriv + 3 * iAt1 + 2, g[2]);
+      atomicAdd(p.deriv + 3 * iAt2f, -g[0]);
+      atomicAdd(p.deriv + 3 * iAt2f + 1, -g[1]);
+      atomicAdd(p.deriv + 3 * iAt2f + 2, -g[2]);
+    }
+    if (p.stress) {  // stress.F90:158-176; vect = -v
+      const double fac = iAt1 != iAt2f ? -2.0 : -1.0;
+      const double v[3] = {v0, v1, v2};
+      for (int ii = 0; ii < 3; ++ii)
+        for (int jj = 0; jj < 3; ++jj) atomicAdd(p.stress + jj + 3 * ii, fac * g[jj] * v[ii]);
+    }
   }
 }
 
@@ -424,31 +462,40 @@ int launchRichardson(dftbp_b200_ctx *ctx, const K5Params &p, long long chunks) {
   return 0;
 }
 
-template <int LMAX>
-int launchTyped(dftbp_b200_ctx *ctx, const K5Params &p, long long items, int warps, size_t smemBytes) {
-  DFTBP_CUDA(ctx, cudaFuncSetAttribute(k5_derivative_shift<LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smemBytes));
+template <int LMAX, bool STRESS>
+int launchTypedS(dftbp_b200_ctx *ctx, const K5Params &p, long long items, int warps, size_t smemBytes) {
+  DFTBP_CUDA(ctx, cudaFuncSetAttribute(k5_derivative_shift<LMAX, STRESS>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
   int perSm = 1;  // resident CTAs per SM (registers and the weight tile decide)
-  DFTBP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k5_derivative_shift<LMAX>, 32 * warps,
-                                                                smemBytes));
+  DFTBP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k5_derivative_shift<LMAX, STRESS>,
+                                                                32 * warps, smemBytes));
   const int grid = (int)std::max<long long>(
       1, std::min<long long>((items + warps - 1) / warps, (long long)ctx->smCount * std::max(perSm, 1)));
-  k5_derivative_shift<LMAX><<<grid, 32 * warps, smemBytes, ctx->stream>>>(p);
+  k5_derivative_shift<LMAX, STRESS><<<grid, 32 * warps, smemBytes, ctx->stream>>>(p);
   return 0;
+}
+
+template <int LMAX>
+int launchTyped(dftbp_b200_ctx *ctx, const K5Params &p, long long items, int warps, size_t smemBytes) {
+  if (p.stress) return launchTypedS<LMAX, true>(ctx, p, items, warps, smemBytes);
+  return launchTypedS<LMAX, false>(ctx, p, items, warps, smemBytes);
 }
 
 }  // namespace
 
-extern "C" int dftbp_b200_derivative_shift(dftbp_b200_ctx *ctx, double *deriv, const double *DM, int nSpin,
-                                           const double *EDM, const double *shift, int diffType,
-                                           double delta) {
+namespace {
+
+// derivative_shift (deriv != nullptr) and / or the stress tensor (st != nullptr) from one pass over the pairs
+int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, const double *DM, int nSpin,
+               const double *EDM, const double *shift, int diffType, double delta) {
   if (!ctx) return DFTBP_B200_EINVAL;
   const Geometry &g = ctx->geo;
   DFTBP_CHECK(ctx, g.nAtom > 0, "derivative_shift: no geometry set");
-  DFTBP_CHECK(ctx, deriv && DM && EDM, "derivative_shift: null argument");
+  DFTBP_CHECK(ctx, (deriv || st) && DM && EDM, "derivative_shift: null argument");
   DFTBP_CHECK(ctx, nSpin == 1 || nSpin == 2 || nSpin == 4, "derivative_shift: nSpin must be 1, 2 or 4");
   DFTBP_CHECK(ctx, diffType == DFTBP_B200_DIFF_FINITE || diffType == DFTBP_B200_DIFF_RICHARDSON,
               "derivative_shift: invalid differentiator type");
+  DFTBP_CHECK(ctx, !st || cellVol > 0.0, "stress: cell volume must be positive");
   DFTBP_TRY(syncPrograms(ctx));
   const SortedPairs *sched;
   DFTBP_TRY(ensureSortedPairs(ctx, true, &sched));
@@ -458,6 +505,7 @@ extern "C" int dftbp_b200_derivative_shift(dftbp_b200_ctx *ctx, double *deriv, c
   p.mOrb = ctx->mOrb; p.nAtom = g.nAtom; p.nSpin = nSpin; p.sparseSize = g.sparseSize;
   // nonscc.F90:43: deltaXDiff = epsilon(1.0_dp)**0.25_dp
   p.delta = delta > 0.0 ? delta : 1.220703125e-4;
+  p.deriv = nullptr; p.stress = nullptr;
   // the non-SCC routine takes DM(:) only; the block routine DM(:, nSpin)
   const int nDm = shift ? nSpin : 1;
   DFTBP_TRY(devIn(ctx, kSlotA, DM, (size_t)g.sparseSize * nDm, &p.DM));
@@ -465,8 +513,18 @@ extern "C" int dftbp_b200_derivative_shift(dftbp_b200_ctx *ctx, double *deriv, c
   const double *dEDM = p.negWS, *dShift = nullptr;
   if (shift)
     DFTBP_TRY(devIn(ctx, kSlotC, shift, (size_t)ctx->mOrb * ctx->mOrb * g.nAtom * nSpin, &dShift));
-  DFTBP_TRY(devOut(ctx, kSlotD, deriv, (size_t)3 * g.nAtom, false, &p.deriv));
-  DFTBP_CUDA(ctx, cudaMemsetAsync(p.deriv, 0, sizeof(double) * 3 * g.nAtom, ctx->stream));
+  if (deriv) {
+    DFTBP_TRY(devOut(ctx, kSlotD, deriv, (size_t)3 * g.nAtom, false, &p.deriv));
+    DFTBP_CUDA(ctx, cudaMemsetAsync(p.deriv, 0, sizeof(double) * 3 * g.nAtom, ctx->stream));
+  }
+  double *dSt = nullptr;
+  if (st) {
+    void *acc;
+    DFTBP_TRY(stagingGet(ctx, kSlotF, sizeof(double) * 9, &acc));
+    p.stress = (double *)acc;
+    DFTBP_CUDA(ctx, cudaMemsetAsync(p.stress, 0, sizeof(double) * 9, ctx->stream));
+    DFTBP_TRY(devOut(ctx, kSlotG, st, 9, false, &dSt));
+  }
   if (g.nWorkLoad > 0) {
     ScopedTimer timer(ctx, kTimerForceCalc);
     if (shift) {
@@ -481,6 +539,7 @@ extern "C" int dftbp_b200_derivative_shift(dftbp_b200_ctx *ctx, double *deriv, c
       wp.desc = g.descLoad; wp.nWork = g.nWorkLoad; wp.mOrb = ctx->mOrb;
       wp.nAtom = g.nAtom; wp.nSpin = nSpin; wp.sparseSize = g.sparseSize;
       wp.DM = p.DM; wp.EDM = dEDM; wp.shift = dShift; wp.shiftFull = flag; wp.negWS = (double *)scratch;
+      wp.selfImages = st ? 1 : 0;
       const int wGrid = gridFor(ctx, (wp.nWork + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, 4);
       // both instantiations are launched; the one that does not match the device flag returns at once
       {
@@ -513,5 +572,27 @@ extern "C" int dftbp_b200_derivative_shift(dftbp_b200_ctx *ctx, double *deriv, c
     if (rc) return rc;
     ctx->launches++;
   }
+  if (st) {
+    k5_stress_scale<<<1, 32, 0, ctx->stream>>>(p.stress, cellVol, dSt);
+    ctx->launches++;
+  }
   return finish(ctx);
 }
+
+}  // namespace
+
+extern "C" {
+
+int dftbp_b200_derivative_shift(dftbp_b200_ctx *ctx, double *deriv, const double *DM, int nSpin, const double *EDM,
+                                const double *shift, int diffType, double delta) {
+  if (ctx && !deriv) return fail(ctx, DFTBP_B200_EINVAL, "derivative_shift: deriv is null");
+  return forcesImpl(ctx, deriv, nullptr, 0.0, DM, nSpin, EDM, shift, diffType, delta);
+}
+
+int dftbp_b200_stress(dftbp_b200_ctx *ctx, double *st, const double *DM, int nSpin, const double *EDM,
+                      const double *shift, int diffType, double delta, double cellVol) {
+  if (ctx && !st) return fail(ctx, DFTBP_B200_EINVAL, "stress: st is null");
+  return forcesImpl(ctx, nullptr, st, cellVol, DM, nSpin, EDM, shift, diffType, delta);
+}
+
+}  // extern "C"

@@ -12,7 +12,7 @@ module dftbp_b200_shim
   public :: TB200Ctx, b200_init, b200_setGeometry
   public :: b200_buildH0, b200_buildS, b200_unpackHS_real, b200_unpackHS_cmplx
   public :: b200_packHS_real, b200_packHS_cmplx, b200_getDensityMatrix_real
-  public :: b200_mullikenPerOrbital, b200_derivative_shift, b200_addShift_block, b200_addShift_atom
+  public :: b200_mullikenPerOrbital, b200_derivative_shift, b200_addShift_block, b200_addShift_atom, b200_getBlockStress
 
   integer, parameter :: dp = c_double
 
@@ -110,6 +110,16 @@ module dftbp_b200_shim
       type(c_ptr), value :: ctx
       real(c_double), intent(inout) :: qq(*)
       real(c_double), intent(in) :: over(*), rho(*)
+    end function
+    integer(c_int) function dftbp_b200_stress(ctx, st, DM, nSpin, EDM, shift, diffType, delta, cellVol)&
+        & bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(out) :: st(3,3)
+      real(c_double), intent(in) :: DM(*), EDM(*)
+      integer(c_int), value :: nSpin, diffType
+      type(c_ptr), value :: shift
+      real(c_double), value :: delta, cellVol
     end function
     integer(c_int) function dftbp_b200_add_shift_atom(ctx, ham, over, shift, nSpin, isInputZero) bind(C)
       import :: c_ptr, c_int, c_double
@@ -277,6 +287,21 @@ contains
     real(dp), intent(in) :: over(:), rho(:)
     call check(ctx, dftbp_b200_mulliken_orbital(ctx%h, qq, over, rho))
   end subroutine b200_mullikenPerOrbital
+
+  !> getBlockStress, dftb/stress.F90:188 (getNonSCCStress, :70, when shift is absent)
+  subroutine b200_getBlockStress(ctx, st, DM, EDM, shift, diffType, deltaXDiff, cellVol)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(out) :: st(:,:)
+    real(dp), intent(in), target :: DM(:,:), EDM(:)
+    real(dp), intent(in), target, optional :: shift(:,:,:,:)
+    integer, intent(in) :: diffType
+    real(dp), intent(in) :: deltaXDiff, cellVol
+    type(c_ptr) :: pShift
+    pShift = c_null_ptr
+    if (present(shift)) pShift = c_loc(shift)
+    call check(ctx, dftbp_b200_stress(ctx%h, st, DM, size(DM, dim=2), EDM, pShift, diffType, deltaXDiff,&
+        & cellVol))
+  end subroutine b200_getBlockStress
 
   !> addShift_atom, dftb/shift.F90:41 -- shift(nAtom, nSpin)
   subroutine b200_addShift_atom(ctx, ham, over, shift, isInputZero)

@@ -159,6 +159,14 @@ int dftbp_b200_mulliken_orbital(dftbp_b200_ctx *ctx, double *qq, const double *o
 int dftbp_b200_mulliken_block(dftbp_b200_ctx *ctx, double *qq, const double *over,
                               const double *rho);
 
+/* getNonSCCStress (shift == NULL) / getBlockStress, dftb/stress.F90:70-184 / 188-326 (SURVEY 8(f)
+ * N3; callers dftbplus/main.F90:1829, 7491): the pair loop of derivative_shift with the outer
+ * product of the pair gradient and the bond vector, st = -0.5 / cellVol * sum fac * g(jj) * vect(ii),
+ * fac = 2 (1 for an atom and its own periodic image).  st(3,3) column-major, OVERWRITTEN; the other
+ * arguments as for dftbp_b200_derivative_shift.  With nRanks > 1: this rank's atoms only. */
+int dftbp_b200_stress(dftbp_b200_ctx *ctx, double *st, const double *DM, int nSpin, const double *EDM,
+                      const double *shift, int diffType, double delta, double cellVol);
+
 /* ---- K6: SCC contribution to the sparse Hamiltonian ------------------------ */
 
 /* addShift_atom, dftb/shift.F90:41-127 (caller: getSccHamiltonian, dftbplus/main.F90:1449):

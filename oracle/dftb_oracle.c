@@ -1084,8 +1084,55 @@ void orc_mulliken_per_block(double *qq, int mOrb, const double *over, const doub
  * dftb/forces.F90 : derivative_shift
  * ---------------------------------------------------------------------------------------- */
 
-/* derivativeNonSccEuclidian (shift == NULL, forces.F90:119-217) and derivative_blockEuclidean
- * (shift(mOrb,mOrb,nAtom,nSpin), forces.F90:548-669).  DM(sparseSize, nSpin), EDM(sparseSize),
+/* Per-pair gradient shared by derivative_shift and the stress routines:
+ *   derivTmp(ii) = 2 (sum rho.H'_ii - sum Erho.S'_ii)                         (forces.F90:196-199, stress.F90:150-154)
+ *                + 2 sum_spin sum 1/2 (S'_ii V1 + V2 S'_ii) . rho_spin          (forces.F90:640-656, stress.F90:291-300) */
+static void pairGradient(const orc_model *m, const double *DM, int nSpin, const double *EDM,
+                         int sparseSize, const double *shift, int nAtom, const double *coords,
+                         const int *species, int iAtom1, int iAtom2, int iAtom2f, int iOrig,
+                         int diffType, double delta, double *derivTmp)
+{
+  const int mo = m->mOrb, sz = mo * mo;
+  double hPrime[3 * ORC_MAXORB * ORC_MAXORB], sPrime[3 * ORC_MAXORB * ORC_MAXORB];
+  double shiftSprime[ORC_MAXORB * ORC_MAXORB];
+  int nOrb1 = m->nOrbSpecies[species[iAtom1 - 1] - 1], nOrb2 = m->nOrbSpecies[species[iAtom2f - 1] - 1];
+  int ii, a, b, c, iSpin;
+  orc_first_deriv_block(m, 0, hPrime, coords, species, iAtom1, iAtom2, diffType, delta);
+  orc_first_deriv_block(m, 1, sPrime, coords, species, iAtom1, iAtom2, diffType, delta);
+  for (ii = 0; ii < 3; ++ii) {
+    double sH = 0.0, sS = 0.0;
+    for (a = 0; a < nOrb1; ++a)
+      for (b = 0; b < nOrb2; ++b) {
+        sH += DM[iOrig + b + nOrb2 * a] * hPrime[b + mo * a + sz * ii];
+        sS += EDM[iOrig + b + nOrb2 * a] * sPrime[b + mo * a + sz * ii];
+      }
+    derivTmp[ii] = 2.0 * (sH - sS);
+  }
+  if (shift)
+    for (iSpin = 0; iSpin < nSpin; ++iSpin) {
+      const double *V1 = shift + (size_t)sz * ((iAtom1 - 1) + (size_t)nAtom * iSpin);
+      const double *V2 = shift + (size_t)sz * ((iAtom2f - 1) + (size_t)nAtom * iSpin);
+      const double *P = DM + iOrig + (size_t)sparseSize * iSpin;
+      for (ii = 0; ii < 3; ++ii) {
+        const double *Sp = sPrime + sz * ii;
+        double s = 0.0;
+        for (a = 0; a < nOrb1; ++a)
+          for (b = 0; b < nOrb2; ++b) {
+            double x = 0.0, y = 0.0;
+            for (c = 0; c < nOrb1; ++c) x += Sp[b + mo * c] * V1[c + mo * a];
+            for (c = 0; c < nOrb2; ++c) y += V2[b + mo * c] * Sp[c + mo * a];
+            shiftSprime[b + mo * a] = 0.5 * (x + y);
+          }
+        for (a = 0; a < nOrb1; ++a)
+          for (b = 0; b < nOrb2; ++b) s += shiftSprime[b + mo * a] * P[b + nOrb2 * a];
+        derivTmp[ii] = derivTmp[ii] + 2.0 * s;
+      }
+    }
+}
+
+/* derivative_shift generic (dftb/forces.F90:27-38): shift == NULL -> derivativeNonSccEuclidian
+ * (:119-217), else derivative_blockEuclidean (:548-669).  DM(sparseSize, nSpin) (only the first
+ * channel enters the H' term), EDM(sparseSize), shift(mOrb, mOrb, nAtom, nSpin).
  * deriv(3, nAtom) is overwritten.  OpenMP over the outer atom loop with a reduction on deriv,
  * as in the reference (:176, :620). */
 void orc_derivative_shift(double *deriv, const orc_model *m, const double *DM, int nSpin,
@@ -1095,7 +1142,7 @@ void orc_derivative_shift(double *deriv, const orc_model *m, const double *DM, i
                           const int *iPair, int diffType, double delta, const int *iterIndices,
                           int nIter)
 {
-  const int ld = mNeigh + 1, mo = m->mOrb, sz = mo * mo;
+  const int ld = mNeigh + 1;
   int nThreads = 1, iIter, t, k;
   double *part;
   orc_init();
@@ -1106,10 +1153,9 @@ void orc_derivative_shift(double *deriv, const orc_model *m, const double *DM, i
   part = (double *)calloc((size_t)nThreads * 3 * nAtom, sizeof(double));
 #pragma omp parallel for schedule(runtime)
   for (iIter = 0; iIter < nIter; ++iIter) {
-    double hPrime[3 * ORC_MAXORB * ORC_MAXORB], sPrime[3 * ORC_MAXORB * ORC_MAXORB];
-    double shiftSprime[ORC_MAXORB * ORC_MAXORB], derivTmp[3];
+    double derivTmp[3];
     int iAtom1 = iterIndices ? iterIndices[iIter] : iIter + 1;
-    int iSp1 = species[iAtom1 - 1], nOrb1 = m->nOrbSpecies[iSp1 - 1], iNeigh, ii, a, b, c, iSpin;
+    int iNeigh, ii;
     double *my = part;
 #ifdef _OPENMP
     my = part + (size_t)omp_get_thread_num() * 3 * nAtom;
@@ -1117,41 +1163,9 @@ void orc_derivative_shift(double *deriv, const orc_model *m, const double *DM, i
     for (iNeigh = 1; iNeigh <= nNeighbourSK[iAtom1 - 1]; ++iNeigh) {
       int iAtom2 = iNeighbour[iNeigh + ld * (iAtom1 - 1)];
       int iAtom2f = img2CentCell[iAtom2 - 1];
-      int iSp2 = species[iAtom2f - 1], nOrb2, iOrig;
       if (iAtom1 == iAtom2f) continue;
-      nOrb2 = m->nOrbSpecies[iSp2 - 1];
-      iOrig = iPair[iNeigh + ld * (iAtom1 - 1)];
-      orc_first_deriv_block(m, 0, hPrime, coords, species, iAtom1, iAtom2, diffType, delta);
-      orc_first_deriv_block(m, 1, sPrime, coords, species, iAtom1, iAtom2, diffType, delta);
-      for (ii = 0; ii < 3; ++ii) {
-        double sH = 0.0, sS = 0.0;
-        for (a = 0; a < nOrb1; ++a)
-          for (b = 0; b < nOrb2; ++b) {
-            sH += DM[iOrig + b + nOrb2 * a] * hPrime[b + mo * a + sz * ii];
-            sS += EDM[iOrig + b + nOrb2 * a] * sPrime[b + mo * a + sz * ii];
-          }
-        derivTmp[ii] = 2.0 * (sH - sS);
-      }
-      if (shift)
-        for (iSpin = 0; iSpin < nSpin; ++iSpin) {
-          const double *V1 = shift + (size_t)sz * ((iAtom1 - 1) + (size_t)nAtom * iSpin);
-          const double *V2 = shift + (size_t)sz * ((iAtom2f - 1) + (size_t)nAtom * iSpin);
-          const double *P = DM + iOrig + (size_t)sparseSize * iSpin;
-          for (ii = 0; ii < 3; ++ii) {
-            const double *Sp = sPrime + sz * ii;
-            double s = 0.0;
-            for (a = 0; a < nOrb1; ++a)
-              for (b = 0; b < nOrb2; ++b) {
-                double x = 0.0, y = 0.0;
-                for (c = 0; c < nOrb1; ++c) x += Sp[b + mo * c] * V1[c + mo * a];
-                for (c = 0; c < nOrb2; ++c) y += V2[b + mo * c] * Sp[c + mo * a];
-                shiftSprime[b + mo * a] = 0.5 * (x + y);
-              }
-            for (a = 0; a < nOrb1; ++a)
-              for (b = 0; b < nOrb2; ++b) s += shiftSprime[b + mo * a] * P[b + nOrb2 * a];
-            derivTmp[ii] = derivTmp[ii] + 2.0 * s;
-          }
-        }
+      pairGradient(m, DM, nSpin, EDM, sparseSize, shift, nAtom, coords, species, iAtom1, iAtom2, iAtom2f,
+                   iPair[iNeigh + ld * (iAtom1 - 1)], diffType, delta, derivTmp);
       for (ii = 0; ii < 3; ++ii) {
         my[ii + 3 * (iAtom1 - 1)] += derivTmp[ii];
         my[ii + 3 * (iAtom2f - 1)] -= derivTmp[ii];
@@ -1162,6 +1176,40 @@ void orc_derivative_shift(double *deriv, const orc_model *m, const double *DM, i
   for (t = 0; t < nThreads; ++t)
     for (k = 0; k < 3 * nAtom; ++k) deriv[k] += part[(size_t)t * 3 * nAtom + k];
   free(part);
+}
+
+/* getNonSCCStress (dftb/stress.F90:70-184; shift == NULL) / getBlockStress (:188-326):
+ *   st(jj,ii) += fac * intermed(jj) * vect(ii),  vect = coords(:,iAtom1) - coords(:,iAtom2),
+ *   fac = 2 unless iAtom2 is a periodic image of iAtom1 (then 1);  st = -0.5 * st / cellVol.
+ * st(3,3) column-major (st[jj + 3*ii]) is overwritten. */
+void orc_stress(double *st, const orc_model *m, const double *DM, int nSpin, const double *EDM,
+                int sparseSize, const double *shift, int nAtom, const double *coords,
+                const int *species, const int *iNeighbour, int mNeigh, const int *nNeighbourSK,
+                const int *img2CentCell, const int *iPair, int diffType, double delta, double cellVol,
+                const int *iterIndices, int nIter)
+{
+  const int ld = mNeigh + 1;
+  int iIter, k;
+  double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  orc_init();
+  if (!iterIndices) nIter = nAtom;
+#pragma omp parallel for schedule(runtime) reduction(+ : acc[:9])
+  for (iIter = 0; iIter < nIter; ++iIter) {
+    double intermed[3], vect[3];
+    int iAtom1 = iterIndices ? iterIndices[iIter] : iIter + 1;
+    int iNeigh, ii, jj;
+    for (iNeigh = 1; iNeigh <= nNeighbourSK[iAtom1 - 1]; ++iNeigh) {
+      int iAtom2 = iNeighbour[iNeigh + ld * (iAtom1 - 1)];
+      int iAtom2f = img2CentCell[iAtom2 - 1];
+      double fac = iAtom1 != iAtom2f ? 2.0 : 1.0;
+      pairGradient(m, DM, nSpin, EDM, sparseSize, shift, nAtom, coords, species, iAtom1, iAtom2, iAtom2f,
+                   iPair[iNeigh + ld * (iAtom1 - 1)], diffType, delta, intermed);
+      for (ii = 0; ii < 3; ++ii) vect[ii] = coords[ii + 3 * (iAtom1 - 1)] - coords[ii + 3 * (iAtom2 - 1)];
+      for (ii = 0; ii < 3; ++ii)
+        for (jj = 0; jj < 3; ++jj) acc[jj + 3 * ii] += fac * intermed[jj] * vect[ii];
+    }
+  }
+  for (k = 0; k < 9; ++k) st[k] = -0.5 * acc[k] / cellVol;
 }
 
 int orc_num_threads(void)

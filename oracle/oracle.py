@@ -384,3 +384,18 @@ def derivative_shift(model, geo, dm, edm, shift=None, diff_type=1, delta=DELTA_X
                                _i(geo["img2CentCell"]), _i(geo["iPair"]), diff_type,
                                ctypes.c_double(delta), _i(it), 0 if it is None else len(it))
     return deriv
+
+
+def stress(model, geo, dm, edm, cell_vol, shift=None, diff_type=1, delta=DELTA_X_DIFF, iter_indices=None):
+    """getNonSCCStress / getBlockStress (dftb/stress.F90:70-326).  Returns st[3, 3] with
+    st[ii, jj] = reference st(jj, ii) (numpy sees the column-major array transposed)."""
+    dm = np.ascontiguousarray(np.atleast_2d(dm), dtype=np.float64)
+    edm = np.ascontiguousarray(edm, dtype=np.float64)
+    sh = None if shift is None else np.ascontiguousarray(shift, dtype=np.float64)
+    it = None if iter_indices is None else np.ascontiguousarray(iter_indices, dtype=np.int32)
+    st = np.zeros((3, 3))
+    lib().orc_stress(_d(st), model._h, _d(dm), dm.shape[0], _d(edm), geo["sparseSize"], _d(sh), geo["nAtom"],
+                     _d(geo["coords"]), _i(geo["species"]), _i(geo["iNeighbour"]), geo["mNeigh"],
+                     _i(geo["nNeighbourSK"]), _i(geo["img2CentCell"]), _i(geo["iPair"]), diff_type,
+                     ctypes.c_double(delta), ctypes.c_double(cell_vol), _i(it), 0 if it is None else len(it))
+    return st

@@ -1,0 +1,153 @@
+"""Host-side SCC single-point driver used by the end-to-end parity test (BASELINE config 1: "H2O
+molecule SCC single point"; north_star: total energy within 1e-8 Ha, identical SCC iteration
+counts, forces within 1e-7 Ha/bohr).
+
+Everything that SURVEY.md marks OUT OF SCOPE stays on the host and is SHARED by the two arms: the
+atom-resolved short-range gamma (the closed forms behind dftb/shortgamma.F90 / shortgammafuncs.F90:
+gamma_ij = 1/R - S(tau_i, tau_j, R), tau = 16/5 U, gamma_ii = U_i; cluster boundary conditions, so
+no Ewald sum), Fermi filling, simple charge mixing and the convergence test on the Mulliken charges
+(dftbplus/main.F90:4884-4930).  What differs between the arms is only the hot path: the oracle arm
+calls the CPU restatement (+ scipy.linalg.eigh), the device arm calls the CUDA library through
+dftbplus_b200.api (+ cuSOLVER) in the order of processGeometry (dftbplus/main.F90:1219-1221, 1449,
+3536-3566, 4101-4108, 4705, 6572-6691, 7264): buildH0/buildS -> [addShift -> unpackHS -> diag ->
+getDensityMatrix -> packHS -> mulliken]* -> getEDensityMatrix -> packHS -> derivative_shift."""
+import numpy as np
+import scipy.linalg
+
+
+def short_gamma(coords, species0, hubb_u):
+    """gamma[nAtom, nAtom] for a cluster (Elstner et al. 1998, eqs. (12)-(14))."""
+    n = len(species0)
+    tau = np.array([3.2 * hubb_u[s - 1] for s in species0])
+    g = np.zeros((n, n))
+    for i in range(n):
+        for j in range(n):
+            if i == j:
+                g[i, j] = hubb_u[species0[i] - 1]
+                continue
+            r = np.linalg.norm(coords[i] - coords[j])
+            a, b = tau[i], tau[j]
+            if abs(a - b) < 1e-12:
+                s = np.exp(-a * r) * (48.0 + 33.0 * a * r + 9.0 * (a * r) ** 2 + (a * r) ** 3) / (48.0 * r)
+            else:
+                s = (np.exp(-a * r) * (b ** 4 * a / (2.0 * (a * a - b * b) ** 2)
+                                       - (b ** 6 - 3.0 * b ** 4 * a * a) / ((a * a - b * b) ** 3 * r))
+                     + np.exp(-b * r) * (a ** 4 * b / (2.0 * (b * b - a * a) ** 2)
+                                         - (a ** 6 - 3.0 * a ** 4 * b * b) / ((b * b - a * a) ** 3 * r)))
+            g[i, j] = 1.0 / r - s
+    return g
+
+
+def fermi(eigen, n_elec, kT=0.001):
+    lo, hi = eigen.min() - 1.0, eigen.max() + 1.0
+    for _ in range(200):
+        mu = 0.5 * (lo + hi)
+        f = 2.0 / (1.0 + np.exp(np.clip((eigen - mu) / kT, -700, 700)))
+        if f.sum() > n_elec:
+            hi = mu
+        else:
+            lo = mu
+    return f
+
+
+class OracleArm:
+    def __init__(self, oracle, model, geo, selfegy):
+        self.o, self.m, self.geo, self.selfegy = oracle, model, geo, selfegy
+
+    def build(self):
+        return self.o.build_h0(self.m, self.geo, self.selfegy), self.o.build_s(self.m, self.geo)
+
+    def add_shift(self, h0, over, shift_atom):
+        ham = self.o.add_shift(self.m, self.geo, np.zeros((1, self.geo["sparseSize"])), over, shift_atom[None, :],
+                               is_input_zero=True)
+        ham[0] += h0
+        return ham[0]
+
+    def solve(self, ham, over):
+        H, S = self.o.unpack_hs_real(self.geo, ham), self.o.unpack_hs_real(self.geo, over)
+        eig, C = scipy.linalg.eigh(H, S, lower=True)
+        return eig, np.asfortranarray(C)
+
+    def rho(self, C, f):
+        return self.o.pack_hs_real(self.geo, np.zeros(self.geo["sparseSize"]), self.o.density_matrix(C, f))
+
+    def erho(self, C, f, eig):
+        return self.o.pack_hs_real(self.geo, np.zeros(self.geo["sparseSize"]), self.o.energy_density_matrix(C, f, eig))
+
+    def mulliken(self, over, rho):
+        return self.o.mulliken_per_orbital(self.m, self.geo, over, rho)
+
+    def forces(self, rho, erho, shift_block):
+        return self.o.derivative_shift(self.m, self.geo, rho, erho, shift=shift_block)
+
+
+class DeviceArm:
+    """The same calls through the C ABI (host numpy buffers in, host buffers out)."""
+
+    def __init__(self, hp, sk, geo):
+        self.hp, self.sk, self.geo = hp, sk, geo
+
+    def build(self):
+        return self.hp.buildH0S(self.sk.selfegy)
+
+    def add_shift(self, h0, over, shift_atom):
+        ham = np.zeros((1, self.geo["sparseSize"]))
+        self.hp.addShift(ham, over, np.ascontiguousarray(shift_atom[None, :]), is_input_zero=True)
+        ham[0] += h0
+        return ham[0]
+
+    def solve(self, ham, over):
+        H, S = self.hp.unpackHS(ham), self.hp.unpackHS(over)
+        eig = self.hp.diagDenseMtx(H, S)        # H <- eigenvectors
+        return eig, H
+
+    def rho(self, C, f):
+        return self.hp.packHS(np.zeros(self.geo["sparseSize"]), self.hp.getDensityMatrix(C, f))
+
+    def erho(self, C, f, eig):
+        return self.hp.packHS(np.zeros(self.geo["sparseSize"]), self.hp.getEDensityMatrix(C, f, eig))
+
+    def mulliken(self, over, rho):
+        return self.hp.mulliken(over, rho)
+
+    def forces(self, rho, erho, shift_block):
+        return self.hp.derivative_shift(rho, erho, shift=shift_block)
+
+
+def scc_single_point(arm, workload, sk, geo, m_orb, tol=1e-8, mix=0.4, max_iter=200):
+    """Returns dict(n_iter, energy, q, forces).  Convergence: max |q_out - q_in| < tol on the
+    orbital-resolved Mulliken charges (main.F90:4884-4930 with a simple mixer)."""
+    species0 = np.asarray(workload["species0"])
+    n_atom = geo["nAtom"]
+    hubb = [sk.hubbU[s][0] for s in range(len(sk.hubbU))]
+    gamma = short_gamma(np.asarray(workload["coord0"], dtype=float), species0, hubb)
+    q0 = np.zeros((n_atom, m_orb))
+    for i, s in enumerate(species0):           # reference (neutral atom) orbital populations
+        k = 0
+        for l, occ in zip(sk.ang_shells[s - 1], sk.occ[s - 1]):
+            q0[i, k:k + 2 * l + 1] = occ / (2 * l + 1)
+            k += 2 * l + 1
+    n_elec = q0.sum()
+    h0, over = arm.build()
+    q_in = q0.copy()
+    for it in range(1, max_iter + 1):
+        dq = (q_in - q0).sum(axis=1)
+        shift_atom = gamma @ dq
+        ham = arm.add_shift(h0, over, shift_atom)
+        eig, C = arm.solve(ham, over)
+        f = fermi(np.asarray(eig), n_elec)
+        rho = arm.rho(C, f)
+        q_out = arm.mulliken(over, rho)
+        err = np.abs(q_out - q_in).max()
+        if err < tol:
+            break
+        q_in = q_in + mix * (q_out - q_in)
+    dq = (q_out - q0).sum(axis=1)
+    e_h0 = arm.mulliken(h0, rho).sum()                     # Tr[rho H0], getenergies.F90:198
+    e_scc = 0.5 * dq @ gamma @ dq
+    erho = arm.erho(C, f, np.asarray(eig))
+    shift_block = np.zeros((1, n_atom, m_orb, m_orb))
+    idx = np.arange(m_orb)
+    shift_block[0, :, idx, idx] = (gamma @ dq)[None, :]
+    forces = arm.forces(rho, erho, shift_block)
+    return dict(n_iter=it, energy=e_h0 + e_scc, e_h0=e_h0, e_scc=e_scc, q=q_out, forces=forces, err=err)

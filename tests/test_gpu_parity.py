@@ -283,6 +283,37 @@ def test_k6_add_shift(name, hp_cache):
         assert_sparse_close(parts, oracle.add_shift(model, geo, ham, s, v_full, is_input_zero=True), what="addShift ranks")
 
 
+@pytest.mark.parametrize("name", ["si2", "fec128", "si512"])
+def test_k5_stress(name, hp_cache):
+    """getNonSCCStress / getBlockStress (dftb/stress.F90:70-326): same pair loop as derivative_shift,
+    including the pairs between an atom and its own periodic image (si2: most pairs are)."""
+    w, sk, geo, model, selfegy = case(name)
+    hp = hp_cache(name)
+    rng = np.random.default_rng(17)
+    s = oracle.build_s(model, geo)
+    dm = s * rng.normal(size=(2, geo["sparseSize"]))
+    edm = s * rng.normal(size=geo["sparseSize"])
+    vol = abs(np.linalg.det(w["latvec"]))
+    sh = 0.1 * rng.normal(size=(2, geo["nAtom"], model.mOrb, model.mOrb))
+    sh = 0.5 * (sh + sh.transpose(0, 1, 3, 2))
+    shd = np.zeros_like(sh)
+    idx = np.arange(model.mOrb)
+    shd[:, :, idx, idx] = sh[:, :, idx, idx]
+    cases = [(dm[0], None, 1), (dm, shd, 1), (dm, sh, 1)]
+    if name != "si512":
+        cases.append((dm[:1], sh[:1], 2))                 # Richardson derivator
+    for d, shift, diff_type in cases:
+        ref = oracle.stress(model, geo, d, edm, vol, shift=shift, diff_type=diff_type)
+        got = hp.stress(d, edm, vol, shift=shift, diff_type=diff_type)
+        assert np.abs(got - ref).max() < 1e-9 * max(1.0, np.abs(ref).max()), (diff_type, np.abs(got - ref).max())
+    # forces are unchanged by the stress plumbing (self-image pairs stay excluded there)
+    ref = oracle.derivative_shift(model, geo, dm, edm, shift=sh)
+    assert np.abs(hp.derivative_shift(dm, edm, shift=sh) - ref).max() < TOL_FORCE
+    if name == "fec128":
+        parts = sum(hp_cache(name, r, 3).stress(dm, edm, vol, shift=sh) for r in range(3))
+        assert np.abs(parts - oracle.stress(model, geo, dm, edm, vol, shift=sh)).max() < 1e-9
+
+
 def test_hegv_cusolver(hp_cache):
     w, sk, geo, model, selfegy, H, S, eig, C, f = _eig_case("ce_o")
     hp = hp_cache("ce_o")

@@ -196,3 +196,45 @@ def test_add_shift_variants_agree():
     lhs = oracle.mulliken_per_orbital(model, geo, dh, s).sum()   # sum over all elements of dH .* S (both triangles)
     rhs = np.einsum("iab,iab->", v_full[0], qb)
     assert abs(lhs - rhs) < 1e-10 * max(1.0, abs(rhs))
+
+
+def test_stress_is_strain_derivative_of_the_band_functional():
+    """getNonSCCStress (dftb/stress.F90:70-184): with rho and E-rho held fixed,
+    st(a,b) = -(1/V) d/d eps_ab sum_blocks fac (rho . H0 - Erho . S) under x_a -> x_a + eps_ab x_b,
+    fac = 2 for blocks between different atoms (lower-triangle storage), 1 for an atom and its own
+    periodic image; on-site blocks do not move.  Pins sign, factors and the index order of st."""
+    w, sk, geo, model, selfegy = case("fec128")
+    rng = np.random.default_rng(21)
+    s0 = oracle.build_s(model, geo)
+    dm = s0 * rng.normal(size=geo["sparseSize"])
+    edm = s0 * rng.normal(size=geo["sparseSize"])
+    vol = abs(np.linalg.det(w["latvec"]))
+    st = oracle.stress(model, geo, dm, edm, vol)
+    st_rich = oracle.stress(model, geo, dm, edm, vol, diff_type=2)
+    assert np.abs(st - st_rich).max() < 1e-9
+    # element weights fac per block
+    fac = np.zeros(geo["sparseSize"])
+    for i in range(geo["nAtom"]):
+        for k in range(1, geo["nNeighbourSK"][i] + 1):
+            j = geo["img2CentCell"][geo["iNeighbour"][i, k] - 1] - 1
+            n = geo["nOrbAtom"][i] * geo["nOrbAtom"][j]
+            fac[geo["iPair"][i, k]:geo["iPair"][i, k] + n] = 2.0 if j != i else 1.0
+
+    def functional(eps):
+        g = dict(geo)
+        g["coords"] = np.ascontiguousarray(geo["coords"] @ (np.eye(3) + eps).T)
+        h, s = oracle.build_h0(model, g, selfegy), oracle.build_s(model, g)
+        return float(np.sum(fac * (dm * h - edm * s)))
+    hstep = 1e-5
+    for a, b in [(0, 0), (0, 1), (2, 1), (1, 2)]:
+        eps = np.zeros((3, 3))
+        eps[a, b] = hstep
+        num = -(functional(eps) - functional(-eps)) / (2 * hstep) / vol
+        assert abs(num - st[b, a]) < 1e-7 * max(1.0, np.abs(st).max()), (a, b, num, st[b, a])   # st[ii, jj] = st(jj, ii)
+    # block (SCC) variant with zero shift equals the non-SCC routine; workload-split parts add up
+    sh = np.zeros((1, geo["nAtom"], model.mOrb, model.mOrb))
+    assert np.allclose(oracle.stress(model, geo, dm, edm, vol, shift=sh), st, atol=1e-14)
+    parts = sum(oracle.stress(model, geo, dm, edm, vol,
+                              iter_indices=oracle.indices_with_workload(3, r, 1, geo["nAtom"], geo["nNeighbourSK"]))
+                for r in range(3))
+    assert np.allclose(parts, st, atol=1e-13)

@@ -1,0 +1,63 @@
+"""End-to-end SCC single point (BASELINE config 1 and two larger clusters): the device arm against
+the oracle arm with a shared host-side SCC model (tests/scc_harness.py).
+
+north_star bars: total energy within 1e-8 Ha, forces within 1e-7 Ha/bohr, IDENTICAL SCC iteration
+counts; Mulliken charges within 1e-9."""
+import numpy as np
+import pytest
+
+from helpers import oracle, case
+from oracle import oldskdata
+from dftbplus_b200 import workloads
+import scc_harness as sh
+
+TOL_ENERGY = 1e-8    # Ha
+TOL_FORCE = 1e-7     # Ha / bohr
+
+
+def _setup(name):
+    if name == "watercluster24":
+        w = workloads.water_box(8, 1)
+        w["latvec"], w["name"] = None, name
+        sk, geo, directory = workloads.prepare(w)
+        model, selfegy = oldskdata.load_model(directory, w["names"], sk.ang_shells)
+        return w, sk, geo, model, selfegy
+    return case(name)
+
+
+MIX = {"h2o": 0.4, "watercluster24": 0.1, "ce_o": 0.05}
+
+
+def test_oracle_scc_converges_and_is_variational():
+    """CPU: the oracle arm converges, conserves the electron count, and its SCC forces are the
+    derivative of nothing less than the SCC-consistent energy only up to the gamma' term that the
+    harness leaves out -- so check what must hold exactly: sum of forces = 0 and q sums to N."""
+    w, sk, geo, model, selfegy = _setup("h2o")
+    r = sh.scc_single_point(sh.OracleArm(oracle, model, geo, selfegy), w, sk, geo, model.mOrb, mix=MIX["h2o"])
+    assert r["err"] < 1e-8 and 5 < r["n_iter"] < 100
+    assert abs(r["q"].sum() - 8.0) < 1e-10
+    assert np.abs(r["forces"].sum(axis=0)).max() < 1e-10
+    assert r["e_scc"] > 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["h2o", "watercluster24", "ce_o"])
+def test_scc_single_point_device_vs_oracle(name):
+    from dftbplus_b200.api import HotPath
+    w, sk, geo, model, selfegy = _setup(name)
+    ref = sh.scc_single_point(sh.OracleArm(oracle, model, geo, selfegy), w, sk, geo, model.mOrb, mix=MIX[name],
+                              max_iter=600)
+    hp = HotPath(0)
+    try:
+        sk.upload(hp)
+        hp.set_geometry(geo)
+        got = sh.scc_single_point(sh.DeviceArm(hp, sk, geo), w, sk, geo, model.mOrb, mix=MIX[name], max_iter=600)
+        assert hp.kernel_launches > 5 * got["n_iter"]          # the CUDA path ran, every iteration
+    finally:
+        hp.close()
+    assert ref["err"] < 1e-8, "oracle arm did not converge"
+    assert got["n_iter"] == ref["n_iter"], (got["n_iter"], ref["n_iter"])
+    assert abs(got["energy"] - ref["energy"]) < TOL_ENERGY, (got["energy"], ref["energy"])
+    assert abs(got["e_h0"] - ref["e_h0"]) < TOL_ENERGY and abs(got["e_scc"] - ref["e_scc"]) < TOL_ENERGY
+    assert np.abs(got["q"] - ref["q"]).max() < 1e-9
+    assert np.abs(got["forces"] - ref["forces"]).max() < TOL_FORCE
