@@ -95,6 +95,28 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the newest committed
+    `ncu --set full` summary under profiles/ (tools/ncu_summary.py); None if there is none.  The
+    capture is a separate run of tools/gpu_probe.py under ncu, never the timed run."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_all_kernels*.txt")))
+    for path in reversed(files):
+        txt = open(path).read()
+        for block in txt.split("## launch")[1:]:
+            if kernel_substr not in block.splitlines()[0]:
+                continue
+            rd = re.search(r"dram read\s+([0-9.]+)\s+(\w+)", block)
+            wr = re.search(r"dram write\s+([0-9.]+)\s+(\w+)", block)
+            if not (rd and wr):
+                continue
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            total = float(rd.group(1)) * scale.get(rd.group(2), 1.0) + float(wr.group(1)) * scale.get(wr.group(2), 1.0)
+            return {"bytes_per_launch": total, "source": os.path.relpath(path, ROOT)}
+    return None
+
+
 def algorithmic_bytes_k1(geo):
     """16*n1*n2 + 8 per pair (H0 + S blocks written, iNeighbour + iPair read) + 16*n1^2 per atom
     (on-site blocks); DESIGN.md section K1 / SURVEY.md 8(d)."""
@@ -266,7 +288,9 @@ def main():
     k1_bytes = algorithmic_bytes_k1(geo)
     roofline = {"kernel": "k1_pair_build<H0+S>", "bound": "hbm", "achieved": k1_bytes / k1_ms / 1e6,
                 "peak": hbm_peak, "unit": "GB/s", "frac": k1_bytes / k1_ms / 1e6 / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
+                "traffic": (ncu_traffic("k1_pair_build") or {}).get("bytes_per_launch"),
+                "traffic_source": (ncu_traffic("k1_pair_build") or {}).get("source"),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
                 "ms_per_launch": k1_ms, "l2": "flushed between steps (256 MB memset)"}
     kernels = {"sparseH0S": {"ms": k1_ms, "pairs_per_s": pairs / k1_ms * 1e3},
                "forceCalc": {"ms": k5_ms, "pairs_per_s_this_rank": hpw.num_pairs / k5_ms * 1e3,
