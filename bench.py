@@ -343,7 +343,16 @@ def main():
     # ---- SCC step (dense section): (k, spin) sharded over ranks ----------------------------------
     scc, roofline_dm = None, None
     if not a.no_dense:
-        my_ks = schedule.parallel_ks(world, rank, 1, n_spin)
+        # (k, spin) pairs round-robin over ranks (TParallelKS); with more GPUs than pairs every pair
+        # gets a group of GPUs and its density matrix is split into column panels (schedule.dm_panels)
+        n_units = n_spin
+        if world <= n_units:
+            my_ks, my_panel, group_size = schedule.parallel_ks(world, rank, 1, n_spin), None, 1
+        else:
+            group_size = world // n_units
+            unit = rank // group_size
+            my_ks = [(1, unit + 1)] if unit < n_units else []
+            my_panel = schedule.dm_panels(geo["iAtomStart"], group_size)[rank % group_size] if my_ks else None
         n_elec = float(sum(sum(sk.occ[s - 1]) for s in w["species0"]))
         n_occ = int(round(n_elec / 2))
         with torch.cuda.stream(stream):
@@ -388,8 +397,12 @@ def main():
                 hp.unpackHS(ham_scc[iS - 1], square=sq)                      # H (this spin)
                 hp.unpackHS(over, square=sq)                                 # S
                 # (cuSOLVER hegvd would run here: H, S -> eigenvectors; timed separately below)
-                hp.getDensityMatrix(C, fill, dm=sq)
-                hp.packHS(rho[iS - 1], sq)
+                if my_panel is None:
+                    hp.getDensityMatrix(C, fill, dm=sq)
+                    hp.packHS(rho[iS - 1], sq)
+                elif my_panel[0] <= my_panel[1]:
+                    hp.getDensityMatrix(C, fill, dm=sq, cols=(my_panel[2], my_panel[3]))
+                    hp.packHS(rho[iS - 1], sq, atoms=(my_panel[0], my_panel[1]))
             if world > 1:
                 with torch.cuda.stream(stream):
                     dist.all_reduce(rho)                                     # main.F90:4179
@@ -406,6 +419,9 @@ def main():
         dm_ms = per["densityMatrix"]
         if dm_ms:
             flops = float(nOrb) * nOrb * n_occ          # n^2 * nLevels, one triangle, FMA = 2 flops
+            if my_panel is not None:                    # this rank's share of the triangle
+                c0, c1 = my_panel[2] - 1, my_panel[3]
+                flops *= (c1 - c0) * (2.0 * nOrb - c0 - c1) / (float(nOrb) * nOrb)
             roofline_dm = {"kernel": "k3_dm_real (DMMA m8n8k4)", "bound": "tensor",
                            "achieved": flops / dm_ms / 1e9, "peak": dgemm_tflops, "unit": "TFLOP/s",
                            "frac": flops / dm_ms / 1e9 / dgemm_tflops, "traffic": None,
@@ -423,7 +439,8 @@ def main():
         mk = tw["mulliken"]
         if mk[1]:
             kernels["mulliken"] = {"ms": mk[0] / mk[1], "GBs": 16.0 * ss / (mk[0] / mk[1]) / 1e6}
-        scc = {"ms_without_eigensolve": scc_ms, "ks_pairs_this_rank": len(my_ks), "n_spin": n_spin, "nOrb": nOrb,
+        scc = {"ms_without_eigensolve": scc_ms, "ks_pairs_this_rank": len(my_ks), "gpus_per_ks_pair": group_size,
+               "dm_panel_this_rank": list(my_panel) if my_panel is not None else None, "n_spin": n_spin, "nOrb": nOrb,
                "eigensolve_ms": None, "cublas_dgemm_tflops": dgemm_tflops,
                "note": "addShift (SCC Hamiltonian), then unpack(H), unpack(S), density matrix, pack per local (k,spin); all-reduce rho; Mulliken per spin"}
         del sq, C

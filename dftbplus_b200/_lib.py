@@ -36,6 +36,12 @@ SIGNATURES = {
     "dftbp_b200_pack_hs_cplx": (c_int, [c_void_p, c_void_p, c_void_p, c_int, P(c_double), c_double]),
     "dftbp_b200_density_matrix_real": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "dftbp_b200_density_matrix_cplx": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "dftbp_b200_density_matrix_real_cols": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                                    c_int, c_int]),
+    "dftbp_b200_density_matrix_cplx_cols": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                                    c_int, c_int]),
+    "dftbp_b200_pack_hs_real_atoms": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]),
+    "dftbp_b200_pack_hs_cplx_atoms": (c_int, [c_void_p, c_void_p, c_void_p, c_int, P(c_double), c_double, c_int, c_int]),
     "dftbp_b200_mulliken_orbital": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "dftbp_b200_mulliken_block": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "dftbp_b200_add_shift_atom": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),

@@ -210,18 +210,20 @@ class HotPath:
             self._ck(self._L.dftbp_b200_unpack_hs_cplx(self._h, _ptr(_f64(orig)), kp, _ptr(square), _ld(square)))
         return square
 
-    def packHS(self, primitive, square, kpoint=None, kweight=1.0):
-        """Accumulates into primitive (in place) like the reference."""
+    def packHS(self, primitive, square, kpoint=None, kweight=1.0, atoms=None):
+        """Accumulates into primitive (in place) like the reference.  atoms = (atomFirst, atomLast),
+        1-based inclusive: only the blocks of those atoms (a column panel, schedule.dm_panels)."""
+        a0, a1 = (1, self.geo["nAtom"]) if atoms is None else (int(atoms[0]), int(atoms[1]))
         if kpoint is None:
-            self._ck(self._L.dftbp_b200_pack_hs_real(self._h, _ptr(primitive), _ptr(square), _ld(square)))
+            self._ck(self._L.dftbp_b200_pack_hs_real_atoms(self._h, _ptr(primitive), _ptr(square), _ld(square), a0, a1))
         else:
             kp = (ctypes.c_double * 3)(*[float(x) for x in kpoint])
-            self._ck(self._L.dftbp_b200_pack_hs_cplx(self._h, _ptr(primitive), _ptr(square), _ld(square), kp,
-                                                     float(kweight)))
+            self._ck(self._L.dftbp_b200_pack_hs_cplx_atoms(self._h, _ptr(primitive), _ptr(square), _ld(square), kp,
+                                                           float(kweight), a0, a1))
         return primitive
 
     # ---- K3 ---------------------------------------------------------------------------------
-    def _dm(self, eigvecs, filling, weights, dm):
+    def _dm(self, eigvecs, filling, weights, dm, cols=None):
         cplx = (str(eigvecs.dtype).endswith("complex128"))
         n = eigvecs.shape[0]
         if dm is None:
@@ -229,19 +231,25 @@ class HotPath:
                 dm = new_dense(n, dtype=eigvecs.dtype, device=eigvecs.device)
             else:
                 dm = np.zeros((n, n), order="F", dtype=eigvecs.dtype)
-        fn = self._L.dftbp_b200_density_matrix_cplx if cplx else self._L.dftbp_b200_density_matrix_real
-        self._ck(fn(self._h, _ptr(dm), _ptr(eigvecs), n, _ld(eigvecs), _ptr(_f64(filling)),
-                    _ptr(None if weights is None else _f64(weights))))
+        if cols is None:
+            fn = self._L.dftbp_b200_density_matrix_cplx if cplx else self._L.dftbp_b200_density_matrix_real
+            self._ck(fn(self._h, _ptr(dm), _ptr(eigvecs), n, _ld(eigvecs), _ptr(_f64(filling)),
+                        _ptr(None if weights is None else _f64(weights))))
+        else:
+            fn = self._L.dftbp_b200_density_matrix_cplx_cols if cplx else self._L.dftbp_b200_density_matrix_real_cols
+            self._ck(fn(self._h, _ptr(dm), _ptr(eigvecs), n, _ld(eigvecs), _ptr(_f64(filling)),
+                        _ptr(None if weights is None else _f64(weights)), int(cols[0]), int(cols[1])))
         return dm
 
-    def getDensityMatrix(self, eigvecs, filling, dm=None):
-        """TDensityMatrix%getDensityMatrix (full, real or complex by dtype)."""
-        return self._dm(eigvecs, filling, None, dm)
+    def getDensityMatrix(self, eigvecs, filling, dm=None, cols=None):
+        """TDensityMatrix%getDensityMatrix (full, real or complex by dtype).  cols = (colFirst, colLast),
+        1-based inclusive: only that column panel of the lower triangle (schedule.dm_panels)."""
+        return self._dm(eigvecs, filling, None, dm, cols)
 
-    def getEDensityMatrix(self, eigvecs, filling, eigen, dm=None):
+    def getEDensityMatrix(self, eigvecs, filling, eigen, dm=None, cols=None):
         """TDensityMatrix%getEDensityMatrix: weights filling*eigen, nLevels from filling."""
         w = filling * eigen
-        return self._dm(eigvecs, filling, w, dm)
+        return self._dm(eigvecs, filling, w, dm, cols)
 
     # ---- K4 ---------------------------------------------------------------------------------
     def mulliken(self, over, rho, qq=None, block=False):

@@ -133,6 +133,8 @@ struct dftbp_b200_ctx {
   bool ownStream = true;
   std::string err;
   long long launches = 0;
+  int dmColFirst = 1, dmColLast = 0;            // column panel of the current density-matrix call
+  std::vector<long long> blockStartOfAtom;      // first entry of every atom in workAll / descAll (nAtom + 1)
   int smCount = 148;
   size_t smemOptin = 232448;  // max dynamic shared memory per CTA
   size_t smemPerSm = 233472;

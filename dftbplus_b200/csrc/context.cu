@@ -459,6 +459,8 @@ int dftbp_b200_set_geometry(dftbp_b200_ctx *ctx, int nAtom, int nAllAtom, int mN
   }
   DFTBP_TRY(uploadNew(ctx, &g.workAll, all.data(), all.size()));
   g.nWorkAll = (long long)all.size();
+  ctx->blockStartOfAtom.assign(nAtom + 1, 0);
+  for (int i = 0; i < nAtom; ++i) ctx->blockStartOfAtom[i + 1] = ctx->blockStartOfAtom[i] + hN[i] + 1;
   // resolve iNeighbour -> img2CentCell -> iAtomStart / iCellVec / iPair once per geometry (block_desc.cuh)
   auto describe = [&](const std::vector<int> &work) {
     std::vector<BlockDesc> d(work.size());

@@ -179,11 +179,13 @@ int unpackImpl(dftbp_b200_ctx *ctx, const double *orig, const double *kPoint, vo
 }
 
 int packImpl(dftbp_b200_ctx *ctx, double *primitive, const void *square, int ld, const double *kPoint,
-             double kWeight, bool cplx) {
+             double kWeight, bool cplx, int atomFirst = 1, int atomLast = 0) {
   if (!ctx) return DFTBP_B200_EINVAL;
   const Geometry &g = ctx->geo;
   DFTBP_CHECK(ctx, g.nAtom > 0, "packHS: no geometry set");
   DFTBP_CHECK(ctx, primitive && square && ld >= g.nOrb, "packHS: bad arguments");
+  if (atomLast <= 0) atomLast = g.nAtom;
+  DFTBP_CHECK(ctx, atomFirst >= 1 && atomFirst <= atomLast && atomLast <= g.nAtom, "packHS: bad atom range");
   const size_t nSq = (size_t)ld * g.nOrb * (cplx ? 2 : 1);
   double *dPrim;
   const double *dSq;
@@ -191,7 +193,10 @@ int packImpl(dftbp_b200_ctx *ctx, double *primitive, const void *square, int ld,
   DFTBP_TRY(devIn(ctx, kSlotB, (const double *)square, nSq, &dSq));
   {
     ScopedTimer timer(ctx, kTimerDenseToSparse);
-    const K2Params p = makeParams(ctx, ld, kPoint, kWeight);
+    K2Params p = makeParams(ctx, ld, kPoint, kWeight);
+    // only the blocks of atoms atomFirst..atomLast (= dense columns of those atoms): the work list is atom-major
+    p.desc = g.descAll + ctx->blockStartOfAtom[atomFirst - 1];
+    p.nWork = ctx->blockStartOfAtom[atomLast] - ctx->blockStartOfAtom[atomFirst - 1];
     const int grid = gridForChunks(ctx, p.nWork);
     const char *env = getenv("DFTBP_B200_K2_BATCH");  // tuning switch (tools/gpu_probe.py)
     const int batch = env ? atoi(env) : 1;
@@ -230,6 +235,17 @@ int dftbp_b200_pack_hs_cplx(dftbp_b200_ctx *ctx, double *primitive, const void *
                             const double kPoint[3], double kWeight) {
   if (ctx && !kPoint) return fail(ctx, DFTBP_B200_EINVAL, "pack_hs_cplx: kPoint is null");
   return packImpl(ctx, primitive, square, ld, kPoint, kWeight, true);
+}
+
+int dftbp_b200_pack_hs_real_atoms(dftbp_b200_ctx *ctx, double *primitive, const double *square, int ld,
+                                  int atomFirst, int atomLast) {
+  return packImpl(ctx, primitive, square, ld, nullptr, 1.0, false, atomFirst, atomLast);
+}
+
+int dftbp_b200_pack_hs_cplx_atoms(dftbp_b200_ctx *ctx, double *primitive, const void *square, int ld,
+                                  const double kPoint[3], double kWeight, int atomFirst, int atomLast) {
+  if (ctx && !kPoint) return fail(ctx, DFTBP_B200_EINVAL, "pack_hs_cplx: kPoint is null");
+  return packImpl(ctx, primitive, square, ld, kPoint, kWeight, true, atomFirst, atomLast);
 }
 
 }  // extern "C"

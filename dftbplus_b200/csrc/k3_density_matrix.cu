@@ -43,6 +43,7 @@ __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_grou
 // lower triangle of super-blocks, row-major inside.  Returns false when (ti, tj) is above the diagonal.
 struct TileOrder {
   int nT, G, nSB;
+  int tjFirst, tjLast;  // column panel (in tiles, inclusive): tiles outside are skipped (multi-GPU split of one dm)
 };
 
 __device__ __forceinline__ bool tileAt(const TileOrder &o, long long idx, int *ti, int *tj) {
@@ -57,7 +58,7 @@ __device__ __forceinline__ bool tileAt(const TileOrder &o, long long idx, int *t
   const int sj = (int)(sb - (long long)si * (si + 1) / 2);
   *ti = si * o.G + in / o.G;
   *tj = sj * o.G + in % o.G;
-  return *ti < o.nT && *tj <= *ti;
+  return *ti < o.nT && *tj <= *ti && *tj >= o.tjFirst && *tj <= o.tjLast;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -303,11 +304,13 @@ __global__ void k3_count_levels(const double *filling, int n, int *out) {
   if (threadIdx.x == 0) *out = best;
 }
 
-TileOrder makeOrder(int n, int BM) {
+TileOrder makeOrder(int n, int BM, int colFirst, int colLast) {
   TileOrder o;
   o.nT = (n + BM - 1) / BM;
   o.G = 12;
   o.nSB = (o.nT + o.G - 1) / o.G;
+  o.tjFirst = (colFirst - 1) / BM;  // 1-based inclusive dense columns -> tiles that overlap them
+  o.tjLast = (colLast - 1) / BM;
   return o;
 }
 
@@ -321,7 +324,7 @@ template <int BM, int BK, int ST, int WMn, int WNn, int VEC>
 int launchReal(dftbp_b200_ctx *ctx, int ctasPerSm, const double *dC, int ld, const double *dW, int n,
                const int *K, double *dDm, unsigned long long *counter) {
   const size_t smemB = sizeof(double) * (2 * ST * BK * (BM + 4) + ST * BK);
-  const TileOrder o = makeOrder(n, BM);
+  const TileOrder o = makeOrder(n, BM, ctx->dmColFirst, ctx->dmColLast);
   const long long nTiles = (long long)o.nT * (o.nT + 1) / 2;
   const int grid = (int)std::min<long long>(nTiles, (long long)ctasPerSm * ctx->smCount);
   auto kern = k3_dm_real<BM, BK, ST, WMn, WNn, VEC>;
@@ -331,9 +334,13 @@ int launchReal(dftbp_b200_ctx *ctx, int ctasPerSm, const double *dC, int ld, con
 }
 
 int densityImpl(dftbp_b200_ctx *ctx, void *dm, const void *eigvecs, int n, int ld, const double *filling,
-                const double *weights, bool cplx) {
+                const double *weights, bool cplx, int colFirst = 1, int colLast = 0) {
   if (!ctx) return DFTBP_B200_EINVAL;
   DFTBP_CHECK(ctx, dm && eigvecs && filling && n > 0 && ld >= n, "density_matrix: bad arguments");
+  if (colLast <= 0) colLast = n;
+  DFTBP_CHECK(ctx, colFirst >= 1 && colFirst <= colLast && colLast <= n, "density_matrix: bad column panel");
+  ctx->dmColFirst = colFirst;
+  ctx->dmColLast = colLast;
   const size_t el = cplx ? 2 : 1;
   const double *dC, *dF, *dW;
   double *dDm;
@@ -384,7 +391,7 @@ int densityImpl(dftbp_b200_ctx *ctx, void *dm, const void *eigvecs, int n, int l
   } else {
     constexpr int BM = 64, BK = 8, ST = 4;
     const size_t smemB = sizeof(double2) * (2 * ST * BK * (BM + 2)) + sizeof(double) * ST * BK;
-    const TileOrder o = makeOrder(n, BM);
+    const TileOrder o = makeOrder(n, BM, ctx->dmColFirst, ctx->dmColLast);
     const long long nTiles = (long long)o.nT * (o.nT + 1) / 2;
     const int grid = (int)std::min<long long>(nTiles, 2LL * ctx->smCount);
     auto kern = k3_dm_cplx<BM, BK, ST, 2, 2>;
@@ -408,6 +415,16 @@ int dftbp_b200_density_matrix_real(dftbp_b200_ctx *ctx, double *dm, const double
 int dftbp_b200_density_matrix_cplx(dftbp_b200_ctx *ctx, void *dm, const void *eigvecs, int n, int ld,
                                    const double *filling, const double *weights) {
   return densityImpl(ctx, dm, eigvecs, n, ld, filling, weights, true);
+}
+
+int dftbp_b200_density_matrix_real_cols(dftbp_b200_ctx *ctx, double *dm, const double *eigvecs, int n, int ld,
+                                        const double *filling, const double *weights, int colFirst, int colLast) {
+  return densityImpl(ctx, dm, eigvecs, n, ld, filling, weights, false, colFirst, colLast);
+}
+
+int dftbp_b200_density_matrix_cplx_cols(dftbp_b200_ctx *ctx, void *dm, const void *eigvecs, int n, int ld,
+                                        const double *filling, const double *weights, int colFirst, int colLast) {
+  return densityImpl(ctx, dm, eigvecs, n, ld, filling, weights, true, colFirst, colLast);
 }
 
 }  // extern "C"

@@ -46,3 +46,25 @@ def assemble_chunks(tensor, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=group)
     return tensor
+
+
+def dm_panels(i_atom_start, n_panel):
+    """Column panels of one density matrix for n_panel GPUs ("beyond (k,spin)
+    sharding"): contiguous atom ranges whose dense columns carry about equal shares of the LOWER
+    triangle (column c has nOrb - c rows below it, so the boundaries follow
+    nOrb * (1 - sqrt(1 - p / n_panel))), snapped to atom starts.
+    i_atom_start: iAtomStart(nAtom + 1), 1-based.  Returns [(atomFirst, atomLast, colFirst, colLast)]
+    (1-based, inclusive), one per panel; a panel may be empty (atomFirst > atomLast)."""
+    start = np.asarray(i_atom_start, dtype=np.int64)
+    n_atom, n_orb = len(start) - 1, int(start[-1] - 1)
+    cuts = [0]
+    for p in range(1, n_panel):
+        col = n_orb * (1.0 - np.sqrt(1.0 - p / n_panel))        # 0-based column boundary
+        a = int(np.searchsorted(start[:-1] - 1, col, side="left"))
+        cuts.append(min(max(a, cuts[-1]), n_atom))
+    cuts.append(n_atom)
+    out = []
+    for p in range(n_panel):
+        a0, a1 = cuts[p] + 1, cuts[p + 1]
+        out.append((a0, a1, int(start[a0 - 1]) if a0 <= n_atom else n_orb + 1, int(start[a1]) - 1 if a1 >= 1 else 0))
+    return out

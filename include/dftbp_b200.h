@@ -150,6 +150,24 @@ int dftbp_b200_density_matrix_real(dftbp_b200_ctx *ctx, double *dm, const double
 int dftbp_b200_density_matrix_cplx(dftbp_b200_ctx *ctx, void *dm_c128, const void *eigvecs_c128,
                                    int n, int ld, const double *filling, const double *weights);
 
+/* Multi-GPU split of ONE density matrix (more GPUs than (k-point, spin) pairs): only
+ * the lower-triangle tiles that overlap the dense columns colFirst..colLast (1-based, inclusive)
+ * are computed; entries outside the panel are unspecified.  With panels that start and end on atom
+ * boundaries, dftbp_b200_pack_hs_*_atoms folds exactly the panel's blocks (blocks of iAtom1 in
+ * atomFirst..atomLast, 1-based) into the sparse array, and the sum of the ranks' sparse arrays
+ * (the all-reduce of rhoPrim the reference does anyway, main.F90:4179) is the full result. */
+int dftbp_b200_density_matrix_real_cols(dftbp_b200_ctx *ctx, double *dm, const double *eigvecs, int n,
+                                        int ld, const double *filling, const double *weights,
+                                        int colFirst, int colLast);
+int dftbp_b200_density_matrix_cplx_cols(dftbp_b200_ctx *ctx, void *dm_c128, const void *eigvecs_c128,
+                                        int n, int ld, const double *filling, const double *weights,
+                                        int colFirst, int colLast);
+int dftbp_b200_pack_hs_real_atoms(dftbp_b200_ctx *ctx, double *primitive, const double *square, int ld,
+                                  int atomFirst, int atomLast);
+int dftbp_b200_pack_hs_cplx_atoms(dftbp_b200_ctx *ctx, double *primitive, const void *square_c128,
+                                  int ld, const double kPoint[3], double kWeight, int atomFirst,
+                                  int atomLast);
+
 /* ---- K4: Mulliken populations -------------------------------------------------------------- */
 
 /* mullikenPerOrbital, dftb/populations.F90:120-187.  qq(mOrb, nAtom) ACCUMULATES. */

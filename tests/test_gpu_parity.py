@@ -314,6 +314,29 @@ def test_k5_stress(name, hp_cache):
         assert np.abs(parts - oracle.stress(model, geo, dm, edm, vol, shift=sh)).max() < 1e-9
 
 
+@pytest.mark.parametrize("name,n_panel", [("fec128", 3), ("si512", 4), ("water1002", 8)])
+def test_k3_column_panels_sum_to_full(name, n_panel, hp_cache):
+    """One density matrix split over n_panel GPUs: column panels of the lower triangle + pack of the
+    panel's atoms; the ranks' sparse arrays add up to the single-GPU result bit for bit."""
+    from dftbplus_b200 import schedule
+    w, sk, geo, model, selfegy, H, S, eig, C, f = _eig_case(name)
+    hp = hp_cache(name)
+    ss = geo["sparseSize"]
+    full = hp.packHS(np.zeros(ss), hp.getDensityMatrix(C, f))
+    efull = hp.packHS(np.zeros(ss), hp.getEDensityMatrix(C, f, eig))
+    parts, eparts = np.zeros(ss), np.zeros(ss)
+    for (a0, a1, c0, c1) in schedule.dm_panels(geo["iAtomStart"], n_panel):
+        if a0 > a1:
+            continue
+        part = hp.packHS(np.zeros(ss), hp.getDensityMatrix(C, f, cols=(c0, c1)), atoms=(a0, a1))
+        assert np.count_nonzero(part) <= np.count_nonzero(full)
+        parts += part
+        eparts += hp.packHS(np.zeros(ss), hp.getEDensityMatrix(C, f, eig, cols=(c0, c1)), atoms=(a0, a1))
+    assert np.array_equal(parts, full)
+    assert np.array_equal(eparts, efull)
+    assert_sparse_close(full, oracle.pack_hs_real(geo, np.zeros(ss), oracle.density_matrix(C, f)), what="rho")
+
+
 def test_hegv_cusolver(hp_cache):
     w, sk, geo, model, selfegy, H, S, eig, C, f = _eig_case("ce_o")
     hp = hp_cache("ce_o")

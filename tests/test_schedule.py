@@ -54,3 +54,25 @@ def test_parallel_ks_round_robin():
     allks = sorted(sum(got, []))
     assert allks == sorted((k, s) for s in (1, 2) for k in (1, 2, 3, 4))
     assert schedule.parallel_ks(1, 0, 2, 2) == [(1, 1), (2, 1), (1, 2), (2, 2)]
+
+
+def test_dm_panels_cover_and_balance():
+    """Column panels of one density matrix (multi-GPU split beyond (k, spin) sharding): contiguous,
+    disjoint, complete, on atom boundaries, and about equal shares of the lower triangle."""
+    from dftbplus_b200 import schedule
+    rng = np.random.default_rng(4)
+    n_orb_atom = rng.choice([1, 4, 9], size=500)
+    start = np.concatenate([[1], 1 + np.cumsum(n_orb_atom)])
+    n = int(start[-1] - 1)
+    for n_panel in (1, 2, 3, 4, 8):
+        panels = schedule.dm_panels(start, n_panel)
+        assert len(panels) == n_panel
+        assert panels[0][0] == 1 and panels[-1][1] == 500 and panels[0][2] == 1 and panels[-1][3] == n
+        area = []
+        for k, (a0, a1, c0, c1) in enumerate(panels):
+            assert c0 == start[a0 - 1] and c1 == start[a1] - 1
+            if k:
+                assert a0 == panels[k - 1][1] + 1 and c0 == panels[k - 1][3] + 1
+            cols = np.arange(c0 - 1, c1)
+            area.append(float(np.sum(n - cols)))
+        assert max(area) / (sum(area) / n_panel) < 1.05
