@@ -52,35 +52,59 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The
+    sampler is started before the warm-up (nvidia-smi needs a few hundred ms to come up, the timed
+    region of this benchmark is only milliseconds long) and read after the per-routine timing loop;
+    a reader thread keeps the lines, `mark()` brackets the part that belongs to the GPU-busy window."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc = index, None
+        self.index, self.proc, self.lines, self.t0, self.thread = index, None, [], None, None
 
     def start(self):
+        import threading
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
+            return
+
+        def reader():
+            try:
+                for line in self.proc.stdout:
+                    self.lines.append((time.perf_counter(), line))
+            except Exception:
+                pass
+        self.thread = threading.Thread(target=reader, daemon=True)
+        self.thread.start()
+
+    def mark(self):
+        """start of the GPU-busy window"""
+        self.t0 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            deadline = time.perf_counter() + 3.0       # at least one sample inside the window
+            while time.perf_counter() < deadline and not any(t >= (self.t0 or 0.0) for t, _ in self.lines):
+                time.sleep(0.02)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
         except Exception:
-            self.proc.kill()
-            out = ""
+            pass
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
+        for t, line in list(self.lines):
+            if self.t0 is not None and t < self.t0:
+                continue
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -92,7 +116,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons),
+                "window": "timed steps + per-routine timing loop (GPU busy throughout)"}
 
 
 def ncu_traffic(kernel_substr):
@@ -251,11 +276,12 @@ def main():
                 dist.all_reduce(deriv)                                   # assembleChunks(env, deriv)
 
     # ---- value: device-resident, CUDA events on the launch stream -------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(a.warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark()
     l0 = hp.kernel_launches + (hpw.kernel_launches if hpw is not hp else 0)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * a.steps)]
     for i in range(a.steps):
@@ -266,7 +292,6 @@ def main():
         ev[2 * i + 1].record(stream)
     stream.synchronize()
     barrier()
-    clocks = sampler.stop()
     launches = hp.kernel_launches + (hpw.kernel_launches if hpw is not hp else 0) - l0
     ms_dev = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(a.steps)) / a.steps
     ms_dev = max_over_ranks(ms_dev)
@@ -282,6 +307,13 @@ def main():
         step_device()
     t = hp.timer_read()
     tw = hpw.timer_read()
+    # keep the GPU busy until nvidia-smi has delivered samples from inside the window
+    for i in range(200):
+        if any(ts >= sampler.t0 for ts, _ in sampler.lines) and i >= 20:
+            break
+        step_device()
+    stream.synchronize()
+    clocks = sampler.stop()
     k1_ms = t["sparseH0S"][0] / max(1, t["sparseH0S"][1])
     k5_ms = tw["forceCalc"][0] / max(1, tw["forceCalc"][1])
     hbm_peak, peak_src = peaks()
