@@ -308,8 +308,8 @@ def main():
     t = hp.timer_read()
     tw = hpw.timer_read()
     # keep the GPU busy until nvidia-smi has delivered samples from inside the window
-    for i in range(200):
-        if any(ts >= sampler.t0 for ts, _ in sampler.lines) and i >= 20:
+    for i in range(1500):
+        if sum(1 for ts, _ in sampler.lines if ts >= sampler.t0) >= 4 and i >= 20:
             break
         step_device()
     stream.synchronize()
