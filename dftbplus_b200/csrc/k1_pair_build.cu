@@ -30,7 +30,9 @@ struct K1Params {
   int firstAtom, lastAtom;  // on-site blocks of this rank
   const int *species;
   const int *iPair;
-  const double *selfE;  // (mOrb, nSpecies)
+  const double *selfegy;  // (mShell, nSpecies) on-site energies per shell (atomEigVal)
+  const int *orbShell;    // (mOrb, nSpecies) shell index of each orbital
+  int mShell;
   double *ham;
   double *over;
 };
@@ -128,19 +130,12 @@ __global__ void __launch_bounds__(32 * WARPS, CTAS) k1_pair_build(const K1Params
     const int ind = __ldg(p.iPair + (size_t)p.ld * iAt);
     for (int e = lane; e < nElem; e += 32) {
       const int a = e / n, b = e - a * n;
-      if (p.ham) p.ham[ind + e] = (a == b) ? __ldg(p.selfE + a + p.mOrb * sp) : 0.0;
+      // ham(iOrig + iOrb) = selfegy(iShellOrb(iOrb, sp), sp) on the diagonal (nonscc.F90:109-116)
+      if (p.ham)
+        p.ham[ind + e] = (a == b) ? __ldg(p.selfegy + __ldg(p.orbShell + a + p.mOrb * sp) + p.mShell * sp) : 0.0;
       if (p.over) p.over[ind + e] = (a == b) ? 1.0 : 0.0;
     }
   }
-}
-
-// selfegy(mShell, nSpecies) -> per-orbital on-site energies (mOrb, nSpecies)
-__global__ void k1_expand_selfegy(const double *selfegy, const int *orbShell, const int *nOrbSpecies,
-                                  int mShell, int mOrb, int nSpecies, double *selfE) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= mOrb * nSpecies) return;
-  const int sp = i / mOrb, o = i - sp * mOrb;
-  selfE[i] = o < nOrbSpecies[sp] ? selfegy[orbShell[i] + mShell * sp] : 0.0;
 }
 
 template <int LMAX, int WARPS, int CTAS>
@@ -182,17 +177,12 @@ int launchBuild(dftbp_b200_ctx *ctx, const double *selfegy, double *ham, double 
   p.ld = g.mNeigh + 1; p.nSpecies = ctx->nSpecies; p.mOrb = ctx->mOrb;
   p.firstAtom = g.firstAtomMine; p.lastAtom = g.lastAtomMine;
   p.species = g.species;
-  p.iPair = g.iPair; p.selfE = ctx->dSelfE; p.ham = nullptr; p.over = nullptr;
+  p.iPair = g.iPair; p.selfegy = nullptr; p.orbShell = ctx->dOrbShell; p.mShell = ctx->mShell;
+  p.ham = nullptr; p.over = nullptr;
   const bool partial = ctx->nRanks > 1;  // other ranks' segments stay zero (assembleChunks sums)
   if (ham) {
     DFTBP_CHECK(ctx, selfegy != nullptr, "build_h0: selfegy is null");
-    const double *dSelf;
-    DFTBP_TRY(devIn(ctx, kSlotC, selfegy, (size_t)ctx->mShell * ctx->nSpecies, &dSelf));
-    const int n = ctx->mOrb * ctx->nSpecies;
-    k1_expand_selfegy<<<(n + 127) / 128, 128, 0, ctx->stream>>>(dSelf, ctx->dOrbShell, ctx->dNOrbSpecies,
-                                                               ctx->mShell, ctx->mOrb, ctx->nSpecies,
-                                                               ctx->dSelfE);
-    ctx->launches++;
+    DFTBP_TRY(devIn(ctx, kSlotC, selfegy, (size_t)ctx->mShell * ctx->nSpecies, &p.selfegy));
     DFTBP_TRY(devOut(ctx, kSlotA, ham, (size_t)g.sparseSize, false, &p.ham));
     if (partial) DFTBP_CUDA(ctx, cudaMemsetAsync(p.ham, 0, sizeof(double) * g.sparseSize, ctx->stream));
   }

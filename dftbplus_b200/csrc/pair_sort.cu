@@ -66,8 +66,11 @@ __global__ void __launch_bounds__(kSortThreads) ps_keys(const int *__restrict__ 
 }
 
 // one CTA: exclusive scan bucket by bucket (nBins entries each), every bucket starts on a multiple of 32
+// The padding slots behind every bucket get ind = -1 / item = -1 here (at most 31 per bucket), so the
+// schedule arrays need no fill pass.
 __global__ void __launch_bounds__(1024) ps_scan(int *__restrict__ hist, int nBuckets, int nBins,
-                                                int *__restrict__ total) {
+                                                int *__restrict__ total, int *__restrict__ items,
+                                                PairRec *__restrict__ recs) {
   __shared__ int warpSum[32];
   __shared__ int baseSh;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -97,6 +100,11 @@ __global__ void __launch_bounds__(1024) ps_scan(int *__restrict__ hist, int nBuc
     const int incl = x + (w > 0 ? warpSum[w - 1] : 0);
     if (t < nBins) hist[b * nBins + t] = base + incl - v;
     __syncthreads();
+    const int endB = base + warpSum[31];  // first slot behind the bucket
+    if (t < 32 && endB + t < ((endB + 31) & ~31)) {
+      items[endB + t] = -1;
+      recs[endB + t].ind = -1;
+    }
     if (t == 1023) baseSh = (base + incl + 31) & ~31;
     __syncthreads();
   }
@@ -212,9 +220,7 @@ int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out
   DFTBP_TRY(growTo(ctx, &ctx->sortKeys, &ctx->sortKeysCap, std::max(nWork, 1LL)));
   DFTBP_TRY(growTo(ctx, &ctx->sortBins, &ctx->sortBinsCap, nBins64));
   DFTBP_CUDA(ctx, cudaMemsetAsync(ctx->sortBins, 0, sizeof(int) * nBins64, ctx->stream));
-  DFTBP_CUDA(ctx, cudaMemsetAsync(sp.items, 0xFF, sizeof(int) * sp.capacity, ctx->stream));
-  // padding slots: ind = -1 (the consumers then shadow lane 0 of the chunk)
-  DFTBP_CUDA(ctx, cudaMemsetAsync(sp.recs, 0xFF, sizeof(PairRec) * sp.capacity, ctx->stream));
+  // padding slots (item = -1, ind = -1: the consumers then shadow lane 0 of the chunk) are written by ps_scan
   const double binScale = (double)nBins / (ctx->cutoff > 0.0 ? ctx->cutoff : 1.0);
   if (nWork > 0) {
     // slabs of at least 2048 items per CTA (aggregation), at most one CTA per SM
@@ -225,7 +231,7 @@ int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out
     ps_keys<<<grid, kSortThreads, smemBytes, ctx->stream>>>(work, nWork, g.mNeigh + 1, ctx->nSpecies, nBins, nKeys,
                                                            g.coords, g.species, g.iNeighbour, binScale,
                                                            ctx->sortKeys, ctx->sortBins);
-    ps_scan<<<1, 1024, 0, ctx->stream>>>(ctx->sortBins, nBuckets, nBins, sp.total);
+    ps_scan<<<1, 1024, 0, ctx->stream>>>(ctx->sortBins, nBuckets, nBins, sp.total, sp.items, sp.recs);
     ps_scatter<<<grid, kSortThreads, smemBytes, ctx->stream>>>(work, nWork, nKeys, ctx->sortKeys, ctx->sortBins,
                                                               sp.items, sp.recs, sp.atoms, g.mNeigh + 1,
                                                               ctx->nSpecies, g.coords, g.species, g.iNeighbour,

@@ -337,6 +337,37 @@ def test_k3_column_panels_sum_to_full(name, n_panel, hp_cache):
     assert_sparse_close(full, oracle.pack_hs_real(geo, np.zeros(ss), oracle.density_matrix(C, f)), what="rho")
 
 
+@pytest.mark.parametrize("name", ["water1002", "fec128"])
+def test_md_like_coordinate_updates(name):
+    """BASELINE config 5 pattern: the atoms move every step while the neighbour list stays; the host
+    calls update_coords (the device re-sorts its pair schedule) and rebuilds H0 / S and the forces.
+    Every step is compared with the oracle on the moved geometry; the images move with their atoms."""
+    from dftbplus_b200.api import HotPath
+    w, sk, geo, model, selfegy = case(name)
+    rng = np.random.default_rng(23)
+    hp = HotPath(0)
+    try:
+        sk.upload(hp)
+        hp.set_geometry(geo)
+        s0 = oracle.build_s(model, geo)
+        dm = s0 * rng.normal(size=geo["sparseSize"])
+        edm = s0 * rng.normal(size=geo["sparseSize"])
+        coords = geo["coords"].copy()
+        for step in range(4):
+            coords = coords + 0.02 * rng.normal(size=(geo["nAtom"], 3))[geo["img2CentCell"] - 1]
+            g = dict(geo)
+            g["coords"] = np.ascontiguousarray(coords)
+            hp.update_coords(g["coords"])
+            h, s = hp.buildH0S(sk.selfegy)
+            assert_sparse_close(h, oracle.build_h0(model, g, selfegy), what="H0 step %d" % step)
+            assert_sparse_close(s, oracle.build_s(model, g), what="S step %d" % step)
+            d = hp.derivative_shift(dm, edm)
+            assert np.abs(d - oracle.derivative_shift(model, g, dm, edm)).max() < TOL_FORCE
+        assert not np.array_equal(s, s0)
+    finally:
+        hp.close()
+
+
 def test_hegv_cusolver(hp_cache):
     w, sk, geo, model, selfegy, H, S, eig, C, f = _eig_case("ce_o")
     hp = hp_cache("ce_o")
