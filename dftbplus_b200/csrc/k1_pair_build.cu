@@ -154,15 +154,15 @@ int launchTyped(dftbp_b200_ctx *ctx, const K1Params &p, long long items) {
   return 0;
 }
 
-// resident warps per SM: 8 x 2 (128 registers) or 6 x 3 (112 registers); the staging tiles
-// (11.5 KB per warp for spd) allow at most 19
+// resident warps per SM (fec4096): the time hardly depends on it -- 8 warps at 255 registers 75 us,
+// 12 at 168 63 us, 16 at 128 65 us, 18 at 96 66 us; the staging tiles (11.5 KB per warp for spd) allow at most 19
 template <int LMAX>
 int launchTypedAny(dftbp_b200_ctx *ctx, const K1Params &p, long long items) {
   const char *env = getenv("DFTBP_B200_K1_CFG");  // tuning switch (tools/gpu_probe.py)
-  const int cfg = env ? atoi(env) : 82;
-  if (cfg == 63) return launchTyped<LMAX, 6, 3>(ctx, p, items);
-  if (cfg == 44) return launchTyped<LMAX, 4, 4>(ctx, p, items);
-  return launchTyped<LMAX, 8, 2>(ctx, p, items);
+  const int cfg = env ? atoi(env) : 62;
+  if (cfg == 82) return launchTyped<LMAX, 8, 2>(ctx, p, items);  // 16 warps per SM, 128 registers: 65 us
+  if (cfg == 63) return launchTyped<LMAX, 6, 3>(ctx, p, items);  // 18 warps, 96 registers: 66 us
+  return launchTyped<LMAX, 6, 2>(ctx, p, items);                  // 12 warps, 168 registers: 63 us (default)
 }
 
 int launchBuild(dftbp_b200_ctx *ctx, const double *selfegy, double *ham, double *over) {

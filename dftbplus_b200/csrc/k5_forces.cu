@@ -226,8 +226,8 @@ void launchWeightsDiag(const K5WeightParams &wp, int nSpin, int grid, cudaStream
   else k5_force_weights_diag<BATCH, 4><<<grid, 256, 0, stream>>>(wp);
 }
 
-template <int LMAX, bool STRESS>
-__global__ void __launch_bounds__(320, 1) k5_derivative_shift(const K5Params p) {
+template <int LMAX, bool STRESS, int WARPS, int UNR>
+__global__ void __launch_bounds__(32 * WARPS, 1) k5_derivative_shift(const K5Params p) {
   extern __shared__ double smem[];
   double st[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // STRESS: this lane's share of st(jj,ii)
   const int lane = threadIdx.x & 31, wIn = threadIdx.x >> 5, nW = blockDim.x >> 5;
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(320, 1) k5_derivative_shift(const K5Params p) 
     double g0 = 0.0, g1 = 0.0, g2 = 0.0;
     if (__any_sync(0xffffffffu, live)) {
       if (live) skLaneWBuildAny<LMAX>(pg, row);
-#pragma unroll 1
+#pragma unroll UNR
       for (int k = 0; k < 6; ++k) {
         const int jj = k >> 1;
         // vect(jj) = vect(jj) - real(2*ii-3) * deltaXDiff : ii=1 -> +delta, ii=2 -> -delta
@@ -462,23 +462,36 @@ int launchRichardson(dftbp_b200_ctx *ctx, const K5Params &p, long long chunks) {
   return 0;
 }
 
-template <int LMAX, bool STRESS>
-int launchTypedS(dftbp_b200_ctx *ctx, const K5Params &p, long long items, int warps, size_t smemBytes) {
-  DFTBP_CUDA(ctx, cudaFuncSetAttribute(k5_derivative_shift<LMAX, STRESS>,
+template <int LMAX, bool STRESS, int WARPS, int UNR>
+int launchTypedS(dftbp_b200_ctx *ctx, const K5Params &p, long long items, int warpsMax, size_t perWarp) {
+  const int warps = std::min(WARPS, warpsMax);
+  if (warps < WARPS) return fail(ctx, DFTBP_B200_EINVAL, "derivative_shift: weight tile too large for %d warps", WARPS);
+  const size_t smemBytes = perWarp * WARPS;
+  DFTBP_CUDA(ctx, cudaFuncSetAttribute(k5_derivative_shift<LMAX, STRESS, WARPS, UNR>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
   int perSm = 1;  // resident CTAs per SM (registers and the weight tile decide)
-  DFTBP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k5_derivative_shift<LMAX, STRESS>,
-                                                                32 * warps, smemBytes));
+  DFTBP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k5_derivative_shift<LMAX, STRESS, WARPS, UNR>,
+                                                                32 * WARPS, smemBytes));
   const int grid = (int)std::max<long long>(
-      1, std::min<long long>((items + warps - 1) / warps, (long long)ctx->smCount * std::max(perSm, 1)));
-  k5_derivative_shift<LMAX, STRESS><<<grid, 32 * warps, smemBytes, ctx->stream>>>(p);
+      1, std::min<long long>((items + WARPS - 1) / WARPS, (long long)ctx->smCount * std::max(perSm, 1)));
+  k5_derivative_shift<LMAX, STRESS, WARPS, UNR><<<grid, 32 * WARPS, smemBytes, ctx->stream>>>(p);
   return 0;
 }
 
+// Warps per CTA (one CTA per SM): the weight tile is 32 x mOrb^2 doubles per warp -- 21 KB for spd,
+// 66 KB with f shells.  s/p/d: 8 warps with the full 255 registers beat 10 warps at 168 registers
+// (119 vs 135 us on fec4096: the evaluator is register starved, not occupancy starved); unrolling
+// the displacement loop by two does not help (136 us).
+template <int LMAX, bool STRESS>
+int launchByWarps(dftbp_b200_ctx *ctx, const K5Params &p, long long items, int warpsMax, size_t perWarp) {
+  if constexpr (LMAX <= 2) return launchTypedS<LMAX, STRESS, 8, 1>(ctx, p, items, warpsMax, perWarp);
+  else return launchTypedS<LMAX, STRESS, 2, 1>(ctx, p, items, warpsMax, perWarp);
+}
+
 template <int LMAX>
-int launchTyped(dftbp_b200_ctx *ctx, const K5Params &p, long long items, int warps, size_t smemBytes) {
-  if (p.stress) return launchTypedS<LMAX, true>(ctx, p, items, warps, smemBytes);
-  return launchTypedS<LMAX, false>(ctx, p, items, warps, smemBytes);
+int launchTyped(dftbp_b200_ctx *ctx, const K5Params &p, long long items, int warpsMax, size_t perWarp) {
+  if (p.stress) return launchByWarps<LMAX, true>(ctx, p, items, warpsMax, perWarp);
+  return launchByWarps<LMAX, false>(ctx, p, items, warpsMax, perWarp);
 }
 
 }  // namespace
@@ -556,9 +569,8 @@ int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, c
     p.pitch = (ctx->mOrb * ctx->mOrb) | 1;
     const size_t perWarp = sizeof(double) * 32 * (size_t)p.pitch;
     // 10 warps x <= 204 registers fill the register file; the weight tile usually limits first
-    int warps = (int)std::min<size_t>(10, (ctx->smemOptin - 2048) / perWarp);
+    const int warps = (int)std::min<size_t>(10, (ctx->smemOptin - 2048) / perWarp);
     DFTBP_CHECK(ctx, warps >= 1, "derivative_shift: weight tile does not fit into shared memory");
-    const size_t smemBytes = perWarp * warps;
     const long long items = 2 * ((g.nWorkLoad + 31) / 32 + ctx->nSpecies * ctx->nSpecies);
     int rc;
     if (diffType == DFTBP_B200_DIFF_RICHARDSON) {
@@ -566,9 +578,9 @@ int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, c
       if (ctx->lMaxAll <= 1) rc = launchRichardson<1>(ctx, p, chunks);
       else if (ctx->lMaxAll == 2) rc = launchRichardson<2>(ctx, p, chunks);
       else rc = launchRichardson<3>(ctx, p, chunks);
-    } else if (ctx->lMaxAll <= 1) rc = launchTyped<1>(ctx, p, items, warps, smemBytes);
-    else if (ctx->lMaxAll == 2) rc = launchTyped<2>(ctx, p, items, warps, smemBytes);
-    else rc = launchTyped<3>(ctx, p, items, warps, smemBytes);
+    } else if (ctx->lMaxAll <= 1) rc = launchTyped<1>(ctx, p, items, warps, perWarp);
+    else if (ctx->lMaxAll == 2) rc = launchTyped<2>(ctx, p, items, warps, perWarp);
+    else rc = launchTyped<3>(ctx, p, items, warps, perWarp);
     if (rc) return rc;
     ctx->launches++;
   }
