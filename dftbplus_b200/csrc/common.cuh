@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -298,6 +299,12 @@ inline int uploadNew(dftbp_b200_ctx *ctx, T **dst, const T *src, size_t count) {
   // the source may be a temporary host vector: make the copy complete before returning
   DFTBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
+}
+
+// tuning switch read from the environment (tools/gpu_probe.py A/B runs); def when unset
+inline int tuneInt(const char *name, int def) {
+  const char *env = getenv(name);
+  return env ? atoi(env) : def;
 }
 
 inline int gridFor(const dftbp_b200_ctx *ctx, long long nWarpItems, int warpsPerCta, int ctasPerSm) {

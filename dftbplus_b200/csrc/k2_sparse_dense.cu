@@ -148,7 +148,7 @@ K2Params makeParams(dftbp_b200_ctx *ctx, int ldSq, const double *k, double kWeig
 
 // one chunk of blocks per warp and pass; enough CTAs to fill the machine, 8 resident per SM
 int gridForChunks(const dftbp_b200_ctx *ctx, long long nBlocks) {
-  return gridFor(ctx, (nBlocks + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, 8);
+  return gridFor(ctx, (nBlocks + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, tuneInt("DFTBP_B200_K2_CTAS", 8));
 }
 
 int unpackImpl(dftbp_b200_ctx *ctx, const double *orig, const double *kPoint, void *square, int ld, bool cplx) {

@@ -136,7 +136,7 @@ int mullikenImpl(dftbp_b200_ctx *ctx, double *qq, const double *over, const doub
   p.desc = g.descLoad; p.nWork = g.nWorkLoad; p.mOrb = ctx->mOrb;
   if (p.nWork > 0) {
     ScopedTimer timer(ctx, kTimerMulliken);
-    const int grid = gridFor(ctx, (p.nWork + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, 8);
+    const int grid = gridFor(ctx, (p.nWork + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, tuneInt("DFTBP_B200_K4_CTAS", 8));
     if (block) {
       k4_mulliken_block<<<grid, 256, 0, ctx->stream>>>(p, dOver, dRho, dQ);
     } else if (ctx->mOrb <= 9) {  // 8 warps x BATCH blocks x 96 doubles

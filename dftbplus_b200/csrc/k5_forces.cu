@@ -553,7 +553,7 @@ int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, c
       wp.nAtom = g.nAtom; wp.nSpin = nSpin; wp.sparseSize = g.sparseSize;
       wp.DM = p.DM; wp.EDM = dEDM; wp.shift = dShift; wp.shiftFull = flag; wp.negWS = (double *)scratch;
       wp.selfImages = st ? 1 : 0;
-      const int wGrid = gridFor(ctx, (wp.nWork + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, 4);
+      const int wGrid = gridFor(ctx, (wp.nWork + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, tuneInt("DFTBP_B200_K5W_CTAS", 4));
       // both instantiations are launched; the one that does not match the device flag returns at once
       {
         const char *env = getenv("DFTBP_B200_K5W_BATCH");  // tuning switch (tools/gpu_probe.py)

@@ -137,7 +137,7 @@ int addShiftImpl(dftbp_b200_ctx *ctx, double *ham, const double *over, const dou
   p.shiftFull = ctx->dInfo + 1;
   if (p.nWork > 0) {
     ScopedTimer timer(ctx, kTimerAddShift);
-    const int grid = gridFor(ctx, (p.nWork + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, 4);
+    const int grid = gridFor(ctx, (p.nWork + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, tuneInt("DFTBP_B200_K6_CTAS", 4));
     if (!block) {
       launchMode<0>(p, isInputZero != 0, grid, ctx->stream);
       ctx->launches++;
