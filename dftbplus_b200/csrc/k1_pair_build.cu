@@ -159,10 +159,10 @@ int launchTyped(dftbp_b200_ctx *ctx, const K1Params &p, long long items) {
 template <int LMAX>
 int launchTypedAny(dftbp_b200_ctx *ctx, const K1Params &p, long long items) {
   const char *env = getenv("DFTBP_B200_K1_CFG");  // tuning switch (tools/gpu_probe.py)
-  const int cfg = env ? atoi(env) : 62;
-  if (cfg == 82) return launchTyped<LMAX, 8, 2>(ctx, p, items);  // 16 warps per SM, 128 registers: 65 us
+  const int cfg = env ? atoi(env) : 82;
+  if (cfg == 62) return launchTyped<LMAX, 6, 2>(ctx, p, items);  // 12 warps, 168 registers: 63 us warm, 74 us with L2 flushed
   if (cfg == 63) return launchTyped<LMAX, 6, 3>(ctx, p, items);  // 18 warps, 96 registers: 66 us
-  return launchTyped<LMAX, 6, 2>(ctx, p, items);                  // 12 warps, 168 registers: 63 us (default)
+  return launchTyped<LMAX, 8, 2>(ctx, p, items);                  // 16 warps, 128 registers: 65 us warm, 69 us flushed (default)
 }
 
 int launchBuild(dftbp_b200_ctx *ctx, const double *selfegy, double *ham, double *over) {
