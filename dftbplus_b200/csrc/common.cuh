@@ -29,23 +29,10 @@ struct SkTableDev {
   int mIndM1;  // skEqGridOld: mInd - 1, the first grid interval beyond the tail (slakoeqgrid.F90:268,295)
 };
 
-// A_k = sum_mu t[mu] * V[vBase + mu]   (tools/gen_sk_gaunt.py)
-struct ADesc {
-  double t[4];
-  int vBase, cnt, pad0, pad1;  // 48 bytes: keeps 16-byte alignment for vector loads
-};
-
-struct DevTerm {
-  double coef;
-  int y, aslot;
-};
-
 // Everything the pair kernels need for one ordered species pair (sp1 = atom, sp2 = neighbour).
 struct SpPairProg {
   SkTableDev H, S;
   int nOrb1, nOrb2, nInteg, nY;
-  int aOff;     // first ADesc
-  int elemOff;  // first entry of elemStart (nOrb1*nOrb2 + 1 entries, absolute term indices)
   int nSh1, nSh2;                     // shells of the atom / of the neighbour
   unsigned long long shells1, shells2;  // angular momentum per shell, 4 bits each (shell 0 lowest)
   int canon1, canon2;  // lmax if the species' shells are exactly l = 0..lmax in order (s, sp, spd, spdf), else -1
@@ -149,10 +136,6 @@ struct dftbp_b200_ctx {
   // SK programs
   std::vector<dftbp_b200::SpPairProg> progs;  // [sp1 + nSpecies*sp2]
   dftbp_b200::SpPairProg *dProgs = nullptr;
-  dftbp_b200::ADesc *dADesc = nullptr;
-  int *dElemStart = nullptr;
-  dftbp_b200::DevTerm *dTerms = nullptr;
-  void *dYDesc = nullptr;
   bool progsDirty = true;
   std::vector<void *> tableAllocs;
   double cutoff = 0.0;
@@ -165,7 +148,6 @@ struct dftbp_b200_ctx {
   long long sortKeysCap = 0, sortBinsCap = 0;
   std::vector<dftbp_b200::Staging> staging;
   std::vector<dftbp_b200::PendingCopy> pending;
-  double *dSelfE = nullptr;  // (mOrb, nSpecies) on-site energy per orbital
   bool timing = false;
   std::vector<dftbp_b200::TimedSpan> spans;
   std::vector<cudaEvent_t> eventPool;

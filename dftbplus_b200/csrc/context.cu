@@ -3,7 +3,6 @@
 #include <cmath>
 
 #include "block_desc.cuh"
-#include "sk_gaunt_tables.h"
 
 using namespace dftbp_b200;
 
@@ -162,8 +161,7 @@ int dftbp_b200_destroy(dftbp_b200_ctx *ctx) {
   freeSortedPairs(ctx);
   for (void *p : ctx->tableAllocs) cudaFree(p);
   for (Staging &s : ctx->staging) cudaFree(s.ptr);
-  cudaFree(ctx->dNOrbSpecies); cudaFree(ctx->dOrbShell); cudaFree(ctx->dProgs); cudaFree(ctx->dADesc);
-  cudaFree(ctx->dElemStart); cudaFree(ctx->dTerms); cudaFree(ctx->dYDesc); cudaFree(ctx->dSelfE);
+  cudaFree(ctx->dNOrbSpecies); cudaFree(ctx->dOrbShell); cudaFree(ctx->dProgs);
   cudaFree(ctx->solverWork); cudaFree(ctx->dInfo);
   solverDestroy(ctx);
   for (TimedSpan &sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -252,7 +250,7 @@ int dftbp_b200_set_orbitals(dftbp_b200_ctx *ctx, int nSpecies, int mShell, const
     DFTBP_CHECK(ctx, nShell[sp] >= 1 && nShell[sp] <= mShell, "set_orbitals: nShell out of range");
     for (int sh = 0; sh < nShell[sp]; ++sh) {
       int l = angShell[sh + mShell * sp];
-      DFTBP_CHECK(ctx, l >= 0 && l <= skg::kLMax, "set_orbitals: angular momentum must be 0..3");
+      DFTBP_CHECK(ctx, l >= 0 && l <= 3, "set_orbitals: angular momentum must be 0..3");  // mAngRot_ = 3, sk.F90:28
       ctx->nOrbSpecies[sp] += 2 * l + 1;
       ctx->lMaxAll = std::max(ctx->lMaxAll, l);
     }
@@ -268,12 +266,8 @@ int dftbp_b200_set_orbitals(dftbp_b200_ctx *ctx, int nSpecies, int mShell, const
   }
   DFTBP_TRY(uploadNew(ctx, &ctx->dNOrbSpecies, ctx->nOrbSpecies.data(), nSpecies));
   DFTBP_TRY(uploadNew(ctx, &ctx->dOrbShell, orbShell.data(), orbShell.size()));
-  DFTBP_TRY(uploadNew(ctx, (skg::YDesc **)&ctx->dYDesc, skg::kYDesc, skg::kNY));
-
-  // Build the per-species-pair programs from the generic Gaunt tables.
-  std::vector<ADesc> aDesc;
-  std::vector<int> elemStart;
-  std::vector<DevTerm> terms;
+  // Per-species-pair programs: shell structure and integral count (the rotation itself is the
+  // generated code of sk_gaunt_code.cuh; the SK tables are attached by set_sk_table).
   ctx->progs.assign((size_t)nSpecies * nSpecies, SpPairProg());
   for (int sp2 = 0; sp2 < nSpecies; ++sp2)
     for (int sp1 = 0; sp1 < nSpecies; ++sp1) {
@@ -281,37 +275,16 @@ int dftbp_b200_set_orbitals(dftbp_b200_ctx *ctx, int nSpecies, int mShell, const
       std::memset(&pg, 0, sizeof(pg));
       pg.nOrb1 = ctx->nOrbSpecies[sp1];
       pg.nOrb2 = ctx->nOrbSpecies[sp2];
-      pg.aOff = (int)aDesc.size();
-      pg.elemOff = (int)elemStart.size();
-      std::vector<std::vector<DevTerm>> perElem((size_t)pg.nOrb1 * pg.nOrb2);
-      int ind = 0, iCol = 0, lmax1 = 0, lmax2 = 0;
+      int ind = 0, lmax1 = 0, lmax2 = 0;
+      // integrals in getFullTable order (dftbplus/parser.F90:4096-4127): atom-1 shells outer, min(l1,l2)+1 each
       for (int sh1 = 0; sh1 < nShell[sp1]; ++sh1) {
-        int l1 = angShell[sh1 + mShell * sp1];
+        const int l1 = angShell[sh1 + mShell * sp1];
         lmax1 = std::max(lmax1, l1);
-        int iRow = 0;
         for (int sh2 = 0; sh2 < nShell[sp2]; ++sh2) {
-          int l2 = angShell[sh2 + mShell * sp2], lmin = std::min(l1, l2);
+          const int l2 = angShell[sh2 + mShell * sp2];
           lmax2 = std::max(lmax2, l2);
-          for (int k = 0; k <= lmin; ++k) {
-            ADesc d;
-            for (int mu = 0; mu < 4; ++mu) d.t[mu] = mu <= lmin ? skg::kT[l1][l2][k][mu] : 0.0;
-            d.vBase = ind;
-            d.cnt = lmin + 1;
-            d.pad0 = d.pad1 = 0;
-            aDesc.push_back(d);
-          }
-          for (int a = 0; a < 2 * l1 + 1; ++a)
-            for (int b = 0; b < 2 * l2 + 1; ++b) {
-              int e = (iRow + b) + pg.nOrb2 * (iCol + a);
-              int t0 = skg::kElemStart[l1][l2][a * (2 * l2 + 1) + b];
-              int t1 = skg::kElemStart[l1][l2][a * (2 * l2 + 1) + b + 1];
-              for (int t = t0; t < t1; ++t)
-                perElem[e].push_back({skg::kTerms[t].coef, skg::kTerms[t].y, ind + skg::kTerms[t].k});
-            }
-          ind += lmin + 1;
-          iRow += 2 * l2 + 1;
+          ind += std::min(l1, l2) + 1;
         }
-        iCol += 2 * l1 + 1;
       }
       pg.nInteg = ind;
       DFTBP_CHECK(ctx, ind <= kMaxInteg, "set_orbitals: too many integrals per species pair");
@@ -329,18 +302,7 @@ int dftbp_b200_set_orbitals(dftbp_b200_ctx *ctx, int nSpecies, int mShell, const
       for (int sh = 0; sh < nShell[sp2]; ++sh)
         pg.shells2 |= (unsigned long long)angShell[sh + mShell * sp2] << (4 * sh);
       pg.nY = (lmax1 + lmax2 + 1) * (lmax1 + lmax2 + 1);
-      for (auto &v : perElem) {
-        elemStart.push_back((int)terms.size());
-        terms.insert(terms.end(), v.begin(), v.end());
-      }
-      elemStart.push_back((int)terms.size());
     }
-  DFTBP_TRY(uploadNew(ctx, &ctx->dADesc, aDesc.data(), aDesc.size()));
-  DFTBP_TRY(uploadNew(ctx, &ctx->dElemStart, elemStart.data(), elemStart.size()));
-  DFTBP_TRY(uploadNew(ctx, &ctx->dTerms, terms.data(), terms.size()));
-  cudaFree(ctx->dSelfE);
-  ctx->dSelfE = nullptr;
-  DFTBP_CUDA(ctx, cudaMalloc((void **)&ctx->dSelfE, sizeof(double) * ctx->mOrb * nSpecies));
   ctx->progsDirty = true;
   return 0;
 }

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Generate dftbplus_b200/csrc/sk_gaunt_tables.h -- the constant tables behind the CUDA
+"""Generate dftbplus_b200/csrc/sk_gaunt_code.cuh (and, with --tables, sk_gaunt_tables.h) -- the constants behind the CUDA
 Slater-Koster rotation.
 
 Design (B200-first, not a transcription of sk.F90's Maple polynomials): a two-centre block is
@@ -131,7 +131,7 @@ def self_check(tables):
     return worst
 
 
-def emit(tables):
+def emit(tables, write=False):
     lines = []
     ap = lines.append
     ap("// GENERATED by tools/gen_sk_gaunt.py -- do not edit.  See that script for the derivation.")
@@ -200,8 +200,9 @@ def emit(tables):
         ap(" },")
     ap("};")
     ap("}}  // namespace")
-    with open(OUT, "w") as fh:
-        fh.write("\n".join(lines) + "\n")
+    if write:
+        with open(OUT, "w") as fh:
+            fh.write("\n".join(lines) + "\n")
     return len(terms_all)
 
 
@@ -491,7 +492,10 @@ def emit_code(tables):
 if __name__ == "__main__":
     tb = build()
     err = self_check(tb)
-    n = emit(tb)
+    import sys
+    # the table form (term lists for a table-driven evaluator) is only written on request: the
+    # library uses the generated straight-line code
+    n = emit(tb, write="--tables" in sys.argv)
     nl = emit_code(tb)
     print("straight-line code: %d lines -> %s" % (nl, os.path.normpath(OUT_CODE)))
-    print("self-check max err %.2e; %d Gaunt terms -> %s" % (err, n, os.path.normpath(OUT)))
+    print("self-check max err %.2e; %d Gaunt terms%s" % (err, n, " -> " + os.path.normpath(OUT) if "--tables" in sys.argv else ""))
