@@ -44,7 +44,7 @@ enum {
   DFTBP_B200_EINVAL = 1,     /* bad argument / call order */
   DFTBP_B200_ENODEVICE = 2,  /* no CUDA device: there is no CPU fallback */
   DFTBP_B200_ECUDA = 3,      /* CUDA runtime / cuSOLVER error */
-  DFTBP_B200_ENOTIMPL = 4,   /* valid reference option that is not built yet */
+  DFTBP_B200_ENOTIMPL = 4,   /* valid reference option that is not built (none at present) */
   DFTBP_B200_ENOMEM = 5
 };
 

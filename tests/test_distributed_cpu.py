@@ -74,3 +74,57 @@ def test_two_rank_gloo_matches_single_rank(tmp_path):
     assert np.allclose(r["q"], oracle.mulliken_per_orbital(model, geo, s, rho), atol=1e-12)
     assert abs(r["q"].sum() - 8.0) < 1e-10                       # 2 Si atoms x 4 electrons
     assert np.allclose(r["d"], oracle.derivative_shift(model, geo, rho, 0.1 * rho), atol=1e-12)
+
+
+def _panel_worker(rank, world, port, out_dir):
+    """More ranks than (k,spin) pairs: the ranks of a group split ONE density matrix into column
+    panels (schedule.dm_panels); a rank keeps only its panel's columns, packs only its panel's atoms
+    (here: the oracle's pack on a matrix zeroed outside the panel), and the all-reduce assembles rho."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import scipy.linalg
+    from helpers import oracle, case, fermi_fillings, n_electrons
+    from dftbplus_b200 import schedule
+    w, sk, geo, model, selfegy = case("fec128")
+    h0, s = oracle.build_h0(model, geo, selfegy), oracle.build_s(model, geo)
+    eig, C = scipy.linalg.eigh(oracle.unpack_hs_real(geo, h0), oracle.unpack_hs_real(geo, s), lower=True)
+    f = fermi_fillings(eig, n_electrons(w, sk))
+    a0, a1, c0, c1 = schedule.dm_panels(geo["iAtomStart"], world)[rank]
+    dm = oracle.density_matrix(np.asfortranarray(C), f)
+    panel = np.zeros_like(dm)
+    panel[:, c0 - 1:c1] = dm[:, c0 - 1:c1]                      # what *_density_matrix_*_cols leaves valid
+    # pack only the blocks of atoms a0..a1 (packHS_real, sparse2dense.F90:1024-1096, restricted to the panel)
+    part = np.zeros(geo["sparseSize"])
+    for i in range(a0 - 1, a1):
+        for k in range(0, geo["nNeighbourSK"][i] + 1):
+            j = geo["img2CentCell"][geo["iNeighbour"][i, k] - 1] - 1
+            n1, n2 = geo["nOrbAtom"][i], geo["nOrbAtom"][j]
+            ii, jj = geo["iAtomStart"][i] - 1, geo["iAtomStart"][j] - 1
+            blk = panel[jj:jj + n2, ii:ii + n1].copy()
+            if i == j:                                            # on-site: symmetrised from the lower triangle
+                blk = np.tril(blk) + np.tril(blk, -1).T
+            part[geo["iPair"][i, k]:geo["iPair"][i, k] + n1 * n2] += blk.T.reshape(-1)
+    rho = schedule.assemble_chunks(torch.from_numpy(part)).numpy()
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "p.npz"), rho=rho)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_column_panels_over_two_gloo_ranks(tmp_path):
+    world, port = 2, 30100 + os.getpid() % 500
+    mp.spawn(_panel_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import scipy.linalg
+    from helpers import oracle, case, fermi_fillings, n_electrons
+    w, sk, geo, model, selfegy = case("fec128")
+    h0, s = oracle.build_h0(model, geo, selfegy), oracle.build_s(model, geo)
+    eig, C = scipy.linalg.eigh(oracle.unpack_hs_real(geo, h0), oracle.unpack_hs_real(geo, s), lower=True)
+    f = fermi_fillings(eig, n_electrons(w, sk))
+    ref = oracle.pack_hs_real(geo, np.zeros(geo["sparseSize"]), oracle.density_matrix(np.asfortranarray(C), f))
+    got = np.load(os.path.join(str(tmp_path), "p.npz"))["rho"]
+    assert np.allclose(got, ref, atol=1e-14)
