@@ -307,11 +307,13 @@ def main():
         step_device()
     t = hp.timer_read()
     tw = hpw.timer_read()
-    # keep the GPU busy until nvidia-smi has delivered samples from inside the window
+    # keep the GPU busy until nvidia-smi has delivered samples from inside the window.  LOCAL work
+    # only: the number of iterations differs from rank to rank, so no collective may be in here.
     for i in range(1500):
         if sum(1 for ts, _ in sampler.lines if ts >= sampler.t0) >= 4 and i >= 20:
             break
-        step_device()
+        hp.buildH0S(sk.selfegy, ham, over)
+        hpw.derivative_shift(dm, edm, shift=shift, deriv=deriv)
     stream.synchronize()
     clocks = sampler.stop()
     k1_ms = t["sparseH0S"][0] / max(1, t["sparseH0S"][1])
