@@ -536,7 +536,8 @@ def main():
                 "config": {"workload": a.workload, "nAtom": nAtom, "nOrb": nOrb, "pairs": pairs,
                            "sparseSize": ss, "n_spin": n_spin, "sk_tables": "synthetic .skf, 0.02 bohr x 500",
                            "l2": "flushed between timed steps (256 MB memset); H0+S output 2x%.0f MB" % (ss * 8 / 1e6),
-                           "parallelism": "K1 replicated, K5 atom-sharded + all-reduce, (k,spin) round-robin"},
+                           "parallelism": "K1 replicated, K5 atom-sharded + all-reduce, (k,spin) round-robin, "
+                                          "density-matrix column panels beyond"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "roofline_dm": roofline_dm, "kernels": kernels, "scc_step": scc, "cpu_baseline": cpu}
         print(json.dumps(line))

@@ -1,0 +1,42 @@
+#!/usr/bin/env python3
+"""Regression vectors of the oracle itself (NOT of the Fortran reference, which cannot be built in
+this image): outputs of oracle/ for two tiny workloads, so that a later change to the restatement
+cannot drift unnoticed.  Usage: python tests/golden/make_oracle_regression.py  (rewrites the .npz)"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, ".."))
+from helpers import oracle, case  # noqa: E402
+
+
+def vectors():
+    out = {}
+    for name in ("h2o", "si2"):
+        w, sk, geo, model, selfegy = case(name)
+        rng = np.random.default_rng(31)
+        h0, s = oracle.build_h0(model, geo, selfegy), oracle.build_s(model, geo)
+        rho = s * rng.normal(size=geo["sparseSize"])
+        erho = s * rng.normal(size=geo["sparseSize"])
+        sh = 0.1 * rng.normal(size=(1, geo["nAtom"], model.mOrb, model.mOrb))
+        sh = 0.5 * (sh + sh.transpose(0, 1, 3, 2))
+        out[name + "_h0"], out[name + "_s"] = h0, s
+        out[name + "_rho"], out[name + "_erho"], out[name + "_shift"] = rho, erho, sh
+        out[name + "_q"] = oracle.mulliken_per_orbital(model, geo, s, rho)
+        out[name + "_ham_scc"] = oracle.add_shift(model, geo, h0[None, :], s, sh)
+        out[name + "_deriv"] = oracle.derivative_shift(model, geo, rho, erho, shift=sh)
+        out[name + "_deriv_rich"] = oracle.derivative_shift(model, geo, rho, erho, diff_type=2)
+        if w["latvec"] is not None:
+            out[name + "_stress"] = oracle.stress(model, geo, rho, erho, abs(np.linalg.det(w["latvec"])), shift=sh)
+            kp = w["kpoints"][3]
+            out[name + "_hk"] = oracle.unpack_hs_cplx(geo, h0, kp)
+        w1, sk1, geo1, model1, selfegy1 = case(name, 1)
+        out[name + "_s_old_interp"] = oracle.build_s(model1, geo1)
+    return out
+
+
+if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "oracle_regression.npz"), **vectors())
+    print("wrote oracle_regression.npz")

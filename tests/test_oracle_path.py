@@ -238,3 +238,20 @@ def test_stress_is_strain_derivative_of_the_band_functional():
                               iter_indices=oracle.indices_with_workload(3, r, 1, geo["nAtom"], geo["nNeighbourSK"]))
                 for r in range(3))
     assert np.allclose(parts, st, atol=1e-13)
+
+
+def test_oracle_regression_vectors():
+    """The oracle against its own committed outputs (tests/golden/make_oracle_regression.py): a
+    change to the restatement that moves any of these by more than rounding must be deliberate."""
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_oracle_regression", os.path.join(here, "make_oracle_regression.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = np.load(os.path.join(here, "oracle_regression.npz"))
+    now = mod.vectors()
+    assert set(gold.files) == set(now)
+    for k in gold.files:
+        scale = max(1.0, float(np.abs(gold[k]).max()))
+        assert np.abs(now[k] - gold[k]).max() <= 1e-13 * scale, k
