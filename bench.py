@@ -164,6 +164,7 @@ def reference_arm(a, rank, world):
         return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from helpers import oracle, case
+    oracle.set_num_threads()          # all host cores (torchrun exports OMP_NUM_THREADS=1)
     w, sk, geo, model, selfegy = case(a.workload)
     rng = np.random.default_rng(1)
     s = oracle.build_s(model, geo)
@@ -511,6 +512,7 @@ def main():
     if rank == 0 and world == 1:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from helpers import oracle, case
+        oracle.set_num_threads()
         _, _, geo_o, model, selfegy = case(a.workload)
         dm_h, edm_h, sh_h = h_dm.copy(), h_edm.copy(), h_shift.copy()
 

@@ -1212,6 +1212,17 @@ void orc_stress(double *st, const orc_model *m, const double *DM, int nSpin, con
   for (k = 0; k < 9; ++k) st[k] = -0.5 * acc[k] / cellVol;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline must use the cores the reference's OpenMP
+ * build would use (OMP_NUM_THREADS = all host cores). */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

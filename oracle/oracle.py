@@ -59,6 +59,14 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def set_num_threads(n=None):
+    """OpenMP threads of the restatement; None = all host cores (the scheduler affinity mask)."""
+    if n is None:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
+
+
 def sk_eval(tab, dist, r, method=2):
     """SlakoEqGrid_getSKIntegrals for one table; tab is [nGrid, nInteg] order='F'."""
     tab = np.asfortranarray(tab, dtype=np.float64)
