@@ -188,7 +188,9 @@ def reference_arm(a, rank, world):
     line = {"impl": "reference", "metric": "sk_pairs_per_s_h0s_plus_force", "value": val, "unit": "pairs/s",
             "n_gpus": a.gpus, "steps": steps, "warmup": min(a.warmup, 1), "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": a.workload, "nAtom": geo["nAtom"], "pairs": pairs},
+            "data": "synthetic",
+            "config": {"workload": a.workload, "nAtom": int(geo["nAtom"]), "nOrb": int(geo["nOrb"]), "pairs": pairs,
+                       "sparseSize": int(geo["sparseSize"]), "n_spin": 2, "sk_tables": "synthetic .skf, 0.02 bohr x 500"},
             "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": oracle.num_threads(), "kind": "port",
                              "sample": "full workload, %d steps: buildH0 + buildS + derivative_shift(SCC, 2 spins)" % steps},
             "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
