@@ -80,6 +80,7 @@ struct Geometry {
   BlockDesc *descLoad = nullptr; // same for workLoad (== descAll on one rank)
   long long nWorkAll = 0, nWorkMine = 0, nWorkLoad = 0, nPairsMine = 0;
   bool hasDuplicates = false;    // two blocks of one atom fold onto the same dense block
+  bool coversAll = true;         // the blocks tile [0, sparseSize) completely (no zero fill needed)
   int firstAtomMine = 0, lastAtomMine = -1;  // 0-based inclusive atom chunk of workMine
 };
 

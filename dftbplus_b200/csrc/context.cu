@@ -393,8 +393,22 @@ int dftbp_b200_set_geometry(dftbp_b200_ctx *ctx, int nAtom, int nAllAtom, int mN
       DFTBP_CHECK(ctx, hVec[a2 - 1] >= 1 && hVec[a2 - 1] <= nCellVec, "set_geometry: iCellVec entry out of range");
     }
   }
+  // every block must lie inside the sparse arrays; the build kernels write each element exactly
+  // once and skip the zero fill only if the blocks cover the arrays completely (they do for
+  // getSparseDescriptor, sparse2dense.F90:3617-3662; an over-allocated caller gets a memset)
+  long long covered = 0;
+  for (int i = 0; i < nAtom; ++i)
+    for (int k = 0; k <= hN[i]; ++k) {
+      const long long f = k + (long long)ld * i;
+      const int n1 = hStart[i + 1] - hStart[i];
+      const int j = hImg[hNb[f] - 1] - 1, n2 = hStart[j + 1] - hStart[j];
+      DFTBP_CHECK(ctx, hPair[f] >= 0 && (long long)hPair[f] + (long long)n1 * n2 <= sparseSize,
+                  "set_geometry: iPair block exceeds sparseSize");
+      covered += (long long)n1 * n2;
+    }
   Geometry g;
   freeGeometry(ctx->geo);
+  g.coversAll = covered == sparseSize;
   g.nAtom = nAtom; g.nAllAtom = nAllAtom; g.mNeigh = mNeigh; g.nCellVec = nCellVec;
   g.sparseSize = sparseSize; g.nOrb = hStart[nAtom] - 1;
   DFTBP_TRY(uploadNew(ctx, &g.coords, coords, (size_t)3 * nAllAtom));

@@ -179,7 +179,9 @@ int launchBuild(dftbp_b200_ctx *ctx, const double *selfegy, double *ham, double 
   p.species = g.species;
   p.iPair = g.iPair; p.selfegy = nullptr; p.orbShell = ctx->dOrbShell; p.mShell = ctx->mShell;
   p.ham = nullptr; p.over = nullptr;
-  const bool partial = ctx->nRanks > 1;  // other ranks' segments stay zero (assembleChunks sums)
+  // zero fill only where the kernel does not write every element: other ranks' segments stay zero
+  // (assembleChunks sums), or the caller's arrays are larger than the blocks
+  const bool partial = ctx->nRanks > 1 || !g.coversAll;
   if (ham) {
     DFTBP_CHECK(ctx, selfegy != nullptr, "build_h0: selfegy is null");
     DFTBP_TRY(devIn(ctx, kSlotC, selfegy, (size_t)ctx->mShell * ctx->nSpecies, &p.selfegy));

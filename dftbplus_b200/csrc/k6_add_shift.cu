@@ -128,7 +128,7 @@ int addShiftImpl(dftbp_b200_ctx *ctx, double *ham, const double *over, const dou
   DFTBP_TRY(devIn(ctx, kSlotC, shift, nShift, &p.shift));
   if (isInputZero) {
     // several ranks: the blocks of the other ranks' atoms stay zero (assembleChunks sums the arrays)
-    if (ctx->nRanks > 1)
+    if (ctx->nRanks > 1 || !g.coversAll)
       DFTBP_CUDA(ctx, cudaMemsetAsync(p.ham, 0, sizeof(double) * (size_t)g.sparseSize * nSpin, ctx->stream));
     p.desc = g.descLoad; p.nWork = g.nWorkLoad;
   } else {
