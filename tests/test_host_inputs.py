@@ -69,3 +69,21 @@ def test_synthetic_overlap_is_positive_definite():
         S = oracle.unpack_hs_real(geo, oracle.build_s(model, geo))
         ev = np.linalg.eigvalsh(np.tril(S) + np.tril(S, -1).T)
         assert ev.min() > 1e-3, (name, ev.min())
+
+
+def test_generated_rotation_code_is_in_sync(tmp_path):
+    """dftbplus_b200/csrc/sk_gaunt_code.cuh is generated (tools/gen_sk_gaunt.py: Gaunt coefficients
+    by exact quadrature, self-checked against the rotation-matrix definition); the committed file
+    must be what the generator writes today."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_sk_gaunt", os.path.join(root, "tools", "gen_sk_gaunt.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    tables = gen.build()
+    assert gen.self_check(tables) < 1e-13
+    committed = open(gen.OUT_CODE).read()
+    gen.OUT_CODE = str(tmp_path / "sk_gaunt_code.cuh")
+    gen.emit_code(tables)
+    assert open(gen.OUT_CODE).read() == committed
