@@ -135,3 +135,74 @@ def test_old_interpolation_branches():
     tail = np.array([oracle.sk_eval(quad, dist, x, method=1)[1] for x in np.linspace(10.0, end, 15)])
     assert np.all(np.diff(tail) < 0) and tail[-1] >= 0
     assert abs(oracle.lib().orc_sk_cutoff(n, ctypes.c_double(dist), 1) - (n * dist + 0.3)) < 1e-14
+
+
+def test_interpolation_against_exact_rational_arithmetic():
+    """SlakoEqGrid_interNew_ / _interOld_ restated a third time in exact rational arithmetic
+    (fractions.Fraction): the unique interpolating polynomial through the reference's window
+    (rows iLast-nInter+1..iLast, iLast = max(min(nGrid, ind+nRight), nInter)), the free cubic spline
+    and the 5th-order tail as closed forms.  The oracle (floating-point Neville in the reference's
+    operation order) must agree to rounding -- independent of how either is coded."""
+    from fractions import Fraction as Fr
+    rng = np.random.default_rng(12)
+    n_grid, dist = 40, 0.25
+    tab = np.asfortranarray(rng.normal(size=(n_grid, 2)) * np.exp(-0.1 * np.arange(n_grid))[:, None])
+    D = Fr(dist)
+
+    def lagrange(rows, x, col):
+        xs = [Fr(j + 1) * D for j in rows]                      # row j (0-based) sits at (j+1)*dist
+        ys = [Fr(float(tab[j, col])) for j in rows]
+        tot = Fr(0)
+        for i, (xi, yi) in enumerate(zip(xs, ys)):
+            term = yi
+            for k, xk in enumerate(xs):
+                if k != i:
+                    term *= (x - xk) / (xi - xk)
+            tot += term
+        return tot
+
+    def poly5(y0, y0p, y0pp, xx, dx):
+        dx1, dx2 = y0p * dx, y0pp * dx * dx
+        dd, ee, ff = 10 * y0 - 4 * dx1 + dx2 / 2, -15 * y0 + 7 * dx1 - dx2, 6 * y0 - 3 * dx1 + dx2 / 2
+        xr = xx / dx
+        return ((ff * xr + ee) * xr + dd) * xr ** 3
+
+    def exact(r, col, method):
+        x = Fr(r)
+        ind = int(x // D)
+        if method == 2:
+            r_max = n_grid * D + 1
+            if x >= r_max:
+                return Fr(0)
+            if ind < n_grid:
+                i_last = max(min(n_grid, ind + 4), 8)
+                return lagrange(range(i_last - 8, i_last), x, col)
+            return None                                             # tail: FD derivatives, not a closed form
+        m_ind = n_grid + int(Fr(3, 10) // D)
+        y0, y1, y2 = (Fr(float(tab[n_grid - 3 + k, col])) for k in range(3))
+        y1p, y1pp = (y2 - y0) / (2 * D), (y2 + y0 - 2 * y1) / (D * D)
+        cub_d = (((y2 - y1) / D - y1p) / D - y1pp / 2) / D
+        if ind < n_grid - 1:
+            i_last = max(min(n_grid, ind + 2), 3)
+            return lagrange(range(i_last - 3, i_last), x, col)
+        if ind < n_grid:
+            xx = x - (n_grid - 1) * D
+            return ((cub_d * xx + y1pp / 2) * xx + y1p) * xx + y1
+        if ind < m_ind - 1:
+            yp = (3 * cub_d * D + y1pp) * D + y1p
+            ypp = 6 * cub_d * D + y1pp
+            return poly5(y2, yp, ypp, x - (m_ind - 1) * D, -(m_ind - n_grid - 1) * D)
+        return Fr(0)
+
+    checked = 0
+    for method in (1, 2):
+        for r in (0.26, 0.9, 1.13, 3.77, 8.01, 9.4, 9.74, 9.76, 9.99, 10.01, 10.2, 10.9, 11.01):
+            got = oracle.sk_eval(tab, dist, r, method=method)
+            for col in range(2):
+                ref = exact(r, col, method)
+                if ref is None:
+                    continue
+                scale = np.abs(tab[:, col]).max()
+                assert abs(got[col] - float(ref)) <= 5e-13 * scale, (method, r, col, got[col], float(ref))
+                checked += 1
+    assert checked > 40
