@@ -76,3 +76,21 @@ def test_dm_panels_cover_and_balance():
             cols = np.arange(c0 - 1, c1)
             area.append(float(np.sum(n - cols)))
         assert max(area) / (sum(area) / n_panel) < 1.05
+
+
+def test_reference_periodic_unit_tests():
+    """Known-answer tests of the reference's own unit suite, test/src/dftbp/unit/dftb/periodic.F90:
+    distributeAtoms (singleRank, multipleRanks: same arithmetic as getChunkRanges) and
+    neighbourdistance (two atoms at minNeighDist = 1e-2 bohr are accepted, at minNeighDist**2 the
+    neighbour list must raise "too close")."""
+    from dftbplus_b200 import schedule
+    for fn in (schedule.get_chunk_ranges, oracle.chunk_ranges):
+        assert tuple(fn(1, 0, 1, 42)) == (1, 42)              # singleRank
+        assert tuple(fn(2, 0, 1, 13)) == (1, 7)               # multipleRanks
+        assert tuple(fn(2, 1, 1, 13)) == (8, 13)
+    m = oracle.Model([[0]])
+    min_neigh_dist = 1.0e-2                                     # common/accuracy.F90:69
+    ok = oracle.neighbour_geometry(m, np.array([[0.0, 0, 0], [min_neigh_dist, 0, 0]]), np.array([1, 1]), cutoff=1.0)
+    assert ok["nNeighbourSK"].tolist() == [0, 1] or ok["nNeighbourSK"].sum() == 1
+    with pytest.raises(RuntimeError, match="too close"):
+        oracle.neighbour_geometry(m, np.array([[0.0, 0, 0], [min_neigh_dist ** 2, 0, 0]]), np.array([1, 1]), cutoff=1.0)
