@@ -26,6 +26,11 @@ SIGNATURES = {
     "dftbp_b200_get_sk_cutoff": (c_int, [c_void_p, P(c_double)]),
     "dftbp_b200_set_geometry": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    "dftbp_b200_cell_translations": (c_int, [c_void_p, c_void_p, c_double, c_int, P(c_int), c_void_p, c_void_p]),
+    "dftbp_b200_update_neighbour_list": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                                 c_double, c_double, P(c_int), P(c_int), P(c_int)]),
+    "dftbp_b200_get_neighbour_list": (c_int, [c_void_p] + [c_void_p] * 10),
+    "dftbp_b200_adopt_neighbour_list": (c_int, [c_void_p]),
     "dftbp_b200_update_coords": (c_int, [c_void_p, c_void_p]),
     "dftbp_b200_build_h0": (c_int, [c_void_p, c_void_p, c_void_p]),
     "dftbp_b200_build_s": (c_int, [c_void_p, c_void_p]),

@@ -104,7 +104,7 @@ class HotPath:
         self.set_stream(s if s != 0 else 1)      # 0 = legacy default stream -> cudaStreamLegacy
 
     TIMERS = ("sparseH0S", "sparseToDense", "denseToSparse", "densityMatrix", "mulliken", "forceCalc",
-              "diagonalization", "addShift")
+              "diagonalization", "addShift", "neighbourList")
 
     def timer_enable(self, on=True):
         self._ck(self._L.dftbp_b200_timer_enable(self._h, 1 if on else 0))
@@ -165,6 +165,61 @@ class HotPath:
             _ptr(_f64(g["cellVec"])), _ptr(_i32(g["nNeighbourSK"])), _ptr(_i32(g["iNeighbour"])),
             _ptr(_i32(g["iPair"])), _ptr(_i32(g["iAtomStart"])), g["sparseSize"]))
         self.geo = g
+
+    def getCellTranslations(self, latvec, cutoff):
+        """getCellTranslations (dftb/periodic.F90:227-263).  latvec[i] = i-th lattice vector (rows; the
+        memory is Fortran's latVec(:, i)).  Returns (cellVec[nCellVec, 3], rCellVec[nCellVec, 3])."""
+        latvec = np.ascontiguousarray(latvec, dtype=np.float64)
+        rec = np.ascontiguousarray(np.linalg.inv(latvec).T)   # recVec2p(:, i), initprogram.F90 (invLatVec^T)
+        n = ctypes.c_int()
+        rc = self._L.dftbp_b200_cell_translations(_ptr(latvec), _ptr(rec), float(cutoff), 0, ctypes.byref(n), None, None)
+        if rc != 0:
+            raise DftbB200Error(rc, "cell_translations: bad arguments")
+        cell, rcell = np.zeros((n.value, 3)), np.zeros((n.value, 3))
+        rc = self._L.dftbp_b200_cell_translations(_ptr(latvec), _ptr(rec), float(cutoff), n.value, ctypes.byref(n),
+                                                  _ptr(cell), _ptr(rcell))
+        if rc != 0:
+            raise DftbB200Error(rc, "cell_translations: bad arguments")
+        return cell, rcell
+
+    def updateNeighbourListAndSpecies(self, coord0, species0, cutoff, latvec=None, sk_cutoff=None, adopt=True,
+                                      fetch=True):
+        """updateNeighbourListAndSpecies + getNrOfNeighboursForAll + getSparseDescriptor on the device
+        (handleCoordinateChange, dftbplus/main.F90:2562-2578).  coord0[nAtom, 3] (host array or CUDA
+        tensor), species0[nAtom] 1-based, cutoff = list cutoff, sk_cutoff (default: cutoff).
+        adopt: make the result the context's geometry without a host round trip; fetch: return the
+        geometry dict of SURVEY.md section 8.0 (host copies), else only the sizes."""
+        sk_cutoff = cutoff if sk_cutoff is None else sk_cutoff
+        if latvec is None:
+            cell, rcell = np.zeros((1, 3)), np.zeros((1, 3))
+        else:
+            cell, rcell = self.getCellTranslations(latvec, cutoff)
+        coord0, species0 = _f64(coord0), _i32(species0)
+        nAtom = int(coord0.shape[0])
+        nAll, mN, sparse = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self._ck(self._L.dftbp_b200_update_neighbour_list(
+            self._h, nAtom, _ptr(coord0), _ptr(species0), cell.shape[0], _ptr(cell), _ptr(rcell), float(cutoff),
+            float(sk_cutoff), ctypes.byref(nAll), ctypes.byref(mN), ctypes.byref(sparse)))
+        g = dict(nAtom=nAtom, nAllAtom=nAll.value, mNeigh=mN.value, sparseSize=sparse.value, cellVec=cell,
+                 rCellVec=rcell, cutoff=cutoff, latvec=latvec)
+        if fetch:
+            g.update(coords=np.zeros((g["nAllAtom"], 3)), species=np.zeros(g["nAllAtom"], np.int32),
+                     img2CentCell=np.zeros(g["nAllAtom"], np.int32), iCellVec=np.zeros(g["nAllAtom"], np.int32),
+                     nNeighbour=np.zeros(nAtom, np.int32), iNeighbour=np.zeros((nAtom, g["mNeigh"] + 1), np.int32),
+                     neighDist2=np.zeros((nAtom, g["mNeigh"] + 1)), nNeighbourSK=np.zeros(nAtom, np.int32),
+                     iPair=np.zeros((nAtom, g["mNeigh"] + 1), np.int32), iAtomStart=np.zeros(nAtom + 1, np.int32))
+            self._ck(self._L.dftbp_b200_get_neighbour_list(
+                self._h, _ptr(g["coords"]), _ptr(g["species"]), _ptr(g["img2CentCell"]), _ptr(g["iCellVec"]),
+                _ptr(g["nNeighbour"]), _ptr(g["iNeighbour"]), _ptr(g["neighDist2"]), _ptr(g["nNeighbourSK"]),
+                _ptr(g["iPair"]), _ptr(g["iAtomStart"])))
+            g["nOrb"] = int(g["iAtomStart"][-1] - 1)
+            g["species0"] = np.asarray(g["species"][:nAtom])
+            g["nOrbAtom"] = np.diff(g["iAtomStart"]).astype(np.int32)
+        if adopt:
+            self._ck(self._L.dftbp_b200_adopt_neighbour_list(self._h))
+            if fetch:
+                self.geo = g
+        return g
 
     def update_coords(self, coords):
         self._ck(self._L.dftbp_b200_update_coords(self._h, _ptr(_f64(coords))))

@@ -106,6 +106,7 @@ enum TimerSlot {
   kTimerForceCalc,        // "Force calculation"              K5
   kTimerDiagonalization,  // "Diagonalisation"                cuSOLVER
   kTimerAddShift,         // addShift (part of "SCC")         K6
+  kTimerNeighbourList,    // updateNeighbourList + sparse descriptor          N2
   kTimerCount
 };
 
@@ -158,6 +159,7 @@ struct dftbp_b200_ctx {
   void *solverWork = nullptr;
   size_t solverWorkBytes = 0;
   int *dInfo = nullptr;
+  void *neighbourState = nullptr;  // device-built neighbour list (n2_neighbour_list.cu)
 };
 
 namespace dftbp_b200 {
@@ -332,5 +334,6 @@ int syncPrograms(dftbp_b200_ctx *ctx);
 int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out);
 void freeSortedPairs(dftbp_b200_ctx *ctx);
 void solverDestroy(dftbp_b200_ctx *ctx);
+void freeNeighbourList(dftbp_b200_ctx *ctx);
 
 }  // namespace dftbp_b200

@@ -82,6 +82,7 @@ int dftbp_b200_destroy(dftbp_b200_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   freeGeometry(ctx->geo);
   freeSortedPairs(ctx);
+  freeNeighbourList(ctx);
   for (void *p : ctx->tableAllocs) cudaFree(p);
   for (Staging &s : ctx->staging) cudaFree(s.ptr);
   cudaFree(ctx->dNOrbSpecies); cudaFree(ctx->dOrbShell); cudaFree(ctx->dProgs);

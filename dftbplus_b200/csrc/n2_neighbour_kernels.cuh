@@ -1,0 +1,342 @@
+// n2_neighbour_kernels.cuh -- neighbour list and sparse descriptor on the device.
+//
+// Reference: updateNeighbourList (dftb/periodic.F90:446-694), getNrOfNeighbours (:1026-1054, the
+// bisection search_asc_real_geq of math/binarysearch.F90:63-94), getSparseDescriptor
+// (dftb/sparse2dense.F90:3617-3662), index_heap_sort (math/sorting.F90:142-199).
+//
+// The reference scans all nCellVec * nAtom * nAtom / 2 (image, atom) combinations on one thread.
+// Here the central-cell atoms are binned into a uniform grid (bin edge >= cutoff) and one thread per
+// CANDIDATE IMAGE (cell vector ii, central atom iAtom1) looks only at the 27 bins around the image.
+// Everything the reference's loop order decides is reproduced from the candidate number
+// c = ii * nAtom + iAtom1, which is the position of the image in that loop:
+//   * image numbers  = exclusive prefix sum over c of "has a neighbour iAtom2 <= iAtom1 in range";
+//   * the unsorted neighbour rows are in ascending image number (the loops append them that way);
+//   * the error pair is the first (c, iAtom2) in loop order that is closer than minNeighDist.
+// The distance sort is the reference's heap sort with its tolerance comparison and its exact
+// control flow (the comparison is not transitive, so only the same algorithm on the same input
+// order gives the same order inside shells of equal distance, hence the same iPair layout).
+//
+// The kernels are grid-stride loops with atomics only (no shared memory, no warp collectives), so
+// that tests/host_eval/host_nl.cpp can run the very same source on the CPU, one emulated thread
+// after the other in a shuffled order, against the oracle (no GPU in the development container).
+#pragma once
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define NL_KERNEL __global__
+#define NL_DEV __device__ __forceinline__
+#define NL_TID ((long long)blockIdx.x * blockDim.x + threadIdx.x)
+#define NL_STRIDE ((long long)gridDim.x * blockDim.x)
+// IEEE operations that must not be contracted into FMAs (the reference is compiled without contraction
+// across statements; the oracle with -ffp-contract=off)
+#define NL_ADD(a, b) __dadd_rn((a), (b))
+#define NL_SUB(a, b) __dsub_rn((a), (b))
+#define NL_MUL(a, b) __dmul_rn((a), (b))
+#define NL_BITS(x) ((unsigned long long)__double_as_longlong(x))
+#define NL_FROM_BITS(u) __longlong_as_double((long long)(u))
+#else
+// host emulation: the includer defines NL_TID / NL_STRIDE and the atomics (tests/host_eval/host_nl.cpp)
+#define NL_KERNEL
+#define NL_DEV inline
+#define NL_ADD(a, b) ((a) + (b))
+#define NL_SUB(a, b) ((a) - (b))
+#define NL_MUL(a, b) ((a) * (b))
+#endif
+
+namespace dftbp_b200 {
+namespace nl {
+
+typedef unsigned long long ull;
+
+constexpr int kMaxBinsPerDim = 32;
+constexpr int kMaxBins = kMaxBinsPerDim * kMaxBinsPerDim * kMaxBinsPerDim;
+constexpr double kTolSameDist2 = 1.0e-5 * 1.0e-5;   // tolSameDist**2, common/accuracy.F90:68-72
+constexpr double kMinNeighDist2 = 1.0e-2 * 1.0e-2;  // minNeighDist**2, common/accuracy.F90:77-82
+constexpr double kBinSlack = 1.0001;                // bin edge >= kBinSlack * cutoff (rounding margin)
+
+// slots of the small int array the host reads back
+enum { kSizeAllAtom = 0, kSizeMaxNeigh = 1, kSizeSparse = 2, kSizeOrb = 3, kSizeCount = 4 };
+
+struct Grid {
+  double lo[3];    // lower corner of the bounding box of the central-cell atoms
+  double invW[3];  // 1 / bin edge
+  int nb[3];       // bins per dimension
+  int pad;
+};
+
+// order-preserving map double -> unsigned 64 bit (for atomicMin / atomicMax on coordinates)
+NL_DEV ull encodeOrdered(double x) {
+  const ull u = NL_BITS(x);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+NL_DEV double decodeOrdered(ull e) {
+  const ull u = (e >> 63) ? (e & 0x7fffffffffffffffull) : ~e;
+  return NL_FROM_BITS(u);
+}
+
+NL_DEV int binCoord(double x, double lo, double invW, int nb) {
+  const int i = (int)floor((x - lo) * invW);
+  return i < 0 ? 0 : (i >= nb ? nb - 1 : i);
+}
+
+NL_DEV int binOf(const double *__restrict__ p, const Grid &g) {
+  return binCoord(p[0], g.lo[0], g.invW[0], g.nb[0]) +
+         g.nb[0] * (binCoord(p[1], g.lo[1], g.invW[1], g.nb[1]) +
+                    g.nb[1] * binCoord(p[2], g.lo[2], g.invW[2], g.nb[2]));
+}
+
+// box[0..2] = min, box[3..5] = max of coord0 (encoded); box is preset to all-ones / zero
+NL_KERNEL void nl_bbox(int nAtom, const double *__restrict__ coord0, ull *__restrict__ box) {
+  for (long long a = NL_TID; a < nAtom; a += NL_STRIDE)
+    for (int k = 0; k < 3; ++k) {
+      const ull e = encodeOrdered(coord0[3 * a + k]);
+      atomicMin(box + k, e);
+      atomicMax(box + 3 + k, e);
+    }
+}
+
+// one thread: bins per dimension so that the bin edge is at least kBinSlack * cutoff
+NL_KERNEL void nl_grid_setup(const ull *__restrict__ box, double cutoff, Grid *__restrict__ grid) {
+  if (NL_TID != 0) return;
+  const double w0 = cutoff > 0.0 ? cutoff * kBinSlack : 1.0;
+  Grid g;
+  for (int k = 0; k < 3; ++k) {
+    const double lo = decodeOrdered(box[k]), ext = decodeOrdered(box[3 + k]) - lo;
+    int n = (int)floor(ext / w0);
+    n = n < 1 ? 1 : (n > kMaxBinsPerDim ? kMaxBinsPerDim : n);
+    const double w = ext / n > w0 ? ext / n : w0;
+    g.lo[k] = lo;
+    g.invW[k] = 1.0 / w;
+    g.nb[k] = n;
+  }
+  g.pad = 0;
+  *grid = g;
+}
+
+NL_KERNEL void nl_bin_count(int nAtom, const double *__restrict__ coord0, const Grid *__restrict__ grid,
+                            int *__restrict__ binCount) {
+  const Grid g = *grid;
+  for (long long a = NL_TID; a < nAtom; a += NL_STRIDE) atomicAdd(binCount + binOf(coord0 + 3 * a, g), 1);
+}
+
+// atoms of a bin stored contiguously with their coordinates (order inside a bin: arbitrary)
+NL_KERNEL void nl_bin_fill(int nAtom, const double *__restrict__ coord0, const Grid *__restrict__ grid,
+                           const int *__restrict__ binStart, int *__restrict__ binCursor,
+                           int *__restrict__ binAtom, double *__restrict__ binXyz) {
+  const Grid g = *grid;
+  for (long long a = NL_TID; a < nAtom; a += NL_STRIDE) {
+    const int b = binOf(coord0 + 3 * a, g);
+    const int pos = binStart[b] + atomicAdd(binCursor + b, 1);
+    binAtom[pos] = (int)a;
+    binXyz[3 * pos] = coord0[3 * a];
+    binXyz[3 * pos + 1] = coord0[3 * a + 1];
+    binXyz[3 * pos + 2] = coord0[3 * a + 2];
+  }
+}
+
+// Image of atom a1 (0-based) in cell ii (0-based): rr = coord0(:,a1) + rCellVec(:,ii)
+// (periodic.F90:579), and every central atom a2 <= a1 with dist2 = sum((coord0(:,a2) - rr)**2) <=
+// cutoff2 (:597-600) is handed to visit(a2, dist2).  Returns false if the image is too far from the
+// bounding box to have any.
+template <class F>
+NL_DEV bool visitNeighbours(int ii, int a1, const double *__restrict__ coord0,
+                            const double *__restrict__ rCellVec, const Grid &g,
+                            const int *__restrict__ binStart, const int *__restrict__ binAtom,
+                            const double *__restrict__ binXyz, double cutoff2, double *rr, F &&visit) {
+  int ip[3];
+  for (int k = 0; k < 3; ++k) {
+    rr[k] = NL_ADD(coord0[3 * a1 + k], rCellVec[3 * ii + k]);
+    const double f = (rr[k] - g.lo[k]) * g.invW[k];
+    if (!(f >= -1.0 && f < (double)(g.nb[k] + 1))) return false;  // farther than one bin edge (>= cutoff) from the box
+    ip[k] = (int)floor(f);
+  }
+  const int z0 = ip[2] - 1 < 0 ? 0 : ip[2] - 1, z1 = ip[2] + 1 > g.nb[2] - 1 ? g.nb[2] - 1 : ip[2] + 1;
+  const int y0 = ip[1] - 1 < 0 ? 0 : ip[1] - 1, y1 = ip[1] + 1 > g.nb[1] - 1 ? g.nb[1] - 1 : ip[1] + 1;
+  const int x0 = ip[0] - 1 < 0 ? 0 : ip[0] - 1, x1 = ip[0] + 1 > g.nb[0] - 1 ? g.nb[0] - 1 : ip[0] + 1;
+  for (int iz = z0; iz <= z1; ++iz)
+    for (int iy = y0; iy <= y1; ++iy) {
+      // bins x0..x1 of one (iy, iz) row are contiguous
+      const int row = g.nb[0] * (iy + g.nb[1] * iz);
+      const int pEnd = binStart[row + x1 + 1];
+      for (int p = binStart[row + x0]; p < pEnd; ++p) {
+        const int a2 = binAtom[p];
+        if (a2 > a1) continue;  // non-symmetric list: iAtom2 = 1 .. iAtom1 (:580-584)
+        const double d0 = NL_SUB(binXyz[3 * p], rr[0]);
+        const double d1 = NL_SUB(binXyz[3 * p + 1], rr[1]);
+        const double d2 = NL_SUB(binXyz[3 * p + 2], rr[2]);
+        const double dist2 = NL_ADD(NL_ADD(NL_MUL(d0, d0), NL_MUL(d1, d1)), NL_MUL(d2, d2));
+        if (dist2 > cutoff2) continue;
+        visit(a2, dist2);
+      }
+    }
+  return true;
+}
+
+// pass 1: which candidate images interact at all (flag), neighbours per atom, first too-close pair
+NL_KERNEL void nl_count(long long nCand, int nAtom, const double *__restrict__ coord0,
+                        const double *__restrict__ rCellVec, const Grid *__restrict__ grid,
+                        const int *__restrict__ binStart, const int *__restrict__ binAtom,
+                        const double *__restrict__ binXyz, double cutoff2, int *__restrict__ flag,
+                        int *__restrict__ nNeighbour, ull *__restrict__ firstError) {
+  const Grid g = *grid;
+  for (long long c = NL_TID; c < nCand; c += NL_STRIDE) {
+    const int ii = (int)(c / nAtom), a1 = (int)(c - (long long)ii * nAtom);
+    double rr[3];
+    int found = 0;
+    visitNeighbours(ii, a1, coord0, rCellVec, g, binStart, binAtom, binXyz, cutoff2, rr,
+                    [&](int a2, double dist2) {
+                      found = 1;  // the image is appended before the proximity check (:604-614)
+                      if (dist2 < kMinNeighDist2) {
+                        if (!(ii == 0 && a1 == a2)) atomicMin(firstError, (ull)c * (ull)nAtom + (ull)a2);
+                        return;  // the atom itself in the central cell is not its own neighbour (:619-622)
+                      }
+                      atomicAdd(nNeighbour + a2, 1);
+                    });
+    flag[c] = found;
+  }
+}
+
+// sizes[kSizeAllAtom] = number of flagged candidates, sizes[kSizeMaxNeigh] = max nNeighbour
+NL_KERNEL void nl_sizes(long long nCand, int nAtom, const int *__restrict__ imgIndex,
+                        const int *__restrict__ nNeighbour, int *__restrict__ sizes) {
+  for (long long a = NL_TID; a < nAtom; a += NL_STRIDE) {
+    atomicMax(sizes + kSizeMaxNeigh, nNeighbour[a]);
+    if (a == 0) sizes[kSizeAllAtom] = imgIndex[nCand];
+  }
+}
+
+// pass 2: image arrays (coord, img2CentCell, iCellVec, species; periodic.F90:610-613, :437) and the
+// unsorted neighbour rows (slots in arrival order; nl_sort puts them into the reference's order)
+NL_KERNEL void nl_fill(long long nCand, int nAtom, int ld, const double *__restrict__ coord0,
+                       const int *__restrict__ species0, const double *__restrict__ rCellVec,
+                       const Grid *__restrict__ grid, const int *__restrict__ binStart,
+                       const int *__restrict__ binAtom, const double *__restrict__ binXyz, double cutoff2,
+                       const int *__restrict__ flag, const int *__restrict__ imgIndex,
+                       double *__restrict__ coords, int *__restrict__ species, int *__restrict__ img2CentCell,
+                       int *__restrict__ iCellVec, int *__restrict__ cursor, int *__restrict__ iNeighbour,
+                       double *__restrict__ neighDist2) {
+  const Grid g = *grid;
+  for (long long c = NL_TID; c < nCand; c += NL_STRIDE) {
+    if (!flag[c]) continue;
+    const int ii = (int)(c / nAtom), a1 = (int)(c - (long long)ii * nAtom);
+    const int img = imgIndex[c];
+    double rr[3];
+    visitNeighbours(ii, a1, coord0, rCellVec, g, binStart, binAtom, binXyz, cutoff2, rr,
+                    [&](int a2, double dist2) {
+                      if (dist2 < kMinNeighDist2) return;
+                      const int slot = atomicAdd(cursor + a2, 1) + 1;
+                      iNeighbour[slot + (long long)ld * a2] = img + 1;
+                      neighDist2[slot + (long long)ld * a2] = dist2;
+                    });
+    coords[3 * (long long)img] = rr[0];
+    coords[3 * (long long)img + 1] = rr[1];
+    coords[3 * (long long)img + 2] = rr[2];
+    img2CentCell[img] = a1 + 1;
+    iCellVec[img] = ii + 1;
+    species[img] = species0[a1];
+  }
+}
+
+// index_heap_sort (math/sorting.F90:142-199) acting on the records (key[i], val[i]), i = 1..n,
+// instead of on an index vector: the algorithm only compares values and moves indices, so moving
+// the records gives the same order.  less(kA, vA, kB, vB) is the reference's comparison.
+template <class Less>
+NL_DEV void heapSortRecords(int n, int *__restrict__ key, double *__restrict__ val, Less less) {
+  if (n <= 1) return;
+  int il = n / 2 + 1, ir = n;
+  for (;;) {
+    int kTmp;
+    double vTmp;
+    if (il > 1) {
+      il -= 1;
+      kTmp = key[il];
+      vTmp = val[il];
+    } else {
+      kTmp = key[ir];
+      vTmp = val[ir];
+      key[ir] = key[1];
+      val[ir] = val[1];
+      ir -= 1;
+      if (ir < 1) {
+        key[1] = kTmp;
+        val[1] = vTmp;
+        return;
+      }
+    }
+    int ii = il, ij = 2 * il;
+    while (ij <= ir) {
+      if (ij < ir && less(key[ij], val[ij], key[ij + 1], val[ij + 1])) ij += 1;
+      if (less(kTmp, vTmp, key[ij], val[ij])) {
+        key[ii] = key[ij];
+        val[ii] = val[ij];
+        ii = ij;
+        ij = 2 * ij;
+      } else {
+        ij = ir + 1;
+      }
+    }
+    key[ii] = kTmp;
+    val[ii] = vTmp;
+  }
+}
+
+// One thread per atom: rows into the reference's order, row 0 = the atom itself (fillNeighbourArrays),
+// nNeighbourSK for the SK cutoff, and the number of sparse elements / orbitals of the atom.
+NL_KERNEL void nl_sort(int nAtom, int ld, double skCutoff2, const int *__restrict__ nNeighbour,
+                       const int *__restrict__ species0, const int *__restrict__ nOrbSpecies,
+                       const int *__restrict__ img2CentCell, int *__restrict__ iNeighbour,
+                       double *__restrict__ neighDist2, int *__restrict__ nNeighbourSK,
+                       int *__restrict__ atomSize, int *__restrict__ orbCount) {
+  for (long long a = NL_TID; a < nAtom; a += NL_STRIDE) {
+    int *in = iNeighbour + (long long)ld * a;      // in[1..n]
+    double *dn = neighDist2 + (long long)ld * a;
+    const int n = nNeighbour[a];
+    // (1) the order the reference's loops append in: ascending image number (plain comparison)
+    heapSortRecords(n, in, dn, [](int kA, double, int kB, double) { return kA < kB; });
+    // (2) index_heap_sort(indx, neighDist2(1:nn1, iAtom1), tolSameDist2), periodic.F90:677-680
+    heapSortRecords(n, in, dn,
+                    [](int, double vA, int, double vB) { return vA < NL_SUB(vB, kTolSameDist2); });
+    in[0] = (int)a + 1;
+    dn[0] = 0.0;
+    // getNrOfNeighbours: search_asc_real_geq(nNeighbour, neighDist2(1:n), cutoff**2, tolSameDist2)
+    int jlower = 0, jupper = n;
+    while (jlower < jupper) {
+      const int jcurr = jlower + (jupper - jlower + 1) / 2;
+      if (NL_SUB(skCutoff2, dn[jcurr]) >= -kTolSameDist2) jlower = jcurr;
+      else jupper = jcurr - 1;
+    }
+    nNeighbourSK[a] = jlower;
+    const int nOrb1 = nOrbSpecies[species0[a] - 1];
+    int sum = 0;
+    for (int k = 0; k <= jlower; ++k) sum += nOrb1 * nOrbSpecies[species0[img2CentCell[in[k] - 1] - 1] - 1];
+    atomSize[a] = sum;
+    orbCount[a] = nOrb1;
+  }
+}
+
+// getSparseDescriptor (sparse2dense.F90:3651-3660) from the per-atom offsets, and iAtomStart
+NL_KERNEL void nl_ipair(int nAtom, int ld, const int *__restrict__ nNeighbourSK,
+                        const int *__restrict__ species0, const int *__restrict__ nOrbSpecies,
+                        const int *__restrict__ img2CentCell, const int *__restrict__ iNeighbour,
+                        const int *__restrict__ atomOffset, const int *__restrict__ orbOffset,
+                        int *__restrict__ iPair, int *__restrict__ iAtomStart, int *__restrict__ sizes) {
+  for (long long a = NL_TID; a < nAtom; a += NL_STRIDE) {
+    const int *in = iNeighbour + (long long)ld * a;
+    int *ip = iPair + (long long)ld * a;
+    const int nOrb1 = nOrbSpecies[species0[a] - 1];
+    int ind = atomOffset[a];
+    for (int k = 0; k <= nNeighbourSK[a]; ++k) {
+      ip[k] = ind;
+      ind += nOrb1 * nOrbSpecies[species0[img2CentCell[in[k] - 1] - 1] - 1];
+    }
+    iAtomStart[a] = orbOffset[a] + 1;
+    if (a == nAtom - 1) {
+      iAtomStart[nAtom] = orbOffset[nAtom] + 1;
+      sizes[kSizeSparse] = atomOffset[nAtom];
+      sizes[kSizeOrb] = orbOffset[nAtom];
+    }
+  }
+}
+
+}  // namespace nl
+}  // namespace dftbp_b200

@@ -45,7 +45,8 @@ enum {
   DFTBP_B200_ENODEVICE = 2,  /* no CUDA device: there is no CPU fallback */
   DFTBP_B200_ECUDA = 3,      /* CUDA runtime / cuSOLVER error */
   DFTBP_B200_ENOTIMPL = 4,   /* valid reference option that is not built (none at present) */
-  DFTBP_B200_ENOMEM = 5
+  DFTBP_B200_ENOMEM = 5,
+  DFTBP_B200_EGEOMETRY = 6   /* "Atoms i and j too close together" (dftb/periodic.F90:645-648) */
 };
 
 /* skIntMethod, dftb/slakoeqgrid.F90:62-65 */
@@ -104,6 +105,43 @@ int dftbp_b200_set_geometry(dftbp_b200_ctx *ctx, int nAtom, int nAllAtom, int mN
                             const int *iCellVec, int nCellVec, const double *cellVec,
                             const int *nNeighbourSK, const int *iNeighbour, const int *iPair,
                             const int *iAtomStart, int sparseSize);
+
+/* ---- N2: neighbour list and sparse descriptor on the device -------------------- */
+
+/* getCellTranslations, dftb/periodic.F90:227-263 (host side; runs when the lattice changes):
+ * the zero vector first, then every other point of the parallelepiped +-(floor(cutoff*|b_i|)+1),
+ * third index fastest (type/latpointiter.F90:214-274).  latVec(3,3), recVec2p(3,3) column-major
+ * (reciprocal vectors in units of 2 pi).  cellVec / rCellVec (3, maxCellVec) may be NULL to query
+ * *nCellVec. */
+int dftbp_b200_cell_translations(const double *latVec, const double *recVec2p, double cutoff,
+                                 int maxCellVec, int *nCellVec, double *cellVec, double *rCellVec);
+
+/* updateNeighbourListAndSpecies (dftb/periodic.F90:380-440, 446-694; non-symmetric list, no helical
+ * boundary conditions) + getNrOfNeighboursForAll(skCutoff) (:996-1054) + getSparseDescriptor
+ * (dftb/sparse2dense.F90:3617-3662), as called by handleCoordinateChange
+ * (dftbplus/main.F90:2562-2578), with a cell list on the device instead of the reference's
+ * O(nCellVec nAtom^2) scan.  coord0(3, nAtom) (already folded into the cell by the caller),
+ * species0(nAtom), cellVec / rCellVec(3, nCellVec) with the zero vector first (nCellVec = 1 and
+ * zeros for a cluster), cutoff = list cutoff (mCutOff), skCutoff <= cutoff.  Image numbering, row
+ * order (including the order inside shells of equal distance, which fixes the iPair layout) and
+ * all values are the reference's.  The result stays on the device; the sizes the caller needs to
+ * allocate its copies come back in nAllAtom, mNeigh (= maxval(nNeighbour)) and sparseSize.
+ * Atoms closer than minNeighDist: DFTBP_B200_EGEOMETRY, message as the reference's. */
+int dftbp_b200_update_neighbour_list(dftbp_b200_ctx *ctx, int nAtom, const double *coord0,
+                                     const int *species0, int nCellVec, const double *cellVec,
+                                     const double *rCellVec, double cutoff, double skCutoff,
+                                     int *nAllAtom, int *mNeigh, int *sparseSize);
+
+/* Copies of the arrays of the last update (any pointer may be NULL; host or device memory):
+ * coords(3, nAllAtom), species / img2CentCell / iCellVec(nAllAtom), nNeighbour(nAtom),
+ * iNeighbour / neighDist2 / iPair(0:mNeigh, nAtom), nNeighbourSK(nAtom), iAtomStart(nAtom+1). */
+int dftbp_b200_get_neighbour_list(dftbp_b200_ctx *ctx, double *coords, int *species, int *img2CentCell,
+                                  int *iCellVec, int *nNeighbour, int *iNeighbour, double *neighDist2,
+                                  int *nNeighbourSK, int *iPair, int *iAtomStart);
+
+/* Make the list of the last update the context's geometry (what dftbp_b200_set_geometry does
+ * with caller arrays), without the round trip through the host. */
+int dftbp_b200_adopt_neighbour_list(dftbp_b200_ctx *ctx);
 
 /* Coordinates only (same neighbour map): geometry steps that keep the list, and finite
  * differences.  coords(3, nAllAtom). */
@@ -233,6 +271,7 @@ enum {
   DFTBP_B200_TIMER_FORCE_CALC,         /* "Force calculation"       */
   DFTBP_B200_TIMER_DIAGONALIZATION,    /* "Diagonalisation"         */
   DFTBP_B200_TIMER_ADD_SHIFT,          /* addShift (inside "SCC")   */
+  DFTBP_B200_TIMER_NEIGHBOUR_LIST,     /* updateNeighbourList + getSparseDescriptor */
   DFTBP_B200_TIMER_COUNT
 };
 int dftbp_b200_timer_enable(dftbp_b200_ctx *ctx, int on);   /* also resets the accumulators */

@@ -768,20 +768,23 @@ int orc_update_neighbour_list(int nAtom, const double *coord0, double cutoff, in
   return 0;
 }
 
-/* getNrOfNeighbours, periodic.F90:1026-1054 -> search_asc_real_geq semantics: the number of
- * leading entries of the ascending list that are <= cutoff^2 within tolSameDist2. */
+/* getNrOfNeighbours, periodic.F90:1026-1054 -> search_asc_real_geq (math/binarysearch.F90:63-94):
+ * bisection for the last entry of neighDist2(1:nNeighbour) with cutoff^2 - entry >= -tolSameDist2.
+ * (The bisection is kept literally: the list is only ascending within tolSameDist2.) */
 void orc_nr_of_neighbours(int nAtom, const int *nNeighbour, const double *neighDist2, int maxNeigh,
                           double cutoff, int *nNeighbourSK)
 {
   const int ld = maxNeigh + 1;
   const double c2 = cutoff * cutoff;
-  int iAtom, k;
+  int iAtom;
   for (iAtom = 0; iAtom < nAtom; ++iAtom) {
-    int n = 0;
-    for (k = 1; k <= nNeighbour[iAtom]; ++k) {
-      if (neighDist2[k + ld * iAtom] <= c2 + tolSameDist2) n = k; else break;
+    const double *xx = neighDist2 + ld * iAtom; /* xx[j] = neighDist2(j, iAtom), j = 1.. */
+    int jlower = 0, jupper = nNeighbour[iAtom], jcurr;
+    while (jlower < jupper) {
+      jcurr = jlower + (jupper - jlower + 1) / 2;
+      if (c2 - xx[jcurr] >= -tolSameDist2) jlower = jcurr; else jupper = jcurr - 1;
     }
-    nNeighbourSK[iAtom] = n;
+    nNeighbourSK[iAtom] = jlower;
   }
 }
 

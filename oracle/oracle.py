@@ -206,6 +206,53 @@ def neighbour_geometry(model, coord0, species0, latvec=None, cutoff=None):
                 neighDist2=np.ascontiguousarray(d2[:, :mNeigh + 1]))
 
 
+def neighbour_list_full(n_orb_species, coord0, species0, rcell, cutoff, sk_cutoff):
+    """updateNeighbourList(cutoff) + getNrOfNeighboursForAll(sk_cutoff) + getSparseDescriptor with
+    the arrays exactly as the reference holds them (rows of iNeighbour / neighDist2 / iPair are
+    0:mNeigh with mNeigh = maxval(nNeighbour) of the LIST cutoff).  rcell[nCellVec,3], zero vector
+    first.  Raises RuntimeError("Atoms i and j too close together") like the reference."""
+    L = lib()
+    coord0 = np.ascontiguousarray(coord0, dtype=np.float64)
+    species0 = np.ascontiguousarray(species0, dtype=np.int32)
+    rcell = np.ascontiguousarray(rcell, dtype=np.float64)
+    n_orb_species = np.asarray(n_orb_species, dtype=np.int32)
+    nAtom = coord0.shape[0]
+    maxAll, maxNeigh = max(4 * nAtom, 64), 64
+    while True:
+        coord = np.zeros((maxAll, 3))
+        img = np.zeros(maxAll, dtype=np.int32)
+        icv = np.zeros(maxAll, dtype=np.int32)
+        nN = np.zeros(nAtom, dtype=np.int32)
+        iN = np.zeros((nAtom, maxNeigh + 1), dtype=np.int32)
+        d2 = np.zeros((nAtom, maxNeigh + 1))
+        nAll, mN = ctypes.c_int(), ctypes.c_int()
+        perr = np.zeros(2, dtype=np.int32)
+        rc = L.orc_update_neighbour_list(nAtom, _d(coord0), ctypes.c_double(cutoff), rcell.shape[0],
+                                         _d(rcell), maxAll, maxNeigh, _d(coord), _i(img), _i(icv),
+                                         _i(nN), _i(iN), _d(d2), ctypes.byref(nAll),
+                                         ctypes.byref(mN), _i(perr))
+        if rc == -1:
+            raise RuntimeError("Atoms %d and %d too close together" % (perr[0], perr[1]))
+        if rc == 0 and maxNeigh == mN.value:
+            break
+        maxAll = max(maxAll, nAll.value)
+        maxNeigh = mN.value
+    nAll, mN = nAll.value, mN.value
+    nSK = np.zeros(nAtom, dtype=np.int32)
+    L.orc_nr_of_neighbours(nAtom, _i(nN), _d(d2), mN, ctypes.c_double(sk_cutoff), _i(nSK))
+    img2CentCell = np.ascontiguousarray(img[:nAll])
+    nOrbAtom = np.ascontiguousarray(n_orb_species[species0 - 1])
+    iPair = np.zeros((nAtom, mN + 1), dtype=np.int32)
+    sparseSize = L.orc_sparse_descriptor(nAtom, _i(iN), mN, _i(nSK), _i(img2CentCell), _i(nOrbAtom), _i(iPair))
+    iAtomStart = np.ones(nAtom + 1, dtype=np.int32)
+    iAtomStart[1:] = 1 + np.cumsum(nOrbAtom)
+    return dict(nAtom=nAtom, nAllAtom=nAll, mNeigh=mN, coords=np.ascontiguousarray(coord[:nAll]),
+                species=np.ascontiguousarray(species0[img2CentCell - 1]), img2CentCell=img2CentCell,
+                iCellVec=np.ascontiguousarray(icv[:nAll]), nNeighbour=nN, nNeighbourSK=nSK, iNeighbour=iN,
+                neighDist2=d2, iPair=iPair, iAtomStart=iAtomStart, sparseSize=int(sparseSize),
+                nOrb=int(iAtomStart[-1] - 1))
+
+
 def _build(model, geo, selfegy, rank, nranks):
     out = np.zeros(geo["sparseSize"])
     se = None

@@ -1,0 +1,118 @@
+// host_nl.cpp -- runs the PRODUCT's neighbour-list kernels and launch sequence
+// (dftbplus_b200/csrc/n2_neighbour_kernels.cuh + n2_neighbour_driver.h) on the CPU, so that the CPU
+// test suite can check them against the oracle without a GPU.  Test infrastructure.
+//
+// The kernels are grid-stride loops that communicate through atomics only, so executing the
+// emulated threads one after the other is one of the interleavings the GPU may produce; the
+// launcher runs them in a shuffled order (seeded) to show that the results do not depend on it.
+// What this cannot cover: the CUDA backend itself (cub::DeviceScan, copies, launch shapes) -- the
+// `-m gpu` parity tests do.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <random>
+#include <vector>
+
+typedef unsigned long long ull_t;
+
+static long long g_tid = 0, g_stride = 1;
+#define NL_TID g_tid
+#define NL_STRIDE g_stride
+
+inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }
+inline int atomicMax(int *p, int v) { int o = *p; if (v > o) *p = v; return o; }
+inline ull_t atomicMin(ull_t *p, ull_t v) { ull_t o = *p; if (v < o) *p = v; return o; }
+inline ull_t atomicMax(ull_t *p, ull_t v) { ull_t o = *p; if (v > o) *p = v; return o; }
+inline ull_t nlBits(double x) { ull_t u; std::memcpy(&u, &x, 8); return u; }
+inline double nlFromBits(ull_t u) { double x; std::memcpy(&x, &u, 8); return x; }
+#define NL_BITS(x) nlBits(x)
+#define NL_FROM_BITS(u) nlFromBits(u)
+
+#include "../../dftbplus_b200/csrc/n2_neighbour_driver.h"
+
+using namespace dftbp_b200;
+
+namespace {
+
+struct HostBackend {
+  int nThreads;
+  std::mt19937 rng;
+  long long launches = 0;
+
+  int alloc(void **p, size_t bytes) {
+    *p = std::malloc(bytes ? bytes : 1);
+    if (!*p) return 5;
+    std::memset(*p, 0xA5, bytes);  // poison: nothing may rely on fresh memory being zero
+    return 0;
+  }
+  void release(void *p) { std::free(p); }
+  int upload(void *dst, const void *src, size_t bytes) { std::memcpy(dst, src, bytes); return 0; }
+  int download(void *dst, const void *src, size_t bytes) { std::memcpy(dst, src, bytes); return 0; }
+  int fill(void *p, int v, size_t bytes) { std::memset(p, v, bytes); return 0; }
+  int scan(const int *in, int *out, long long n) {
+    long long s = 0;
+    for (long long i = 0; i < n; ++i) { out[i] = (int)s; s += in[i]; }
+    return 0;
+  }
+  template <class... P, class... A>
+  int launch(void (*kernel)(P...), long long nItems, A... args) {
+    if (nItems <= 0) return 0;
+    std::vector<int> order(nThreads);
+    std::iota(order.begin(), order.end(), 0);
+    std::shuffle(order.begin(), order.end(), rng);
+    g_stride = nThreads;
+    for (int t : order) {
+      g_tid = t;
+      kernel(args...);
+    }
+    ++launches;
+    return 0;
+  }
+};
+
+nl::NeighbourList g_list;
+int *g_nOrbSpecies = nullptr;
+
+}  // namespace
+
+extern "C" {
+
+// out[0..7] = nAllAtom, mNeigh, sparseSize, nOrb, errAtom1, errAtom2, valid, launches
+int host_nl_update(int nAtom, const double *coord0, const int *species0, int nSpecies, const int *nOrbSpecies,
+                   int nCellVec, const double *cellVec, const double *rCellVec, double cutoff, double skCutoff,
+                   int nThreads, unsigned seed, int *out) {
+  HostBackend be{nThreads, std::mt19937(seed)};
+  std::free(g_nOrbSpecies);
+  g_nOrbSpecies = (int *)std::malloc(sizeof(int) * nSpecies);
+  std::memcpy(g_nOrbSpecies, nOrbSpecies, sizeof(int) * nSpecies);
+  const int rc = nl::updateNeighbourList(be, g_list, nAtom, coord0, species0, g_nOrbSpecies, nCellVec, cellVec,
+                                         rCellVec, cutoff, skCutoff);
+  out[0] = g_list.nAllAtom; out[1] = g_list.mNeigh; out[2] = g_list.sparseSize; out[3] = g_list.nOrb;
+  out[4] = g_list.errAtom1; out[5] = g_list.errAtom2; out[6] = g_list.valid ? 1 : 0; out[7] = (int)be.launches;
+  return rc;
+}
+
+void host_nl_get(double *coords, int *species, int *img2CentCell, int *iCellVec, int *nNeighbour, int *iNeighbour,
+                 double *neighDist2, int *nNeighbourSK, int *iPair, int *iAtomStart) {
+  const nl::NeighbourList &L = g_list;
+  const size_t rows = (size_t)(L.mNeigh + 1) * L.nAtom;
+  std::memcpy(coords, L.coords.p, sizeof(double) * 3 * L.nAllAtom);
+  std::memcpy(species, L.species.p, sizeof(int) * L.nAllAtom);
+  std::memcpy(img2CentCell, L.img2CentCell.p, sizeof(int) * L.nAllAtom);
+  std::memcpy(iCellVec, L.iCellVec.p, sizeof(int) * L.nAllAtom);
+  std::memcpy(nNeighbour, L.nNeighbour.p, sizeof(int) * L.nAtom);
+  std::memcpy(iNeighbour, L.iNeighbour.p, sizeof(int) * rows);
+  std::memcpy(neighDist2, L.neighDist2.p, sizeof(double) * rows);
+  std::memcpy(nNeighbourSK, L.nNeighbourSK.p, sizeof(int) * L.nAtom);
+  std::memcpy(iPair, L.iPair.p, sizeof(int) * rows);
+  std::memcpy(iAtomStart, L.iAtomStart.p, sizeof(int) * (L.nAtom + 1));
+}
+
+// the grid the last update used: nb[3], lo[3], invW[3]
+void host_nl_grid(int *nb, double *lo, double *invW) {
+  for (int k = 0; k < 3; ++k) { nb[k] = g_list.grid.p->nb[k]; lo[k] = g_list.grid.p->lo[k]; invW[k] = g_list.grid.p->invW[k]; }
+}
+
+}  // extern "C"

@@ -1,0 +1,233 @@
+"""The PRODUCT's neighbour-list kernels and launch sequence (dftbplus_b200/csrc/n2_neighbour_kernels.cuh,
+n2_neighbour_driver.h) compiled for the host and run thread by thread in shuffled order
+(tests/host_eval/host_nl.cpp), against the oracle restatement of updateNeighbourList /
+getNrOfNeighboursForAll / getSparseDescriptor -- every array bit for bit, no GPU needed.
+
+The `-m gpu` tests (test_neighbour_list_gpu.py) cover the CUDA backend around the same kernels."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import oracle, case, ROOT
+from dftbplus_b200 import workloads
+
+SRC = os.path.join(ROOT, "tests", "host_eval", "host_nl.cpp")
+SO = os.path.join(ROOT, "oracle", "_build", "libhostnl.so")
+DEPS = [SRC] + [os.path.join(ROOT, "dftbplus_b200", "csrc", f)
+                for f in ("n2_neighbour_kernels.cuh", "n2_neighbour_driver.h")]
+
+ARRAYS = ("coords", "species", "img2CentCell", "iCellVec", "nNeighbour", "iNeighbour", "neighDist2",
+          "nNeighbourSK", "iPair", "iAtomStart")
+
+
+@pytest.fixture(scope="module")
+def host():
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in DEPS):
+        os.makedirs(os.path.dirname(SO), exist_ok=True)
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", SO, SRC])
+    return ctypes.CDLL(SO)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+def host_list(lib, coord0, species0, n_orb_species, cell, rcell, cutoff, sk_cutoff, n_threads=61, seed=1):
+    coord0 = np.ascontiguousarray(coord0, dtype=np.float64)
+    species0 = np.ascontiguousarray(species0, dtype=np.int32)
+    nos = np.ascontiguousarray(n_orb_species, dtype=np.int32)
+    cell = np.ascontiguousarray(cell, dtype=np.float64)
+    rcell = np.ascontiguousarray(rcell, dtype=np.float64)
+    n = coord0.shape[0]
+    out = np.zeros(8, dtype=np.int32)
+    di, dd = ctypes.c_int, ctypes.c_double
+    rc = lib.host_nl_update(n, _p(coord0, dd), _p(species0, di), len(nos), _p(nos, di), cell.shape[0], _p(cell, dd),
+                            _p(rcell, dd), dd(cutoff), dd(sk_cutoff), n_threads, ctypes.c_uint(seed), _p(out, di))
+    assert rc == 0
+    nAll, mN, sparse, nOrb, e1, e2, valid, launches = (int(v) for v in out)
+    if e1:
+        raise RuntimeError("Atoms %d and %d too close together" % (e1, e2))
+    assert valid
+    g = dict(nAtom=n, nAllAtom=nAll, mNeigh=mN, sparseSize=sparse, nOrb=nOrb, launches=launches,
+             coords=np.zeros((nAll, 3)), species=np.zeros(nAll, np.int32), img2CentCell=np.zeros(nAll, np.int32),
+             iCellVec=np.zeros(nAll, np.int32), nNeighbour=np.zeros(n, np.int32),
+             iNeighbour=np.zeros((n, mN + 1), np.int32), neighDist2=np.zeros((n, mN + 1)),
+             nNeighbourSK=np.zeros(n, np.int32), iPair=np.zeros((n, mN + 1), np.int32),
+             iAtomStart=np.zeros(n + 1, np.int32))
+    lib.host_nl_get(_p(g["coords"], dd), _p(g["species"], di), _p(g["img2CentCell"], di), _p(g["iCellVec"], di),
+                    _p(g["nNeighbour"], di), _p(g["iNeighbour"], di), _p(g["neighDist2"], dd),
+                    _p(g["nNeighbourSK"], di), _p(g["iPair"], di), _p(g["iAtomStart"], di))
+    return g
+
+
+def assert_same_list(got, ref):
+    for k in ("nAllAtom", "mNeigh", "sparseSize", "nOrb"):
+        assert got[k] == ref[k], k
+    for k in ARRAYS:
+        assert got[k].shape == ref[k].shape, k
+        assert np.array_equal(got[k], ref[k]), k      # bit for bit, doubles included
+
+
+def cells_of(w, cutoff):
+    if w["latvec"] is None:
+        return np.zeros((1, 3)), np.zeros((1, 3))
+    return oracle.cell_translations(w["latvec"], cutoff)
+
+
+@pytest.mark.parametrize("name", ["h2o", "ce_o", "scan", "si2", "fec128", "si512", "water1002"])
+def test_host_run_of_the_kernels_equals_the_oracle(name, host):
+    w, sk, geo, model, selfegy = case(name)
+    cutoff = sk.cutoff()
+    cell, rcell = cells_of(w, cutoff)
+    ref = oracle.neighbour_list_full(sk.n_orb_species, w["coord0"], w["species0"], rcell, cutoff, cutoff)
+    got = host_list(host, w["coord0"], w["species0"], sk.n_orb_species, cell, rcell, cutoff, cutoff)
+    assert_same_list(got, ref)
+    # the trimmed arrays are what the harness' own producer (geometry.py) and the parity tests use
+    assert got["sparseSize"] == geo["sparseSize"] and got["nAllAtom"] == geo["nAllAtom"]
+
+
+def test_perfect_crystal_equal_distance_shells_keep_the_reference_order(host):
+    """Unjittered lattices: every shell holds many neighbours at distances equal within tolSameDist2,
+    where the order is whatever the reference's tolerance heap sort leaves -- and it fixes iPair."""
+    a = 5.42
+    basis = np.array([[0, 0, 0], [.5, .5, .5]])
+    cc = np.array([[i, j, k] for i in range(3) for j in range(3) for k in range(2)])
+    coord0 = (cc[:, None, :] + basis[None, :, :]).reshape(-1, 3) * a
+    species0 = np.array([1 + (i % 3 == 0) for i in range(len(coord0))], dtype=np.int32)
+    lat = np.diag([3 * a, 3 * a, 2 * a])
+    cell, rcell = oracle.cell_translations(lat, 11.0)
+    ref = oracle.neighbour_list_full([9, 4], coord0, species0, rcell, 11.0, 11.0)
+    assert np.any(np.abs(np.diff(ref["neighDist2"][:, 1:], axis=1)) < 1e-10)
+    for seed in (1, 2):
+        got = host_list(host, coord0, species0, [9, 4], cell, rcell, 11.0, 11.0, n_threads=17 + 40 * seed, seed=seed)
+        assert_same_list(got, ref)
+
+
+def test_list_cutoff_larger_than_sk_cutoff(host):
+    """mCutOff > skCutOff (repulsive / dispersion reach further): rows keep all neighbours of the list
+    cutoff, nNeighbourSK and iPair only those of the SK cutoff (main.F90:2562-2578)."""
+    w, sk, geo, model, selfegy = case("fec128")
+    cutoff, skc = 14.5, sk.cutoff()
+    cell, rcell = oracle.cell_translations(w["latvec"], cutoff)
+    ref = oracle.neighbour_list_full(sk.n_orb_species, w["coord0"], w["species0"], rcell, cutoff, skc)
+    got = host_list(host, w["coord0"], w["species0"], sk.n_orb_species, cell, rcell, cutoff, skc)
+    assert_same_list(got, ref)
+    assert np.all(got["nNeighbourSK"] <= got["nNeighbour"]) and got["nNeighbourSK"].sum() < got["nNeighbour"].sum() // 2
+    assert got["sparseSize"] == geo["sparseSize"]
+
+
+def test_sk_cutoff_inside_a_shell_of_equal_distances(host):
+    """search_asc_real_geq with tolSameDist2: a cutoff that cuts a shell of a perfect lattice within
+    the tolerance, once from below and once from above."""
+    a = 4.0
+    coord0 = np.array([[i, j, k] for i in range(3) for j in range(3) for k in range(3)], dtype=np.float64) * a
+    species0 = np.ones(27, dtype=np.int32)
+    cell, rcell = np.zeros((1, 3)), np.zeros((1, 3))
+    for skc in (np.sqrt(32.0 - 0.5e-10), np.sqrt(32.0 + 0.5e-10), np.sqrt(32.0 - 3e-10), 4.0, 0.5):
+        ref = oracle.neighbour_list_full([4], coord0, species0, rcell, 9.0, skc)
+        got = host_list(host, coord0, species0, [4], cell, rcell, 9.0, skc)
+        assert_same_list(got, ref)
+
+
+@pytest.mark.parametrize("shape", ["planar", "line", "single", "wide"])
+def test_degenerate_bounding_boxes(shape, host):
+    rng = np.random.default_rng(5)
+    if shape == "planar":
+        coord0 = np.c_[rng.uniform(0, 40, (60, 2)), np.full(60, 1.5)]
+    elif shape == "line":
+        coord0 = np.c_[np.zeros(40), np.zeros(40), np.arange(40) * 1.7]
+    elif shape == "single":
+        coord0 = np.array([[0.3, -0.2, 0.9]])
+    else:  # more than kMaxBinsPerDim cutoffs wide: the bin edge grows instead of the bin count
+        coord0 = np.c_[np.arange(120) * 3.9, rng.uniform(0, 3, 120), rng.uniform(0, 3, 120)]
+    species0 = np.ones(len(coord0), dtype=np.int32)
+    cell, rcell = np.zeros((1, 3)), np.zeros((1, 3))
+    ref = oracle.neighbour_list_full([4], coord0, species0, rcell, 11.0, 11.0)
+    got = host_list(host, coord0, species0, [4], cell, rcell, 11.0, 11.0)
+    assert_same_list(got, ref)
+    if shape == "single":
+        assert got["mNeigh"] == 0 and got["nAllAtom"] == 1 and got["sparseSize"] == 16
+
+
+def test_small_cell_periodic_images_of_the_atom_itself(host):
+    """One atom in a small cell: all neighbours are its own images (fac = 1 pairs of the stress)."""
+    lat = np.array([[4.1, 0.0, 0.0], [1.0, 4.3, 0.0], [0.2, 0.7, 5.0]])
+    coord0 = np.array([[0.4, 0.1, 0.2]])
+    cell, rcell = oracle.cell_translations(lat, 9.0)
+    ref = oracle.neighbour_list_full([9], coord0, [1], rcell, 9.0, 9.0)
+    got = host_list(host, coord0, [1], [9], cell, rcell, 9.0, 9.0)
+    assert_same_list(got, ref)
+    assert np.all(got["img2CentCell"] == 1) and got["mNeigh"] > 20
+
+
+def test_results_do_not_depend_on_the_thread_order_or_count(host):
+    w, sk, geo, model, selfegy = case("fec128")
+    cutoff = sk.cutoff()
+    cell, rcell = oracle.cell_translations(w["latvec"], cutoff)
+    first = host_list(host, w["coord0"], w["species0"], sk.n_orb_species, cell, rcell, cutoff, cutoff, 1, 0)
+    for n_threads, seed in ((7, 3), (256, 4), (5000, 5)):
+        again = host_list(host, w["coord0"], w["species0"], sk.n_orb_species, cell, rcell, cutoff, cutoff,
+                          n_threads, seed)
+        assert_same_list(again, first)
+
+
+def test_too_close_atoms_report_the_reference_pair(host):
+    """pairError = first (cell, iAtom1, iAtom2) in the reference's loop order (periodic.F90:616-628)."""
+    w, sk, geo, model, selfegy = case("fec128")
+    coord0 = w["coord0"].copy()
+    coord0[77] = coord0[12] + [0.003, 0.0, -0.002]
+    coord0[90] = coord0[31] + [0.0, 0.004, 0.0]
+    cutoff = sk.cutoff()
+    cell, rcell = oracle.cell_translations(w["latvec"], cutoff)
+    with pytest.raises(RuntimeError) as ref:
+        oracle.neighbour_list_full(sk.n_orb_species, coord0, w["species0"], rcell, cutoff, cutoff)
+    with pytest.raises(RuntimeError) as got:
+        host_list(host, coord0, w["species0"], sk.n_orb_species, cell, rcell, cutoff, cutoff)
+    assert str(got.value) == str(ref.value) == "Atoms 78 and 13 too close together"
+    # an atom on top of its own periodic image is an error as well (only cell 1 is exempt)
+    lat = np.diag([0.008, 30.0, 30.0])
+    cell, rcell = oracle.cell_translations(lat, 2.0)
+    with pytest.raises(RuntimeError) as ref:
+        oracle.neighbour_list_full([4], np.zeros((1, 3)), [1], rcell, 2.0, 2.0)
+    with pytest.raises(RuntimeError) as got:
+        host_list(host, np.zeros((1, 3)), [1], [4], cell, rcell, 2.0, 2.0)
+    assert str(got.value) == str(ref.value)
+
+
+def test_grid_never_has_bins_narrower_than_the_cutoff(host):
+    w, sk, geo, model, selfegy = case("si512")
+    cutoff = sk.cutoff()
+    cell, rcell = oracle.cell_translations(w["latvec"], cutoff)
+    host_list(host, w["coord0"], w["species0"], sk.n_orb_species, cell, rcell, cutoff, cutoff)
+    nb, lo, inv = np.zeros(3, np.int32), np.zeros(3), np.zeros(3)
+    host.host_nl_grid(_p(nb, ctypes.c_int), _p(lo, ctypes.c_double), _p(inv, ctypes.c_double))
+    assert np.all(1.0 / inv >= cutoff * 1.0001 * (1 - 1e-15)) and np.all(nb >= 1) and np.all(nb <= 32)
+    ext = w["coord0"].max(axis=0) - w["coord0"].min(axis=0)
+    assert np.all(nb / inv >= ext * (1 - 1e-15)) and np.allclose(lo, w["coord0"].min(axis=0), rtol=0, atol=0)
+
+
+def test_cell_translations_through_the_c_abi_equal_the_oracle():
+    """dftbp_b200_cell_translations is host code of the shipped library (no device needed)."""
+    from dftbplus_b200 import _lib, build as build_mod
+    if not os.path.exists(_lib.SO_PATH):
+        build_mod.build()
+    L = _lib.load()
+    dd = ctypes.c_double
+    for lat, cutoff in ((np.array([[10.0, 0, 0], [2.0, 9.0, 0], [0, 1.0, 12.0]]), 11.0),
+                        (0.5 * 10.263 * np.array([[0.0, 1, 1], [1, 0, 1], [1, 1, 0]]), 11.0),
+                        (np.diag([86.8, 86.8, 43.4]), 11.0), (np.diag([3.0, 50.0, 7.0]), 0.0)):
+        lat = np.ascontiguousarray(lat)
+        rec = np.ascontiguousarray(np.linalg.inv(lat).T)
+        n = ctypes.c_int()
+        assert L.dftbp_b200_cell_translations(_p(lat, dd), _p(rec, dd), cutoff, 0, ctypes.byref(n), None, None) == 0
+        cell, rcell = np.zeros((n.value, 3)), np.zeros((n.value, 3))
+        assert L.dftbp_b200_cell_translations(_p(lat, dd), _p(rec, dd), cutoff, n.value, ctypes.byref(n),
+                                              _p(cell, dd), _p(rcell, dd)) == 0
+        c_ref, r_ref = oracle.cell_translations(lat, cutoff)
+        assert np.array_equal(cell, c_ref) and np.array_equal(rcell, r_ref)
+        # too small an output array is refused, not overrun
+        assert L.dftbp_b200_cell_translations(_p(lat, dd), _p(rec, dd), cutoff, n.value - 1, ctypes.byref(n),
+                                              _p(cell, dd), _p(rcell, dd)) == 1
