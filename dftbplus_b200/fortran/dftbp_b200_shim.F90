@@ -145,6 +145,29 @@ module dftbp_b200_shim
       type(c_ptr), value :: shift
       real(c_double), value :: delta
     end function
+    integer(c_int) function dftbp_b200_update_neighbour_list(ctx, nAtom, coord0, species0, nCellVec, cellVec,&
+        & rCellVec, cutoff, skCutoff, nAllAtom, mNeigh, sparseSize) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nAtom, nCellVec
+      real(c_double), intent(in) :: coord0(*), cellVec(*), rCellVec(*)
+      integer(c_int), intent(in) :: species0(*)
+      real(c_double), value :: cutoff, skCutoff
+      integer(c_int), intent(out) :: nAllAtom, mNeigh, sparseSize
+    end function
+    integer(c_int) function dftbp_b200_get_neighbour_list(ctx, coords, species, img2CentCell, iCellVec,&
+        & nNeighbour, iNeighbour, neighDist2, nNeighbourSK, iPair, iAtomStart) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(out) :: coords(*), neighDist2(*)
+      integer(c_int), intent(out) :: species(*), img2CentCell(*), iCellVec(*), nNeighbour(*), iNeighbour(*)
+      integer(c_int), intent(out) :: nNeighbourSK(*), iPair(*)
+      type(c_ptr), value :: iAtomStart
+    end function
+    integer(c_int) function dftbp_b200_adopt_neighbour_list(ctx) bind(C)
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx
+    end function
   end interface
 
 contains
@@ -222,6 +245,40 @@ contains
         & img2CentCell, iCellVec, size(cellVec, dim=2), cellVec, nNeighbourSK, iNeighbour,&
         & iSparseStart(0:mNeigh, :), iAtomStart, sparseSize))
   end subroutine b200_setGeometry
+
+  !> updateNeighbourListAndSpecies (dftb/periodic.F90:380) + getNrOfNeighboursForAll (:996) +
+  !> getSparseDescriptor (dftb/sparse2dense.F90:3617) in one device pass; replaces the three calls of
+  !> handleCoordinateChange (dftbplus/main.F90:2562-2578) and the later b200_setGeometry.  The
+  !> arrays come back with the reference's shapes (rows 0:maxval(nNeighbour)) for the host-side
+  !> consumers (repulsive, SCC, dispersion).
+  subroutine b200_updateNeighbourListAndSpecies(ctx, coord, species, img2CentCell, iCellVec, neigh,&
+      & nAllAtom, coord0, species0, cutoff, skCutoff, cellVec, rCellVec, nNeighbourSK, iSparseStart,&
+      & sparseSize)
+    use dftbp_dftb_periodic, only : TNeighbourList, allocateNeighbourArrays
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), allocatable, intent(inout) :: coord(:,:)
+    integer, allocatable, intent(inout) :: species(:), img2CentCell(:), iCellVec(:), iSparseStart(:,:)
+    type(TNeighbourList), intent(inout) :: neigh
+    integer, intent(out) :: nAllAtom, sparseSize
+    real(dp), intent(in) :: coord0(:,:), cutoff, skCutoff, cellVec(:,:), rCellVec(:,:)
+    integer, intent(in) :: species0(:)
+    integer, intent(out) :: nNeighbourSK(:)
+    integer :: nAtom, mNeigh
+    if (neigh%setExternally) return
+    nAtom = size(species0)
+    call check(ctx, dftbp_b200_update_neighbour_list(ctx%h, nAtom, coord0, species0, size(rCellVec, dim=2),&
+        & cellVec, rCellVec, cutoff, skCutoff, nAllAtom, mNeigh, sparseSize))
+    if (allocated(coord)) deallocate(coord, species, img2CentCell, iCellVec)
+    allocate(coord(3, nAllAtom), species(nAllAtom), img2CentCell(nAllAtom), iCellVec(nAllAtom))
+    ! iNeighbour / neighDist2 are pointers into memory the list owns (periodic.F90:881-922)
+    call allocateNeighbourArrays(neigh, mNeigh, nAtom)
+    if (allocated(iSparseStart)) deallocate(iSparseStart)
+    allocate(iSparseStart(0:mNeigh, nAtom))
+    neigh%cutoff = cutoff
+    call check(ctx, dftbp_b200_get_neighbour_list(ctx%h, coord, species, img2CentCell, iCellVec,&
+        & neigh%nNeighbour, neigh%iNeighbour, neigh%neighDist2, nNeighbourSK, iSparseStart, c_null_ptr))
+    call check(ctx, dftbp_b200_adopt_neighbour_list(ctx%h))
+  end subroutine b200_updateNeighbourListAndSpecies
 
   !> buildH0, dftb/nonscc.F90:66 (env, skHamCont, coords, ... are held by the context)
   subroutine b200_buildH0(ctx, ham, selfegy)
