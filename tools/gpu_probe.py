@@ -117,6 +117,34 @@ def main():
             ms = timeit(lambda: torch.matmul(Cc, Cc.t()), stream, n=2, warm=1)
         out["cublas_gemm_same_shape_ms"] = ms
         out["cublas_gemm_same_shape_tflops"] = 2.0 * nOrb * nOrb * nocc / ms / 1e9
+    # N2: neighbour list + sparse descriptor on the device (host wall clock: the call ends with the
+    # read-back of the sizes), without and with the copies of the arrays back to the host, against
+    # the same geometry through the host producer + set_geometry
+    try:
+        cutoff = sk.cutoff()
+        def wall(fn, n=5):
+            n = 1 if ONCE else n
+            fn()
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            for _ in range(n):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t) / n * 1e3
+        hp.timer_enable(True)
+        out["n2_update_wall_ms"] = wall(lambda: hp.updateNeighbourListAndSpecies(
+            w["coord0"], w["species0"], cutoff, w["latvec"], adopt=False, fetch=False))
+        t = hp.timer_read()["neighbourList"]
+        out["n2_update_device_ms"] = t[0] / max(1, t[1])
+        hp.timer_enable(False)
+        out["n2_update_fetch_wall_ms"] = wall(lambda: hp.updateNeighbourListAndSpecies(
+            w["coord0"], w["species0"], cutoff, w["latvec"], adopt=False, fetch=True), n=3)
+        out["n2_update_adopt_wall_ms"] = wall(lambda: hp.updateNeighbourListAndSpecies(
+            w["coord0"], w["species0"], cutoff, w["latvec"], adopt=True, fetch=False), n=3)
+        out["set_geometry_from_host_wall_ms"] = wall(lambda: hp.set_geometry(geo), n=3)
+        out["n2_candidate_images"] = int(len(w["coord0"]) * (27 if w["latvec"] is not None else 1))
+    except Exception as e:  # keep the kernel numbers above if this young path fails
+        out["n2_error"] = repr(e)
     out["launches"] = hp.kernel_launches
     print(json.dumps(out))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
