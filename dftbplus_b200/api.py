@@ -182,6 +182,15 @@ class HotPath:
             raise DftbB200Error(rc, "cell_translations: bad arguments")
         return cell, rcell
 
+    def foldCoordsToCell(self, coord, latvec):
+        """boundaryCond%foldCoordsToCell (pbc3d): coord[nAtom, 3] (numpy: a folded copy is returned;
+        CUDA tensor: folded in place), latvec[i] = i-th lattice vector."""
+        latvec = np.ascontiguousarray(latvec, dtype=np.float64)
+        if not _is_torch(coord):
+            coord = np.array(coord, dtype=np.float64, order="C", copy=True)
+        self._ck(self._L.dftbp_b200_fold_coords_to_cell(self._h, int(coord.shape[0]), _ptr(coord), _ptr(latvec)))
+        return coord
+
     def updateNeighbourListAndSpecies(self, coord0, species0, cutoff, latvec=None, sk_cutoff=None, adopt=True,
                                       fetch=True):
         """updateNeighbourListAndSpecies + getNrOfNeighboursForAll + getSparseDescriptor on the device

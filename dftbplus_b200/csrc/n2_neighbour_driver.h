@@ -12,6 +12,7 @@
 //   int  launch(kernel, long long nItems, args...);            // grid-stride kernel over nItems
 // All return 0 on success.
 #pragma once
+#include <cmath>
 #include <cstddef>
 
 #include "n2_neighbour_kernels.cuh"
@@ -86,6 +87,34 @@ struct NeighbourList {
     valid = false;
   }
 };
+
+// invert33 (invertInOut with determinant33, math/simplealgebra.F90:45-66 and the cofactor form after
+// it) and the column norms of latVec(3,3) column-major, for nl_fold.  Host arithmetic in the
+// reference's operation order.  Returns false for a singular cell.
+inline bool foldSetup(const double *latVec, FoldParams &fp) {
+  auto M = [&](int i, int j) { return latVec[(i - 1) + 3 * (j - 1)]; };
+  double tmp = M(1, 1) * (M(2, 2) * M(3, 3) - M(3, 2) * M(2, 3));
+  tmp = tmp - M(1, 2) * (M(2, 1) * M(3, 3) - M(3, 1) * M(2, 3));
+  tmp = tmp + M(1, 3) * (M(2, 1) * M(3, 2) - M(3, 1) * M(2, 2));
+  const double det = tmp;
+  if (!(det != 0.0)) return false;
+  double *inv = fp.inv;
+  inv[0] = -M(2, 3) * M(3, 2) + M(2, 2) * M(3, 3);
+  inv[1] = M(2, 3) * M(3, 1) - M(2, 1) * M(3, 3);
+  inv[2] = -M(2, 2) * M(3, 1) + M(2, 1) * M(3, 2);
+  inv[3] = M(1, 3) * M(3, 2) - M(1, 2) * M(3, 3);
+  inv[4] = -M(1, 3) * M(3, 1) + M(1, 1) * M(3, 3);
+  inv[5] = M(1, 2) * M(3, 1) - M(1, 1) * M(3, 2);
+  inv[6] = -M(1, 3) * M(2, 2) + M(1, 2) * M(2, 3);
+  inv[7] = M(1, 3) * M(2, 1) - M(1, 1) * M(2, 3);
+  inv[8] = -M(1, 2) * M(2, 1) + M(1, 1) * M(2, 2);
+  for (int k = 0; k < 9; ++k) {
+    inv[k] = inv[k] / det;
+    fp.lat[k] = latVec[k];
+  }
+  for (int j = 1; j <= 3; ++j) fp.vecLen[j - 1] = std::sqrt(M(1, j) * M(1, j) + M(2, j) * M(2, j) + M(3, j) * M(3, j));
+  return true;
+}
 
 // updateNeighbourListAndSpecies + getNrOfNeighboursForAll(skCutoff) + getSparseDescriptor
 // (handleCoordinateChange, dftbplus/main.F90:2562-2578).  coord0(3,nAtom), species0(nAtom),

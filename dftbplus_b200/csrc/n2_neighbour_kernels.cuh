@@ -85,6 +85,30 @@ NL_DEV int binOf(const double *__restrict__ p, const Grid &g) {
                     g.nb[1] * binCoord(p[2], g.lo[2], g.invW[2], g.nb[2]));
 }
 
+// foldCoordsToCell, pbc3d without contacts (dftb/boundarycond.F90:369-380): inv = invert33(latVec),
+// vecLen = column norms, all column-major; prepared on the host by foldSetup (n2_neighbour_driver.h).
+struct FoldParams {
+  double inv[9], lat[9], vecLen[3];
+};
+
+NL_KERNEL void nl_fold(int nAtom, FoldParams fp, double *__restrict__ coord) {
+  for (long long a = NL_TID; a < nAtom; a += NL_STRIDE) {
+    double *x = coord + 3 * a;
+    const double x0 = x[0], x1 = x[1], x2 = x[2];
+    double frac[3];
+    for (int i = 0; i < 3; ++i) {
+      // frac(:) = matmul(invLatVecs, coord(:,iAt)); frac = frac - floor(frac)
+      double f = NL_ADD(NL_ADD(NL_MUL(fp.inv[i], x0), NL_MUL(fp.inv[i + 3], x1)), NL_MUL(fp.inv[i + 6], x2));
+      f = NL_SUB(f, floor(f));
+      // where (abs(vecLen * (1.0_dp - frac)) < epsilon(0.0_dp)) frac = 0.0_dp
+      if (fabs(NL_MUL(fp.vecLen[i], NL_SUB(1.0, f))) < 2.220446049250313e-16) f = 0.0;
+      frac[i] = f;
+    }
+    for (int i = 0; i < 3; ++i)  // coord(:, iAt) = matmul(latVec, frac)
+      x[i] = NL_ADD(NL_ADD(NL_MUL(fp.lat[i], frac[0]), NL_MUL(fp.lat[i + 3], frac[1])), NL_MUL(fp.lat[i + 6], frac[2]));
+  }
+}
+
 // box[0..2] = min, box[3..5] = max of coord0 (encoded); box is preset to all-ones / zero
 NL_KERNEL void nl_bbox(int nAtom, const double *__restrict__ coord0, ull *__restrict__ box) {
   for (long long a = NL_TID; a < nAtom; a += NL_STRIDE)

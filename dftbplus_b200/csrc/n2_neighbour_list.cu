@@ -133,6 +133,24 @@ int dftbp_b200_cell_translations(const double *latVec, const double *recVec2p, d
   return 0;
 }
 
+int dftbp_b200_fold_coords_to_cell(dftbp_b200_ctx *ctx, int nAtom, double *coord, const double *latVec) {
+  if (!ctx) return DFTBP_B200_EINVAL;
+  DFTBP_CHECK(ctx, nAtom > 0 && coord && latVec, "fold_coords_to_cell: bad arguments");
+  double lat[9];
+  if (isDevicePtr(latVec)) {
+    DFTBP_CUDA(ctx, cudaMemcpy(lat, latVec, sizeof(lat), cudaMemcpyDeviceToHost));
+  } else {
+    std::memcpy(lat, latVec, sizeof(lat));
+  }
+  nl::FoldParams fp;
+  DFTBP_CHECK(ctx, nl::foldSetup(lat, fp), "fold_coords_to_cell: singular lattice");
+  double *d;
+  DFTBP_TRY(devOut(ctx, kSlotA, coord, (size_t)3 * nAtom, true, &d));
+  CudaBackend be{ctx};
+  DFTBP_TRY(be.launch(nl::nl_fold, nAtom, nAtom, fp, d));
+  return finish(ctx);
+}
+
 int dftbp_b200_update_neighbour_list(dftbp_b200_ctx *ctx, int nAtom, const double *coord0, const int *species0,
                                      int nCellVec, const double *cellVec, const double *rCellVec, double cutoff,
                                      double skCutoff, int *nAllAtom, int *mNeigh, int *sparseSize) {

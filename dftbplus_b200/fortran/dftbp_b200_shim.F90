@@ -145,6 +145,13 @@ module dftbp_b200_shim
       type(c_ptr), value :: shift
       real(c_double), value :: delta
     end function
+    integer(c_int) function dftbp_b200_fold_coords_to_cell(ctx, nAtom, coord, latVec) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nAtom
+      real(c_double), intent(inout) :: coord(*)
+      real(c_double), intent(in) :: latVec(3, 3)
+    end function
     integer(c_int) function dftbp_b200_update_neighbour_list(ctx, nAtom, coord0, species0, nCellVec, cellVec,&
         & rCellVec, cutoff, skCutoff, nAllAtom, mNeigh, sparseSize) bind(C)
       import :: c_ptr, c_int, c_double
@@ -245,6 +252,14 @@ contains
         & img2CentCell, iCellVec, size(cellVec, dim=2), cellVec, nNeighbourSK, iNeighbour,&
         & iSparseStart(0:mNeigh, :), iAtomStart, sparseSize))
   end subroutine b200_setGeometry
+
+  !> boundaryCond%foldCoordsToCell, pbc3d without contacts (dftb/boundarycond.F90:369-380)
+  subroutine b200_foldCoordsToCell(ctx, coord, latVec)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(inout) :: coord(:,:)
+    real(dp), intent(in) :: latVec(:,:)
+    call check(ctx, dftbp_b200_fold_coords_to_cell(ctx%h, size(coord, dim=2), coord, latVec))
+  end subroutine b200_foldCoordsToCell
 
   !> updateNeighbourListAndSpecies (dftb/periodic.F90:380) + getNrOfNeighboursForAll (:996) +
   !> getSparseDescriptor (dftb/sparse2dense.F90:3617) in one device pass; replaces the three calls of

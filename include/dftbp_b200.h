@@ -116,6 +116,12 @@ int dftbp_b200_set_geometry(dftbp_b200_ctx *ctx, int nAtom, int nAllAtom, int mN
 int dftbp_b200_cell_translations(const double *latVec, const double *recVec2p, double cutoff,
                                  int maxCellVec, int *nCellVec, double *cellVec, double *rCellVec);
 
+/* foldCoordsToCell, pbc3d branch without contacts (dftb/boundarycond.F90:369-380; the step before
+ * the list in handleCoordinateChange, dftbplus/main.F90:2559-2561): coord(3, nAtom) is folded into
+ * the cell of latVec(3,3) (column-major, column i = i-th lattice vector) in place, with the
+ * reference's invert33 and operation order.  Cluster geometries are not folded (no call). */
+int dftbp_b200_fold_coords_to_cell(dftbp_b200_ctx *ctx, int nAtom, double *coord, const double *latVec);
+
 /* updateNeighbourListAndSpecies (dftb/periodic.F90:380-440, 446-694; non-symmetric list, no helical
  * boundary conditions) + getNrOfNeighboursForAll(skCutoff) (:996-1054) + getSparseDescriptor
  * (dftb/sparse2dense.F90:3617-3662), as called by handleCoordinateChange

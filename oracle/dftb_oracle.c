@@ -20,6 +20,7 @@
  * Build: gcc -O2 -funroll-all-loops -fopenmp -ffp-contract=off -fPIC -shared
  * (the flags of the reference's Release build, sys/gnu.cmake:27; x86-64 baseline => no FMA).
  */
+#include <float.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -658,6 +659,44 @@ static void index_heap_sort(int n, int *indx, const double *array, double tol)
     }
     indx[ii - 1] = indxTmp;
   }
+}
+
+/* foldCoordsToCell, pbc3d branch without contacts (dftb/boundarycond.F90:369-380), with invert33 =
+ * invertInOut + determinant33 (math/simplealgebra.F90:45-66 and the cofactor form that follows).
+ * coord(3,nAtom) in/out, latVec(3,3) column-major (column i = i-th lattice vector). */
+void orc_fold_coords_to_cell(int nAtom, double *coord, const double *latVec)
+{
+#define M(i, j) latVec[((i) - 1) + 3 * ((j) - 1)]
+#define INV(i, j) inv[((i) - 1) + 3 * ((j) - 1)]
+  double inv[9], vecLen[3], det, tmp;
+  int iAt, i, j;
+  tmp = M(1, 1) * (M(2, 2) * M(3, 3) - M(3, 2) * M(2, 3));
+  tmp = tmp - M(1, 2) * (M(2, 1) * M(3, 3) - M(3, 1) * M(2, 3));
+  tmp = tmp + M(1, 3) * (M(2, 1) * M(3, 2) - M(3, 1) * M(2, 2));
+  det = tmp;
+  INV(1, 1) = -M(2, 3) * M(3, 2) + M(2, 2) * M(3, 3);
+  INV(2, 1) = M(2, 3) * M(3, 1) - M(2, 1) * M(3, 3);
+  INV(3, 1) = -M(2, 2) * M(3, 1) + M(2, 1) * M(3, 2);
+  INV(1, 2) = M(1, 3) * M(3, 2) - M(1, 2) * M(3, 3);
+  INV(2, 2) = -M(1, 3) * M(3, 1) + M(1, 1) * M(3, 3);
+  INV(3, 2) = M(1, 2) * M(3, 1) - M(1, 1) * M(3, 2);
+  INV(1, 3) = -M(1, 3) * M(2, 2) + M(1, 2) * M(2, 3);
+  INV(2, 3) = M(1, 3) * M(2, 1) - M(1, 1) * M(2, 3);
+  INV(3, 3) = -M(1, 2) * M(2, 1) + M(1, 1) * M(2, 2);
+  for (i = 0; i < 9; ++i) inv[i] = inv[i] / det;
+  for (j = 1; j <= 3; ++j) vecLen[j - 1] = sqrt(M(1, j) * M(1, j) + M(2, j) * M(2, j) + M(3, j) * M(3, j));
+  for (iAt = 0; iAt < nAtom; ++iAt) {
+    double *x = coord + 3 * iAt, frac[3], out[3];
+    for (i = 1; i <= 3; ++i) frac[i - 1] = INV(i, 1) * x[0] + INV(i, 2) * x[1] + INV(i, 3) * x[2];
+    for (i = 0; i < 3; ++i) {
+      frac[i] = frac[i] - floor(frac[i]);
+      if (fabs(vecLen[i] * (1.0 - frac[i])) < DBL_EPSILON) frac[i] = 0.0;
+    }
+    for (i = 1; i <= 3; ++i) out[i - 1] = M(i, 1) * frac[0] + M(i, 2) * frac[1] + M(i, 3) * frac[2];
+    x[0] = out[0]; x[1] = out[1]; x[2] = out[2];
+  }
+#undef M
+#undef INV
 }
 
 /* getCellTranslations -> getLatticePoints -> TLatPointIter (periodic.F90:227-263,272-336;

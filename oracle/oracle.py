@@ -206,6 +206,14 @@ def neighbour_geometry(model, coord0, species0, latvec=None, cutoff=None):
                 neighDist2=np.ascontiguousarray(d2[:, :mNeigh + 1]))
 
 
+def fold_coords_to_cell(coord0, latvec):
+    """foldCoordsToCell (pbc3d): coord0[nAtom,3], latvec[i] = i-th lattice vector.  Returns a copy."""
+    c = np.array(coord0, dtype=np.float64, order="C", copy=True)
+    lat = np.ascontiguousarray(latvec, dtype=np.float64)
+    lib().orc_fold_coords_to_cell(c.shape[0], _d(c), _d(lat))
+    return c
+
+
 def neighbour_list_full(n_orb_species, coord0, species0, rcell, cutoff, sk_cutoff):
     """updateNeighbourList(cutoff) + getNrOfNeighboursForAll(sk_cutoff) + getSparseDescriptor with
     the arrays exactly as the reference holds them (rows of iNeighbour / neighDist2 / iPair are

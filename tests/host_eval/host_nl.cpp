@@ -110,6 +110,14 @@ void host_nl_get(double *coords, int *species, int *img2CentCell, int *iCellVec,
   std::memcpy(iAtomStart, L.iAtomStart.p, sizeof(int) * (L.nAtom + 1));
 }
 
+// foldCoordsToCell through foldSetup + nl_fold; returns 0, or 1 for a singular lattice
+int host_nl_fold(int nAtom, double *coord, const double *latVec, int nThreads, unsigned seed) {
+  nl::FoldParams fp;
+  if (!nl::foldSetup(latVec, fp)) return 1;
+  HostBackend be{nThreads, std::mt19937(seed)};
+  return be.launch(nl::nl_fold, nAtom, nAtom, fp, coord);
+}
+
 // the grid the last update used: nb[3], lo[3], invW[3]
 void host_nl_grid(int *nb, double *lo, double *invW) {
   for (int k = 0; k < 3; ++k) { nb[k] = g_list.grid.p->nb[k]; lo[k] = g_list.grid.p->lo[k]; invW[k] = g_list.grid.p->invW[k]; }

@@ -231,3 +231,28 @@ def test_cell_translations_through_the_c_abi_equal_the_oracle():
         # too small an output array is refused, not overrun
         assert L.dftbp_b200_cell_translations(_p(lat, dd), _p(rec, dd), cutoff, n.value - 1, ctypes.byref(n),
                                               _p(cell, dd), _p(rcell, dd)) == 1
+
+
+def test_fold_coords_to_cell_equals_the_oracle(host):
+    """foldCoordsToCell (boundarycond.F90:369-380): the step before the list in handleCoordinateChange."""
+    rng = np.random.default_rng(21)
+    dd = ctypes.c_double
+    lats = [np.diag([86.8, 86.8, 43.4]), np.array([[10.0, 0, 0], [2.0, 9.0, 0], [0, 1.0, 12.0]]),
+            0.5 * 10.263 * np.array([[0.0, 1, 1], [1, 0, 1], [1, 1, 0]])]
+    for lat in lats:
+        lat = np.ascontiguousarray(lat)
+        frac = rng.uniform(-3.0, 3.0, (500, 3))
+        frac[:20] = rng.integers(-2, 3, (20, 3))                   # lattice points: the frac = 1 - eps guard
+        frac[20:40] = np.round(frac[20:40] * 4) / 4
+        coord = frac @ lat
+        ref = oracle.fold_coords_to_cell(coord, lat)
+        got = np.array(coord, copy=True)
+        assert host.host_nl_fold(len(got), _p(got, dd), _p(lat, dd), 37, 3) == 0
+        assert np.array_equal(got, ref)
+        back = np.linalg.solve(lat.T, ref.T).T
+        assert back.min() > -1e-12 and back.max() < 1 + 1e-12
+        shift = np.linalg.solve(lat.T, (coord - ref).T).T
+        assert np.abs(shift - np.round(shift)).max() < 1e-9        # moved by lattice vectors only
+    sing = np.ascontiguousarray(np.array([[1.0, 0, 0], [2.0, 0, 0], [0, 0, 1.0]]))
+    c = np.zeros((2, 3))
+    assert host.host_nl_fold(2, _p(c, dd), _p(sing, dd), 4, 1) == 1

@@ -152,3 +152,47 @@ def test_md_like_sequence_of_updates(hp_for):
         assert_same_list(got, ref)
         s = hp.buildS()
         assert s.shape[0] == ref["sparseSize"] and np.isfinite(s).all()
+
+
+def test_fold_coords_to_cell_on_the_device(hp_for):
+    """foldCoordsToCell (boundarycond.F90:369-380) bit for bit, host array and CUDA tensor."""
+    import torch
+    hp = hp_for("fec128")
+    rng = np.random.default_rng(21)
+    for lat in (np.diag([86.8, 86.8, 43.4]), np.array([[10.0, 0, 0], [2.0, 9.0, 0], [0, 1.0, 12.0]]),
+                0.5 * 10.263 * np.array([[0.0, 1, 1], [1, 0, 1], [1, 1, 0]])):
+        frac = rng.uniform(-3.0, 3.0, (700, 3))
+        frac[:20] = rng.integers(-2, 3, (20, 3))
+        coord = frac @ lat
+        ref = oracle.fold_coords_to_cell(coord, lat)
+        assert np.array_equal(hp.foldCoordsToCell(coord, lat), ref)
+        t = torch.from_numpy(np.ascontiguousarray(coord)).cuda()
+        torch.cuda.synchronize()
+        hp.foldCoordsToCell(t, lat)
+        hp.synchronize()
+        assert np.array_equal(t.cpu().numpy(), ref)
+    from dftbplus_b200.api import DftbB200Error
+    with pytest.raises(DftbB200Error):
+        hp.foldCoordsToCell(np.zeros((2, 3)), np.array([[1.0, 0, 0], [2.0, 0, 0], [0, 0, 1.0]]))
+
+
+def test_md_step_from_unfolded_device_coordinates(hp_for):
+    """The whole handleCoordinateChange chain on device-resident coordinates: fold -> list -> adopt ->
+    H0/S, against the oracle's chain on the same (drifted, partly outside the cell) coordinates."""
+    import torch
+    w, sk, geo, model, selfegy = case("fec128")
+    hp = hp_for("fec128")
+    rng = np.random.default_rng(4)
+    lat = np.asarray(w["latvec"])
+    coord = w["coord0"] + rng.normal(scale=0.05, size=w["coord0"].shape) + rng.integers(-1, 2, (len(w["coord0"]), 3)) @ lat
+    folded = oracle.fold_coords_to_cell(coord, lat)
+    ogeo = oracle.neighbour_geometry(model, folded, w["species0"], lat)
+    t = torch.from_numpy(np.ascontiguousarray(coord)).cuda()
+    torch.cuda.synchronize()
+    hp.foldCoordsToCell(t, lat)
+    g = hp.updateNeighbourListAndSpecies(t, w["species0"], sk.cutoff(), lat, adopt=True)
+    assert g["sparseSize"] == ogeo["sparseSize"] and np.array_equal(g["iPair"][:, :ogeo["mNeigh"] + 1], ogeo["iPair"])
+    assert np.array_equal(g["coords"], ogeo["coords"])
+    h, s = hp.buildH0S(sk.selfegy)
+    assert_sparse_close(h, oracle.build_h0(model, ogeo, selfegy), what="H0 after fold + device list")
+    assert_sparse_close(s, oracle.build_s(model, ogeo), what="S after fold + device list")
