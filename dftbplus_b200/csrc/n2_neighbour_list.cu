@@ -144,7 +144,7 @@ int dftbp_b200_fold_coords_to_cell(dftbp_b200_ctx *ctx, int nAtom, double *coord
   }
   nl::FoldParams fp;
   DFTBP_CHECK(ctx, nl::foldSetup(lat, fp), "fold_coords_to_cell: singular lattice");
-  double *d;
+  double *d = nullptr;
   DFTBP_TRY(devOut(ctx, kSlotA, coord, (size_t)3 * nAtom, true, &d));
   CudaBackend be{ctx};
   DFTBP_TRY(be.launch(nl::nl_fold, nAtom, nAtom, fp, d));

@@ -256,3 +256,26 @@ def test_fold_coords_to_cell_equals_the_oracle(host):
     sing = np.ascontiguousarray(np.array([[1.0, 0, 0], [2.0, 0, 0], [0, 0, 1.0]]))
     c = np.zeros((2, 3))
     assert host.host_nl_fold(2, _p(c, dd), _p(sing, dd), 4, 1) == 1
+
+
+def test_sm100a_code_of_the_distance_kernels_has_no_fused_multiply_add():
+    """Bit-exact distances need the reference's separate multiplies and adds: the SASS of the built
+    library must not contain DFMA in the kernels that produce coordinates / squared distances."""
+    import shutil
+    from dftbplus_b200 import build as build_mod
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    build_mod.build()
+    obj = os.path.join(ROOT, "dftbplus_b200", "lib", "n2_neighbour_list.o")
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
+    fn, dfma, seen = None, {}, set()
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+            seen.add(fn)
+        elif "DFMA" in line and fn:
+            dfma[fn] = dfma.get(fn, 0) + 1
+    for kernel in ("nl_count", "nl_fill", "nl_sort", "nl_fold"):
+        names = [f for f in seen if kernel in f]
+        assert names, kernel
+        assert all(dfma.get(f, 0) == 0 for f in names), (kernel, dfma)
