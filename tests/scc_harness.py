@@ -114,9 +114,10 @@ class DeviceArm:
         return self.hp.derivative_shift(rho, erho, shift=shift_block)
 
 
-def scc_single_point(arm, workload, sk, geo, m_orb, tol=1e-8, mix=0.4, max_iter=200):
+def scc_single_point(arm, workload, sk, geo, m_orb, tol=1e-8, mix=0.4, max_iter=200, q_init=None):
     """Returns dict(n_iter, energy, q, forces).  Convergence: max |q_out - q_in| < tol on the
-    orbital-resolved Mulliken charges (main.F90:4884-4930 with a simple mixer)."""
+    orbital-resolved Mulliken charges (main.F90:4884-4930 with a simple mixer).  q_init: input
+    charges of the first iteration (the previous geometry step's output: "SCC restart")."""
     species0 = np.asarray(workload["species0"])
     n_atom = geo["nAtom"]
     hubb = [sk.hubbU[s][0] for s in range(len(sk.hubbU))]
@@ -129,7 +130,7 @@ def scc_single_point(arm, workload, sk, geo, m_orb, tol=1e-8, mix=0.4, max_iter=
             k += 2 * l + 1
     n_elec = q0.sum()
     h0, over = arm.build()
-    q_in = q0.copy()
+    q_in = q0.copy() if q_init is None else np.array(q_init, dtype=float, copy=True)
     for it in range(1, max_iter + 1):
         dq = (q_in - q0).sum(axis=1)
         shift_atom = gamma @ dq
@@ -151,3 +152,34 @@ def scc_single_point(arm, workload, sk, geo, m_orb, tol=1e-8, mix=0.4, max_iter=
     shift_block[0, :, idx, idx] = (gamma @ dq)[None, :]
     forces = arm.forces(rho, erho, shift_block)
     return dict(n_iter=it, energy=e_h0 + e_scc, e_h0=e_h0, e_scc=e_scc, q=q_out, forces=forces, err=err)
+
+
+def velocity_verlet(make_arm, workload, sk, m_orb, n_steps, dt=20.670687, mix=0.1, seed=7, v_scale=2.0e-4):
+    """BASELINE config 5's pattern on a cluster: velocity-Verlet steps, every step rebuilds the
+    neighbour list / sparse descriptor for the new coordinates (handleCoordinateChange) and runs an
+    SCC cycle restarted from the previous step's charges.  make_arm(coords) -> (arm, geo) builds the
+    arm's geometry its own way (oracle: CPU restatement; device: dftbp_b200_update_neighbour_list +
+    adopt).  dt in atomic time units (20.67 = 0.5 fs).  Returns per-step records and the final state."""
+    species0 = np.asarray(workload["species0"])
+    mass = np.array([sk.mass[s - 1] for s in species0])[:, None]
+    rng = np.random.default_rng(seed)
+    x = np.array(workload["coord0"], dtype=float, copy=True)
+    v = rng.normal(scale=v_scale, size=x.shape)
+    v -= (mass * v).sum(axis=0) / mass.sum()
+
+    def evaluate(x, q_init):
+        arm, geo = make_arm(x)
+        w = dict(workload, coord0=x)
+        return scc_single_point(arm, w, sk, geo, m_orb, mix=mix, max_iter=600, q_init=q_init), geo
+
+    r, geo = evaluate(x, None)
+    steps = [dict(n_iter=r["n_iter"], energy=r["energy"], sparseSize=geo["sparseSize"])]
+    for _ in range(n_steps):
+        a = -r["forces"] / mass
+        v = v + 0.5 * dt * a
+        x = x + dt * v
+        r, geo = evaluate(x, r["q"])
+        v = v + 0.5 * dt * (-r["forces"] / mass)
+        steps.append(dict(n_iter=r["n_iter"], energy=r["energy"], sparseSize=geo["sparseSize"],
+                          e_kin=0.5 * float((mass * v * v).sum())))
+    return dict(steps=steps, x=x, v=v, q=r["q"], forces=r["forces"])
