@@ -50,6 +50,8 @@ SIGNATURES = {
     "dftbp_b200_pack_hs_cplx_atoms": (c_int, [c_void_p, c_void_p, c_void_p, c_int, P(c_double), c_double, c_int, c_int]),
     "dftbp_b200_mulliken_orbital": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "dftbp_b200_mulliken_block": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dftbp_b200_mulliken_atom": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dftbp_b200_onsite_population": (c_int, [c_void_p, c_void_p, c_void_p]),
     "dftbp_b200_add_shift_atom": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "dftbp_b200_add_shift_block": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "dftbp_b200_derivative_shift": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_double]),

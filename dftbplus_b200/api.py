@@ -324,6 +324,20 @@ class HotPath:
         self._ck(fn(self._h, _ptr(qq), _ptr(_f64(over)), _ptr(_f64(rho))))
         return qq
 
+    def mullikenPerAtom(self, over, rho, qq=None):
+        """mullikenPerAtom (dftb/populations.F90:68-112): qq[nAtom] accumulates."""
+        if qq is None:
+            qq = np.zeros(self.geo["nAtom"])
+        self._ck(self._L.dftbp_b200_mulliken_atom(self._h, _ptr(qq), _ptr(_f64(over)), _ptr(_f64(rho))))
+        return qq
+
+    def getOnsitePopulation(self, rho, qq=None):
+        """getOnsitePopulation (dftb/populations.F90:1195-1222): qq[nAtom] = trace of the on-site blocks."""
+        if qq is None:
+            qq = np.zeros(self.geo["nAtom"])
+        self._ck(self._L.dftbp_b200_onsite_population(self._h, _ptr(_f64(rho)), _ptr(qq)))
+        return qq
+
     # ---- K6 ---------------------------------------------------------------------------------
     def addShift(self, ham, over, shift, is_input_zero=False):
         """addShift (dftb/shift.F90:41-228), in place on ham[nSpin, sparseSize] (or 1-D for one spin):

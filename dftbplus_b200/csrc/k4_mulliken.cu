@@ -11,6 +11,7 @@
 #include <cstdlib>
 
 #include "block_desc.cuh"
+#include "k4_atom_population.cuh"
 
 using namespace dftbp_b200;
 
@@ -164,6 +165,38 @@ int dftbp_b200_mulliken_orbital(dftbp_b200_ctx *ctx, double *qq, const double *o
 
 int dftbp_b200_mulliken_block(dftbp_b200_ctx *ctx, double *qq, const double *over, const double *rho) {
   return mullikenImpl(ctx, qq, over, rho, true);
+}
+
+int dftbp_b200_mulliken_atom(dftbp_b200_ctx *ctx, double *qq, const double *over, const double *rho) {
+  if (!ctx) return DFTBP_B200_EINVAL;
+  const Geometry &g = ctx->geo;
+  DFTBP_CHECK(ctx, g.nAtom > 0, "mulliken_atom: no geometry set");
+  DFTBP_CHECK(ctx, qq && over && rho, "mulliken_atom: null argument");
+  // qPerOrbital(:,:) = 0; call mullikenPerOrbital(...); qq(:) = qq + sum(qPerOrbital, dim=1)   (:103-110)
+  void *tmp;
+  const size_t nOrbQ = (size_t)ctx->mOrb * g.nAtom;
+  DFTBP_TRY(stagingGet(ctx, kSlotD, sizeof(double) * nOrbQ, &tmp));
+  DFTBP_CUDA(ctx, cudaMemsetAsync(tmp, 0, sizeof(double) * nOrbQ, ctx->stream));
+  DFTBP_TRY(mullikenImpl(ctx, static_cast<double *>(tmp), over, rho, false));  // device output: no read-back
+  double *dQ;
+  DFTBP_TRY(devOut(ctx, kSlotE, qq, (size_t)g.nAtom, true, &dQ));
+  pop::pop_atom_sum<<<(g.nAtom + 127) / 128, 128, 0, ctx->stream>>>(g.nAtom, ctx->mOrb, static_cast<const double *>(tmp), dQ);
+  ctx->launches++;
+  return finish(ctx);
+}
+
+int dftbp_b200_onsite_population(dftbp_b200_ctx *ctx, const double *rho, double *qq) {
+  if (!ctx) return DFTBP_B200_EINVAL;
+  const Geometry &g = ctx->geo;
+  DFTBP_CHECK(ctx, g.nAtom > 0, "onsite_population: no geometry set");
+  DFTBP_CHECK(ctx, qq && rho, "onsite_population: null argument");
+  const double *dRho;
+  double *dQ;
+  DFTBP_TRY(devIn(ctx, kSlotA, rho, (size_t)g.sparseSize, &dRho));
+  DFTBP_TRY(devOut(ctx, kSlotC, qq, (size_t)g.nAtom, false, &dQ));
+  pop::pop_onsite<<<(g.nAtom + 127) / 128, 128, 0, ctx->stream>>>(g.nAtom, g.mNeigh + 1, g.iPair, g.iAtomStart, dRho, dQ);
+  ctx->launches++;
+  return finish(ctx);
 }
 
 }  // extern "C"

@@ -21,27 +21,7 @@
 // after the other in a shuffled order, against the oracle (no GPU in the development container).
 #pragma once
 
-#ifdef __CUDACC__
-#include <cuda_runtime.h>
-#define NL_KERNEL __global__
-#define NL_DEV __device__ __forceinline__
-#define NL_TID ((long long)blockIdx.x * blockDim.x + threadIdx.x)
-#define NL_STRIDE ((long long)gridDim.x * blockDim.x)
-// IEEE operations that must not be contracted into FMAs (the reference is compiled without contraction
-// across statements; the oracle with -ffp-contract=off)
-#define NL_ADD(a, b) __dadd_rn((a), (b))
-#define NL_SUB(a, b) __dsub_rn((a), (b))
-#define NL_MUL(a, b) __dmul_rn((a), (b))
-#define NL_BITS(x) ((unsigned long long)__double_as_longlong(x))
-#define NL_FROM_BITS(u) __longlong_as_double((long long)(u))
-#else
-// host emulation: the includer defines NL_TID / NL_STRIDE and the atomics (tests/host_eval/host_nl.cpp)
-#define NL_KERNEL
-#define NL_DEV inline
-#define NL_ADD(a, b) ((a) + (b))
-#define NL_SUB(a, b) ((a) - (b))
-#define NL_MUL(a, b) ((a) * (b))
-#endif
+#include "emu_kernel.cuh"
 
 namespace dftbp_b200 {
 namespace nl {

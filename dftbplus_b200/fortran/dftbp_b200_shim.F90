@@ -145,6 +145,18 @@ module dftbp_b200_shim
       type(c_ptr), value :: shift
       real(c_double), value :: delta
     end function
+    integer(c_int) function dftbp_b200_mulliken_atom(ctx, qq, over, rho) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(inout) :: qq(*)
+      real(c_double), intent(in) :: over(*), rho(*)
+    end function
+    integer(c_int) function dftbp_b200_onsite_population(ctx, rho, qq) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(in) :: rho(*)
+      real(c_double), intent(out) :: qq(*)
+    end function
     integer(c_int) function dftbp_b200_fold_coords_to_cell(ctx, nAtom, coord, latVec) bind(C)
       import :: c_ptr, c_int, c_double
       type(c_ptr), value :: ctx
@@ -359,6 +371,22 @@ contains
     real(dp), intent(in) :: over(:), rho(:)
     call check(ctx, dftbp_b200_mulliken_orbital(ctx%h, qq, over, rho))
   end subroutine b200_mullikenPerOrbital
+
+  !> mullikenPerAtom, dftb/populations.F90:68 (the rank-1 overload of the generic mulliken)
+  subroutine b200_mullikenPerAtom(ctx, qq, over, rho)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(inout) :: qq(:)
+    real(dp), intent(in) :: over(:), rho(:)
+    call check(ctx, dftbp_b200_mulliken_atom(ctx%h, qq, over, rho))
+  end subroutine b200_mullikenPerAtom
+
+  !> getOnsitePopulation, dftb/populations.F90:1195
+  subroutine b200_getOnsitePopulation(ctx, rho, qq)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(in) :: rho(:)
+    real(dp), intent(out) :: qq(:)
+    call check(ctx, dftbp_b200_onsite_population(ctx%h, rho, qq))
+  end subroutine b200_getOnsitePopulation
 
   !> getBlockStress, dftb/stress.F90:188 (getNonSCCStress, :70, when shift is absent)
   subroutine b200_getBlockStress(ctx, st, DM, EDM, shift, diffType, deltaXDiff, cellVol)

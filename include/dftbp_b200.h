@@ -220,6 +220,12 @@ int dftbp_b200_mulliken_orbital(dftbp_b200_ctx *ctx, double *qq, const double *o
 /* mullikenPerBlock, dftb/populations.F90:306-375.  qq(mOrb, mOrb, nAtom) ACCUMULATES. */
 int dftbp_b200_mulliken_block(dftbp_b200_ctx *ctx, double *qq, const double *over,
                               const double *rho);
+/* mullikenPerAtom, dftb/populations.F90:68-112 (e.g. Tr[rho H0] per atom, dftb/getenergies.F90:198):
+ * qq(nAtom) ACCUMULATES sum over the orbitals of mullikenPerOrbital. */
+int dftbp_b200_mulliken_atom(dftbp_b200_ctx *ctx, double *qq, const double *over, const double *rho);
+/* getOnsitePopulation, dftb/populations.F90:1195-1222 (caller dftbplus/main.F90:4726): qq(nAtom) =
+ * trace of the on-site block of rho (net atomic population); OVERWRITTEN. */
+int dftbp_b200_onsite_population(dftbp_b200_ctx *ctx, const double *rho, double *qq);
 
 /* getNonSCCStress (shift == NULL) / getBlockStress, dftb/stress.F90:70-184 / 188-326 (SURVEY 8(f)
  * N3; callers dftbplus/main.F90:1829, 7491): the pair loop of derivative_shift with the outer

@@ -409,6 +409,29 @@ def mulliken_per_orbital(model, geo, over, rho, qq=None, iter_indices=None):
     return qq
 
 
+def mulliken_per_atom(model, geo, over, rho, qq=None, iter_indices=None):
+    """mullikenPerAtom, populations.F90:68-112: qq(:) = qq + sum(qPerOrbital, dim=1) (orbitals summed
+    in index order)."""
+    q_orb = mulliken_per_orbital(model, geo, over, rho, iter_indices=iter_indices)
+    s = np.zeros(geo["nAtom"])
+    for o in range(q_orb.shape[1]):
+        s = s + q_orb[:, o]
+    return s if qq is None else qq + s
+
+
+def onsite_population(geo, rho):
+    """getOnsitePopulation, populations.F90:1195-1222: trace of the on-site block of every atom."""
+    qq = np.zeros(geo["nAtom"])
+    for i in range(geo["nAtom"]):
+        n = int(geo["iAtomStart"][i + 1] - geo["iAtomStart"][i])
+        o0 = int(geo["iPair"][i, 0])
+        s = 0.0
+        for k in range(n):
+            s = s + rho[o0 + k * (n + 1)]
+        qq[i] = s
+    return qq
+
+
 def mulliken_per_block(model, geo, over, rho, qq=None, iter_indices=None):
     if qq is None:
         qq = np.zeros((geo["nAtom"], model.mOrb, model.mOrb))

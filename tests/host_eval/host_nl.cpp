@@ -31,6 +31,7 @@ inline double nlFromBits(ull_t u) { double x; std::memcpy(&x, &u, 8); return x; 
 #define NL_FROM_BITS(u) nlFromBits(u)
 
 #include "../../dftbplus_b200/csrc/n2_neighbour_driver.h"
+#include "../../dftbplus_b200/csrc/k4_atom_population.cuh"
 
 using namespace dftbp_b200;
 
@@ -116,6 +117,17 @@ int host_nl_fold(int nAtom, double *coord, const double *latVec, int nThreads, u
   if (!nl::foldSetup(latVec, fp)) return 1;
   HostBackend be{nThreads, std::mt19937(seed)};
   return be.launch(nl::nl_fold, nAtom, nAtom, fp, coord);
+}
+
+// mullikenPerAtom's final sum and getOnsitePopulation (k4_atom_population.cuh)
+void host_pop_atom_sum(int nAtom, int mOrb, const double *qPerOrbital, double *qq, int nThreads, unsigned seed) {
+  HostBackend be{nThreads, std::mt19937(seed)};
+  be.launch(pop::pop_atom_sum, nAtom, nAtom, mOrb, qPerOrbital, qq);
+}
+void host_pop_onsite(int nAtom, int ld, const int *iPair, const int *iAtomStart, const double *rho, double *qq,
+                     int nThreads, unsigned seed) {
+  HostBackend be{nThreads, std::mt19937(seed)};
+  be.launch(pop::pop_onsite, nAtom, nAtom, ld, iPair, iAtomStart, rho, qq);
 }
 
 // the grid the last update used: nb[3], lo[3], invW[3]

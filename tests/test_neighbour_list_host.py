@@ -17,7 +17,7 @@ from dftbplus_b200 import workloads
 SRC = os.path.join(ROOT, "tests", "host_eval", "host_nl.cpp")
 SO = os.path.join(ROOT, "oracle", "_build", "libhostnl.so")
 DEPS = [SRC] + [os.path.join(ROOT, "dftbplus_b200", "csrc", f)
-                for f in ("n2_neighbour_kernels.cuh", "n2_neighbour_driver.h")]
+                for f in ("n2_neighbour_kernels.cuh", "n2_neighbour_driver.h", "emu_kernel.cuh", "k4_atom_population.cuh")]
 
 ARRAYS = ("coords", "species", "img2CentCell", "iCellVec", "nNeighbour", "iNeighbour", "neighDist2",
           "nNeighbourSK", "iPair", "iAtomStart")
@@ -279,3 +279,31 @@ def test_sm100a_code_of_the_distance_kernels_has_no_fused_multiply_add():
         names = [f for f in seen if kernel in f]
         assert names, kernel
         assert all(dfma.get(f, 0) == 0 for f in names), (kernel, dfma)
+
+
+@pytest.mark.parametrize("name", ["h2o", "ce_o", "si2", "fec128"])
+def test_per_atom_population_kernels_equal_the_oracle(name, host):
+    """mullikenPerAtom's sum over orbitals and getOnsitePopulation, host run of
+    k4_atom_population.cuh: bit for bit."""
+    w, sk, geo, model, selfegy = case(name)
+    rng = np.random.default_rng(17)
+    dd, di = ctypes.c_double, ctypes.c_int
+    over = oracle.build_s(model, geo)
+    rho = over * rng.normal(size=over.shape)
+    q_orb = np.ascontiguousarray(oracle.mulliken_per_orbital(model, geo, over, rho))
+    q0 = rng.normal(size=geo["nAtom"])
+    qq = q0.copy()
+    host.host_pop_atom_sum(geo["nAtom"], q_orb.shape[1], _p(q_orb, dd), _p(qq, dd), 13, 2)
+    assert np.array_equal(qq, oracle.mulliken_per_atom(model, geo, over, rho, qq=q0))
+    assert abs(oracle.mulliken_per_atom(model, geo, over, rho).sum() - q_orb.sum()) < 1e-10
+    ipair = np.ascontiguousarray(geo["iPair"], dtype=np.int32)
+    start = np.ascontiguousarray(geo["iAtomStart"], dtype=np.int32)
+    out = np.full(geo["nAtom"], np.nan)
+    host.host_pop_onsite(geo["nAtom"], ipair.shape[1], _p(ipair, di), _p(start, di), _p(rho, dd), _p(out, dd), 29, 3)
+    ref = oracle.onsite_population(geo, rho)
+    assert np.array_equal(out, ref)
+    # independent statement: dense diagonal of the unpacked matrix, atom by atom (gamma point, no self images)
+    if name in ("h2o", "ce_o"):
+        dense = oracle.unpack_hs_real(geo, rho)
+        d = np.diag(dense)
+        assert np.allclose(ref, [d[start[i] - 1:start[i + 1] - 1].sum() for i in range(geo["nAtom"])], atol=1e-13)
