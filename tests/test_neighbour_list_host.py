@@ -307,3 +307,26 @@ def test_per_atom_population_kernels_equal_the_oracle(name, host):
         dense = oracle.unpack_hs_real(geo, rho)
         d = np.diag(dense)
         assert np.allclose(ref, [d[start[i] - 1:start[i + 1] - 1].sum() for i in range(geo["nAtom"])], atol=1e-13)
+
+
+def test_zero_cutoff_and_pairs_exactly_at_the_cutoff(host):
+    """dist2 > cutoff2 skips, so dist2 == cutoff2 is a neighbour (periodic.F90:598); cutoff = 0 leaves
+    every atom with itself only."""
+    cell, rcell = np.zeros((1, 3)), np.zeros((1, 3))
+    chain = np.c_[np.arange(40) * 8.0, np.zeros(40), np.zeros(40)]           # spaced exactly one cutoff apart
+    species0 = np.ones(40, dtype=np.int32)
+    ref = oracle.neighbour_list_full([4], chain, species0, rcell, 8.0, 8.0)
+    got = host_list(host, chain, species0, [4], cell, rcell, 8.0, 8.0)
+    assert_same_list(got, ref)
+    assert got["nNeighbour"].sum() == 39 and np.all(got["neighDist2"][:-1, 1] == 64.0)
+    ref = oracle.neighbour_list_full([4], chain, species0, rcell, 0.0, 0.0)
+    got = host_list(host, chain, species0, [4], cell, rcell, 0.0, 0.0)
+    assert_same_list(got, ref)
+    assert got["mNeigh"] == 0 and got["nAllAtom"] == 40 and got["sparseSize"] == 40 * 16
+    # periodic, images exactly at the cutoff: cubic cell of edge = cutoff, one atom
+    lat = np.eye(3) * 6.0
+    cell, rcell = oracle.cell_translations(lat, 6.0)
+    ref = oracle.neighbour_list_full([1], np.zeros((1, 3)), [1], rcell, 6.0, 6.0)
+    got = host_list(host, np.zeros((1, 3)), [1], [1], cell, rcell, 6.0, 6.0)
+    assert_same_list(got, ref)
+    assert got["nNeighbour"][0] == 6            # the six face neighbours at exactly 6.0
