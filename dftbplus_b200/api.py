@@ -224,10 +224,12 @@ class HotPath:
             g["nOrb"] = int(g["iAtomStart"][-1] - 1)
             g["species0"] = np.asarray(g["species"][:nAtom])
             g["nOrbAtom"] = np.diff(g["iAtomStart"]).astype(np.int32)
+        if not fetch:
+            sp = species0.cpu().numpy() if _is_torch(species0) else species0
+            g["nOrb"] = int(self.nOrbSpecies[np.asarray(sp) - 1].sum())
         if adopt:
             self._ck(self._L.dftbp_b200_adopt_neighbour_list(self._h))
-            if fetch:
-                self.geo = g
+            self.geo = g        # without fetch: the sizes only (enough for the default output buffers)
         return g
 
     def update_coords(self, coords):
