@@ -284,6 +284,18 @@ NL_DEV void heapSortRecords(int n, int *__restrict__ key, double *__restrict__ v
   }
 }
 
+// search_asc_real_geq (math/binarysearch.F90:63-94): last jj in 1..n with xVal - xx(jj) >= -tol, 0 if
+// none; xx1[jj] = xx(jj) (the element before xx(1) is never touched).
+NL_DEV int searchAscRealGeq(int n, const double *__restrict__ xx1, double xVal, double tol) {
+  int jlower = 0, jupper = n;
+  while (jlower < jupper) {
+    const int jcurr = jlower + (jupper - jlower + 1) / 2;
+    if (NL_SUB(xVal, xx1[jcurr]) >= -tol) jlower = jcurr;
+    else jupper = jcurr - 1;
+  }
+  return jlower;
+}
+
 // One thread per atom: rows into the reference's order, row 0 = the atom itself (fillNeighbourArrays),
 // nNeighbourSK for the SK cutoff, and the number of sparse elements / orbitals of the atom.
 NL_KERNEL void nl_sort(int nAtom, int ld, double skCutoff2, const int *__restrict__ nNeighbour,
@@ -303,12 +315,7 @@ NL_KERNEL void nl_sort(int nAtom, int ld, double skCutoff2, const int *__restric
     in[0] = (int)a + 1;
     dn[0] = 0.0;
     // getNrOfNeighbours: search_asc_real_geq(nNeighbour, neighDist2(1:n), cutoff**2, tolSameDist2)
-    int jlower = 0, jupper = n;
-    while (jlower < jupper) {
-      const int jcurr = jlower + (jupper - jlower + 1) / 2;
-      if (NL_SUB(skCutoff2, dn[jcurr]) >= -kTolSameDist2) jlower = jcurr;
-      else jupper = jcurr - 1;
-    }
+    const int jlower = searchAscRealGeq(n, dn, skCutoff2, kTolSameDist2);
     nNeighbourSK[a] = jlower;
     const int nOrb1 = nOrbSpecies[species0[a] - 1];
     int sum = 0;

@@ -807,24 +807,35 @@ int orc_update_neighbour_list(int nAtom, const double *coord0, double cutoff, in
   return 0;
 }
 
-/* getNrOfNeighbours, periodic.F90:1026-1054 -> search_asc_real_geq (math/binarysearch.F90:63-94):
- * bisection for the last entry of neighDist2(1:nNeighbour) with cutoff^2 - entry >= -tolSameDist2.
- * (The bisection is kept literally: the list is only ascending within tolSameDist2.) */
+/* search_asc_real_geq, math/binarysearch.F90:63-94: last jj with xVal - xx(jj) >= -tol on an ascending
+ * array xx(1:n) (0 if none).  xx points at xx(1). */
+int orc_search_asc_real_geq(int n, const double *xx, double xVal, double tol)
+{
+  int jlower = 0, jupper = n, jcurr;
+  while (jlower < jupper) {
+    jcurr = jlower + (jupper - jlower + 1) / 2;
+    if (xVal - xx[jcurr - 1] >= -tol) jlower = jcurr; else jupper = jcurr - 1;
+  }
+  return jlower;
+}
+
+/* index_heap_sort (math/sorting.F90:142-199) for the tests: indx(n) 1-based on return */
+void orc_index_heap_sort(int n, int *indx, const double *array, double tol)
+{
+  index_heap_sort(n, indx, array, tol);
+}
+
+/* getNrOfNeighbours, periodic.F90:1026-1054: search_asc_real_geq(nNeighbour, neighDist2(1:nNeighbour(iAtom),
+ * iAtom), cutoff**2, tolSameDist2).  (The bisection is kept literally: the list is only ascending
+ * within tolSameDist2.) */
 void orc_nr_of_neighbours(int nAtom, const int *nNeighbour, const double *neighDist2, int maxNeigh,
                           double cutoff, int *nNeighbourSK)
 {
   const int ld = maxNeigh + 1;
   const double c2 = cutoff * cutoff;
   int iAtom;
-  for (iAtom = 0; iAtom < nAtom; ++iAtom) {
-    const double *xx = neighDist2 + ld * iAtom; /* xx[j] = neighDist2(j, iAtom), j = 1.. */
-    int jlower = 0, jupper = nNeighbour[iAtom], jcurr;
-    while (jlower < jupper) {
-      jcurr = jlower + (jupper - jlower + 1) / 2;
-      if (c2 - xx[jcurr] >= -tolSameDist2) jlower = jcurr; else jupper = jcurr - 1;
-    }
-    nNeighbourSK[iAtom] = jlower;
-  }
+  for (iAtom = 0; iAtom < nAtom; ++iAtom)
+    nNeighbourSK[iAtom] = orc_search_asc_real_geq(nNeighbour[iAtom], neighDist2 + ld * iAtom + 1, c2, tolSameDist2);
 }
 
 /* getSparseDescriptor, sparse2dense.F90:3617-3662; returns sparseSize.  nOrbAtom(nAtom). */

@@ -130,6 +130,15 @@ void host_pop_onsite(int nAtom, int ld, const int *iPair, const int *iAtomStart,
   be.launch(pop::pop_onsite, nAtom, nAtom, ld, iPair, iAtomStart, rho, qq);
 }
 
+// the product's bisection and record heap sort on their own (reference known-answer tests)
+int host_search_asc_real_geq(int n, const double *xx, double xVal, double tol) {
+  return nl::searchAscRealGeq(n, xx - 1, xVal, tol);
+}
+// keys(n) = 1..n on entry (the index vector), vals(n) the values; sorted in place with the tolerance comparison
+void host_heap_sort_records(int n, int *keys, double *vals, double tol) {
+  nl::heapSortRecords(n, keys - 1, vals - 1, [tol](int, double vA, int, double vB) { return vA < vB - tol; });
+}
+
 // the grid the last update used: nb[3], lo[3], invW[3]
 void host_nl_grid(int *nb, double *lo, double *invW) {
   for (int k = 0; k < 3; ++k) { nb[k] = g_list.grid.p->nb[k]; lo[k] = g_list.grid.p->lo[k]; invW[k] = g_list.grid.p->invW[k]; }

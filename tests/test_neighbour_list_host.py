@@ -330,3 +330,62 @@ def test_zero_cutoff_and_pairs_exactly_at_the_cutoff(host):
     got = host_list(host, np.zeros((1, 3)), [1], [1], cell, rcell, 6.0, 6.0)
     assert_same_list(got, ref)
     assert got["nNeighbour"][0] == 6            # the six face neighbours at exactly 6.0
+
+
+def test_reference_known_answers_of_the_bisection(host):
+    """test/src/dftbp/unit/math/binarysearch.F90, "binarysearch_real_simple" (search_asc_real_geq part):
+    the reference's own data, probes and expected results, for the oracle and the product's routine."""
+    L = oracle.lib()
+    dd = ctypes.c_double
+    tol = float(np.finfo(np.float32).eps)                      # real(epsilon(0.0_rsp), dp)
+    data = np.array([0.1, 0.2, 0.3, 0.4, 0.4, 0.5, 0.6, 0.8])
+    x = [-1.0, 0.1 + tol / 2.0, 10.0, 0.8 - tol / 2.0, 0.4]
+    expect_geq = [0, 1, 8, 8, 5]
+    host.host_search_asc_real_geq.restype = ctypes.c_int
+    L.orc_search_asc_real_geq.restype = ctypes.c_int
+    for xv, e in zip(x, expect_geq):
+        assert L.orc_search_asc_real_geq(len(data), _p(data, dd), dd(xv), dd(tol)) == e
+        assert host.host_search_asc_real_geq(len(data), _p(data, dd), dd(xv), dd(tol)) == e
+    for n in (0, 1):                                           # empty and one-element arrays
+        for xv in (0.05, 0.1, 0.2):
+            assert (host.host_search_asc_real_geq(n, _p(data, dd), dd(xv), dd(tol))
+                    == L.orc_search_asc_real_geq(n, _p(data, dd), dd(xv), dd(tol)) == (1 if n == 1 and xv >= 0.1 else 0))
+
+
+# data of the reference's sorting unit test (test/src/dftbp/unit/math/sorting.F90, from C60_OscWindow):
+# clusters of values equal within tolerance
+SORT_DATA = [
+    1.0009256850962192E-1, 1.0009256850980475E-1, 1.0009256850996931E-1, 1.0009256824902155E-1,
+    1.0009256824920437E-1, 1.0009256824936894E-1, 1.0009256824896715E-1, 1.0009256824914997E-1,
+    1.0009256824931453E-1, 1.0009256824891125E-1, 1.0009256824909407E-1, 1.0009256824925863E-1,
+    6.6042780967860620E-2, 6.6042780968043446E-2, 6.6042780968208009E-2, 9.4447988867716701E-2,
+    9.4447988867874991E-2, 9.4447988868041677E-2, 6.6042780967824899E-2, 6.6042780968007725E-2,
+    6.6042780968172288E-2, 9.4447988867680979E-2, 9.4447988867839269E-2, 9.4447988868005955E-2,
+    6.6042780967797060E-2, 6.6042780967979886E-2, 6.6042780968144449E-2, 9.4447988867653140E-2,
+    9.4447988867811430E-2, 9.4447988867978117E-2, 6.6042780825941200E-2, 6.6042780826124026E-2,
+    6.6042780826288588E-2, 9.4447988725797280E-2, 9.4447988725955570E-2, 9.4447988726122256E-2,
+    6.6042780825940506E-2, 6.6042780826123332E-2, 6.6042780826287895E-2, 9.4447988725796586E-2,
+    9.4447988725954876E-2, 9.4447988726121562E-2]
+
+
+def test_record_heap_sort_equals_the_index_heap_sort_on_the_reference_data(host):
+    """The product sorts records where the reference sorts an index vector (math/sorting.F90:142-199):
+    same permutation on the reference's own test data (near-equal clusters), for several tolerances
+    and for random data with ties; the result is ascending within the tolerance."""
+    L = oracle.lib()
+    dd, di = ctypes.c_double, ctypes.c_int
+    rng = np.random.default_rng(31)
+    sets = [np.array(SORT_DATA), np.round(rng.uniform(0, 1, 200), 2), rng.uniform(0, 1, 77), np.zeros(9),
+            np.array([3.0]), np.array([2.0, 1.0])]
+    for data in sets:
+        for tol in (float(np.finfo(np.float32).eps), 1e-10, 0.0, 1e-3):
+            n = len(data)
+            indx = np.zeros(n, dtype=np.int32)
+            L.orc_index_heap_sort(n, _p(indx, di), _p(np.ascontiguousarray(data), dd), dd(tol))
+            keys = np.arange(1, n + 1, dtype=np.int32)
+            vals = np.array(data, copy=True)
+            host.host_heap_sort_records(n, _p(keys, di), _p(vals, dd), dd(tol))
+            assert np.array_equal(keys, indx)
+            assert np.array_equal(vals, data[indx - 1])
+            assert sorted(keys) == list(range(1, n + 1))
+            assert np.all(vals[:-1] - vals[1:] <= tol)         # never descending by more than the tolerance
