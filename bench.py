@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--workload", default="fec4096")
     ap.add_argument("--no-dense", action="store_true", help="skip the SCC-step (dense) section")
     ap.add_argument("--eigensolve", action="store_true", help="include cuSOLVER at the full workload size")
+    ap.add_argument("--no-n2", action="store_true", help="skip the neighbour-list report (tools/n2_probe.py)")
     return ap.parse_args()
 
 
@@ -533,6 +534,20 @@ def main():
                "sample": "the full workload once (best of 3): buildH0 + buildS + derivative_shift(SCC, %d spins); "
                          "C/OpenMP restatement of the reference CPU path, gcc -O2 -funroll-all-loops -fopenmp" % n_spin}
 
+    # ---- neighbour list on the device, N = 1 only, in a child process -------------
+    # Not part of `value`: a separate report.  Own process = own CUDA context and a timeout, so this
+    # young path can neither hang nor disturb the numbers above (all of which are final here).
+    n2 = None
+    if rank == 0 and world == 1 and not a.no_n2:
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "n2_probe.py"), a.workload],
+                               capture_output=True, text=True, timeout=300)
+            last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            n2 = json.loads(last[-1]) if r.returncode == 0 and last else {
+                "error": "exit %d: %s" % (r.returncode, (r.stderr or r.stdout).strip().splitlines()[-1:])}
+        except Exception as e:  # noqa: BLE001  (timeout included)
+            n2 = {"error": repr(e)}
+
     if rank == 0:
         line = {"metric": "sk_pairs_per_s_h0s_plus_force", "value": value, "unit": "pairs/s", "n_gpus": world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
@@ -543,7 +558,8 @@ def main():
                            "parallelism": "K1 replicated, K5 atom-sharded + all-reduce, (k,spin) round-robin, "
                                           "density-matrix column panels beyond"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-                "roofline_dm": roofline_dm, "kernels": kernels, "scc_step": scc, "cpu_baseline": cpu}
+                "roofline_dm": roofline_dm, "kernels": kernels, "scc_step": scc, "cpu_baseline": cpu,
+                "neighbour_list": n2}
         print(json.dumps(line))
     hp.close()
     if hpw is not hp:
