@@ -475,18 +475,3 @@ def test_full_size_properties_fec4096():
     assert torch.equal(back, xd)
     del sq
     hp.close()
-
-
-@pytest.mark.parametrize("name", ["h2o", "si2", "fec128"])
-def test_k4_per_atom_populations(name, hp_cache):
-    """mullikenPerAtom (populations.F90:68-112) and getOnsitePopulation (:1195-1222), SURVEY 8(a) a15."""
-    w, sk, geo, model, selfegy = case(name)
-    hp = hp_cache(name)
-    rng = np.random.default_rng(23)
-    over = oracle.build_s(model, geo)
-    rho = over * rng.normal(size=over.shape)
-    q0 = rng.normal(size=geo["nAtom"])
-    got = hp.mullikenPerAtom(over, rho, qq=q0.copy())
-    ref = oracle.mulliken_per_atom(model, geo, over, rho, qq=q0)
-    assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
-    assert np.array_equal(hp.getOnsitePopulation(rho), oracle.onsite_population(geo, rho))   # pure gather + ordered sum

@@ -196,3 +196,19 @@ def test_md_step_from_unfolded_device_coordinates(hp_for):
     h, s = hp.buildH0S(sk.selfegy)
     assert_sparse_close(h, oracle.build_h0(model, ogeo, selfegy), what="H0 after fold + device list")
     assert_sparse_close(s, oracle.build_s(model, ogeo), what="S after fold + device list")
+
+
+@pytest.mark.parametrize("name", ["h2o", "si2", "fec128"])
+def test_k4_per_atom_populations(name, hp_for):
+    """mullikenPerAtom (populations.F90:68-112) and getOnsitePopulation (:1195-1222), SURVEY 8(a) a15."""
+    w, sk, geo, model, selfegy = case(name)
+    hp = hp_for(name)
+    hp.set_geometry(geo)
+    rng = np.random.default_rng(23)
+    over = oracle.build_s(model, geo)
+    rho = over * rng.normal(size=over.shape)
+    q0 = rng.normal(size=geo["nAtom"])
+    got = hp.mullikenPerAtom(over, rho, qq=q0.copy())
+    ref = oracle.mulliken_per_atom(model, geo, over, rho, qq=q0)
+    assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+    assert np.array_equal(hp.getOnsitePopulation(rho), oracle.onsite_population(geo, rho))   # pure gather + ordered sum
