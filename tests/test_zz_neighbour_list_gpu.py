@@ -49,6 +49,22 @@ def _rcell(w, cutoff):
     return np.zeros((1, 3)) if w["latvec"] is None else oracle.cell_translations(w["latvec"], cutoff)[1]
 
 
+@pytest.mark.parametrize("name", ["h2o", "si2", "fec128"])
+def test_k4_per_atom_populations(name, hp_for):
+    """mullikenPerAtom (populations.F90:68-112) and getOnsitePopulation (:1195-1222), SURVEY 8(a) a15."""
+    w, sk, geo, model, selfegy = case(name)
+    hp = hp_for(name)
+    hp.set_geometry(geo)
+    rng = np.random.default_rng(23)
+    over = oracle.build_s(model, geo)
+    rho = over * rng.normal(size=over.shape)
+    q0 = rng.normal(size=geo["nAtom"])
+    got = hp.mullikenPerAtom(over, rho, qq=q0.copy())
+    ref = oracle.mulliken_per_atom(model, geo, over, rho, qq=q0)
+    assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+    assert np.array_equal(hp.getOnsitePopulation(rho), oracle.onsite_population(geo, rho))   # pure gather + ordered sum
+
+
 @pytest.mark.parametrize("name", ["h2o", "ce_o", "scan", "si2", "fec128", "si512", "water1002"])
 def test_device_neighbour_list_equals_the_oracle(name, hp_for):
     w, sk, geo, model, selfegy = case(name)
@@ -196,19 +212,3 @@ def test_md_step_from_unfolded_device_coordinates(hp_for):
     h, s = hp.buildH0S(sk.selfegy)
     assert_sparse_close(h, oracle.build_h0(model, ogeo, selfegy), what="H0 after fold + device list")
     assert_sparse_close(s, oracle.build_s(model, ogeo), what="S after fold + device list")
-
-
-@pytest.mark.parametrize("name", ["h2o", "si2", "fec128"])
-def test_k4_per_atom_populations(name, hp_for):
-    """mullikenPerAtom (populations.F90:68-112) and getOnsitePopulation (:1195-1222), SURVEY 8(a) a15."""
-    w, sk, geo, model, selfegy = case(name)
-    hp = hp_for(name)
-    hp.set_geometry(geo)
-    rng = np.random.default_rng(23)
-    over = oracle.build_s(model, geo)
-    rho = over * rng.normal(size=over.shape)
-    q0 = rng.normal(size=geo["nAtom"])
-    got = hp.mullikenPerAtom(over, rho, qq=q0.copy())
-    ref = oracle.mulliken_per_atom(model, geo, over, rho, qq=q0)
-    assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
-    assert np.array_equal(hp.getOnsitePopulation(rho), oracle.onsite_population(geo, rho))   # pure gather + ordered sum
