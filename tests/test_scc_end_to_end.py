@@ -80,29 +80,3 @@ def test_oracle_md_steps_restart_and_momentum():
     mass = np.array([sk.mass[s - 1] for s in w["species0"]])[:, None]
     assert np.abs((mass * r["v"]).sum(axis=0)).max() < 1e-9 * mass.mean()
     assert np.abs(r["forces"].sum(axis=0)).max() < 1e-9
-
-
-@pytest.mark.gpu
-def test_md_steps_device_vs_oracle():
-    """BASELINE config 5's pattern (MD with SCC restart per step) on a 24-atom water cluster, 4 steps:
-    the device arm rebuilds the neighbour list on the GPU every step (update + adopt) and runs the
-    whole chain through the C ABI; identical SCC iteration counts in every step, energies within
-    1e-8 Ha, final positions / velocities within 1e-8."""
-    from dftbplus_b200.api import HotPath
-    w, sk, geo, model, selfegy = _setup("watercluster24")
-    ref = sh.velocity_verlet(_oracle_arm_factory(model, selfegy, w["species0"]), w, sk, model.mOrb, n_steps=4)
-    hp = HotPath(0)
-    try:
-        sk.upload(hp)
-
-        def make(x):
-            g = hp.updateNeighbourListAndSpecies(x, w["species0"], sk.cutoff(), None, adopt=True)
-            return sh.DeviceArm(hp, sk, g), g
-        got = sh.velocity_verlet(make, w, sk, model.mOrb, n_steps=4)
-    finally:
-        hp.close()
-    for a, b in zip(got["steps"], ref["steps"]):
-        assert a["n_iter"] == b["n_iter"] and a["sparseSize"] == b["sparseSize"], (a, b)
-        assert abs(a["energy"] - b["energy"]) < TOL_ENERGY
-    assert np.abs(got["x"] - ref["x"]).max() < 1e-8 and np.abs(got["v"] - ref["v"]).max() < 1e-8
-    assert np.abs(got["forces"] - ref["forces"]).max() < TOL_FORCE

@@ -212,3 +212,30 @@ def test_md_step_from_unfolded_device_coordinates(hp_for):
     h, s = hp.buildH0S(sk.selfegy)
     assert_sparse_close(h, oracle.build_h0(model, ogeo, selfegy), what="H0 after fold + device list")
     assert_sparse_close(s, oracle.build_s(model, ogeo), what="S after fold + device list")
+
+
+def test_md_steps_device_vs_oracle():
+    """BASELINE config 5's pattern (MD with SCC restart per step) on a 24-atom water cluster, 4 steps:
+    the device arm rebuilds the neighbour list on the GPU every step (update + adopt) and runs the
+    whole chain through the C ABI; identical SCC iteration counts in every step, energies within
+    1e-8 Ha, final positions / velocities within 1e-8."""
+    from dftbplus_b200.api import HotPath
+    import scc_harness as sh
+    from test_scc_end_to_end import _setup, _oracle_arm_factory, TOL_ENERGY, TOL_FORCE
+    w, sk, geo, model, selfegy = _setup("watercluster24")
+    ref = sh.velocity_verlet(_oracle_arm_factory(model, selfegy, w["species0"]), w, sk, model.mOrb, n_steps=4)
+    hp = HotPath(0)
+    try:
+        sk.upload(hp)
+
+        def make(x):
+            g = hp.updateNeighbourListAndSpecies(x, w["species0"], sk.cutoff(), None, adopt=True)
+            return sh.DeviceArm(hp, sk, g), g
+        got = sh.velocity_verlet(make, w, sk, model.mOrb, n_steps=4)
+    finally:
+        hp.close()
+    for a, b in zip(got["steps"], ref["steps"]):
+        assert a["n_iter"] == b["n_iter"] and a["sparseSize"] == b["sparseSize"], (a, b)
+        assert abs(a["energy"] - b["energy"]) < TOL_ENERGY
+    assert np.abs(got["x"] - ref["x"]).max() < 1e-8 and np.abs(got["v"] - ref["v"]).max() < 1e-8
+    assert np.abs(got["forces"] - ref["forces"]).max() < TOL_FORCE
