@@ -221,6 +221,9 @@ int dftbp_b200_set_orbitals(dftbp_b200_ctx *ctx, int nSpecies, int mShell, const
       };
       pg.canon1 = canon(sp1);
       pg.canon2 = canon(sp2);
+      // tuning switch: every species pair through the run-time shell loops (22 KB of code for spd
+      // instead of 16-38 KB per canonical case) -- A/B of the instruction-fetch bound
+      if (tuneInt("DFTBP_B200_FORCE_GENERIC", 0)) pg.canon1 = pg.canon2 = -1;
       for (int sh = 0; sh < nShell[sp1]; ++sh)
         pg.shells1 |= (unsigned long long)angShell[sh + mShell * sp1] << (4 * sh);
       for (int sh = 0; sh < nShell[sp2]; ++sh)
