@@ -7,6 +7,10 @@ echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 |
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke_$TAG.log
 echo "== probe (all kernels, device resident)"
 timeout 600 python tools/gpu_probe.py fec4096 --dense --no-k3 2>&1 | tail -1 | tee gpurun_out/probe_$TAG.log
+echo "== A/B: every species pair through the looped evaluator (instruction-fetch experiment, DESIGN section 8)"
+DFTBP_B200_FORCE_GENERIC=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "k1_ or k5_ or derivative or stress" 2>&1 | tail -3 | tee gpurun_out/pytest_generic_$TAG.log
+DFTBP_B200_FORCE_GENERIC=1 timeout 600 python tools/gpu_probe.py fec4096 2>&1 | tail -1 | tee gpurun_out/probe_generic_$TAG.log
+echo "== neighbour list (N2) probe"; timeout 300 python tools/n2_probe.py fec4096 2>&1 | tail -1 | tee gpurun_out/n2_probe_$TAG.log
 echo "== bench"; timeout 900 python bench.py 2>&1 | tail -3 | tee gpurun_out/bench_$TAG.log
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -2 | tee gpurun_out/bench_ref_$TAG.log
 echo "== ncu launch list (bench, pair path only)"
