@@ -389,3 +389,44 @@ def test_record_heap_sort_equals_the_index_heap_sort_on_the_reference_data(host)
             assert np.array_equal(vals, data[indx - 1])
             assert sorted(keys) == list(range(1, n + 1))
             assert np.all(vals[:-1] - vals[1:] <= tol)         # never descending by more than the tolerance
+
+
+def test_randomized_geometries_against_the_oracle(host):
+    """Seeded sweep: triclinic and very flat cells, tiny cells with hundreds of images, sparse clusters,
+    atoms on exact multiples of the bin edge, several list / SK cutoffs and species mixes."""
+    rng = np.random.default_rng(2025)
+    n_case = 0
+    for trial in range(60):
+        n_atom = int(rng.integers(1, 40))
+        n_orb_species = [int(v) for v in rng.choice([1, 4, 9, 16], size=int(rng.integers(1, 4)))]
+        species0 = rng.integers(1, len(n_orb_species) + 1, n_atom).astype(np.int32)
+        cutoff = float(rng.choice([2.5, 4.0, 6.3, 9.0, 11.0]))
+        skc = cutoff if trial % 3 else float(cutoff * rng.uniform(0.3, 1.0))
+        kind = trial % 4
+        if kind == 0:      # cluster, sparse and wide
+            coord0 = rng.uniform(-1, 1, (n_atom, 3)) * rng.choice([3.0, 30.0, 300.0])
+            lat = None
+        elif kind == 1:    # triclinic cell
+            lat = np.diag(rng.uniform(3.0, 14.0, 3)) + rng.uniform(-2.0, 2.0, (3, 3))
+            coord0 = rng.uniform(0, 1, (n_atom, 3)) @ lat
+        elif kind == 2:    # flat / needle cells
+            lat = np.diag(rng.permutation([rng.uniform(2.5, 4.0), rng.uniform(8.0, 12.0), rng.uniform(25.0, 40.0)]))
+            coord0 = rng.uniform(0, 1, (n_atom, 3)) @ lat
+        else:              # atoms on exact multiples of 1.0001 * cutoff (bin edges), non-periodic
+            coord0 = rng.integers(0, 6, (n_atom, 3)) * (1.0001 * cutoff) + rng.choice([0.0, 1e-13, -1e-13], (n_atom, 3))
+            lat = None
+        if lat is None:
+            cell, rcell = np.zeros((1, 3)), np.zeros((1, 3))
+        else:
+            cell, rcell = oracle.cell_translations(lat, cutoff)
+        try:
+            ref = oracle.neighbour_list_full(n_orb_species, coord0, species0, rcell, cutoff, skc)
+        except RuntimeError as e:
+            with pytest.raises(RuntimeError) as got:
+                host_list(host, coord0, species0, n_orb_species, cell, rcell, cutoff, skc, 23, trial)
+            assert str(got.value) == str(e)
+            continue
+        got = host_list(host, coord0, species0, n_orb_species, cell, rcell, cutoff, skc, n_threads=23 + trial, seed=trial)
+        assert_same_list(got, ref)
+        n_case += 1
+    assert n_case > 40
