@@ -430,3 +430,31 @@ def test_randomized_geometries_against_the_oracle(host):
         assert_same_list(got, ref)
         n_case += 1
     assert n_case > 40
+
+
+def test_randomized_many_bin_grids_against_the_oracle(host):
+    """Larger random systems whose grid has many bins per dimension (up to the 32 cap and beyond)."""
+    rng = np.random.default_rng(77)
+    for trial in range(8):
+        n_atom = int(rng.integers(150, 500))
+        cutoff = float(rng.choice([3.0, 5.0, 7.5]))
+        box = rng.uniform(8.0, 45.0, 3) * cutoff / 3.0 * np.array([1.0, 1.0, rng.choice([0.3, 1.0, 4.0])])
+        coord0 = rng.uniform(0, 1, (n_atom, 3)) * box
+        # keep atoms apart (no proximity error): drop the later atom of every pair closer than 0.3
+        keep = np.ones(n_atom, dtype=bool)
+        for i in range(n_atom):
+            if keep[i]:
+                d = np.linalg.norm(coord0[i + 1:] - coord0[i], axis=1)
+                keep[i + 1:] &= d > 0.3
+        coord0 = coord0[keep]
+        species0 = rng.integers(1, 3, len(coord0)).astype(np.int32)
+        periodic = trial % 2 == 0
+        lat = np.diag(box + 0.4) if periodic else None
+        cell, rcell = oracle.cell_translations(lat, cutoff) if periodic else (np.zeros((1, 3)), np.zeros((1, 3)))
+        ref = oracle.neighbour_list_full([4, 9], coord0, species0, rcell, cutoff, cutoff)
+        got = host_list(host, coord0, species0, [4, 9], cell, rcell, cutoff, cutoff, n_threads=97, seed=trial)
+        assert_same_list(got, ref)
+        nb = np.zeros(3, np.int32)
+        lo, inv = np.zeros(3), np.zeros(3)
+        host.host_nl_grid(_p(nb, ctypes.c_int), _p(lo, ctypes.c_double), _p(inv, ctypes.c_double))
+        assert nb.max() >= 3
