@@ -32,6 +32,17 @@ def vectors():
             out[name + "_stress"] = oracle.stress(model, geo, rho, erho, abs(np.linalg.det(w["latvec"])), shift=sh)
             kp = w["kpoints"][3]
             out[name + "_hk"] = oracle.unpack_hs_cplx(geo, h0, kp)
+        # neighbour list / sparse descriptor / fold / per-atom populations
+        cutoff = sk.cutoff()
+        rcell = np.zeros((1, 3)) if w["latvec"] is None else oracle.cell_translations(w["latvec"], cutoff)[1]
+        nl = oracle.neighbour_list_full(sk.n_orb_species, w["coord0"], w["species0"], rcell, cutoff, 0.8 * cutoff)
+        for k in ("coords", "img2CentCell", "iCellVec", "nNeighbour", "nNeighbourSK", "iNeighbour", "neighDist2", "iPair"):
+            out[name + "_nl_" + k] = np.asarray(nl[k], dtype=np.float64)
+        out[name + "_q_atom"] = oracle.mulliken_per_atom(model, geo, s, rho)
+        out[name + "_q_onsite"] = oracle.onsite_population(geo, rho)
+        if w["latvec"] is not None:
+            far = w["coord0"] + np.array([[3.0, -2.0, 5.0], [-1.0, 4.0, 0.0]]) @ np.asarray(w["latvec"]) + 0.123
+            out[name + "_folded"] = oracle.fold_coords_to_cell(far, w["latvec"])
         w1, sk1, geo1, model1, selfegy1 = case(name, 1)
         out[name + "_s_old_interp"] = oracle.build_s(model1, geo1)
     return out
