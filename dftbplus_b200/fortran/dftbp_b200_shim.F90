@@ -197,18 +197,40 @@ contains
     use dftbp_io_message, only : error
     type(TB200Ctx), intent(in) :: ctx
     integer(c_int), intent(in) :: rc
-    character(kind=c_char), pointer :: cmsg(:)
     character(len=512) :: msg
-    integer :: ii
     if (rc == 0) return
-    call c_f_pointer(dftbp_b200_last_error(ctx%h), cmsg, [512])
+    call lastError(ctx, msg)
+    call error("libdftbp_b200: " // trim(msg))
+  end subroutine check
+
+  !> Message of the last failed call
+  subroutine lastError(ctx, msg)
+    type(TB200Ctx), intent(in) :: ctx
+    character(len=*), intent(out) :: msg
+    character(kind=c_char), pointer :: cmsg(:)
+    integer :: ii
+    call c_f_pointer(dftbp_b200_last_error(ctx%h), cmsg, [len(msg)])
     msg = ""
-    do ii = 1, 512
+    do ii = 1, len(msg)
       if (cmsg(ii) == c_null_char) exit
       msg(ii:ii) = cmsg(ii)
     end do
-    call error("libdftbp_b200: " // trim(msg))
-  end subroutine check
+  end subroutine lastError
+
+  !> Non-zero status -> TStatus, for routines that carry one (what @:RAISE_ERROR expands to,
+  !> include/error.fypp:87-90, without the return)
+  subroutine checkStatus(ctx, rc, errStatus, line)
+    use dftbp_common_status, only : TStatus
+    type(TB200Ctx), intent(in) :: ctx
+    integer(c_int), intent(in) :: rc
+    type(TStatus), intent(inout) :: errStatus
+    integer, intent(in) :: line
+    character(len=512) :: msg
+    if (rc == 0) return
+    call lastError(ctx, msg)
+    ! the reference raises code -1 with "Atoms i and j too close together" (periodic.F90:645-648)
+    call errStatus%setError(-1, trim(msg), "dftbp_b200_shim.F90", line)
+  end subroutine checkStatus
 
   !> Once per run, after readSKFiles (dftbplus/parser.F90:3668): flattens TOrbitals + TSlakoCont.
   !> skHam/skOver(iSp1,iSp2) hold the arrays that were passed to SlakoEqGrid_init.
@@ -280,7 +302,8 @@ contains
   !> consumers (repulsive, SCC, dispersion).
   subroutine b200_updateNeighbourListAndSpecies(ctx, coord, species, img2CentCell, iCellVec, neigh,&
       & nAllAtom, coord0, species0, cutoff, skCutoff, cellVec, rCellVec, nNeighbourSK, iSparseStart,&
-      & sparseSize)
+      & sparseSize, errStatus)
+    use dftbp_common_status, only : TStatus
     use dftbp_dftb_periodic, only : TNeighbourList, allocateNeighbourArrays
     type(TB200Ctx), intent(in) :: ctx
     real(dp), allocatable, intent(inout) :: coord(:,:)
@@ -290,11 +313,14 @@ contains
     real(dp), intent(in) :: coord0(:,:), cutoff, skCutoff, cellVec(:,:), rCellVec(:,:)
     integer, intent(in) :: species0(:)
     integer, intent(out) :: nNeighbourSK(:)
+    type(TStatus), intent(out) :: errStatus
     integer :: nAtom, mNeigh
     if (neigh%setExternally) return
     nAtom = size(species0)
-    call check(ctx, dftbp_b200_update_neighbour_list(ctx%h, nAtom, coord0, species0, size(rCellVec, dim=2),&
-        & cellVec, rCellVec, cutoff, skCutoff, nAllAtom, mNeigh, sparseSize))
+    call checkStatus(ctx, dftbp_b200_update_neighbour_list(ctx%h, nAtom, coord0, species0,&
+        & size(rCellVec, dim=2), cellVec, rCellVec, cutoff, skCutoff, nAllAtom, mNeigh, sparseSize), errStatus,&
+        & __LINE__)
+    if (errStatus%hasError()) return   ! @:PROPAGATE_ERROR(errStatus) at the call site, main.F90:2572
     if (allocated(coord)) deallocate(coord, species, img2CentCell, iCellVec)
     allocate(coord(3, nAllAtom), species(nAllAtom), img2CentCell(nAllAtom), iCellVec(nAllAtom))
     ! iNeighbour / neighDist2 are pointers into memory the list owns (periodic.F90:881-922)
