@@ -540,7 +540,7 @@ def main():
     n2 = None
     if rank == 0 and world == 1 and not a.no_n2:
         try:
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "n2_probe.py"), a.workload],
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "n2_probe.py"), a.workload, "--oracle"],
                                capture_output=True, text=True, timeout=300)
             last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
             n2 = json.loads(last[-1]) if r.returncode == 0 and last else {

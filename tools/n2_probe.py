@@ -3,10 +3,11 @@
 line.  bench.py runs this in a child process at the end of the N = 1 run (own CUDA context, timeout),
 so that a problem in this young path can neither hang nor poison the measured one.
 
-Checks need no oracle: the arrays are compared with the host producer the bench already uses
+Checks without the oracle (always): the arrays are compared with the host producer the bench already uses
 (dftbplus_b200/geometry.py; identical unless two neighbours of an atom are equidistant within
 1e-10 bohr^2, where that producer orders by image number), and S built on the adopted device list
-is compared bit for bit with S built on the host-produced geometry."""
+is compared bit for bit with S built on the host-produced geometry.  With --oracle (bench.py passes it) the
+oracle is timed on the same workload as this row's CPU baseline and every array is compared with it."""
 import json
 import os
 import sys
@@ -74,6 +75,20 @@ def main():
     out["S_on_adopted_list_equals_S_on_host_geometry"] = bool(out["arrays_equal_host_producer"]
                                                               and np.array_equal(s_dev, s_host))
     hp.close()
+    if "--oracle" in sys.argv:
+        # the checker and the CPU baseline of this row (bench.py's cpu_baseline leg): the oracle's
+        # restatement of the reference's serial O(nCellVec nAtom^2) scan + heap sorts + descriptor
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import oracle
+        rcell = np.zeros((1, 3)) if lat is None else oracle.cell_translations(lat, cutoff)[1]
+        t0 = time.perf_counter()
+        ref = oracle.neighbour_list_full(sk.n_orb_species, coord0, species0, rcell, cutoff, cutoff)
+        out["cpu_baseline"] = {"value": (time.perf_counter() - t0) * 1e3, "unit": "ms", "cores": 1, "kind": "port",
+                               "sample": "the full workload once: updateNeighbourList + getNrOfNeighboursForAll + "
+                                         "getSparseDescriptor restated in C (serial, like the reference without MPI)"}
+        out["arrays_equal_oracle"] = bool(
+            g["nAllAtom"] == ref["nAllAtom"] and g["mNeigh"] == ref["mNeigh"] and g["sparseSize"] == ref["sparseSize"]
+            and all(np.array_equal(g[k], ref[k]) for k in keys + ("coords", "nNeighbour", "neighDist2")))
     print(json.dumps(out))
 
 
