@@ -458,3 +458,15 @@ def test_randomized_many_bin_grids_against_the_oracle(host):
         lo, inv = np.zeros(3), np.zeros(3)
         host.host_nl_grid(_p(nb, ctypes.c_int), _p(lo, ctypes.c_double), _p(inv, ctypes.c_double))
         assert nb.max() >= 3
+
+
+def test_reference_neighbourdistance_unit_test_on_the_product_kernels(host):
+    """test/src/dftbp/unit/dftb/periodic.F90 "neighbourdistance": two atoms at minNeighDist = 1e-2 bohr
+    are accepted, at minNeighDist**2 the list must fail with "too close" -- for the product's kernels."""
+    cell, rcell = np.zeros((1, 3)), np.zeros((1, 3))
+    min_neigh_dist = 1.0e-2                                     # common/accuracy.F90:69
+    ok = host_list(host, np.array([[0.0, 0, 0], [min_neigh_dist, 0, 0]]), [1, 1], [1], cell, rcell, 1.0, 1.0)
+    assert ok["nNeighbour"].tolist() == [1, 0] and ok["nAllAtom"] == 2 and ok["sparseSize"] == 3
+    assert ok["neighDist2"][0, 1] == min_neigh_dist ** 2
+    with pytest.raises(RuntimeError, match="Atoms 2 and 1 too close together"):
+        host_list(host, np.array([[0.0, 0, 0], [min_neigh_dist ** 2, 0, 0]]), [1, 1], [1], cell, rcell, 1.0, 1.0)
