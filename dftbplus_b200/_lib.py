@@ -29,7 +29,7 @@ SIGNATURES = {
     "dftbp_b200_cell_translations": (c_int, [c_void_p, c_void_p, c_double, c_int, P(c_int), c_void_p, c_void_p]),
     "dftbp_b200_fold_coords_to_cell": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "dftbp_b200_update_neighbour_list": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                                                 c_double, c_double, P(c_int), P(c_int), P(c_int)]),
+                                                 c_double, c_double, c_int, P(c_int), P(c_int), P(c_int)]),
     "dftbp_b200_get_neighbour_list": (c_int, [c_void_p] + [c_void_p] * 10),
     "dftbp_b200_adopt_neighbour_list": (c_int, [c_void_p]),
     "dftbp_b200_update_coords": (c_int, [c_void_p, c_void_p]),

@@ -192,12 +192,13 @@ class HotPath:
         return coord
 
     def updateNeighbourListAndSpecies(self, coord0, species0, cutoff, latvec=None, sk_cutoff=None, adopt=True,
-                                      fetch=True):
+                                      fetch=True, symmetric=False):
         """updateNeighbourListAndSpecies + getNrOfNeighboursForAll + getSparseDescriptor on the device
         (handleCoordinateChange, dftbplus/main.F90:2562-2578).  coord0[nAtom, 3] (host array or CUDA
         tensor), species0[nAtom] 1-based, cutoff = list cutoff, sk_cutoff (default: cutoff).
         adopt: make the result the context's geometry without a host round trip; fetch: return the
-        geometry dict of SURVEY.md section 8.0 (host copies), else only the sizes."""
+        geometry dict of SURVEY.md section 8.0 (host copies), else only the sizes.  symmetric: the reference's
+        symmetric list (for the host's use; never adopted)."""
         sk_cutoff = cutoff if sk_cutoff is None else sk_cutoff
         if latvec is None:
             cell, rcell = np.zeros((1, 3)), np.zeros((1, 3))
@@ -208,7 +209,7 @@ class HotPath:
         nAll, mN, sparse = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         self._ck(self._L.dftbp_b200_update_neighbour_list(
             self._h, nAtom, _ptr(coord0), _ptr(species0), cell.shape[0], _ptr(cell), _ptr(rcell), float(cutoff),
-            float(sk_cutoff), ctypes.byref(nAll), ctypes.byref(mN), ctypes.byref(sparse)))
+            float(sk_cutoff), 1 if symmetric else 0, ctypes.byref(nAll), ctypes.byref(mN), ctypes.byref(sparse)))
         g = dict(nAtom=nAtom, nAllAtom=nAll.value, mNeigh=mN.value, sparseSize=sparse.value, cellVec=cell,
                  rCellVec=rcell, cutoff=cutoff, latvec=latvec)
         if fetch:
@@ -227,7 +228,7 @@ class HotPath:
         if not fetch:
             sp = species0.cpu().numpy() if _is_torch(species0) else species0
             g["nOrb"] = int(self.nOrbSpecies[np.asarray(sp) - 1].sum())
-        if adopt:
+        if adopt and not symmetric:
             self._ck(self._L.dftbp_b200_adopt_neighbour_list(self._h))
             self.geo = g        # without fetch: the sizes only (enough for the default output buffers)
         return g

@@ -57,6 +57,7 @@ struct NeighbourList {
   long long nCand = 0;
   double cutoff = 0.0, skCutoff = 0.0;
   bool valid = false;
+  bool symmetric = false;  // symmetric list: not a geometry for the pair kernels (they expect every pair once)
   int errAtom1 = 0, errAtom2 = 0;  // "Atoms i and j too close together" (periodic.F90:645-648); 0 = none
 
   // inputs kept on the device
@@ -119,18 +120,20 @@ inline bool foldSetup(const double *latVec, FoldParams &fp) {
 // updateNeighbourListAndSpecies + getNrOfNeighboursForAll(skCutoff) + getSparseDescriptor
 // (handleCoordinateChange, dftbplus/main.F90:2562-2578).  coord0(3,nAtom), species0(nAtom),
 // cellVec / rCellVec(3,nCellVec) with the zero vector first, nOrbSpecies on the device.
+// symmetric: the symmetric list (periodic.F90:580-584).
 // Returns 0, or the backend's error code; a too-close pair is reported in nb.errAtom1/2 with
 // nb.valid = false and return value 0.
 template <class Backend>
 int updateNeighbourList(Backend &be, NeighbourList &nb, int nAtom, const double *coord0, const int *species0,
                         const int *dNOrbSpecies, int nCellVec, const double *cellVec, const double *rCellVec,
-                        double cutoff, double skCutoff) {
+                        double cutoff, double skCutoff, bool symmetric = false) {
   nb.valid = false;
   nb.errAtom1 = nb.errAtom2 = 0;
   nb.nAtom = nAtom;
   nb.nCellVec = nCellVec;
   nb.cutoff = cutoff;
   nb.skCutoff = skCutoff;
+  nb.symmetric = symmetric;
   const long long nCand = (long long)nCellVec * nAtom;
   nb.nCand = nCand;
   const double cutoff2 = cutoff * cutoff;  // cutoff2 = cutoff**2, periodic.F90:536
@@ -173,7 +176,7 @@ int updateNeighbourList(Backend &be, NeighbourList &nb, int nAtom, const double 
   NL_TRY(be.fill(nb.flag.p + nCand, 0, sizeof(int)));
   NL_TRY(be.fill(nb.nNeighbour.p, 0, sizeof(int) * nAtom));
   NL_TRY(be.fill(nb.sizes.p, 0, sizeof(int) * kSizeCount));
-  NL_TRY(be.launch(nl_count, nCand, nCand, nAtom, (const double *)nb.coord0.p, (const double *)nb.rCellVec.p,
+  NL_TRY(be.launch(nl_count, nCand, nCand, nAtom, symmetric ? 1 : 0, (const double *)nb.coord0.p, (const double *)nb.rCellVec.p,
                    (const Grid *)nb.grid.p, (const int *)nb.binStart.p, (const int *)nb.binAtom.p,
                    (const double *)nb.binXyz.p, cutoff2, nb.flag.p, nb.nNeighbour.p, nb.box.p + 6));
   NL_TRY(be.scan(nb.flag.p, nb.imgIndex.p, nCand + 1));
@@ -211,7 +214,7 @@ int updateNeighbourList(Backend &be, NeighbourList &nb, int nAtom, const double 
   NL_TRY(be.fill(nb.iNeighbour.p, 0, sizeof(int) * ld * nAtom));    // iNeighbour(:,:) = 0, :565
   NL_TRY(be.fill(nb.neighDist2.p, 0, sizeof(double) * ld * nAtom));  // neighDist2(:,:) = 0.0_dp, :566
   NL_TRY(be.fill(nb.iPair.p, 0, sizeof(int) * ld * nAtom));          // iPair(:,:) = 0, sparse2dense.F90:3648
-  NL_TRY(be.launch(nl_fill, nCand, nCand, nAtom, ld, (const double *)nb.coord0.p, (const int *)nb.species0.p,
+  NL_TRY(be.launch(nl_fill, nCand, nCand, nAtom, symmetric ? 1 : 0, ld, (const double *)nb.coord0.p, (const int *)nb.species0.p,
                    (const double *)nb.rCellVec.p, (const Grid *)nb.grid.p, (const int *)nb.binStart.p,
                    (const int *)nb.binAtom.p, (const double *)nb.binXyz.p, cutoff2, (const int *)nb.flag.p,
                    (const int *)nb.imgIndex.p, nb.coords.p, nb.species.p, nb.img2CentCell.p, nb.iCellVec.p,

@@ -140,10 +140,10 @@ NL_KERNEL void nl_bin_fill(int nAtom, const double *__restrict__ coord0, const G
 
 // Image of atom a1 (0-based) in cell ii (0-based): rr = coord0(:,a1) + rCellVec(:,ii)
 // (periodic.F90:579), and every central atom a2 <= a1 with dist2 = sum((coord0(:,a2) - rr)**2) <=
-// cutoff2 (:597-600) is handed to visit(a2, dist2).  Returns false if the image is too far from the
-// bounding box to have any.
+// cutoff2 (:597-600) is handed to visit(a2, dist2) -- every central atom for the symmetric list
+// (iAtom2End = nAtom).  Returns false if the image is too far from the bounding box to have any.
 template <class F>
-NL_DEV bool visitNeighbours(int ii, int a1, const double *__restrict__ coord0,
+NL_DEV bool visitNeighbours(bool symmetric, int ii, int a1, const double *__restrict__ coord0,
                             const double *__restrict__ rCellVec, const Grid &g,
                             const int *__restrict__ binStart, const int *__restrict__ binAtom,
                             const double *__restrict__ binXyz, double cutoff2, double *rr, F &&visit) {
@@ -164,7 +164,7 @@ NL_DEV bool visitNeighbours(int ii, int a1, const double *__restrict__ coord0,
       const int pEnd = binStart[row + x1 + 1];
       for (int p = binStart[row + x0]; p < pEnd; ++p) {
         const int a2 = binAtom[p];
-        if (a2 > a1) continue;  // non-symmetric list: iAtom2 = 1 .. iAtom1 (:580-584)
+        if (a2 > a1 && !symmetric) continue;  // non-symmetric list: iAtom2 = 1 .. iAtom1 (:580-584)
         const double d0 = NL_SUB(binXyz[3 * p], rr[0]);
         const double d1 = NL_SUB(binXyz[3 * p + 1], rr[1]);
         const double d2 = NL_SUB(binXyz[3 * p + 2], rr[2]);
@@ -177,7 +177,7 @@ NL_DEV bool visitNeighbours(int ii, int a1, const double *__restrict__ coord0,
 }
 
 // pass 1: which candidate images interact at all (flag), neighbours per atom, first too-close pair
-NL_KERNEL void nl_count(long long nCand, int nAtom, const double *__restrict__ coord0,
+NL_KERNEL void nl_count(long long nCand, int nAtom, int symmetric, const double *__restrict__ coord0,
                         const double *__restrict__ rCellVec, const Grid *__restrict__ grid,
                         const int *__restrict__ binStart, const int *__restrict__ binAtom,
                         const double *__restrict__ binXyz, double cutoff2, int *__restrict__ flag,
@@ -187,7 +187,7 @@ NL_KERNEL void nl_count(long long nCand, int nAtom, const double *__restrict__ c
     const int ii = (int)(c / nAtom), a1 = (int)(c - (long long)ii * nAtom);
     double rr[3];
     int found = 0;
-    visitNeighbours(ii, a1, coord0, rCellVec, g, binStart, binAtom, binXyz, cutoff2, rr,
+    visitNeighbours(symmetric != 0, ii, a1, coord0, rCellVec, g, binStart, binAtom, binXyz, cutoff2, rr,
                     [&](int a2, double dist2) {
                       found = 1;  // the image is appended before the proximity check (:604-614)
                       if (dist2 < kMinNeighDist2) {
@@ -211,7 +211,7 @@ NL_KERNEL void nl_sizes(long long nCand, int nAtom, const int *__restrict__ imgI
 
 // pass 2: image arrays (coord, img2CentCell, iCellVec, species; periodic.F90:610-613, :437) and the
 // unsorted neighbour rows (slots in arrival order; nl_sort puts them into the reference's order)
-NL_KERNEL void nl_fill(long long nCand, int nAtom, int ld, const double *__restrict__ coord0,
+NL_KERNEL void nl_fill(long long nCand, int nAtom, int symmetric, int ld, const double *__restrict__ coord0,
                        const int *__restrict__ species0, const double *__restrict__ rCellVec,
                        const Grid *__restrict__ grid, const int *__restrict__ binStart,
                        const int *__restrict__ binAtom, const double *__restrict__ binXyz, double cutoff2,
@@ -225,7 +225,7 @@ NL_KERNEL void nl_fill(long long nCand, int nAtom, int ld, const double *__restr
     const int ii = (int)(c / nAtom), a1 = (int)(c - (long long)ii * nAtom);
     const int img = imgIndex[c];
     double rr[3];
-    visitNeighbours(ii, a1, coord0, rCellVec, g, binStart, binAtom, binXyz, cutoff2, rr,
+    visitNeighbours(symmetric != 0, ii, a1, coord0, rCellVec, g, binStart, binAtom, binXyz, cutoff2, rr,
                     [&](int a2, double dist2) {
                       if (dist2 < kMinNeighDist2) return;
                       const int slot = atomicAdd(cursor + a2, 1) + 1;

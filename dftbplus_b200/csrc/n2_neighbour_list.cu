@@ -153,7 +153,7 @@ int dftbp_b200_fold_coords_to_cell(dftbp_b200_ctx *ctx, int nAtom, double *coord
 
 int dftbp_b200_update_neighbour_list(dftbp_b200_ctx *ctx, int nAtom, const double *coord0, const int *species0,
                                      int nCellVec, const double *cellVec, const double *rCellVec, double cutoff,
-                                     double skCutoff, int *nAllAtom, int *mNeigh, int *sparseSize) {
+                                     double skCutoff, int symmetric, int *nAllAtom, int *mNeigh, int *sparseSize) {
   if (!ctx) return DFTBP_B200_EINVAL;
   DFTBP_CHECK(ctx, ctx->nSpecies > 0, "update_neighbour_list: call set_orbitals first");
   DFTBP_CHECK(ctx, nAtom > 0 && nCellVec >= 1 && coord0 && species0 && cellVec && rCellVec,
@@ -175,7 +175,7 @@ int dftbp_b200_update_neighbour_list(dftbp_b200_ctx *ctx, int nAtom, const doubl
   be.scanTemp = st->scanTemp;
   ScopedTimer timer(ctx, kTimerNeighbourList);
   const int rc = nl::updateNeighbourList(be, st->list, nAtom, coord0, species0, ctx->dNOrbSpecies, nCellVec, cellVec,
-                                         rCellVec, cutoff, skCutoff);
+                                         rCellVec, cutoff, skCutoff, symmetric != 0);
   st->scanTemp = be.scanTemp;
   // host inputs were staged with asynchronous copies: they have been consumed once the stream is idle
   // (updateNeighbourList ends with a blocking read-back unless it failed early)
@@ -219,6 +219,7 @@ int dftbp_b200_adopt_neighbour_list(dftbp_b200_ctx *ctx) {
   DFTBP_CHECK(ctx, ctx->neighbourState && stateOf(ctx)->list.valid,
               "adopt_neighbour_list: no neighbour list (call update_neighbour_list first)");
   const nl::NeighbourList &L = stateOf(ctx)->list;
+  DFTBP_CHECK(ctx, !L.symmetric, "adopt_neighbour_list: a symmetric list is not a geometry for the pair kernels");
   DFTBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   // device pointers: set_geometry copies them device-to-device and reads what it validates
   return dftbp_b200_set_geometry(ctx, L.nAtom, L.nAllAtom, L.mNeigh, L.coords.p, L.species.p, L.img2CentCell.p,

@@ -165,13 +165,14 @@ module dftbp_b200_shim
       real(c_double), intent(in) :: latVec(3, 3)
     end function
     integer(c_int) function dftbp_b200_update_neighbour_list(ctx, nAtom, coord0, species0, nCellVec, cellVec,&
-        & rCellVec, cutoff, skCutoff, nAllAtom, mNeigh, sparseSize) bind(C)
+        & rCellVec, cutoff, skCutoff, symmetric, nAllAtom, mNeigh, sparseSize) bind(C)
       import :: c_ptr, c_int, c_double
       type(c_ptr), value :: ctx
       integer(c_int), value :: nAtom, nCellVec
       real(c_double), intent(in) :: coord0(*), cellVec(*), rCellVec(*)
       integer(c_int), intent(in) :: species0(*)
       real(c_double), value :: cutoff, skCutoff
+      integer(c_int), value :: symmetric
       integer(c_int), intent(out) :: nAllAtom, mNeigh, sparseSize
     end function
     integer(c_int) function dftbp_b200_get_neighbour_list(ctx, coords, species, img2CentCell, iCellVec,&
@@ -318,7 +319,8 @@ contains
     if (neigh%setExternally) return
     nAtom = size(species0)
     call checkStatus(ctx, dftbp_b200_update_neighbour_list(ctx%h, nAtom, coord0, species0,&
-        & size(rCellVec, dim=2), cellVec, rCellVec, cutoff, skCutoff, nAllAtom, mNeigh, sparseSize), errStatus,&
+        & size(rCellVec, dim=2), cellVec, rCellVec, cutoff, skCutoff, 0_c_int, nAllAtom, mNeigh, sparseSize),&
+        & errStatus,&
         & __LINE__)
     if (errStatus%hasError()) return   ! @:PROPAGATE_ERROR(errStatus) at the call site, main.F90:2572
     if (allocated(coord)) deallocate(coord, species, img2CentCell, iCellVec)

@@ -122,8 +122,7 @@ int dftbp_b200_cell_translations(const double *latVec, const double *recVec2p, d
  * reference's invert33 and operation order.  Cluster geometries are not folded (no call). */
 int dftbp_b200_fold_coords_to_cell(dftbp_b200_ctx *ctx, int nAtom, double *coord, const double *latVec);
 
-/* updateNeighbourListAndSpecies (dftb/periodic.F90:380-440, 446-694; non-symmetric list, no helical
- * boundary conditions) + getNrOfNeighboursForAll(skCutoff) (:996-1054) + getSparseDescriptor
+/* updateNeighbourListAndSpecies (dftb/periodic.F90:380-440, 446-694; no helical boundary conditions) + getNrOfNeighboursForAll(skCutoff) (:996-1054) + getSparseDescriptor
  * (dftb/sparse2dense.F90:3617-3662), as called by handleCoordinateChange
  * (dftbplus/main.F90:2562-2578), with a cell list on the device instead of the reference's
  * O(nCellVec nAtom^2) scan.  coord0(3, nAtom) (already folded into the cell by the caller),
@@ -132,11 +131,14 @@ int dftbp_b200_fold_coords_to_cell(dftbp_b200_ctx *ctx, int nAtom, double *coord
  * order (including the order inside shells of equal distance, which fixes the iPair layout) and
  * all values are the reference's.  The result stays on the device; the sizes the caller needs to
  * allocate its copies come back in nAllAtom, mNeigh (= maxval(nNeighbour)) and sparseSize.
+ * symmetric = 0: the non-symmetric list every routine of this library expects; != 0: the reference's
+ * `symmetric` option (iAtom2 runs over all atoms, :580-584; symNeighbourList of the hybrid functionals,
+ * dftbplus/main.F90:2587) for the host's use -- such a list cannot be adopted.
  * Atoms closer than minNeighDist: DFTBP_B200_EGEOMETRY, message as the reference's. */
 int dftbp_b200_update_neighbour_list(dftbp_b200_ctx *ctx, int nAtom, const double *coord0,
                                      const int *species0, int nCellVec, const double *cellVec,
                                      const double *rCellVec, double cutoff, double skCutoff,
-                                     int *nAllAtom, int *mNeigh, int *sparseSize);
+                                     int symmetric, int *nAllAtom, int *mNeigh, int *sparseSize);
 
 /* Copies of the arrays of the last update (any pointer may be NULL; host or device memory):
  * coords(3, nAllAtom), species / img2CentCell / iCellVec(nAllAtom), nNeighbour(nAtom),

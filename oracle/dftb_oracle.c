@@ -730,7 +730,7 @@ int orc_cell_translations(const double *latVec, const double *recVec2p, double c
   return n;
 }
 
-/* updateNeighbourList (non-symmetric half list), periodic.F90:446-694, followed by
+/* updateNeighbourList (isSymm = 0: the non-symmetric half list; 1: the symmetric one), periodic.F90:446-694, followed by
  * getNrOfNeighboursForAll (:996-1054) for the SK cutoff.  Outputs sized by the caller:
  *   coord(3,maxAllAtom), img2CentCell/iCellVec(maxAllAtom), iNeighbour(0:maxNeigh, nAtom),
  *   neighDist2(0:maxNeigh, nAtom).
@@ -739,7 +739,7 @@ int orc_cell_translations(const double *latVec, const double *recVec2p, double c
 int orc_update_neighbour_list(int nAtom, const double *coord0, double cutoff, int nCellVec,
                               const double *rCellVec, int maxAllAtom, int maxNeigh, double *coord,
                               int *img2CentCell, int *iCellVec, int *nNeighbour, int *iNeighbour,
-                              double *neighDist2, int *nAllAtomOut, int *mNeighOut, int *pairError)
+                              double *neighDist2, int *nAllAtomOut, int *mNeighOut, int *pairError, int isSymm)
 {
   const double cutoff2 = cutoff * cutoff;
   const int ld = maxNeigh + 1;
@@ -755,7 +755,8 @@ int orc_update_neighbour_list(int nAtom, const double *coord0, double cutoff, in
     for (iAtom1 = 1; iAtom1 <= nAtom; ++iAtom1) {
       double rr[3];
       for (k = 0; k < 3; ++k) rr[k] = coord0[k + 3 * (iAtom1 - 1)] + rCell[k];
-      for (iAtom2 = 1; iAtom2 <= iAtom1; ++iAtom2) {
+      /* iAtom2End = nAtom for the symmetric list, iAtom1 otherwise (periodic.F90:580-584) */
+      for (iAtom2 = 1; iAtom2 <= (isSymm ? nAtom : iAtom1); ++iAtom2) {
         double d0 = coord0[0 + 3 * (iAtom2 - 1)] - rr[0];
         double d1 = coord0[1 + 3 * (iAtom2 - 1)] - rr[1];
         double d2 = coord0[2 + 3 * (iAtom2 - 1)] - rr[2];

@@ -176,7 +176,7 @@ def neighbour_geometry(model, coord0, species0, latvec=None, cutoff=None):
         rc = L.orc_update_neighbour_list(nAtom, _d(coord0), ctypes.c_double(cutoff), cell.shape[0],
                                          _d(rcell), maxAll, maxNeigh, _d(coord), _i(img), _i(icv),
                                          _i(nN), _i(iN), _d(d2), ctypes.byref(nAll),
-                                         ctypes.byref(mN), _i(perr))
+                                         ctypes.byref(mN), _i(perr), 0)
         if rc == -1:
             raise RuntimeError("Atoms %d and %d too close together" % (perr[0], perr[1]))
         if rc == 0:
@@ -214,11 +214,13 @@ def fold_coords_to_cell(coord0, latvec):
     return c
 
 
-def neighbour_list_full(n_orb_species, coord0, species0, rcell, cutoff, sk_cutoff):
+def neighbour_list_full(n_orb_species, coord0, species0, rcell, cutoff, sk_cutoff, symmetric=False):
     """updateNeighbourList(cutoff) + getNrOfNeighboursForAll(sk_cutoff) + getSparseDescriptor with
     the arrays exactly as the reference holds them (rows of iNeighbour / neighDist2 / iPair are
     0:mNeigh with mNeigh = maxval(nNeighbour) of the LIST cutoff).  rcell[nCellVec,3], zero vector
-    first.  Raises RuntimeError("Atoms i and j too close together") like the reference."""
+    first.  symmetric: the symmetric list (every image within reach of ANY central atom, all pairs in both
+    directions; symNeighbourList of the hybrid functionals, main.F90:2587).  Raises
+    RuntimeError("Atoms i and j too close together") like the reference."""
     L = lib()
     coord0 = np.ascontiguousarray(coord0, dtype=np.float64)
     species0 = np.ascontiguousarray(species0, dtype=np.int32)
@@ -238,7 +240,7 @@ def neighbour_list_full(n_orb_species, coord0, species0, rcell, cutoff, sk_cutof
         rc = L.orc_update_neighbour_list(nAtom, _d(coord0), ctypes.c_double(cutoff), rcell.shape[0],
                                          _d(rcell), maxAll, maxNeigh, _d(coord), _i(img), _i(icv),
                                          _i(nN), _i(iN), _d(d2), ctypes.byref(nAll),
-                                         ctypes.byref(mN), _i(perr))
+                                         ctypes.byref(mN), _i(perr), 1 if symmetric else 0)
         if rc == -1:
             raise RuntimeError("Atoms %d and %d too close together" % (perr[0], perr[1]))
         if rc == 0 and maxNeigh == mN.value:

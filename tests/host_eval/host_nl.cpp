@@ -83,13 +83,13 @@ extern "C" {
 // out[0..7] = nAllAtom, mNeigh, sparseSize, nOrb, errAtom1, errAtom2, valid, launches
 int host_nl_update(int nAtom, const double *coord0, const int *species0, int nSpecies, const int *nOrbSpecies,
                    int nCellVec, const double *cellVec, const double *rCellVec, double cutoff, double skCutoff,
-                   int nThreads, unsigned seed, int *out) {
+                   int nThreads, unsigned seed, int symmetric, int *out) {
   HostBackend be{nThreads, std::mt19937(seed)};
   std::free(g_nOrbSpecies);
   g_nOrbSpecies = (int *)std::malloc(sizeof(int) * nSpecies);
   std::memcpy(g_nOrbSpecies, nOrbSpecies, sizeof(int) * nSpecies);
   const int rc = nl::updateNeighbourList(be, g_list, nAtom, coord0, species0, g_nOrbSpecies, nCellVec, cellVec,
-                                         rCellVec, cutoff, skCutoff);
+                                         rCellVec, cutoff, skCutoff, symmetric != 0);
   out[0] = g_list.nAllAtom; out[1] = g_list.mNeigh; out[2] = g_list.sparseSize; out[3] = g_list.nOrb;
   out[4] = g_list.errAtom1; out[5] = g_list.errAtom2; out[6] = g_list.valid ? 1 : 0; out[7] = (int)be.launches;
   return rc;

@@ -35,7 +35,8 @@ def _p(a, t):
     return a.ctypes.data_as(ctypes.POINTER(t))
 
 
-def host_list(lib, coord0, species0, n_orb_species, cell, rcell, cutoff, sk_cutoff, n_threads=61, seed=1):
+def host_list(lib, coord0, species0, n_orb_species, cell, rcell, cutoff, sk_cutoff, n_threads=61, seed=1,
+              symmetric=False):
     coord0 = np.ascontiguousarray(coord0, dtype=np.float64)
     species0 = np.ascontiguousarray(species0, dtype=np.int32)
     nos = np.ascontiguousarray(n_orb_species, dtype=np.int32)
@@ -45,7 +46,8 @@ def host_list(lib, coord0, species0, n_orb_species, cell, rcell, cutoff, sk_cuto
     out = np.zeros(8, dtype=np.int32)
     di, dd = ctypes.c_int, ctypes.c_double
     rc = lib.host_nl_update(n, _p(coord0, dd), _p(species0, di), len(nos), _p(nos, di), cell.shape[0], _p(cell, dd),
-                            _p(rcell, dd), dd(cutoff), dd(sk_cutoff), n_threads, ctypes.c_uint(seed), _p(out, di))
+                            _p(rcell, dd), dd(cutoff), dd(sk_cutoff), n_threads, ctypes.c_uint(seed),
+                            1 if symmetric else 0, _p(out, di))
     assert rc == 0
     nAll, mN, sparse, nOrb, e1, e2, valid, launches = (int(v) for v in out)
     if e1:
@@ -470,3 +472,21 @@ def test_reference_neighbourdistance_unit_test_on_the_product_kernels(host):
     assert ok["neighDist2"][0, 1] == min_neigh_dist ** 2
     with pytest.raises(RuntimeError, match="Atoms 2 and 1 too close together"):
         host_list(host, np.array([[0.0, 0, 0], [min_neigh_dist ** 2, 0, 0]]), [1, 1], [1], cell, rcell, 1.0, 1.0)
+
+
+@pytest.mark.parametrize("name", ["ce_o", "si2", "fec128"])
+def test_symmetric_list_equals_the_oracle(name, host):
+    """The reference's `symmetric` option (periodic.F90:580-584; symNeighbourList of the hybrid
+    functionals): iAtom2 over all atoms -- every pair appears in both rows, more images are numbered."""
+    w, sk, geo, model, selfegy = case(name)
+    cutoff = sk.cutoff()
+    cell, rcell = cells_of(w, cutoff)
+    ref = oracle.neighbour_list_full(sk.n_orb_species, w["coord0"], w["species0"], rcell, cutoff, cutoff, symmetric=True)
+    got = host_list(host, w["coord0"], w["species0"], sk.n_orb_species, cell, rcell, cutoff, cutoff, symmetric=True)
+    assert_same_list(got, ref)
+    half = oracle.neighbour_list_full(sk.n_orb_species, w["coord0"], w["species0"], rcell, cutoff, cutoff)
+    n_self = int(sum((half["img2CentCell"][half["iNeighbour"][i, 1:half["nNeighbour"][i] + 1] - 1] == i + 1).sum()
+                     for i in range(half["nAtom"])))
+    # every off-site pair twice; images of the atom itself appear once per direction in the half list already
+    assert got["nNeighbour"].sum() == 2 * (half["nNeighbour"].sum() - n_self) + n_self
+    assert got["nAllAtom"] >= half["nAllAtom"]

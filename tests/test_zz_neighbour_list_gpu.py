@@ -239,3 +239,21 @@ def test_md_steps_device_vs_oracle():
         assert abs(a["energy"] - b["energy"]) < TOL_ENERGY
     assert np.abs(got["x"] - ref["x"]).max() < 1e-8 and np.abs(got["v"] - ref["v"]).max() < 1e-8
     assert np.abs(got["forces"] - ref["forces"]).max() < TOL_FORCE
+
+
+def test_symmetric_list_on_the_device(hp_for):
+    """The reference's `symmetric` option (periodic.F90:580-584): equal to the oracle; such a list is for
+    the host's use and cannot become the geometry of the pair kernels."""
+    from dftbplus_b200.api import DftbB200Error
+    w, sk, geo, model, selfegy = case("fec128")
+    hp = hp_for("fec128")
+    cutoff = sk.cutoff()
+    ref = oracle.neighbour_list_full(sk.n_orb_species, w["coord0"], w["species0"], _rcell(w, cutoff), cutoff, cutoff,
+                                     symmetric=True)
+    got = hp.updateNeighbourListAndSpecies(w["coord0"], w["species0"], cutoff, w["latvec"], symmetric=True)
+    assert_same_list(got, ref)
+    with pytest.raises(DftbB200Error):
+        hp._ck(hp._L.dftbp_b200_adopt_neighbour_list(hp._h))
+    # the context takes a normal list again afterwards
+    got = hp.updateNeighbourListAndSpecies(w["coord0"], w["species0"], cutoff, w["latvec"], adopt=True)
+    assert got["sparseSize"] == geo["sparseSize"]
