@@ -76,6 +76,9 @@ struct NeighbourList {
   // the lists
   Buf<double> coords, neighDist2;
   Buf<int> species, img2CentCell, iCellVec, iNeighbour, iPair;
+  // scratch rows of the ordering step: arrival order, ascending image number; rows with near-ties
+  Buf<int> arriveKey, byKeyKey, rowHasTies;
+  Buf<double> arriveDist, byKeyDist;
 
   template <class Backend>
   void free(Backend &be) {
@@ -84,7 +87,8 @@ struct NeighbourList {
     imgIndex.free(be); nNeighbour.free(be); cursor.free(be); nNeighbourSK.free(be); atomSize.free(be);
     atomOffset.free(be); orbCount.free(be); orbOffset.free(be); iAtomStart.free(be); sizes.free(be);
     coords.free(be); neighDist2.free(be); species.free(be); img2CentCell.free(be); iCellVec.free(be);
-    iNeighbour.free(be); iPair.free(be);
+    iNeighbour.free(be); iPair.free(be); arriveKey.free(be); byKeyKey.free(be); rowHasTies.free(be);
+    arriveDist.free(be); byKeyDist.free(be);
     valid = false;
   }
 };
@@ -204,6 +208,11 @@ int updateNeighbourList(Backend &be, NeighbourList &nb, int nAtom, const double 
   NL_TRY(nb.iNeighbour.ensure(be, (size_t)ld * nAtom));
   NL_TRY(nb.neighDist2.ensure(be, (size_t)ld * nAtom));
   NL_TRY(nb.iPair.ensure(be, (size_t)ld * nAtom));
+  NL_TRY(nb.arriveKey.ensure(be, (size_t)ld * nAtom));
+  NL_TRY(nb.arriveDist.ensure(be, (size_t)ld * nAtom));
+  NL_TRY(nb.byKeyKey.ensure(be, (size_t)ld * nAtom));
+  NL_TRY(nb.byKeyDist.ensure(be, (size_t)ld * nAtom));
+  NL_TRY(nb.rowHasTies.ensure(be, nAtom));
   NL_TRY(nb.nNeighbourSK.ensure(be, nAtom));
   NL_TRY(nb.atomSize.ensure(be, (size_t)nAtom + 1));
   NL_TRY(nb.atomOffset.ensure(be, (size_t)nAtom + 1));
@@ -218,13 +227,18 @@ int updateNeighbourList(Backend &be, NeighbourList &nb, int nAtom, const double 
                    (const double *)nb.rCellVec.p, (const Grid *)nb.grid.p, (const int *)nb.binStart.p,
                    (const int *)nb.binAtom.p, (const double *)nb.binXyz.p, cutoff2, (const int *)nb.flag.p,
                    (const int *)nb.imgIndex.p, nb.coords.p, nb.species.p, nb.img2CentCell.p, nb.iCellVec.p,
-                   nb.cursor.p, nb.iNeighbour.p, nb.neighDist2.p));
+                   nb.cursor.p, nb.arriveKey.p, nb.arriveDist.p));
 
   // order of the rows, nNeighbourSK, sparse descriptor
   NL_TRY(be.fill(nb.atomSize.p + nAtom, 0, sizeof(int)));
   NL_TRY(be.fill(nb.orbCount.p + nAtom, 0, sizeof(int)));
+  NL_TRY(be.fill(nb.rowHasTies.p, 0, sizeof(int) * nAtom));
+  NL_TRY(be.launch(nl_rank, (long long)ld * nAtom, nAtom, ld, (const int *)nb.nNeighbour.p,
+                   (const int *)nb.arriveKey.p, (const double *)nb.arriveDist.p, nb.byKeyKey.p, nb.byKeyDist.p,
+                   nb.iNeighbour.p, nb.neighDist2.p, nb.rowHasTies.p));
   NL_TRY(be.launch(nl_sort, nAtom, nAtom, ld, skCutoff * skCutoff, (const int *)nb.nNeighbour.p,
-                   (const int *)nb.species0.p, dNOrbSpecies, (const int *)nb.img2CentCell.p, nb.iNeighbour.p,
+                   (const int *)nb.species0.p, dNOrbSpecies, (const int *)nb.img2CentCell.p,
+                   (const int *)nb.rowHasTies.p, nb.byKeyKey.p, nb.byKeyDist.p, nb.iNeighbour.p,
                    nb.neighDist2.p, nb.nNeighbourSK.p, nb.atomSize.p, nb.orbCount.p));
   NL_TRY(be.scan(nb.atomSize.p, nb.atomOffset.p, (long long)nAtom + 1));
   NL_TRY(be.scan(nb.orbCount.p, nb.orbOffset.p, (long long)nAtom + 1));

@@ -210,7 +210,7 @@ NL_KERNEL void nl_sizes(long long nCand, int nAtom, const int *__restrict__ imgI
 }
 
 // pass 2: image arrays (coord, img2CentCell, iCellVec, species; periodic.F90:610-613, :437) and the
-// unsorted neighbour rows (slots in arrival order; nl_sort puts them into the reference's order)
+// unsorted neighbour rows (slots in arrival order; nl_rank / nl_sort put them into the reference's order)
 NL_KERNEL void nl_fill(long long nCand, int nAtom, int symmetric, int ld, const double *__restrict__ coord0,
                        const int *__restrict__ species0, const double *__restrict__ rCellVec,
                        const Grid *__restrict__ grid, const int *__restrict__ binStart,
@@ -296,22 +296,71 @@ NL_DEV int searchAscRealGeq(int n, const double *__restrict__ xx1, double xVal, 
   return jlower;
 }
 
-// One thread per atom: rows into the reference's order, row 0 = the atom itself (fillNeighbourArrays),
-// nNeighbourSK for the SK cutoff, and the number of sparse elements / orbitals of the atom.
+// One thread per row entry: position of the entry (a) in ascending image number -- the order in which
+// the reference's loops append, i.e. the INPUT order of its sort -- and (b) in ascending distance.
+// If no two distances of a row are within tolSameDist2 of each other, the reference's comparison
+// a < b - tol coincides with a < b on that row (a < b excludes b < a - tol, so a < b - tol must hold),
+// which is a strict total order: every correct comparison sort, the reference's heap sort included,
+// returns the one ascending sequence, and the rank by distance IS the final position.  Rows with a
+// near-tie (perfect lattices) are flagged and go through the reference's algorithm in nl_sort; their
+// by-distance slots written here are overwritten there.
+//   arrive*:  rows in arrival order (nl_fill)         byKey*: rows in ascending image number
+//   iNeighbour / neighDist2: rows in ascending distance (final for rows without ties)
+NL_KERNEL void nl_rank(int nAtom, int ld, const int *__restrict__ nNeighbour, const int *__restrict__ arriveKey,
+                       const double *__restrict__ arriveDist, int *__restrict__ byKeyKey,
+                       double *__restrict__ byKeyDist, int *__restrict__ iNeighbour,
+                       double *__restrict__ neighDist2, int *__restrict__ rowHasTies) {
+  const long long total = (long long)ld * nAtom;
+  for (long long e = NL_TID; e < total; e += NL_STRIDE) {
+    const int a = (int)(e / ld), k = (int)(e - (long long)a * ld);
+    const int n = nNeighbour[a];
+    if (k == 0 || k > n) continue;
+    const int *__restrict__ keys = arriveKey + (long long)ld * a;
+    const double *__restrict__ dist = arriveDist + (long long)ld * a;
+    const int myKey = keys[k];
+    const double myDist = dist[k];
+    const double myDistMinusTol = NL_SUB(myDist, kTolSameDist2);
+    int rankKey = 0, rankDist = 0;
+    bool tie = false;
+    for (int j = 1; j <= n; ++j) {
+      if (j == k) continue;
+      if (keys[j] < myKey) ++rankKey;
+      const double dj = dist[j];
+      if (dj < myDistMinusTol) ++rankDist;                          // dj  <  myDist - tol
+      else if (!(myDist < NL_SUB(dj, kTolSameDist2))) tie = true;  // neither is smaller by more than tol
+    }
+    const long long row = (long long)ld * a;
+    byKeyKey[row + 1 + rankKey] = myKey;
+    byKeyDist[row + 1 + rankKey] = myDist;
+    iNeighbour[row + 1 + rankDist] = myKey;
+    neighDist2[row + 1 + rankDist] = myDist;
+    if (tie) rowHasTies[a] = 1;  // every writer stores the same value
+  }
+}
+
+// One thread per atom: rows with near-ties through the reference's heap sort (input = the row in
+// ascending image number), row 0 = the atom itself (fillNeighbourArrays), nNeighbourSK for the SK
+// cutoff, and the number of sparse elements / orbitals of the atom.
 NL_KERNEL void nl_sort(int nAtom, int ld, double skCutoff2, const int *__restrict__ nNeighbour,
                        const int *__restrict__ species0, const int *__restrict__ nOrbSpecies,
-                       const int *__restrict__ img2CentCell, int *__restrict__ iNeighbour,
+                       const int *__restrict__ img2CentCell, const int *__restrict__ rowHasTies,
+                       int *__restrict__ byKeyKey, double *__restrict__ byKeyDist, int *__restrict__ iNeighbour,
                        double *__restrict__ neighDist2, int *__restrict__ nNeighbourSK,
                        int *__restrict__ atomSize, int *__restrict__ orbCount) {
   for (long long a = NL_TID; a < nAtom; a += NL_STRIDE) {
     int *in = iNeighbour + (long long)ld * a;      // in[1..n]
     double *dn = neighDist2 + (long long)ld * a;
     const int n = nNeighbour[a];
-    // (1) the order the reference's loops append in: ascending image number (plain comparison)
-    heapSortRecords(n, in, dn, [](int kA, double, int kB, double) { return kA < kB; });
-    // (2) index_heap_sort(indx, neighDist2(1:nn1, iAtom1), tolSameDist2), periodic.F90:677-680
-    heapSortRecords(n, in, dn,
-                    [](int, double vA, int, double vB) { return vA < NL_SUB(vB, kTolSameDist2); });
+    if (rowHasTies[a]) {
+      int *kk = byKeyKey + (long long)ld * a;
+      double *kd = byKeyDist + (long long)ld * a;
+      // index_heap_sort(indx, neighDist2(1:nn1, iAtom1), tolSameDist2), periodic.F90:677-680
+      heapSortRecords(n, kk, kd, [](int, double vA, int, double vB) { return vA < NL_SUB(vB, kTolSameDist2); });
+      for (int k = 1; k <= n; ++k) {
+        in[k] = kk[k];
+        dn[k] = kd[k];
+      }
+    }
     in[0] = (int)a + 1;
     dn[0] = 0.0;
     // getNrOfNeighbours: search_asc_real_geq(nNeighbour, neighDist2(1:n), cutoff**2, tolSameDist2)

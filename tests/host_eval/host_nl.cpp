@@ -139,6 +139,14 @@ void host_heap_sort_records(int n, int *keys, double *vals, double tol) {
   nl::heapSortRecords(n, keys - 1, vals - 1, [tol](int, double vA, int, double vB) { return vA < vB - tol; });
 }
 
+// rows of the last update that went through the reference's heap sort (near-ties) / all rows
+void host_nl_tie_rows(int *out) {
+  int t = 0;
+  for (int a = 0; a < g_list.nAtom; ++a) t += g_list.rowHasTies.p[a] != 0;
+  out[0] = t;
+  out[1] = g_list.nAtom;
+}
+
 // the grid the last update used: nb[3], lo[3], invW[3]
 void host_nl_grid(int *nb, double *lo, double *invW) {
   for (int k = 0; k < 3; ++k) { nb[k] = g_list.grid.p->nb[k]; lo[k] = g_list.grid.p->lo[k]; invW[k] = g_list.grid.p->invW[k]; }

@@ -277,7 +277,7 @@ def test_sm100a_code_of_the_distance_kernels_has_no_fused_multiply_add():
             seen.add(fn)
         elif "DFMA" in line and fn:
             dfma[fn] = dfma.get(fn, 0) + 1
-    for kernel in ("nl_count", "nl_fill", "nl_sort", "nl_fold"):
+    for kernel in ("nl_count", "nl_fill", "nl_rank", "nl_sort", "nl_fold"):
         names = [f for f in seen if kernel in f]
         assert names, kernel
         assert all(dfma.get(f, 0) == 0 for f in names), (kernel, dfma)
@@ -490,3 +490,33 @@ def test_symmetric_list_equals_the_oracle(name, host):
     # every off-site pair twice; images of the atom itself appear once per direction in the half list already
     assert got["nNeighbour"].sum() == 2 * (half["nNeighbour"].sum() - n_self) + n_self
     assert got["nAllAtom"] >= half["nAllAtom"]
+
+
+def test_both_ordering_paths_are_exercised(host):
+    """Rows without near-ties are placed by rank (nl_rank), rows with near-ties go through the reference's
+    heap sort (nl_sort): jittered systems take the first path only, perfect lattices the second."""
+    out = np.zeros(2, dtype=np.int32)
+    w, sk, geo, model, selfegy = case("fec128")
+    cutoff = sk.cutoff()
+    cell, rcell = oracle.cell_translations(w["latvec"], cutoff)
+    host_list(host, w["coord0"], w["species0"], sk.n_orb_species, cell, rcell, cutoff, cutoff)
+    host.host_nl_tie_rows(_p(out, ctypes.c_int))
+    assert out[0] == 0 and out[1] == 128
+    w, sk, geo, model, selfegy = case("si512")                 # unjittered diamond: every shell is a tie
+    cutoff = sk.cutoff()
+    cell, rcell = oracle.cell_translations(w["latvec"], cutoff)
+    host_list(host, w["coord0"], w["species0"], sk.n_orb_species, cell, rcell, cutoff, cutoff)
+    host.host_nl_tie_rows(_p(out, ctypes.c_int))
+    assert out[0] > 400
+    # one tied pair in an otherwise generic cluster: only the rows that see both atoms at equal distance
+    rng = np.random.default_rng(3)
+    coord0 = rng.uniform(0, 12, (30, 3))
+    coord0[7] = coord0[0] + [2.0, 0.0, 0.0]
+    coord0[9] = coord0[0] + [0.0, 2.0, 0.0]                     # atoms 8 and 10 equidistant from atom 1
+    species0 = np.ones(30, dtype=np.int32)
+    cell, rcell = np.zeros((1, 3)), np.zeros((1, 3))
+    ref = oracle.neighbour_list_full([4], coord0, species0, rcell, 9.0, 9.0)
+    got = host_list(host, coord0, species0, [4], cell, rcell, 9.0, 9.0)
+    assert_same_list(got, ref)
+    host.host_nl_tie_rows(_p(out, ctypes.c_int))
+    assert 1 <= out[0] <= 3
