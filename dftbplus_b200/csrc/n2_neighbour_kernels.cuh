@@ -12,9 +12,11 @@
 //   * image numbers  = exclusive prefix sum over c of "has a neighbour iAtom2 <= iAtom1 in range";
 //   * the unsorted neighbour rows are in ascending image number (the loops append them that way);
 //   * the error pair is the first (c, iAtom2) in loop order that is closer than minNeighDist.
-// The distance sort is the reference's heap sort with its tolerance comparison and its exact
-// control flow (the comparison is not transitive, so only the same algorithm on the same input
-// order gives the same order inside shells of equal distance, hence the same iPair layout).
+// The distance order: the reference's heap sort compares with a tolerance, which is not transitive,
+// so inside shells of equal distance only the same algorithm on the same input order gives the same
+// order (and with it the same iPair layout).  Rows without two distances within the tolerance have
+// a unique order and are placed by counting, fully in parallel (nl_rank); rows with near-ties run
+// the reference's heap sort with its exact control flow (nl_sort).
 //
 // The kernels are grid-stride loops with atomics only (no shared memory, no warp collectives), so
 // that tests/host_eval/host_nl.cpp can run the very same source on the CPU, one emulated thread
