@@ -50,6 +50,9 @@ struct Buf {
     if (rc_ != 0) return rc_; \
   } while (0)
 
+// rows up to this length are ordered by counting (n^2 per row, fully parallel), longer ones by heap sorts
+constexpr int kRankMaxDefault = 192;
+
 // Result of one update: sizes, and the device arrays of the reference's neighbour list / sparse
 // descriptor in the reference's layout (1-based values, iPair 0-based, ld = mNeigh + 1).
 struct NeighbourList {
@@ -130,7 +133,7 @@ inline bool foldSetup(const double *latVec, FoldParams &fp) {
 template <class Backend>
 int updateNeighbourList(Backend &be, NeighbourList &nb, int nAtom, const double *coord0, const int *species0,
                         const int *dNOrbSpecies, int nCellVec, const double *cellVec, const double *rCellVec,
-                        double cutoff, double skCutoff, bool symmetric = false) {
+                        double cutoff, double skCutoff, bool symmetric = false, int rankMax = kRankMaxDefault) {
   nb.valid = false;
   nb.errAtom1 = nb.errAtom2 = 0;
   nb.nAtom = nAtom;
@@ -233,12 +236,13 @@ int updateNeighbourList(Backend &be, NeighbourList &nb, int nAtom, const double 
   NL_TRY(be.fill(nb.atomSize.p + nAtom, 0, sizeof(int)));
   NL_TRY(be.fill(nb.orbCount.p + nAtom, 0, sizeof(int)));
   NL_TRY(be.fill(nb.rowHasTies.p, 0, sizeof(int) * nAtom));
-  NL_TRY(be.launch(nl_rank, (long long)ld * nAtom, nAtom, ld, (const int *)nb.nNeighbour.p,
+  NL_TRY(be.launch(nl_rank, (long long)ld * nAtom, nAtom, ld, rankMax, (const int *)nb.nNeighbour.p,
                    (const int *)nb.arriveKey.p, (const double *)nb.arriveDist.p, nb.byKeyKey.p, nb.byKeyDist.p,
                    nb.iNeighbour.p, nb.neighDist2.p, nb.rowHasTies.p));
   NL_TRY(be.launch(nl_sort, nAtom, nAtom, ld, skCutoff * skCutoff, (const int *)nb.nNeighbour.p,
                    (const int *)nb.species0.p, dNOrbSpecies, (const int *)nb.img2CentCell.p,
-                   (const int *)nb.rowHasTies.p, nb.byKeyKey.p, nb.byKeyDist.p, nb.iNeighbour.p,
+                   (const int *)nb.rowHasTies.p, (const int *)nb.arriveKey.p, (const double *)nb.arriveDist.p,
+                   nb.byKeyKey.p, nb.byKeyDist.p, nb.iNeighbour.p,
                    nb.neighDist2.p, nb.nNeighbourSK.p, nb.atomSize.p, nb.orbCount.p));
   NL_TRY(be.scan(nb.atomSize.p, nb.atomOffset.p, (long long)nAtom + 1));
   NL_TRY(be.scan(nb.orbCount.p, nb.orbOffset.p, (long long)nAtom + 1));

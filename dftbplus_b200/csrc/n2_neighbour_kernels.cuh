@@ -308,7 +308,9 @@ NL_DEV int searchAscRealGeq(int n, const double *__restrict__ xx1, double xVal, 
 // by-distance slots written here are overwritten there.
 //   arrive*:  rows in arrival order (nl_fill)         byKey*: rows in ascending image number
 //   iNeighbour / neighDist2: rows in ascending distance (final for rows without ties)
-NL_KERNEL void nl_rank(int nAtom, int ld, const int *__restrict__ nNeighbour, const int *__restrict__ arriveKey,
+// Rows longer than rankMax skip the counting (quadratic in the row length) and take the n log n path of
+// nl_sort from the arrival order (flag 2).
+NL_KERNEL void nl_rank(int nAtom, int ld, int rankMax, const int *__restrict__ nNeighbour, const int *__restrict__ arriveKey,
                        const double *__restrict__ arriveDist, int *__restrict__ byKeyKey,
                        double *__restrict__ byKeyDist, int *__restrict__ iNeighbour,
                        double *__restrict__ neighDist2, int *__restrict__ rowHasTies) {
@@ -317,6 +319,10 @@ NL_KERNEL void nl_rank(int nAtom, int ld, const int *__restrict__ nNeighbour, co
     const int a = (int)(e / ld), k = (int)(e - (long long)a * ld);
     const int n = nNeighbour[a];
     if (k == 0 || k > n) continue;
+    if (n > rankMax) {
+      if (k == 1) rowHasTies[a] = 2;
+      continue;
+    }
     const int *__restrict__ keys = arriveKey + (long long)ld * a;
     const double *__restrict__ dist = arriveDist + (long long)ld * a;
     const int myKey = keys[k];
@@ -346,6 +352,7 @@ NL_KERNEL void nl_rank(int nAtom, int ld, const int *__restrict__ nNeighbour, co
 NL_KERNEL void nl_sort(int nAtom, int ld, double skCutoff2, const int *__restrict__ nNeighbour,
                        const int *__restrict__ species0, const int *__restrict__ nOrbSpecies,
                        const int *__restrict__ img2CentCell, const int *__restrict__ rowHasTies,
+                       const int *__restrict__ arriveKey, const double *__restrict__ arriveDist,
                        int *__restrict__ byKeyKey, double *__restrict__ byKeyDist, int *__restrict__ iNeighbour,
                        double *__restrict__ neighDist2, int *__restrict__ nNeighbourSK,
                        int *__restrict__ atomSize, int *__restrict__ orbCount) {
@@ -356,6 +363,13 @@ NL_KERNEL void nl_sort(int nAtom, int ld, double skCutoff2, const int *__restric
     if (rowHasTies[a]) {
       int *kk = byKeyKey + (long long)ld * a;
       double *kd = byKeyDist + (long long)ld * a;
+      if (rowHasTies[a] == 2) {  // long row: not ranked; ascending image number by a plain heap sort
+        for (int k = 1; k <= n; ++k) {
+          kk[k] = arriveKey[(long long)ld * a + k];
+          kd[k] = arriveDist[(long long)ld * a + k];
+        }
+        heapSortRecords(n, kk, kd, [](int kA, double, int kB, double) { return kA < kB; });
+      }
       // index_heap_sort(indx, neighDist2(1:nn1, iAtom1), tolSameDist2), periodic.F90:677-680
       heapSortRecords(n, kk, kd, [](int, double vA, int, double vB) { return vA < NL_SUB(vB, kTolSameDist2); });
       for (int k = 1; k <= n; ++k) {

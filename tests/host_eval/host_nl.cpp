@@ -74,6 +74,7 @@ struct HostBackend {
 };
 
 nl::NeighbourList g_list;
+int g_rankMax = nl::kRankMaxDefault;
 int *g_nOrbSpecies = nullptr;
 
 }  // namespace
@@ -89,7 +90,7 @@ int host_nl_update(int nAtom, const double *coord0, const int *species0, int nSp
   g_nOrbSpecies = (int *)std::malloc(sizeof(int) * nSpecies);
   std::memcpy(g_nOrbSpecies, nOrbSpecies, sizeof(int) * nSpecies);
   const int rc = nl::updateNeighbourList(be, g_list, nAtom, coord0, species0, g_nOrbSpecies, nCellVec, cellVec,
-                                         rCellVec, cutoff, skCutoff, symmetric != 0);
+                                         rCellVec, cutoff, skCutoff, symmetric != 0, g_rankMax);
   out[0] = g_list.nAllAtom; out[1] = g_list.mNeigh; out[2] = g_list.sparseSize; out[3] = g_list.nOrb;
   out[4] = g_list.errAtom1; out[5] = g_list.errAtom2; out[6] = g_list.valid ? 1 : 0; out[7] = (int)be.launches;
   return rc;
@@ -138,6 +139,9 @@ int host_search_asc_real_geq(int n, const double *xx, double xVal, double tol) {
 void host_heap_sort_records(int n, int *keys, double *vals, double tol) {
   nl::heapSortRecords(n, keys - 1, vals - 1, [tol](int, double vA, int, double vB) { return vA < vB - tol; });
 }
+
+// test hook: row length above which the counting is skipped (default nl::kRankMaxDefault)
+void host_nl_set_rank_max(int v) { g_rankMax = v > 0 ? v : nl::kRankMaxDefault; }
 
 // rows of the last update that went through the reference's heap sort (near-ties) / all rows
 void host_nl_tie_rows(int *out) {

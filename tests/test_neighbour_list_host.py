@@ -520,3 +520,29 @@ def test_both_ordering_paths_are_exercised(host):
     assert_same_list(got, ref)
     host.host_nl_tie_rows(_p(out, ctypes.c_int))
     assert 1 <= out[0] <= 3
+
+
+def test_long_rows_skip_the_counting(host):
+    """Rows longer than rankMax are ordered by the two heap sorts (n log n) instead of by counting (n^2):
+    same result whatever the threshold."""
+    w, sk, geo, model, selfegy = case("fec128")
+    cutoff = 14.5
+    cell, rcell = oracle.cell_translations(w["latvec"], cutoff)
+    ref = oracle.neighbour_list_full(sk.n_orb_species, w["coord0"], w["species0"], rcell, cutoff, sk.cutoff())
+    out = np.zeros(2, dtype=np.int32)
+    try:
+        for rank_max, some_long in ((1, True), (40, True), (100000, False)):
+            host.host_nl_set_rank_max(rank_max)
+            got = host_list(host, w["coord0"], w["species0"], sk.n_orb_species, cell, rcell, cutoff, sk.cutoff())
+            assert_same_list(got, ref)
+            host.host_nl_tie_rows(_p(out, ctypes.c_int))
+            assert (out[0] > 0) == some_long
+        # a perfect lattice with a low threshold: long rows and tie rows together
+        w2, sk2, geo2, model2, selfegy2 = case("si512")
+        c2, r2 = oracle.cell_translations(w2["latvec"], sk2.cutoff())
+        ref2 = oracle.neighbour_list_full(sk2.n_orb_species, w2["coord0"], w2["species0"], r2, sk2.cutoff(), sk2.cutoff())
+        host.host_nl_set_rank_max(20)
+        assert_same_list(host_list(host, w2["coord0"], w2["species0"], sk2.n_orb_species, c2, r2, sk2.cutoff(),
+                                   sk2.cutoff()), ref2)
+    finally:
+        host.host_nl_set_rank_max(0)
