@@ -122,7 +122,8 @@ int dftbp_b200_cell_translations(const double *latVec, const double *recVec2p, d
  * reference's invert33 and operation order.  Cluster geometries are not folded (no call). */
 int dftbp_b200_fold_coords_to_cell(dftbp_b200_ctx *ctx, int nAtom, double *coord, const double *latVec);
 
-/* updateNeighbourListAndSpecies (dftb/periodic.F90:380-440, 446-694; no helical boundary conditions) + getNrOfNeighboursForAll(skCutoff) (:996-1054) + getSparseDescriptor
+/* updateNeighbourListAndSpecies (dftb/periodic.F90:380-440, 446-694; no helical boundary
+ * conditions) + getNrOfNeighboursForAll(skCutoff) (:996-1054) + getSparseDescriptor
  * (dftb/sparse2dense.F90:3617-3662), as called by handleCoordinateChange
  * (dftbplus/main.F90:2562-2578), with a cell list on the device instead of the reference's
  * O(nCellVec nAtom^2) scan.  coord0(3, nAtom) (already folded into the cell by the caller),
@@ -148,7 +149,9 @@ int dftbp_b200_get_neighbour_list(dftbp_b200_ctx *ctx, double *coords, int *spec
                                   int *nNeighbourSK, int *iPair, int *iAtomStart);
 
 /* Make the list of the last update the context's geometry (what dftbp_b200_set_geometry does
- * with caller arrays), without the round trip through the host. */
+ * with caller arrays): the arrays are taken from the device copies, the caller passes nothing.
+ * (The work lists / block descriptors of set_geometry are still formed on the host from a read-back
+ * of the index arrays.) */
 int dftbp_b200_adopt_neighbour_list(dftbp_b200_ctx *ctx);
 
 /* Coordinates only (same neighbour map): geometry steps that keep the list, and finite
