@@ -11,7 +11,9 @@
  * machine translation of the reference's own closed forms (oracle/gen_ref_sk.py ->
  * oracle/_ref/, golden vectors in tests/golden/sk_rot_golden.npz); chunk-range logic is
  * checked against the expectations of the reference's own unit test
- * (test/src/dftbp/unit/common/schedule.F90).
+ * (test/src/dftbp/unit/common/schedule.F90); the bisection search_asc_real_geq against the known
+ * answers of unit/math/binarysearch.F90; the neighbour list's proximity rule against
+ * unit/dftb/periodic.F90 ("neighbourdistance").
  *
  * Every routine cites the reference file:line (relative to /root/reference/src/dftbp/)
  * whose arithmetic and loop order it follows.  Arrays use the reference's layout:
