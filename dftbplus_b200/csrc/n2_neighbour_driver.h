@@ -72,7 +72,7 @@ struct NeighbourList {
   Buf<int> binCount, binStart, binAtom;
   Buf<double> binXyz;
   // candidate images
-  Buf<int> flag, imgIndex;
+  Buf<int> flag, imgIndex, activeList, nActive;
   // per atom
   Buf<int> nNeighbour, cursor, nNeighbourSK, atomSize, atomOffset, orbCount, orbOffset, iAtomStart;
   Buf<int> sizes;
@@ -87,7 +87,7 @@ struct NeighbourList {
   void free(Backend &be) {
     coord0.free(be); rCellVec.free(be); cellVec.free(be); species0.free(be); box.free(be); grid.free(be);
     binCount.free(be); binStart.free(be); binAtom.free(be); binXyz.free(be); flag.free(be);
-    imgIndex.free(be); nNeighbour.free(be); cursor.free(be); nNeighbourSK.free(be); atomSize.free(be);
+    imgIndex.free(be); activeList.free(be); nActive.free(be); nNeighbour.free(be); cursor.free(be); nNeighbourSK.free(be); atomSize.free(be);
     atomOffset.free(be); orbCount.free(be); orbOffset.free(be); iAtomStart.free(be); sizes.free(be);
     coords.free(be); neighDist2.free(be); species.free(be); img2CentCell.free(be); iCellVec.free(be);
     iNeighbour.free(be); iPair.free(be); arriveKey.free(be); byKeyKey.free(be); rowHasTies.free(be);
@@ -180,10 +180,16 @@ int updateNeighbourList(Backend &be, NeighbourList &nb, int nAtom, const double 
   NL_TRY(nb.nNeighbour.ensure(be, nAtom));
   NL_TRY(nb.cursor.ensure(be, nAtom));
   NL_TRY(nb.sizes.ensure(be, kSizeCount));
-  NL_TRY(be.fill(nb.flag.p + nCand, 0, sizeof(int)));
+  NL_TRY(nb.activeList.ensure(be, (size_t)nCand));
+  NL_TRY(nb.nActive.ensure(be, 1));
+  NL_TRY(be.fill(nb.nActive.p, 0, sizeof(int)));
+  NL_TRY(be.launch(nl_active, nCand, nCand, nAtom, (const double *)nb.coord0.p, (const double *)nb.rCellVec.p,
+                   (const Grid *)nb.grid.p, nb.nActive.p, nb.activeList.p));
+  NL_TRY(be.fill(nb.flag.p, 0, sizeof(int) * ((size_t)nCand + 1)));
   NL_TRY(be.fill(nb.nNeighbour.p, 0, sizeof(int) * nAtom));
   NL_TRY(be.fill(nb.sizes.p, 0, sizeof(int) * kSizeCount));
-  NL_TRY(be.launch(nl_count, nCand, nCand, nAtom, symmetric ? 1 : 0, (const double *)nb.coord0.p, (const double *)nb.rCellVec.p,
+  NL_TRY(be.launch(nl_count, nCand, (const int *)nb.nActive.p, (const int *)nb.activeList.p, nAtom,
+                   symmetric ? 1 : 0, (const double *)nb.coord0.p, (const double *)nb.rCellVec.p,
                    (const Grid *)nb.grid.p, (const int *)nb.binStart.p, (const int *)nb.binAtom.p,
                    (const double *)nb.binXyz.p, cutoff2, nb.flag.p, nb.nNeighbour.p, nb.box.p + 6));
   NL_TRY(be.scan(nb.flag.p, nb.imgIndex.p, nCand + 1));
@@ -226,7 +232,8 @@ int updateNeighbourList(Backend &be, NeighbourList &nb, int nAtom, const double 
   NL_TRY(be.fill(nb.iNeighbour.p, 0, sizeof(int) * ld * nAtom));    // iNeighbour(:,:) = 0, :565
   NL_TRY(be.fill(nb.neighDist2.p, 0, sizeof(double) * ld * nAtom));  // neighDist2(:,:) = 0.0_dp, :566
   NL_TRY(be.fill(nb.iPair.p, 0, sizeof(int) * ld * nAtom));          // iPair(:,:) = 0, sparse2dense.F90:3648
-  NL_TRY(be.launch(nl_fill, nCand, nCand, nAtom, symmetric ? 1 : 0, ld, (const double *)nb.coord0.p, (const int *)nb.species0.p,
+  NL_TRY(be.launch(nl_fill, nCand, (const int *)nb.nActive.p, (const int *)nb.activeList.p, nAtom,
+                   symmetric ? 1 : 0, ld, (const double *)nb.coord0.p, (const int *)nb.species0.p,
                    (const double *)nb.rCellVec.p, (const Grid *)nb.grid.p, (const int *)nb.binStart.p,
                    (const int *)nb.binAtom.p, (const double *)nb.binXyz.p, cutoff2, (const int *)nb.flag.p,
                    (const int *)nb.imgIndex.p, nb.coords.p, nb.species.p, nb.img2CentCell.p, nb.iCellVec.p,

@@ -140,6 +140,37 @@ NL_KERNEL void nl_bin_fill(int nAtom, const double *__restrict__ coord0, const G
   }
 }
 
+// rr = coord0(:,a1) + rCellVec(:,ii) (periodic.F90:579) and its (unclamped) bin coordinates; false if
+// the image is farther than one bin edge (>= cutoff) from the bounding box of the central cell, i.e.
+// cannot have a neighbour there.
+NL_DEV bool imageInReach(int ii, int a1, const double *__restrict__ coord0, const double *__restrict__ rCellVec,
+                         const Grid &g, double *rr, int *ip) {
+  for (int k = 0; k < 3; ++k) {
+    rr[k] = NL_ADD(coord0[3 * a1 + k], rCellVec[3 * ii + k]);
+    const double f = (rr[k] - g.lo[k]) * g.invW[k];
+    if (!(f >= -1.0 && f < (double)(g.nb[k] + 1))) return false;
+    ip[k] = (int)floor(f);
+  }
+  return true;
+}
+
+// Stream compaction of the candidate images: with a cell larger than the cutoff only the images in
+// a shell of one bin edge around the central cell can interact (fec4096: 9.5 k of 110 k), and they are
+// scattered over the candidate numbers -- looping over all candidates would leave one or two
+// active lanes per warp in the search kernels.  The order of the list is arbitrary (atomic cursor);
+// everything downstream is keyed by the candidate number itself.
+NL_KERNEL void nl_active(long long nCand, int nAtom, const double *__restrict__ coord0,
+                         const double *__restrict__ rCellVec, const Grid *__restrict__ grid,
+                         int *__restrict__ nActive, int *__restrict__ activeList) {
+  const Grid g = *grid;
+  for (long long c = NL_TID; c < nCand; c += NL_STRIDE) {
+    const int ii = (int)(c / nAtom), a1 = (int)(c - (long long)ii * nAtom);
+    double rr[3];
+    int ip[3];
+    if (imageInReach(ii, a1, coord0, rCellVec, g, rr, ip)) activeList[atomicAdd(nActive, 1)] = (int)c;
+  }
+}
+
 // Image of atom a1 (0-based) in cell ii (0-based): rr = coord0(:,a1) + rCellVec(:,ii)
 // (periodic.F90:579), and every central atom a2 <= a1 with dist2 = sum((coord0(:,a2) - rr)**2) <=
 // cutoff2 (:597-600) is handed to visit(a2, dist2) -- every central atom for the symmetric list
@@ -150,12 +181,7 @@ NL_DEV bool visitNeighbours(bool symmetric, int ii, int a1, const double *__rest
                             const int *__restrict__ binStart, const int *__restrict__ binAtom,
                             const double *__restrict__ binXyz, double cutoff2, double *rr, F &&visit) {
   int ip[3];
-  for (int k = 0; k < 3; ++k) {
-    rr[k] = NL_ADD(coord0[3 * a1 + k], rCellVec[3 * ii + k]);
-    const double f = (rr[k] - g.lo[k]) * g.invW[k];
-    if (!(f >= -1.0 && f < (double)(g.nb[k] + 1))) return false;  // farther than one bin edge (>= cutoff) from the box
-    ip[k] = (int)floor(f);
-  }
+  if (!imageInReach(ii, a1, coord0, rCellVec, g, rr, ip)) return false;
   const int z0 = ip[2] - 1 < 0 ? 0 : ip[2] - 1, z1 = ip[2] + 1 > g.nb[2] - 1 ? g.nb[2] - 1 : ip[2] + 1;
   const int y0 = ip[1] - 1 < 0 ? 0 : ip[1] - 1, y1 = ip[1] + 1 > g.nb[1] - 1 ? g.nb[1] - 1 : ip[1] + 1;
   const int x0 = ip[0] - 1 < 0 ? 0 : ip[0] - 1, x1 = ip[0] + 1 > g.nb[0] - 1 ? g.nb[0] - 1 : ip[0] + 1;
@@ -179,13 +205,17 @@ NL_DEV bool visitNeighbours(bool symmetric, int ii, int a1, const double *__rest
 }
 
 // pass 1: which candidate images interact at all (flag), neighbours per atom, first too-close pair
-NL_KERNEL void nl_count(long long nCand, int nAtom, int symmetric, const double *__restrict__ coord0,
+// (flag is zero-filled by the caller: candidates that are not in the list stay 0)
+NL_KERNEL void nl_count(const int *__restrict__ nActive, const int *__restrict__ activeList, int nAtom,
+                        int symmetric, const double *__restrict__ coord0,
                         const double *__restrict__ rCellVec, const Grid *__restrict__ grid,
                         const int *__restrict__ binStart, const int *__restrict__ binAtom,
                         const double *__restrict__ binXyz, double cutoff2, int *__restrict__ flag,
                         int *__restrict__ nNeighbour, ull *__restrict__ firstError) {
   const Grid g = *grid;
-  for (long long c = NL_TID; c < nCand; c += NL_STRIDE) {
+  const long long nAct = *nActive;
+  for (long long i = NL_TID; i < nAct; i += NL_STRIDE) {
+    const long long c = activeList[i];
     const int ii = (int)(c / nAtom), a1 = (int)(c - (long long)ii * nAtom);
     double rr[3];
     int found = 0;
@@ -213,7 +243,8 @@ NL_KERNEL void nl_sizes(long long nCand, int nAtom, const int *__restrict__ imgI
 
 // pass 2: image arrays (coord, img2CentCell, iCellVec, species; periodic.F90:610-613, :437) and the
 // unsorted neighbour rows (slots in arrival order; nl_rank / nl_sort put them into the reference's order)
-NL_KERNEL void nl_fill(long long nCand, int nAtom, int symmetric, int ld, const double *__restrict__ coord0,
+NL_KERNEL void nl_fill(const int *__restrict__ nActive, const int *__restrict__ activeList, int nAtom,
+                       int symmetric, int ld, const double *__restrict__ coord0,
                        const int *__restrict__ species0, const double *__restrict__ rCellVec,
                        const Grid *__restrict__ grid, const int *__restrict__ binStart,
                        const int *__restrict__ binAtom, const double *__restrict__ binXyz, double cutoff2,
@@ -222,7 +253,9 @@ NL_KERNEL void nl_fill(long long nCand, int nAtom, int symmetric, int ld, const 
                        int *__restrict__ iCellVec, int *__restrict__ cursor, int *__restrict__ iNeighbour,
                        double *__restrict__ neighDist2) {
   const Grid g = *grid;
-  for (long long c = NL_TID; c < nCand; c += NL_STRIDE) {
+  const long long nAct = *nActive;
+  for (long long i = NL_TID; i < nAct; i += NL_STRIDE) {
+    const long long c = activeList[i];
     if (!flag[c]) continue;
     const int ii = (int)(c / nAtom), a1 = (int)(c - (long long)ii * nAtom);
     const int img = imgIndex[c];
