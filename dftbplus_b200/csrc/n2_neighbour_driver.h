@@ -188,7 +188,7 @@ int updateNeighbourList(Backend &be, NeighbourList &nb, int nAtom, const double 
   NL_TRY(be.fill(nb.flag.p, 0, sizeof(int) * ((size_t)nCand + 1)));
   NL_TRY(be.fill(nb.nNeighbour.p, 0, sizeof(int) * nAtom));
   NL_TRY(be.fill(nb.sizes.p, 0, sizeof(int) * kSizeCount));
-  NL_TRY(be.launch(nl_count, nCand, (const int *)nb.nActive.p, (const int *)nb.activeList.p, nAtom,
+  NL_TRY(be.launch(nl_count, nCand * kSearchParts, (const int *)nb.nActive.p, (const int *)nb.activeList.p, nAtom,
                    symmetric ? 1 : 0, (const double *)nb.coord0.p, (const double *)nb.rCellVec.p,
                    (const Grid *)nb.grid.p, (const int *)nb.binStart.p, (const int *)nb.binAtom.p,
                    (const double *)nb.binXyz.p, cutoff2, nb.flag.p, nb.nNeighbour.p, nb.box.p + 6));
@@ -232,7 +232,7 @@ int updateNeighbourList(Backend &be, NeighbourList &nb, int nAtom, const double 
   NL_TRY(be.fill(nb.iNeighbour.p, 0, sizeof(int) * ld * nAtom));    // iNeighbour(:,:) = 0, :565
   NL_TRY(be.fill(nb.neighDist2.p, 0, sizeof(double) * ld * nAtom));  // neighDist2(:,:) = 0.0_dp, :566
   NL_TRY(be.fill(nb.iPair.p, 0, sizeof(int) * ld * nAtom));          // iPair(:,:) = 0, sparse2dense.F90:3648
-  NL_TRY(be.launch(nl_fill, nCand, (const int *)nb.nActive.p, (const int *)nb.activeList.p, nAtom,
+  NL_TRY(be.launch(nl_fill, nCand * kSearchParts, (const int *)nb.nActive.p, (const int *)nb.activeList.p, nAtom,
                    symmetric ? 1 : 0, ld, (const double *)nb.coord0.p, (const int *)nb.species0.p,
                    (const double *)nb.rCellVec.p, (const Grid *)nb.grid.p, (const int *)nb.binStart.p,
                    (const int *)nb.binAtom.p, (const double *)nb.binXyz.p, cutoff2, (const int *)nb.flag.p,

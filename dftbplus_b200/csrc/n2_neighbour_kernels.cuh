@@ -34,7 +34,8 @@ constexpr int kMaxBinsPerDim = 32;
 constexpr int kMaxBins = kMaxBinsPerDim * kMaxBinsPerDim * kMaxBinsPerDim;
 constexpr double kTolSameDist2 = 1.0e-5 * 1.0e-5;   // tolSameDist**2, common/accuracy.F90:68-72
 constexpr double kMinNeighDist2 = 1.0e-2 * 1.0e-2;  // minNeighDist**2, common/accuracy.F90:77-82
-constexpr double kBinSlack = 1.0001;                // bin edge >= kBinSlack * cutoff (rounding margin)
+constexpr double kBinSlack = 1.0001;
+constexpr int kSearchParts = 8;  // threads that share the search around one image (consecutive lanes)                // bin edge >= kBinSlack * cutoff (rounding margin)
 
 // slots of the small int array the host reads back
 enum { kSizeAllAtom = 0, kSizeMaxNeigh = 1, kSizeSparse = 2, kSizeOrb = 3, kSizeCount = 4 };
@@ -174,9 +175,10 @@ NL_KERNEL void nl_active(long long nCand, int nAtom, const double *__restrict__ 
 // Image of atom a1 (0-based) in cell ii (0-based): rr = coord0(:,a1) + rCellVec(:,ii)
 // (periodic.F90:579), and every central atom a2 <= a1 with dist2 = sum((coord0(:,a2) - rr)**2) <=
 // cutoff2 (:597-600) is handed to visit(a2, dist2) -- every central atom for the symmetric list
-// (iAtom2End = nAtom).  Returns false if the image is too far from the bounding box to have any.
+// (iAtom2End = nAtom).  The atoms of the 27 bins are shared by nParts threads (thread `part` takes
+// every nParts-th atom of each bin row).  Returns false if the image is too far from the bounding box.
 template <class F>
-NL_DEV bool visitNeighbours(bool symmetric, int ii, int a1, const double *__restrict__ coord0,
+NL_DEV bool visitNeighbours(bool symmetric, int part, int nParts, int ii, int a1, const double *__restrict__ coord0,
                             const double *__restrict__ rCellVec, const Grid &g,
                             const int *__restrict__ binStart, const int *__restrict__ binAtom,
                             const double *__restrict__ binXyz, double cutoff2, double *rr, F &&visit) {
@@ -190,7 +192,7 @@ NL_DEV bool visitNeighbours(bool symmetric, int ii, int a1, const double *__rest
       // bins x0..x1 of one (iy, iz) row are contiguous
       const int row = g.nb[0] * (iy + g.nb[1] * iz);
       const int pEnd = binStart[row + x1 + 1];
-      for (int p = binStart[row + x0]; p < pEnd; ++p) {
+      for (int p = binStart[row + x0] + part; p < pEnd; p += nParts) {  // this thread's share of the row
         const int a2 = binAtom[p];
         if (a2 > a1 && !symmetric) continue;  // non-symmetric list: iAtom2 = 1 .. iAtom1 (:580-584)
         const double d0 = NL_SUB(binXyz[3 * p], rr[0]);
@@ -213,13 +215,14 @@ NL_KERNEL void nl_count(const int *__restrict__ nActive, const int *__restrict__
                         const double *__restrict__ binXyz, double cutoff2, int *__restrict__ flag,
                         int *__restrict__ nNeighbour, ull *__restrict__ firstError) {
   const Grid g = *grid;
-  const long long nAct = *nActive;
-  for (long long i = NL_TID; i < nAct; i += NL_STRIDE) {
-    const long long c = activeList[i];
+  const long long nItems = (long long)*nActive * kSearchParts;
+  for (long long i = NL_TID; i < nItems; i += NL_STRIDE) {
+    const long long c = activeList[i / kSearchParts];
+    const int part = (int)(i % kSearchParts);
     const int ii = (int)(c / nAtom), a1 = (int)(c - (long long)ii * nAtom);
     double rr[3];
     int found = 0;
-    visitNeighbours(symmetric != 0, ii, a1, coord0, rCellVec, g, binStart, binAtom, binXyz, cutoff2, rr,
+    visitNeighbours(symmetric != 0, part, kSearchParts, ii, a1, coord0, rCellVec, g, binStart, binAtom, binXyz, cutoff2, rr,
                     [&](int a2, double dist2) {
                       found = 1;  // the image is appended before the proximity check (:604-614)
                       if (dist2 < kMinNeighDist2) {
@@ -228,7 +231,7 @@ NL_KERNEL void nl_count(const int *__restrict__ nActive, const int *__restrict__
                       }
                       atomicAdd(nNeighbour + a2, 1);
                     });
-    flag[c] = found;
+    if (found) flag[c] = 1;  // the threads of an image store the same value
   }
 }
 
@@ -253,20 +256,22 @@ NL_KERNEL void nl_fill(const int *__restrict__ nActive, const int *__restrict__ 
                        int *__restrict__ iCellVec, int *__restrict__ cursor, int *__restrict__ iNeighbour,
                        double *__restrict__ neighDist2) {
   const Grid g = *grid;
-  const long long nAct = *nActive;
-  for (long long i = NL_TID; i < nAct; i += NL_STRIDE) {
-    const long long c = activeList[i];
+  const long long nItems = (long long)*nActive * kSearchParts;
+  for (long long i = NL_TID; i < nItems; i += NL_STRIDE) {
+    const long long c = activeList[i / kSearchParts];
+    const int part = (int)(i % kSearchParts);
     if (!flag[c]) continue;
     const int ii = (int)(c / nAtom), a1 = (int)(c - (long long)ii * nAtom);
     const int img = imgIndex[c];
     double rr[3];
-    visitNeighbours(symmetric != 0, ii, a1, coord0, rCellVec, g, binStart, binAtom, binXyz, cutoff2, rr,
+    visitNeighbours(symmetric != 0, part, kSearchParts, ii, a1, coord0, rCellVec, g, binStart, binAtom, binXyz, cutoff2, rr,
                     [&](int a2, double dist2) {
                       if (dist2 < kMinNeighDist2) return;
                       const int slot = atomicAdd(cursor + a2, 1) + 1;
                       iNeighbour[slot + (long long)ld * a2] = img + 1;
                       neighDist2[slot + (long long)ld * a2] = dist2;
                     });
+    if (part != 0) continue;  // one thread of the image writes its entry of the image arrays
     coords[3 * (long long)img] = rr[0];
     coords[3 * (long long)img + 1] = rr[1];
     coords[3 * (long long)img + 2] = rr[2];
