@@ -5,8 +5,9 @@
 // (dftb/sparse2dense.F90:3617-3662), index_heap_sort (math/sorting.F90:142-199).
 //
 // The reference scans all nCellVec * nAtom * nAtom / 2 (image, atom) combinations on one thread.
-// Here the central-cell atoms are binned into a uniform grid (bin edge >= cutoff) and one thread per
-// CANDIDATE IMAGE (cell vector ii, central atom iAtom1) looks only at the 27 bins around the image.
+// Here the central-cell atoms are binned into a uniform grid (bin edge >= cutoff); the CANDIDATE
+// IMAGES (cell vector ii, central atom iAtom1) that lie within one bin edge of the central cell are
+// compacted into a list, and eight threads per listed image share the atoms of the 27 bins around it.
 // Everything the reference's loop order decides is reproduced from the candidate number
 // c = ii * nAtom + iAtom1, which is the position of the image in that loop:
 //   * image numbers  = exclusive prefix sum over c of "has a neighbour iAtom2 <= iAtom1 in range";
