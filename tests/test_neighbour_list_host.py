@@ -398,7 +398,7 @@ def test_randomized_geometries_against_the_oracle(host):
     atoms on exact multiples of the bin edge, several list / SK cutoffs and species mixes."""
     rng = np.random.default_rng(2025)
     n_case = 0
-    for trial in range(60):
+    for trial in range(100):
         n_atom = int(rng.integers(1, 40))
         n_orb_species = [int(v) for v in rng.choice([1, 4, 9, 16], size=int(rng.integers(1, 4)))]
         species0 = rng.integers(1, len(n_orb_species) + 1, n_atom).astype(np.int32)
@@ -417,21 +417,30 @@ def test_randomized_geometries_against_the_oracle(host):
         else:              # atoms on exact multiples of 1.0001 * cutoff (bin edges), non-periodic
             coord0 = rng.integers(0, 6, (n_atom, 3)) * (1.0001 * cutoff) + rng.choice([0.0, 1e-13, -1e-13], (n_atom, 3))
             lat = None
+        if trial % 5 == 4:  # simple cubic lattice, periodic: exact ties in every shell
+            a, m = float(rng.uniform(2.0, 5.0)), int(rng.integers(1, 4))
+            coord0 = np.array([[i, j, k] for i in range(m) for j in range(m) for k in range(m)], dtype=float) * a
+            n_atom, lat = len(coord0), np.eye(3) * a * m
+            species0 = rng.integers(1, len(n_orb_species) + 1, n_atom).astype(np.int32)
+        symmetric = trial % 7 == 0
         if lat is None:
             cell, rcell = np.zeros((1, 3)), np.zeros((1, 3))
         else:
             cell, rcell = oracle.cell_translations(lat, cutoff)
+        if cell.shape[0] * n_atom > 300000:
+            continue
         try:
-            ref = oracle.neighbour_list_full(n_orb_species, coord0, species0, rcell, cutoff, skc)
+            ref = oracle.neighbour_list_full(n_orb_species, coord0, species0, rcell, cutoff, skc, symmetric=symmetric)
         except RuntimeError as e:
             with pytest.raises(RuntimeError) as got:
-                host_list(host, coord0, species0, n_orb_species, cell, rcell, cutoff, skc, 23, trial)
+                host_list(host, coord0, species0, n_orb_species, cell, rcell, cutoff, skc, 23, trial, symmetric=symmetric)
             assert str(got.value) == str(e)
             continue
-        got = host_list(host, coord0, species0, n_orb_species, cell, rcell, cutoff, skc, n_threads=23 + trial, seed=trial)
+        got = host_list(host, coord0, species0, n_orb_species, cell, rcell, cutoff, skc, n_threads=23 + trial, seed=trial,
+                        symmetric=symmetric)
         assert_same_list(got, ref)
         n_case += 1
-    assert n_case > 40
+    assert n_case > 60
 
 
 def test_randomized_many_bin_grids_against_the_oracle(host):
