@@ -32,6 +32,7 @@ SIGNATURES = {
                                                  c_double, c_double, c_int, P(c_int), P(c_int), P(c_int)]),
     "dftbp_b200_get_neighbour_list": (c_int, [c_void_p] + [c_void_p] * 10),
     "dftbp_b200_adopt_neighbour_list": (c_int, [c_void_p]),
+    "dftbp_b200_nr_of_neighbours": (c_int, [c_void_p, c_double, c_void_p]),
     "dftbp_b200_update_coords": (c_int, [c_void_p, c_void_p]),
     "dftbp_b200_build_h0": (c_int, [c_void_p, c_void_p, c_void_p]),
     "dftbp_b200_build_s": (c_int, [c_void_p, c_void_p]),

@@ -233,6 +233,12 @@ class HotPath:
             self.geo = g        # without fetch: the sizes only (enough for the default output buffers)
         return g
 
+    def getNrOfNeighboursForAll(self, cutoff, n_atom=None):
+        """getNrOfNeighboursForAll (dftb/periodic.F90:996-1054) on the list of the last update."""
+        out = np.zeros(self.geo["nAtom"] if n_atom is None else n_atom, dtype=np.int32)
+        self._ck(self._L.dftbp_b200_nr_of_neighbours(self._h, float(cutoff), _ptr(out)))
+        return out
+
     def update_coords(self, coords):
         self._ck(self._L.dftbp_b200_update_coords(self._h, _ptr(_f64(coords))))
 

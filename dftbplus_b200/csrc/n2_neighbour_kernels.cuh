@@ -429,6 +429,13 @@ NL_KERNEL void nl_sort(int nAtom, int ld, double skCutoff2, const int *__restric
   }
 }
 
+// getNrOfNeighboursForAll (periodic.F90:996-1020) for another cutoff on the finished list
+NL_KERNEL void nl_nr_of_neighbours(int nAtom, int ld, double cutoff2, const int *__restrict__ nNeighbour,
+                                   const double *__restrict__ neighDist2, int *__restrict__ out) {
+  for (long long a = NL_TID; a < nAtom; a += NL_STRIDE)
+    out[a] = searchAscRealGeq(nNeighbour[a], neighDist2 + (long long)ld * a, cutoff2, kTolSameDist2);
+}
+
 // getSparseDescriptor (sparse2dense.F90:3651-3660) from the per-atom offsets, and iAtomStart
 NL_KERNEL void nl_ipair(int nAtom, int ld, const int *__restrict__ nNeighbourSK,
                         const int *__restrict__ species0, const int *__restrict__ nOrbSpecies,

@@ -214,6 +214,20 @@ int dftbp_b200_get_neighbour_list(dftbp_b200_ctx *ctx, double *coords, int *spec
   return 0;
 }
 
+int dftbp_b200_nr_of_neighbours(dftbp_b200_ctx *ctx, double cutoff, int *nNeighbour) {
+  if (!ctx) return DFTBP_B200_EINVAL;
+  DFTBP_CHECK(ctx, ctx->neighbourState && stateOf(ctx)->list.valid,
+              "nr_of_neighbours: no neighbour list (call update_neighbour_list first)");
+  DFTBP_CHECK(ctx, cutoff >= 0.0 && nNeighbour, "nr_of_neighbours: bad arguments");
+  const nl::NeighbourList &L = stateOf(ctx)->list;
+  int *dOut;
+  DFTBP_TRY(devOut(ctx, kSlotA, nNeighbour, (size_t)L.nAtom, false, &dOut));
+  CudaBackend be{ctx};
+  DFTBP_TRY(be.launch(nl::nl_nr_of_neighbours, L.nAtom, L.nAtom, L.mNeigh + 1, cutoff * cutoff,
+                      (const int *)L.nNeighbour.p, (const double *)L.neighDist2.p, dOut));
+  return finish(ctx);
+}
+
 int dftbp_b200_adopt_neighbour_list(dftbp_b200_ctx *ctx) {
   if (!ctx) return DFTBP_B200_EINVAL;
   DFTBP_CHECK(ctx, ctx->neighbourState && stateOf(ctx)->list.valid,

@@ -184,6 +184,12 @@ module dftbp_b200_shim
       integer(c_int), intent(out) :: nNeighbourSK(*), iPair(*)
       type(c_ptr), value :: iAtomStart
     end function
+    integer(c_int) function dftbp_b200_nr_of_neighbours(ctx, cutoff, nNeighbour) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), value :: cutoff
+      integer(c_int), intent(out) :: nNeighbour(*)
+    end function
     integer(c_int) function dftbp_b200_adopt_neighbour_list(ctx) bind(C)
       import :: c_ptr, c_int
       type(c_ptr), value :: ctx
@@ -287,6 +293,14 @@ contains
         & img2CentCell, iCellVec, size(cellVec, dim=2), cellVec, nNeighbourSK, iNeighbour,&
         & iSparseStart(0:mNeigh, :), iAtomStart, sparseSize))
   end subroutine b200_setGeometry
+
+  !> getNrOfNeighboursForAll, dftb/periodic.F90:996 (another cutoff on the device list)
+  subroutine b200_getNrOfNeighboursForAll(ctx, nNeighbour, cutoff)
+    type(TB200Ctx), intent(in) :: ctx
+    integer, intent(out) :: nNeighbour(:)
+    real(dp), intent(in) :: cutoff
+    call check(ctx, dftbp_b200_nr_of_neighbours(ctx%h, cutoff, nNeighbour))
+  end subroutine b200_getNrOfNeighboursForAll
 
   !> boundaryCond%foldCoordsToCell, pbc3d without contacts (dftb/boundarycond.F90:369-380)
   subroutine b200_foldCoordsToCell(ctx, coord, latVec)

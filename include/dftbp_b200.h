@@ -148,6 +148,11 @@ int dftbp_b200_get_neighbour_list(dftbp_b200_ctx *ctx, double *coords, int *spec
                                   int *iCellVec, int *nNeighbour, int *iNeighbour, double *neighDist2,
                                   int *nNeighbourSK, int *iPair, int *iAtomStart);
 
+/* getNrOfNeighboursForAll, dftb/periodic.F90:996-1054 (search_asc_real_geq with tolSameDist2), for
+ * another cutoff <= the list cutoff on the list of the last update (the reference counts again for
+ * the repulsive / CAM ranges, e.g. dftbplus/main.F90:2583).  nNeighbour(nAtom) out. */
+int dftbp_b200_nr_of_neighbours(dftbp_b200_ctx *ctx, double cutoff, int *nNeighbour);
+
 /* Make the list of the last update the context's geometry (what dftbp_b200_set_geometry does
  * with caller arrays): the arrays are taken from the device copies, the caller passes nothing.
  * (The work lists / block descriptors of set_geometry are still formed on the host from a read-back

@@ -140,6 +140,13 @@ void host_heap_sort_records(int n, int *keys, double *vals, double tol) {
   nl::heapSortRecords(n, keys - 1, vals - 1, [tol](int, double vA, int, double vB) { return vA < vB - tol; });
 }
 
+// getNrOfNeighboursForAll for another cutoff on the last list
+void host_nl_nr_of_neighbours(double cutoff, int *out, int nThreads, unsigned seed) {
+  HostBackend be{nThreads, std::mt19937(seed)};
+  be.launch(nl::nl_nr_of_neighbours, g_list.nAtom, g_list.nAtom, g_list.mNeigh + 1, cutoff * cutoff,
+            (const int *)g_list.nNeighbour.p, (const double *)g_list.neighDist2.p, out);
+}
+
 // test hook: row length above which the counting is skipped (default nl::kRankMaxDefault)
 void host_nl_set_rank_max(int v) { g_rankMax = v > 0 ? v : nl::kRankMaxDefault; }
 

@@ -555,3 +555,21 @@ def test_long_rows_skip_the_counting(host):
                                    sk2.cutoff()), ref2)
     finally:
         host.host_nl_set_rank_max(0)
+
+
+def test_nr_of_neighbours_for_other_cutoffs(host):
+    """getNrOfNeighboursForAll on the finished list for shorter cutoffs (repulsive / CAM ranges)."""
+    w, sk, geo, model, selfegy = case("si512")                  # perfect lattice: cutoffs inside tie shells
+    cutoff = sk.cutoff()
+    cell, rcell = oracle.cell_translations(w["latvec"], cutoff)
+    got = host_list(host, w["coord0"], w["species0"], sk.n_orb_species, cell, rcell, cutoff, cutoff)
+    a = 5.431 / 0.529177249
+    L = oracle.lib()
+    for c in (0.0, a * np.sqrt(3) / 4, a / np.sqrt(2), a / np.sqrt(2) - 1e-6, 7.3, cutoff):
+        ref = np.zeros(got["nAtom"], dtype=np.int32)
+        L.orc_nr_of_neighbours(got["nAtom"], _p(got["nNeighbour"], ctypes.c_int), _p(got["neighDist2"], ctypes.c_double),
+                               got["mNeigh"], ctypes.c_double(c), _p(ref, ctypes.c_int))
+        out = np.full(got["nAtom"], -1, dtype=np.int32)
+        host.host_nl_nr_of_neighbours(ctypes.c_double(c), _p(out, ctypes.c_int), 19, 5)
+        assert np.array_equal(out, ref)
+    assert np.array_equal(out, got["nNeighbour"])               # the list cutoff itself: everything

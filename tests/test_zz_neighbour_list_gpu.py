@@ -257,3 +257,20 @@ def test_symmetric_list_on_the_device(hp_for):
     # the context takes a normal list again afterwards
     got = hp.updateNeighbourListAndSpecies(w["coord0"], w["species0"], cutoff, w["latvec"], adopt=True)
     assert got["sparseSize"] == geo["sparseSize"]
+
+
+def test_nr_of_neighbours_for_other_cutoffs_on_the_device(hp_for):
+    """getNrOfNeighboursForAll (periodic.F90:996-1054) on the device list for shorter cutoffs."""
+    import ctypes
+    w, sk, geo, model, selfegy = case("si512")
+    hp = hp_for("si512")
+    cutoff = sk.cutoff()
+    g = hp.updateNeighbourListAndSpecies(w["coord0"], w["species0"], cutoff, w["latvec"], adopt=True)
+    a = 5.431 / 0.529177249
+    L = oracle.lib()
+    for c in (0.0, a * np.sqrt(3) / 4, a / np.sqrt(2), 7.3, cutoff):
+        ref = np.zeros(g["nAtom"], dtype=np.int32)
+        L.orc_nr_of_neighbours(g["nAtom"], g["nNeighbour"].ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+                               g["neighDist2"].ctypes.data_as(ctypes.POINTER(ctypes.c_double)), g["mNeigh"],
+                               ctypes.c_double(c), ref.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+        assert np.array_equal(hp.getNrOfNeighboursForAll(c), ref)
