@@ -7,6 +7,7 @@ The `-m gpu` tests (test_neighbour_list_gpu.py) cover the CUDA backend around th
 import ctypes
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -573,3 +574,21 @@ def test_nr_of_neighbours_for_other_cutoffs(host):
         host.host_nl_nr_of_neighbours(ctypes.c_double(c), _p(out, ctypes.c_int), 19, 5)
         assert np.array_equal(out, ref)
     assert np.array_equal(out, got["nNeighbour"])               # the list cutoff itself: everything
+
+
+def test_kernels_are_clean_under_address_sanitizer(host):
+    """The same kernels and launch sequence under ASan / UBSan: the CPU backend allocates every buffer
+    with exactly the size the GPU backend would, so an out-of-range index (an illegal address on the
+    device) fails here."""
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not asan or not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan not available")
+    so = os.path.join(ROOT, "oracle", "_build", "libhostnl_asan.so")
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in DEPS):
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                               "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-o", so, SRC])
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host_eval", "asan_run.py"), so], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "asan/ubsan run finished" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
+    assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr, r.stderr[-4000:]
