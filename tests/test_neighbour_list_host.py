@@ -24,12 +24,16 @@ ARRAYS = ("coords", "species", "img2CentCell", "iCellVec", "nNeighbour", "iNeigh
           "nNeighbourSK", "iPair", "iAtomStart")
 
 
-@pytest.fixture(scope="module")
-def host():
+def build_host_so():
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in DEPS):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", SO, SRC])
-    return ctypes.CDLL(SO)
+    return SO
+
+
+@pytest.fixture(scope="module")
+def host():
+    return ctypes.CDLL(build_host_so())
 
 
 def _p(a, t):
