@@ -27,4 +27,16 @@ w, sk, geo, model, selfegy = case("si512"); cutoff=sk.cutoff(); cell, rcell = T.
 T.host_list(lib, w["coord0"], w["species0"], sk.n_orb_species, cell, rcell, cutoff, cutoff)
 c = np.random.default_rng(1).uniform(-30,30,(50,3)); lat=np.ascontiguousarray(np.diag([7.,8.,9.]))
 lib.host_nl_fold(50, c.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), lat.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 9, 2)
+# per-atom population kernels and the stand-alone sort / bisection entry points
+w, sk, geo, model, selfegy = case("ce_o")
+rho = np.random.default_rng(2).normal(size=geo["sparseSize"])
+ipair = np.ascontiguousarray(geo["iPair"], dtype=np.int32); start = np.ascontiguousarray(geo["iAtomStart"], dtype=np.int32)
+q = np.zeros(geo["nAtom"]); dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+lib.host_pop_onsite(geo["nAtom"], ipair.shape[1], ipair.ctypes.data_as(ip), start.ctypes.data_as(ip), rho.ctypes.data_as(dp), q.ctypes.data_as(dp), 5, 1)
+qo = np.random.default_rng(3).normal(size=(geo["nAtom"], 16))
+lib.host_pop_atom_sum(geo["nAtom"], 16, qo.ctypes.data_as(dp), q.ctypes.data_as(dp), 5, 1)
+for m in (0, 1, 2, 33):
+    keys = np.arange(1, m + 1, dtype=np.int32); vals = np.random.default_rng(m).uniform(size=max(m, 1))[:m].copy()
+    lib.host_heap_sort_records(m, keys.ctypes.data_as(ip), vals.ctypes.data_as(dp), ctypes.c_double(1e-10))
+    lib.host_search_asc_real_geq(m, vals.ctypes.data_as(dp), ctypes.c_double(0.5), ctypes.c_double(1e-10))
 print("asan/ubsan run finished,", n, "lists compared")
