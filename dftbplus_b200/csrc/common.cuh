@@ -36,7 +36,24 @@ struct SpPairProg {
   int nSh1, nSh2;                     // shells of the atom / of the neighbour
   unsigned long long shells1, shells2;  // angular momentum per shell, 4 bits each (shell 0 lowest)
   int canon1, canon2;  // lmax if the species' shells are exactly l = 0..lmax in order (s, sp, spd, spdf), else -1
-  int pad0, pad1;
+  int sameGrid;  // the H and the S table have the same grid (length, spacing, method)
+  int nShPair;   // nSh1 * nSh2
+  // Shell-pair program of the compact evaluator (sk_dmat_eval.cuh; filled by fillShellProgram,
+  // sk_table_prep.h).  Shell pairs in the order of rotateH0's loops (atom-1 shells outer):
+  //   shPair[i]   = (first element of the sub-block in the column-major block) << 4 | (l1 * 4 + l2)
+  //   integDst[k] = element of the block where integral k is parked until its shell pair is rotated
+  //                 (the first lmin + 1 elements of that sub-block)
+  unsigned short shPair[kMaxInteg];
+  unsigned short integDst[kMaxInteg];
+  // Two-kernel build (k1_pair_build.cu), species whose shells all have different l ("simple"):
+  //   caseOff[c]   = first element of the sub-block of shell-pair type c = l1 * 4 + l2, 0xFFFF if absent
+  //   integSlot[k] = position of integral k in the exchange row of a pair, which is ordered by
+  //                  shell-pair type (caseSlot<LMAX>, sk_dmat_eval.cuh) instead of by shell loops
+  //   shellOfL1[l] = shell of the atom (species 1) with angular momentum l, -1 if none
+  alignas(16) unsigned short caseOff[16];
+  unsigned char integSlot[kMaxInteg];
+  signed char shellOfL1[4];
+  int simple;
 };
 
 // Device-built schedule of the lane-per-pair kernels (pair_sort.cu): the off-site pairs of one work
@@ -50,10 +67,13 @@ struct __align__(16) PairRec {
   int sp;             // sp1 + nSpecies * sp2 (0-based): index of the species-pair program
 };
 static_assert(sizeof(PairRec) == 32, "PairRec must be two 16-byte words");
+constexpr int kRecOnsite = 1 << 30;  // PairRec::sp of an on-site block (records in work-list order only)
 
 struct SortedPairs {
-  int *items = nullptr;    // flat ids iNeigh + ld*iAtom0, -1 = padding
+  int *items = nullptr;    // per slot: position of the pair in the work list, -1 = padding
   PairRec *recs = nullptr; // per slot, same order as items
+  PairRec *recsMem = nullptr;  // per work-list entry (the order of the sparse arrays), on-site blocks included
+  long long recsMemCap = 0;
   int2 *atoms = nullptr;   // per slot: (iAtom1, iAtom2f), 0-based (K5: where the gradient goes)
   int *total = nullptr;    // device scalar: padded length (multiple of 32)
   long long capacity = 0;  // allocated entries of items / recs / atoms
@@ -129,6 +149,9 @@ struct dftbp_b200_ctx {
   size_t smemOptin = 232448;  // max dynamic shared memory per CTA
   size_t smemPerSm = 233472;
   int lMaxAll = 0;            // highest angular momentum of any species
+  bool allSimple = false;     // no species has two shells of the same l (two-kernel pair build possible)
+  double *pairExchange = nullptr;  // per work-list entry: interpolated integrals of H0 and S (k1_pair_build.cu)
+  long long pairExchangeCap = 0;   // allocated doubles
 
   // orbitals
   int nSpecies = 0, mShell = 0, mOrb = 0;

@@ -86,6 +86,7 @@ int dftbp_b200_destroy(dftbp_b200_ctx *ctx) {
   for (void *p : ctx->tableAllocs) cudaFree(p);
   for (Staging &s : ctx->staging) cudaFree(s.ptr);
   cudaFree(ctx->dNOrbSpecies); cudaFree(ctx->dOrbShell); cudaFree(ctx->dProgs);
+  cudaFree(ctx->pairExchange);
   cudaFree(ctx->solverWork); cudaFree(ctx->dInfo);
   solverDestroy(ctx);
   for (TimedSpan &sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -229,7 +230,10 @@ int dftbp_b200_set_orbitals(dftbp_b200_ctx *ctx, int nSpecies, int mShell, const
       for (int sh = 0; sh < nShell[sp2]; ++sh)
         pg.shells2 |= (unsigned long long)angShell[sh + mShell * sp2] << (4 * sh);
       pg.nY = (lmax1 + lmax2 + 1) * (lmax1 + lmax2 + 1);
+      DFTBP_CHECK(ctx, fillShellProgram(pg, ctx->lMaxAll), "set_orbitals: too many shell pairs per species pair");
     }
+  ctx->allSimple = true;
+  for (const SpPairProg &pg : ctx->progs) ctx->allSimple = ctx->allSimple && pg.simple;
   ctx->progsDirty = true;
   return 0;
 }
@@ -420,10 +424,14 @@ namespace dftbp_b200 {
 // (re-)upload the species-pair programs after tables changed
 int syncPrograms(dftbp_b200_ctx *ctx) {
   if (!ctx->progsDirty) return 0;
-  for (const SpPairProg &pg : ctx->progs)
+  for (SpPairProg &pg : ctx->progs) {
     if (pg.H.tab == nullptr || pg.S.tab == nullptr)
       return fail(ctx, DFTBP_B200_EINVAL,
                   "SK tables missing: set_sk_table must be called for H and S of every species pair");
+    // H and S of one .skf file share the grid: the kernels then form the interpolation window and
+    // weights once per pair
+    pg.sameGrid = pg.H.nGrid == pg.S.nGrid && pg.H.dist == pg.S.dist && pg.H.method == pg.S.method;
+  }
   DFTBP_TRY(uploadNew(ctx, &ctx->dProgs, ctx->progs.data(), ctx->progs.size()));
   ctx->progsDirty = false;
   return 0;

@@ -24,18 +24,28 @@ constexpr int kSortThreads = 1024;  // one big CTA aggregates many items per his
 // a few rows)
 int binsFor(int nBuckets) { return nBuckets <= 8 ? 1024 : nBuckets <= 32 ? 256 : nBuckets <= 128 ? 64 : 16; }
 
+// key of work item `flat` and its record (bond vector, sparse offset, species-pair program); on-site
+// blocks (iNeigh = 0) get key -1 and a record flagged kRecOnsite with a zero bond vector
 __device__ __forceinline__ int pairKey(int flat, int ld, int nSpecies, int nBins, double binScale,
                                        const double *__restrict__ coords, const int *__restrict__ species,
-                                       const int *__restrict__ iNeighbour) {
+                                       const int *__restrict__ iNeighbour, const int *__restrict__ iPair, PairRec &r) {
   const int iAt1 = flat / ld, iNeigh = flat - iAt1 * ld;
-  if (iNeigh == 0) return -1;  // on-site blocks are not pairs
+  const int sp1 = __ldg(species + iAt1) - 1;
+  r.ind = __ldg(iPair + flat);
+  if (iNeigh == 0) {  // on-site blocks are not pairs
+    r.vx = r.vy = r.vz = 0.0;
+    r.sp = (sp1 + nSpecies * sp1) | kRecOnsite;
+    return -1;
+  }
   const int iAt2 = __ldg(iNeighbour + flat) - 1;
-  const int sp1 = __ldg(species + iAt1) - 1, sp2 = __ldg(species + iAt2) - 1;
-  const double vx = __ldg(coords + 3 * iAt2) - __ldg(coords + 3 * iAt1);
-  const double vy = __ldg(coords + 3 * iAt2 + 1) - __ldg(coords + 3 * iAt1 + 1);
-  const double vz = __ldg(coords + 3 * iAt2 + 2) - __ldg(coords + 3 * iAt1 + 2);
-  const double r = sqrt(vx * vx + vy * vy + vz * vz);
-  const int bin = min(nBins - 1, max(0, (int)(r * binScale)));
+  const int sp2 = __ldg(species + iAt2) - 1;
+  // vect(:) = coords(:,iAt2) - coords(:,iAt1), nonscc.F90:413
+  r.vx = __ldg(coords + 3 * iAt2) - __ldg(coords + 3 * iAt1);
+  r.vy = __ldg(coords + 3 * iAt2 + 1) - __ldg(coords + 3 * iAt1 + 1);
+  r.vz = __ldg(coords + 3 * iAt2 + 2) - __ldg(coords + 3 * iAt1 + 2);
+  r.sp = sp1 + nSpecies * sp2;
+  const double d = sqrt(r.vx * r.vx + r.vy * r.vy + r.vz * r.vz);
+  const int bin = min(nBins - 1, max(0, (int)(d * binScale)));
   return (sp1 + nSpecies * sp2) * nBins + bin;
 }
 
@@ -46,16 +56,20 @@ __global__ void __launch_bounds__(kSortThreads) ps_keys(const int *__restrict__ 
                                                         int nSpecies, int nBins, int nKeys,
                                                         const double *__restrict__ coords,
                                                         const int *__restrict__ species,
-                                                        const int *__restrict__ iNeighbour, double binScale,
-                                                        int *__restrict__ keys, int *__restrict__ hist) {
+                                                        const int *__restrict__ iNeighbour,
+                                                        const int *__restrict__ iPair, double binScale,
+                                                        int *__restrict__ keys, int *__restrict__ hist,
+                                                        PairRec *__restrict__ recsMem) {
   extern __shared__ int sh[];
   for (int k = threadIdx.x; k < nKeys; k += kSortThreads) sh[k] = 0;
   __syncthreads();
   const long long per = (nWork + gridDim.x - 1) / gridDim.x;
   const long long lo = per * blockIdx.x, hi = min(nWork, lo + per);
   for (long long i = lo + threadIdx.x; i < hi; i += kSortThreads) {
-    const int key = pairKey(__ldg(work + i), ld, nSpecies, nBins, binScale, coords, species, iNeighbour);
+    PairRec r;
+    const int key = pairKey(__ldg(work + i), ld, nSpecies, nBins, binScale, coords, species, iNeighbour, iPair, r);
     keys[i] = key;
+    recsMem[i] = r;  // the same record in the order of the work list (= the order of the sparse arrays)
     if (key >= 0) atomicAdd(sh + key, 1);
   }
   __syncthreads();
@@ -120,10 +134,8 @@ __global__ void __launch_bounds__(kSortThreads) ps_scatter(const int *__restrict
                                                            int nKeys, const int *__restrict__ keys,
                                                            int *__restrict__ cursors, int *__restrict__ items,
                                                            PairRec *__restrict__ recs, int2 *__restrict__ atoms,
-                                                           int ld, int nSpecies, const double *__restrict__ coords,
-                                                           const int *__restrict__ species,
+                                                           int ld, const PairRec *__restrict__ recsMem,
                                                            const int *__restrict__ iNeighbour,
-                                                           const int *__restrict__ iPair,
                                                            const int *__restrict__ img2CentCell) {
   extern __shared__ int sh[];
   for (int k = threadIdx.x; k < nKeys; k += kSortThreads) sh[k] = 0;
@@ -146,16 +158,13 @@ __global__ void __launch_bounds__(kSortThreads) ps_scatter(const int *__restrict
     const int flat = __ldg(work + i);
     const int iAt1 = flat / ld;
     const int iAt2 = __ldg(iNeighbour + flat) - 1;
-    PairRec r;
-    // vect(:) = coords(:,iAt2) - coords(:,iAt1), nonscc.F90:413
-    r.vx = __ldg(coords + 3 * iAt2) - __ldg(coords + 3 * iAt1);
-    r.vy = __ldg(coords + 3 * iAt2 + 1) - __ldg(coords + 3 * iAt1 + 1);
-    r.vz = __ldg(coords + 3 * iAt2 + 2) - __ldg(coords + 3 * iAt1 + 2);
-    r.ind = __ldg(iPair + flat);
-    r.sp = (__ldg(species + iAt1) - 1) + nSpecies * (__ldg(species + iAt2) - 1);
+    const int4 *src = reinterpret_cast<const int4 *>(recsMem + i);
+    const int4 lo = __ldg(src), hi = __ldg(src + 1);
     const int pos = atomicAdd(sh + key, 1);
-    items[pos] = flat;
-    recs[pos] = r;
+    items[pos] = (int)i;  // position in the work list: row of the pair in per-pair exchange buffers
+    int4 *dst = reinterpret_cast<int4 *>(recs + pos);
+    dst[0] = lo;
+    dst[1] = hi;
     atoms[pos] = make_int2(iAt1, __ldg(img2CentCell + iAt2) - 1);
   }
 }
@@ -182,6 +191,7 @@ void freeSortedPairs(dftbp_b200_ctx *g) {
   for (SortedPairs *sp : {&g->sortLoad, &g->sortMine}) {
     cudaFree(sp->items);
     cudaFree(sp->recs);
+    cudaFree(sp->recsMem);
     cudaFree(sp->atoms);
     cudaFree(sp->total);
   }
@@ -217,6 +227,7 @@ int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out
     sp.capacity = c;
   }
   if (!sp.total) DFTBP_CUDA(ctx, cudaMalloc((void **)&sp.total, sizeof(int)));
+  DFTBP_TRY(growTo(ctx, &sp.recsMem, &sp.recsMemCap, std::max(nWork, 1LL)));
   DFTBP_TRY(growTo(ctx, &ctx->sortKeys, &ctx->sortKeysCap, std::max(nWork, 1LL)));
   DFTBP_TRY(growTo(ctx, &ctx->sortBins, &ctx->sortBinsCap, nBins64));
   DFTBP_CUDA(ctx, cudaMemsetAsync(ctx->sortBins, 0, sizeof(int) * nBins64, ctx->stream));
@@ -229,13 +240,12 @@ int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out
     DFTBP_CUDA(ctx, cudaFuncSetAttribute(ps_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
     DFTBP_CUDA(ctx, cudaFuncSetAttribute(ps_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
     ps_keys<<<grid, kSortThreads, smemBytes, ctx->stream>>>(work, nWork, g.mNeigh + 1, ctx->nSpecies, nBins, nKeys,
-                                                           g.coords, g.species, g.iNeighbour, binScale,
-                                                           ctx->sortKeys, ctx->sortBins);
+                                                           g.coords, g.species, g.iNeighbour, g.iPair, binScale,
+                                                           ctx->sortKeys, ctx->sortBins, sp.recsMem);
     ps_scan<<<1, 1024, 0, ctx->stream>>>(ctx->sortBins, nBuckets, nBins, sp.total, sp.items, sp.recs);
     ps_scatter<<<grid, kSortThreads, smemBytes, ctx->stream>>>(work, nWork, nKeys, ctx->sortKeys, ctx->sortBins,
-                                                              sp.items, sp.recs, sp.atoms, g.mNeigh + 1,
-                                                              ctx->nSpecies, g.coords, g.species, g.iNeighbour,
-                                                              g.iPair, g.img2CentCell);
+                                                              sp.items, sp.recs, sp.atoms, g.mNeigh + 1, sp.recsMem,
+                                                              g.iNeighbour, g.img2CentCell);
     ctx->launches += 3;
   } else {
     DFTBP_CUDA(ctx, cudaMemsetAsync(sp.total, 0, sizeof(int), ctx->stream));

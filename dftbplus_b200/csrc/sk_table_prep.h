@@ -116,6 +116,63 @@ inline bool prepareSkTable(SkTableDev &t, int nGrid, int nInteg, double dist, in
   return true;
 }
 
+// Position of the integrals of shell-pair type c = l1 * 4 + l2 in an exchange row ordered by type,
+// types with l1, l2 <= lmax only (the device-side twin is skd::caseSlot<LMAX>, sk_dmat_eval.cuh).
+inline int caseSlotHost(int c, int lmax) {
+  int n = 0;
+  for (int cc = 0; cc < c; ++cc) {
+    const int l1 = cc >> 2, l2 = cc & 3;
+    if (l1 <= lmax && l2 <= lmax) n += (l1 < l2 ? l1 : l2) + 1;
+  }
+  return n;
+}
+
+// Shell-pair program of a species pair (SpPairProg::shPair / integDst / caseOff / integSlot) from its
+// shell lists; lmaxAll = highest angular momentum of any species of the run.
+// Returns false if the pair has more shell pairs or integrals than the program holds.
+inline bool fillShellProgram(SpPairProg &pg, int lmaxAll = 3) {
+  for (int c = 0; c < 16; ++c) pg.caseOff[c] = 0xFFFF;
+  for (int l = 0; l < 4; ++l) pg.shellOfL1[l] = -1;
+  pg.simple = 1;
+  for (int sh = 0; sh < pg.nSh1; ++sh) {
+    const int l = (int)((pg.shells1 >> (4 * sh)) & 0xF);
+    if (l > 3) return false;
+    if (pg.shellOfL1[l] >= 0) pg.simple = 0;
+    pg.shellOfL1[l] = (signed char)sh;
+  }
+  {
+    int seen = 0;
+    for (int sh = 0; sh < pg.nSh2; ++sh) {
+      const int l = (int)((pg.shells2 >> (4 * sh)) & 0xF);
+      if (l > 3) return false;
+      if (seen & (1 << l)) pg.simple = 0;
+      seen |= 1 << l;
+    }
+  }
+  int ind = 0, iCol = 0, n = 0;
+  for (int sh1 = 0; sh1 < pg.nSh1; ++sh1) {
+    const int l1 = (int)((pg.shells1 >> (4 * sh1)) & 0xF);
+    int iRow = 0;
+    for (int sh2 = 0; sh2 < pg.nSh2; ++sh2) {
+      const int l2 = (int)((pg.shells2 >> (4 * sh2)) & 0xF);
+      const int lmin = l1 < l2 ? l1 : l2;
+      if (n >= kMaxInteg || ind + lmin + 1 > kMaxInteg || l1 > 3 || l2 > 3) return false;
+      const int first = iRow + pg.nOrb2 * iCol;
+      pg.shPair[n++] = (unsigned short)((first << 4) | (l1 * 4 + l2));
+      for (int k = 0; k <= lmin; ++k) pg.integDst[ind + k] = (unsigned short)(first + k);
+      if (pg.simple) {
+        pg.caseOff[l1 * 4 + l2] = (unsigned short)first;
+        for (int k = 0; k <= lmin; ++k) pg.integSlot[ind + k] = (unsigned char)(caseSlotHost(l1 * 4 + l2, lmaxAll) + k);
+      }
+      ind += lmin + 1;
+      iRow += 2 * l2 + 1;
+    }
+    iCol += 2 * l1 + 1;
+  }
+  pg.nShPair = n;
+  return true;
+}
+
 // SlakoEqGrid_getCutoff, slakoeqgrid.F90:162-179
 inline double skTableCutoff(int nGrid, double dist, int method) {
   return (double)nGrid * dist + (method == DFTBP_B200_SK_EQGRID_OLD ? kDistFudgeOld : kDistFudge);

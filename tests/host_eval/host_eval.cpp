@@ -15,6 +15,7 @@ template <class T>
 inline T __ldg(const T *p) { return *p; }
 
 #include "../../dftbplus_b200/csrc/sk_lane_eval.cuh"
+#include "../../dftbplus_b200/csrc/sk_dmat_eval.cuh"
 #include "../../dftbplus_b200/csrc/sk_table_prep.h"
 
 using namespace dftbp_b200;
@@ -48,6 +49,7 @@ SpPairProg makeProg(int nSh1, const int *sh1, int nSh2, const int *sh2) {
   pg.canon1 = canon(nSh1, sh1);
   pg.canon2 = canon(nSh2, sh2);
   pg.nY = (lmax1 + lmax2 + 1) * (lmax1 + lmax2 + 1);
+  fillShellProgram(pg);
   return pg;
 }
 
@@ -72,6 +74,35 @@ int host_eval_block(int nSh1, const int *sh1, int nSh2, const int *sh2, int nGri
   pg.H = t; pg.S = t;
   skLaneEvalAny<3>(
       pg, t, r, d[0], d[1], d[2], [&](int first, int e, double v) { out[first + e] = v; }, [](int, int) {});
+  return pg.nOrb1 * pg.nOrb2;
+}
+
+// The same block through the compact D-matrix evaluator of K1 (sk_dmat_eval.cuh: frame, D^1 / D^2,
+// shell-pair loops; f shells through the Gaunt code).
+int host_eval_block_d(int nSh1, const int *sh1, int nSh2, const int *sh2, int nGrid, double dist, int method,
+                      const double *tab, double r, const double *d, int lmaxT, double *out) {
+  SpPairProg pg = makeProg(nSh1, sh1, nSh2, sh2);
+  SkTableDev t;
+  std::vector<double> tail, padded(tab, tab + (size_t)nGrid * pg.nInteg);
+  if (!prepareSkTable(t, nGrid, pg.nInteg, dist, method, tab, tail)) return -1;
+  padded.resize(padded.size() + 8, 0.0);
+  t.tab = padded.data(); t.tail = tail.data();
+  pg.H = t; pg.S = t;
+  LaneInterp li;
+  laneInterpSetup(t, r, li);
+  skd::DMat D;
+  skd::buildD<true>(d[0], d[1], d[2], D);
+  if (lmaxT == 3) {
+    double Y[49];
+    skg::harmonics<6>(d[0], d[1], d[2], Y);
+    skd::evalBlock<3>(pg, t, li, D, Y, out);
+  } else if (lmaxT == 2) {
+    double Y[1] = {1.0};
+    skd::evalBlock<2>(pg, t, li, D, Y, out);
+  } else {
+    double Y[1] = {1.0};
+    skd::evalBlock<1>(pg, t, li, D, Y, out);
+  }
   return pg.nOrb1 * pg.nOrb2;
 }
 

@@ -31,6 +31,8 @@ def host():
     lib.host_eval_block.argtypes = common
     lib.host_eval_block.restype = ctypes.c_int
     lib.host_eval_wdot.argtypes = common
+    lib.host_eval_block_d.argtypes = common
+    lib.host_eval_block_d.restype = ctypes.c_int
     lib.host_eval_wdot.restype = ctypes.c_double
     return lib
 
@@ -84,6 +86,45 @@ def test_blocks_match_the_oracle(method, host):
                     assert np.all(got == 0.0)
                 worst = max(worst, err / scale if scale > 1e-200 else 0.0)
     assert worst < 1e-11
+
+
+# poles and axes of the frame construction of the D-matrix evaluator
+DIRS = [(0, 0, 1), (0, 0, -1), (1, 0, 0), (0, 1, 0), (-1, 0, 0), (0, -1, 0), (1e-9, 0, -1), (1e-160, 1e-160, -1),
+        (0.6, 0.0, -0.8), (1, 1, 1), (-1, 2, -3)]
+
+
+@pytest.mark.parametrize("method", [1, 2])
+def test_dmatrix_blocks_match_the_oracle(method, host):
+    """K1's compact evaluator (sk_dmat_eval.cuh: frame -> D^1, D^2 -> shell-pair loops; f shells through
+    the Gaunt code), every instantiation that can take the species pair, poles of the frame included."""
+    rng = np.random.default_rng(300 + method)
+    dist, n_grid = 0.02, 500
+    worst = 0.0
+    for sh1, sh2 in SHELLS + [([0, 0, 1], [0, 1, 2, 2]), ([2, 1, 0, 1], [1])]:
+        m = oracle.Model([sh1, sh2])
+        n_int = m.n_integrals(1, 2)
+        tab = _table(rng, n_grid, n_int, dist)
+        n1, n2 = sum(2 * l + 1 for l in sh1), sum(2 * l + 1 for l in sh2)
+        a1, a2 = np.array(sh1, dtype=np.int32), np.array(sh2, dtype=np.int32)
+        lmax = max(sh1 + sh2)
+        dirs = [np.array(d, dtype=np.float64) for d in DIRS] + [rng.normal(size=3) for _ in range(6)]
+        for i, d in enumerate(dirs):
+            d = d / np.linalg.norm(d)
+            r = DISTS[i % len(DISTS)]
+            sk = oracle.sk_eval(tab, dist, r, method=method)
+            ref = oracle.rotate_h0(m, sk, d, 1, 2)[:n2, :n1]
+            for lmax_t in range(max(lmax, 1), 4):
+                out = np.full(n1 * n2, np.nan)
+                n = host.host_eval_block_d(len(sh1), _ptr(a1, ctypes.c_int), len(sh2), _ptr(a2, ctypes.c_int), n_grid,
+                                           dist, method, _ptr(tab, ctypes.c_double), r, _ptr(d, ctypes.c_double), lmax_t,
+                                           _ptr(out, ctypes.c_double))
+                assert n == n1 * n2
+                got = out.reshape(n1, n2).T
+                scale = max(np.abs(ref).max(), 1e-300)
+                err = np.abs(got - ref).max()
+                assert err <= 1e-12 * scale + 1e-18, (sh1, sh2, r, d, lmax_t, err, scale)
+                worst = max(worst, err / scale if scale > 1e-200 else 0.0)
+    assert worst < 1e-12
 
 
 def test_weight_contracted_form_equals_direct_contraction(host):

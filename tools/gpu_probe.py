@@ -66,6 +66,18 @@ def main():
     out["k1_ms"] = ms
     out["k1_pairs_per_s"] = pairs / ms * 1e3
     out["k1_GBs"] = 16.0 * ss / ms / 1e6
+    if "--k1-only" in sys.argv:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        def flushed():
+            flush.zero_()
+            hp.buildH0S(sk.selfegy, ham, over)
+        with torch.cuda.stream(stream):
+            msf = timeit(flushed, stream)
+            msz = timeit(lambda: flush.zero_(), stream)
+        out["k1_flushed_ms"] = msf - msz
+        print(json.dumps(out))
+        hp.close()
+        return
     rho = over * torch.randn(ss, **f64)
     edm = over * torch.randn(ss, **f64)
     qq = torch.zeros((nAtom, hp.mOrb), **f64)
