@@ -37,9 +37,6 @@ struct K5Params {
   const int2 *atoms;    // (iAtom1, iAtom2f) per slot
   const int *total;
   int ld, nSpecies, mOrb, nAtom, nSpin, sparseSize, pitch;
-  int nIntMax;  // integral columns per table the shared windows hold
-  const double *EDM, *shift;  // SCC, diagonal shift blocks: the S weights are formed in the kernel from these
-  const int *shiftFull;       // device flag: some shift block has off-diagonal elements
   const double *DM;     // rho, first spin channel = wH
   const double *negWS;  // -wS: Erho (no SCC) or the array prepared by k5_force_weights
   double delta;
@@ -229,292 +226,101 @@ void launchWeightsDiag(const K5WeightParams &wp, int nSpin, int grid, cudaStream
   else k5_force_weights_diag<BATCH, 4><<<grid, 256, 0, stream>>>(wp);
 }
 
-// ---- round 2: displacement-parallel form ------------------------------------------------------------
-// One CTA of six warps per chunk of 32 sorted pairs; warp d evaluates displacement d (bond vector
-// +- delta e_j) of all 32 pairs, BOTH matrices, against weight tiles that the whole CTA staged once:
-//   0. every warp loads the records of the 32 pairs; warp 0 determines the union of the table windows;
-//   1. staging, one exposed HBM / L2 round trip per chunk:
-//      - the 32 rho_1 blocks (H weights) arrive as 32 TMA bulk copies (cp.async.bulk + mbarrier), one
-//        per pair, issued by the lane that owns the pair; so do the S weights when they are an array
-//        (Erho without SCC; the -wS array of k5_force_weights<true> for full shift blocks);
-//      - plain SCC / collinear spin (diagonal shift blocks): the S weights
-//        -wS = Erho - sum_spin 1/2 rho_s (V1_s(a,a) + V2_s(b,b)) are formed by the 192 threads on
-//        the way into the tile (the separate 74 us streaming pass of round 1 and its 130 MB are gone);
-//      - cp.async of the table windows: rows [jLo, jLo + nRows) of every integral column of H0 and S;
-//        every displaced distance of the chunk interpolates from these few rows;
-//   2. the weights are folded into their Gaunt-contracted form W in place, shell pairs dealt out over
-//      the warps (warp d: matrix d & 1, every third shell pair), lanes on pairs;
-//   3. warp d, lane q: distance and harmonics of the displaced vector, interpolation from the
-//      shared windows (8 LDS + 8 FMA per integral), sum_L a_L(r) sum_M W_LM Y_LM for both matrices;
-//   4. warps 0-2 combine (+) and (-) of their Cartesian direction and add to deriv.
-// Compared with the round-1 kernel (one warp = one matrix of a chunk, six displacements one after the
-// other in every lane, 255 registers, 8 warps per SM): distance, window and harmonics are shared by
-// the two matrices, the table reads come from shared memory instead of 1344 LDG per pair, and 18
-// warps per SM are resident.
-constexpr int kWinRowsF = 24;
-
-struct K5Shared {
-  unsigned long long mbar;
-  int jLo[2], nRows[2];
-};
-
-// first element of pair q's block inside its tile row: row q starts at q * pitch (odd pitch, one or two
-// spare elements in front) and the block is placed so that tile and sparse array agree in the
-// 16-byte phase of every element -- a bulk copy of the enclosing 16-byte aligned range then lands right
-__device__ __forceinline__ int k5RowStart(int q, int pitch, int ind) {
-  const int r = q * pitch + 1;
-  return r + ((ind ^ r) & 1);
-}
-
-template <int LMAX, bool STRESS, int NB>
-__global__ void __launch_bounds__(192, NB) k5_pair_forces(const K5Params p) {
-  constexpr int NY = (2 * LMAX + 1) * (2 * LMAX + 1);
-  extern __shared__ __align__(16) double smem[];
-  const int tid = threadIdx.x, lane = tid & 31, d = tid >> 5;  // d = displacement handled by this warp
-  const int pitch = p.pitch, nIntMax = p.nIntMax;
-  double *tileH = smem, *tileS = tileH + 32 * pitch;
-  double *win = tileS + 32 * pitch;             // [2][nIntMax][kWinRowsF]
-  double *red = win + 2 * nIntMax * kWinRowsF;  // [6][32]
-  K5Shared *info = reinterpret_cast<K5Shared *>(red + 6 * 32);
-  const unsigned tileH0 = (unsigned)__cvta_generic_to_shared(tileH), tileS0 = (unsigned)__cvta_generic_to_shared(tileS),
-                 winS0 = (unsigned)__cvta_generic_to_shared(win), mbarS = (unsigned)__cvta_generic_to_shared(&info->mbar);
-  double st[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // STRESS (warp 0): this lane's share of st(jj,ii)
+template <int LMAX, bool STRESS, int WARPS, int UNR>
+__global__ void __launch_bounds__(32 * WARPS, 1) k5_derivative_shift(const K5Params p) {
+  extern __shared__ double smem[];
+  double st[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // STRESS: this lane's share of st(jj,ii)
+  const int lane = threadIdx.x & 31, wIn = threadIdx.x >> 5, nW = blockDim.x >> 5;
+  double *stage = smem + (size_t)wIn * 32 * p.pitch;
+  double *row = stage + (size_t)lane * p.pitch;
   const int nChunks = __ldg(p.total) >> 5;
-  const double inv = 1.0 / p.delta;
-  // where the S weights come from: 0 = an array (p.negWS), 1 = formed here from Erho, rho_s and diagonal shifts
-  const bool fuse = p.shift != nullptr && __ldg(p.shiftFull) == 0;
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbarS) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  unsigned phase = 0;
-  for (int chunk = blockIdx.x; chunk < nChunks; chunk += gridDim.x) {
+  const int nItems = 2 * nChunks;
+  for (int item = blockIdx.x * nW + wIn; item < nItems; item += gridDim.x * nW) {
+    const int chunk = item >> 1;
+    const bool isS = item & 1;
     const K5Pair pr = k5LoadPair(p, chunk, lane);
     const bool live = pr.live;
+    const int ind = pr.ind, iAt1 = pr.iAt1, iAt2f = pr.iAt2f;
     const SpPairProg &pg = p.progs[pr.sp];
-    const int n2 = pg.nOrb2, nElem = pg.nOrb1 * n2, nInteg = pg.nInteg;
-    const double v0 = pr.v0, v1 = pr.v1, v2 = pr.v2;
-    const int rowStart = k5RowStart(lane, pitch, pr.ind);
-    if (d == 0) {
-      // ---- 0. union of the table windows of the chunk; one more row on either side: a displaced
-      // distance may fall into the neighbouring grid interval
-      const double dist = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
-#pragma unroll
-      for (int mat = 0; mat < 2; ++mat) {
-        const SkTableDev &t = mat ? pg.S : pg.H;
-        LaneInterp li;
-        laneInterpSetup(t, dist, li);
-        int lo = (live && li.mode == 0) ? li.j0 : 0x7fffffff, hi = (live && li.mode == 0) ? li.j0 : -1;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-          hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-        }
-        if (lane == 0) {
-          const int first = max(0, lo - 1), last = min(t.nGrid - 8, hi + 1);
-          const int nR = hi >= 0 ? last - first + 8 : 0;
-          info->jLo[mat] = first;
-          info->nRows[mat] = (nR <= kWinRowsF && nInteg <= nIntMax) ? nR : 0;  // 0: everybody reads global memory
-        }
-      }
-      // ---- 1a. bulk copies of the weight blocks: [ind, ind + nElem) widened to 16-byte boundaries
-      // (never past the end of the array: the last element then comes by a plain load)
-      int gs = pr.ind & ~1, ge = (pr.ind + nElem + 1) & ~1;
-      const bool clip = ge > p.sparseSize;
-      if (clip) ge -= 2;
-      const int nCopy = (live && ge > gs) ? 8 * (ge - gs) : 0;
-      const int nArr = fuse ? 1 : 2;
-      int bytes = nCopy * nArr;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
-      if (lane == 0)
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbarS), "r"(bytes) : "memory");
-      __syncwarp();
-      if (nCopy > 0) {
-        const unsigned dstOff = 8u * (unsigned)(rowStart - (pr.ind - gs));
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         tileH0 + dstOff),
-                     "l"(p.DM + gs), "r"(nCopy), "r"(mbarS)
-                     : "memory");
-        if (!fuse)
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                           tileS0 + dstOff),
-                       "l"(p.negWS + gs), "r"(nCopy), "r"(mbarS)
-                       : "memory");
-      }
-      if (live && clip) {
-        tileH[rowStart + nElem - 1] = __ldg(p.DM + pr.ind + nElem - 1);
-        if (!fuse) tileS[rowStart + nElem - 1] = __ldg(p.negWS + pr.ind + nElem - 1);
-      }
-    }
-    __syncthreads();
-    // ---- 1b. table windows
-#pragma unroll
-    for (int mat = 0; mat < 2; ++mat) {
-      const SkTableDev &t = mat ? pg.S : pg.H;
-      const int nR = info->nRows[mat], n = nR * nInteg;
-      if (n > 0) {
-        const double *__restrict__ src = t.tab + info->jLo[mat];
-        const unsigned dst = winS0 + 8u * (unsigned)(mat * nIntMax * kWinRowsF);
-        const unsigned M = (65536u + (unsigned)nR - 1u) / (unsigned)nR;  // idx / nR = idx * M >> 16 (idx < 768)
-        for (int idx = tid; idx < n; idx += 192) {
-          const unsigned k = ((unsigned)idx * M) >> 16, rr = (unsigned)idx - k * (unsigned)nR;
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * (k * kWinRowsF + rr)),
-                       "l"(src + (size_t)k * t.nGrid + rr)
-                       : "memory");
-        }
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    // ---- 1c. S weights of plain SCC: -wS(b,a) = Erho(b,a) - sum_spin 1/2 rho_s(b,a) (V1_s(a,a) + V2_s(b,b))
-    // (derivative_blockEuclidean, forces.F90:640-656, with diagonal shift blocks), element by element over
-    // the 32 blocks: flat index -> (pair, element) by multiply-shift, the pair's data from the lane that owns it
-    if (fuse) {
-      const int desc = live ? pr.ind : -1;
+    const SkTableDev tab = isS ? pg.S : pg.H;
+    const int nElem = pg.nOrb1 * pg.nOrb2;
+
+    // ---- 1. stage the contraction weights of the 32 pairs: rho_1 blocks for the H part, -wS blocks
+    // (Erho without SCC, the array prepared by k5_force_weights with SCC) for the S part.  Flat
+    // index idx = lane + 32 k over the 32 * nElem elements, (pair, element) = (idx / nElem,
+    // idx % nElem) by multiply-shift; cp.async (LDGSTS) moves the 8-byte elements global -> shared
+    // without passing through registers, so the whole tile is in flight at once: one HBM latency
+    // per item.
+    {
+      const int desc = live ? ind : -1;
       const unsigned M = (1048576u + (unsigned)nElem - 1u) / (unsigned)nElem;
-      const unsigned M2 = (1048576u + (unsigned)n2 - 1u) / (unsigned)n2;  // e / n2 = e * M2 >> 20 (e < 256)
-      const int nTot = 32 * nElem, mo2 = p.mOrb * p.mOrb, dstep = p.mOrb + 1;
-      for (int base = 0; base < nTot; base += 192) {
-        const unsigned idx = (unsigned)(base + tid);
-        const unsigned q = min((idx * M) >> 20, 31u);
+      const double *__restrict__ src = isS ? p.negWS : p.DM;
+      const unsigned stageS = (unsigned)__cvta_generic_to_shared(stage);
+#pragma unroll 4
+      for (int k = 0; k < nElem; ++k) {
+        const unsigned idx = (unsigned)(lane + 32 * k);
+        const unsigned q = (idx * M) >> 20;
         const unsigned e = idx - q * (unsigned)nElem;
         const int bq = __shfl_sync(0xffffffffu, desc, (int)q);
-        const int a1 = __shfl_sync(0xffffffffu, pr.iAt1, (int)q), a2 = __shfl_sync(0xffffffffu, pr.iAt2f, (int)q);
-        if (bq >= 0 && idx < (unsigned)nTot) {  // dead pairs never read their row
-          const unsigned a = (e * M2) >> 20, b = e - a * (unsigned)n2;  // element (row b, col a)
-          double s = __ldg(p.EDM + bq + e);
-          for (int iSpin = 0; iSpin < p.nSpin; ++iSpin) {
-            const double r = __ldg(p.DM + (size_t)p.sparseSize * iSpin + bq + e);
-            const double x1 = __ldg(p.shift + (size_t)mo2 * (a1 + (size_t)p.nAtom * iSpin) + a * dstep);
-            const double x2 = __ldg(p.shift + (size_t)mo2 * (a2 + (size_t)p.nAtom * iSpin) + b * dstep);
-            s = fma(-0.5 * r, x1 + x2, s);
-          }
-          tileS[k5RowStart((int)q, pitch, bq) + e] = s;
-        }
+        if (bq >= 0)  // dead pairs never read their row
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(stageS + 8u * (q * (unsigned)p.pitch + e)),
+                       "l"(src + bq + e)
+                       : "memory");
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-    {
-      // the bulk copies have landed when the barrier's phase flips
-      asm volatile(
-          "{\n\t"
-          ".reg .pred P1;\n\t"
-          "K5_WAIT:\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-          "@P1 bra K5_DONE;\n\t"
-          "bra K5_WAIT;\n\t"
-          "K5_DONE:\n\t"
-          "}" ::"r"(mbarS),
-          "r"(phase)
-          : "memory");
-      phase ^= 1u;
-    }
-    __syncthreads();
-    // ---- 2. weights -> W in place; warp d takes matrix d & 1 and every third shell pair
-    const int canon = canonCase(pg);
-    if (live) {
-      double *row = ((d & 1) ? tileS : tileH) + rowStart;
-      const int part = d >> 1;
-      switch (canon) {
-        case 0: skLaneWBuildCanonPart<0, 0>(row, part, 3); break;
-        case 1: if constexpr (LMAX >= 1) skLaneWBuildCanonPart<0, 1>(row, part, 3); break;
-        case 2: if constexpr (LMAX >= 2) skLaneWBuildCanonPart<0, 2>(row, part, 3); break;
-        case 3: if constexpr (LMAX >= 1) skLaneWBuildCanonPart<1, 0>(row, part, 3); break;
-        case 4: if constexpr (LMAX >= 1) skLaneWBuildCanonPart<1, 1>(row, part, 3); break;
-        case 5: if constexpr (LMAX >= 2) skLaneWBuildCanonPart<1, 2>(row, part, 3); break;
-        case 6: if constexpr (LMAX >= 2) skLaneWBuildCanonPart<2, 0>(row, part, 3); break;
-        case 7: if constexpr (LMAX >= 2) skLaneWBuildCanonPart<2, 1>(row, part, 3); break;
-        case 8: if constexpr (LMAX >= 2) skLaneWBuildCanonPart<2, 2>(row, part, 3); break;
-        default: {
-          const int nShPair = pg.nShPair;
-          for (int i = part; i < nShPair; i += 3) {
-            const int e = pg.shPair[i];
-            double *sub = row + (e >> 4);
-            skg::wbuildDispatch<LMAX>(
-                (e >> 2) & 3, e & 3, [&](int a, int b) { return sub[b + n2 * a]; },
-                [&](int a, int b, double v) { sub[b + n2 * a] = v; });
-          }
-        }
-      }
-    }
-    __syncthreads();
-    // ---- 3. displacement d of every pair
-    {
-      const int jj = d >> 1;
-      // vect(jj) = vect(jj) - real(2*ii-3) * deltaXDiff : ii=1 -> +delta, ii=2 -> -delta
-      const double sgn = (d & 1) ? -1.0 : 1.0;
-      const double d0 = jj == 0 ? v0 + sgn * p.delta : v0;
-      const double d1 = jj == 1 ? v1 + sgn * p.delta : v1;
-      const double d2 = jj == 2 ? v2 + sgn * p.delta : v2;
-      double t = 0.0;
-      if (live) {
+    __syncwarp();
+
+    // ---- 2. fold the weights of this lane's pair into W (independent of the bond vector), then six
+    // displaced evaluations, each an interpolation + harmonics + short dot product (sk_lane_eval.cuh)
+    const double v0 = pr.v0, v1 = pr.v1, v2 = pr.v2;
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+    if (__any_sync(0xffffffffu, live)) {
+      if (live) skLaneWBuildAny<LMAX>(pg, row);
+#pragma unroll UNR
+      for (int k = 0; k < 6; ++k) {
+        const int jj = k >> 1;
+        // vect(jj) = vect(jj) - real(2*ii-3) * deltaXDiff : ii=1 -> +delta, ii=2 -> -delta
+        const double sgn = (k & 1) ? -1.0 : 1.0;
+        const double d0 = jj == 0 ? v0 + sgn * p.delta : v0;
+        const double d1 = jj == 1 ? v1 + sgn * p.delta : v1;
+        const double d2 = jj == 2 ? v2 + sgn * p.delta : v2;
         const double dist = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
         const double rinv = 1.0 / dist;
-        const double ux = d0 * rinv, uy = d1 * rinv, uz = d2 * rinv;
-        LaneInterp liH, liS;
-        laneInterpSetup(pg.H, dist, liH);
-        if (pg.sameGrid) liS = liH;
-        else laneInterpSetup(pg.S, dist, liS);
-        // this lane's window inside the shared rows, or nullptr: global loads (tail of the table, chunk too wide)
-        const double *yH = nullptr, *yS = nullptr;
-        {
-          const int oH = liH.j0 - info->jLo[0], oS = liS.j0 - info->jLo[1];
-          if (liH.mode == 0 && oH >= 0 && oH + 8 <= info->nRows[0]) yH = win + oH;
-          if (liS.mode == 0 && oS >= 0 && oS + 8 <= info->nRows[1]) yS = win + nIntMax * kWinRowsF + oS;
-        }
-        const double *rowH = tileH + rowStart, *rowS = tileS + rowStart;
-        double Y[NY];
-        switch (canon) {
-          case 0: harmonicsInto<0>(ux, uy, uz, Y); t = skLanePairDotCanon<0, 0>(pg, liH, liS, yH, yS, kWinRowsF, Y, rowH, rowS); break;
-          case 1: if constexpr (LMAX >= 1) { harmonicsInto<1>(ux, uy, uz, Y); t = skLanePairDotCanon<0, 1>(pg, liH, liS, yH, yS, kWinRowsF, Y, rowH, rowS); } break;
-          case 2: if constexpr (LMAX >= 2) { harmonicsInto<2>(ux, uy, uz, Y); t = skLanePairDotCanon<0, 2>(pg, liH, liS, yH, yS, kWinRowsF, Y, rowH, rowS); } break;
-          case 3: if constexpr (LMAX >= 1) { harmonicsInto<1>(ux, uy, uz, Y); t = skLanePairDotCanon<1, 0>(pg, liH, liS, yH, yS, kWinRowsF, Y, rowH, rowS); } break;
-          case 4: if constexpr (LMAX >= 1) { harmonicsInto<2>(ux, uy, uz, Y); t = skLanePairDotCanon<1, 1>(pg, liH, liS, yH, yS, kWinRowsF, Y, rowH, rowS); } break;
-          case 5: if constexpr (LMAX >= 2) { harmonicsInto<3>(ux, uy, uz, Y); t = skLanePairDotCanon<1, 2>(pg, liH, liS, yH, yS, kWinRowsF, Y, rowH, rowS); } break;
-          case 6: if constexpr (LMAX >= 2) { harmonicsInto<2>(ux, uy, uz, Y); t = skLanePairDotCanon<2, 0>(pg, liH, liS, yH, yS, kWinRowsF, Y, rowH, rowS); } break;
-          case 7: if constexpr (LMAX >= 2) { harmonicsInto<3>(ux, uy, uz, Y); t = skLanePairDotCanon<2, 1>(pg, liH, liS, yH, yS, kWinRowsF, Y, rowH, rowS); } break;
-          case 8: if constexpr (LMAX >= 2) { harmonicsInto<4>(ux, uy, uz, Y); t = skLanePairDotCanon<2, 2>(pg, liH, liS, yH, yS, kWinRowsF, Y, rowH, rowS); } break;
-          default:
-            skg::harmonics<2 * LMAX>(ux, uy, uz, Y);
-            t = skLanePairDot<LMAX>(pg, liH, liS, yH, yS, kWinRowsF, Y, rowH, rowS);
-        }
+        double acc = live ? skLaneWDotAny<LMAX>(pg, tab, dist, d0 * rinv, d1 * rinv, d2 * rinv, row) : 0.0;
+        acc *= isS ? sgn : -sgn;  // (tmp(ii=2) - tmp(ii=1)); the S tile holds -wS
+        if (jj == 0) g0 += acc;
+        if (jj == 1) g1 += acc;
+        if (jj == 2) g2 += acc;
       }
-      red[32 * d + lane] = t;
     }
-    // generic-proxy accesses of the tiles end here; the next chunk's bulk copies write them through the async proxy
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    // ---- 4. g(jj) = (t(+) - t(-)) / delta (the S tile holds -wS); deriv(:,iAtom1) += g, deriv(:,iAtom2f) -= g
-    if (!STRESS) {
-      if (d < 3 && live && pr.iAt1 != pr.iAt2f) {
-        const double g = (red[32 * (2 * d) + lane] - red[32 * (2 * d + 1) + lane]) * inv;
-        atomicAdd(p.deriv + 3 * pr.iAt1 + d, g);
-        atomicAdd(p.deriv + 3 * pr.iAt2f + d, -g);
+    // ---- 3. deriv(:,iAtom1) += g, deriv(:,iAtom2f) -= g
+    if (live) {
+      const double inv = 1.0 / p.delta;
+      g0 *= inv; g1 *= inv; g2 *= inv;
+      if (p.deriv && iAt1 != iAt2f) {
+        atomicAdd(p.deriv + 3 * iAt1, g0);
+        atomicAdd(p.deriv + 3 * iAt1 + 1, g1);
+        atomicAdd(p.deriv + 3 * iAt1 + 2, g2);
+        atomicAdd(p.deriv + 3 * iAt2f, -g0);
+        atomicAdd(p.deriv + 3 * iAt2f + 1, -g1);
+        atomicAdd(p.deriv + 3 * iAt2f + 2, -g2);
       }
-    } else if (d == 0 && live) {
-      double g[3];
+      if (STRESS) {
+        // st(jj,ii) += fac * intermed(jj) * vect(ii), vect = coords(:,iAtom1) - coords(:,iAtom2) = -v,
+        // fac = 2 unless the neighbour is a periodic image of the atom itself (stress.F90:158-176)
+        const double fac = iAt1 != iAt2f ? -2.0 : -1.0;
+        const double g[3] = {fac * g0, fac * g1, fac * g2}, v[3] = {v0, v1, v2};
 #pragma unroll
-      for (int j = 0; j < 3; ++j) g[j] = (red[32 * (2 * j) + lane] - red[32 * (2 * j + 1) + lane]) * inv;
-      if (p.deriv && pr.iAt1 != pr.iAt2f) {
+        for (int ii = 0; ii < 3; ++ii)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          atomicAdd(p.deriv + 3 * pr.iAt1 + j, g[j]);
-          atomicAdd(p.deriv + 3 * pr.iAt2f + j, -g[j]);
-        }
+          for (int jj = 0; jj < 3; ++jj) st[jj + 3 * ii] = fma(g[jj], v[ii], st[jj + 3 * ii]);
       }
-      // st(jj,ii) += fac * intermed(jj) * vect(ii), vect = coords(:,iAtom1) - coords(:,iAtom2) = -v,
-      // fac = 2 unless the neighbour is a periodic image of the atom itself (stress.F90:158-176)
-      const double fac = pr.iAt1 != pr.iAt2f ? -2.0 : -1.0;
-      const double v[3] = {v0, v1, v2};
-#pragma unroll
-      for (int ii = 0; ii < 3; ++ii)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) st[j + 3 * ii] = fma(fac * g[j], v[ii], st[j + 3 * ii]);
     }
-    // (red is rewritten only after three more barriers)
+    __syncwarp();  // the tile is restaged by the next item
   }
-  if (STRESS && d == 0) {  // one reduction per CTA and kernel: 9 atomics
+  if (STRESS) {  // one reduction per warp and kernel: 9 atomics per warp
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
       double x = st[k];
@@ -656,36 +462,36 @@ int launchRichardson(dftbp_b200_ctx *ctx, const K5Params &p, long long chunks) {
   return 0;
 }
 
-template <int LMAX, bool STRESS, int NB>
-int launchForces(dftbp_b200_ctx *ctx, K5Params p, long long chunks) {
-  int nIntMax = 1;
-  for (const SpPairProg &pg : ctx->progs) nIntMax = std::max(nIntMax, pg.nInteg);
-  p.nIntMax = nIntMax;
-  const size_t smemBytes = sizeof(double) * (2 * 32 * (size_t)p.pitch + 2 * (size_t)nIntMax * kWinRowsF + 6 * 32) + sizeof(K5Shared);
-  DFTBP_CHECK(ctx, smemBytes <= ctx->smemOptin, "derivative_shift: weight tiles do not fit into shared memory");
-  DFTBP_CUDA(ctx, cudaFuncSetAttribute(k5_pair_forces<LMAX, STRESS, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smemBytes));
-  int perSm = 1;  // resident CTAs per SM (registers and the weight tiles decide)
-  DFTBP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k5_pair_forces<LMAX, STRESS, NB>, 192, smemBytes));
-  const int grid = (int)std::max<long long>(1, std::min<long long>(chunks, (long long)ctx->smCount * std::max(perSm, 1)));
-  k5_pair_forces<LMAX, STRESS, NB><<<grid, 192, smemBytes, ctx->stream>>>(p);
+template <int LMAX, bool STRESS, int WARPS, int UNR>
+int launchTypedS(dftbp_b200_ctx *ctx, const K5Params &p, long long items, int warpsMax, size_t perWarp) {
+  const int warps = std::min(WARPS, warpsMax);
+  if (warps < WARPS) return fail(ctx, DFTBP_B200_EINVAL, "derivative_shift: weight tile too large for %d warps", WARPS);
+  const size_t smemBytes = perWarp * WARPS;
+  DFTBP_CUDA(ctx, cudaFuncSetAttribute(k5_derivative_shift<LMAX, STRESS, WARPS, UNR>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+  int perSm = 1;  // resident CTAs per SM (registers and the weight tile decide)
+  DFTBP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k5_derivative_shift<LMAX, STRESS, WARPS, UNR>,
+                                                                32 * WARPS, smemBytes));
+  const int grid = (int)std::max<long long>(
+      1, std::min<long long>((items + WARPS - 1) / WARPS, (long long)ctx->smCount * std::max(perSm, 1)));
+  k5_derivative_shift<LMAX, STRESS, WARPS, UNR><<<grid, 32 * WARPS, smemBytes, ctx->stream>>>(p);
   return 0;
 }
 
+// Warps per CTA (one CTA per SM): the weight tile is 32 x mOrb^2 doubles per warp -- 21 KB for spd,
+// 66 KB with f shells.  s/p/d: 8 warps with the full 255 registers beat 10 warps at 168 registers
+// (119 vs 135 us on fec4096: the evaluator is register starved, not occupancy starved); unrolling
+// the displacement loop by two does not help (136 us).
+template <int LMAX, bool STRESS>
+int launchByWarps(dftbp_b200_ctx *ctx, const K5Params &p, long long items, int warpsMax, size_t perWarp) {
+  if constexpr (LMAX <= 2) return launchTypedS<LMAX, STRESS, 8, 1>(ctx, p, items, warpsMax, perWarp);
+  else return launchTypedS<LMAX, STRESS, 2, 1>(ctx, p, items, warpsMax, perWarp);
+}
+
 template <int LMAX>
-int launchTyped(dftbp_b200_ctx *ctx, const K5Params &p, long long chunks) {
-  if constexpr (LMAX <= 2) {
-    const int nb = tuneInt("DFTBP_B200_K5_NB", 2);  // resident CTAs per SM the register budget aims at (A/B)
-    if (nb == 3) {
-      if (p.stress) return launchForces<LMAX, true, 3>(ctx, p, chunks);
-      return launchForces<LMAX, false, 3>(ctx, p, chunks);
-    }
-    if (p.stress) return launchForces<LMAX, true, 2>(ctx, p, chunks);
-    return launchForces<LMAX, false, 2>(ctx, p, chunks);
-  } else {
-    if (p.stress) return launchForces<LMAX, true, 1>(ctx, p, chunks);
-    return launchForces<LMAX, false, 1>(ctx, p, chunks);
-  }
+int launchTyped(dftbp_b200_ctx *ctx, const K5Params &p, long long items, int warpsMax, size_t perWarp) {
+  if (p.stress) return launchByWarps<LMAX, true>(ctx, p, items, warpsMax, perWarp);
+  return launchByWarps<LMAX, false>(ctx, p, items, warpsMax, perWarp);
 }
 
 }  // namespace
@@ -713,7 +519,6 @@ int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, c
   // nonscc.F90:43: deltaXDiff = epsilon(1.0_dp)**0.25_dp
   p.delta = delta > 0.0 ? delta : 1.220703125e-4;
   p.deriv = nullptr; p.stress = nullptr;
-  p.EDM = nullptr; p.shift = nullptr; p.shiftFull = nullptr;
   // the non-SCC routine takes DM(:) only; the block routine DM(:, nSpin)
   const int nDm = shift ? nSpin : 1;
   DFTBP_TRY(devIn(ctx, kSlotA, DM, (size_t)g.sparseSize * nDm, &p.DM));
@@ -748,31 +553,34 @@ int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, c
       wp.nAtom = g.nAtom; wp.nSpin = nSpin; wp.sparseSize = g.sparseSize;
       wp.DM = p.DM; wp.EDM = dEDM; wp.shift = dShift; wp.shiftFull = flag; wp.negWS = (double *)scratch;
       wp.selfImages = st ? 1 : 0;
-      const int wGrid = gridFor(ctx, (wp.nWork + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, 4);
-      // Diagonal shift blocks (plain SCC, collinear spin): the finite-difference kernel forms -wS itself while
-      // it stages the blocks (k5_pair_forces, step 1c); the streaming pass k5_force_weights_diag is only
-      // needed by the Richardson kernel, which reads -wS as an array.  Full shift blocks: k5_force_weights<true>.
-      // Every kernel looks at the device flag and returns at once if the shift structure is not its own.
-      if (diffType == DFTBP_B200_DIFF_RICHARDSON) {
-        launchWeightsDiag<1>(wp, nSpin, wGrid, ctx->stream);
-        ctx->launches++;
+      const int wGrid = gridFor(ctx, (wp.nWork + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, tuneInt("DFTBP_B200_K5W_CTAS", 4));
+      // both instantiations are launched; the one that does not match the device flag returns at once
+      {
+        const char *env = getenv("DFTBP_B200_K5W_BATCH");  // tuning switch (tools/gpu_probe.py)
+        const int batch = env ? atoi(env) : 1;  // measured: 1 block per pass 98 us, 2 blocks 160 us, generic kernel 135 us
+        if (batch == 0) k5_force_weights<false><<<wGrid, 256, 0, ctx->stream>>>(wp);
+        else if (batch == 1) launchWeightsDiag<1>(wp, nSpin, wGrid, ctx->stream);
+        else launchWeightsDiag<2>(wp, nSpin, wGrid, ctx->stream);
       }
       k5_force_weights<true><<<wGrid, 256, 0, ctx->stream>>>(wp);
       p.negWS = (const double *)scratch;
-      p.EDM = dEDM; p.shift = dShift; p.shiftFull = flag;
-      ctx->launches += 2;
+      ctx->launches += 3;
     }
-    // tile row of the finite-difference kernel: the block plus up to three alignment elements, odd
-    p.pitch = (ctx->mOrb * ctx->mOrb + 3) | 1;
-    const long long chunks = (g.nWorkLoad + 31) / 32 + ctx->nSpecies * ctx->nSpecies;
+    p.pitch = (ctx->mOrb * ctx->mOrb) | 1;
+    const size_t perWarp = sizeof(double) * 32 * (size_t)p.pitch;
+    // 10 warps x <= 204 registers fill the register file; the weight tile usually limits first
+    const int warps = (int)std::min<size_t>(10, (ctx->smemOptin - 2048) / perWarp);
+    DFTBP_CHECK(ctx, warps >= 1, "derivative_shift: weight tile does not fit into shared memory");
+    const long long items = 2 * ((g.nWorkLoad + 31) / 32 + ctx->nSpecies * ctx->nSpecies);
     int rc;
     if (diffType == DFTBP_B200_DIFF_RICHARDSON) {
+      const long long chunks = items / 2;
       if (ctx->lMaxAll <= 1) rc = launchRichardson<1>(ctx, p, chunks);
       else if (ctx->lMaxAll == 2) rc = launchRichardson<2>(ctx, p, chunks);
       else rc = launchRichardson<3>(ctx, p, chunks);
-    } else if (ctx->lMaxAll <= 1) rc = launchTyped<1>(ctx, p, chunks);
-    else if (ctx->lMaxAll == 2) rc = launchTyped<2>(ctx, p, chunks);
-    else rc = launchTyped<3>(ctx, p, chunks);
+    } else if (ctx->lMaxAll <= 1) rc = launchTyped<1>(ctx, p, items, warps, perWarp);
+    else if (ctx->lMaxAll == 2) rc = launchTyped<2>(ctx, p, items, warps, perWarp);
+    else rc = launchTyped<3>(ctx, p, items, warps, perWarp);
     if (rc) return rc;
     ctx->launches++;
   }

@@ -418,103 +418,4 @@ __device__ __forceinline__ double skLaneWDotAny(const SpPairProg &pg, const SkTa
   return skLaneWDot<LMAX>(pg, t, r, dx, dy, dz, row);
 }
 
-// ---- both matrices of one displaced evaluation, table windows in shared memory (K5, round 2) ----------
-// yH / yS: this lane's 8-row window inside the chunk's shared copy of the H0 / S table (integral
-// column c at y + c * winPitch), or nullptr: the lane falls back to the global table (tail of the
-// table, window outside the shared rows).
-__device__ __forceinline__ double laneInterpWin(const SkTableDev &t, const LaneInterp &li, const double *y, int winPitch,
-                                                int col) {
-  if (y) {
-    const double *__restrict__ yc = y + col * winPitch;
-    double acc = li.w[0] * yc[0];
-#pragma unroll
-    for (int j = 1; j < 8; ++j) acc = fma(li.w[j], yc[j], acc);
-    return acc;
-  }
-  return laneInterp(t, li, col);
-}
-
-// sum_e wS_e S_e - sum_e wH_e H_e of one pair at one displaced bond vector; rowH / rowS hold W
-// (skLaneWBuild), Y the harmonics of the direction
-template <int LM1, int LM2, int NY>
-__device__ __forceinline__ double skLanePairDotCanon(const SpPairProg &pg, const LaneInterp &liH, const LaneInterp &liS,
-                                                     const double *yH, const double *yS, int winPitch,
-                                                     const double (&Y)[NY], const double *rowH, const double *rowS) {
-  constexpr int N2 = (LM2 + 1) * (LM2 + 1);
-  double acc = 0.0;
-  staticFor<LM1 + 1>([&](auto l1c) {
-    constexpr int l1 = decltype(l1c)::value;
-    staticFor<LM2 + 1>([&](auto l2c) {
-      constexpr int l2 = decltype(l2c)::value;
-      constexpr int lmin = canonMin(l1, l2), first = canonIntegStart(l1, l2, LM2);
-      double vH[4], vS[4], aH[4], aS[4];
-#pragma unroll
-      for (int k = 0; k <= lmin; ++k) {
-        vH[k] = laneInterpWin(pg.H, liH, yH, winPitch, first + k);
-        vS[k] = laneInterpWin(pg.S, liS, yS, winPitch, first + k);
-      }
-      skg::acoefT<l1, l2>(vH, aH);
-      skg::acoefT<l1, l2>(vS, aS);
-      const double *subH = rowH + l2 * l2 + N2 * l1 * l1, *subS = rowS + l2 * l2 + N2 * l1 * l1;
-      acc += skg::wdotT<l1, l2>(Y, aS, [&](int a, int b) { return subS[b + N2 * a]; }) -
-             skg::wdotT<l1, l2>(Y, aH, [&](int a, int b) { return subH[b + N2 * a]; });
-    });
-  });
-  return acc;
-}
-
-// generic shell structure: run-time loops over the shell-pair program
-template <int LMAX>
-__device__ __forceinline__ double skLanePairDot(const SpPairProg &pg, const LaneInterp &liH, const LaneInterp &liS,
-                                                const double *yH, const double *yS, int winPitch,
-                                                const double (&Y)[(2 * LMAX + 1) * (2 * LMAX + 1)], const double *rowH,
-                                                const double *rowS) {
-  const int nShPair = pg.nShPair, n2 = pg.nOrb2;
-  int ind = 0;
-  double acc = 0.0;
-  for (int i = 0; i < nShPair; ++i) {
-    const int e = pg.shPair[i];
-    const int l1 = (e >> 2) & 3, l2 = e & 3, lmin = min(l1, l2), first = e >> 4;
-    double vH[4] = {0.0, 0.0, 0.0, 0.0}, vS[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (k <= LMAX && k <= lmin) {
-        vH[k] = laneInterpWin(pg.H, liH, yH, winPitch, ind + k);
-        vS[k] = laneInterpWin(pg.S, liS, yS, winPitch, ind + k);
-      }
-    const double *subH = rowH + first, *subS = rowS + first;
-    acc += skg::wdotDispatch<LMAX>(l1, l2, Y, vS, [&](int a, int b) { return subS[b + n2 * a]; }) -
-           skg::wdotDispatch<LMAX>(l1, l2, Y, vH, [&](int a, int b) { return subH[b + n2 * a]; });
-    ind += lmin + 1;
-  }
-  return acc;
-}
-
-// harmonics up to LY (compile time) into the front of a larger array
-template <int LY, int NY>
-__device__ __forceinline__ void harmonicsInto(double x, double y, double z, double (&Y)[NY]) {
-  double T[(LY + 1) * (LY + 1)];
-  skg::harmonics<LY>(x, y, z, T);
-#pragma unroll
-  for (int k = 0; k < (LY + 1) * (LY + 1); ++k) Y[k] = T[k];
-}
-
-// weights -> W for the shell pairs i = l1 * (LM2 + 1) + l2 with i % nParts == part (the shell pairs of
-// a row are dealt out over several warps)
-template <int LM1, int LM2>
-__device__ __forceinline__ void skLaneWBuildCanonPart(double *row, int part, int nParts) {
-  constexpr int N2 = (LM2 + 1) * (LM2 + 1);
-  staticFor<LM1 + 1>([&](auto l1c) {
-    constexpr int l1 = decltype(l1c)::value;
-    staticFor<LM2 + 1>([&](auto l2c) {
-      constexpr int l2 = decltype(l2c)::value;
-      if ((l1 * (LM2 + 1) + l2) % nParts == part) {
-        double *sub = row + l2 * l2 + N2 * l1 * l1;
-        skg::wbuildT<l1, l2>([&](int a, int b) { return sub[b + N2 * a]; },
-                             [&](int a, int b, double v) { sub[b + N2 * a] = v; });
-      }
-    });
-  });
-}
-
 }  // namespace dftbp_b200
