@@ -56,6 +56,7 @@ SIGNATURES = {
     "dftbp_b200_add_shift_atom": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "dftbp_b200_add_shift_block": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "dftbp_b200_derivative_shift": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_double]),
+    "dftbp_b200_set_pair_partition": (c_int, [c_void_p, c_int, c_int]),
     "dftbp_b200_stress": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_double, c_double]),
     "dftbp_b200_hegv_real": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_char]),
     "dftbp_b200_hegv_cplx": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_char]),

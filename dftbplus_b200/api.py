@@ -358,6 +358,11 @@ class HotPath:
         return ham
 
     # ---- K5 ---------------------------------------------------------------------------------
+    def set_pair_partition(self, part, n_parts):
+        """Subsequent derivative_shift / stress calls take the chunks part, part + n_parts, ... of the
+        pair schedule (dftbp_b200_set_pair_partition); the partial results add up to the full one."""
+        self._ck(self._L.dftbp_b200_set_pair_partition(self._h, int(part), int(n_parts)))
+
     def derivative_shift(self, dm, edm, shift=None, diff_type=1, delta=0.0, deriv=None):
         """dm[nSpin, sparseSize] (or 1-D), edm[sparseSize], shift[nSpin, nAtom, mOrb, mOrb] or None."""
         if not _is_torch(dm):

@@ -144,6 +144,7 @@ struct dftbp_b200_ctx {
   std::string err;
   long long launches = 0;
   int dmColFirst = 1, dmColLast = 0;            // column panel of the current density-matrix call
+  int pairPart = 0, pairParts = 1;              // share of the pair schedule the force calls take (set_pair_partition)
   std::vector<long long> blockStartOfAtom;      // first entry of every atom in workAll / descAll (nAtom + 1)
   int smCount = 148;
   size_t smemOptin = 232448;  // max dynamic shared memory per CTA

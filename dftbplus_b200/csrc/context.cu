@@ -270,6 +270,14 @@ int dftbp_b200_set_sk_table(dftbp_b200_ctx *ctx, int which, int sp1, int sp2, in
   return 0;
 }
 
+int dftbp_b200_set_pair_partition(dftbp_b200_ctx *ctx, int part, int nParts) {
+  if (!ctx) return DFTBP_B200_EINVAL;
+  DFTBP_CHECK(ctx, nParts >= 1 && part >= 0 && part < nParts, "set_pair_partition: need 0 <= part < nParts");
+  ctx->pairPart = part;
+  ctx->pairParts = nParts;
+  return 0;
+}
+
 int dftbp_b200_get_sk_cutoff(dftbp_b200_ctx *ctx, double *cutoff) {
   if (!ctx || !cutoff) return DFTBP_B200_EINVAL;
   *cutoff = ctx->cutoff;

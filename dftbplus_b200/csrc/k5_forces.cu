@@ -37,6 +37,7 @@ struct K5Params {
   const int2 *atoms;    // (iAtom1, iAtom2f) per slot
   const int *total;
   int ld, nSpecies, mOrb, nAtom, nSpin, sparseSize, pitch;
+  int part, nParts;  // this call takes the chunks part, part + nParts, ... of the schedule (dftbp_b200_set_pair_partition)
   const double *DM;     // rho, first spin channel = wH
   const double *negWS;  // -wS: Erho (no SCC) or the array prepared by k5_force_weights
   double delta;
@@ -87,143 +88,103 @@ __global__ void __launch_bounds__(256) k5_shift_structure(const double *__restri
   if (__any_sync(0xffffffffu, any) && lane == 0) atomicOr(flag, 1);
 }
 
-// -wS = Erho - sum_spin 1/2 (rho_s V1_s^T + V2_s^T rho_s) for every off-site block of this rank's
-// work list (the SCC part of derivative_blockEuclidean, forces.F90:640-656, independent of the
-// Cartesian direction).  One warp per block, lanes on consecutive elements: a streaming kernel.
-// Plain SCC and collinear-spin shifts are diagonal blocks (the device flag says so); then
-// (rho V1^T + V2^T rho)(b,a) = rho(b,a) (V1(a,a) + V2(b,b)) and no matrix product is needed.
-struct K5WeightParams {
-  const BlockDesc *desc;
-  long long nWork;
-  int mOrb, nAtom, nSpin, sparseSize;
-  const double *DM, *EDM, *shift;
-  const int *shiftFull;
-  double *negWS;
-  int selfImages;  // 1: also blocks between an atom and its own periodic image (stress)
-};
-
-template <bool FULL>
-__global__ void __launch_bounds__(256, 4) k5_force_weights(const K5WeightParams p) {
-  if ((__ldg(p.shiftFull) != 0) != FULL) return;  // the other instantiation handles this shift structure
-  const int lane = threadIdx.x & 31;
-  const int mo2 = p.mOrb * p.mOrb;
-  forEachBlock(
-      p.desc, p.nWork, [] {},
-      [&](const BlockDesc &blk) {
-        if (blk.iNeigh == 0 || (blk.iAt1 == blk.iAt2f && !p.selfImages)) return;
-        const int n1 = blk.n12 & 0xFF, n2 = blk.n12 >> 8, ind = blk.ind;
-        const int nElem = n1 * n2;
-        const unsigned M2 = (1048576u + (unsigned)n2 - 1u) / (unsigned)n2;  // e / n2 = e * M2 >> 20 (e < 256)
-        const double *__restrict__ edm = p.EDM + ind;
-        double *__restrict__ out = p.negWS + ind;
-        for (int e0 = lane; e0 < nElem; e0 += 96) {
-          // three elements per lane and pass, all loads independent
-          int e[3], a[3], b[3];
-          bool on[3];
-          double s[3];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            e[k] = e0 + 32 * k;
-            on[k] = e[k] < nElem;
-            if (!on[k]) e[k] = 0;
-            a[k] = (int)(((unsigned)e[k] * M2) >> 20);  // element (row b, col a) of the n2 x n1 block
-            b[k] = e[k] - a[k] * n2;
-            s[k] = __ldg(edm + e[k]);
-          }
-          for (int iSpin = 0; iSpin < p.nSpin; ++iSpin) {
-            const double *__restrict__ rho = p.DM + (size_t)p.sparseSize * iSpin + ind;
-            const double *__restrict__ V1 = p.shift + (size_t)mo2 * (blk.iAt1 + (size_t)p.nAtom * iSpin);
-            const double *__restrict__ V2 = p.shift + (size_t)mo2 * (blk.iAt2f + (size_t)p.nAtom * iSpin);
-            if (!FULL) {
-              double r[3], x1[3], x2[3];
-#pragma unroll
-              for (int k = 0; k < 3; ++k) {
-                r[k] = __ldg(rho + e[k]);
-                x1[k] = __ldg(V1 + a[k] * (p.mOrb + 1));
-                x2[k] = __ldg(V2 + b[k] * (p.mOrb + 1));
-              }
-#pragma unroll
-              for (int k = 0; k < 3; ++k) s[k] = fma(-0.5 * r[k], x1[k] + x2[k], s[k]);
-            } else {
-              // (rho V1^T)(b,a) = sum_c rho(b,c) V1(a,c);  (V2^T rho)(b,a) = sum_c V2(c,b) rho(c,a)
-#pragma unroll
-              for (int k = 0; k < 3; ++k) {
-                double x = 0.0;
-                for (int c = 0; c < n1; ++c) x = fma(__ldg(rho + b[k] + n2 * c), __ldg(V1 + a[k] + p.mOrb * c), x);
-                for (int c = 0; c < n2; ++c) x = fma(__ldg(V2 + c + p.mOrb * b[k]), __ldg(rho + c + n2 * a[k]), x);
-                s[k] = fma(-0.5, x, s[k]);
-              }
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < 3; ++k)
-            if (on[k]) out[e[k]] = s[k];
-        }
-      },
-      [] {});
-}
-
-// Diagonal shift blocks (the common case), streaming form: the spin loop is unrolled so that all
-// loads of a pass -- (1 + 3 NSPIN) per element, three elements per lane and block -- are issued
-// before the first use (the generic kernel above: 35 % of the HBM roofline, latency bound,
-// profiles/r01d_ncu_all_kernels.txt).  BATCH > 1 blocks per pass costs more occupancy than it wins.
-template <int BATCH, int NSPIN>
-__global__ void __launch_bounds__(256) k5_force_weights_diag(const K5WeightParams p) {
-  if (__ldg(p.shiftFull) != 0) return;  // full blocks: k5_force_weights<true>
-  const int lane = threadIdx.x & 31;
+// -wS = Erho - sum_spin 1/2 (rho_s V1_s^T + V2_s^T rho_s) for every off-site block of the call's chunks
+// (the SCC part of derivative_blockEuclidean, forces.F90:640-656, independent of the Cartesian
+// direction): a streaming kernel.  Plain SCC and collinear-spin shifts are diagonal blocks (the
+// device flag says so); then (rho V1^T + V2^T rho)(b,a) = rho(b,a) (V1(a,a) + V2(b,b)) and no matrix
+// product is needed: spin loop unrolled, all loads of a block -- (1 + 3 NSPIN) per element, three
+// elements per lane -- issued before the first use.
+// It walks along the pair schedule: one warp per chunk of 32 sorted pairs (one species pair: the
+// block shape is warp-uniform), the 32 blocks one after the other with lanes on consecutive
+// elements -- the form the partition of the force call needs (dftbp_b200_set_pair_partition: a call
+// only touches the chunks part, part + nParts, ... and only their blocks get weights).
+template <int NSPIN, bool FULL>
+__global__ void __launch_bounds__(256) k5_force_weights_sched(const K5Params p, const double *__restrict__ EDM,
+                                                              const double *__restrict__ shift,
+                                                              const int *__restrict__ shiftFull,
+                                                              double *__restrict__ negWS, int selfImages) {
+  if ((__ldg(shiftFull) != 0) != FULL) return;  // the other instantiation handles this shift structure
+  const int lane = threadIdx.x & 31, wIn = threadIdx.x >> 5, nW = blockDim.x >> 5;
+  const int nChunks = __ldg(p.total) >> 5;
   const int mo2 = p.mOrb * p.mOrb, dstep = p.mOrb + 1;
-  forEachBlockBatch<BATCH>(p.desc, p.nWork, [&](const BlockDesc(&b)[BATCH], int count) {
-    int maxElem = 0;
+  const int nSpin = FULL ? p.nSpin : NSPIN;
+  for (int chunk = p.part + p.nParts * (blockIdx.x * nW + wIn); chunk < nChunks; chunk += p.nParts * gridDim.x * nW) {
+    const PairRec *r = p.recs + 32 * (size_t)chunk + lane;
+    const int4 w = __ldg(reinterpret_cast<const int4 *>(r) + 1);
+    const int2 at = __ldg(p.atoms + 32 * (size_t)chunk + lane);
+    const int sp = __shfl_sync(0xffffffffu, w.w, 0);  // lane 0 of a chunk is never padding
+    const SpPairProg &pg = p.progs[sp];
+    const int n1 = pg.nOrb1, n2 = pg.nOrb2, nElem = n1 * n2;
+    const bool liveMine = w.z >= 0 && (at.x != at.y || selfImages);
+    const unsigned M2 = (1048576u + (unsigned)n2 - 1u) / (unsigned)n2;  // e / n2 = e * M2 >> 20 (e < 256)
+    // this lane's elements of every block: e = lane, lane + 32, lane + 64 (+ a loop for f shells)
+    int a[3], b[3];
+    bool on[3];
 #pragma unroll
-    for (int q = 0; q < BATCH; ++q) {
-      const bool off = q < count && b[q].iNeigh != 0 && (b[q].iAt1 != b[q].iAt2f || p.selfImages);
-      if (off) maxElem = max(maxElem, (b[q].n12 & 0xFF) * (b[q].n12 >> 8));
+    for (int k = 0; k < 3; ++k) {
+      const int e = lane + 32 * k;
+      on[k] = e < nElem;
+      const int ee = on[k] ? e : 0;
+      a[k] = (int)(((unsigned)ee * M2) >> 20);  // element (row b, col a) of the n2 x n1 block
+      b[k] = ee - a[k] * n2;
     }
-    for (int e0 = lane; e0 < maxElem; e0 += 96) {
-      double s[BATCH][3], r[BATCH][3][NSPIN], x1[BATCH][3][NSPIN], x2[BATCH][3][NSPIN];
-#pragma unroll
-      for (int q = 0; q < BATCH; ++q) {
-        const bool off = q < count && b[q].iNeigh != 0 && (b[q].iAt1 != b[q].iAt2f || p.selfImages);
-        const int n2 = b[q].n12 >> 8, nElem = off ? (b[q].n12 & 0xFF) * n2 : 0;
-        const unsigned M2 = (1048576u + (unsigned)n2 - 1u) / (unsigned)n2;  // e / n2 = e * M2 >> 20 (e < 256)
+    const unsigned liveMask = __ballot_sync(0xffffffffu, liveMine);
+    for (int q = 0; q < 32; ++q) {
+      if (!((liveMask >> q) & 1u)) continue;  // warp-uniform
+      const int ind = __shfl_sync(0xffffffffu, w.z, q);
+      const int iAt1 = __shfl_sync(0xffffffffu, at.x, q), iAt2f = __shfl_sync(0xffffffffu, at.y, q);
+      const double *__restrict__ edm = EDM + ind;
+      double *__restrict__ out = negWS + ind;
+      if (!FULL) {
+        double s[3], rr[3][NSPIN], x1[3][NSPIN], x2[3][NSPIN];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          const int e = e0 + 32 * k;
-          const bool on = e < nElem;
-          const int ee = on ? e : 0;
-          const int a = (int)(((unsigned)ee * M2) >> 20), bb = ee - a * n2;  // element (row bb, col a)
-          s[q][k] = on ? __ldg(p.EDM + b[q].ind + ee) : 0.0;
+          const int e = lane + 32 * k;
+          s[k] = on[k] ? __ldg(edm + e) : 0.0;
 #pragma unroll
           for (int iSpin = 0; iSpin < NSPIN; ++iSpin) {
-            r[q][k][iSpin] = on ? __ldg(p.DM + (size_t)p.sparseSize * iSpin + b[q].ind + ee) : 0.0;
-            x1[q][k][iSpin] = on ? __ldg(p.shift + (size_t)mo2 * (b[q].iAt1 + (size_t)p.nAtom * iSpin) + a * dstep) : 0.0;
-            x2[q][k][iSpin] = on ? __ldg(p.shift + (size_t)mo2 * (b[q].iAt2f + (size_t)p.nAtom * iSpin) + bb * dstep) : 0.0;
+            rr[k][iSpin] = on[k] ? __ldg(p.DM + (size_t)p.sparseSize * iSpin + ind + e) : 0.0;
+            x1[k][iSpin] = on[k] ? __ldg(shift + (size_t)mo2 * (iAt1 + (size_t)p.nAtom * iSpin) + a[k] * dstep) : 0.0;
+            x2[k][iSpin] = on[k] ? __ldg(shift + (size_t)mo2 * (iAt2f + (size_t)p.nAtom * iSpin) + b[k] * dstep) : 0.0;
           }
         }
-      }
-#pragma unroll
-      for (int q = 0; q < BATCH; ++q) {
-        const bool off = q < count && b[q].iNeigh != 0 && (b[q].iAt1 != b[q].iAt2f || p.selfImages);
-        const int nElem = off ? (b[q].n12 & 0xFF) * (b[q].n12 >> 8) : 0;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          const int e = e0 + 32 * k;
-          double v = s[q][k];
+          double v = s[k];
+#pragma unroll
+          for (int iSpin = 0; iSpin < NSPIN; ++iSpin) v = fma(-0.5 * rr[k][iSpin], x1[k][iSpin] + x2[k][iSpin], v);
+          if (on[k]) out[lane + 32 * k] = v;
+        }
+        for (int e = lane + 96; e < nElem; e += 32) {  // blocks with f shells
+          const int aa = (int)(((unsigned)e * M2) >> 20), bb = e - aa * n2;
+          double v = __ldg(edm + e);
 #pragma unroll
           for (int iSpin = 0; iSpin < NSPIN; ++iSpin)
-            v = fma(-0.5 * r[q][k][iSpin], x1[q][k][iSpin] + x2[q][k][iSpin], v);
-          if (e < nElem) p.negWS[b[q].ind + e] = v;
+            v = fma(-0.5 * __ldg(p.DM + (size_t)p.sparseSize * iSpin + ind + e),
+                    __ldg(shift + (size_t)mo2 * (iAt1 + (size_t)p.nAtom * iSpin) + aa * dstep) +
+                        __ldg(shift + (size_t)mo2 * (iAt2f + (size_t)p.nAtom * iSpin) + bb * dstep),
+                    v);
+          out[e] = v;
+        }
+      } else {
+        for (int e = lane; e < nElem; e += 32) {
+          const int aa = (int)(((unsigned)e * M2) >> 20), bb = e - aa * n2;
+          double v = __ldg(edm + e);
+          for (int iSpin = 0; iSpin < nSpin; ++iSpin) {
+            const double *__restrict__ rho = p.DM + (size_t)p.sparseSize * iSpin + ind;
+            const double *__restrict__ V1 = shift + (size_t)mo2 * (iAt1 + (size_t)p.nAtom * iSpin);
+            const double *__restrict__ V2 = shift + (size_t)mo2 * (iAt2f + (size_t)p.nAtom * iSpin);
+            // (rho V1^T)(b,a) = sum_c rho(b,c) V1(a,c);  (V2^T rho)(b,a) = sum_c V2(c,b) rho(c,a)
+            double x = 0.0;
+            for (int c = 0; c < n1; ++c) x = fma(__ldg(rho + bb + n2 * c), __ldg(V1 + aa + p.mOrb * c), x);
+            for (int c = 0; c < n2; ++c) x = fma(__ldg(V2 + c + p.mOrb * bb), __ldg(rho + c + n2 * aa), x);
+            v = fma(-0.5, x, v);
+          }
+          out[e] = v;
         }
       }
     }
-  });
-}
-
-template <int BATCH>
-void launchWeightsDiag(const K5WeightParams &wp, int nSpin, int grid, cudaStream_t stream) {
-  if (nSpin == 1) k5_force_weights_diag<BATCH, 1><<<grid, 256, 0, stream>>>(wp);
-  else if (nSpin == 2) k5_force_weights_diag<BATCH, 2><<<grid, 256, 0, stream>>>(wp);
-  else k5_force_weights_diag<BATCH, 4><<<grid, 256, 0, stream>>>(wp);
+  }
 }
 
 template <int LMAX, bool STRESS, int WARPS, int UNR>
@@ -234,9 +195,10 @@ __global__ void __launch_bounds__(32 * WARPS, 1) k5_derivative_shift(const K5Par
   double *stage = smem + (size_t)wIn * 32 * p.pitch;
   double *row = stage + (size_t)lane * p.pitch;
   const int nChunks = __ldg(p.total) >> 5;
-  const int nItems = 2 * nChunks;
+  const int nMine = (nChunks - p.part + p.nParts - 1) / p.nParts;  // chunks part, part + nParts, ...
+  const int nItems = 2 * nMine;
   for (int item = blockIdx.x * nW + wIn; item < nItems; item += gridDim.x * nW) {
-    const int chunk = item >> 1;
+    const int chunk = p.part + p.nParts * (item >> 1);
     const bool isS = item & 1;
     const K5Pair pr = k5LoadPair(p, chunk, lane);
     const bool live = pr.live;
@@ -361,7 +323,7 @@ __global__ void __launch_bounds__(64) k5_derivative_shift_richardson(const K5Par
   double rowB[(kMaxCols + 1) * kSlice];
   double done[kSlice];                   // converged value per element
   bool conv[kSlice];
-  for (int chunk = blockIdx.x * nW + wIn; chunk < nChunks; chunk += gridDim.x * nW) {
+  for (int chunk = p.part + p.nParts * (blockIdx.x * nW + wIn); chunk < nChunks; chunk += p.nParts * gridDim.x * nW) {
     const K5Pair pr = k5LoadPair(p, chunk, lane);
     if (!pr.live) continue;  // the evaluator has no warp-level synchronisation: lanes may diverge
     const int ind = pr.ind, iAt1 = pr.iAt1, iAt2f = pr.iAt2f;
@@ -519,6 +481,7 @@ int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, c
   // nonscc.F90:43: deltaXDiff = epsilon(1.0_dp)**0.25_dp
   p.delta = delta > 0.0 ? delta : 1.220703125e-4;
   p.deriv = nullptr; p.stress = nullptr;
+  p.part = ctx->pairPart; p.nParts = ctx->pairParts;
   // the non-SCC routine takes DM(:) only; the block routine DM(:, nSpin)
   const int nDm = shift ? nSpin : 1;
   DFTBP_TRY(devIn(ctx, kSlotA, DM, (size_t)g.sparseSize * nDm, &p.DM));
@@ -548,21 +511,14 @@ int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, c
           dShift, ctx->mOrb, g.nAtom * nSpin, flag);
       void *scratch;
       DFTBP_TRY(stagingGet(ctx, kSlotE, sizeof(double) * (size_t)g.sparseSize, &scratch));
-      K5WeightParams wp;
-      wp.desc = g.descLoad; wp.nWork = g.nWorkLoad; wp.mOrb = ctx->mOrb;
-      wp.nAtom = g.nAtom; wp.nSpin = nSpin; wp.sparseSize = g.sparseSize;
-      wp.DM = p.DM; wp.EDM = dEDM; wp.shift = dShift; wp.shiftFull = flag; wp.negWS = (double *)scratch;
-      wp.selfImages = st ? 1 : 0;
-      const int wGrid = gridFor(ctx, (wp.nWork + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, tuneInt("DFTBP_B200_K5W_CTAS", 4));
       // both instantiations are launched; the one that does not match the device flag returns at once
-      {
-        const char *env = getenv("DFTBP_B200_K5W_BATCH");  // tuning switch (tools/gpu_probe.py)
-        const int batch = env ? atoi(env) : 1;  // measured: 1 block per pass 98 us, 2 blocks 160 us, generic kernel 135 us
-        if (batch == 0) k5_force_weights<false><<<wGrid, 256, 0, ctx->stream>>>(wp);
-        else if (batch == 1) launchWeightsDiag<1>(wp, nSpin, wGrid, ctx->stream);
-        else launchWeightsDiag<2>(wp, nSpin, wGrid, ctx->stream);
-      }
-      k5_force_weights<true><<<wGrid, 256, 0, ctx->stream>>>(wp);
+      const long long myChunks = (((g.nWorkLoad + 31) / 32 + ctx->nSpecies * ctx->nSpecies) + p.nParts - 1) / p.nParts;
+      const int wGrid = gridFor(ctx, myChunks, 8, 6);
+      const int self = st ? 1 : 0;
+      if (nSpin == 1) k5_force_weights_sched<1, false><<<wGrid, 256, 0, ctx->stream>>>(p, dEDM, dShift, flag, (double *)scratch, self);
+      else if (nSpin == 2) k5_force_weights_sched<2, false><<<wGrid, 256, 0, ctx->stream>>>(p, dEDM, dShift, flag, (double *)scratch, self);
+      else k5_force_weights_sched<4, false><<<wGrid, 256, 0, ctx->stream>>>(p, dEDM, dShift, flag, (double *)scratch, self);
+      k5_force_weights_sched<1, true><<<wGrid, 256, 0, ctx->stream>>>(p, dEDM, dShift, flag, (double *)scratch, self);
       p.negWS = (const double *)scratch;
       ctx->launches += 3;
     }
@@ -571,7 +527,7 @@ int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, c
     // 10 warps x <= 204 registers fill the register file; the weight tile usually limits first
     const int warps = (int)std::min<size_t>(10, (ctx->smemOptin - 2048) / perWarp);
     DFTBP_CHECK(ctx, warps >= 1, "derivative_shift: weight tile does not fit into shared memory");
-    const long long items = 2 * ((g.nWorkLoad + 31) / 32 + ctx->nSpecies * ctx->nSpecies);
+    const long long items = 2 * ((((g.nWorkLoad + 31) / 32 + ctx->nSpecies * ctx->nSpecies) + p.nParts - 1) / p.nParts);
     int rc;
     if (diffType == DFTBP_B200_DIFF_RICHARDSON) {
       const long long chunks = items / 2;

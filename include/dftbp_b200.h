@@ -261,6 +261,14 @@ int dftbp_b200_add_shift_block(dftbp_b200_ctx *ctx, double *ham, const double *o
 
 /* ---- K5: force contraction ----------------------------------------------------------------- */
 
+/* Optional finer decomposition of derivative_shift / stress across GPUs than the reference's per-atom
+ * one (getIndicesWithWorkload, common/schedule.F90:267-307): subsequent force calls of this context
+ * take the chunks part, part + nParts, ... (0-based) of its device-built pair schedule -- perfectly
+ * balanced, and every GPU can keep ONE context (nRanks = 1: full H0 / S build) instead of a second,
+ * atom-sharded one with its own schedule.  The partial deriv / stress arrays add up to the full
+ * result, i.e. the caller's assembleChunks (all-reduce) is unchanged.  Default: part 0 of 1. */
+int dftbp_b200_set_pair_partition(dftbp_b200_ctx *ctx, int part, int nParts);
+
 /* derivative_shift generic, dftb/forces.F90:27-38: shift == NULL -> derivativeNonSccEuclidian
  * (:119-217), else derivative_blockEuclidean (:548-669).  DM(sparseSize, nSpin),
  * EDM(sparseSize), shift(mOrb, mOrb, nAtom, nSpin), deriv(3, nAtom) is overwritten.
