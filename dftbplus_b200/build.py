@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed on " + src)
     if force or procs or _newer(SO, objs):
         cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO] + objs + [
-            "-L" + CUDA_LIB, "-lcusolver", "-Xlinker", "-rpath," + CUDA_LIB]
+            "-L" + CUDA_LIB, "-lcusolver", "-lcublas", "-Xlinker", "-rpath," + CUDA_LIB]
         subprocess.check_call(cmd)
     return SO
 

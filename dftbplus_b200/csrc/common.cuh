@@ -180,6 +180,7 @@ struct dftbp_b200_ctx {
   double timerMs[dftbp_b200::kTimerCount] = {0};
   long long timerCalls[dftbp_b200::kTimerCount] = {0};
   void *solverHandle = nullptr;
+  void *blasHandle = nullptr;  // cuBLAS, for the triangular solves of the large-n generalized eigensolve
   void *solverWork = nullptr;
   size_t solverWorkBytes = 0;
   int *dInfo = nullptr;

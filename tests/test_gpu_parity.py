@@ -379,6 +379,33 @@ def test_hegv_cusolver(hp_cache):
     assert np.abs(Hc.T @ Sf @ Hc - np.eye(len(ev))).max() < 1e-9
 
 
+def test_hegv_large_n_path(hp_cache, monkeypatch):
+    """The 64-bit composite path (Xpotrf -> two trsm -> Xsyevd -> trsm) that takes over where the 32-bit
+    workspace size of cusolverDn?sygvd overflows (n = 31744), forced here at small n; real and complex."""
+    monkeypatch.setenv("DFTBP_B200_HEGV_LARGE", "1")
+    w, sk, geo, model, selfegy, H, S, eig, C, f = _eig_case("fec128")
+    hp = hp_cache("fec128")
+    Hc, Sc = np.tril(H).copy(order="F"), np.tril(S).copy(order="F")     # only the lower triangles are referenced
+    ev = hp.diagDenseMtx(Hc, Sc)
+    assert np.abs(ev - eig).max() < 1e-10
+    Hs, Ss = np.tril(H) + np.tril(H, -1).T, np.tril(S) + np.tril(S, -1).T
+    assert np.abs(Hs @ Hc - Ss @ Hc * ev[None, :]).max() < 1e-9
+    assert np.abs(Hc.T @ Ss @ Hc - np.eye(len(ev))).max() < 1e-9
+    w, sk, geo, model, selfegy = case("si2")
+    h0, s = oracle.build_h0(model, geo, selfegy), oracle.build_s(model, geo)
+    kp = w["kpoints"][3]
+    Hk, Sk = oracle.unpack_hs_cplx(geo, h0, kp), oracle.unpack_hs_cplx(geo, s, kp)
+    Hf = np.tril(Hk) + np.tril(Hk, -1).conj().T
+    Sf = np.tril(Sk) + np.tril(Sk, -1).conj().T
+    eig = scipy.linalg.eigh(Hf, Sf, eigvals_only=True)
+    Hc, Sc = np.tril(Hk).copy(order="F"), np.tril(Sk).copy(order="F")
+    ev = hp.diagDenseMtx(Hc, Sc)
+    assert np.abs(ev - eig).max() < 1e-10
+    assert np.abs(Hf @ Hc - Sf @ Hc * ev[None, :]).max() < 1e-9
+    ev_n = hp.diagDenseMtx(np.tril(Hk).copy(order="F"), np.tril(Sk).copy(order="F"), jobz="N")
+    assert np.abs(ev_n - eig).max() < 1e-10
+
+
 def test_device_resident_scc_step(hp_cache):
     """The whole chain on device pointers (torch tensors), no host copies between kernels:
     build -> unpack -> hegvd -> DM -> pack -> Mulliken -> E-DM -> forces; against the oracle chain."""
