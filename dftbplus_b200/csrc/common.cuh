@@ -324,6 +324,30 @@ inline int gridFor(const dftbp_b200_ctx *ctx, long long nWarpItems, int warpsPer
   return (int)(need < cap ? need : cap);
 }
 
+// Opt-in shared memory size and resident CTAs per SM of one kernel instantiation, asked from the
+// runtime once per (device, size) instead of on every launch: the two calls cost a few microseconds
+// of host time each, which showed up as idle gaps between the short kernels of a pair step.
+struct LaunchInfo {
+  int device = -1;
+  size_t smemBytes = ~(size_t)0;
+  int perSm = 1;
+};
+
+template <class Kernel>
+inline int launchInfo(dftbp_b200_ctx *ctx, LaunchInfo &cache, Kernel kernel, int threads, size_t smemBytes, int *perSm) {
+  if (cache.device != ctx->device || cache.smemBytes != smemBytes) {
+    if (smemBytes > 48 * 1024)
+      DFTBP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+    int n = 1;
+    DFTBP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smemBytes));
+    cache.device = ctx->device;
+    cache.smemBytes = smemBytes;
+    cache.perSm = n > 0 ? n : 1;
+  }
+  if (perSm) *perSm = cache.perSm;
+  return 0;
+}
+
 // RAII span: records an event pair around the launches of one routine when timing is enabled.
 struct ScopedTimer {
   dftbp_b200_ctx *ctx;

@@ -165,11 +165,9 @@ int launchCompact(dftbp_b200_ctx *ctx, K1Params p, long long chunks) {
   p.dbgNoStore = tuneInt("DFTBP_B200_K1_NOSTORE", 0);
   const size_t smemBytes = sizeof(double) * (32 * (size_t)p.pitch * WARPS + 96);
   DFTBP_CHECK(ctx, smemBytes <= ctx->smemOptin, "build: staging tile does not fit into shared memory");
-  DFTBP_CUDA(ctx, cudaFuncSetAttribute(k1_pair_build_d<LMAX, WARPS, CTAS>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+  static LaunchInfo info;
   int perSm = 1;
-  DFTBP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k1_pair_build_d<LMAX, WARPS, CTAS>,
-                                                                32 * WARPS, smemBytes));
+  DFTBP_TRY(launchInfo(ctx, info, k1_pair_build_d<LMAX, WARPS, CTAS>, 32 * WARPS, smemBytes, &perSm));
   const int grid = (int)std::max<long long>(
       1, std::min<long long>((chunks + WARPS - 1) / WARPS, (long long)ctx->smCount * std::max(perSm, 1)));
   k1_pair_build_d<LMAX, WARPS, CTAS><<<grid, 32 * WARPS, smemBytes, ctx->stream>>>(p);
@@ -502,8 +500,8 @@ int launchTwoKernel(dftbp_b200_ctx *ctx, K1Params p, long long chunks) {
   if (only == 1) return 0;
   const size_t smemBytes = sizeof(double) * (size_t)p.imgCap * WARPS;
   DFTBP_CHECK(ctx, smemBytes <= ctx->smemOptin, "build: block images do not fit into shared memory");
-  DFTBP_CUDA(ctx, cudaFuncSetAttribute(k1_rotate_store<LMAX, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smemBytes));
+  static LaunchInfo info;
+  DFTBP_TRY(launchInfo(ctx, info, k1_rotate_store<LMAX, WARPS>, 32 * WARPS, smemBytes, nullptr));
   const long long items = (g.nWorkMine + 31) / 32;
   const int grid = (int)std::max<long long>(1, std::min<long long>((items + WARPS - 1) / WARPS, (long long)ctx->smCount));
   k1_rotate_store<LMAX, WARPS><<<grid, 32 * WARPS, smemBytes, ctx->stream>>>(p);

@@ -429,11 +429,9 @@ int launchTypedS(dftbp_b200_ctx *ctx, const K5Params &p, long long items, int wa
   const int warps = std::min(WARPS, warpsMax);
   if (warps < WARPS) return fail(ctx, DFTBP_B200_EINVAL, "derivative_shift: weight tile too large for %d warps", WARPS);
   const size_t smemBytes = perWarp * WARPS;
-  DFTBP_CUDA(ctx, cudaFuncSetAttribute(k5_derivative_shift<LMAX, STRESS, WARPS, UNR>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+  static LaunchInfo info;
   int perSm = 1;  // resident CTAs per SM (registers and the weight tile decide)
-  DFTBP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k5_derivative_shift<LMAX, STRESS, WARPS, UNR>,
-                                                                32 * WARPS, smemBytes));
+  DFTBP_TRY(launchInfo(ctx, info, k5_derivative_shift<LMAX, STRESS, WARPS, UNR>, 32 * WARPS, smemBytes, &perSm));
   const int grid = (int)std::max<long long>(
       1, std::min<long long>((items + WARPS - 1) / WARPS, (long long)ctx->smCount * std::max(perSm, 1)));
   k5_derivative_shift<LMAX, STRESS, WARPS, UNR><<<grid, 32 * WARPS, smemBytes, ctx->stream>>>(p);

@@ -237,8 +237,9 @@ int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out
     // slabs of at least 2048 items per CTA (aggregation), at most one CTA per SM
     const int grid = (int)std::max<long long>(1, std::min<long long>(ctx->smCount, (nWork + 2047) / 2048));
     const size_t smemBytes = sizeof(int) * (size_t)nKeys;
-    DFTBP_CUDA(ctx, cudaFuncSetAttribute(ps_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-    DFTBP_CUDA(ctx, cudaFuncSetAttribute(ps_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+    static LaunchInfo infoKeys, infoScatter;
+    DFTBP_TRY(launchInfo(ctx, infoKeys, ps_keys, kSortThreads, smemBytes, nullptr));
+    DFTBP_TRY(launchInfo(ctx, infoScatter, ps_scatter, kSortThreads, smemBytes, nullptr));
     ps_keys<<<grid, kSortThreads, smemBytes, ctx->stream>>>(work, nWork, g.mNeigh + 1, ctx->nSpecies, nBins, nKeys,
                                                            g.coords, g.species, g.iNeighbour, g.iPair, binScale,
                                                            ctx->sortKeys, ctx->sortBins, sp.recsMem);

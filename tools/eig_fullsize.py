@@ -18,10 +18,12 @@ from dftbplus_b200.api import HotPath  # noqa: E402
 
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "fec4096"
+    device = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     assert "torch" not in sys.modules
     rt = ctypes.CDLL("/usr/local/cuda/lib64/libcudart.so")
     rt.cudaMalloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]
     rt.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    rt.cudaSetDevice(device)
 
     def dmalloc(nbytes):
         p = ctypes.c_void_p()
@@ -32,7 +34,7 @@ def main():
 
     w = workloads.BY_NAME[name]()
     sk, geo, _ = workloads.prepare(w)
-    hp = HotPath(0)
+    hp = HotPath(device)
     sk.upload(hp)
     hp.set_geometry(geo)
     L, h = hp._L, hp._h
