@@ -101,6 +101,47 @@ __device__ __forceinline__ void forEachBlockBatch(const BlockDesc *__restrict__ 
     }
   }
 }
+// forEachBlockBatch with one more int per block from a parallel array (aux[i] belongs to desc[i]):
+// f(const BlockDesc (&b)[kBatch], const int (&aux)[kBatch], int count)
+template <int kBatch, class Body>
+__device__ __forceinline__ void forEachBlockBatchAux(const BlockDesc *__restrict__ desc, const int *__restrict__ aux,
+                                                     long long nBlocks, Body &&f) {
+  static_assert(kBlocksPerChunk % kBatch == 0, "batch must divide the chunk");
+  const int lane = threadIdx.x & 31;
+  const long long nWarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long nChunks = (nBlocks + kBlocksPerChunk - 1) / kBlocksPerChunk;
+  for (long long c = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < nChunks; c += nWarps) {
+    const long long i = c * kBlocksPerChunk + lane;
+    int4 lo = make_int4(0, 0, 0, 0), hi = make_int4(0, 0, 0, 0);
+    int ax = 0;
+    if (lane < kBlocksPerChunk && i < nBlocks) {
+      const int4 *src = reinterpret_cast<const int4 *>(desc + i);
+      lo = __ldg(src);
+      hi = __ldg(src + 1);
+      ax = __ldg(aux + i);
+    }
+    const int cnt = (int)min((long long)kBlocksPerChunk, nBlocks - c * kBlocksPerChunk);
+    for (int j0 = 0; j0 < cnt; j0 += kBatch) {
+      BlockDesc b[kBatch];
+      int a[kBatch];
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        const int j = min(j0 + k, cnt - 1);
+        b[k].ind = __shfl_sync(0xffffffffu, lo.x, j);
+        b[k].ii = __shfl_sync(0xffffffffu, lo.y, j);
+        b[k].jj = __shfl_sync(0xffffffffu, lo.z, j);
+        b[k].n12 = __shfl_sync(0xffffffffu, lo.w, j);
+        b[k].iAt1 = __shfl_sync(0xffffffffu, hi.x, j);
+        b[k].iAt2f = __shfl_sync(0xffffffffu, hi.y, j);
+        b[k].iVec = __shfl_sync(0xffffffffu, hi.z, j);
+        b[k].iNeigh = __shfl_sync(0xffffffffu, hi.w, j);
+        a[k] = __shfl_sync(0xffffffffu, ax, j);
+      }
+      f(b, a, min(kBatch, cnt - j0));
+    }
+  }
+}
 #endif
+
 
 }  // namespace dftbp_b200

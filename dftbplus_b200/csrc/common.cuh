@@ -74,6 +74,8 @@ struct SortedPairs {
   PairRec *recs = nullptr; // per slot, same order as items
   PairRec *recsMem = nullptr;  // per work-list entry (the order of the sparse arrays), on-site blocks included
   long long recsMemCap = 0;
+  int *slotOf = nullptr;       // per work-list entry: its slot in the schedule (-1: on-site block)
+  long long slotOfCap = 0;
   int2 *atoms = nullptr;   // per slot: (iAtom1, iAtom2f), 0-based (K5: where the gradient goes)
   int *total = nullptr;    // device scalar: padded length (multiple of 32)
   long long capacity = 0;  // allocated entries of items / recs / atoms

@@ -546,9 +546,7 @@ int launchBuild(dftbp_b200_ctx *ctx, const double *selfegy, double *ham, double 
     const bool twoKernel = kcfg != 0 && ctx->allSimple && ctx->lMaxAll <= 2 && g.coversAll;
     if (twoKernel) {
       if (ctx->lMaxAll <= 1) rc = launchTwoKernel<1, 16>(ctx, p, chunks);
-      else if (kcfg == 8) rc = launchTwoKernel<2, 8>(ctx, p, chunks);
-      else if (kcfg == 10) rc = launchTwoKernel<2, 10>(ctx, p, chunks);
-      else rc = launchTwoKernel<2, 9>(ctx, p, chunks);
+      else rc = launchTwoKernel<2, 8>(ctx, p, chunks);  // 8 warps x 254 registers: 32 us; 9 / 10 warps (168 registers, spills): 47 us
     } else if (ctx->lMaxAll <= 1) rc = launchCompact<1, 8, 2>(ctx, p, chunks);
     else if (ctx->lMaxAll == 2) rc = launchCompact<2, 5, 2>(ctx, p, chunks);
     else rc = launchCompact<3, 3, 1>(ctx, p, chunks);

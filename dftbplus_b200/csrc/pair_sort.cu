@@ -136,7 +136,8 @@ __global__ void __launch_bounds__(kSortThreads) ps_scatter(const int *__restrict
                                                            PairRec *__restrict__ recs, int2 *__restrict__ atoms,
                                                            int ld, const PairRec *__restrict__ recsMem,
                                                            const int *__restrict__ iNeighbour,
-                                                           const int *__restrict__ img2CentCell) {
+                                                           const int *__restrict__ img2CentCell,
+                                                           int *__restrict__ slotOf) {
   extern __shared__ int sh[];
   for (int k = threadIdx.x; k < nKeys; k += kSortThreads) sh[k] = 0;
   __syncthreads();
@@ -154,7 +155,10 @@ __global__ void __launch_bounds__(kSortThreads) ps_scatter(const int *__restrict
   __syncthreads();
   for (long long i = lo + threadIdx.x; i < hi; i += kSortThreads) {
     const int key = keys[i];
-    if (key < 0) continue;
+    if (key < 0) {
+      slotOf[i] = -1;  // on-site block: in no chunk of the schedule
+      continue;
+    }
     const int flat = __ldg(work + i);
     const int iAt1 = flat / ld;
     const int iAt2 = __ldg(iNeighbour + flat) - 1;
@@ -162,6 +166,7 @@ __global__ void __launch_bounds__(kSortThreads) ps_scatter(const int *__restrict
     const int4 lo = __ldg(src), hi = __ldg(src + 1);
     const int pos = atomicAdd(sh + key, 1);
     items[pos] = (int)i;  // position in the work list: row of the pair in per-pair exchange buffers
+    slotOf[i] = pos;      // and the inverse: where the schedule holds work-list entry i
     int4 *dst = reinterpret_cast<int4 *>(recs + pos);
     dst[0] = lo;
     dst[1] = hi;
@@ -192,6 +197,7 @@ void freeSortedPairs(dftbp_b200_ctx *g) {
     cudaFree(sp->items);
     cudaFree(sp->recs);
     cudaFree(sp->recsMem);
+    cudaFree(sp->slotOf);
     cudaFree(sp->atoms);
     cudaFree(sp->total);
   }
@@ -228,6 +234,7 @@ int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out
   }
   if (!sp.total) DFTBP_CUDA(ctx, cudaMalloc((void **)&sp.total, sizeof(int)));
   DFTBP_TRY(growTo(ctx, &sp.recsMem, &sp.recsMemCap, std::max(nWork, 1LL)));
+  DFTBP_TRY(growTo(ctx, &sp.slotOf, &sp.slotOfCap, std::max(nWork, 1LL)));
   DFTBP_TRY(growTo(ctx, &ctx->sortKeys, &ctx->sortKeysCap, std::max(nWork, 1LL)));
   DFTBP_TRY(growTo(ctx, &ctx->sortBins, &ctx->sortBinsCap, nBins64));
   DFTBP_CUDA(ctx, cudaMemsetAsync(ctx->sortBins, 0, sizeof(int) * nBins64, ctx->stream));
@@ -246,7 +253,7 @@ int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out
     ps_scan<<<1, 1024, 0, ctx->stream>>>(ctx->sortBins, nBuckets, nBins, sp.total, sp.items, sp.recs);
     ps_scatter<<<grid, kSortThreads, smemBytes, ctx->stream>>>(work, nWork, nKeys, ctx->sortKeys, ctx->sortBins,
                                                               sp.items, sp.recs, sp.atoms, g.mNeigh + 1, sp.recsMem,
-                                                              g.iNeighbour, g.img2CentCell);
+                                                              g.iNeighbour, g.img2CentCell, sp.slotOf);
     ctx->launches += 3;
   } else {
     DFTBP_CUDA(ctx, cudaMemsetAsync(sp.total, 0, sizeof(int), ctx->stream));
