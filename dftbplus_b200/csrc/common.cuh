@@ -197,7 +197,12 @@ inline int fail(dftbp_b200_ctx *ctx, int code, const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(buf, sizeof(buf), fmt, ap);
   va_end(ap);
-  if (ctx) ctx->err = buf;
+  if (ctx) {
+    ctx->err = buf;
+    // a failed call must not leave copy-back requests behind: the next successful call's finish()
+    // would write staging data into the failed caller's (possibly dead) host buffers
+    ctx->pending.clear();
+  }
   return code;
 }
 

@@ -547,9 +547,17 @@ int launchBuild(dftbp_b200_ctx *ctx, const double *selfegy, double *ham, double 
     if (twoKernel) {
       if (ctx->lMaxAll <= 1) rc = launchTwoKernel<1, 16>(ctx, p, chunks);
       else rc = launchTwoKernel<2, 8>(ctx, p, chunks);  // 8 warps x 254 registers: 32 us; 9 / 10 warps (168 registers, spills): 47 us
-    } else if (ctx->lMaxAll <= 1) rc = launchCompact<1, 8, 2>(ctx, p, chunks);
-    else if (ctx->lMaxAll == 2) rc = launchCompact<2, 5, 2>(ctx, p, chunks);
-    else rc = launchCompact<3, 3, 1>(ctx, p, chunks);
+    } else {
+      // one-kernel form in schedule order; warps per CTA by what the staging rows (mOrb^2 doubles per lane)
+      // leave of the shared memory: species with repeated shells have blocks of up to 16 x 16
+      const size_t perWarp = sizeof(double) * 32 * (size_t)((ctx->mOrb * ctx->mOrb) | 1);
+      const int fit = (int)((ctx->smemOptin - 1024) / perWarp);
+      if (ctx->lMaxAll <= 1) rc = fit >= 16 ? launchCompact<1, 8, 2>(ctx, p, chunks) : fit >= 4 ? launchCompact<1, 4, 1>(ctx, p, chunks)
+                                                                                                 : launchCompact<1, 1, 1>(ctx, p, chunks);
+      else if (ctx->lMaxAll == 2) rc = fit >= 10 ? launchCompact<2, 5, 2>(ctx, p, chunks) : fit >= 3 ? launchCompact<2, 3, 1>(ctx, p, chunks)
+                                                                                                    : launchCompact<2, 1, 1>(ctx, p, chunks);
+      else rc = fit >= 3 ? launchCompact<3, 3, 1>(ctx, p, chunks) : launchCompact<3, 1, 1>(ctx, p, chunks);
+    }
     if (rc) return rc;
     ctx->launches++;
   }

@@ -492,8 +492,13 @@ int launchTypedS(dftbp_b200_ctx *ctx, const K5Params &p, long long items, int wa
 // the displacement loop by two does not help (136 us).
 template <int LMAX, bool STRESS>
 int launchByWarps(dftbp_b200_ctx *ctx, const K5Params &p, long long items, int warpsMax, size_t perWarp) {
-  if constexpr (LMAX <= 2) return launchTypedS<LMAX, STRESS, 8, 1>(ctx, p, items, warpsMax, perWarp);
-  else return launchTypedS<LMAX, STRESS, 2, 1>(ctx, p, items, warpsMax, perWarp);
+  // (species with repeated shells have weight blocks of up to 16 x 16: fewer warps fit)
+  if constexpr (LMAX <= 2) {
+    if (warpsMax >= 8) return launchTypedS<LMAX, STRESS, 8, 1>(ctx, p, items, warpsMax, perWarp);
+    if (warpsMax >= 4) return launchTypedS<LMAX, STRESS, 4, 1>(ctx, p, items, warpsMax, perWarp);
+  }
+  if (warpsMax >= 2) return launchTypedS<LMAX, STRESS, 2, 1>(ctx, p, items, warpsMax, perWarp);
+  return launchTypedS<LMAX, STRESS, 1, 1>(ctx, p, items, warpsMax, perWarp);
 }
 
 template <int LMAX>

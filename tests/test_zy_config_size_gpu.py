@@ -180,3 +180,55 @@ def test_fec4096_density_matrix_sampled_entries():
     assert float(up.abs().max()) == 0.0
     del C, dm
     hp.close()
+
+
+# ---- species that the .skf format cannot describe: repeated and unordered shells ---------------------
+def _table(rng, n_grid, n_int, dist):
+    r = dist * np.arange(1, n_grid + 1)
+    amp = rng.uniform(0.1, 0.5, n_int) * rng.choice([-1.0, 1.0], n_int)
+    a, b = rng.uniform(0.2, 0.6, n_int), rng.uniform(0.8, 1.4, n_int)
+    return np.asfortranarray(amp[None, :] * (1.0 + a[None, :] * r[:, None]) * np.exp(-b[None, :] * r[:, None]))
+
+
+@pytest.mark.parametrize("shells", [([0, 0, 1], [0, 1, 2, 2]), ([1, 0], [2, 1, 0, 1]), ([0, 1, 2], [0, 0]), ([3, 0], [0, 1, 2])])
+def test_non_canonical_shell_sets(shells):
+    """Advisor finding of round 1: species with repeated or unordered shells (s s* p, s p d d*, ...) go through
+    the generic paths of the pair kernels -- staging rows and write-out sized from the real block, not from
+    (lmax + 1)^2.  Tables come in through set_sk_table on both sides (no .skf file can hold such a species)."""
+    from dftbplus_b200.api import HotPath
+    from dftbplus_b200 import geometry
+    rng = np.random.default_rng(47)
+    dist, n_grid = 0.02, 300
+    model = oracle.Model(list(shells))
+    hp = HotPath(0)
+    hp.set_orbitals(list(shells))
+    for i in (1, 2):
+        for j in (1, 2):
+            n_int = model.n_integrals(i, j)
+            for which in (0, 1):
+                tab = _table(rng, n_grid, n_int, dist)
+                model.set_table(which, i, j, dist, tab)
+                hp.set_sk_table(which, i, j, dist, tab)
+    cutoff = model.cutoff()
+    assert abs(cutoff - hp.sk_cutoff()) < 1e-12
+    n_atom = 40
+    coord0 = rng.uniform(0.0, 11.0, size=(n_atom, 3))
+    species0 = rng.integers(1, 3, n_atom).astype(np.int32)
+    geo = geometry.build_geometry(coord0, species0, model.nOrbSpecies, np.eye(3) * 11.0, cutoff)
+    hp.set_geometry(geo)
+    selfegy = [list(rng.normal(size=len(s))) for s in shells]
+    h, s = hp.buildH0S(selfegy)
+    assert_sparse_close(h, oracle.build_h0(model, geo, selfegy), what="H0 " + str(shells))
+    assert_sparse_close(s, oracle.build_s(model, geo), what="S " + str(shells))
+    dm = s * rng.normal(size=(2, geo["sparseSize"]))
+    edm = s * rng.normal(size=geo["sparseSize"])
+    q = hp.mulliken(s, dm[0])
+    assert np.abs(q - oracle.mulliken_per_orbital(model, geo, s, dm[0])).max() < 1e-11
+    for sh in (None, _diag_shift(rng, 2, n_atom, model.mOrb), _full_shift(rng, 2, n_atom, model.mOrb)):
+        d = dm[0] if sh is None else dm
+        ref = oracle.derivative_shift(model, geo, d, edm, shift=sh)
+        got = hp.derivative_shift(d, edm, shift=sh)
+        assert np.abs(got - ref).max() < TOL_FORCE, (shells, np.abs(got - ref).max())
+    sq = hp.unpackHS(s)
+    assert np.array_equal(sq, oracle.unpack_hs_real(geo, s))
+    hp.close()
