@@ -105,6 +105,24 @@ static void polyInterU2(int nn, const double *xp, int nInt, const double *yp, do
   }
 }
 
+/* exported for tests/test_oracle_math_ref.py: these restatements against the machine translation of the
+ * reference's own routines (oracle/gen_ref_math.py -> oracle/_ref/libmathref.so) and its golden vectors */
+double orc_poly5_to_zero(double y0, double y0p, double y0pp, double xx, double dx, double invdx)
+{
+  return poly5ToZero(y0, y0p, y0pp, xx, dx, invdx);
+}
+
+void orc_free_cubic_spline(double y0, double y0p, double y0pp, double dx, double ydx, double xx,
+                           double *yy, double *yp, double *ypp)
+{
+  freeCubicSpline(y0, y0p, y0pp, dx, ydx, xx, yy, yp, ypp);
+}
+
+void orc_poly_inter_u2(int nn, const double *xp, int nInt, const double *yp, double xx, double *yy)
+{
+  polyInterU2(nn, xp, nInt, yp, xx, yy);
+}
+
 /* ------------------------------------------------------------------------------------------
  * dftb/slakoeqgrid.F90 : one equidistant SK table.  skTab(nGrid, nInteg) column-major.
  * ---------------------------------------------------------------------------------------- */
