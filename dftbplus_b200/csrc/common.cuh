@@ -104,6 +104,10 @@ struct Geometry {
   bool hasDuplicates = false;    // two blocks of one atom fold onto the same dense block
   bool coversAll = true;         // the blocks tile [0, sparseSize) completely (no zero fill needed)
   int firstAtomMine = 0, lastAtomMine = -1;  // 0-based inclusive atom chunk of workMine
+  // element -> descriptor index of the TMA-streamed element-wise kernels (flat_stream.cuh): per group of
+  // 32 elements of the sparse arrays the descriptor of the block its first element lies in; null when a
+  // list is not sorted by offset (those lists take the warp-per-block kernels)
+  int *groupFirstAll = nullptr, *groupFirstLoad = nullptr;
 };
 
 struct Staging {
@@ -155,6 +159,8 @@ struct dftbp_b200_ctx {
   bool allSimple = false;     // no species has two shells of the same l (two-kernel pair build possible)
   double *pairExchange = nullptr;  // per work-list entry: interpolated integrals of H0 and S (k1_pair_build.cu)
   long long pairExchangeCap = 0;   // allocated doubles
+  double *shiftDiag = nullptr;     // (mOrb, nAtom, nSpin): diagonals of the block shifts of the current call, compact
+  long long shiftDiagCap = 0;
 
   // orbitals
   int nSpecies = 0, mShell = 0, mOrb = 0;
@@ -315,6 +321,22 @@ inline int uploadNew(dftbp_b200_ctx *ctx, T **dst, const T *src, size_t count) {
   DFTBP_CUDA(ctx, cudaMemcpyAsync(*dst, src, count * sizeof(T), kind, ctx->stream));
   // the source may be a temporary host vector: make the copy complete before returning
   DFTBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// grow-only buffer for the compact diagonals of block shifts (k5_forces.cu, k6_add_shift.cu)
+inline int shiftDiagBuffer(dftbp_b200_ctx *ctx, long long need, double **out) {
+  if (ctx->shiftDiagCap < need) {
+    if (ctx->shiftDiag) cudaFree(ctx->shiftDiag);
+    ctx->shiftDiag = nullptr;
+    ctx->shiftDiagCap = 0;
+    cudaError_t e = cudaMalloc((void **)&ctx->shiftDiag, sizeof(double) * (size_t)need);
+    if (e != cudaSuccess)
+      return fail(ctx, DFTBP_B200_ENOMEM, "cudaMalloc(%lld) for the shift diagonals failed: %s",
+                  (long long)(sizeof(double) * need), cudaGetErrorString(e));
+    ctx->shiftDiagCap = need;
+  }
+  *out = ctx->shiftDiag;
   return 0;
 }
 

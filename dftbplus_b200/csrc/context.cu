@@ -3,6 +3,7 @@
 #include <cmath>
 
 #include "block_desc.cuh"
+#include "flat_stream.cuh"
 #include "sk_table_prep.h"
 
 using namespace dftbp_b200;
@@ -18,6 +19,8 @@ void freeGeometry(Geometry &g) {
   cudaFree(g.workAll);
   if (g.descLoad != g.descAll) cudaFree(g.descLoad);
   cudaFree(g.descAll);
+  if (g.groupFirstLoad != g.groupFirstAll) cudaFree(g.groupFirstLoad);
+  cudaFree(g.groupFirstAll);
   g = Geometry();
 }
 
@@ -87,6 +90,7 @@ int dftbp_b200_destroy(dftbp_b200_ctx *ctx) {
   for (Staging &s : ctx->staging) cudaFree(s.ptr);
   cudaFree(ctx->dNOrbSpecies); cudaFree(ctx->dOrbShell); cudaFree(ctx->dProgs);
   cudaFree(ctx->pairExchange);
+  cudaFree(ctx->shiftDiag);
   cudaFree(ctx->solverWork); cudaFree(ctx->dInfo);
   solverDestroy(ctx);
   for (TimedSpan &sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -374,13 +378,21 @@ int dftbp_b200_set_geometry(dftbp_b200_ctx *ctx, int nAtom, int nAllAtom, int mN
     }
     return d;
   };
+  // element -> descriptor index of a descriptor list for the TMA-streamed kernels (flat_stream.cuh)
+  auto groupIndex = [&](const std::vector<BlockDesc> &d, int **out) -> int {
+    std::vector<int> first;
+    if (!flat::buildGroupIndex(d.data(), (long long)d.size(), sparseSize, first)) return 0;
+    return uploadNew(ctx, out, first.data(), first.size());
+  };
   {
     std::vector<BlockDesc> d = describe(all);
     DFTBP_TRY(uploadNew(ctx, &g.descAll, d.data(), d.size()));
+    DFTBP_TRY(groupIndex(d, &g.groupFirstAll));
   }
   if (ctx->nRanks == 1) {
     g.workMine = g.workLoad = g.workAll;
     g.descLoad = g.descAll;
+    g.groupFirstLoad = g.groupFirstAll;
     g.nWorkMine = g.nWorkLoad = g.nWorkAll;
     g.nPairsMine = g.nWorkAll - nAtom;
     g.firstAtomMine = 0;
@@ -403,6 +415,7 @@ int dftbp_b200_set_geometry(dftbp_b200_ctx *ctx, int nAtom, int nAllAtom, int mN
     {
       std::vector<BlockDesc> d = describe(load);
       DFTBP_TRY(uploadNew(ctx, &g.descLoad, d.data(), d.size()));
+      DFTBP_TRY(groupIndex(d, &g.groupFirstLoad));
     }
     g.nWorkMine = (long long)mine.size();
     g.nWorkLoad = (long long)load.size();

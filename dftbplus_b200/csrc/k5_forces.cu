@@ -25,6 +25,7 @@
 #include <cstdlib>
 
 #include "block_desc.cuh"
+#include "flat_stream.cuh"
 #include "sk_lane_eval.cuh"
 
 using namespace dftbp_b200;
@@ -73,16 +74,20 @@ __device__ __forceinline__ K5Pair k5LoadPair(const K5Params &p, int chunk, int l
   return k;
 }
 
-// flag = 1 if any off-diagonal element of any shift block is non-zero (one warp per block)
+// flag = 1 if any off-diagonal element of any shift block is non-zero (one warp per block); the
+// diagonals go to diag(mOrb, nBlocks), compact: the element-wise kernels read V(a,a) of the two atoms
+// of every sparse element, and in the blocks every value sits in a sector of its own
 __global__ void __launch_bounds__(256) k5_shift_structure(const double *__restrict__ shift, int mOrb, int nBlocks,
-                                                          int *flag) {
+                                                          int *flag, double *__restrict__ diag) {
   const int lane = threadIdx.x & 31, mo2 = mOrb * mOrb;
   bool any = false;
   for (int blk = blockIdx.x * 8 + (threadIdx.x >> 5); blk < nBlocks; blk += gridDim.x * 8) {
     const double *__restrict__ v = shift + (size_t)mo2 * blk;
     for (int e = lane; e < mo2; e += 32) {
       const int a = e / mOrb, b = e - a * mOrb;
-      if (a != b && __ldg(v + e) != 0.0) any = true;
+      const double x = __ldg(v + e);
+      if (a != b && x != 0.0) any = true;
+      if (a == b) diag[(size_t)mOrb * blk + a] = x;
     }
   }
   if (__any_sync(0xffffffffu, any) && lane == 0) atomicOr(flag, 1);
@@ -233,6 +238,54 @@ __global__ void __launch_bounds__(256) k5_force_weights_diag(const K5Params p, c
       }
     }
   });
+}
+
+// Diagonal shift blocks through the span pipeline of flat_stream.cuh: Erho and the NSPIN channels of
+// rho arrive by TMA bulk copies, lanes on consecutive elements of the sparse arrays whatever block
+// they belong to; the shift diagonals come from the compact copy k5_shift_structure leaves.  Weights
+// of every block of the list are formed (a force call with a partition reads only its own): used on
+// one rank / one partition.
+template <int NSPIN>
+__global__ void __launch_bounds__(32 * flat::warpsFor(1 + NSPIN), 1)
+    k5_force_weights_flat(const K5Params p, const BlockDesc *__restrict__ desc, long long nWork,
+                          const int *__restrict__ groupFirst, const double *__restrict__ EDM,
+                          const double *__restrict__ diag, const int *__restrict__ shiftFull,
+                          double *__restrict__ negWS) {
+  if (__ldg(shiftFull) != 0) return;  // full blocks: k5_force_weights_sched<1, true>
+  constexpr int NIN = 1 + NSPIN, WARPS = flat::warpsFor(NIN);
+  extern __shared__ __align__(128) unsigned char flatRaw[];
+  flat::Smem<NIN, WARPS> &sm = *reinterpret_cast<flat::Smem<NIN, WARPS> *>(flatRaw);
+  __shared__ unsigned m2[kMaxOrb + 1];
+  flat::initDivTable(m2);
+  const double *src[NIN];
+  src[0] = EDM;
+#pragma unroll
+  for (int iSpin = 0; iSpin < NSPIN; ++iSpin) src[1 + iSpin] = p.DM + (size_t)p.sparseSize * iSpin;
+  const int mOrb = p.mOrb;
+  const int spinStride = mOrb * p.nAtom;  // diag(:, :, iSpin + 1) - diag(:, :, iSpin)
+  flat::streamSpans<NIN, WARPS>(
+      sm, src, p.sparseSize, desc, (int)nWork, groupFirst, [&](const flat::Elem<NIN>(&el)[flat::kBatch]) {
+        double x1[flat::kBatch][NSPIN], x2[flat::kBatch][NSPIN];
+#pragma unroll
+        for (int u = 0; u < flat::kBatch; ++u) {
+          const int n2 = el[u].lo.w >> 8, e = el[u].e;
+          const int a = (int)(((unsigned)e * m2[n2]) >> 20), bb = e - a * n2;  // element (row bb, col a)
+          const double *__restrict__ V1 = diag + (mOrb * el[u].hi.x + a);
+          const double *__restrict__ V2 = diag + (mOrb * el[u].hi.y + bb);
+#pragma unroll
+          for (int iSpin = 0; iSpin < NSPIN; ++iSpin) {
+            x1[u][iSpin] = __ldg(V1 + (size_t)spinStride * iSpin);
+            x2[u][iSpin] = __ldg(V2 + (size_t)spinStride * iSpin);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < flat::kBatch; ++u) {
+          double w = el[u].v[0];
+#pragma unroll
+          for (int iSpin = 0; iSpin < NSPIN; ++iSpin) w = fma(-0.5 * el[u].v[1 + iSpin], x1[u][iSpin] + x2[u][iSpin], w);
+          if (el[u].ok) negWS[el[u].x] = w;
+        }
+      });
 }
 
 template <int LMAX, bool STRESS, int WARPS, int UNR>
@@ -511,6 +564,27 @@ int launchTyped(dftbp_b200_ctx *ctx, const K5Params &p, long long items, int war
 
 namespace {
 
+template <int NSPIN>
+int launchWeightsFlatT(dftbp_b200_ctx *ctx, const K5Params &p, const BlockDesc *desc, long long nWork,
+                       const int *groupFirst, const double *EDM, const double *diag, const int *flag, double *negWS) {
+  constexpr int NIN = 1 + NSPIN, WARPS = flat::warpsFor(NIN);
+  const size_t smemBytes = sizeof(flat::Smem<NIN, WARPS>);
+  static LaunchInfo info;
+  DFTBP_TRY(launchInfo(ctx, info, k5_force_weights_flat<NSPIN>, 32 * WARPS, smemBytes, nullptr));
+  const long long nSpans = ((long long)p.sparseSize + flat::kSpan - 1) / flat::kSpan;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((nSpans + WARPS - 1) / WARPS, ctx->smCount));
+  k5_force_weights_flat<NSPIN><<<grid, 32 * WARPS, smemBytes, ctx->stream>>>(p, desc, nWork, groupFirst, EDM, diag, flag,
+                                                                            negWS);
+  return 0;
+}
+
+int launchWeightsFlat(dftbp_b200_ctx *ctx, int nSpin, const K5Params &p, const BlockDesc *desc, long long nWork,
+                      const int *groupFirst, const double *EDM, const double *diag, const int *flag, double *negWS) {
+  if (nSpin == 1) return launchWeightsFlatT<1>(ctx, p, desc, nWork, groupFirst, EDM, diag, flag, negWS);
+  if (nSpin == 2) return launchWeightsFlatT<2>(ctx, p, desc, nWork, groupFirst, EDM, diag, flag, negWS);
+  return launchWeightsFlatT<4>(ctx, p, desc, nWork, groupFirst, EDM, diag, flag, negWS);
+}
+
 // derivative_shift (deriv != nullptr) and / or the stress tensor (st != nullptr) from one pass over the pairs
 int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, const double *DM, int nSpin,
                const double *EDM, const double *shift, int diffType, double delta) {
@@ -558,8 +632,10 @@ int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, c
       // plain SCC / collinear spin shifts are diagonal blocks: detect it, then form -wS once per block
       int *flag = ctx->dInfo + 1;
       DFTBP_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+      double *dDiag;
+      DFTBP_TRY(shiftDiagBuffer(ctx, (long long)ctx->mOrb * g.nAtom * nSpin, &dDiag));
       k5_shift_structure<<<std::min(ctx->smCount * 8, (g.nAtom * nSpin + 7) / 8), 256, 0, ctx->stream>>>(
-          dShift, ctx->mOrb, g.nAtom * nSpin, flag);
+          dShift, ctx->mOrb, g.nAtom * nSpin, flag, dDiag);
       void *scratch;
       DFTBP_TRY(stagingGet(ctx, kSlotE, sizeof(double) * (size_t)g.sparseSize, &scratch));
       // both instantiations are launched; the one that does not match the device flag returns at once
@@ -568,7 +644,12 @@ int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, c
       const int self = st ? 1 : 0;
       // diagonal shifts: the blocks in memory order (descriptors of the work list + their schedule slots)
       const int dGrid = gridFor(ctx, (g.nWorkLoad + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, 4);
-      if (nSpin == 1) k5_force_weights_diag<1><<<dGrid, 256, 0, ctx->stream>>>(p, g.descLoad, sched->slotOf, g.nWorkLoad, dEDM, dShift, flag, (double *)scratch, self);
+      // one partition and a sorted list of not too small blocks: the TMA span pipeline (flat_stream.cuh)
+      const bool useFlat = p.nParts == 1 && g.groupFirstLoad != nullptr && (long long)ctx->mOrb * g.nAtom * nSpin < (1LL << 31) &&
+                           tuneInt("DFTBP_B200_K5_FLAT", 1) != 0;
+      if (useFlat) {
+        DFTBP_TRY(launchWeightsFlat(ctx, nSpin, p, g.descLoad, g.nWorkLoad, g.groupFirstLoad, dEDM, dDiag, flag, (double *)scratch));
+      } else if (nSpin == 1) k5_force_weights_diag<1><<<dGrid, 256, 0, ctx->stream>>>(p, g.descLoad, sched->slotOf, g.nWorkLoad, dEDM, dShift, flag, (double *)scratch, self);
       else if (nSpin == 2) k5_force_weights_diag<2><<<dGrid, 256, 0, ctx->stream>>>(p, g.descLoad, sched->slotOf, g.nWorkLoad, dEDM, dShift, flag, (double *)scratch, self);
       else k5_force_weights_diag<4><<<dGrid, 256, 0, ctx->stream>>>(p, g.descLoad, sched->slotOf, g.nWorkLoad, dEDM, dShift, flag, (double *)scratch, self);
       k5_force_weights_sched<1, true><<<wGrid, 256, 0, ctx->stream>>>(p, dEDM, dShift, flag, (double *)scratch, self);

@@ -14,6 +14,7 @@
 // isInputZero: the reference zeroes ham and loops over this rank's workload-balanced atoms
 // (distributeRangeWithWorkload; assembleChunks sums the ranks); otherwise every rank does all atoms.
 #include "block_desc.cuh"
+#include "flat_stream.cuh"
 
 using namespace dftbp_b200;
 
@@ -25,19 +26,24 @@ struct K6Params {
   int mOrb, nAtom, nSpin, sparseSize;
   const double *over, *shift;
   const int *shiftFull;  // device flag (block variant): 1 = some block has off-diagonal elements
+  const double *diag;    // (mOrb, nAtom, nSpin): diagonals of the block shifts, compact (k6_shift_structure)
   double *ham;
 };
 
-// flag = 1 if any off-diagonal element of any shift block is non-zero (one warp per block)
+// flag = 1 if any off-diagonal element of any shift block is non-zero (one warp per block); the
+// diagonals go to diag(mOrb, nBlocks), compact: the element-wise kernels read V(a,a) of the two atoms
+// of every sparse element, and in the blocks every value sits in a sector of its own
 __global__ void __launch_bounds__(256) k6_shift_structure(const double *__restrict__ shift, int mOrb, int nBlocks,
-                                                          int *flag) {
+                                                          int *flag, double *__restrict__ diag) {
   const int lane = threadIdx.x & 31, mo2 = mOrb * mOrb;
   bool any = false;
   for (int blk = blockIdx.x * 8 + (threadIdx.x >> 5); blk < nBlocks; blk += gridDim.x * 8) {
     const double *__restrict__ v = shift + (size_t)mo2 * blk;
     for (int e = lane; e < mo2; e += 32) {
       const int a = e / mOrb, b = e - a * mOrb;
-      if (a != b && __ldg(v + e) != 0.0) any = true;
+      const double x = __ldg(v + e);
+      if (a != b && x != 0.0) any = true;
+      if (a == b) diag[(size_t)mOrb * blk + a] = x;
     }
   }
   if (__any_sync(0xffffffffu, any) && lane == 0) atomicOr(flag, 1);
@@ -100,6 +106,80 @@ __global__ void __launch_bounds__(256) k6_add_shift(const K6Params p) {
       [] {});
 }
 
+// Atom shifts and diagonal block shifts through the span pipeline of flat_stream.cuh: `over` (and,
+// when accumulating, the NSPIN channels of `ham`) arrive by TMA bulk copies; lanes on consecutive
+// elements of the sparse arrays whatever block they belong to.
+template <int MODE, int NSPIN, bool ZERO>
+__global__ void __launch_bounds__(32 * flat::warpsFor(ZERO ? 1 : 1 + NSPIN), 1)
+    k6_add_shift_flat(const K6Params p, const int *__restrict__ groupFirst) {
+  if (MODE == 1 && __ldg(p.shiftFull) != 0) return;  // the MODE 2 launch handles it
+  constexpr int NIN = ZERO ? 1 : 1 + NSPIN, WARPS = flat::warpsFor(NIN);
+  extern __shared__ __align__(128) unsigned char flatRaw[];
+  flat::Smem<NIN, WARPS> &sm = *reinterpret_cast<flat::Smem<NIN, WARPS> *>(flatRaw);
+  __shared__ unsigned m2[kMaxOrb + 1];
+  flat::initDivTable(m2);
+  const double *src[NIN];
+  src[0] = p.over;
+  if constexpr (!ZERO) {
+#pragma unroll
+    for (int iSpin = 0; iSpin < NSPIN; ++iSpin) src[1 + iSpin] = p.ham + (size_t)p.sparseSize * iSpin;
+  }
+  const int mOrb = p.mOrb;
+  const int spinStride = (MODE == 0 ? 1 : mOrb) * p.nAtom;
+  flat::streamSpans<NIN, WARPS>(
+      sm, src, p.sparseSize, p.desc, (int)p.nWork, groupFirst, [&](const flat::Elem<NIN>(&el)[flat::kBatch]) {
+        double v1[flat::kBatch][NSPIN], v2[flat::kBatch][NSPIN];
+#pragma unroll
+        for (int u = 0; u < flat::kBatch; ++u) {
+          const double *__restrict__ V1, *__restrict__ V2;
+          if (MODE == 0) {
+            V1 = p.shift + el[u].hi.x;
+            V2 = p.shift + el[u].hi.y;
+          } else {
+            const int n2 = el[u].lo.w >> 8, e = el[u].e;
+            const int a = (int)(((unsigned)e * m2[n2]) >> 20), b = e - a * n2;  // element (row b, col a)
+            V1 = p.diag + (mOrb * el[u].hi.x + a);
+            V2 = p.diag + (mOrb * el[u].hi.y + b);
+          }
+#pragma unroll
+          for (int iSpin = 0; iSpin < NSPIN; ++iSpin) {
+            v1[u][iSpin] = __ldg(V1 + (size_t)spinStride * iSpin);
+            v2[u][iSpin] = __ldg(V2 + (size_t)spinStride * iSpin);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < flat::kBatch; ++u) {
+          const double s = el[u].v[0];
+#pragma unroll
+          for (int iSpin = 0; iSpin < NSPIN; ++iSpin) {
+            const double xs = MODE == 0 ? s * 0.5 * (v1[u][iSpin] + v2[u][iSpin]) : 0.5 * (s * (v1[u][iSpin] + v2[u][iSpin]));
+            double h = 0.0;
+            if constexpr (!ZERO) h = el[u].v[1 + iSpin];
+            if (el[u].ok) p.ham[(size_t)p.sparseSize * iSpin + el[u].x] = h + xs;
+          }
+        }
+      });
+}
+
+template <int MODE, int NSPIN, bool ZERO>
+int launchFlatT(dftbp_b200_ctx *ctx, const K6Params &p, const int *groupFirst) {
+  constexpr int NIN = ZERO ? 1 : 1 + NSPIN, WARPS = flat::warpsFor(NIN);
+  const size_t smemBytes = sizeof(flat::Smem<NIN, WARPS>);
+  static LaunchInfo info;
+  DFTBP_TRY(launchInfo(ctx, info, k6_add_shift_flat<MODE, NSPIN, ZERO>, 32 * WARPS, smemBytes, nullptr));
+  const long long nSpans = ((long long)p.sparseSize + flat::kSpan - 1) / flat::kSpan;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((nSpans + WARPS - 1) / WARPS, ctx->smCount));
+  k6_add_shift_flat<MODE, NSPIN, ZERO><<<grid, 32 * WARPS, smemBytes, ctx->stream>>>(p, groupFirst);
+  return 0;
+}
+
+template <int MODE>
+int launchFlat(dftbp_b200_ctx *ctx, const K6Params &p, bool zero, const int *groupFirst) {
+  if (p.nSpin == 1) return zero ? launchFlatT<MODE, 1, true>(ctx, p, groupFirst) : launchFlatT<MODE, 1, false>(ctx, p, groupFirst);
+  if (p.nSpin == 2) return zero ? launchFlatT<MODE, 2, true>(ctx, p, groupFirst) : launchFlatT<MODE, 2, false>(ctx, p, groupFirst);
+  return zero ? launchFlatT<MODE, 4, true>(ctx, p, groupFirst) : launchFlatT<MODE, 4, false>(ctx, p, groupFirst);
+}
+
 template <int MODE, bool ZERO>
 void launchModeZ(const K6Params &p, int grid, cudaStream_t st) {
   if (p.nSpin == 1) k6_add_shift<MODE, 1, ZERO><<<grid, 256, 0, st>>>(p);
@@ -126,28 +206,39 @@ int addShiftImpl(dftbp_b200_ctx *ctx, double *ham, const double *over, const dou
   DFTBP_TRY(devOut(ctx, kSlotA, ham, (size_t)g.sparseSize * nSpin, !isInputZero, &p.ham));
   DFTBP_TRY(devIn(ctx, kSlotB, over, (size_t)g.sparseSize, &p.over));
   DFTBP_TRY(devIn(ctx, kSlotC, shift, nShift, &p.shift));
+  const int *groupFirst;
   if (isInputZero) {
     // several ranks: the blocks of the other ranks' atoms stay zero (assembleChunks sums the arrays)
     if (ctx->nRanks > 1 || !g.coversAll)
       DFTBP_CUDA(ctx, cudaMemsetAsync(p.ham, 0, sizeof(double) * (size_t)g.sparseSize * nSpin, ctx->stream));
     p.desc = g.descLoad; p.nWork = g.nWorkLoad;
+    groupFirst = g.groupFirstLoad;
   } else {
     p.desc = g.descAll; p.nWork = g.nWorkAll;
+    groupFirst = g.groupFirstAll;
   }
+  // sorted lists of not too small blocks: the TMA span pipeline (flat_stream.cuh)
+  const bool useFlat = groupFirst != nullptr && nShift < ((size_t)1 << 31) && tuneInt("DFTBP_B200_K6_FLAT", 1) != 0;
   p.shiftFull = ctx->dInfo + 1;
+  p.diag = nullptr;
   if (p.nWork > 0) {
     ScopedTimer timer(ctx, kTimerAddShift);
     const int grid = gridFor(ctx, (p.nWork + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, tuneInt("DFTBP_B200_K6_CTAS", 4));
     if (!block) {
-      launchMode<0>(p, isInputZero != 0, grid, ctx->stream);
+      if (useFlat) DFTBP_TRY(launchFlat<0>(ctx, p, isInputZero != 0, groupFirst));
+      else launchMode<0>(p, isInputZero != 0, grid, ctx->stream);
       ctx->launches++;
     } else {
       int *flag = ctx->dInfo + 1;
       DFTBP_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+      double *dDiag;
+      DFTBP_TRY(shiftDiagBuffer(ctx, (long long)ctx->mOrb * g.nAtom * nSpin, &dDiag));
+      p.diag = dDiag;
       k6_shift_structure<<<std::min(ctx->smCount * 8, (g.nAtom * nSpin + 7) / 8), 256, 0, ctx->stream>>>(
-          p.shift, ctx->mOrb, g.nAtom * nSpin, flag);
+          p.shift, ctx->mOrb, g.nAtom * nSpin, flag, dDiag);
       // both forms are launched; the one that does not match the device flag returns at once
-      launchMode<1>(p, isInputZero != 0, grid, ctx->stream);
+      if (useFlat) DFTBP_TRY(launchFlat<1>(ctx, p, isInputZero != 0, groupFirst));
+      else launchMode<1>(p, isInputZero != 0, grid, ctx->stream);
       launchMode<2>(p, isInputZero != 0, grid, ctx->stream);
       ctx->launches += 3;
     }
