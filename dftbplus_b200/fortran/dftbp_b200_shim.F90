@@ -9,10 +9,15 @@ module dftbp_b200_shim
   implicit none
   private
 
-  public :: TB200Ctx, b200_init, b200_setGeometry
+  public :: TB200Ctx, b200_init, b200_destroy, b200_setGeometry, b200_updateCoords
+  public :: b200_updateNeighbourListAndSpecies, b200_foldCoordsToCell, b200_getNrOfNeighboursForAll
   public :: b200_buildH0, b200_buildS, b200_unpackHS_real, b200_unpackHS_cmplx
-  public :: b200_packHS_real, b200_packHS_cmplx, b200_getDensityMatrix_real
-  public :: b200_mullikenPerOrbital, b200_derivative_shift, b200_addShift_block, b200_addShift_atom, b200_getBlockStress
+  public :: b200_packHS_real, b200_packHS_cmplx
+  public :: b200_getDensityMatrix_real, b200_getDensityMatrix_cmplx
+  public :: b200_getEDensityMatrix_real, b200_getEDensityMatrix_cmplx
+  public :: b200_mullikenPerOrbital, b200_mullikenPerBlock, b200_mullikenPerAtom, b200_getOnsitePopulation
+  public :: b200_derivative_shift, b200_addShift_block, b200_addShift_atom, b200_getBlockStress
+  public :: b200_hegv_real, b200_hegv_cmplx
 
   integer, parameter :: dp = c_double
 
@@ -189,6 +194,47 @@ module dftbp_b200_shim
       type(c_ptr), value :: ctx
       real(c_double), value :: cutoff
       integer(c_int), intent(out) :: nNeighbour(*)
+    end function
+    integer(c_int) function dftbp_b200_destroy(ctx) bind(C)
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx
+    end function
+    integer(c_int) function dftbp_b200_update_coords(ctx, coords) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(in) :: coords(*)
+    end function
+    integer(c_int) function dftbp_b200_density_matrix_cplx(ctx, dm, eigvecs, n, ld, filling, weights)&
+        & bind(C)
+      import :: c_ptr, c_int, c_double, c_double_complex
+      type(c_ptr), value :: ctx
+      complex(c_double_complex), intent(out) :: dm(*)
+      complex(c_double_complex), intent(in) :: eigvecs(*)
+      real(c_double), intent(in) :: filling(*)
+      integer(c_int), value :: n, ld
+      type(c_ptr), value :: weights
+    end function
+    integer(c_int) function dftbp_b200_mulliken_block(ctx, qq, over, rho) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(inout) :: qq(*)
+      real(c_double), intent(in) :: over(*), rho(*)
+    end function
+    integer(c_int) function dftbp_b200_hegv_real(ctx, H, S, eigen, n, ld, jobz) bind(C)
+      import :: c_ptr, c_int, c_double, c_char
+      type(c_ptr), value :: ctx
+      real(c_double), intent(inout) :: H(*), S(*)
+      real(c_double), intent(out) :: eigen(*)
+      integer(c_int), value :: n, ld
+      character(kind=c_char), value :: jobz
+    end function
+    integer(c_int) function dftbp_b200_hegv_cplx(ctx, H, S, eigen, n, ld, jobz) bind(C)
+      import :: c_ptr, c_int, c_double, c_double_complex, c_char
+      type(c_ptr), value :: ctx
+      complex(c_double_complex), intent(inout) :: H(*), S(*)
+      real(c_double), intent(out) :: eigen(*)
+      integer(c_int), value :: n, ld
+      character(kind=c_char), value :: jobz
     end function
     integer(c_int) function dftbp_b200_adopt_neighbour_list(ctx) bind(C)
       import :: c_ptr, c_int
@@ -405,6 +451,87 @@ contains
     call check(ctx, dftbp_b200_density_matrix_real(ctx%h, dm, eigenvecs, size(dm, dim=2),&
         & size(dm, dim=1), filling, c_null_ptr))
   end subroutine b200_getDensityMatrix_real
+
+  !> fullDensityMatrix_cmplx, dftb/densitymatrix.F90:597 (caller: getDensityFromCplxEigvecs,
+  !> dftbplus/main.F90:4289 -- one call per local (k-point, spin) of TParallelKS)
+  subroutine b200_getDensityMatrix_cmplx(ctx, dm, eigenvecs, filling)
+    type(TB200Ctx), intent(in) :: ctx
+    complex(dp), intent(out) :: dm(:,:)
+    complex(dp), intent(in) :: eigenvecs(:,:)
+    real(dp), intent(in) :: filling(:)
+    call check(ctx, dftbp_b200_density_matrix_cplx(ctx%h, dm, eigenvecs, size(dm, dim=2),&
+        & size(dm, dim=1), filling, c_null_ptr))
+  end subroutine b200_getDensityMatrix_cmplx
+
+  !> fullEnergyDensityMatrix_real, dftb/densitymatrix.F90:664 (caller: getEDensityMtxFromRealEigvecs,
+  !> dftbplus/main.F90:6572): dm = C diag(filling * eigen) C^T; filling decides the number of levels
+  subroutine b200_getEDensityMatrix_real(ctx, dm, eigenvecs, filling, eigen)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(out) :: dm(:,:)
+    real(dp), intent(in) :: eigenvecs(:,:), filling(:), eigen(:)
+    real(dp), allocatable, target :: weights(:)
+    weights = filling * eigen
+    call check(ctx, dftbp_b200_density_matrix_real(ctx%h, dm, eigenvecs, size(dm, dim=2),&
+        & size(dm, dim=1), filling, c_loc(weights)))
+  end subroutine b200_getEDensityMatrix_real
+
+  !> fullEnergyDensityMatrix_cmplx, dftb/densitymatrix.F90:739 (caller: getEDensityMtxFromComplexEigvecs,
+  !> dftbplus/main.F90:6808)
+  subroutine b200_getEDensityMatrix_cmplx(ctx, dm, eigenvecs, filling, eigen)
+    type(TB200Ctx), intent(in) :: ctx
+    complex(dp), intent(out) :: dm(:,:)
+    complex(dp), intent(in) :: eigenvecs(:,:)
+    real(dp), intent(in) :: filling(:), eigen(:)
+    real(dp), allocatable, target :: weights(:)
+    weights = filling * eigen
+    call check(ctx, dftbp_b200_density_matrix_cplx(ctx%h, dm, eigenvecs, size(dm, dim=2),&
+        & size(dm, dim=1), filling, c_loc(weights)))
+  end subroutine b200_getEDensityMatrix_cmplx
+
+  !> diagDenseMtx, dftbplus/eigenvects.F90:85-100 (hegvd branch, real): on exit HSqr holds the
+  !> eigenvectors, SSqr its Cholesky factor
+  subroutine b200_hegv_real(ctx, HSqr, SSqr, eigen, jobz)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(inout) :: HSqr(:,:), SSqr(:,:)
+    real(dp), intent(out) :: eigen(:)
+    character, intent(in) :: jobz
+    call check(ctx, dftbp_b200_hegv_real(ctx%h, HSqr, SSqr, eigen, size(HSqr, dim=2), size(HSqr, dim=1),&
+        & jobz))
+  end subroutine b200_hegv_real
+
+  !> diagDenseMtx, complex Hermitian case (k-points)
+  subroutine b200_hegv_cmplx(ctx, HSqr, SSqr, eigen, jobz)
+    type(TB200Ctx), intent(in) :: ctx
+    complex(dp), intent(inout) :: HSqr(:,:), SSqr(:,:)
+    real(dp), intent(out) :: eigen(:)
+    character, intent(in) :: jobz
+    call check(ctx, dftbp_b200_hegv_cplx(ctx%h, HSqr, SSqr, eigen, size(HSqr, dim=2), size(HSqr, dim=1),&
+        & jobz))
+  end subroutine b200_hegv_cmplx
+
+  !> mullikenPerBlock, dftb/populations.F90:306 -- qq(mOrb, mOrb, nAtom) accumulates
+  subroutine b200_mullikenPerBlock(ctx, qq, over, rho)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(inout) :: qq(:,:,:)
+    real(dp), intent(in) :: over(:), rho(:)
+    call check(ctx, dftbp_b200_mulliken_block(ctx%h, qq, over, rho))
+  end subroutine b200_mullikenPerBlock
+
+  !> New coordinates on an unchanged neighbour list (geometry steps between list rebuilds):
+  !> coords(3, nAllAtom) as updateNeighbourListAndSpecies left them
+  subroutine b200_updateCoords(ctx, coords)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(in) :: coords(:,:)
+    call check(ctx, dftbp_b200_update_coords(ctx%h, coords))
+  end subroutine b200_updateCoords
+
+  !> End of run (the counterpart of b200_init)
+  subroutine b200_destroy(ctx)
+    type(TB200Ctx), intent(inout) :: ctx
+    integer(c_int) :: rc
+    if (c_associated(ctx%h)) rc = dftbp_b200_destroy(ctx%h)
+    ctx%h = c_null_ptr
+  end subroutine b200_destroy
 
   !> mullikenPerOrbital, dftb/populations.F90:120
   subroutine b200_mullikenPerOrbital(ctx, qq, over, rho)

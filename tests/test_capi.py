@@ -57,3 +57,35 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "dftb_oracle" not in text and "liboracle" not in text, f
+
+
+def _build_c_driver(tmp_path):
+    """tests/c_driver/chain.c: the hot path from plain C99 through include/dftbp_b200.h."""
+    import subprocess
+    exe = str(tmp_path / "chain")
+    libdir = os.path.dirname(_lib.SO_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_driver", "chain.c"), "-o", exe,
+                           "-L" + libdir, "-ldftbp_b200", "-lm", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_c_driver_links_and_refuses_without_gpu(lib, tmp_path):
+    import subprocess
+    import torch
+    exe = _build_c_driver(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the run itself is test_c_driver_chain")
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 77, p.stdout + p.stderr      # DFTBP_B200_ENODEVICE -> 77
+    assert "no CPU fallback" in p.stdout
+
+
+@pytest.mark.gpu
+def test_c_driver_chain(lib, tmp_path):
+    """build_h0_s -> unpack -> hegv -> density_matrix -> pack -> mulliken -> derivative_shift from C."""
+    import subprocess
+    exe = _build_c_driver(tmp_path)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "chain.c: OK" in p.stdout
