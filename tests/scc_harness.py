@@ -14,6 +14,8 @@ getDensityMatrix -> packHS -> mulliken]* -> getEDensityMatrix -> packHS -> deriv
 import numpy as np
 import scipy.linalg
 
+from oracle import scc_model
+
 
 def short_gamma(coords, species0, hubb_u):
     """gamma[nAtom, nAtom] for a cluster (Elstner et al. 1998, eqs. (12)-(14))."""
@@ -114,35 +116,73 @@ class DeviceArm:
         return self.hp.derivative_shift(rho, erho, shift=shift_block)
 
 
-def scc_single_point(arm, workload, sk, geo, m_orb, tol=1e-8, mix=0.4, max_iter=200, q_init=None):
-    """Returns dict(n_iter, energy, q, forces).  Convergence: max |q_out - q_in| < tol on the
-    orbital-resolved Mulliken charges (main.F90:4884-4930 with a simple mixer).  q_init: input
-    charges of the first iteration (the previous geometry step's output: "SCC restart")."""
+def scc_single_point(arm, workload, sk, geo, m_orb, tol=1e-8, mix=0.4, max_iter=200, q_init=None,
+                     reference_defaults=False, kT=None):
+    """Returns dict(n_iter, energy, q, forces).  q_init: input charges of the first iteration (the
+    previous geometry step's output: "SCC restart").
+
+    reference_defaults = False: simple mixing of the orbital-resolved charges with parameter `mix`,
+    bisection Fermi level at kT = 0.001 (the round-1 model).
+    reference_defaults = True: the SCC loop as DFTB+ runs it by default (getNextInputCharges,
+    dftbplus/main.F90:4890-4935): the charges are reduced to one value per atom (non-orbital-resolved
+    SCC: all orbitals of an atom are equivalent, reduceCharges), the error is max |qOutRed - qInpRed|,
+    the reduced charges go through the modified Broyden mixer with the parser's defaults
+    (oracle/scc_model.py, pinned to the reference's unit test), and the fillings come from the
+    restated Efilling at the reference's default electronic temperature (0 K -> minTemp)."""
     species0 = np.asarray(workload["species0"])
     n_atom = geo["nAtom"]
     hubb = [sk.hubbU[s][0] for s in range(len(sk.hubbU))]
     gamma = short_gamma(np.asarray(workload["coord0"], dtype=float), species0, hubb)
     q0 = np.zeros((n_atom, m_orb))
+    n_orb_atom = np.zeros(n_atom, dtype=int)
     for i, s in enumerate(species0):           # reference (neutral atom) orbital populations
         k = 0
         for l, occ in zip(sk.ang_shells[s - 1], sk.occ[s - 1]):
             q0[i, k:k + 2 * l + 1] = occ / (2 * l + 1)
             k += 2 * l + 1
+        n_orb_atom[i] = k
     n_elec = q0.sum()
+    if kT is None:
+        kT = scc_model.MIN_TEMP if reference_defaults else 0.001
+
+    def fill(eig):
+        if reference_defaults:
+            return scc_model.fillings_and_band_energies(np.asarray(eig), n_elec, kT)["filling"][:, 0, 0]
+        return fermi(np.asarray(eig), n_elec, kT)
+
+    def expand(q_red):
+        # expandCharges for atom-wise equivalence: the atom's charge spread evenly over its orbitals
+        q = np.zeros((n_atom, m_orb))
+        for i in range(n_atom):
+            q[i, :n_orb_atom[i]] = q_red[i] / n_orb_atom[i]
+        return q
+
+    mixer = scc_model.BroydenMixer(max_scc_iter=max(max_iter, 2)) if reference_defaults else None
+    if mixer is not None:
+        mixer.reset(n_atom)
     h0, over = arm.build()
     q_in = q0.copy() if q_init is None else np.array(q_init, dtype=float, copy=True)
+    q_in_red = q_in.sum(axis=1)
     for it in range(1, max_iter + 1):
         dq = (q_in - q0).sum(axis=1)
         shift_atom = gamma @ dq
         ham = arm.add_shift(h0, over, shift_atom)
         eig, C = arm.solve(ham, over)
-        f = fermi(np.asarray(eig), n_elec)
+        f = fill(eig)
         rho = arm.rho(C, f)
         q_out = arm.mulliken(over, rho)
-        err = np.abs(q_out - q_in).max()
-        if err < tol:
-            break
-        q_in = q_in + mix * (q_out - q_in)
+        if reference_defaults:
+            q_diff_red = q_out.sum(axis=1) - q_in_red
+            err = np.abs(q_diff_red).max()
+            if err < tol:
+                break
+            mixer.mix(q_in_red, q_diff_red)
+            q_in = expand(q_in_red)
+        else:
+            err = np.abs(q_out - q_in).max()
+            if err < tol:
+                break
+            q_in = q_in + mix * (q_out - q_in)
     dq = (q_out - q0).sum(axis=1)
     e_h0 = arm.mulliken(h0, rho).sum()                     # Tr[rho H0], getenergies.F90:198
     e_scc = 0.5 * dq @ gamma @ dq

@@ -40,6 +40,43 @@ def test_oracle_scc_converges_and_is_variational():
     assert r["e_scc"] > 0.0
 
 
+def test_oracle_scc_reference_defaults_converge():
+    """CPU: the same single point with the reference's default SCC machinery (Broyden mixer on the
+    atom charges, Efilling at minTemp; oracle/scc_model.py) reaches the same fixed point as the
+    simple-mixing loop, in far fewer iterations."""
+    w, sk, geo, model, selfegy = _setup("h2o")
+    arm = sh.OracleArm(oracle, model, geo, selfegy)
+    slow = sh.scc_single_point(arm, w, sk, geo, model.mOrb, mix=MIX["h2o"], kT=1e-8, tol=1e-10, max_iter=400)
+    fast = sh.scc_single_point(arm, w, sk, geo, model.mOrb, reference_defaults=True, tol=1e-10)
+    assert fast["err"] < 1e-10 and fast["n_iter"] < slow["n_iter"] and fast["n_iter"] <= 20
+    assert abs(fast["energy"] - slow["energy"]) < 1e-9
+    assert np.abs(fast["q"].sum(axis=1) - slow["q"].sum(axis=1)).max() < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["h2o", "watercluster24", "ce_o"])
+def test_scc_reference_defaults_device_vs_oracle(name):
+    """The SCC loop with the reference's defaults (Broyden, Efilling; see scc_harness): identical
+    iteration counts, energy 1e-8 Ha, forces 1e-7 Ha/bohr between the oracle arm and the device arm."""
+    from dftbplus_b200.api import HotPath
+    w, sk, geo, model, selfegy = _setup(name)
+    ref = sh.scc_single_point(sh.OracleArm(oracle, model, geo, selfegy), w, sk, geo, model.mOrb,
+                              reference_defaults=True, tol=1e-9, max_iter=100)
+    hp = HotPath(0)
+    try:
+        sk.upload(hp)
+        hp.set_geometry(geo)
+        got = sh.scc_single_point(sh.DeviceArm(hp, sk, geo), w, sk, geo, model.mOrb, reference_defaults=True,
+                                  tol=1e-9, max_iter=100)
+    finally:
+        hp.close()
+    assert ref["err"] < 1e-9, "oracle arm did not converge"
+    assert got["n_iter"] == ref["n_iter"], (got["n_iter"], ref["n_iter"])
+    assert abs(got["energy"] - ref["energy"]) < TOL_ENERGY, (got["energy"], ref["energy"])
+    assert np.abs(got["q"] - ref["q"]).max() < 1e-9
+    assert np.abs(got["forces"] - ref["forces"]).max() < TOL_FORCE
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["h2o", "watercluster24", "ce_o"])
 def test_scc_single_point_device_vs_oracle(name):
