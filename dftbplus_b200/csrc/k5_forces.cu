@@ -104,11 +104,9 @@ __global__ void __launch_bounds__(256) k5_shift_structure(const double *__restri
 // elements -- the form the partition of the force call needs (dftbp_b200_set_pair_partition: a call
 // only touches the chunks part, part + nParts, ... and only their blocks get weights).
 template <int NSPIN, bool FULL>
-__global__ void __launch_bounds__(256) k5_force_weights_sched(const K5Params p, const double *__restrict__ EDM,
-                                                              const double *__restrict__ shift,
-                                                              const int *__restrict__ shiftFull,
-                                                              double *__restrict__ negWS, int selfImages) {
-  if ((__ldg(shiftFull) != 0) != FULL) return;  // the other instantiation handles this shift structure
+__device__ __forceinline__ void forceWeightsSched(const K5Params &p, const double *__restrict__ EDM,
+                                                  const double *__restrict__ shift, double *__restrict__ negWS,
+                                                  int selfImages) {
   const int lane = threadIdx.x & 31, wIn = threadIdx.x >> 5, nW = blockDim.x >> 5;
   const int nChunks = __ldg(p.total) >> 5;
   const int mo2 = p.mOrb * p.mOrb, dstep = p.mOrb + 1;
@@ -192,6 +190,15 @@ __global__ void __launch_bounds__(256) k5_force_weights_sched(const K5Params p, 
   }
 }
 
+template <int NSPIN, bool FULL>
+__global__ void __launch_bounds__(256) k5_force_weights_sched(const K5Params p, const double *__restrict__ EDM,
+                                                              const double *__restrict__ shift,
+                                                              const int *__restrict__ shiftFull,
+                                                              double *__restrict__ negWS, int selfImages) {
+  if ((__ldg(shiftFull) != 0) != FULL) return;  // the other instantiation handles this shift structure
+  forceWeightsSched<NSPIN, FULL>(p, EDM, shift, negWS, selfImages);
+}
+
 // Diagonal shift blocks, the blocks visited in the order of the sparse arrays instead of along the
 // schedule: reads and writes of consecutive blocks are then neighbours in memory (measured on
 // fec4096: 75 us against 88 us for k5_force_weights_sched<2, false>, whose 648-byte pieces are
@@ -250,8 +257,11 @@ __global__ void __launch_bounds__(32 * flat::warpsFor(1 + NSPIN), 1)
     k5_force_weights_flat(const K5Params p, const BlockDesc *__restrict__ desc, long long nWork,
                           const int *__restrict__ groupFirst, const double *__restrict__ EDM,
                           const double *__restrict__ diag, const int *__restrict__ shiftFull,
-                          double *__restrict__ negWS) {
-  if (__ldg(shiftFull) != 0) return;  // full blocks: k5_force_weights_sched<1, true>
+                          double *__restrict__ negWS, const double *__restrict__ shift, int selfImages) {
+  if (__ldg(shiftFull) != 0) {  // full shift blocks (DFTB+U-like): per-pair matrix products along the schedule
+    forceWeightsSched<1, true>(p, EDM, shift, negWS, selfImages);
+    return;
+  }
   constexpr int NIN = 1 + NSPIN, WARPS = flat::warpsFor(NIN);
   extern __shared__ __align__(128) unsigned char flatRaw[];
   flat::Smem<NIN, WARPS> &sm = *reinterpret_cast<flat::Smem<NIN, WARPS> *>(flatRaw);
@@ -566,7 +576,8 @@ namespace {
 
 template <int NSPIN>
 int launchWeightsFlatT(dftbp_b200_ctx *ctx, const K5Params &p, const BlockDesc *desc, long long nWork,
-                       const int *groupFirst, const double *EDM, const double *diag, const int *flag, double *negWS) {
+                       const int *groupFirst, const double *EDM, const double *diag, const int *flag, double *negWS,
+                       const double *shift, int selfImages) {
   constexpr int NIN = 1 + NSPIN, WARPS = flat::warpsFor(NIN);
   const size_t smemBytes = sizeof(flat::Smem<NIN, WARPS>);
   static LaunchInfo info;
@@ -574,15 +585,16 @@ int launchWeightsFlatT(dftbp_b200_ctx *ctx, const K5Params &p, const BlockDesc *
   const long long nSpans = ((long long)p.sparseSize + flat::kSpan - 1) / flat::kSpan;
   const int grid = (int)std::max<long long>(1, std::min<long long>((nSpans + WARPS - 1) / WARPS, ctx->smCount));
   k5_force_weights_flat<NSPIN><<<grid, 32 * WARPS, smemBytes, ctx->stream>>>(p, desc, nWork, groupFirst, EDM, diag, flag,
-                                                                            negWS);
+                                                                            negWS, shift, selfImages);
   return 0;
 }
 
 int launchWeightsFlat(dftbp_b200_ctx *ctx, int nSpin, const K5Params &p, const BlockDesc *desc, long long nWork,
-                      const int *groupFirst, const double *EDM, const double *diag, const int *flag, double *negWS) {
-  if (nSpin == 1) return launchWeightsFlatT<1>(ctx, p, desc, nWork, groupFirst, EDM, diag, flag, negWS);
-  if (nSpin == 2) return launchWeightsFlatT<2>(ctx, p, desc, nWork, groupFirst, EDM, diag, flag, negWS);
-  return launchWeightsFlatT<4>(ctx, p, desc, nWork, groupFirst, EDM, diag, flag, negWS);
+                      const int *groupFirst, const double *EDM, const double *diag, const int *flag, double *negWS,
+                      const double *shift, int selfImages) {
+  if (nSpin == 1) return launchWeightsFlatT<1>(ctx, p, desc, nWork, groupFirst, EDM, diag, flag, negWS, shift, selfImages);
+  if (nSpin == 2) return launchWeightsFlatT<2>(ctx, p, desc, nWork, groupFirst, EDM, diag, flag, negWS, shift, selfImages);
+  return launchWeightsFlatT<4>(ctx, p, desc, nWork, groupFirst, EDM, diag, flag, negWS, shift, selfImages);
 }
 
 // derivative_shift (deriv != nullptr) and / or the stress tensor (st != nullptr) from one pass over the pairs
@@ -648,13 +660,18 @@ int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, c
       const bool useFlat = p.nParts == 1 && g.groupFirstLoad != nullptr && (long long)ctx->mOrb * g.nAtom * nSpin < (1LL << 31) &&
                            tuneInt("DFTBP_B200_K5_FLAT", 1) != 0;
       if (useFlat) {
-        DFTBP_TRY(launchWeightsFlat(ctx, nSpin, p, g.descLoad, g.nWorkLoad, g.groupFirstLoad, dEDM, dDiag, flag, (double *)scratch));
-      } else if (nSpin == 1) k5_force_weights_diag<1><<<dGrid, 256, 0, ctx->stream>>>(p, g.descLoad, sched->slotOf, g.nWorkLoad, dEDM, dShift, flag, (double *)scratch, self);
-      else if (nSpin == 2) k5_force_weights_diag<2><<<dGrid, 256, 0, ctx->stream>>>(p, g.descLoad, sched->slotOf, g.nWorkLoad, dEDM, dShift, flag, (double *)scratch, self);
-      else k5_force_weights_diag<4><<<dGrid, 256, 0, ctx->stream>>>(p, g.descLoad, sched->slotOf, g.nWorkLoad, dEDM, dShift, flag, (double *)scratch, self);
-      k5_force_weights_sched<1, true><<<wGrid, 256, 0, ctx->stream>>>(p, dEDM, dShift, flag, (double *)scratch, self);
+        // one launch: the kernel takes the full-block path itself when the device flag says so
+        DFTBP_TRY(launchWeightsFlat(ctx, nSpin, p, g.descLoad, g.nWorkLoad, g.groupFirstLoad, dEDM, dDiag, flag, (double *)scratch,
+                                    dShift, self));
+        ctx->launches += 2;
+      } else {
+        if (nSpin == 1) k5_force_weights_diag<1><<<dGrid, 256, 0, ctx->stream>>>(p, g.descLoad, sched->slotOf, g.nWorkLoad, dEDM, dShift, flag, (double *)scratch, self);
+        else if (nSpin == 2) k5_force_weights_diag<2><<<dGrid, 256, 0, ctx->stream>>>(p, g.descLoad, sched->slotOf, g.nWorkLoad, dEDM, dShift, flag, (double *)scratch, self);
+        else k5_force_weights_diag<4><<<dGrid, 256, 0, ctx->stream>>>(p, g.descLoad, sched->slotOf, g.nWorkLoad, dEDM, dShift, flag, (double *)scratch, self);
+        k5_force_weights_sched<1, true><<<wGrid, 256, 0, ctx->stream>>>(p, dEDM, dShift, flag, (double *)scratch, self);
+        ctx->launches += 3;
+      }
       p.negWS = (const double *)scratch;
-      ctx->launches += 3;
     }
     p.pitch = (ctx->mOrb * ctx->mOrb) | 1;
     const size_t perWarp = sizeof(double) * 32 * (size_t)p.pitch;

@@ -53,9 +53,7 @@ __global__ void __launch_bounds__(256) k6_shift_structure(const double *__restri
 // ZERO: isInputZero -- ham is written, not accumulated: no read of ham and (on one rank, where the
 // work list covers every block) no zero fill either.
 template <int MODE, int NSPIN, bool ZERO>
-__global__ void __launch_bounds__(256) k6_add_shift(const K6Params p) {
-  if (MODE == 1 && __ldg(p.shiftFull) != 0) return;  // the MODE 2 launch handles it
-  if (MODE == 2 && __ldg(p.shiftFull) == 0) return;
+__device__ __forceinline__ void addShiftBlocks(const K6Params &p) {
   const int lane = threadIdx.x & 31;
   const int mo2 = p.mOrb * p.mOrb, dstep = p.mOrb + 1;
   forEachBlock(
@@ -106,13 +104,23 @@ __global__ void __launch_bounds__(256) k6_add_shift(const K6Params p) {
       [] {});
 }
 
+template <int MODE, int NSPIN, bool ZERO>
+__global__ void __launch_bounds__(256) k6_add_shift(const K6Params p) {
+  if (MODE == 1 && __ldg(p.shiftFull) != 0) return;  // the MODE 2 launch handles it
+  if (MODE == 2 && __ldg(p.shiftFull) == 0) return;
+  addShiftBlocks<MODE, NSPIN, ZERO>(p);
+}
+
 // Atom shifts and diagonal block shifts through the span pipeline of flat_stream.cuh: `over` (and,
 // when accumulating, the NSPIN channels of `ham`) arrive by TMA bulk copies; lanes on consecutive
 // elements of the sparse arrays whatever block they belong to.
 template <int MODE, int NSPIN, bool ZERO>
 __global__ void __launch_bounds__(32 * flat::warpsFor(ZERO ? 1 : 1 + NSPIN), 1)
     k6_add_shift_flat(const K6Params p, const int *__restrict__ groupFirst) {
-  if (MODE == 1 && __ldg(p.shiftFull) != 0) return;  // the MODE 2 launch handles it
+  if (MODE == 1 && __ldg(p.shiftFull) != 0) {  // full shift blocks: per-block matrix products, warp per block
+    addShiftBlocks<2, NSPIN, ZERO>(p);
+    return;
+  }
   constexpr int NIN = ZERO ? 1 : 1 + NSPIN, WARPS = flat::warpsFor(NIN);
   extern __shared__ __align__(128) unsigned char flatRaw[];
   flat::Smem<NIN, WARPS> &sm = *reinterpret_cast<flat::Smem<NIN, WARPS> *>(flatRaw);
@@ -237,10 +245,16 @@ int addShiftImpl(dftbp_b200_ctx *ctx, double *ham, const double *over, const dou
       k6_shift_structure<<<std::min(ctx->smCount * 8, (g.nAtom * nSpin + 7) / 8), 256, 0, ctx->stream>>>(
           p.shift, ctx->mOrb, g.nAtom * nSpin, flag, dDiag);
       // both forms are launched; the one that does not match the device flag returns at once
-      if (useFlat) DFTBP_TRY(launchFlat<1>(ctx, p, isInputZero != 0, groupFirst));
-      else launchMode<1>(p, isInputZero != 0, grid, ctx->stream);
-      launchMode<2>(p, isInputZero != 0, grid, ctx->stream);
-      ctx->launches += 3;
+      if (useFlat) {
+        // one launch: the kernel takes the full-block path itself when the device flag says so
+        DFTBP_TRY(launchFlat<1>(ctx, p, isInputZero != 0, groupFirst));
+        ctx->launches += 2;
+      } else {
+        // both forms are launched; the one that does not match the device flag returns at once
+        launchMode<1>(p, isInputZero != 0, grid, ctx->stream);
+        launchMode<2>(p, isInputZero != 0, grid, ctx->stream);
+        ctx->launches += 3;
+      }
     }
   }
   return finish(ctx);

@@ -5,8 +5,8 @@
 // ordered species pair -- the shell loops and the generated rotation code are then warp-uniform --
 // and (b) sit at neighbouring distances, so that the 8-row windows of the SK tables they
 // interpolate from fall into the same one or two cache lines (broadcast loads instead of gathers).
-// A counting sort by key = (species pair, distance bin) gives both; it runs on the device in three
-// small launches (histogram, single-CTA scan with per-bucket padding to a multiple of 32, scatter;
+// A counting sort by key = (species pair, distance bin) gives both; it runs on the device in two
+// small launches (histogram, whose last CTA scans it with per-bucket padding to a multiple of 32; scatter;
 // histogram and scatter aggregate in shared memory, one global atomic per CTA and occupied bin)
 // and is redone whenever the coordinates change.  The order inside a bin is arbitrary (atomic
 // cursors): every pair is evaluated independently and written to its own iPair offset, so the
@@ -49,49 +49,18 @@ __device__ __forceinline__ int pairKey(int flat, int ld, int nSpecies, int nBins
   return (sp1 + nSpecies * sp2) * nBins + bin;
 }
 
-// pass 1: key of every work item + histogram.  Each CTA owns a contiguous slab of the work list and
-// counts in shared memory first, so only one global atomic per (CTA, occupied bin) remains --
-// crystalline systems put thousands of pairs into the same few bins.
-__global__ void __launch_bounds__(kSortThreads) ps_keys(const int *__restrict__ work, long long nWork, int ld,
-                                                        int nSpecies, int nBins, int nKeys,
-                                                        const double *__restrict__ coords,
-                                                        const int *__restrict__ species,
-                                                        const int *__restrict__ iNeighbour,
-                                                        const int *__restrict__ iPair, double binScale,
-                                                        int *__restrict__ keys, int *__restrict__ hist,
-                                                        PairRec *__restrict__ recsMem) {
-  extern __shared__ int sh[];
-  for (int k = threadIdx.x; k < nKeys; k += kSortThreads) sh[k] = 0;
-  __syncthreads();
-  const long long per = (nWork + gridDim.x - 1) / gridDim.x;
-  const long long lo = per * blockIdx.x, hi = min(nWork, lo + per);
-  for (long long i = lo + threadIdx.x; i < hi; i += kSortThreads) {
-    PairRec r;
-    const int key = pairKey(__ldg(work + i), ld, nSpecies, nBins, binScale, coords, species, iNeighbour, iPair, r);
-    keys[i] = key;
-    recsMem[i] = r;  // the same record in the order of the work list (= the order of the sparse arrays)
-    if (key >= 0) atomicAdd(sh + key, 1);
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < nKeys; k += kSortThreads) {
-    const int c = sh[k];
-    if (c) atomicAdd(hist + k, c);
-  }
-}
-
 // one CTA: exclusive scan bucket by bucket (nBins entries each), every bucket starts on a multiple of 32
 // The padding slots behind every bucket get ind = -1 / item = -1 here (at most 31 per bucket), so the
-// schedule arrays need no fill pass.
-__global__ void __launch_bounds__(1024) ps_scan(int *__restrict__ hist, int nBuckets, int nBins,
-                                                int *__restrict__ total, int *__restrict__ items,
-                                                PairRec *__restrict__ recs) {
-  __shared__ int warpSum[32];
-  __shared__ int baseSh;
+// schedule arrays need no fill pass.  Runs in the last CTA of ps_keys to finish (ticket counter): the
+// histogram is complete then, and a launch of its own would cost more than the scan.
+__device__ __forceinline__ void scanBuckets(int *__restrict__ hist, int nBuckets, int nBins, int *__restrict__ total,
+                                            int *__restrict__ items, PairRec *__restrict__ recs, int *warpSum,
+                                            int *baseSh) {
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  if (t == 0) baseSh = 0;
+  if (t == 0) *baseSh = 0;
   __syncthreads();
   for (int b = 0; b < nBuckets; ++b) {
-    const int v = t < nBins ? hist[b * nBins + t] : 0;
+    const int v = t < nBins ? __ldcg(hist + b * nBins + t) : 0;
     int x = v;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -110,7 +79,7 @@ __global__ void __launch_bounds__(1024) ps_scan(int *__restrict__ hist, int nBuc
       warpSum[lane] = s;  // inclusive sums of the warps
     }
     __syncthreads();
-    const int base = baseSh;
+    const int base = *baseSh;
     const int incl = x + (w > 0 ? warpSum[w - 1] : 0);
     if (t < nBins) hist[b * nBins + t] = base + incl - v;
     __syncthreads();
@@ -119,10 +88,53 @@ __global__ void __launch_bounds__(1024) ps_scan(int *__restrict__ hist, int nBuc
       items[endB + t] = -1;
       recs[endB + t].ind = -1;
     }
-    if (t == 1023) baseSh = (base + incl + 31) & ~31;
+    if (t == 1023) *baseSh = (base + incl + 31) & ~31;
     __syncthreads();
   }
-  if (t == 0) *total = baseSh;
+  if (t == 0) *total = *baseSh;
+}
+
+// pass 1: key of every work item + histogram.  Each CTA owns a contiguous slab of the work list and
+// counts in shared memory first, so only one global atomic per (CTA, occupied bin) remains --
+// crystalline systems put thousands of pairs into the same few bins.
+__global__ void __launch_bounds__(kSortThreads) ps_keys(const int *__restrict__ work, long long nWork, int ld,
+                                                        int nSpecies, int nBins, int nKeys,
+                                                        const double *__restrict__ coords,
+                                                        const int *__restrict__ species,
+                                                        const int *__restrict__ iNeighbour,
+                                                        const int *__restrict__ iPair, double binScale,
+                                                        int *__restrict__ keys, int *__restrict__ hist,
+                                                        PairRec *__restrict__ recsMem, int *__restrict__ ticket,
+                                                        int nBuckets, int *__restrict__ total,
+                                                        int *__restrict__ items, PairRec *__restrict__ recs) {
+  extern __shared__ int sh[];
+  __shared__ int warpSum[32];
+  __shared__ int baseSh, lastSh;
+  for (int k = threadIdx.x; k < nKeys; k += kSortThreads) sh[k] = 0;
+  __syncthreads();
+  const long long per = (nWork + gridDim.x - 1) / gridDim.x;
+  const long long lo = per * blockIdx.x, hi = min(nWork, lo + per);
+  for (long long i = lo + threadIdx.x; i < hi; i += kSortThreads) {
+    PairRec r;
+    const int key = pairKey(__ldg(work + i), ld, nSpecies, nBins, binScale, coords, species, iNeighbour, iPair, r);
+    keys[i] = key;
+    recsMem[i] = r;  // the same record in the order of the work list (= the order of the sparse arrays)
+    if (key >= 0) atomicAdd(sh + key, 1);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nKeys; k += kSortThreads) {
+    const int c = sh[k];
+    if (c) atomicAdd(hist + k, c);
+  }
+  // the last CTA to get here scans the complete histogram
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) lastSh = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!lastSh) return;
+  __threadfence();
+  scanBuckets(hist, nBuckets, nBins, total, items, recs, warpSum, &baseSh);
+  if (threadIdx.x == 0) *ticket = 0;  // ready for the next sort
 }
 
 // pass 2: every CTA counts its slab again (from the stored keys), reserves one contiguous range
@@ -236,25 +248,26 @@ int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out
   DFTBP_TRY(growTo(ctx, &sp.recsMem, &sp.recsMemCap, std::max(nWork, 1LL)));
   DFTBP_TRY(growTo(ctx, &sp.slotOf, &sp.slotOfCap, std::max(nWork, 1LL)));
   DFTBP_TRY(growTo(ctx, &ctx->sortKeys, &ctx->sortKeysCap, std::max(nWork, 1LL)));
-  DFTBP_TRY(growTo(ctx, &ctx->sortBins, &ctx->sortBinsCap, nBins64));
-  DFTBP_CUDA(ctx, cudaMemsetAsync(ctx->sortBins, 0, sizeof(int) * nBins64, ctx->stream));
+  DFTBP_TRY(growTo(ctx, &ctx->sortBins, &ctx->sortBinsCap, nBins64 + 1));  // + the ticket of ps_keys
+  DFTBP_CUDA(ctx, cudaMemsetAsync(ctx->sortBins, 0, sizeof(int) * (nBins64 + 1), ctx->stream));
   // padding slots (item = -1, ind = -1: the consumers then shadow lane 0 of the chunk) are written by ps_scan
   const double binScale = (double)nBins / (ctx->cutoff > 0.0 ? ctx->cutoff : 1.0);
   if (nWork > 0) {
-    // slabs of at least 2048 items per CTA (aggregation), at most one CTA per SM
-    const int grid = (int)std::max<long long>(1, std::min<long long>(ctx->smCount, (nWork + 2047) / 2048));
+    // slabs of at least 512 items per CTA (aggregation in shared memory), at most one CTA per SM: the
+    // kernels are chains of dependent loads, so all SMs should share them
+    const int grid = (int)std::max<long long>(1, std::min<long long>(ctx->smCount, (nWork + 511) / 512));
     const size_t smemBytes = sizeof(int) * (size_t)nKeys;
     static LaunchInfo infoKeys, infoScatter;
     DFTBP_TRY(launchInfo(ctx, infoKeys, ps_keys, kSortThreads, smemBytes, nullptr));
     DFTBP_TRY(launchInfo(ctx, infoScatter, ps_scatter, kSortThreads, smemBytes, nullptr));
     ps_keys<<<grid, kSortThreads, smemBytes, ctx->stream>>>(work, nWork, g.mNeigh + 1, ctx->nSpecies, nBins, nKeys,
                                                            g.coords, g.species, g.iNeighbour, g.iPair, binScale,
-                                                           ctx->sortKeys, ctx->sortBins, sp.recsMem);
-    ps_scan<<<1, 1024, 0, ctx->stream>>>(ctx->sortBins, nBuckets, nBins, sp.total, sp.items, sp.recs);
+                                                           ctx->sortKeys, ctx->sortBins, sp.recsMem,
+                                                           ctx->sortBins + nBins64, nBuckets, sp.total, sp.items, sp.recs);
     ps_scatter<<<grid, kSortThreads, smemBytes, ctx->stream>>>(work, nWork, nKeys, ctx->sortKeys, ctx->sortBins,
                                                               sp.items, sp.recs, sp.atoms, g.mNeigh + 1, sp.recsMem,
                                                               g.iNeighbour, g.img2CentCell, sp.slotOf);
-    ctx->launches += 3;
+    ctx->launches += 2;
   } else {
     DFTBP_CUDA(ctx, cudaMemsetAsync(sp.total, 0, sizeof(int), ctx->stream));
   }
