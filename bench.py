@@ -630,8 +630,23 @@ def main():
         hp.derivative_shift(dm, edm, shift=shift, deriv=deriv)
     stream.synchronize()
     clocks = sampler.stop()
-    k1_ms = t["sparseH0S"][0] / max(1, t["sparseH0S"][1])
+    k1_ms_in_step = t["sparseH0S"][0] / max(1, t["sparseH0S"][1])
     k5_ms = t["forceCalc"][0] / max(1, t["forceCalc"][1])
+    # The pair build on its own: K launches back to back on the launch stream, one event pair around all
+    # of them -- the GPU, not the host's launch rate or the event pair around a single short call, sets
+    # the time (the library timer above brackets ONE call of two kernels with events and sees the idle
+    # gap between them when the host is the slower side).  Each call writes 130 MB (> L2) afresh.
+    hp.timer_enable(False)
+    reps_k1 = max(20, a.steps)
+    for _ in range(3):
+        hp.buildH0S(sk.selfegy, ham, over)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps_k1):
+        hp.buildH0S(sk.selfegy, ham, over)
+    e1.record(stream)
+    e1.synchronize()
+    k1_ms = e0.elapsed_time(e1) / reps_k1
     hbm_peak, peak_src = peaks()
     k1_bytes = algorithmic_bytes_k1(geo)
     tr = ncu_traffic("k1_rotate_store")
@@ -641,7 +656,41 @@ def main():
                 "traffic": (tr or {}).get("bytes_per_launch"), "traffic_source": (tr or {}).get("source"),
                 "traffic_note": "k1_rotate_store alone (the kernel that writes H0 and S)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
-                "ms_per_launch": k1_ms, "l2": "as in config.l2"}
+                "ms_per_launch": k1_ms, "launches_timed": reps_k1,
+                "timing": "CUDA events around %d back-to-back calls on the launch stream (two kernels per call); "
+                          "every call rewrites 130 MB, more than the L2 holds" % reps_k1,
+                "ms_inside_step_library_timer": k1_ms_in_step}
+    # what plain element-wise kernels reach on arrays of THIS size (65 MB each): torch kernels with the same
+    # read : write mix as the streaming kernels of the path, L2 flushed before each -- the practical ceiling
+    # next to the 2 GB copy peak of MEASURED_PEAKS.json (short kernels pay ramp-up and tail)
+    stream_mix = None
+    if True:
+        with torch.cuda.stream(stream):
+            ta, tb, tc = torch.randn(ss, **f64), torch.randn(ss, **f64), torch.randn(ss, **f64)
+            to, to2 = torch.empty(ss, **f64), torch.empty((2, ss), **f64)
+
+            def timed(fn, reps=10):
+                for _ in range(2):
+                    fn()
+                tot = 0.0
+                for _ in range(reps):
+                    flush.zero_()
+                    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    x0.record(stream)
+                    fn()
+                    x1.record(stream)
+                    x1.synchronize()
+                    tot += x0.elapsed_time(x1)
+                return tot / reps
+            t31 = timed(lambda: torch.addcmul(ta, tb, tc, out=to))
+            t11 = timed(lambda: to.copy_(ta))
+            t12 = timed(lambda: torch.mul(ta.unsqueeze(0).expand(2, ss), 0.5, out=to2))
+            t20 = timed(lambda: torch.dot(ta, tb))
+            stream_mix = {"elements": ss,
+                          "read3_write1_GBs": 32.0 * ss / t31 / 1e6, "read1_write1_GBs": 16.0 * ss / t11 / 1e6,
+                          "read1_write2_GBs": 24.0 * ss / t12 / 1e6, "read2_GBs": 16.0 * ss / t20 / 1e6,
+                          "note": "torch.addcmul / copy_ / broadcast mul / dot on float64 arrays of sparseSize elements"}
+            del ta, tb, tc, to, to2
     kernels = {"sparseH0S": {"ms": k1_ms, "pairs_per_s": pairs / k1_ms * 1e3},
                "forceCalc": {"ms": k5_ms, "pairs_per_s_this_rank": pairs / world / k5_ms * 1e3,
                              "shift": "diagonal blocks (collinear-spin SCC)"}}
@@ -892,10 +941,15 @@ def main():
             "densityMatrix": {"ms": dm_ms, "TFLOPs": roofline_dm["achieved"] if roofline_dm else None},
         })
         if per.get("addShift"):
-            kernels["addShift"] = {"ms": per["addShift"], "GBs": gbs(8.0 * ss * (1 + 2 * n_spin), per["addShift"])}
+            # isInputZero: over read once, ham written per spin (not read)
+            kernels["addShift"] = {"ms": per["addShift"], "GBs": gbs(8.0 * ss * (1 + n_spin), per["addShift"]),
+                                   "bytes": "8 * sparseSize * (1 + nSpin), isInputZero"}
         mk = t["mulliken"]
         if mk[1]:
             kernels["mulliken"] = {"ms": mk[0] / mk[1], "GBs": 16.0 * ss / (mk[0] / mk[1]) / 1e6}
+        for kname in ("sparseToDense", "denseToSparse", "addShift", "mulliken"):
+            if kernels.get(kname, {}).get("GBs"):
+                kernels[kname]["frac_of_copy_peak"] = kernels[kname]["GBs"] / hbm_peak
         scc = {"ms_without_eigensolve": scc_ms, "ks_pairs_this_rank": len(my_ks), "gpus_per_ks_pair": group_size,
                "dm_panel_this_rank": list(my_panel) if my_panel is not None else None, "n_spin": n_spin, "nOrb": nOrb,
                "eigensolve_ms": None, "cublas_dgemm_tflops": dgemm_tflops,
@@ -983,7 +1037,8 @@ def main():
                 "parallelism": "one context per GPU: pair build replicated, force chunks dealt out round-robin + all-reduce of deriv, "
                                "(k,spin) round-robin, density-matrix column panels beyond",
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-                "roofline_k5": roofline_k5, "roofline_dm": roofline_dm, "kernels": kernels, "scc_step": scc,
+                "roofline_k5": roofline_k5, "roofline_dm": roofline_dm, "kernels": kernels, "stream_mix_same_size": stream_mix,
+                "scc_step": scc,
                 "kpoints_si512": kp_sec, "md_water2046": md_sec, "multi_gpu": multi, "cpu_baseline": cpu,
                 "neighbour_list": n2}
         print(json.dumps(line), flush=True)
