@@ -44,6 +44,7 @@ struct K1Params {
   const PairRec *recsMem;  // records in work-list order, on-site blocks included
   double *exch;            // exchange rows, one per work-list entry
   int nWork, imgCap, bulkOK;
+  int dbgSkip;  // timing experiments on k1_interp: 1 = no window copies, 2 = no interpolation, 4 = no row stores
 };
 
 // ---- round 2: compact evaluator -------------------------------------------------------------------
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(128) k1_interp(const K1Params p) {
       nRows[mat] = hi >= 0 ? hi - lo + 8 : 0;
       inSmem = inSmem && nRows[mat] <= kWinRows && nInteg <= NI;
     }
-    if (inSmem) {
+    if (inSmem && !(p.dbgSkip & 1)) {
 #pragma unroll
       for (int mat = 0; mat < 2; ++mat) {
         if ((mat ? p.over : p.ham) == nullptr) continue;
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(128) k1_interp(const K1Params p) {
       __syncwarp();
     }
     for (int mat = 0; mat < 2; ++mat) {
-      if ((mat ? p.over : p.ham) == nullptr) continue;
+      if ((mat ? p.over : p.ham) == nullptr || (p.dbgSkip & 2)) continue;
       const SkTableDev &t = mat ? pg.S : pg.H;
       const LaneInterp &li = mat ? liS : liH;
       double *__restrict__ dst = mine + mat * VH;
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(128) k1_interp(const K1Params p) {
 #pragma unroll 4
     for (int q = 0; q < 32; ++q) {
       const int row = __shfl_sync(0xffffffffu, slot, q);
-      if (row >= 0 && lane < VROW) p.exch[(size_t)row * VROW + lane] = stage[q * PITCH + lane];
+      if (row >= 0 && lane < VROW && !(p.dbgSkip & 4)) p.exch[(size_t)row * VROW + lane] = stage[q * PITCH + lane];
     }
     __syncwarp();
   }
@@ -492,6 +493,7 @@ int launchTwoKernel(dftbp_b200_ctx *ctx, K1Params p, long long chunks) {
   p.exch = ctx->pairExchange;
   p.nWork = (int)g.nWorkMine;
   p.imgCap = 32 * ctx->mOrb * ctx->mOrb + 2;
+  p.dbgSkip = tuneInt("DFTBP_B200_K1I_SKIP", 0);
   const int only = tuneInt("DFTBP_B200_K1_ONLY", 0);  // timing experiment: 1 = interpolation kernel only, 2 = rotation only
   if (only != 2) {
     const int grid = (int)std::max<long long>(1, std::min<long long>((chunks + 3) / 4, (long long)ctx->smCount * 16));
