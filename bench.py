@@ -542,15 +542,21 @@ def main():
         flush = torch.empty(256 * 1024 * 1024 // 8, **f64)          # > 126 MB L2
     stream.synchronize()
 
-    def step_device():
+    def step_local():
         # a new geometry every step: the coordinates are refreshed, so the device-side pair
-        # schedule (pair_sort.cu: histogram, scan, scatter) is rebuilt inside the timed region
+        # schedule (pair_sort.cu: histogram + scan, scatter) is rebuilt inside the timed region
         hp.update_coords(coords_dev)
         hp.buildH0S(sk.selfegy, ham, over)                               # K1 (all pairs)
         hp.derivative_shift(dm, edm, shift=shift, deriv=deriv)           # K5 (this rank's chunks)
+
+    def reduce_deriv():
         if world > 1:
             with torch.cuda.stream(stream):
                 dist.all_reduce(deriv)                                   # assembleChunks(env, deriv)
+
+    def step_device():
+        step_local()
+        reduce_deriv()
 
     # ---- value: device-resident, CUDA events on the launch stream -------------------------------
     sampler = ClockSampler(local)
@@ -579,19 +585,24 @@ def main():
     # replay the graph with new coordinates in coords_dev.  Falls back to the eager number.
     ms_dev, graph_note = ms_eager, "eager launches"
     graph_ok = 0
-    if world == 1:      # (with several ranks the step contains an NCCL all-reduce: left to eager launches)
+    if True:
         try:
             graph = torch.cuda.CUDAGraph()
             stream.synchronize()
             with torch.cuda.graph(graph, stream=stream, capture_error_mode="thread_local"):
-                step_device()
+                step_local()            # the kernels of this rank; the all-reduce of deriv stays an eager call
             graph_ok = 1
         except Exception as e:  # noqa: BLE001
             graph_ok, graph_note = 0, "eager launches (graph capture failed: %r)" % (e,)
+        if world > 1:
+            # all ranks or none (the timed loops must issue the same collectives everywhere)
+            if max_over_ranks(0.0 if graph_ok else 1.0) > 0.5:
+                graph_ok, graph_note = 0, "eager launches (graph capture failed on some rank)"
     if graph_ok:
         for _ in range(a.warmup):
             with torch.cuda.stream(stream):
                 graph.replay()
+            reduce_deriv()
         barrier()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * a.steps)]
         for i in range(a.steps):
@@ -600,17 +611,20 @@ def main():
                     flush.zero_()
                 ev[2 * i].record(stream)
                 graph.replay()
-                ev[2 * i + 1].record(stream)
+            reduce_deriv()
+            ev[2 * i + 1].record(stream)
         stream.synchronize()
         barrier()
         ms_dev = max_over_ranks(sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(a.steps)) / a.steps)
-        graph_note = "one CUDA graph per step (captured once, replayed)"
+        graph_note = "one CUDA graph per step (captured once, replayed)" + (
+            "" if world == 1 else " + an eager NCCL all-reduce of deriv")
         with torch.cuda.stream(stream):
             check = deriv.clone()
         step_device()
         stream.synchronize()
         if not bool(torch.allclose(check, deriv, rtol=0.0, atol=1e-9)):
-            ms_dev, graph_note = ms_eager, "eager launches (graph replay did not reproduce the eager result)"
+            ms_dev, graph_note = ms_eager, "eager launches (graph replay did not reproduce the eager result: max diff %.3e, %d non-finite)" % (
+                float((check - deriv).abs().nan_to_num(nan=1e300).max()), int((~torch.isfinite(check)).sum()))
     value = pairs / (ms_dev * 1e-3)
 
     # ---- per-routine device times (library timers = the reference's timer names) ----------------

@@ -277,6 +277,7 @@ int dftbp_b200_set_sk_table(dftbp_b200_ctx *ctx, int which, int sp1, int sp2, in
 int dftbp_b200_set_pair_partition(dftbp_b200_ctx *ctx, int part, int nParts) {
   if (!ctx) return DFTBP_B200_EINVAL;
   DFTBP_CHECK(ctx, nParts >= 1 && part >= 0 && part < nParts, "set_pair_partition: need 0 <= part < nParts");
+  if (ctx->pairPart != part || ctx->pairParts != nParts) ctx->sortLoad.valid = false;  // the share is fixed when the schedule is built
   ctx->pairPart = part;
   ctx->pairParts = nParts;
   return 0;

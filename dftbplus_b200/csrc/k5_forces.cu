@@ -618,7 +618,9 @@ int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, c
   // nonscc.F90:43: deltaXDiff = epsilon(1.0_dp)**0.25_dp
   p.delta = delta > 0.0 ? delta : 1.220703125e-4;
   p.deriv = nullptr; p.stress = nullptr;
-  p.part = ctx->pairPart; p.nParts = ctx->pairParts;
+  // a share of the pairs (set_pair_partition) is taken when the schedule is built (pair_sort.cu): the
+  // kernels then walk through all chunks of the schedule they are given
+  p.part = 0; p.nParts = 1;
   // the non-SCC routine takes DM(:) only; the block routine DM(:, nSpin)
   const int nDm = shift ? nSpin : 1;
   DFTBP_TRY(devIn(ctx, kSlotA, DM, (size_t)g.sparseSize * nDm, &p.DM));
@@ -651,13 +653,13 @@ int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, c
       void *scratch;
       DFTBP_TRY(stagingGet(ctx, kSlotE, sizeof(double) * (size_t)g.sparseSize, &scratch));
       // both instantiations are launched; the one that does not match the device flag returns at once
-      const long long myChunks = (((g.nWorkLoad + 31) / 32 + ctx->nSpecies * ctx->nSpecies) + p.nParts - 1) / p.nParts;
+      const long long myChunks = (((g.nWorkLoad + 31) / 32 + ctx->nSpecies * ctx->nSpecies) + ctx->pairParts - 1) / ctx->pairParts;
       const int wGrid = gridFor(ctx, myChunks, 8, 6);
       const int self = st ? 1 : 0;
       // diagonal shifts: the blocks in memory order (descriptors of the work list + their schedule slots)
       const int dGrid = gridFor(ctx, (g.nWorkLoad + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, 4);
       // one partition and a sorted list of not too small blocks: the TMA span pipeline (flat_stream.cuh)
-      const bool useFlat = p.nParts == 1 && g.groupFirstLoad != nullptr && (long long)ctx->mOrb * g.nAtom * nSpin < (1LL << 31) &&
+      const bool useFlat = ctx->pairParts == 1 && g.groupFirstLoad != nullptr && (long long)ctx->mOrb * g.nAtom * nSpin < (1LL << 31) &&
                            tuneInt("DFTBP_B200_K5_FLAT", 1) != 0;
       if (useFlat) {
         // one launch: the kernel takes the full-block path itself when the device flag says so
@@ -678,7 +680,7 @@ int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, c
     // 10 warps x <= 204 registers fill the register file; the weight tile usually limits first
     const int warps = (int)std::min<size_t>(10, (ctx->smemOptin - 2048) / perWarp);
     DFTBP_CHECK(ctx, warps >= 1, "derivative_shift: weight tile does not fit into shared memory");
-    const long long items = 2 * ((((g.nWorkLoad + 31) / 32 + ctx->nSpecies * ctx->nSpecies) + p.nParts - 1) / p.nParts);
+    const long long items = 2 * ((((g.nWorkLoad + 31) / 32 + ctx->nSpecies * ctx->nSpecies) + ctx->pairParts - 1) / ctx->pairParts);
     int rc;
     if (diffType == DFTBP_B200_DIFF_RICHARDSON) {
       const long long chunks = items / 2;

@@ -263,10 +263,13 @@ int dftbp_b200_add_shift_block(dftbp_b200_ctx *ctx, double *ham, const double *o
 
 /* Optional finer decomposition of derivative_shift / stress across GPUs than the reference's per-atom
  * one (getIndicesWithWorkload, common/schedule.F90:267-307): subsequent force calls of this context
- * take the chunks part, part + nParts, ... (0-based) of its device-built pair schedule -- perfectly
- * balanced, and every GPU can keep ONE context (nRanks = 1: full H0 / S build) instead of a second,
- * atom-sharded one with its own schedule.  The partial deriv / stress arrays add up to the full
- * result, i.e. the caller's assembleChunks (all-reduce) is unchanged.  Default: part 0 of 1. */
+ * take the pairs part, part + nParts, ... (0-based, counted along the neighbour list) of the geometry --
+ * perfectly balanced, and every GPU can keep ONE context (nRanks = 1: full H0 / S build) instead of a
+ * second, atom-sharded one.  The share is a property of the pair (its position in the neighbour list),
+ * not of the device-built schedule, whose order inside a distance bin differs from run to run and from
+ * GPU to GPU: contexts on different GPUs holding the same geometry take disjoint, complete shares.
+ * The partial deriv / stress arrays add up to the full result, i.e. the caller's assembleChunks
+ * (all-reduce) is unchanged.  Default: part 0 of 1. */
 int dftbp_b200_set_pair_partition(dftbp_b200_ctx *ctx, int part, int nParts);
 
 /* derivative_shift generic, dftb/forces.F90:27-38: shift == NULL -> derivativeNonSccEuclidian

@@ -90,6 +90,39 @@ def test_pair_partition_sums_to_full(name):
     hp.close()
 
 
+def test_pair_partition_across_contexts():
+    """The shares of dftbp_b200_set_pair_partition taken by DIFFERENT contexts (one per GPU in a multi-GPU
+    run), each with its own device-built pair schedule, rebuilt several times: the schedule's order
+    inside a distance bin is not deterministic, the shares must be disjoint and complete anyway."""
+    from dftbplus_b200.api import HotPath
+    w, sk, geo, model, selfegy = case("fec128")
+    rng = np.random.default_rng(47)
+    s = oracle.build_s(model, geo)
+    dm = s * rng.normal(size=(2, geo["sparseSize"]))
+    edm = s * rng.normal(size=geo["sparseSize"])
+    shd = _diag_shift(rng, 2, geo["nAtom"], model.mOrb)
+    ref = oracle.derivative_shift(model, geo, dm, edm, shift=shd)
+    n_parts = 4
+    ctxs = []
+    for part in range(n_parts):
+        hp = HotPath(0)
+        sk.upload(hp)
+        hp.set_geometry(geo)
+        hp.set_pair_partition(part, n_parts)
+        ctxs.append(hp)
+    try:
+        for rep in range(3):
+            acc = np.zeros_like(ref)
+            for hp in ctxs:
+                hp.update_coords(geo["coords"])           # a new schedule, as in every geometry step
+                hp.buildH0S(sk.selfegy)                   # (the full build shares the context)
+                acc += hp.derivative_shift(dm, edm, shift=shd)
+            assert np.abs(acc - ref).max() < TOL_FORCE, (rep, np.abs(acc - ref).max())
+    finally:
+        for hp in ctxs:
+            hp.close()
+
+
 def test_water2046_pair_kernels():
     """BASELINE config 5 geometry (682 H2O, 2046 atoms): H0 / S, Mulliken and SCC forces vs the oracle."""
     from dftbplus_b200.api import HotPath
