@@ -152,6 +152,7 @@ struct dftbp_b200_ctx {
   int dmColFirst = 1, dmColLast = 0;            // column panel of the current density-matrix call
   int pairPart = 0, pairParts = 1;              // share of the pair schedule the force calls take (set_pair_partition)
   std::vector<long long> blockStartOfAtom;      // first entry of every atom in workAll / descAll (nAtom + 1)
+  std::vector<int> loadInd;                     // sparse offset of every entry of descLoad, then the end of the last one
   int smCount = 148;
   size_t smemOptin = 232448;  // max dynamic shared memory per CTA
   size_t smemPerSm = 233472;
@@ -339,6 +340,9 @@ inline int shiftDiagBuffer(dftbp_b200_ctx *ctx, long long need, double **out) {
   *out = ctx->shiftDiag;
   return 0;
 }
+
+// first work-list entry of share `part` of nParts (dftbp_b200_set_pair_partition): contiguous ranges
+inline long long shareBegin(long long nWork, int part, int nParts) { return nWork * part / nParts; }
 
 // tuning switch read from the environment (tools/gpu_probe.py A/B runs); def when unset
 inline int tuneInt(const char *name, int def) {

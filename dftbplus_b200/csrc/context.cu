@@ -424,6 +424,18 @@ int dftbp_b200_set_geometry(dftbp_b200_ctx *ctx, int nAtom, int nAllAtom, int mN
     g.firstAtomMine = first - 1;
     g.lastAtomMine = last - 1;
   }
+  {
+    const std::vector<int> &wl = ctx->nRanks == 1 ? all : load;
+    ctx->loadInd.resize(wl.size() + 1);
+    int end = 0;
+    for (size_t w = 0; w < wl.size(); ++w) {
+      const int flat = wl[w], i = flat / ld;
+      const int f = hImg[hNb[flat] - 1] - 1;
+      ctx->loadInd[w] = hPair[flat];
+      end = hPair[flat] + (hStart[i + 1] - hStart[i]) * (hStart[f + 1] - hStart[f]);
+    }
+    ctx->loadInd[wl.size()] = end;
+  }
   ctx->geo = g;
   ctx->sortMine.valid = ctx->sortLoad.valid = false;
   return 0;

@@ -105,9 +105,9 @@ struct Elem {
 template <int NIN, int WARPS, class Body>
 __device__ __forceinline__ void streamSpans(Smem<NIN, WARPS> &sm, const double *const (&src)[NIN], int n,
                                             const BlockDesc *__restrict__ desc, int nBlocks,
-                                            const int *__restrict__ groupFirst, Body &&body) {
+                                            const int *__restrict__ groupFirst, int spanLo, int spanHi, Body &&body) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int nSpans = (n + kSpan - 1) / kSpan;
+  const int nSpans = min(spanHi, (n + kSpan - 1) / kSpan);  // spans [spanLo, spanHi) of the arrays
   const int stride = (int)gridDim.x * WARPS;
   int phase[NIN];
 #pragma unroll
@@ -163,7 +163,7 @@ __device__ __forceinline__ void streamSpans(Smem<NIN, WARPS> &sm, const double *
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  const int first = (int)blockIdx.x * WARPS + w;
+  const int first = spanLo + (int)blockIdx.x * WARPS + w;
 #pragma unroll
   for (int s = 0; s < kStages; ++s) request(first + s * stride, s);
 

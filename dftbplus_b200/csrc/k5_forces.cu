@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(32 * flat::warpsFor(1 + NSPIN), 1)
     k5_force_weights_flat(const K5Params p, const BlockDesc *__restrict__ desc, long long nWork,
                           const int *__restrict__ groupFirst, const double *__restrict__ EDM,
                           const double *__restrict__ diag, const int *__restrict__ shiftFull,
-                          double *__restrict__ negWS, const double *__restrict__ shift, int selfImages) {
+                          double *__restrict__ negWS, const double *__restrict__ shift, int selfImages, int spanLo,
+                          int spanHi) {
   if (__ldg(shiftFull) != 0) {  // full shift blocks (DFTB+U-like): per-pair matrix products along the schedule
     forceWeightsSched<1, true>(p, EDM, shift, negWS, selfImages);
     return;
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(32 * flat::warpsFor(1 + NSPIN), 1)
   const int mOrb = p.mOrb;
   const int spinStride = mOrb * p.nAtom;  // diag(:, :, iSpin + 1) - diag(:, :, iSpin)
   flat::streamSpans<NIN, WARPS>(
-      sm, src, p.sparseSize, desc, (int)nWork, groupFirst, [&](const flat::Elem<NIN>(&el)[flat::kBatch]) {
+      sm, src, p.sparseSize, desc, (int)nWork, groupFirst, spanLo, spanHi, [&](const flat::Elem<NIN>(&el)[flat::kBatch]) {
         double x1[flat::kBatch][NSPIN], x2[flat::kBatch][NSPIN];
 #pragma unroll
         for (int u = 0; u < flat::kBatch; ++u) {
@@ -577,24 +578,24 @@ namespace {
 template <int NSPIN>
 int launchWeightsFlatT(dftbp_b200_ctx *ctx, const K5Params &p, const BlockDesc *desc, long long nWork,
                        const int *groupFirst, const double *EDM, const double *diag, const int *flag, double *negWS,
-                       const double *shift, int selfImages) {
+                       const double *shift, int selfImages, int spanLo, int spanHi) {
   constexpr int NIN = 1 + NSPIN, WARPS = flat::warpsFor(NIN);
   const size_t smemBytes = sizeof(flat::Smem<NIN, WARPS>);
   static LaunchInfo info;
   DFTBP_TRY(launchInfo(ctx, info, k5_force_weights_flat<NSPIN>, 32 * WARPS, smemBytes, nullptr));
-  const long long nSpans = ((long long)p.sparseSize + flat::kSpan - 1) / flat::kSpan;
+  const long long nSpans = std::max(0, spanHi - spanLo);
   const int grid = (int)std::max<long long>(1, std::min<long long>((nSpans + WARPS - 1) / WARPS, ctx->smCount));
   k5_force_weights_flat<NSPIN><<<grid, 32 * WARPS, smemBytes, ctx->stream>>>(p, desc, nWork, groupFirst, EDM, diag, flag,
-                                                                            negWS, shift, selfImages);
+                                                                            negWS, shift, selfImages, spanLo, spanHi);
   return 0;
 }
 
 int launchWeightsFlat(dftbp_b200_ctx *ctx, int nSpin, const K5Params &p, const BlockDesc *desc, long long nWork,
                       const int *groupFirst, const double *EDM, const double *diag, const int *flag, double *negWS,
-                      const double *shift, int selfImages) {
-  if (nSpin == 1) return launchWeightsFlatT<1>(ctx, p, desc, nWork, groupFirst, EDM, diag, flag, negWS, shift, selfImages);
-  if (nSpin == 2) return launchWeightsFlatT<2>(ctx, p, desc, nWork, groupFirst, EDM, diag, flag, negWS, shift, selfImages);
-  return launchWeightsFlatT<4>(ctx, p, desc, nWork, groupFirst, EDM, diag, flag, negWS, shift, selfImages);
+                      const double *shift, int selfImages, int spanLo, int spanHi) {
+  if (nSpin == 1) return launchWeightsFlatT<1>(ctx, p, desc, nWork, groupFirst, EDM, diag, flag, negWS, shift, selfImages, spanLo, spanHi);
+  if (nSpin == 2) return launchWeightsFlatT<2>(ctx, p, desc, nWork, groupFirst, EDM, diag, flag, negWS, shift, selfImages, spanLo, spanHi);
+  return launchWeightsFlatT<4>(ctx, p, desc, nWork, groupFirst, EDM, diag, flag, negWS, shift, selfImages, spanLo, spanHi);
 }
 
 // derivative_shift (deriv != nullptr) and / or the stress tensor (st != nullptr) from one pass over the pairs
@@ -659,12 +660,18 @@ int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, c
       // diagonal shifts: the blocks in memory order (descriptors of the work list + their schedule slots)
       const int dGrid = gridFor(ctx, (g.nWorkLoad + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, 4);
       // one partition and a sorted list of not too small blocks: the TMA span pipeline (flat_stream.cuh)
-      const bool useFlat = ctx->pairParts == 1 && g.groupFirstLoad != nullptr && (long long)ctx->mOrb * g.nAtom * nSpin < (1LL << 31) &&
-                           tuneInt("DFTBP_B200_K5_FLAT", 1) != 0;
+      const bool useFlat = g.groupFirstLoad != nullptr && (long long)ctx->mOrb * g.nAtom * nSpin < (1LL << 31) &&
+                           (long long)ctx->loadInd.size() == g.nWorkLoad + 1 && tuneInt("DFTBP_B200_K5_FLAT", 1) != 0;
       if (useFlat) {
-        // one launch: the kernel takes the full-block path itself when the device flag says so
+        // one launch: the kernel takes the full-block path itself when the device flag says so.  A share
+        // of the pairs (set_pair_partition) is a contiguous range of the work list = of the sparse arrays:
+        // only the spans it touches are streamed.
+        const long long wLo = shareBegin(g.nWorkLoad, ctx->pairPart, ctx->pairParts),
+                        wHi = shareBegin(g.nWorkLoad, ctx->pairPart + 1, ctx->pairParts);
+        const int spanLo = ctx->loadInd[wLo] / flat::kSpan;
+        const int spanHi = wHi > wLo ? (ctx->loadInd[wHi] + flat::kSpan - 1) / flat::kSpan : spanLo;
         DFTBP_TRY(launchWeightsFlat(ctx, nSpin, p, g.descLoad, g.nWorkLoad, g.groupFirstLoad, dEDM, dDiag, flag, (double *)scratch,
-                                    dShift, self));
+                                    dShift, self, spanLo, spanHi));
         ctx->launches += 2;
       } else {
         if (nSpin == 1) k5_force_weights_diag<1><<<dGrid, 256, 0, ctx->stream>>>(p, g.descLoad, sched->slotOf, g.nWorkLoad, dEDM, dShift, flag, (double *)scratch, self);

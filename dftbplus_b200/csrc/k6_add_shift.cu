@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(32 * flat::warpsFor(ZERO ? 1 : 1 + NSPIN), 1)
   const int mOrb = p.mOrb;
   const int spinStride = (MODE == 0 ? 1 : mOrb) * p.nAtom;
   flat::streamSpans<NIN, WARPS>(
-      sm, src, p.sparseSize, p.desc, (int)p.nWork, groupFirst, [&](const flat::Elem<NIN>(&el)[flat::kBatch]) {
+      sm, src, p.sparseSize, p.desc, (int)p.nWork, groupFirst, 0, 0x7fffffff, [&](const flat::Elem<NIN>(&el)[flat::kBatch]) {
         double v1[flat::kBatch][NSPIN], v2[flat::kBatch][NSPIN];
 #pragma unroll
         for (int u = 0; u < flat::kBatch; ++u) {

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kSortThreads) ps_keys(const int *__restrict__ 
                                                         PairRec *__restrict__ recsMem, int *__restrict__ ticket,
                                                         int nBuckets, int *__restrict__ total,
                                                         int *__restrict__ items, PairRec *__restrict__ recs,
-                                                        int part, int nParts) {
+                                                        long long shareLo, long long shareHi) {
   extern __shared__ int sh[];
   __shared__ int warpSum[32];
   __shared__ int baseSh, lastSh;
@@ -117,11 +117,14 @@ __global__ void __launch_bounds__(kSortThreads) ps_keys(const int *__restrict__ 
   const long long lo = per * blockIdx.x, hi = min(nWork, lo + per);
   for (long long i = lo + threadIdx.x; i < hi; i += kSortThreads) {
     PairRec r;
-    int key = pairKey(__ldg(work + i), ld, nSpecies, nBins, binScale, coords, species, iNeighbour, iPair, r);
-    // a schedule of one share of the pairs (dftbp_b200_set_pair_partition): work-list entries part,
-    // part + nParts, ... -- a property of the pair, not of the (non-deterministic) order inside a bin,
-    // so that the shares of different GPUs are disjoint and complete
-    if (nParts > 1 && (int)(i % nParts) != part) key = -1;
+    // a schedule of one share of the pairs (dftbp_b200_set_pair_partition): a contiguous range of the
+    // work list -- a property of the pair, not of the (non-deterministic) order inside a bin, so that
+    // the shares of different GPUs are disjoint and complete
+    if (i < shareLo || i >= shareHi) {
+      keys[i] = -1;
+      continue;
+    }
+    const int key = pairKey(__ldg(work + i), ld, nSpecies, nBins, binScale, coords, species, iNeighbour, iPair, r);
     keys[i] = key;
     recsMem[i] = r;  // the same record in the order of the work list (= the order of the sparse arrays)
     if (key >= 0) atomicAdd(sh + key, 1);
@@ -231,6 +234,8 @@ int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out
   const bool shared = g.workLoad == g.workMine && ctx->pairParts == 1;
   SortedPairs &sp = (forLoad && !shared) ? ctx->sortLoad : ctx->sortMine;
   const int part = (forLoad && !shared) ? ctx->pairPart : 0, nParts = (forLoad && !shared) ? ctx->pairParts : 1;
+  const long long nWorkAllOfList = (forLoad && !shared) ? g.nWorkLoad : g.nWorkMine;
+  const long long shareLo = shareBegin(nWorkAllOfList, part, nParts), shareHi = shareBegin(nWorkAllOfList, part + 1, nParts);
   *out = &sp;
   if (sp.valid) return 0;
   const int *work = (forLoad && !shared) ? g.workLoad : g.workMine;
@@ -271,7 +276,7 @@ int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out
                                                            g.coords, g.species, g.iNeighbour, g.iPair, binScale,
                                                            ctx->sortKeys, ctx->sortBins, sp.recsMem,
                                                            ctx->sortBins + nBins64, nBuckets, sp.total, sp.items, sp.recs,
-                                                           part, nParts);
+                                                           shareLo, shareHi);
     ps_scatter<<<grid, kSortThreads, smemBytes, ctx->stream>>>(work, nWork, nKeys, ctx->sortKeys, ctx->sortBins,
                                                               sp.items, sp.recs, sp.atoms, g.mNeigh + 1, sp.recsMem,
                                                               g.iNeighbour, g.img2CentCell, sp.slotOf);
