@@ -7,7 +7,9 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/dftbp_b200.h"
@@ -194,6 +196,11 @@ struct dftbp_b200_ctx {
   size_t solverWorkBytes = 0;
   int *dInfo = nullptr;
   void *neighbourState = nullptr;  // device-built neighbour list (n2_neighbour_list.cu)
+  // device blocks of the per-geometry arrays, kept across set_geometry calls (poolAlloc / poolRelease):
+  // a geometry step re-uploads ~20 arrays of nearly the same sizes, and cudaFree + cudaMalloc of each
+  // cost more than everything else in set_geometry (each cudaFree synchronises the device)
+  std::multimap<size_t, void *> poolIdle;        // capacity -> block
+  std::unordered_map<void *, size_t> poolCap;    // every block of the pool, handed out or idle
 };
 
 namespace dftbp_b200 {
@@ -309,15 +316,60 @@ inline int finish(dftbp_b200_ctx *ctx) {
   return 0;
 }
 
+// capacities of pool blocks: multiples of a quarter of the largest power of two below the request
+inline size_t poolRound(size_t bytes) {
+  if (bytes < 512) return 512;
+  size_t p = 512;
+  while (p * 2 <= bytes) p *= 2;
+  const size_t q = p / 4;
+  return (bytes + q - 1) / q * q;
+}
+
+inline int poolAlloc(dftbp_b200_ctx *ctx, void **out, size_t bytes) {
+  const size_t r = poolRound(bytes);
+  auto it = ctx->poolIdle.lower_bound(r);
+  if (it != ctx->poolIdle.end() && it->first <= 2 * r) {
+    *out = it->second;
+    ctx->poolIdle.erase(it);
+    return 0;
+  }
+  cudaError_t e = cudaMalloc(out, r);
+  if (e != cudaSuccess) {  // give the idle blocks back and try once more
+    for (auto &kv : ctx->poolIdle) {
+      ctx->poolCap.erase(kv.second);
+      cudaFree(kv.second);
+    }
+    ctx->poolIdle.clear();
+    cudaGetLastError();
+    e = cudaMalloc(out, r);
+  }
+  if (e != cudaSuccess)
+    return fail(ctx, DFTBP_B200_ENOMEM, "cudaMalloc(%zu) failed: %s", r, cudaGetErrorString(e));
+  ctx->poolCap[*out] = r;
+  return 0;
+}
+
+inline void poolRelease(dftbp_b200_ctx *ctx, void *p) {
+  if (!p) return;
+  auto it = ctx->poolCap.find(p);
+  if (it == ctx->poolCap.end()) cudaFree(p);  // not from the pool
+  else ctx->poolIdle.emplace(it->second, p);
+}
+
+inline void poolDestroy(dftbp_b200_ctx *ctx) {
+  for (auto &kv : ctx->poolIdle) cudaFree(kv.second);
+  ctx->poolIdle.clear();
+  ctx->poolCap.clear();
+}
+
 template <class T>
 inline int uploadNew(dftbp_b200_ctx *ctx, T **dst, const T *src, size_t count) {
-  if (*dst) cudaFree(*dst);
+  if (*dst) poolRelease(ctx, *dst);
   *dst = nullptr;
   if (count == 0) return 0;
-  cudaError_t e = cudaMalloc((void **)dst, count * sizeof(T));
-  if (e != cudaSuccess)
-    return fail(ctx, DFTBP_B200_ENOMEM, "cudaMalloc(%zu) failed: %s", count * sizeof(T),
-                cudaGetErrorString(e));
+  void *blk = nullptr;
+  DFTBP_TRY(poolAlloc(ctx, &blk, count * sizeof(T)));
+  *dst = static_cast<T *>(blk);
   cudaMemcpyKind kind = isDevicePtr(src) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   DFTBP_CUDA(ctx, cudaMemcpyAsync(*dst, src, count * sizeof(T), kind, ctx->stream));
   // the source may be a temporary host vector: make the copy complete before returning

@@ -10,17 +10,18 @@ using namespace dftbp_b200;
 
 namespace {
 
-void freeGeometry(Geometry &g) {
-  cudaFree(g.coords); cudaFree(g.species); cudaFree(g.img2CentCell); cudaFree(g.iCellVec);
-  cudaFree(g.cellVec); cudaFree(g.nNeighbourSK); cudaFree(g.iNeighbour); cudaFree(g.iPair);
-  cudaFree(g.iAtomStart);
-  if (g.workMine != g.workAll) cudaFree(g.workMine);
-  if (g.workLoad != g.workAll) cudaFree(g.workLoad);
-  cudaFree(g.workAll);
-  if (g.descLoad != g.descAll) cudaFree(g.descLoad);
-  cudaFree(g.descAll);
-  if (g.groupFirstLoad != g.groupFirstAll) cudaFree(g.groupFirstLoad);
-  cudaFree(g.groupFirstAll);
+void freeGeometry(dftbp_b200_ctx *ctx, Geometry &g) {
+  auto rel = [&](void *p) { poolRelease(ctx, p); };
+  rel(g.coords); rel(g.species); rel(g.img2CentCell); rel(g.iCellVec);
+  rel(g.cellVec); rel(g.nNeighbourSK); rel(g.iNeighbour); rel(g.iPair);
+  rel(g.iAtomStart);
+  if (g.workMine != g.workAll) rel(g.workMine);
+  if (g.workLoad != g.workAll) rel(g.workLoad);
+  rel(g.workAll);
+  if (g.descLoad != g.descAll) rel(g.descLoad);
+  rel(g.descAll);
+  if (g.groupFirstLoad != g.groupFirstAll) rel(g.groupFirstLoad);
+  rel(g.groupFirstAll);
   g = Geometry();
 }
 
@@ -83,7 +84,8 @@ int dftbp_b200_create(dftbp_b200_ctx **out, int device, int rank, int nRanks) {
 int dftbp_b200_destroy(dftbp_b200_ctx *ctx) {
   if (!ctx) return 0;
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  freeGeometry(ctx->geo);
+  freeGeometry(ctx, ctx->geo);
+  poolDestroy(ctx);
   freeSortedPairs(ctx);
   freeNeighbourList(ctx);
   for (void *p : ctx->tableAllocs) cudaFree(p);
@@ -331,7 +333,7 @@ int dftbp_b200_set_geometry(dftbp_b200_ctx *ctx, int nAtom, int nAllAtom, int mN
       covered += (long long)n1 * n2;
     }
   Geometry g;
-  freeGeometry(ctx->geo);
+  freeGeometry(ctx, ctx->geo);
   g.coversAll = covered == sparseSize;
   g.nAtom = nAtom; g.nAllAtom = nAllAtom; g.mNeigh = mNeigh; g.nCellVec = nCellVec;
   g.sparseSize = sparseSize; g.nOrb = hStart[nAtom] - 1;
