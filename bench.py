@@ -199,6 +199,44 @@ def algorithmic_flops_k5(geo, sk, n_spin):
     return total
 
 
+def cublas_dsyrk_ms(stream, n, k, a_ptr, lda, c_ptr, ldc, reps=2):
+    """cuBLAS DSYRK (lower, C = A A^T, A n x k column-major) on the given stream, through ctypes: the library
+    routine the reference's CPU path uses for the density matrix (dsyrk / zherk, densitymatrix.F90:566-584) --
+    the comparison SURVEY's hard part 6 asks for.  Returns ms per call or None."""
+    import ctypes
+    import torch
+    try:
+        cb = ctypes.CDLL("libcublas.so.12")
+    except OSError:
+        try:
+            cb = ctypes.CDLL("/usr/local/cuda/lib64/libcublas.so")
+        except OSError:
+            return None
+    h = ctypes.c_void_p()
+    if cb.cublasCreate_v2(ctypes.byref(h)) != 0:
+        return None
+    try:
+        cb.cublasSetStream_v2(h, ctypes.c_void_p(stream.cuda_stream))
+        one, zero = ctypes.c_double(1.0), ctypes.c_double(0.0)
+        CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N = 0, 0
+
+        def call():
+            return cb.cublasDsyrk_v2(h, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, ctypes.c_int(n), ctypes.c_int(k),
+                                     ctypes.byref(one), ctypes.c_void_p(a_ptr), ctypes.c_int(lda), ctypes.byref(zero),
+                                     ctypes.c_void_p(c_ptr), ctypes.c_int(ldc))
+        if call() != 0:
+            return None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            call()
+        e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1) / reps
+    finally:
+        cb.cublasDestroy_v2(h)
+
+
 def scc_shift(rng, n_spin, n_atom, m_orb):
     """Block shift of a collinear-spin SCC run without DFTB+U / on-site corrections (BASELINE config
     4): diagonal mOrb x mOrb blocks, one value per orbital (hamiltonian.F90:148-293 -> shift.F90:232-309
@@ -890,6 +928,15 @@ def main():
             C.copy_(torch.randn(nOrb, nOrb, **f64).mul_(nOrb ** -0.5))     # stand-in eigenvectors
             fill = torch.zeros(nOrb, **f64)
             fill[:n_occ] = 2.0 / n_spin
+            # cuBLAS DSYRK on the shape of the density-matrix contraction (n x nLevels panel of C): what a
+            # library call would give for the same n^2 * nLevels flops
+            dsyrk_ms = None
+            if my_panel is None:
+                try:
+                    dsyrk_ms = cublas_dsyrk_ms(stream, nOrb, n_occ, C.data_ptr(), C.stride(1) if C.stride(0) == 1 else C.stride(0),
+                                               sq.data_ptr(), sq.stride(1) if sq.stride(0) == 1 else sq.stride(0))
+                except Exception:  # noqa: BLE001
+                    dsyrk_ms = None
             rho = torch.zeros((n_spin, ss), **f64)
             qq = torch.zeros((nAtom, mo), **f64)
             ham_scc = torch.zeros((n_spin, ss), **f64)
@@ -947,7 +994,10 @@ def main():
                            "achieved": flops / dm_ms / 1e9, "peak": dgemm_tflops, "unit": "TFLOP/s",
                            "frac": flops / dm_ms / 1e9 / dgemm_tflops, "traffic": None,
                            "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 is not in MEASURED_PEAKS.json)",
-                           "n": nOrb, "nLevels": n_occ, "ms_per_launch": dm_ms}
+                           "n": nOrb, "nLevels": n_occ, "ms_per_launch": dm_ms,
+                           "cublas_dsyrk_same_shape_ms": dsyrk_ms,
+                           "cublas_dsyrk_same_shape_tflops": (float(nOrb) * nOrb * n_occ / dsyrk_ms / 1e9) if dsyrk_ms else None,
+                           "speed_vs_cublas_dsyrk": (dsyrk_ms / dm_ms) if dsyrk_ms else None}
         gbs = lambda b, ms: (b / ms / 1e6) if ms else None
         kernels.update({
             "sparseToDense": {"ms": per["sparseToDense"], "GBs": gbs(8.0 * ss + 8.0 * nOrb * nOrb, per["sparseToDense"])},
