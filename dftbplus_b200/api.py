@@ -196,7 +196,8 @@ class HotPath:
         """updateNeighbourListAndSpecies + getNrOfNeighboursForAll + getSparseDescriptor on the device
         (handleCoordinateChange, dftbplus/main.F90:2562-2578).  coord0[nAtom, 3] (host array or CUDA
         tensor), species0[nAtom] 1-based, cutoff = list cutoff, sk_cutoff (default: cutoff).
-        adopt: make the result the context's geometry without a host round trip; fetch: return the
+        adopt: make the result the context's geometry (the caller's arrays are not involved; the library
+        itself reads the index arrays back once, ~2 MB, to build its block descriptors: ~4 ms at 4096 atoms); fetch: return the
         geometry dict of SURVEY.md section 8.0 (host copies), else only the sizes.  symmetric: the reference's
         symmetric list (for the host's use; never adopted)."""
         sk_cutoff = cutoff if sk_cutoff is None else sk_cutoff

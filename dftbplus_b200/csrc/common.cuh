@@ -396,8 +396,22 @@ inline int shiftDiagBuffer(dftbp_b200_ctx *ctx, long long need, double **out) {
 // first work-list entry of share `part` of nParts (dftbp_b200_set_pair_partition): contiguous ranges
 inline long long shareBegin(long long nWork, int part, int nParts) { return nWork * part / nParts; }
 
-// tuning switch read from the environment (tools/gpu_probe.py A/B runs); def when unset
+// tuning switch read from the environment (tools/gpu_probe.py A/B runs); def when unset.  The
+// environment is read once per switch and process, not on every launch.
 inline int tuneInt(const char *name, int def) {
+  struct Entry { const char *name; int value; };
+  static Entry cache[32];
+  static int nCache = 0;
+  for (int i = 0; i < nCache; ++i)
+    if (cache[i].name == name || std::strcmp(cache[i].name, name) == 0) return cache[i].value;
+  const char *env = getenv(name);
+  const int v = env ? atoi(env) : def;
+  if (nCache < 32) cache[nCache++] = Entry{name, v};
+  return v;
+}
+
+// the same without the cache: switches a test flips inside one process (solver path selection; once per call)
+inline int tuneIntNow(const char *name, int def) {
   const char *env = getenv(name);
   return env ? atoi(env) : def;
 }

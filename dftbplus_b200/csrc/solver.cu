@@ -175,7 +175,7 @@ int hegvImpl(dftbp_b200_ctx *ctx, void *H, void *S, double *eigen, int n, int ld
   int lwork = 0;
   cusolverStatus_t st;
   // workspace of the 32-bit API: about 2 n^2 elements -> beyond INT_MAX near n = 23 000 (real)
-  const bool large = (double)n * n * (cplx ? 2.2 : 2.1) > 2.0e9 || tuneInt("DFTBP_B200_HEGV_LARGE", 0);
+  const bool large = (double)n * n * (cplx ? 2.2 : 2.1) > 2.0e9 || tuneIntNow("DFTBP_B200_HEGV_LARGE", 0);
   if (large) {
     int rc = hegvLarge(ctx, h, dH, dS, dE, n, ld, mode, cplx);
     if (rc) {
