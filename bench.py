@@ -421,6 +421,10 @@ def section_md(dev, stream, n_steps):
     dq = torch.zeros(nAtom, **f64)
     kT = 0.02        # the synthetic SK tables leave the box without a gap: Fermi smearing (hartree)
     scc_iters, t_list, t_build, t_scc, t_force = [], 0.0, 0.0, 0.0, 0.0
+    mixer = None
+    if os.environ.get("DFTBP_B200_MD_MIXER", "broyden") == "broyden":
+        from dftbplus_b200.mixer import BroydenMixer
+        mixer = BroydenMixer(max_scc_iter=64)
 
     def forces(x):
         nonlocal dq, fill, t_list, t_build, t_scc, t_force
@@ -440,6 +444,8 @@ def section_md(dev, stream, n_steps):
         t2 = time.perf_counter()
         it = 0
         hist_x, hist_r = [], []
+        if mixer is not None:
+            mixer.reset(nAtom)           # the reference resets its mixer for every geometry
         for it in range(1, 41):
             with torch.cuda.stream(stream):
                 shift.zero_()
@@ -467,6 +473,10 @@ def section_md(dev, stream, n_steps):
                           float(eig[n_occ] - eig[n_occ - 1])), flush=True)
                 if err < 1e-5:
                     break
+                if mixer is not None:
+                    # modified Broyden mixing of the atomic charges, the reference's default (host side, O(nAtom))
+                    dq = torch.from_numpy(mixer.mix(dq.cpu().numpy(), res.cpu().numpy())).to(dev)
+                    continue
                 # Anderson mixing over the last five (input, residual) pairs of this geometry
                 hist_x.append(dq.clone()); hist_r.append(res.clone())
                 if len(hist_x) > 5:
@@ -508,7 +518,8 @@ def section_md(dev, stream, n_steps):
                                      "edm_pack_forces": t_force / n_steps * 1e3},
            "momentum_drift": float(np.abs((mass[:, None] * v).sum(axis=0)).max()),
            "timing": "host wall clock (the step contains cuSOLVER calls and small D2H reads)",
-           "note": "on-site SCC model of the harness (no gamma / Ewald), Anderson mixing (5 vectors, 0.4), tolerance 1e-5, Fermi smearing kT = 0.02 Ha (the synthetic tables leave no gap); "
+           "note": "on-site SCC model of the harness (no gamma / Ewald), " + ("modified Broyden mixing with the reference's defaults (dftbplus_b200/mixer.py)" if mixer is not None else "Anderson mixing (5 vectors, 0.4)") +
+                   ", tolerance 1e-5, at most 40 iterations, Fermi smearing kT = 0.02 Ha (the synthetic tables leave no gap); "
                    "BASELINE asks for 100 steps: --md 100"}
     del H, S, D
     hp.close()

@@ -86,3 +86,38 @@ def test_efilling_limits():
     assert sm.efilling(eig, 0.0, 0.001, [1.0])["filling"].sum() == 0.0
     full = sm.efilling(eig, 2.0, 0.001, [1.0])             # nOrbs * spin <= nElec
     assert np.allclose(full["filling"], 1.0) and full["Ef"] > 0.1
+
+
+def test_product_mixer_matches_reference_known_answer_and_oracle():
+    """dftbplus_b200/mixer.py (the host-side mirror bench.py's MD section uses) against the same reference
+    vector and, on a longer sequence, against the oracle's restatement."""
+    from dftbplus_b200.mixer import BroydenMixer
+    expected = np.array([
+        [6.0000000000000018, 1.0000000000000002, 1.0000000000000002],
+        [6.1761632532030193, 0.91191837339849169, 0.91191837339849169],
+        [6.4798000093100434, 0.76009999534497941, 0.76009999534497941],
+        [6.4625859389302871, 0.76870703053485734, 0.76870703053485745],
+        [6.4635561795150211, 0.76822191024249031, 0.76822191024249042]])
+    difference = np.array([
+        [0.88081626601508667, -0.44040813300754278, -0.44040813300754278],
+        [0.55742893386488124, -0.27871446693244140, -0.27871446693244140],
+        [-3.2497351757903914E-002, 1.6248675878950958E-002, 1.6248675878951291E-002],
+        [1.9288771697691942E-003, -9.6443858488526324E-004, -9.6443858488515222E-004]])
+    mixer = BroydenMixer(100, 0.2, 0.01, 1.0, 100000.0, 0.01)
+    mixer.reset(3)
+    q = expected[0].copy()
+    for ii in range(4):
+        q = mixer.mix(q, difference[ii])
+        assert np.abs(q - expected[ii + 1]).max() <= 100.0 * np.finfo(np.float64).eps
+    rng = np.random.default_rng(9)
+    n = 40
+    A = 0.5 * rng.normal(size=(n, n)) / np.sqrt(n)
+    b = rng.normal(size=n)
+    a, o = BroydenMixer(), sm.BroydenMixer()
+    a.reset(n)
+    o.reset(n)
+    qa, qo = np.zeros(n), np.zeros(n)
+    for _ in range(25):
+        qa = a.mix(qa, A @ qa + b - qa)
+        o.mix(qo, A @ qo + b - qo)
+        assert np.abs(qa - qo).max() < 1e-12
