@@ -64,6 +64,8 @@ SIGNATURES = {
     "dftbp_b200_timer_read": (c_int, [c_void_p, c_int, P(c_double), P(ctypes.c_longlong)]),
     "dftbp_b200_kernel_launches": (ctypes.c_longlong, [c_void_p]),
     "dftbp_b200_num_pairs": (ctypes.c_longlong, [c_void_p]),
+    "dftbp_b200_efilling": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                    c_int, c_double, c_double, c_void_p, c_int]),
 }
 
 _lib = None

@@ -390,6 +390,35 @@ class HotPath:
         return st
 
     # ---- cuSOLVER ---------------------------------------------------------------------------
+    def Efilling(self, eigenvals, n_electrons, kT, k_weight=(1.0,), filling=None):
+        """Efilling (dftb/etemp.F90:59-191, Fermi distribution) on the device.  eigenvals [nSpin][nKpt][nLevels]
+        in memory (= the Fortran array (nLevels, nKpt, nSpin)); lower-dimensional inputs are taken as one
+        k-point / one spin channel.  One electron per level: callers of spin-unpolarised runs pass half the
+        electrons and double the results (getFillingsAndBandEnergies, main.F90:4597-4648).
+        Returns dict(filling, Ef, Ebs, TS, E0); with torch inputs the filling stays on the device."""
+        tor = _is_torch(eigenvals)
+        shape = tuple(eigenvals.shape)
+        n_lev = int(shape[-1])
+        n_k = int(shape[-2]) if len(shape) >= 2 else 1
+        n_spin = int(shape[-3]) if len(shape) >= 3 else 1
+        if tor:
+            import torch
+            eig = eigenvals.contiguous()
+            if filling is None:
+                filling = torch.empty_like(eig)
+            kw = torch.as_tensor(np.asarray(k_weight, dtype=np.float64)).to(eig.device) if not _is_torch(k_weight) else k_weight
+        else:
+            eig = np.ascontiguousarray(eigenvals, dtype=np.float64)
+            if filling is None:
+                filling = np.empty_like(eig)
+            kw = np.ascontiguousarray(k_weight, dtype=np.float64)
+        small = np.zeros(7)        # Ebs(2), TS(2), E0(2), Ef: host outputs
+        self._ck(self._L.dftbp_b200_efilling(
+            self._h, _ptr(small[0:2]), _ptr(small[6:7]), _ptr(small[2:4]), _ptr(small[4:6]), _ptr(filling), _ptr(eig),
+            n_lev, n_k, n_spin, float(n_electrons), float(kT), _ptr(kw), 0))
+        return dict(filling=filling, Ef=float(small[6]), Ebs=small[0:n_spin].copy(), TS=small[2:2 + n_spin].copy(),
+                    E0=small[4:4 + n_spin].copy())
+
     def diagDenseMtx(self, H, S, eigen=None, jobz="V"):
         """hegvd: H, S column-major, overwritten (H <- eigenvectors); returns eigenvalues."""
         n = H.shape[0]

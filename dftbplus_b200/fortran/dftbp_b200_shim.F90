@@ -17,7 +17,7 @@ module dftbp_b200_shim
   public :: b200_getEDensityMatrix_real, b200_getEDensityMatrix_cmplx
   public :: b200_mullikenPerOrbital, b200_mullikenPerBlock, b200_mullikenPerAtom, b200_getOnsitePopulation
   public :: b200_derivative_shift, b200_addShift_block, b200_addShift_atom, b200_getBlockStress
-  public :: b200_hegv_real, b200_hegv_cmplx
+  public :: b200_hegv_real, b200_hegv_cmplx, b200_Efilling
 
   integer, parameter :: dp = c_double
 
@@ -235,6 +235,15 @@ module dftbp_b200_shim
       real(c_double), intent(out) :: eigen(*)
       integer(c_int), value :: n, ld
       character(kind=c_char), value :: jobz
+    end function
+    integer(c_int) function dftbp_b200_efilling(ctx, Ebs, Ef, TS, E0, filling, eigenvals, nLevels, nKpt, nSpin,&
+        & nElectrons, kT, kWeight, distrib) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(out) :: Ebs(*), Ef, TS(*), E0(*), filling(*)
+      real(c_double), intent(in) :: eigenvals(*), kWeight(*)
+      integer(c_int), value :: nLevels, nKpt, nSpin, distrib
+      real(c_double), value :: nElectrons, kT
     end function
     integer(c_int) function dftbp_b200_adopt_neighbour_list(ctx) bind(C)
       import :: c_ptr, c_int
@@ -508,6 +517,17 @@ contains
     call check(ctx, dftbp_b200_hegv_cplx(ctx%h, HSqr, SSqr, eigen, size(HSqr, dim=2), size(HSqr, dim=1),&
         & jobz))
   end subroutine b200_hegv_cmplx
+
+  !> Efilling, dftb/etemp.F90:59 (same dummy arguments; Fermi distribution only -- other values of distrib
+  !> stay with the Fortran routine)
+  subroutine b200_Efilling(ctx, Ebs, Ef, TS, E0, filling, eigenvals, nElectrons, kT, kWeight, distrib)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(out) :: Ebs(:), Ef, TS(:), E0(:), filling(:,:,:)
+    real(dp), intent(in) :: eigenvals(:,:,:), nElectrons, kT, kWeight(:)
+    integer, intent(in) :: distrib
+    call check(ctx, dftbp_b200_efilling(ctx%h, Ebs, Ef, TS, E0, filling, eigenvals, size(eigenvals, dim=1),&
+        & size(eigenvals, dim=2), size(eigenvals, dim=3), nElectrons, kT, kWeight, int(distrib, c_int)))
+  end subroutine b200_Efilling
 
   !> mullikenPerBlock, dftb/populations.F90:306 -- qq(mOrb, mOrb, nAtom) accumulates
   subroutine b200_mullikenPerBlock(ctx, qq, over, rho)

@@ -281,6 +281,25 @@ int dftbp_b200_derivative_shift(dftbp_b200_ctx *ctx, double *deriv, const double
                                 const double *EDM, const double *shift, int diffType,
                                 double delta);
 
+/* ---- N4 (first piece): electron filling on the device ------------------------------------- */
+
+/* fillingTypes, dftb/etemp.F90:28-40 */
+enum { DFTBP_B200_FILLING_FERMI = 0, DFTBP_B200_FILLING_GAUSSIAN = 1, DFTBP_B200_FILLING_METHFESSEL = 2 };
+
+/* Efilling, dftb/etemp.F90:59-191 (caller getFillingsAndBandEnergies, dftbplus/main.F90:4597-4648; SURVEY
+ * 8(f) N4): common Fermi level Ef for nElectrons over eigenvals(nLevels, nKpt, nSpin) with k-point weights
+ * kWeight(nKpt) at thermal energy kT, fillings (one electron per level: the caller halves nElectrons and
+ * doubles the results for spin-unpolarised runs, as the reference does), band energy Ebs(nSpin), entropy
+ * term TS(nSpin), energy extrapolated to 0 K E0(nSpin).  Same control flow as the reference (mid-gap
+ * shortcut for integer electron numbers, bracket widening, bisection to elecTol, cut at elecTol, final
+ * rescaling); distrib = Fermi only (Gaussian / Methfessel-Paxton return DFTBP_B200_ENOTIMPL).  Sits between
+ * dftbp_b200_hegv_* and dftbp_b200_density_matrix_*: with device pointers the eigenvalues and fillings
+ * never leave the GPU.  "Fermi level search did not converge." is returned as DFTBP_B200_EINVAL when the
+ * small outputs are host pointers. */
+int dftbp_b200_efilling(dftbp_b200_ctx *ctx, double *Ebs, double *Ef, double *TS, double *E0,
+                        double *filling, const double *eigenvals, int nLevels, int nKpt, int nSpin,
+                        double nElectrons, double kT, const double *kWeight, int distrib);
+
 /* ---- not rewritten: dense generalized eigensolve via cuSOLVER ------------------------------- */
 
 /* diagDenseMtx, dftbplus/eigenvects.F90:85-100 (hegvd branch): H C = S C diag(eigen), lower
