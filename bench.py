@@ -456,8 +456,11 @@ def section_md(dev, stream, n_steps):
             hp.unpackHS(hscc[0], square=H)
             hp.unpackHS(over, square=S)
             hp.diagDenseMtx(H, S, eigen=eig)
+            # Efilling on the device (dftbp_b200_efilling): n_occ electrons over singly occupied levels, times
+            # two for the spin-unpolarised run (getFillingsAndBandEnergies, main.F90:4597-4648)
+            fill = hp.Efilling(eig, float(n_occ), kT)["filling"]
             with torch.cuda.stream(stream):
-                fill = fermi_fillings_device(eig, 2.0 * n_occ, kT)
+                fill.mul_(2.0)
             hp.getDensityMatrix(H, fill, dm=D)
             with torch.cuda.stream(stream):
                 rho.zero_()
