@@ -162,6 +162,12 @@ struct dftbp_b200_ctx {
   bool allSimple = false;     // no species has two shells of the same l (two-kernel pair build possible)
   double *pairExchange = nullptr;  // per work-list entry: interpolated integrals of H0 and S (k1_pair_build.cu)
   long long pairExchangeCap = 0;   // allocated doubles
+  // What the shift-structure kernel found in the PREVIOUS call with block shifts (pinned host int, written
+  // by an asynchronous copy at the end of that call: -1 unknown, 0 diagonal blocks, 1 full blocks).  Only a
+  // hint: the device flag of the current call decides; the hint picks which launches are queued (full blocks
+  // last time: also the dedicated full-block kernel, which is faster than the fallback inside the
+  // span-pipeline launch).
+  int *hShiftHint = nullptr;
   double *shiftDiag = nullptr;     // (mOrb, nAtom, nSpin): diagonals of the block shifts of the current call, compact
   long long shiftDiagCap = 0;
 

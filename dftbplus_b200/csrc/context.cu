@@ -78,6 +78,8 @@ int dftbp_b200_create(dftbp_b200_ctx **out, int device, int rank, int nRanks) {
   DFTBP_CUDA(ctx, cudaMalloc((void **)&ctx->dInfo, 16 * sizeof(int)));
   // [0] info / nLevels, [1] shift flag, [2..3] K3 tile counter, [4..5] K1 / [6..7] K5 / [8..9] K4 item schedulers
   DFTBP_CUDA(ctx, cudaMemset(ctx->dInfo, 0, 16 * sizeof(int)));
+  DFTBP_CUDA(ctx, cudaMallocHost((void **)&ctx->hShiftHint, sizeof(int)));
+  *ctx->hShiftHint = -1;
   return 0;
 }
 
@@ -93,6 +95,7 @@ int dftbp_b200_destroy(dftbp_b200_ctx *ctx) {
   cudaFree(ctx->dNOrbSpecies); cudaFree(ctx->dOrbShell); cudaFree(ctx->dProgs);
   cudaFree(ctx->pairExchange);
   cudaFree(ctx->shiftDiag);
+  if (ctx->hShiftHint) cudaFreeHost(ctx->hShiftHint);
   cudaFree(ctx->solverWork); cudaFree(ctx->dInfo);
   solverDestroy(ctx);
   for (TimedSpan &sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }

@@ -260,7 +260,8 @@ __global__ void __launch_bounds__(32 * flat::warpsFor(1 + NSPIN), 1)
                           double *__restrict__ negWS, const double *__restrict__ shift, int selfImages, int spanLo,
                           int spanHi) {
   if (__ldg(shiftFull) != 0) {  // full shift blocks (DFTB+U-like): per-pair matrix products along the schedule
-    forceWeightsSched<1, true>(p, EDM, shift, negWS, selfImages);
+    // selfImages bit 1: the dedicated full-block kernel has been queued as well and does this
+    if (!(selfImages & 2)) forceWeightsSched<1, true>(p, EDM, shift, negWS, selfImages & 1);
     return;
   }
   constexpr int NIN = 1 + NSPIN, WARPS = flat::warpsFor(NIN);
@@ -670,8 +671,13 @@ int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, c
                         wHi = shareBegin(g.nWorkLoad, ctx->pairPart + 1, ctx->pairParts);
         const int spanLo = ctx->loadInd[wLo] / flat::kSpan;
         const int spanHi = wHi > wLo ? (ctx->loadInd[wHi] + flat::kSpan - 1) / flat::kSpan : spanLo;
+        const bool fullLastTime = *ctx->hShiftHint == 1;
         DFTBP_TRY(launchWeightsFlat(ctx, nSpin, p, g.descLoad, g.nWorkLoad, g.groupFirstLoad, dEDM, dDiag, flag, (double *)scratch,
-                                    dShift, self, spanLo, spanHi));
+                                    dShift, self | (fullLastTime ? 2 : 0), spanLo, spanHi));
+        if (fullLastTime) {
+          k5_force_weights_sched<1, true><<<wGrid, 256, 0, ctx->stream>>>(p, dEDM, dShift, flag, (double *)scratch, self);
+          ctx->launches++;
+        }
         ctx->launches += 2;
       } else {
         if (nSpin == 1) k5_force_weights_diag<1><<<dGrid, 256, 0, ctx->stream>>>(p, g.descLoad, sched->slotOf, g.nWorkLoad, dEDM, dShift, flag, (double *)scratch, self);
@@ -681,6 +687,8 @@ int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, c
         ctx->launches += 3;
       }
       p.negWS = (const double *)scratch;
+      // hint for the next call (asynchronous; never waited for)
+      DFTBP_CUDA(ctx, cudaMemcpyAsync(ctx->hShiftHint, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     }
     p.pitch = (ctx->mOrb * ctx->mOrb) | 1;
     const size_t perWarp = sizeof(double) * 32 * (size_t)p.pitch;

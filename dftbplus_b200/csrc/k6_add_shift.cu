@@ -116,9 +116,9 @@ __global__ void __launch_bounds__(256) k6_add_shift(const K6Params p) {
 // elements of the sparse arrays whatever block they belong to.
 template <int MODE, int NSPIN, bool ZERO>
 __global__ void __launch_bounds__(32 * flat::warpsFor(ZERO ? 1 : 1 + NSPIN), 1)
-    k6_add_shift_flat(const K6Params p, const int *__restrict__ groupFirst) {
+    k6_add_shift_flat(const K6Params p, const int *__restrict__ groupFirst, int fullElsewhere) {
   if (MODE == 1 && __ldg(p.shiftFull) != 0) {  // full shift blocks: per-block matrix products, warp per block
-    addShiftBlocks<2, NSPIN, ZERO>(p);
+    if (!fullElsewhere) addShiftBlocks<2, NSPIN, ZERO>(p);  // (else: the dedicated kernel has been queued too)
     return;
   }
   constexpr int NIN = ZERO ? 1 : 1 + NSPIN, WARPS = flat::warpsFor(NIN);
@@ -170,22 +170,23 @@ __global__ void __launch_bounds__(32 * flat::warpsFor(ZERO ? 1 : 1 + NSPIN), 1)
 }
 
 template <int MODE, int NSPIN, bool ZERO>
-int launchFlatT(dftbp_b200_ctx *ctx, const K6Params &p, const int *groupFirst) {
+int launchFlatT(dftbp_b200_ctx *ctx, const K6Params &p, const int *groupFirst, int fullElsewhere) {
   constexpr int NIN = ZERO ? 1 : 1 + NSPIN, WARPS = flat::warpsFor(NIN);
   const size_t smemBytes = sizeof(flat::Smem<NIN, WARPS>);
   static LaunchInfo info;
   DFTBP_TRY(launchInfo(ctx, info, k6_add_shift_flat<MODE, NSPIN, ZERO>, 32 * WARPS, smemBytes, nullptr));
   const long long nSpans = ((long long)p.sparseSize + flat::kSpan - 1) / flat::kSpan;
   const int grid = (int)std::max<long long>(1, std::min<long long>((nSpans + WARPS - 1) / WARPS, ctx->smCount));
-  k6_add_shift_flat<MODE, NSPIN, ZERO><<<grid, 32 * WARPS, smemBytes, ctx->stream>>>(p, groupFirst);
+  k6_add_shift_flat<MODE, NSPIN, ZERO><<<grid, 32 * WARPS, smemBytes, ctx->stream>>>(p, groupFirst, fullElsewhere);
   return 0;
 }
 
 template <int MODE>
-int launchFlat(dftbp_b200_ctx *ctx, const K6Params &p, bool zero, const int *groupFirst) {
-  if (p.nSpin == 1) return zero ? launchFlatT<MODE, 1, true>(ctx, p, groupFirst) : launchFlatT<MODE, 1, false>(ctx, p, groupFirst);
-  if (p.nSpin == 2) return zero ? launchFlatT<MODE, 2, true>(ctx, p, groupFirst) : launchFlatT<MODE, 2, false>(ctx, p, groupFirst);
-  return zero ? launchFlatT<MODE, 4, true>(ctx, p, groupFirst) : launchFlatT<MODE, 4, false>(ctx, p, groupFirst);
+int launchFlat(dftbp_b200_ctx *ctx, const K6Params &p, bool zero, const int *groupFirst, int fullElsewhere = 0) {
+  const int fe = fullElsewhere;
+  if (p.nSpin == 1) return zero ? launchFlatT<MODE, 1, true>(ctx, p, groupFirst, fe) : launchFlatT<MODE, 1, false>(ctx, p, groupFirst, fe);
+  if (p.nSpin == 2) return zero ? launchFlatT<MODE, 2, true>(ctx, p, groupFirst, fe) : launchFlatT<MODE, 2, false>(ctx, p, groupFirst, fe);
+  return zero ? launchFlatT<MODE, 4, true>(ctx, p, groupFirst, fe) : launchFlatT<MODE, 4, false>(ctx, p, groupFirst, fe);
 }
 
 template <int MODE, bool ZERO>
@@ -247,7 +248,12 @@ int addShiftImpl(dftbp_b200_ctx *ctx, double *ham, const double *over, const dou
       // both forms are launched; the one that does not match the device flag returns at once
       if (useFlat) {
         // one launch: the kernel takes the full-block path itself when the device flag says so
-        DFTBP_TRY(launchFlat<1>(ctx, p, isInputZero != 0, groupFirst));
+        const bool fullLastTime = *ctx->hShiftHint == 1;
+        DFTBP_TRY(launchFlat<1>(ctx, p, isInputZero != 0, groupFirst, fullLastTime ? 1 : 0));
+        if (fullLastTime) {
+          launchMode<2>(p, isInputZero != 0, grid, ctx->stream);
+          ctx->launches++;
+        }
         ctx->launches += 2;
       } else {
         // both forms are launched; the one that does not match the device flag returns at once
@@ -255,6 +261,8 @@ int addShiftImpl(dftbp_b200_ctx *ctx, double *ham, const double *over, const dou
         launchMode<2>(p, isInputZero != 0, grid, ctx->stream);
         ctx->launches += 3;
       }
+      // hint for the next call (asynchronous; never waited for)
+      DFTBP_CUDA(ctx, cudaMemcpyAsync(ctx->hShiftHint, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     }
   }
   return finish(ctx);
