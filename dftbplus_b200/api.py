@@ -360,8 +360,9 @@ class HotPath:
 
     # ---- K5 ---------------------------------------------------------------------------------
     def set_pair_partition(self, part, n_parts):
-        """Subsequent derivative_shift / stress calls take the chunks part, part + n_parts, ... of the
-        pair schedule (dftbp_b200_set_pair_partition); the partial results add up to the full one."""
+        """Subsequent derivative_shift / stress calls take share `part` of n_parts of the pairs (a contiguous
+        range of the neighbour list, dftbp_b200_set_pair_partition); the partial results add up to the
+        full one, also when the shares are taken by different contexts / GPUs."""
         self._ck(self._L.dftbp_b200_set_pair_partition(self._h, int(part), int(n_parts)))
 
     def derivative_shift(self, dm, edm, shift=None, diff_type=1, delta=0.0, deriv=None):
