@@ -595,8 +595,10 @@ def main():
     stream.synchronize()
 
     def step_local():
-        # a new geometry every step: the coordinates are refreshed, so the device-side pair
-        # schedule (pair_sort.cu: histogram + scan, scatter) is rebuilt inside the timed region
+        # a new geometry every step: the coordinates are refreshed, so the device-side pair schedule
+        # (pair_sort.cu) is brought up to date inside the timed region -- its records are rewritten, and
+        # every 16th update it is sorted again (the CUDA-graph replay below contains the refresh form;
+        # the eager steps contain the mix)
         hp.update_coords(coords_dev)
         hp.buildH0S(sk.selfegy, ham, over)                               # K1 (all pairs)
         hp.derivative_shift(dm, edm, shift=shift, deriv=deriv)           # K5 (this rank's chunks)

@@ -81,7 +81,9 @@ struct SortedPairs {
   int2 *atoms = nullptr;   // per slot: (iAtom1, iAtom2f), 0-based (K5: where the gradient goes)
   int *total = nullptr;    // device scalar: padded length (multiple of 32)
   long long capacity = 0;  // allocated entries of items / recs / atoms
-  bool valid = false;      // false after set_geometry / update_coords
+  bool valid = false;      // false after set_geometry (new neighbour list) / a new pair partition
+  bool stale = false;      // update_coords: same pairs, new bond vectors -- the records must be refreshed
+  int refreshes = 0;       // refreshes since the last full sort
 };
 
 struct BlockDesc;  // block_desc.cuh
@@ -162,8 +164,9 @@ struct dftbp_b200_ctx {
   bool allSimple = false;     // no species has two shells of the same l (two-kernel pair build possible)
   double *pairExchange = nullptr;  // per work-list entry: interpolated integrals of H0 and S (k1_pair_build.cu)
   long long pairExchangeCap = 0;   // allocated doubles
-  // What the shift-structure kernel found in the PREVIOUS call with block shifts (pinned host int, written
-  // by an asynchronous copy at the end of that call: -1 unknown, 0 diagonal blocks, 1 full blocks).  Only a
+  // What the shift-structure kernel found in the PREVIOUS call with block shifts (pinned, mapped host int,
+  // written by one store of that call's span-pipeline kernel -- a copy on the stream cost ~8 us per call:
+  // -1 unknown, 0 diagonal blocks, 1 full blocks).  Only a
   // hint: the device flag of the current call decides; the hint picks which launches are queued (full blocks
   // last time: also the dedicated full-block kernel, which is faster than the fallback inside the
   // span-pipeline launch).

@@ -453,7 +453,9 @@ int dftbp_b200_update_coords(dftbp_b200_ctx *ctx, const double *coords) {
   DFTBP_CUDA(ctx, cudaMemcpyAsync(ctx->geo.coords, coords, sizeof(double) * 3 * ctx->geo.nAllAtom, kind,
                                   ctx->stream));
   if (kind == cudaMemcpyHostToDevice) DFTBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  ctx->sortMine.valid = ctx->sortLoad.valid = false;  // distance bins changed
+  // same pairs, new bond vectors: the records of the schedules are refreshed at their next use; the order
+  // (species pair, distance bin) stays until it has drifted too far (ensureSortedPairs)
+  ctx->sortMine.stale = ctx->sortLoad.stale = true;
   return 0;
 }
 

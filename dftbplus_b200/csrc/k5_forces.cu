@@ -258,7 +258,9 @@ __global__ void __launch_bounds__(32 * flat::warpsFor(1 + NSPIN), 1)
                           const int *__restrict__ groupFirst, const double *__restrict__ EDM,
                           const double *__restrict__ diag, const int *__restrict__ shiftFull,
                           double *__restrict__ negWS, const double *__restrict__ shift, int selfImages, int spanLo,
-                          int spanHi) {
+                          int spanHi, int *hint) {
+  // what this call found, for the launches of the next one (pinned host word, mapped: one posted store)
+  if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile int *>(hint) = __ldg(shiftFull) != 0 ? 1 : 0;
   if (__ldg(shiftFull) != 0) {  // full shift blocks (DFTB+U-like): per-pair matrix products along the schedule
     // selfImages bit 1: the dedicated full-block kernel has been queued as well and does this
     if (!(selfImages & 2)) forceWeightsSched<1, true>(p, EDM, shift, negWS, selfImages & 1);
@@ -587,7 +589,7 @@ int launchWeightsFlatT(dftbp_b200_ctx *ctx, const K5Params &p, const BlockDesc *
   const long long nSpans = std::max(0, spanHi - spanLo);
   const int grid = (int)std::max<long long>(1, std::min<long long>((nSpans + WARPS - 1) / WARPS, ctx->smCount));
   k5_force_weights_flat<NSPIN><<<grid, 32 * WARPS, smemBytes, ctx->stream>>>(p, desc, nWork, groupFirst, EDM, diag, flag,
-                                                                            negWS, shift, selfImages, spanLo, spanHi);
+                                                                            negWS, shift, selfImages, spanLo, spanHi, ctx->hShiftHint);
   return 0;
 }
 
@@ -687,8 +689,6 @@ int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, c
         ctx->launches += 3;
       }
       p.negWS = (const double *)scratch;
-      // hint for the next call (asynchronous; never waited for)
-      DFTBP_CUDA(ctx, cudaMemcpyAsync(ctx->hShiftHint, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     }
     p.pitch = (ctx->mOrb * ctx->mOrb) | 1;
     const size_t perWarp = sizeof(double) * 32 * (size_t)p.pitch;

@@ -116,7 +116,10 @@ __global__ void __launch_bounds__(256) k6_add_shift(const K6Params p) {
 // elements of the sparse arrays whatever block they belong to.
 template <int MODE, int NSPIN, bool ZERO>
 __global__ void __launch_bounds__(32 * flat::warpsFor(ZERO ? 1 : 1 + NSPIN), 1)
-    k6_add_shift_flat(const K6Params p, const int *__restrict__ groupFirst, int fullElsewhere) {
+    k6_add_shift_flat(const K6Params p, const int *__restrict__ groupFirst, int fullElsewhere, int *hint) {
+  // what this call found, for the launches of the next one (pinned host word, mapped: one posted store)
+  if (MODE == 1 && blockIdx.x == 0 && threadIdx.x == 0)
+    *reinterpret_cast<volatile int *>(hint) = __ldg(p.shiftFull) != 0 ? 1 : 0;
   if (MODE == 1 && __ldg(p.shiftFull) != 0) {  // full shift blocks: per-block matrix products, warp per block
     if (!fullElsewhere) addShiftBlocks<2, NSPIN, ZERO>(p);  // (else: the dedicated kernel has been queued too)
     return;
@@ -177,7 +180,7 @@ int launchFlatT(dftbp_b200_ctx *ctx, const K6Params &p, const int *groupFirst, i
   DFTBP_TRY(launchInfo(ctx, info, k6_add_shift_flat<MODE, NSPIN, ZERO>, 32 * WARPS, smemBytes, nullptr));
   const long long nSpans = ((long long)p.sparseSize + flat::kSpan - 1) / flat::kSpan;
   const int grid = (int)std::max<long long>(1, std::min<long long>((nSpans + WARPS - 1) / WARPS, ctx->smCount));
-  k6_add_shift_flat<MODE, NSPIN, ZERO><<<grid, 32 * WARPS, smemBytes, ctx->stream>>>(p, groupFirst, fullElsewhere);
+  k6_add_shift_flat<MODE, NSPIN, ZERO><<<grid, 32 * WARPS, smemBytes, ctx->stream>>>(p, groupFirst, fullElsewhere, ctx->hShiftHint);
   return 0;
 }
 
@@ -261,8 +264,6 @@ int addShiftImpl(dftbp_b200_ctx *ctx, double *ham, const double *over, const dou
         launchMode<2>(p, isInputZero != 0, grid, ctx->stream);
         ctx->launches += 3;
       }
-      // hint for the next call (asynchronous; never waited for)
-      DFTBP_CUDA(ctx, cudaMemcpyAsync(ctx->hShiftHint, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     }
   }
   return finish(ctx);

@@ -194,6 +194,31 @@ __global__ void __launch_bounds__(kSortThreads) ps_scatter(const int *__restrict
   }
 }
 
+// New coordinates on an unchanged neighbour list (dftbp_b200_update_coords): the pairs, their species
+// pairs and their sparse offsets are the same, only the bond vectors change.  The order of the schedule
+// (species pair: still exact; distance bin: a locality heuristic of the table windows) is kept and the
+// records are rewritten in place, both in work-list order and at the slot of every pair.
+__global__ void __launch_bounds__(256) ps_refresh(const int *__restrict__ work, long long nWork, int ld, int nSpecies,
+                                                  const double *__restrict__ coords, const int *__restrict__ species,
+                                                  const int *__restrict__ iNeighbour, const int *__restrict__ iPair,
+                                                  const int *__restrict__ slotOf, PairRec *__restrict__ recsMem,
+                                                  PairRec *__restrict__ recs) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nWork; i += (long long)gridDim.x * blockDim.x) {
+    PairRec r;
+    pairKey(__ldg(work + i), ld, nSpecies, 1, 0.0, coords, species, iNeighbour, iPair, r);
+    int4 *m = reinterpret_cast<int4 *>(recsMem + i);
+    const int4 lo = *reinterpret_cast<const int4 *>(&r), hi = *(reinterpret_cast<const int4 *>(&r) + 1);
+    m[0] = lo;
+    m[1] = hi;
+    const int slot = __ldg(slotOf + i);
+    if (slot >= 0) {
+      int4 *d = reinterpret_cast<int4 *>(recs + slot);
+      d[0] = lo;
+      d[1] = hi;
+    }
+  }
+}
+
 template <class T>
 int growTo(dftbp_b200_ctx *ctx, T **p, long long *cap, long long need) {
   if (*cap >= need) return 0;
@@ -237,7 +262,24 @@ int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out
   const long long nWorkAllOfList = (forLoad && !shared) ? g.nWorkLoad : g.nWorkMine;
   const long long shareLo = shareBegin(nWorkAllOfList, part, nParts), shareHi = shareBegin(nWorkAllOfList, part + 1, nParts);
   *out = &sp;
-  if (sp.valid) return 0;
+  if (sp.valid && !sp.stale) return 0;
+  // kRefreshes updates of the coordinates reuse the order: at MD-sized displacements (~0.01 bohr per step)
+  // the relative distances move by a few table rows in that time, well inside the shared-memory window of
+  // k1_interp; chunks that outgrow it take the global-memory path (slower, same result) until the next sort
+  constexpr int kRefreshes = 16;
+  if (sp.valid && sp.stale && sp.refreshes < kRefreshes && tuneInt("DFTBP_B200_SORT_REFRESH", 1) != 0) {
+    const int *workR = (forLoad && !shared) ? g.workLoad : g.workMine;
+    const long long nWorkR = (forLoad && !shared) ? g.nWorkLoad : g.nWorkMine;
+    if (nWorkR > 0) {
+      const int grid = (int)std::max<long long>(1, std::min<long long>((nWorkR + 255) / 256, (long long)ctx->smCount * 8));
+      ps_refresh<<<grid, 256, 0, ctx->stream>>>(workR, nWorkR, g.mNeigh + 1, ctx->nSpecies, g.coords, g.species,
+                                                g.iNeighbour, g.iPair, sp.slotOf, sp.recsMem, sp.recs);
+      ctx->launches++;
+    }
+    sp.stale = false;
+    sp.refreshes++;
+    return 0;
+  }
   const int *work = (forLoad && !shared) ? g.workLoad : g.workMine;
   const long long nWork = (forLoad && !shared) ? g.nWorkLoad : g.nWorkMine;
   const int nBuckets = ctx->nSpecies * ctx->nSpecies;
@@ -285,6 +327,8 @@ int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out
     DFTBP_CUDA(ctx, cudaMemsetAsync(sp.total, 0, sizeof(int), ctx->stream));
   }
   sp.valid = true;
+  sp.stale = false;
+  sp.refreshes = 0;
   return 0;
 }
 

@@ -368,6 +368,48 @@ def test_md_like_coordinate_updates(name):
         hp.close()
 
 
+def test_many_coordinate_updates_refresh_and_resort():
+    """update_coords on an unchanged neighbour list refreshes the records of the pair schedule instead of
+    sorting again; the distance order drifts with the atoms until the library sorts again (every 16
+    refreshes).  40 steps of a random walk that ends 0.4 bohr away from the start, checked
+    against the oracle along the way and with SCC forces of a share of the pairs at the end."""
+    from dftbplus_b200.api import HotPath
+    w, sk, geo, model, selfegy = case("fec128")
+    rng = np.random.default_rng(29)
+    hp = HotPath(0)
+    try:
+        sk.upload(hp)
+        hp.set_geometry(geo)
+        s0 = oracle.build_s(model, geo)
+        dm = s0 * rng.normal(size=(2, geo["sparseSize"]))
+        edm = s0 * rng.normal(size=geo["sparseSize"])
+        mo, nA = hp.mOrb, geo["nAtom"]
+        shift = np.zeros((2, nA, mo, mo))
+        shift[:, :, np.arange(mo), np.arange(mo)] = 0.05 * rng.normal(size=(2, nA, mo))
+        coords = geo["coords"].copy()
+        drift = 0.01 * rng.normal(size=(nA, 3))
+        for step in range(40):
+            coords = coords + (drift + 0.004 * rng.normal(size=(nA, 3)))[geo["img2CentCell"] - 1]
+            g = dict(geo)
+            g["coords"] = np.ascontiguousarray(coords)
+            hp.update_coords(g["coords"])
+            h, s = hp.buildH0S(sk.selfegy)
+            if step % 8 == 7 or step >= 37:
+                assert_sparse_close(h, oracle.build_h0(model, g, selfegy), what="H0 step %d" % step)
+                assert_sparse_close(s, oracle.build_s(model, g), what="S step %d" % step)
+                d = hp.derivative_shift(dm, edm, shift=shift)
+                assert np.abs(d - oracle.derivative_shift(model, g, dm, edm, shift=shift)).max() < TOL_FORCE, step
+        acc = np.zeros_like(d)
+        for part in range(3):
+            hp.set_pair_partition(part, 3)
+            hp.update_coords(g["coords"])
+            acc += hp.derivative_shift(dm, edm, shift=shift)
+        hp.set_pair_partition(0, 1)
+        assert np.abs(acc - oracle.derivative_shift(model, g, dm, edm, shift=shift)).max() < TOL_FORCE
+    finally:
+        hp.close()
+
+
 def test_hegv_cusolver(hp_cache):
     w, sk, geo, model, selfegy, H, S, eig, C, f = _eig_case("ce_o")
     hp = hp_cache("ce_o")
