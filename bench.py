@@ -65,7 +65,9 @@ def config_for(workload_name, geo, n_spin, flush=False):
     return {"workload": workload_name, "nAtom": int(geo["nAtom"]), "nOrb": int(geo["nOrb"]),
             "pairs": int(geo["nNeighbourSK"].sum()), "sparseSize": ss, "n_spin": int(n_spin),
             "sk_tables": "synthetic .skf, 0.02 bohr x 500",
-            "step": "pair schedule + buildH0 + buildS + derivative_shift(SCC, %d spins, diagonal shift blocks)" % n_spin,
+            "step": "new coordinates on an unchanged neighbour list + buildH0 + buildS + derivative_shift(SCC, %d spins, "
+                    "diagonal shift blocks); GPU arm: the device-side pair schedule is refreshed per step and sorted "
+                    "again every 16th update" % n_spin,
             "l2": ("flushed between timed steps (256 MB memset)" if flush else
                    "no explicit flush: every step streams %.0f MB (H0 + S out, rho / Erho / -wS in and out) through the "
                    "126 MB L2, each array larger than what is left of it at its next use" % stream_mb)}
