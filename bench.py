@@ -499,6 +499,7 @@ def section_md(dev, stream, n_steps):
         hp.getEDensityMatrix(H, fill, eig, dm=D)
         hp.packHS(erho, D)
         hp.derivative_shift(rho.unsqueeze(0), erho, shift=shift, deriv=deriv)
+        stream.synchronize()             # deriv is written on the library's stream
         f = -deriv.cpu().numpy()
         t4 = time.perf_counter()
         t_list += t1 - t0; t_build += t2 - t1; t_scc += t3 - t2; t_force += t4 - t3
