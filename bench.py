@@ -1046,8 +1046,12 @@ def main():
         # (tools/eig_fullsize.py says why): replicas only -- every GPU of a (k,spin) group would run it
         if rank == 0 and not a.no_eigensolve:
             try:
+                # torchrun exports OMP_NUM_THREADS=1; cuSOLVER's divide and conquer has a host-side part that then
+                # runs three times slower (63 s instead of 20 s at n = 31744): give the child this rank's share of the cores
+                env = dict(os.environ)
+                env["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or world) // world))
                 r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "eig_fullsize.py"), a.workload, str(local)],
-                                   capture_output=True, text=True, timeout=600)
+                                   capture_output=True, text=True, timeout=600, env=env)
                 last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
                 if r.returncode == 0 and last:
                     eg = json.loads(last[-1])
