@@ -35,10 +35,23 @@ def make_slako_set(names, directory=None, n_grid=500, dist=0.02, seed=20250101, 
     shells = [SPECIES[n][0] for n in names]
     marker = os.path.join(directory, ".complete")
     if not os.path.exists(marker):
-        slako.write_synthetic_set(directory, names, shells, [SPECIES[n][1] for n in names],
+        # several ranks of a torchrun job may get here at once: every process writes its own private copy and
+        # renames it into place; whoever loses the race throws its copy away (rename of a directory is atomic)
+        import shutil
+        tmp = "%s.tmp.%d" % (directory.rstrip(os.sep), os.getpid())
+        shutil.rmtree(tmp, ignore_errors=True)
+        os.makedirs(os.path.dirname(directory.rstrip(os.sep)) or ".", exist_ok=True)
+        slako.write_synthetic_set(tmp, names, shells, [SPECIES[n][1] for n in names],
                                   [SPECIES[n][2] for n in names], [SPECIES[n][3] for n in names],
                                   [SPECIES[n][4] for n in names], dist=dist, n_grid=n_grid, seed=seed)
-        open(marker, "w").close()
+        open(os.path.join(tmp, ".complete"), "w").close()
+        try:
+            os.rename(tmp, directory)
+        except OSError:
+            if os.path.exists(marker):
+                shutil.rmtree(tmp, ignore_errors=True)      # another process was first
+            else:
+                directory = tmp     # an incomplete directory of an interrupted run is in the way: use the private copy
     return slako.SlakoSet(directory, names, shells, method=method), directory
 
 
