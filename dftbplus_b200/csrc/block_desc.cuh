@@ -25,6 +25,35 @@ struct __align__(16) BlockDesc {
 };
 static_assert(sizeof(BlockDesc) == 32, "BlockDesc must be two 16-byte words");
 
+// Sparse elements [*eLo, *eHi) covered by the entries [wLo, wHi) of the load work list (a share of the
+// pairs, set_pair_partition).  Host-built geometries keep the offsets in ctx->loadInd; a geometry whose
+// descriptors were built on the device (adopt_neighbour_list) reads the two offsets from descLoad, once
+// per (geometry, share).
+inline int loadElementRange(dftbp_b200_ctx *ctx, long long wLo, long long wHi, int *eLo, int *eHi) {
+  const Geometry &g = ctx->geo;
+  if ((long long)ctx->loadInd.size() == g.nWorkLoad + 1) {
+    *eLo = ctx->loadInd[wLo];
+    *eHi = ctx->loadInd[wHi];
+    return 0;
+  }
+  if (ctx->rangeLo != wLo || ctx->rangeHi != wHi) {
+    auto offsetOf = [&](long long w, int *out) -> int {
+      if (w <= 0) { *out = 0; return 0; }
+      if (w >= g.nWorkLoad) { *out = g.sparseSize; return 0; }
+      DFTBP_CUDA(ctx, cudaMemcpyAsync(out, &g.descLoad[w].ind, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      DFTBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      return 0;
+    };
+    DFTBP_TRY(offsetOf(wLo, &ctx->rangeELo));
+    DFTBP_TRY(offsetOf(wHi, &ctx->rangeEHi));
+    ctx->rangeLo = wLo;
+    ctx->rangeHi = wHi;
+  }
+  *eLo = ctx->rangeELo;
+  *eHi = ctx->rangeEHi;
+  return 0;
+}
+
 #ifdef __CUDACC__
 // f(const BlockDesc &) is called by all 32 lanes of a warp for every block of the list, in list
 // order inside chunks of kBlocksPerChunk consecutive blocks; chunks go round-robin over the warps

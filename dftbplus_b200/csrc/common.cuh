@@ -157,6 +157,10 @@ struct dftbp_b200_ctx {
   int pairPart = 0, pairParts = 1;              // share of the pair schedule the force calls take (set_pair_partition)
   std::vector<long long> blockStartOfAtom;      // first entry of every atom in workAll / descAll (nAtom + 1)
   std::vector<int> loadInd;                     // sparse offset of every entry of descLoad, then the end of the last one
+                                                // (empty for a geometry whose descriptors were built on the device:
+                                                // loadElementRange reads the two offsets it needs from descLoad)
+  long long rangeLo = -1, rangeHi = -1;         // cache of loadElementRange: work-list range ...
+  int rangeELo = 0, rangeEHi = 0;               // ... and the sparse elements it covers
   int smCount = 148;
   size_t smemOptin = 232448;  // max dynamic shared memory per CTA
   size_t smemPerSm = 233472;
@@ -492,5 +496,7 @@ int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out
 void freeSortedPairs(dftbp_b200_ctx *ctx);
 void solverDestroy(dftbp_b200_ctx *ctx);
 void freeNeighbourList(dftbp_b200_ctx *ctx);
+// give the arrays of the current geometry back to the block pool (context.cu)
+void releaseGeometry(dftbp_b200_ctx *ctx);
 
 }  // namespace dftbp_b200

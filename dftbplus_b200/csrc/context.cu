@@ -443,6 +443,7 @@ int dftbp_b200_set_geometry(dftbp_b200_ctx *ctx, int nAtom, int nAllAtom, int mN
   }
   ctx->geo = g;
   ctx->sortMine.valid = ctx->sortLoad.valid = false;
+  ctx->rangeLo = ctx->rangeHi = -1;
   return 0;
 }
 
@@ -462,6 +463,8 @@ int dftbp_b200_update_coords(dftbp_b200_ctx *ctx, const double *coords) {
 }  // extern "C"
 
 namespace dftbp_b200 {
+void releaseGeometry(dftbp_b200_ctx *ctx) { freeGeometry(ctx, ctx->geo); }
+
 // (re-)upload the species-pair programs after tables changed
 int syncPrograms(dftbp_b200_ctx *ctx) {
   if (!ctx->progsDirty) return 0;

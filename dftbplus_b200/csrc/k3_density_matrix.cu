@@ -176,6 +176,151 @@ k3_dm_real(const double *__restrict__ C, int ldc, const double *__restrict__ wgt
 }
 
 // ------------------------------------------------------------------------------------------------
+// real, TMA-fed: the same tile walk and fragment layout as k3_dm_real, but the operand panels come in
+// through the bulk-copy (TMA) engine and the k loop has no CTA-wide barrier.  One producer warp asks
+// for the BK columns of the A and the B panel of a stage with one cp.async.bulk per column (BM rows =
+// 512 bytes each, landing at the padded pitch that keeps the fragment loads conflict free -- a
+// tensor-map box would be dense in shared memory and 4-way conflicted, so the copies are the
+// non-tensor form); their bytes complete the stage's `full` mbarrier.  The consumer warps wait on
+// `full`, issue their DMMAs and arrive on the stage's `empty` mbarrier, which is all the producer waits
+// for before it reuses the stage: the warps of a CTA drift apart by up to STAGES k-tiles instead of
+// meeting at a __syncthreads every 16 levels.  Diagonal tiles load one panel only.
+// Needs 16-byte aligned columns: even ld, even n, aligned base (else k3_dm_real).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned k3SmemAddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void k3MbarWait(unsigned bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+template <int BM, int BK, int STAGES, int WARPS_M, int WARPS_N>
+__global__ void __launch_bounds__(32 * (WARPS_M * WARPS_N + 1))
+k3_dm_real_tma(const double *__restrict__ C, int ldc, const double *__restrict__ wgt, int n,
+               const int *__restrict__ nLevels, double *__restrict__ dm, int ldd, TileOrder order,
+               unsigned long long *tileCounter) {
+  static_assert(BK <= 16, "one lane of the producer warp per (panel, column)");
+  const int K = *nLevels;
+  constexpr int NCW = WARPS_M * WARPS_N;  // consumer warps; warp NCW is the producer
+  constexpr int PITCH = BM + 4;
+  constexpr int WM = BM / WARPS_M, WN = BM / WARPS_N;
+  constexpr int MI = WM / 8, NI = WN / 8;
+  extern __shared__ __align__(16) double smem[];
+  double *As = smem;                      // [STAGES][BK][PITCH]
+  double *Bs = As + STAGES * BK * PITCH;  // [STAGES][BK][PITCH]
+  double *Ws = Bs + STAGES * BK * PITCH;  // [STAGES][BK]
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(Ws + STAGES * BK);  // full[STAGES], empty[STAGES]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nK = (K + BK - 1) / BK;
+  const long long nIdx = (long long)order.nSB * (order.nSB + 1) / 2 * order.G * order.G;
+  const unsigned fullBar = k3SmemAddr(bars), emptyBar = k3SmemAddr(bars + STAGES);
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fullBar + 8u * s) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(emptyBar + 8u * s), "r"(NCW) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __shared__ long long nextSlot;
+  unsigned it = 0;  // k-tiles handled so far by this CTA (all warps count alike): stage = it % STAGES
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) nextSlot = atomicAdd(tileCounter, 1ULL);
+    __syncthreads();
+    const long long idx = nextSlot;
+    if (idx >= nIdx) break;
+    int ti, tj;
+    if (!tileAt(order, idx, &ti, &tj)) continue;
+    const int i0 = ti * BM, j0 = tj * BM;
+    const bool diag = ti == tj;
+
+    if (warp == NCW) {
+      // ---------------- producer ----------------
+      const unsigned rowsA = 8u * (unsigned)min(BM, n - i0), rowsB = diag ? 0u : 8u * (unsigned)min(BM, n - j0);
+      const unsigned bytes = (unsigned)BK * (rowsA + rowsB);
+      const bool isB = lane >= 16;
+      const int col = lane & 15;
+      const unsigned myBytes = isB ? rowsB : rowsA;
+      const double *base = C + (isB ? j0 : i0);
+      const unsigned dst0 = k3SmemAddr(isB ? Bs : As) + 8u * (unsigned)(col * PITCH);
+      for (int kt = 0; kt < nK; ++kt, ++it) {
+        const unsigned st = it % STAGES;
+        if (it >= (unsigned)STAGES) k3MbarWait(emptyBar + 8u * st, ((it / STAGES) & 1u) ^ 1u);
+        const int k = kt * BK + col;
+        // levels behind the last one: a valid column with weight zero
+        if (lane < BK) Ws[st * BK + lane] = k < K ? __ldg(wgt + k) : 0.0;
+        __syncwarp();
+        const unsigned bar = fullBar + 8u * st;
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        __syncwarp();
+        if (col < BK && myBytes > 0)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           dst0 + 8u * (unsigned)(st * BK * PITCH)),
+                       "l"(base + (size_t)ldc * (size_t)min(k, K - 1)), "r"(myBytes), "r"(bar)
+                       : "memory");
+      }
+    } else {
+      // ---------------- consumers ----------------
+      const int wm = warp % WARPS_M, wn = warp / WARPS_M;
+      const int fk = lane & 3, fmn = lane >> 2;
+      double acc[MI][NI][2];
+#pragma unroll
+      for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      const double *bPanel = diag ? As : Bs;
+      for (int kt = 0; kt < nK; ++kt, ++it) {
+        const unsigned st = it % STAGES;
+        k3MbarWait(fullBar + 8u * st, (it / STAGES) & 1u);
+        const double *a_s = As + st * BK * PITCH + wm * WM + fmn;
+        const double *b_s = bPanel + st * BK * PITCH + wn * WN + fmn;
+        const double *w_s = Ws + st * BK;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+          const int kr = kk * 4 + fk;
+          const double wk = w_s[kr];
+          double a[MI], b[NI];
+#pragma unroll
+          for (int mi = 0; mi < MI; ++mi) a[mi] = a_s[kr * PITCH + mi * 8];
+#pragma unroll
+          for (int ni = 0; ni < NI; ++ni) b[ni] = b_s[kr * PITCH + ni * 8] * wk;
+#pragma unroll
+          for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(emptyBar + 8u * st) : "memory");
+      }
+#pragma unroll
+      for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) {
+          const int i = i0 + wm * WM + mi * 8 + fmn;
+          const int j = j0 + wn * WN + ni * 8 + 2 * fk;
+          if (i < n) {
+            if (j < n && i >= j) dm[(size_t)i + (size_t)ldd * j] = acc[mi][ni][0];
+            if (j + 1 < n && i >= j + 1) dm[(size_t)i + (size_t)ldd * (j + 1)] = acc[mi][ni][1];
+          }
+        }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // complex:  dm(i,j) = sum_k w_k C(i,k) conj(C(j,k)),  i >= j, imag(diag) = 0 (as xHERK)
 //   re += ar*(w br) + ai*(w bi);  im += ai*(w br) + ar*(-w bi)
 // ------------------------------------------------------------------------------------------------
@@ -333,6 +478,19 @@ int launchReal(dftbp_b200_ctx *ctx, int ctasPerSm, const double *dC, int ld, con
   return 0;
 }
 
+template <int BM, int BK, int ST, int WMn, int WNn>
+int launchRealTma(dftbp_b200_ctx *ctx, int ctasPerSm, const double *dC, int ld, const double *dW, int n,
+                  const int *K, double *dDm, unsigned long long *counter) {
+  const size_t smemB = sizeof(double) * (2 * ST * BK * (BM + 4) + ST * BK) + sizeof(unsigned long long) * 2 * ST;
+  const TileOrder o = makeOrder(n, BM, ctx->dmColFirst, ctx->dmColLast);
+  const long long nTiles = (long long)o.nT * (o.nT + 1) / 2;
+  const int grid = (int)std::min<long long>(nTiles, (long long)ctasPerSm * ctx->smCount);
+  auto kern = k3_dm_real_tma<BM, BK, ST, WMn, WNn>;
+  DFTBP_TRY(setSmem(ctx, kern, smemB));
+  kern<<<grid, 32 * (WMn * WNn + 1), smemB, ctx->stream>>>(dC, ld, dW, n, K, dDm, ld, o, counter);
+  return 0;
+}
+
 int densityImpl(dftbp_b200_ctx *ctx, void *dm, const void *eigvecs, int n, int ld, const double *filling,
                 const double *weights, bool cplx, int colFirst = 1, int colLast = 0) {
   if (!ctx) return DFTBP_B200_EINVAL;
@@ -363,7 +521,21 @@ int densityImpl(dftbp_b200_ctx *ctx, void *dm, const void *eigvecs, int n, int l
     // tuning hook (development only): DFTBP_B200_K3_VARIANT selects a tile configuration
     const char *env = getenv("DFTBP_B200_K3_VARIANT");
     const int variant = env ? atoi(env) : 0;
-    if (n < 1024) {
+    // TMA-fed kernel: 16-byte aligned columns of C (bulk copies) -- even ld, even n, aligned base
+    const bool tmaOk = aligned && n % 2 == 0;
+    if (tmaOk && (variant == 0 || variant >= 30)) {
+      if (variant == 31) {
+        DFTBP_TRY((launchRealTma<64, 16, 3, 2, 2>(ctx, 4, dC, ld, dW, n, K, dDm, counter)));
+      } else if (variant == 32) {
+        DFTBP_TRY((launchRealTma<128, 16, 4, 2, 4>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
+      } else if (variant == 33) {
+        DFTBP_TRY((launchRealTma<64, 16, 6, 2, 2>(ctx, 2, dC, ld, dW, n, K, dDm, counter)));
+      } else if (variant == 34) {
+        DFTBP_TRY((launchRealTma<128, 8, 6, 4, 2>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
+      } else {
+        DFTBP_TRY((launchRealTma<64, 16, 4, 2, 2>(ctx, 3, dC, ld, dW, n, K, dDm, counter)));
+      }
+    } else if (n < 1024) {
       DFTBP_TRY((launchReal<64, 16, 3, 2, 2, 1>(ctx, 2, dC, ld, dW, n, K, dDm, counter)));
     } else if (!aligned) {
       DFTBP_TRY((launchReal<128, 16, 4, 2, 4, 1>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));

@@ -664,15 +664,18 @@ int forcesImpl(dftbp_b200_ctx *ctx, double *deriv, double *st, double cellVol, c
       const int dGrid = gridFor(ctx, (g.nWorkLoad + kBlocksPerChunk - 1) / kBlocksPerChunk, 8, 4);
       // one partition and a sorted list of not too small blocks: the TMA span pipeline (flat_stream.cuh)
       const bool useFlat = g.groupFirstLoad != nullptr && (long long)ctx->mOrb * g.nAtom * nSpin < (1LL << 31) &&
-                           (long long)ctx->loadInd.size() == g.nWorkLoad + 1 && tuneInt("DFTBP_B200_K5_FLAT", 1) != 0;
+                           ((long long)ctx->loadInd.size() == g.nWorkLoad + 1 || (ctx->loadInd.empty() && g.coversAll)) &&
+                           tuneInt("DFTBP_B200_K5_FLAT", 1) != 0;
       if (useFlat) {
         // one launch: the kernel takes the full-block path itself when the device flag says so.  A share
         // of the pairs (set_pair_partition) is a contiguous range of the work list = of the sparse arrays:
         // only the spans it touches are streamed.
         const long long wLo = shareBegin(g.nWorkLoad, ctx->pairPart, ctx->pairParts),
                         wHi = shareBegin(g.nWorkLoad, ctx->pairPart + 1, ctx->pairParts);
-        const int spanLo = ctx->loadInd[wLo] / flat::kSpan;
-        const int spanHi = wHi > wLo ? (ctx->loadInd[wHi] + flat::kSpan - 1) / flat::kSpan : spanLo;
+        int eLo, eHi;
+        DFTBP_TRY(loadElementRange(ctx, wLo, wHi, &eLo, &eHi));
+        const int spanLo = eLo / flat::kSpan;
+        const int spanHi = wHi > wLo ? (eHi + flat::kSpan - 1) / flat::kSpan : spanLo;
         const bool fullLastTime = *ctx->hShiftHint == 1;
         DFTBP_TRY(launchWeightsFlat(ctx, nSpin, p, g.descLoad, g.nWorkLoad, g.groupFirstLoad, dEDM, dDiag, flag, (double *)scratch,
                                     dShift, self | (fullLastTime ? 2 : 0), spanLo, spanHi));

@@ -264,5 +264,33 @@ int updateNeighbourList(Backend &be, NeighbourList &nb, int nAtom, const double 
   return 0;
 }
 
+
+// Work list / block descriptors of a list for adopt_neighbour_list, in two steps because the caller
+// sizes the arrays of the second from the result of the first:
+//   countBlocks:     blockStart(nAtom + 1) on the device and, read back, on the host (hBlockStart)
+//   describeBlocks:  workAll(nBlocks), desc(nBlocks), groupFirst(nGroups), flags[0] = hasDuplicates
+template <class Backend>
+int countBlocks(Backend &be, const NeighbourList &L, int *cnt, int *blockStart, int *hBlockStart) {
+  NL_TRY(be.launch(geo_block_count, (long long)L.nAtom + 1, L.nAtom, (const int *)L.nNeighbourSK.p, cnt));
+  NL_TRY(be.scan(cnt, blockStart, (long long)L.nAtom + 1));
+  NL_TRY(be.download(hBlockStart, blockStart, sizeof(int) * ((size_t)L.nAtom + 1)));
+  return 0;
+}
+
+template <class Backend>
+int describeBlocks(Backend &be, const NeighbourList &L, const int *blockStart, int nBlocks, int groupSize,
+                   int *workAll, GeoDesc *desc, int *groupFirst, int *flags, int *hFlags) {
+  const int ld = L.mNeigh + 1;
+  const int nGroups = (int)(((long long)L.sparseSize + groupSize - 1) / groupSize);
+  NL_TRY(be.fill(flags, 0, sizeof(int)));
+  NL_TRY(be.fill(groupFirst, 0, sizeof(int) * (size_t)nGroups));
+  NL_TRY(be.launch(geo_describe, (long long)ld * L.nAtom, L.nAtom, ld, (const int *)L.nNeighbourSK.p, blockStart,
+                   (const int *)L.iNeighbour.p, (const int *)L.img2CentCell.p, (const int *)L.iCellVec.p,
+                   (const int *)L.iPair.p, (const int *)L.iAtomStart.p, workAll, desc, flags));
+  NL_TRY(be.launch(geo_group_index, nBlocks, nBlocks, nGroups, groupSize, (const GeoDesc *)desc, groupFirst));
+  NL_TRY(be.download(hFlags, flags, sizeof(int)));
+  return 0;
+}
+
 }  // namespace nl
 }  // namespace dftbp_b200

@@ -460,5 +460,67 @@ NL_KERNEL void nl_ipair(int nAtom, int ld, const int *__restrict__ nNeighbourSK,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Work list and block descriptors of the adopted geometry, built on the device (what set_geometry
+// builds on the host from a read-back of the index arrays): one entry per sparse block (iNeigh =
+// 0 .. nNeighbourSK(iAtom), iAtom) in the order of the sparse arrays.
+// ------------------------------------------------------------------------------------------------
+
+// layout of BlockDesc (block_desc.cuh; the .cu that launches these kernels asserts the match)
+struct GeoDesc {
+  int ind, ii, jj, n12, iAt1, iAt2f, iVec, iNeigh;
+};
+
+// cnt[a] = blocks of atom a (on-site block + nNeighbourSK), cnt[nAtom] = 0: its exclusive scan is the
+// first work-list entry of every atom and, at [nAtom], the number of blocks
+NL_KERNEL void geo_block_count(int nAtom, const int *__restrict__ nNeighbourSK, int *__restrict__ cnt) {
+  for (long long a = NL_TID; a <= nAtom; a += NL_STRIDE) cnt[a] = a < nAtom ? nNeighbourSK[a] + 1 : 0;
+}
+
+// one thread per entry (iNeigh, iAtom) of the neighbour rows.  hasDuplicates: two blocks of one atom
+// fold onto the same dense block (an image of the atom itself, or two images of one neighbour)
+NL_KERNEL void geo_describe(int nAtom, int ld, const int *__restrict__ nNeighbourSK,
+                            const int *__restrict__ blockStart, const int *__restrict__ iNeighbour,
+                            const int *__restrict__ img2CentCell, const int *__restrict__ iCellVec,
+                            const int *__restrict__ iPair, const int *__restrict__ iAtomStart,
+                            int *__restrict__ workAll, GeoDesc *__restrict__ desc, int *__restrict__ hasDuplicates) {
+  const long long n = (long long)ld * nAtom;
+  for (long long t = NL_TID; t < n; t += NL_STRIDE) {
+    const int i = (int)(t / ld), k = (int)(t - (long long)i * ld);
+    if (k > nNeighbourSK[i]) continue;
+    const int w = blockStart[i] + k;
+    const int a2 = iNeighbour[t] - 1, f = img2CentCell[a2] - 1;
+    workAll[w] = (int)t;
+    GeoDesc d;
+    d.ind = iPair[t];
+    d.ii = iAtomStart[i] - 1;
+    d.jj = iAtomStart[f] - 1;
+    d.n12 = (iAtomStart[i + 1] - iAtomStart[i]) | ((iAtomStart[f + 1] - iAtomStart[f]) << 8);
+    d.iAt1 = i;
+    d.iAt2f = f;
+    d.iVec = iCellVec[a2] - 1;
+    d.iNeigh = k;
+    desc[w] = d;
+    if (k >= 1) {
+      bool dup = f == i;
+      const int *row = iNeighbour + (long long)i * ld;
+      for (int k2 = 1; k2 < k && !dup; ++k2) dup = img2CentCell[row[k2] - 1] - 1 == f;
+      if (dup) atomicMax(hasDuplicates, 1);
+    }
+  }
+}
+
+// groupFirst[g] = the last block that starts at or before element groupSize * g (flat_stream.cuh); the
+// blocks are in ascending offset order by construction.  groupFirst is preset to zero.
+NL_KERNEL void geo_group_index(int nBlocks, int nGroups, int groupSize, const GeoDesc *__restrict__ desc,
+                               int *__restrict__ groupFirst) {
+  for (long long w = NL_TID; w < nBlocks; w += NL_STRIDE) {
+    const long long g0 = ((long long)desc[w].ind + groupSize - 1) / groupSize;
+    const long long g1 = w + 1 < nBlocks ? ((long long)desc[w + 1].ind + groupSize - 1) / groupSize : nGroups;
+    for (long long g = g0; g < g1 && g < nGroups; ++g) groupFirst[g] = (int)w;
+  }
+}
+
 }  // namespace nl
 }  // namespace dftbp_b200

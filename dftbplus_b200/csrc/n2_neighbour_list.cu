@@ -5,7 +5,8 @@
 
 #include <cub/device/device_scan.cuh>
 
-#include "common.cuh"
+#include "block_desc.cuh"
+#include "flat_stream.cuh"
 #include "n2_neighbour_driver.h"
 
 using namespace dftbp_b200;
@@ -97,6 +98,86 @@ void freeNeighbourList(dftbp_b200_ctx *ctx) {
   ctx->neighbourState = nullptr;
 }
 }  // namespace dftbp_b200
+
+namespace {
+
+static_assert(sizeof(nl::GeoDesc) == sizeof(BlockDesc) && offsetof(nl::GeoDesc, ind) == offsetof(BlockDesc, ind) &&
+                  offsetof(nl::GeoDesc, n12) == offsetof(BlockDesc, n12) &&
+                  offsetof(nl::GeoDesc, iAt2f) == offsetof(BlockDesc, iAt2f) &&
+                  offsetof(nl::GeoDesc, iNeigh) == offsetof(BlockDesc, iNeigh),
+              "nl::GeoDesc must mirror BlockDesc");
+
+template <class T>
+int poolCopy(dftbp_b200_ctx *ctx, T **dst, const T *src, size_t count) {
+  void *blk = nullptr;
+  DFTBP_TRY(poolAlloc(ctx, &blk, (count ? count : 1) * sizeof(T)));
+  *dst = static_cast<T *>(blk);
+  if (count && src)
+    DFTBP_CUDA(ctx, cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+
+// The device list becomes the context's geometry without a round trip of the index arrays: the arrays
+// are copied device-to-device into pool blocks, the work list, the block descriptors, the element ->
+// descriptor index of the span pipeline and the hasDuplicates flag are built by kernels
+// (n2_neighbour_kernels.cuh: geo_*); the host reads back the first block of every atom (nAtom + 1
+// ints: sizes the arrays, serves the atom-range calls of packHS) and one flag word.  The list is valid
+// by construction (species, images and offsets come from the kernels of update_neighbour_list), and its
+// blocks tile [0, sparseSize) exactly.  One rank only (see the caller).
+int adoptOnDevice(dftbp_b200_ctx *ctx, NeighbourState *st) {
+  const nl::NeighbourList &L = st->list;
+  CudaBackend be{ctx};
+  be.scanTemp = st->scanTemp;
+  struct KeepTemp {  // the scan scratch may have grown
+    NeighbourState *st; CudaBackend *be;
+    ~KeepTemp() { st->scanTemp = be->scanTemp; }
+  } keep{st, &be};
+  const int nAtom = L.nAtom, ld = L.mNeigh + 1;
+  releaseGeometry(ctx);
+  Geometry g;
+  g.nAtom = nAtom; g.nAllAtom = L.nAllAtom; g.mNeigh = L.mNeigh; g.nCellVec = L.nCellVec;
+  g.sparseSize = L.sparseSize; g.nOrb = L.nOrb;
+  g.coversAll = true;
+  DFTBP_TRY(poolCopy(ctx, &g.coords, (const double *)L.coords.p, (size_t)3 * L.nAllAtom));
+  DFTBP_TRY(poolCopy(ctx, &g.species, (const int *)L.species.p, L.nAllAtom));
+  DFTBP_TRY(poolCopy(ctx, &g.img2CentCell, (const int *)L.img2CentCell.p, L.nAllAtom));
+  DFTBP_TRY(poolCopy(ctx, &g.iCellVec, (const int *)L.iCellVec.p, L.nAllAtom));
+  DFTBP_TRY(poolCopy(ctx, &g.cellVec, (const double *)L.cellVec.p, (size_t)3 * L.nCellVec));
+  DFTBP_TRY(poolCopy(ctx, &g.nNeighbourSK, (const int *)L.nNeighbourSK.p, nAtom));
+  DFTBP_TRY(poolCopy(ctx, &g.iNeighbour, (const int *)L.iNeighbour.p, (size_t)ld * nAtom));
+  DFTBP_TRY(poolCopy(ctx, &g.iPair, (const int *)L.iPair.p, (size_t)ld * nAtom));
+  DFTBP_TRY(poolCopy(ctx, &g.iAtomStart, (const int *)L.iAtomStart.p, (size_t)nAtom + 1));
+  ctx->geo = g;  // from here on the blocks belong to the context (released with the geometry on any failure)
+
+  // first block of every atom: scratch in the list's own buffers (atomSize / atomOffset are free after the update)
+  std::vector<int> hStart((size_t)nAtom + 1);
+  nl::NeighbourList &Lw = st->list;
+  DFTBP_TRY(nl::countBlocks(be, L, Lw.atomSize.p, Lw.atomOffset.p, hStart.data()));
+  const int nBlocks = hStart[nAtom];
+  ctx->blockStartOfAtom.assign(hStart.begin(), hStart.end());
+  ctx->loadInd.clear();
+  ctx->rangeLo = ctx->rangeHi = -1;
+  const size_t nGroups = ((size_t)L.sparseSize + flat::kGroup - 1) / flat::kGroup;
+  Geometry &G = ctx->geo;
+  DFTBP_TRY(poolCopy(ctx, &G.workAll, (const int *)nullptr, (size_t)nBlocks));
+  DFTBP_TRY(poolCopy(ctx, &G.descAll, (const BlockDesc *)nullptr, (size_t)nBlocks));
+  DFTBP_TRY(poolCopy(ctx, &G.groupFirstAll, (const int *)nullptr, nGroups));
+  int hFlag = 0;
+  DFTBP_TRY(nl::describeBlocks(be, L, (const int *)Lw.atomOffset.p, nBlocks, flat::kGroup, G.workAll,
+                               reinterpret_cast<nl::GeoDesc *>(G.descAll), G.groupFirstAll, Lw.sizes.p, &hFlag));
+  G.hasDuplicates = hFlag != 0;
+  G.workMine = G.workLoad = G.workAll;
+  G.descLoad = G.descAll;
+  G.groupFirstLoad = G.groupFirstAll;
+  G.nWorkAll = G.nWorkMine = G.nWorkLoad = nBlocks;
+  G.nPairsMine = (long long)nBlocks - nAtom;
+  G.firstAtomMine = 0;
+  G.lastAtomMine = nAtom - 1;
+  ctx->sortMine.valid = ctx->sortLoad.valid = false;
+  return 0;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -234,11 +315,15 @@ int dftbp_b200_adopt_neighbour_list(dftbp_b200_ctx *ctx) {
               "adopt_neighbour_list: no neighbour list (call update_neighbour_list first)");
   const nl::NeighbourList &L = stateOf(ctx)->list;
   DFTBP_CHECK(ctx, !L.symmetric, "adopt_neighbour_list: a symmetric list is not a geometry for the pair kernels");
-  DFTBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  // device pointers: set_geometry copies them device-to-device and reads what it validates
-  return dftbp_b200_set_geometry(ctx, L.nAtom, L.nAllAtom, L.mNeigh, L.coords.p, L.species.p, L.img2CentCell.p,
-                                 L.iCellVec.p, L.nCellVec, L.cellVec.p, L.nNeighbourSK.p, L.iNeighbour.p,
-                                 L.iPair.p, L.iAtomStart.p, L.sparseSize);
+  if (ctx->nRanks > 1 || tuneInt("DFTBP_B200_ADOPT_HOST", 0) != 0) {
+    // several ranks: the atom chunks / workload-balanced atom sets of set_geometry are host-side logic
+    DFTBP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // device pointers: set_geometry copies them device-to-device and reads what it validates
+    return dftbp_b200_set_geometry(ctx, L.nAtom, L.nAllAtom, L.mNeigh, L.coords.p, L.species.p, L.img2CentCell.p,
+                                   L.iCellVec.p, L.nCellVec, L.cellVec.p, L.nNeighbourSK.p, L.iNeighbour.p,
+                                   L.iPair.p, L.iAtomStart.p, L.sparseSize);
+  }
+  return adoptOnDevice(ctx, stateOf(ctx));
 }
 
 }  // extern "C"

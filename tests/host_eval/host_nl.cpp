@@ -147,6 +147,31 @@ void host_nl_nr_of_neighbours(double cutoff, int *out, int nThreads, unsigned se
             (const int *)g_list.nNeighbour.p, (const double *)g_list.neighDist2.p, out);
 }
 
+// work list / block descriptors of the last list as adopt_neighbour_list builds them on the device
+// (countBlocks + describeBlocks): hStart(nAtom + 1) -> returns the number of blocks
+int host_geo_count(int *hStart, int nThreads, unsigned seed) {
+  HostBackend be{nThreads, std::mt19937(seed)};
+  if (nl::countBlocks(be, g_list, g_list.atomSize.p, g_list.atomOffset.p, hStart)) return -1;
+  return hStart[g_list.nAtom];
+}
+// desc: 8 ints per block (the BlockDesc layout); returns hasDuplicates
+int host_geo_describe(int nBlocks, int groupSize, int *workAll, int *desc, int *groupFirst, int nThreads, unsigned seed) {
+  HostBackend be{nThreads, std::mt19937(seed)};
+  static_assert(sizeof(nl::GeoDesc) == 32, "GeoDesc is 8 ints");
+  const size_t nGroups = ((size_t)g_list.sparseSize + groupSize - 1) / groupSize;
+  // exactly sized scratch copies (ASan: an index past the end must fail), poisoned like device memory
+  void *w = nullptr, *d = nullptr, *gf = nullptr;
+  be.alloc(&w, sizeof(int) * nBlocks); be.alloc(&d, sizeof(nl::GeoDesc) * nBlocks); be.alloc(&gf, sizeof(int) * nGroups);
+  int hFlag = -1;
+  const int rc = nl::describeBlocks(be, g_list, (const int *)g_list.atomOffset.p, nBlocks, groupSize, (int *)w,
+                                    (nl::GeoDesc *)d, (int *)gf, g_list.sizes.p, &hFlag);
+  std::memcpy(workAll, w, sizeof(int) * nBlocks);
+  std::memcpy(desc, d, sizeof(nl::GeoDesc) * nBlocks);
+  std::memcpy(groupFirst, gf, sizeof(int) * nGroups);
+  be.release(w); be.release(d); be.release(gf);
+  return rc ? -1 : hFlag;
+}
+
 // test hook: row length above which the counting is skipped (default nl::kRankMaxDefault)
 void host_nl_set_rank_max(int v) { g_rankMax = v > 0 ? v : nl::kRankMaxDefault; }
 

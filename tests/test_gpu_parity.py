@@ -172,6 +172,27 @@ def test_k3_large_tiles(n, n_occ, hp_cache):
     assert np.abs(dm - ref).max() <= 1e-12 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("variant", [0, 20, 31, 32, 33, 34])
+@pytest.mark.parametrize("n,n_occ", [(1502, 701), (66, 5), (640, 640)])
+def test_k3_tma_feed_variants(variant, n, n_occ, hp_cache, monkeypatch):
+    """TMA-fed K3 (cp.async.bulk + mbarrier pipeline, producer warp) in every tile configuration against
+    the oracle and against the cp.async kernel (variant 20): ragged row / level edges, a level count
+    that is not a multiple of the k-tile, diagonal tiles (one panel), more tiles than CTAs."""
+    monkeypatch.setenv("DFTBP_B200_K3_VARIANT", str(variant))
+    hp = hp_cache("h2o")
+    rng = np.random.default_rng(n + variant)
+    C = np.asfortranarray(rng.normal(size=(n, n)) / np.sqrt(n))
+    f = np.zeros(n); f[:n_occ] = rng.normal(size=n_occ)
+    f[min(2, n_occ - 1)] = 0.0
+    dm = hp.getDensityMatrix(C, f)
+    ref = oracle.weighted_density_matrix(C, f)
+    assert np.all(np.triu(dm, 1) == 0.0)
+    assert np.abs(dm - ref).max() <= 1e-12 * np.abs(ref).max()
+    # a column panel of the same matrix (multi-GPU split) through the same kernel
+    part = hp.getDensityMatrix(C, f, cols=(n // 3 + 1, 2 * n // 3))
+    assert np.abs(part[:, n // 3:2 * n // 3] - np.tril(ref)[:, n // 3:2 * n // 3]).max() <= 1e-12 * np.abs(ref).max()
+
+
 def test_k3_density_matrix_complex(hp_cache):
     w, sk, geo, model, selfegy = case("si2")
     hp = hp_cache("si2")

@@ -596,3 +596,60 @@ def test_kernels_are_clean_under_address_sanitizer(host):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "asan/ubsan run finished" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
     assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr, r.stderr[-4000:]
+
+
+def _host_descriptors(g, group=32):
+    """set_geometry's host-side work list / BlockDesc records / element -> descriptor index (context.cu,
+    flat_stream.cuh buildGroupIndex) restated with plain loops."""
+    n, ld = g["nAtom"], g["mNeigh"] + 1
+    work, desc, dup = [], [], False
+    start, img, vec = g["iAtomStart"], g["img2CentCell"], g["iCellVec"]
+    for i in range(n):
+        seen = {i}
+        for k in range(g["nNeighbourSK"][i] + 1):
+            a2 = g["iNeighbour"][i, k] - 1
+            f = img[a2] - 1
+            work.append(k + ld * i)
+            desc.append((g["iPair"][i, k], start[i] - 1, start[f] - 1,
+                         (start[i + 1] - start[i]) | ((start[f + 1] - start[f]) << 8), i, f, vec[a2] - 1, k))
+            if k >= 1:
+                dup = dup or f in seen
+                seen.add(f)
+    desc = np.array(desc, dtype=np.int32)
+    n_groups = (g["sparseSize"] + group - 1) // group
+    first = np.searchsorted(desc[:, 0], group * np.arange(n_groups), side="right") - 1
+    return np.array(work, np.int32), desc, np.maximum(first, 0).astype(np.int32), dup
+
+
+@pytest.mark.parametrize("name", ["h2o", "ce_o", "si2", "fec128", "si512", "water1002"])
+def test_device_built_block_descriptors_equal_the_host_built_ones(name, host):
+    """adopt_neighbour_list builds the work list, the BlockDesc records, the span-pipeline index and the
+    hasDuplicates flag with kernels (geo_block_count / geo_describe / geo_group_index); here the same
+    kernels run on the host against a restatement of what set_geometry builds from host arrays."""
+    w, sk, geo, model, selfegy = case(name)
+    cutoff = sk.cutoff()
+    cell, rcell = cells_of(w, cutoff)
+    di = ctypes.c_int
+    for n_threads, seed in ((61, 1), (1, 2), (4099, 3)):
+        g = host_list(host, w["coord0"], w["species0"], sk.n_orb_species, cell, rcell, cutoff, cutoff,
+                      n_threads=n_threads, seed=seed)
+        h_start = np.zeros(g["nAtom"] + 1, np.int32)
+        n_blocks = host.host_geo_count(_p(h_start, di), n_threads, ctypes.c_uint(seed))
+        assert n_blocks == int(g["nNeighbourSK"].sum()) + g["nAtom"]
+        assert np.array_equal(h_start, np.concatenate([[0], np.cumsum(g["nNeighbourSK"] + 1)]))
+        work = np.zeros(n_blocks, np.int32)
+        desc = np.zeros((n_blocks, 8), np.int32)
+        n_groups = (g["sparseSize"] + 31) // 32
+        first = np.full(n_groups, -7, np.int32)
+        dup = host.host_geo_describe(n_blocks, 32, _p(work, di), _p(desc, di), _p(first, di), n_threads,
+                                     ctypes.c_uint(seed))
+        r_work, r_desc, r_first, r_dup = _host_descriptors(g)
+        assert np.array_equal(work, r_work)
+        assert np.array_equal(desc, r_desc)
+        assert np.array_equal(first, r_first)
+        assert dup == int(r_dup)
+    # small cells fold several images onto one dense block; clusters and large boxes do not
+    if name in ("h2o", "ce_o", "water1002"):
+        assert not dup
+    if name in ("si2", "fec128"):
+        assert dup

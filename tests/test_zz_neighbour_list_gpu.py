@@ -138,6 +138,61 @@ def test_adopted_list_feeds_the_pair_kernels(name, hp_for):
     assert np.abs(f - f_ref).max() < 1e-7 * max(1.0, np.abs(f_ref).max())
 
 
+@pytest.mark.parametrize("name", ["ce_o", "si2", "fec128", "water1002"])
+def test_device_adopted_geometry_equals_the_host_built_one(name, hp_for, monkeypatch):
+    """adopt_neighbour_list builds work list, block descriptors, span index and hasDuplicates on the device
+    (geo_* kernels); every kernel family that walks them must give what it gives on the geometry that
+    set_geometry builds on the host from the same arrays: K2 unpack / pack (duplicates -> atomics, atom
+    ranges -> blockStartOfAtom), K4, K6 addShift (span index), SCC forces with diagonal block shifts (span
+    pipeline) also as pair shares (loadElementRange read from the device descriptors)."""
+    from dftbplus_b200.api import HotPath
+    w, sk, geo, model, selfegy = case(name)
+    cutoff = sk.cutoff()
+    dev = hp_for(name)
+    g = dev.updateNeighbourListAndSpecies(w["coord0"], w["species0"], cutoff, w["latvec"], adopt=True)
+    ogeo = oracle.neighbour_geometry(model, w["coord0"], w["species0"], w["latvec"])
+    host = HotPath(0)
+    sk.upload(host)
+    host.set_geometry(ogeo)
+    rng = np.random.default_rng(71)
+    n, ss, nA, mOrb = ogeo["nOrb"], ogeo["sparseSize"], ogeo["nAtom"], dev.mOrb
+    over = oracle.build_s(model, ogeo)
+    rho = rng.normal(size=(2, ss))
+    edm = rng.normal(size=ss)
+    # K2
+    assert np.array_equal(dev.unpackHS(over), host.unpackHS(over))
+    sq = np.asfortranarray(rng.normal(size=(n, n)))
+    assert np.array_equal(dev.packHS(np.zeros(ss), sq), host.packHS(np.zeros(ss), sq))
+    a0, a1 = max(1, nA // 3), max(1, 2 * nA // 3)
+    assert np.array_equal(dev.packHS(np.zeros(ss), sq, atoms=(a0, a1)), host.packHS(np.zeros(ss), sq, atoms=(a0, a1)))
+    # K4
+    qd, qh = dev.mulliken(over, rho[0]), host.mulliken(over, rho[0])
+    assert np.abs(qd - qh).max() <= 1e-13 * max(1.0, np.abs(qh).max())
+    # K6: atom shifts and diagonal block shifts through the span pipeline
+    sh_atom = rng.normal(size=(2, nA))
+    hd, hh = dev.addShift(np.zeros((2, ss)), over, sh_atom, True), host.addShift(np.zeros((2, ss)), over, sh_atom, True)
+    assert np.array_equal(hd, hh)
+    sh = np.zeros((2, nA, mOrb, mOrb))
+    for s_ in range(2):
+        for a in range(nA):
+            sh[s_, a][np.diag_indices(mOrb)] = rng.normal(size=mOrb)
+    hd, hh = dev.addShift(np.zeros((2, ss)), over, sh, True), host.addShift(np.zeros((2, ss)), over, sh, True)
+    assert np.array_equal(hd, hh)
+    # K5, SCC form, whole and as three shares
+    fd, fh = dev.derivative_shift(rho, edm, shift=sh), host.derivative_shift(rho, edm, shift=sh)
+    scale = max(1.0, np.abs(fh).max())
+    assert np.abs(fd - fh).max() <= 1e-11 * scale
+    parts = np.zeros_like(fd)
+    for r in range(3):
+        dev.set_pair_partition(r, 3)
+        parts += dev.derivative_shift(rho, edm, shift=sh)
+    dev.set_pair_partition(0, 1)
+    assert np.abs(parts - fh).max() <= 1e-11 * scale
+    # the host-side adoption (several ranks, or the A/B switch) is still the same geometry
+    assert g["sparseSize"] == ss
+    host.close()
+
+
 def test_too_close_atoms_on_the_device(hp_for):
     from dftbplus_b200.api import DftbB200Error
     w, sk, geo, model, selfegy = case("fec128")
