@@ -1009,7 +1009,7 @@ def main():
             panel_frac = (c1 - c0) * (2.0 * nOrb - c0 - c1) / (float(nOrb) * nOrb)
         if dm_ms:
             flops = float(nOrb) * nOrb * n_occ * panel_frac          # n^2 * nLevels, one triangle, FMA = 2 flops
-            roofline_dm = {"kernel": "k3_dm_real (DMMA m8n8k4)", "bound": "tensor",
+            roofline_dm = {"kernel": "k3_dm_real_tma (DMMA m8n8k4; operand panels by cp.async.bulk + mbarrier pipeline, producer warp)", "bound": "tensor",
                            "achieved": flops / dm_ms / 1e9, "peak": dgemm_tflops, "unit": "TFLOP/s",
                            "frac": flops / dm_ms / 1e9 / dgemm_tflops, "traffic": None,
                            "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (FP64 is not in MEASURED_PEAKS.json)",

@@ -524,16 +524,25 @@ int densityImpl(dftbp_b200_ctx *ctx, void *dm, const void *eigvecs, int n, int l
     // TMA-fed kernel: 16-byte aligned columns of C (bulk copies) -- even ld, even n, aligned base
     const bool tmaOk = aligned && n % 2 == 0;
     if (tmaOk && (variant == 0 || variant >= 30)) {
-      if (variant == 31) {
+      if (variant == 30 || (variant == 0 && n < 4096)) {
+        // small matrices: 64 x 64 tiles, three CTAs per SM (more tiles than CTA slots from n = 1400 on)
+        DFTBP_TRY((launchRealTma<64, 16, 4, 2, 2>(ctx, 3, dC, ld, dW, n, K, dDm, counter)));
+      } else if (variant == 31) {
         DFTBP_TRY((launchRealTma<64, 16, 3, 2, 2>(ctx, 4, dC, ld, dW, n, K, dDm, counter)));
-      } else if (variant == 32) {
-        DFTBP_TRY((launchRealTma<128, 16, 4, 2, 4>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
       } else if (variant == 33) {
-        DFTBP_TRY((launchRealTma<64, 16, 6, 2, 2>(ctx, 2, dC, ld, dW, n, K, dDm, counter)));
+        DFTBP_TRY((launchRealTma<128, 16, 6, 2, 4>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
       } else if (variant == 34) {
         DFTBP_TRY((launchRealTma<128, 8, 6, 4, 2>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
+      } else if (variant == 35) {
+        DFTBP_TRY((launchRealTma<128, 16, 4, 4, 2>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
+      } else if (variant == 36) {
+        DFTBP_TRY((launchRealTma<128, 8, 8, 2, 4>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
+      } else if (variant == 37) {
+        DFTBP_TRY((launchRealTma<128, 16, 3, 2, 4>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
       } else {
-        DFTBP_TRY((launchRealTma<64, 16, 4, 2, 2>(ctx, 3, dC, ld, dW, n, K, dDm, counter)));
+        // 128 x 128 tiles, eight consumer warps of 64 x 32 + the producer warp, one CTA per SM: 34.3 TFLOP/s
+        // at n = 31744 (93 % of cuBLAS DGEMM; 64 x 64 tiles 32.7, the cp.async kernel of round 1 30.5)
+        DFTBP_TRY((launchRealTma<128, 16, 4, 2, 4>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
       }
     } else if (n < 1024) {
       DFTBP_TRY((launchReal<64, 16, 3, 2, 2, 1>(ctx, 2, dC, ld, dW, n, K, dDm, counter)));

@@ -159,8 +159,9 @@ def test_device_adopted_geometry_equals_the_host_built_one(name, hp_for, monkeyp
     over = oracle.build_s(model, ogeo)
     rho = rng.normal(size=(2, ss))
     edm = rng.normal(size=ss)
-    # K2
-    assert np.array_equal(dev.unpackHS(over), host.unpackHS(over))
+    # K2 (blocks that fold onto one dense block are added with atomics: the order of the sum is not fixed)
+    ud, uh = dev.unpackHS(over), host.unpackHS(over)
+    assert np.array_equal(ud, uh) if name in ("ce_o", "water1002") else np.abs(ud - uh).max() <= 1e-15
     sq = np.asfortranarray(rng.normal(size=(n, n)))
     assert np.array_equal(dev.packHS(np.zeros(ss), sq), host.packHS(np.zeros(ss), sq))
     a0, a1 = max(1, nA // 3), max(1, 2 * nA // 3)

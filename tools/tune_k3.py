@@ -15,14 +15,17 @@ hp = HotPath(0)
 hp.use_torch_stream()
 f64 = dict(dtype=torch.float64, device=dev)
 res = {}
-for n, nocc in [(7936, 3584), (16384, 8192)]:
+SIZES = [(31744, 14336)] if "--full" in sys.argv else [(7936, 3584), (16384, 8192)]
+# 0: default (TMA-fed 64x64, 4 stages, 3 CTAs / SM), 20: the cp.async kernel of round 1, 31-34: TMA-fed tile variants
+VARIANTS = [int(v) for v in os.environ.get("K3_VARIANTS", "0,20,31,32,33,34").split(",")]
+for n, nocc in SIZES:
     C = new_dense(n)
     C.copy_(torch.randn(n, n, **f64) / n ** 0.5)
     fill = torch.zeros(n, **f64)
     fill[:nocc] = 2.0
     dm = new_dense(n)
     ref = None
-    for v in [0, 3, 6, 7, 8, 9, 10]:
+    for v in VARIANTS:
         os.environ["DFTBP_B200_K3_VARIANT"] = str(v)
         hp.getDensityMatrix(C, fill, dm=dm)
         torch.cuda.synchronize()
