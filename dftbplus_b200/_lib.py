@@ -66,6 +66,10 @@ SIGNATURES = {
     "dftbp_b200_num_pairs": (ctypes.c_longlong, [c_void_p]),
     "dftbp_b200_efilling": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                     c_int, c_double, c_double, c_void_p, c_int]),
+    "dftbp_b200_invr_cluster": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int]),
+    "dftbp_b200_invr_periodic": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_double, c_double,
+                                         c_double, c_void_p, c_int]),
+    "dftbp_b200_coulomb_shift": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -420,6 +420,39 @@ class HotPath:
         return dict(filling=filling, Ef=float(small[6]), Ebs=small[0:n_spin].copy(), TS=small[2:2 + n_spin].copy(),
                     E0=small[4:4 + n_spin].copy())
 
+    # ---- N4: Coulomb 1/R matrix and shifts -------------------------------------------------------
+    def invRCluster(self, coord, invr=None):
+        """invRCluster (dftb/coulomb.F90:623-733): lower triangle of 1 / |r_i - r_j|, column-major [n, n]."""
+        n = int(coord.shape[0])
+        if invr is None:
+            invr = np.zeros((n, n), order="F")
+        self._ck(self._L.dftbp_b200_invr_cluster(self._h, n, _ptr(_f64(coord)), _ptr(invr), _ld(invr)))
+        return invr
+
+    def invRPeriodic(self, coord, r_lat, g_lat, alpha, volume, r_cutoff, invr=None):
+        """invRPeriodic (dftb/coulomb.F90:815-1024): the Ewald 1/R matrix.  r_lat [nRLat, 3] lattice translations
+        (absolute, origin first, getCellTranslations order), g_lat [nG, 3] reciprocal points (absolute, no origin,
+        no inversion pairs) -- what TCoulomb%updateLatVecs keeps as rLatPoints_ / gLatPoints_."""
+        n = int(coord.shape[0])
+        if invr is None:
+            invr = np.zeros((n, n), order="F")
+        self._ck(self._L.dftbp_b200_invr_periodic(self._h, n, _ptr(_f64(coord)), int(r_lat.shape[0]), _ptr(_f64(r_lat)),
+                                                  int(g_lat.shape[0]), _ptr(_f64(g_lat)), float(alpha), float(volume),
+                                                  float(r_cutoff), _ptr(invr), _ld(invr)))
+        return invr
+
+    def coulombShift(self, invr, dq, shift=None):
+        """TCoulomb%updateShifts (dftb/coulomb.F90:537-586): shiftPerAtom = hemv(invRMat, deltaQAtom, 'L')."""
+        n = int(dq.shape[0])
+        if shift is None:
+            if _is_torch(dq):
+                import torch
+                shift = torch.zeros_like(dq)
+            else:
+                shift = np.zeros(n)
+        self._ck(self._L.dftbp_b200_coulomb_shift(self._h, n, _ptr(invr), _ld(invr), _ptr(_f64(dq)), _ptr(shift)))
+        return shift
+
     def diagDenseMtx(self, H, S, eigen=None, jobz="V"):
         """hegvd: H, S column-major, overwritten (H <- eigenvectors); returns eigenvalues."""
         n = H.shape[0]

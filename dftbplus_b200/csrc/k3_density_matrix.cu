@@ -467,29 +467,112 @@ int setSmem(dftbp_b200_ctx *ctx, Kern k, size_t bytes) {
 
 template <int BM, int BK, int ST, int WMn, int WNn, int VEC>
 int launchReal(dftbp_b200_ctx *ctx, int ctasPerSm, const double *dC, int ld, const double *dW, int n,
-               const int *K, double *dDm, unsigned long long *counter) {
+               const int *K, double *dDm, int ldd, unsigned long long *counter) {
   const size_t smemB = sizeof(double) * (2 * ST * BK * (BM + 4) + ST * BK);
   const TileOrder o = makeOrder(n, BM, ctx->dmColFirst, ctx->dmColLast);
   const long long nTiles = (long long)o.nT * (o.nT + 1) / 2;
   const int grid = (int)std::min<long long>(nTiles, (long long)ctasPerSm * ctx->smCount);
   auto kern = k3_dm_real<BM, BK, ST, WMn, WNn, VEC>;
   DFTBP_TRY(setSmem(ctx, kern, smemB));
-  kern<<<grid, 32 * WMn * WNn, smemB, ctx->stream>>>(dC, ld, dW, n, K, dDm, ld, o, counter);
+  kern<<<grid, 32 * WMn * WNn, smemB, ctx->stream>>>(dC, ld, dW, n, K, dDm, ldd, o, counter);
   return 0;
 }
 
 template <int BM, int BK, int ST, int WMn, int WNn>
 int launchRealTma(dftbp_b200_ctx *ctx, int ctasPerSm, const double *dC, int ld, const double *dW, int n,
-                  const int *K, double *dDm, unsigned long long *counter) {
+                  const int *K, double *dDm, int ldd, unsigned long long *counter) {
   const size_t smemB = sizeof(double) * (2 * ST * BK * (BM + 4) + ST * BK) + sizeof(unsigned long long) * 2 * ST;
   const TileOrder o = makeOrder(n, BM, ctx->dmColFirst, ctx->dmColLast);
   const long long nTiles = (long long)o.nT * (o.nT + 1) / 2;
   const int grid = (int)std::min<long long>(nTiles, (long long)ctasPerSm * ctx->smCount);
   auto kern = k3_dm_real_tma<BM, BK, ST, WMn, WNn>;
   DFTBP_TRY(setSmem(ctx, kern, smemB));
-  kern<<<grid, 32 * (WMn * WNn + 1), smemB, ctx->stream>>>(dC, ld, dW, n, K, dDm, ld, o, counter);
+  kern<<<grid, 32 * (WMn * WNn + 1), smemB, ctx->stream>>>(dC, ld, dW, n, K, dDm, ldd, o, counter);
   return 0;
 }
+
+// tile configuration of the real kernel for (n, ld, alignment); K and the tile counter live on the device
+int launchRealAuto(dftbp_b200_ctx *ctx, const double *dC, int ld, const double *dW, int n, const int *K, double *dDm,
+                   int ldd, unsigned long long *counter) {
+  const bool aligned = (ld % 2 == 0) && ((reinterpret_cast<size_t>(dC) & 15) == 0);
+  // tuning hook (development only): DFTBP_B200_K3_VARIANT selects a tile configuration
+  const char *env = getenv("DFTBP_B200_K3_VARIANT");
+  const int variant = env ? atoi(env) : 0;
+  // TMA-fed kernel: 16-byte aligned columns of C (bulk copies) -- even ld, even n, aligned base
+  const bool tmaOk = aligned && n % 2 == 0;
+  if (tmaOk && (variant == 0 || variant >= 30)) {
+    if (variant == 30 || (variant == 0 && n < 4096)) {
+      // small matrices: 64 x 64 tiles, three CTAs per SM (more tiles than CTA slots from n = 1400 on)
+      DFTBP_TRY((launchRealTma<64, 16, 4, 2, 2>(ctx, 3, dC, ld, dW, n, K, dDm, ldd, counter)));
+    } else if (variant == 31) {
+      DFTBP_TRY((launchRealTma<64, 16, 3, 2, 2>(ctx, 4, dC, ld, dW, n, K, dDm, ldd, counter)));
+    } else if (variant == 33) {
+      DFTBP_TRY((launchRealTma<128, 16, 6, 2, 4>(ctx, 1, dC, ld, dW, n, K, dDm, ldd, counter)));
+    } else if (variant == 34) {
+      DFTBP_TRY((launchRealTma<128, 8, 6, 4, 2>(ctx, 1, dC, ld, dW, n, K, dDm, ldd, counter)));
+    } else if (variant == 35) {
+      DFTBP_TRY((launchRealTma<128, 16, 4, 4, 2>(ctx, 1, dC, ld, dW, n, K, dDm, ldd, counter)));
+    } else if (variant == 36) {
+      DFTBP_TRY((launchRealTma<128, 8, 8, 2, 4>(ctx, 1, dC, ld, dW, n, K, dDm, ldd, counter)));
+    } else if (variant == 37) {
+      DFTBP_TRY((launchRealTma<128, 16, 3, 2, 4>(ctx, 1, dC, ld, dW, n, K, dDm, ldd, counter)));
+    } else {
+      // 128 x 128 tiles, eight consumer warps of 64 x 32 + the producer warp, one CTA per SM: 34.3 TFLOP/s
+      // at n = 31744 (93 % of cuBLAS DGEMM; 64 x 64 tiles 32.7, the cp.async kernel of round 1 30.5)
+      DFTBP_TRY((launchRealTma<128, 16, 4, 2, 4>(ctx, 1, dC, ld, dW, n, K, dDm, ldd, counter)));
+    }
+  } else if (n < 1024) {
+    DFTBP_TRY((launchReal<64, 16, 3, 2, 2, 1>(ctx, 2, dC, ld, dW, n, K, dDm, ldd, counter)));
+  } else if (!aligned) {
+    DFTBP_TRY((launchReal<128, 16, 4, 2, 4, 1>(ctx, 1, dC, ld, dW, n, K, dDm, ldd, counter)));
+  } else if (variant == 1) {
+    DFTBP_TRY((launchReal<128, 16, 4, 4, 4, 2>(ctx, 1, dC, ld, dW, n, K, dDm, ldd, counter)));
+  } else if (variant == 2) {
+    DFTBP_TRY((launchReal<128, 32, 3, 2, 4, 2>(ctx, 1, dC, ld, dW, n, K, dDm, ldd, counter)));
+  } else if (variant == 3) {
+    DFTBP_TRY((launchReal<128, 16, 4, 2, 4, 2>(ctx, 1, dC, ld, dW, n, K, dDm, ldd, counter)));
+  } else if (variant == 6) {
+    DFTBP_TRY((launchReal<64, 16, 3, 2, 2, 2>(ctx, 4, dC, ld, dW, n, K, dDm, ldd, counter)));
+  } else if (variant == 7) {
+    DFTBP_TRY((launchReal<64, 16, 4, 2, 2, 2>(ctx, 2, dC, ld, dW, n, K, dDm, ldd, counter)));
+  } else if (variant == 8) {
+    DFTBP_TRY((launchReal<64, 32, 3, 2, 2, 2>(ctx, 2, dC, ld, dW, n, K, dDm, ldd, counter)));
+  } else if (variant == 9) {
+    DFTBP_TRY((launchReal<64, 16, 4, 4, 2, 2>(ctx, 3, dC, ld, dW, n, K, dDm, ldd, counter)));
+  } else if (variant == 10) {
+    DFTBP_TRY((launchReal<64, 8, 6, 2, 2, 2>(ctx, 4, dC, ld, dW, n, K, dDm, ldd, counter)));
+  } else {
+    // 64x64 tiles, 4 warps of 32x32, three CTAs per SM: independent barrier domains hide the
+    // per-k-tile __syncthreads better than one 128x128 CTA (measured 30.3 vs 26.3 TFLOP/s)
+    DFTBP_TRY((launchReal<64, 16, 4, 2, 2, 2>(ctx, 3, dC, ld, dW, n, K, dDm, ldd, counter)));
+  }
+  return 0;
+}
+
+__global__ void k3_set_levels(int K, int *out) { *out = K; }
+
+}  // namespace
+
+namespace dftbp_b200 {
+// dm(ldd, n) = lower( C(:, 1:K) diag(w) C(:, 1:K)^T ) with C(ldc, K), w(K) on the device and K given by the host
+// (the Ewald structure-factor form of n4_coulomb.cu: K may exceed n); all of dm is zero-filled first.
+int weightedGramLower(dftbp_b200_ctx *ctx, const double *dC, int ldc, const double *dW, int n, int K, double *dDm,
+                      int ldd) {
+  DFTBP_CHECK(ctx, dC && dW && dDm && n > 0 && K > 0 && ldc >= n && ldd >= n, "weightedGramLower: bad arguments");
+  ctx->dmColFirst = 1;
+  ctx->dmColLast = n;
+  DFTBP_CUDA(ctx, cudaMemsetAsync(dDm, 0, sizeof(double) * (size_t)ldd * n, ctx->stream));
+  k3_set_levels<<<1, 1, 0, ctx->stream>>>(K, ctx->dInfo);
+  unsigned long long *counter = reinterpret_cast<unsigned long long *>(ctx->dInfo + 2);
+  DFTBP_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
+  DFTBP_TRY(launchRealAuto(ctx, dC, ldc, dW, n, ctx->dInfo, dDm, ldd, counter));
+  ctx->launches += 2;
+  DFTBP_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+}  // namespace dftbp_b200
+
+namespace {
 
 int densityImpl(dftbp_b200_ctx *ctx, void *dm, const void *eigvecs, int n, int ld, const double *filling,
                 const double *weights, bool cplx, int colFirst = 1, int colLast = 0) {
@@ -517,58 +600,7 @@ int densityImpl(dftbp_b200_ctx *ctx, void *dm, const void *eigvecs, int n, int l
   unsigned long long *counter = reinterpret_cast<unsigned long long *>(ctx->dInfo + 2);
   DFTBP_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
   if (!cplx) {
-    const bool aligned = (ld % 2 == 0) && ((reinterpret_cast<size_t>(dC) & 15) == 0);
-    // tuning hook (development only): DFTBP_B200_K3_VARIANT selects a tile configuration
-    const char *env = getenv("DFTBP_B200_K3_VARIANT");
-    const int variant = env ? atoi(env) : 0;
-    // TMA-fed kernel: 16-byte aligned columns of C (bulk copies) -- even ld, even n, aligned base
-    const bool tmaOk = aligned && n % 2 == 0;
-    if (tmaOk && (variant == 0 || variant >= 30)) {
-      if (variant == 30 || (variant == 0 && n < 4096)) {
-        // small matrices: 64 x 64 tiles, three CTAs per SM (more tiles than CTA slots from n = 1400 on)
-        DFTBP_TRY((launchRealTma<64, 16, 4, 2, 2>(ctx, 3, dC, ld, dW, n, K, dDm, counter)));
-      } else if (variant == 31) {
-        DFTBP_TRY((launchRealTma<64, 16, 3, 2, 2>(ctx, 4, dC, ld, dW, n, K, dDm, counter)));
-      } else if (variant == 33) {
-        DFTBP_TRY((launchRealTma<128, 16, 6, 2, 4>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
-      } else if (variant == 34) {
-        DFTBP_TRY((launchRealTma<128, 8, 6, 4, 2>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
-      } else if (variant == 35) {
-        DFTBP_TRY((launchRealTma<128, 16, 4, 4, 2>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
-      } else if (variant == 36) {
-        DFTBP_TRY((launchRealTma<128, 8, 8, 2, 4>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
-      } else if (variant == 37) {
-        DFTBP_TRY((launchRealTma<128, 16, 3, 2, 4>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
-      } else {
-        // 128 x 128 tiles, eight consumer warps of 64 x 32 + the producer warp, one CTA per SM: 34.3 TFLOP/s
-        // at n = 31744 (93 % of cuBLAS DGEMM; 64 x 64 tiles 32.7, the cp.async kernel of round 1 30.5)
-        DFTBP_TRY((launchRealTma<128, 16, 4, 2, 4>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
-      }
-    } else if (n < 1024) {
-      DFTBP_TRY((launchReal<64, 16, 3, 2, 2, 1>(ctx, 2, dC, ld, dW, n, K, dDm, counter)));
-    } else if (!aligned) {
-      DFTBP_TRY((launchReal<128, 16, 4, 2, 4, 1>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
-    } else if (variant == 1) {
-      DFTBP_TRY((launchReal<128, 16, 4, 4, 4, 2>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
-    } else if (variant == 2) {
-      DFTBP_TRY((launchReal<128, 32, 3, 2, 4, 2>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
-    } else if (variant == 3) {
-      DFTBP_TRY((launchReal<128, 16, 4, 2, 4, 2>(ctx, 1, dC, ld, dW, n, K, dDm, counter)));
-    } else if (variant == 6) {
-      DFTBP_TRY((launchReal<64, 16, 3, 2, 2, 2>(ctx, 4, dC, ld, dW, n, K, dDm, counter)));
-    } else if (variant == 7) {
-      DFTBP_TRY((launchReal<64, 16, 4, 2, 2, 2>(ctx, 2, dC, ld, dW, n, K, dDm, counter)));
-    } else if (variant == 8) {
-      DFTBP_TRY((launchReal<64, 32, 3, 2, 2, 2>(ctx, 2, dC, ld, dW, n, K, dDm, counter)));
-    } else if (variant == 9) {
-      DFTBP_TRY((launchReal<64, 16, 4, 4, 2, 2>(ctx, 3, dC, ld, dW, n, K, dDm, counter)));
-    } else if (variant == 10) {
-      DFTBP_TRY((launchReal<64, 8, 6, 2, 2, 2>(ctx, 4, dC, ld, dW, n, K, dDm, counter)));
-    } else {
-      // 64x64 tiles, 4 warps of 32x32, three CTAs per SM: independent barrier domains hide the
-      // per-k-tile __syncthreads better than one 128x128 CTA (measured 30.3 vs 26.3 TFLOP/s)
-      DFTBP_TRY((launchReal<64, 16, 4, 2, 2, 2>(ctx, 3, dC, ld, dW, n, K, dDm, counter)));
-    }
+    DFTBP_TRY(launchRealAuto(ctx, dC, ld, dW, n, K, dDm, ld, counter));
   } else {
     constexpr int BM = 64, BK = 8, ST = 4;
     const size_t smemB = sizeof(double2) * (2 * ST * BK * (BM + 2)) + sizeof(double) * ST * BK;

@@ -18,6 +18,7 @@ module dftbp_b200_shim
   public :: b200_mullikenPerOrbital, b200_mullikenPerBlock, b200_mullikenPerAtom, b200_getOnsitePopulation
   public :: b200_derivative_shift, b200_addShift_block, b200_addShift_atom, b200_getBlockStress
   public :: b200_hegv_real, b200_hegv_cmplx, b200_Efilling
+  public :: b200_invRCluster, b200_invRPeriodic, b200_coulombShifts
 
   integer, parameter :: dp = c_double
 
@@ -244,6 +245,29 @@ module dftbp_b200_shim
       real(c_double), intent(in) :: eigenvals(*), kWeight(*)
       integer(c_int), value :: nLevels, nKpt, nSpin, distrib
       real(c_double), value :: nElectrons, kT
+    end function
+    integer(c_int) function dftbp_b200_invr_cluster(ctx, nAtom, coord, invRMat, ld) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nAtom, ld
+      real(c_double), intent(in) :: coord(*)
+      real(c_double), intent(out) :: invRMat(*)
+    end function
+    integer(c_int) function dftbp_b200_invr_periodic(ctx, nAtom, coord, nRLat, rLat, nG, gLat, alpha, volume,&
+        & rCutoff, invRMat, ld) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nAtom, nRLat, nG, ld
+      real(c_double), intent(in) :: coord(*), rLat(*), gLat(*)
+      real(c_double), value :: alpha, volume, rCutoff
+      real(c_double), intent(out) :: invRMat(*)
+    end function
+    integer(c_int) function dftbp_b200_coulomb_shift(ctx, nAtom, invRMat, ld, deltaQAtom, shiftPerAtom) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nAtom, ld
+      real(c_double), intent(in) :: invRMat(*), deltaQAtom(*)
+      real(c_double), intent(out) :: shiftPerAtom(*)
     end function
     integer(c_int) function dftbp_b200_adopt_neighbour_list(ctx) bind(C)
       import :: c_ptr, c_int
@@ -528,6 +552,36 @@ contains
     call check(ctx, dftbp_b200_efilling(ctx%h, Ebs, Ef, TS, E0, filling, eigenvals, size(eigenvals, dim=1),&
         & size(eigenvals, dim=2), size(eigenvals, dim=3), nElectrons, kT, kWeight, int(distrib, c_int)))
   end subroutine b200_Efilling
+
+  !> invRCluster, dftb/coulomb.F90:623 (serial branch :704): coord(3, nAtom), invRMat(nAtom, nAtom)
+  subroutine b200_invRCluster(ctx, nAtom, coord, invRMat)
+    type(TB200Ctx), intent(in) :: ctx
+    integer, intent(in) :: nAtom
+    real(dp), intent(in) :: coord(:,:)
+    real(dp), intent(out) :: invRMat(:,:)
+    call check(ctx, dftbp_b200_invr_cluster(ctx%h, int(nAtom, c_int), coord, invRMat, size(invRMat, dim=1)))
+  end subroutine b200_invRCluster
+
+  !> invRPeriodic, dftb/coulomb.F90:815 (serial branch :968).  The dynamic neighbour list argument of the
+  !> reference is replaced by what defines it: the lattice translations this%rLatPoints_ (origin first) and
+  !> the real-space cutoff maxREwald, both from TCoulomb%updateLatVecs (:330-372)
+  subroutine b200_invRPeriodic(ctx, nAtom, coord, rLatPoints, maxREwald, recPoint, alpha, volume, invRMat)
+    type(TB200Ctx), intent(in) :: ctx
+    integer, intent(in) :: nAtom
+    real(dp), intent(in) :: coord(:,:), rLatPoints(:,:), maxREwald, recPoint(:,:), alpha, volume
+    real(dp), intent(out) :: invRMat(:,:)
+    call check(ctx, dftbp_b200_invr_periodic(ctx%h, int(nAtom, c_int), coord, size(rLatPoints, dim=2), rLatPoints,&
+        & size(recPoint, dim=2), recPoint, alpha, volume, maxREwald, invRMat, size(invRMat, dim=1)))
+  end subroutine b200_invRPeriodic
+
+  !> TCoulomb%updateShifts, dftb/coulomb.F90:537: shiftPerAtom = hemv(invRMat, deltaQAtom, 'L')
+  subroutine b200_coulombShifts(ctx, invRMat, deltaQAtom, shiftPerAtom)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(in) :: invRMat(:,:), deltaQAtom(:)
+    real(dp), intent(out) :: shiftPerAtom(:)
+    call check(ctx, dftbp_b200_coulomb_shift(ctx%h, size(deltaQAtom), invRMat, size(invRMat, dim=1), deltaQAtom,&
+        & shiftPerAtom))
+  end subroutine b200_coulombShifts
 
   !> mullikenPerBlock, dftb/populations.F90:306 -- qq(mOrb, mOrb, nAtom) accumulates
   subroutine b200_mullikenPerBlock(ctx, qq, over, rho)

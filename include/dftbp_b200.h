@@ -300,6 +300,27 @@ int dftbp_b200_efilling(dftbp_b200_ctx *ctx, double *Ebs, double *Ef, double *TS
                         double *filling, const double *eigenvals, int nLevels, int nKpt, int nSpin,
                         double nElectrons, double kT, const double *kWeight, int distrib);
 
+/* The Coulomb 1/R matrix of the SCC shifts (second piece).  invRMat(ld, nAtom) column-major,
+ * lower triangle (row >= column) filled, everything else zero -- the storage hemv(..., 'L') reads.
+ * coord(3, nAtom): the central-cell atoms.  Host or device pointers throughout.
+ *
+ * invr_cluster:   invRClusterSerial, dftb/coulomb.F90:704-733 (caller TCoulomb%updateCoords, :291-327).
+ * invr_periodic:  invRPeriodicSerial, dftb/coulomb.F90:968-1024: the Ewald sum with parameter alpha over
+ *   rLat(3, nRLat) -- the lattice translations in absolute coordinates, origin first, as
+ *   getCellTranslations(.., maxREwald) returns them (this%rLatPoints_; the dynamic neighbour list of the
+ *   reference, type/dynneighlist.F90, visits the same points in the same order), real-space terms kept for
+ *   dist^2 <= rCutoff^2 -- and gLat(3, nG), the reciprocal points this%gLatPoints_ (absolute, no origin,
+ *   one of every inversion pair); volume = cell volume.  The reciprocal part is evaluated as a weighted Gram
+ *   matrix of structure factors on the FP64 tensor cores (same value up to rounding).
+ * coulomb_shift:  TCoulomb%updateShifts, dftb/coulomb.F90:537-586: shiftPerAtom(:) = hemv(invRMat,
+ *   deltaQAtom, 'L') (overwrites shiftPerAtom). */
+int dftbp_b200_invr_cluster(dftbp_b200_ctx *ctx, int nAtom, const double *coord, double *invRMat, int ld);
+int dftbp_b200_invr_periodic(dftbp_b200_ctx *ctx, int nAtom, const double *coord, int nRLat, const double *rLat,
+                             int nG, const double *gLat, double alpha, double volume, double rCutoff,
+                             double *invRMat, int ld);
+int dftbp_b200_coulomb_shift(dftbp_b200_ctx *ctx, int nAtom, const double *invRMat, int ld,
+                             const double *deltaQAtom, double *shiftPerAtom);
+
 /* ---- not rewritten: dense generalized eigensolve via cuSOLVER ------------------------------- */
 
 /* diagDenseMtx, dftbplus/eigenvects.F90:85-100 (hegvd branch): H C = S C diag(eigen), lower

@@ -1305,3 +1305,85 @@ int orc_num_threads(void)
   return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Coulomb 1/R matrix of the SCC shifts: invRClusterSerial (dftb/coulomb.F90:704-733),
+ * invRPeriodicSerial (:968-1024) with addNeighbourContribsIS (:1027-1053; the dynamic neighbour list
+ * of type/dynneighlist.F90:207-260 restated as its loops: central cell iAtom2 > iAtom1, then every
+ * other lattice point with iAtom2 >= iAtom1), ewaldReciprocal (:2079-2117), rTerm (:2473-2489), and
+ * updateShifts' hemv(..., 'L') (:537-586).  invRMat(ld, nAtom) column-major, lower triangle
+ * (row >= column) filled, the rest zero.  norm2 is taken as sqrt(sum(x**2)).
+ * rLat(3, nRLat): lattice translations in absolute coordinates, ORIGIN FIRST (getCellTranslations order;
+ * the iterator of the dynamic list visits the same points in the same order without the origin).
+ * gLat(3, nG): reciprocal lattice points in absolute coordinates, no origin, no inversion pairs. */
+void orc_invr_cluster(int nAtom, const double *coord, double *invRMat, int ld)
+{
+  int i1, i2;
+  for (i1 = 0; i1 < nAtom; ++i1) {
+    for (i2 = 0; i2 < nAtom; ++i2) invRMat[i2 + (size_t)ld * i1] = 0.0;
+    for (i2 = i1 + 1; i2 < nAtom; ++i2) {
+      const double x = coord[3 * i1] - coord[3 * i2], y = coord[3 * i1 + 1] - coord[3 * i2 + 1],
+                   z = coord[3 * i1 + 2] - coord[3 * i2 + 2];
+      invRMat[i2 + (size_t)ld * i1] = 1.0 / sqrt(x * x + y * y + z * z);
+    }
+  }
+}
+
+void orc_invr_periodic(int nAtom, const double *coord, int nRLat, const double *rLat, int nG, const double *gLat,
+                       double alpha, double volume, double rCutoff, double *invRMat, int ld)
+{
+  const double pi = 3.14159265358979323846264338327950288;
+  const double cutoff2 = rCutoff * rCutoff;
+  int i1;
+#pragma omp parallel for schedule(dynamic, 8)
+  for (i1 = 0; i1 < nAtom; ++i1) {
+    double *col = invRMat + (size_t)ld * i1;
+    const double *c1 = coord + 3 * i1;
+    int i2, iL, iG;
+    for (i2 = 0; i2 < nAtom; ++i2) col[i2] = 0.0;
+    /* real space part: central cell (no self term), then all other lattice points */
+    for (iL = 0; iL < nRLat; ++iL) {
+      const double *L = rLat + 3 * iL;
+      for (i2 = (iL == 0 ? i1 + 1 : i1); i2 < nAtom; ++i2) {
+        const double nx = coord[3 * i2] + L[0], ny = coord[3 * i2 + 1] + L[1], nz = coord[3 * i2 + 2] + L[2];
+        const double dx = c1[0] - nx, dy = c1[1] - ny, dz = c1[2] - nz;
+        const double dist2 = dx * dx + dy * dy + dz * dz;
+        if (dist2 <= cutoff2) {
+          const double rr = sqrt(dist2);
+          col[i2] += erfc(alpha * rr) / rr; /* rTerm */
+        }
+      }
+    }
+    /* reciprocal space part */
+    for (i2 = i1; i2 < nAtom; ++i2) {
+      const double rx = c1[0] - coord[3 * i2], ry = c1[1] - coord[3 * i2 + 1], rz = c1[2] - coord[3 * i2 + 2];
+      const double g2Factor = -1.0 / (4.0 * alpha * alpha);
+      double s = 0.0;
+      for (iG = 0; iG < nG; ++iG) {
+        const double *g = gLat + 3 * iG;
+        const double g2 = g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+        const double gr = g[0] * rx + g[1] * ry + g[2] * rz;
+        s += exp(g2Factor * g2) / g2 * cos(gr);
+      }
+      col[i2] = col[i2] + 2.0 * s * 4.0 * pi / volume - pi / (volume * alpha * alpha);
+    }
+    /* extra contribution for self interaction */
+    col[i1] = col[i1] - 2.0 * alpha / sqrt(pi);
+  }
+}
+
+/* y = A x with the symmetric A given by its lower triangle (BLAS dsymv 'L' as hemv calls it, beta = 0) */
+void orc_symv_lower(int n, const double *A, int ld, const double *x, double *y)
+{
+  int i, j;
+  for (i = 0; i < n; ++i) y[i] = 0.0;
+  for (j = 0; j < n; ++j) {
+    double t = 0.0;
+    y[j] += A[j + (size_t)ld * j] * x[j];
+    for (i = j + 1; i < n; ++i) {
+      y[i] += A[i + (size_t)ld * j] * x[j];
+      t += A[i + (size_t)ld * j] * x[i];
+    }
+    y[j] += t;
+  }
+}

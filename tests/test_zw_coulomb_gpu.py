@@ -1,0 +1,94 @@
+"""SURVEY 8(f) N4, second piece: the Coulomb 1/R matrix (cluster and Ewald) and the shift product on the
+device, through the C ABI, against the oracle restatement (oracle/dftb_oracle.c orc_invr_*, pinned to the
+Madelung constants in test_coulomb_oracle.py)."""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import oracle, case  # noqa: F401
+from oracle import coulomb_model as cm
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hp():
+    from dftbplus_b200.api import HotPath
+    h = HotPath(0)
+    yield h
+    h.close()
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("n", [3, 64, 257, 1003])
+def test_invr_cluster(n, hp):
+    rng = np.random.default_rng(n)
+    x = rng.uniform(-20, 20, (n, 3))
+    got = hp.invRCluster(x)
+    ref = cm.invr_cluster(x)
+    assert np.all(np.triu(got) == 0.0)
+    assert _rel(got, ref) <= 2e-16      # one division and one square root, same operation order
+
+
+@pytest.mark.parametrize("name,take", [("fec128", None), ("fec128", 127), ("si512", None), ("water1002", None),
+                                       ("water1002", 333)])
+def test_invr_periodic_equals_the_oracle(name, take, hp):
+    """Even atom counts run the reciprocal part through the TMA-fed Gram kernel, odd ones through the
+    cp.async kernel; the real-space sums have the reference's order of terms."""
+    w, sk, geo, model, selfegy = case(name)
+    coord = w["coord0"] if take is None else w["coord0"][:take]
+    s = cm.ewald_setup(w["latvec"])
+    ref = cm.invr_periodic(coord, s)
+    got = hp.invRPeriodic(coord, s["rLat"], s["gLat"], s["alpha"], s["volume"], s["maxR"])
+    assert np.all(np.triu(got, 1) == 0.0)
+    assert _rel(got, ref) <= 1e-12
+    # shifts: the symmetric product with charges that sum to zero
+    rng = np.random.default_rng(7)
+    dq = rng.normal(size=len(coord))
+    dq -= dq.mean()
+    sh = hp.coulombShift(got, dq)
+    assert _rel(sh, cm.coulomb_shift(ref, dq)) <= 1e-12
+
+
+@pytest.mark.parametrize("structure,madelung", [("nacl", 1.7475645946331822), ("cscl", 1.7626747730709)])
+def test_madelung_constants_on_the_device(structure, madelung, hp):
+    a = 5.0 if structure == "nacl" else 4.0
+    lat = np.eye(3) * a
+    if structure == "nacl":
+        pos = np.array([[i, j, k] for i in range(2) for j in range(2) for k in range(2)], dtype=np.float64) * a / 2
+        q = np.array([1.0 if (i + j + k) % 2 == 0 else -1.0 for i in range(2) for j in range(2) for k in range(2)])
+        d = a / 2
+    else:
+        pos = np.array([[0, 0, 0], [a / 2, a / 2, a / 2]])
+        q = np.array([1.0, -1.0])
+        d = a * math.sqrt(3) / 2
+    s = cm.ewald_setup(lat)
+    invr = hp.invRPeriodic(pos, s["rLat"], s["gLat"], s["alpha"], s["volume"], s["maxR"])
+    v = hp.coulombShift(invr, q)
+    assert np.allclose(v * q, -madelung / d, rtol=0, atol=3e-7)
+
+
+def test_device_resident_chain(hp):
+    """Device pointers: the matrix is built and multiplied without leaving the GPU; a padded leading dimension."""
+    import torch
+    w, sk, geo, model, selfegy = case("si512")
+    s = cm.ewald_setup(w["latvec"])
+    n = len(w["coord0"])
+    ld = n + 6
+    hp.use_torch_stream()
+    coord = torch.from_numpy(np.ascontiguousarray(w["coord0"])).cuda()
+    invr = torch.full((n, ld), 7.0, dtype=torch.float64, device="cuda").t()   # column-major [ld, n] storage, junk inside
+    hp.invRPeriodic(coord, s["rLat"], s["gLat"], s["alpha"], s["volume"], s["maxR"], invr=invr)
+    dq = torch.from_numpy(np.random.default_rng(3).normal(size=n)).cuda()
+    sh = hp.coulombShift(invr, dq)
+    hp.synchronize()
+    ref = cm.invr_periodic(w["coord0"], s)
+    got = invr.cpu().numpy()[:n, :]
+    assert _rel(got, ref) <= 1e-12
+    assert np.all(invr.cpu().numpy()[n:, :] == 0.0)
+    assert _rel(sh.cpu().numpy(), cm.coulomb_shift(ref, dq.cpu().numpy())) <= 1e-12
+    hp.set_stream(None)
