@@ -13,7 +13,7 @@ unpack -> [eigensolve] -> DM -> pack -> Mulliken, with the eigensolve at the ful
 process), kpoints_si512 (BASELINE config 3: the complex chain, (k,spin) round-robin over the GPUs),
 md_water2046 (config 5: velocity-Verlet steps with list rebuild and SCC restart), multi_gpu (N > 1: the
 reference's split pair build + all-reduce measured against the replicated build), cpu_baseline (the oracle
-= restatement of the reference CPU path, rank 0, N = 1), neighbour_list.
+= restatement of the reference CPU path, rank 0, N = 1), neighbour_list, coulomb_ewald.
 
 `--impl reference` times that CPU restatement itself (the reference is Fortran and cannot be built in
 this image: no Fortran compiler) with all host threads, same config, same steps.
@@ -1117,6 +1117,18 @@ def main():
         except Exception as e:  # noqa: BLE001  (timeout included)
             n2 = {"error": repr(e)}
 
+    # ---- Coulomb 1/R matrix on the device (second piece), N = 1 only, in a child process ----
+    coul = None
+    if rank == 0 and world == 1 and not a.no_n2 and not a.pair_only:
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "coulomb_probe.py"), a.workload, "--oracle"],
+                               capture_output=True, text=True, timeout=300)
+            last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            coul = json.loads(last[-1]) if r.returncode == 0 and last else {
+                "error": "exit %d: %s" % (r.returncode, (r.stderr or r.stdout).strip().splitlines()[-1:])}
+        except Exception as e:  # noqa: BLE001  (timeout included)
+            coul = {"error": repr(e)}
+
     if rank == 0:
         cfg = config_for(a.workload, geo, n_spin, a.flush_l2)
         line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world,
@@ -1130,7 +1142,7 @@ def main():
                 "roofline_k5": roofline_k5, "roofline_dm": roofline_dm, "kernels": kernels, "stream_mix_same_size": stream_mix,
                 "scc_step": scc,
                 "kpoints_si512": kp_sec, "md_water2046": md_sec, "multi_gpu": multi, "cpu_baseline": cpu,
-                "neighbour_list": n2}
+                "neighbour_list": n2, "coulomb_ewald": coul}
         print(json.dumps(line), flush=True)
     hp.close()
     if world > 1:

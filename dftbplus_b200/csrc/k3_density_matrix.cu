@@ -506,19 +506,18 @@ int launchRealAuto(dftbp_b200_ctx *ctx, const double *dC, int ld, const double *
       DFTBP_TRY((launchRealTma<64, 16, 4, 2, 2>(ctx, 3, dC, ld, dW, n, K, dDm, ldd, counter)));
     } else if (variant == 31) {
       DFTBP_TRY((launchRealTma<64, 16, 3, 2, 2>(ctx, 4, dC, ld, dW, n, K, dDm, ldd, counter)));
-    } else if (variant == 33) {
-      DFTBP_TRY((launchRealTma<128, 16, 6, 2, 4>(ctx, 1, dC, ld, dW, n, K, dDm, ldd, counter)));
     } else if (variant == 34) {
       DFTBP_TRY((launchRealTma<128, 8, 6, 4, 2>(ctx, 1, dC, ld, dW, n, K, dDm, ldd, counter)));
     } else if (variant == 35) {
       DFTBP_TRY((launchRealTma<128, 16, 4, 4, 2>(ctx, 1, dC, ld, dW, n, K, dDm, ldd, counter)));
     } else if (variant == 36) {
       DFTBP_TRY((launchRealTma<128, 8, 8, 2, 4>(ctx, 1, dC, ld, dW, n, K, dDm, ldd, counter)));
-    } else if (variant == 37) {
-      DFTBP_TRY((launchRealTma<128, 16, 3, 2, 4>(ctx, 1, dC, ld, dW, n, K, dDm, ldd, counter)));
     } else {
       // 128 x 128 tiles, eight consumer warps of 64 x 32 + the producer warp, one CTA per SM: 34.3 TFLOP/s
-      // at n = 31744 (93 % of cuBLAS DGEMM; 64 x 64 tiles 32.7, the cp.async kernel of round 1 30.5)
+      // at n = 31744 (93 % of cuBLAS DGEMM; 64 x 64 tiles 32.7, the cp.async kernel of round 1 30.5).
+      // Four stages: the same tile with three or six stages ran 14 times slower (2.4 TFLOP/s, 32 us =
+      // 2^16 cycles per k-tile -- the time limit of mbarrier.try_wait, i.e. waiters that were only released
+      // by their own time-out; not understood, results correct; profiles/r2b_k3_tma.md)
       DFTBP_TRY((launchRealTma<128, 16, 4, 2, 4>(ctx, 1, dC, ld, dW, n, K, dDm, ldd, counter)));
     }
   } else if (n < 1024) {

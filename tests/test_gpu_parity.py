@@ -172,7 +172,7 @@ def test_k3_large_tiles(n, n_occ, hp_cache):
     assert np.abs(dm - ref).max() <= 1e-12 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("variant", [0, 20, 30, 31, 32, 33, 34, 35, 36, 37])
+@pytest.mark.parametrize("variant", [0, 20, 30, 31, 34, 35, 36])
 @pytest.mark.parametrize("n,n_occ", [(1502, 701), (66, 5), (640, 640), (4230, 77)])
 def test_k3_tma_feed_variants(variant, n, n_occ, hp_cache, monkeypatch):
     """TMA-fed K3 (cp.async.bulk + mbarrier pipeline, producer warp) in every tile configuration against
