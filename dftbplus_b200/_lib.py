@@ -70,6 +70,9 @@ SIGNATURES = {
     "dftbp_b200_invr_periodic": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_double, c_double,
                                          c_double, c_void_p, c_int]),
     "dftbp_b200_coulomb_shift": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "dftbp_b200_short_gamma_update": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "dftbp_b200_short_gamma_get": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dftbp_b200_short_gamma_shifts": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -196,8 +196,8 @@ class HotPath:
         """updateNeighbourListAndSpecies + getNrOfNeighboursForAll + getSparseDescriptor on the device
         (handleCoordinateChange, dftbplus/main.F90:2562-2578).  coord0[nAtom, 3] (host array or CUDA
         tensor), species0[nAtom] 1-based, cutoff = list cutoff, sk_cutoff (default: cutoff).
-        adopt: make the result the context's geometry (the caller's arrays are not involved; the library
-        itself reads the index arrays back once, ~2 MB, to build its block descriptors: ~4 ms at 4096 atoms); fetch: return the
+        adopt: make the result the context's geometry (the caller's arrays are not involved; on one rank the
+        work list and block descriptors are built by kernels, the host reads back nAtom + 2 ints); fetch: return the
         geometry dict of SURVEY.md section 8.0 (host copies), else only the sizes.  symmetric: the reference's
         symmetric list (for the host's use; never adopted)."""
         sk_cutoff = cutoff if sk_cutoff is None else sk_cutoff
@@ -229,6 +229,7 @@ class HotPath:
         if not fetch:
             sp = species0.cpu().numpy() if _is_torch(species0) else species0
             g["nOrb"] = int(self.nOrbSpecies[np.asarray(sp) - 1].sum())
+        self._last_list = g
         if adopt and not symmetric:
             self._ck(self._L.dftbp_b200_adopt_neighbour_list(self._h))
             self.geo = g        # without fetch: the sizes only (enough for the default output buffers)
@@ -452,6 +453,33 @@ class HotPath:
                 shift = np.zeros(n)
         self._ck(self._L.dftbp_b200_coulomb_shift(self._h, n, _ptr(invr), _ld(invr), _ptr(_f64(dq)), _ptr(shift)))
         return shift
+
+    def shortGammaUpdate(self, n_hubb_u, uniq_hubb_u, short_cutoffs, fetch=False):
+        """TShortGamma%updateCoords (dftb/shortgamma.F90:177-196) on the device neighbour list of the last
+        updateNeighbourListAndSpecies.  n_hubb_u [nSpecies], uniq_hubb_u [nSpecies, mU], short_cutoffs
+        [nSpecies(sp1), nSpecies(sp2), mU(iU1), mU(iU2)] = the Fortran arrays (mU, nSpecies) / (iU2, iU1, iSp2, iSp1).
+        fetch: return dict(nNeighU [nAtom, nSpecies, mU, mU], maxNeigh [nAtom], shortGamma [nAtom, mNeigh + 1, mU, mU])."""
+        nh = _i32(n_hubb_u)
+        uq = np.ascontiguousarray(uniq_hubb_u, dtype=np.float64)
+        sc = np.ascontiguousarray(short_cutoffs, dtype=np.float64)
+        n_sp, m_u = int(uq.shape[0]), int(uq.shape[1])
+        self._ck(self._L.dftbp_b200_short_gamma_update(self._h, n_sp, m_u, _ptr(nh), _ptr(uq), _ptr(sc)))
+        if not fetch:
+            return None
+        n, ld = self._last_list["nAtom"], self._last_list["mNeigh"] + 1
+        out = dict(nNeighU=np.zeros((n, n_sp, m_u, m_u), dtype=np.int32), maxNeigh=np.zeros(n, dtype=np.int32),
+                   shortGamma=np.zeros((n, ld, m_u, m_u)))
+        self._ck(self._L.dftbp_b200_short_gamma_get(self._h, _ptr(out["nNeighU"]), _ptr(out["maxNeigh"]), _ptr(out["shortGamma"])))
+        return out
+
+    def shortGammaShifts(self, i_hubb_u, dq_shell, shift_shell=None):
+        """TShortGamma%updateShifts (dftb/shortgamma.F90:220-244, buildShifts_ :860-933): dq_shell [nAtom, mShell]
+        -> shiftShell [nAtom, mShell]; i_hubb_u [nSpecies, mShell] (1-based, 0 = no shell)."""
+        dq = _f64(dq_shell)
+        if shift_shell is None:
+            shift_shell = np.zeros(tuple(dq.shape))
+        self._ck(self._L.dftbp_b200_short_gamma_shifts(self._h, _ptr(_i32(i_hubb_u)), _ptr(dq), _ptr(shift_shell)))
+        return shift_shell
 
     def diagDenseMtx(self, H, S, eigen=None, jobz="V"):
         """hegvd: H, S column-major, overwritten (H <- eigenvectors); returns eigenvalues."""

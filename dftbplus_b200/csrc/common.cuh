@@ -209,6 +209,8 @@ struct dftbp_b200_ctx {
   size_t solverWorkBytes = 0;
   int *dInfo = nullptr;
   void *neighbourState = nullptr;  // device-built neighbour list (n2_neighbour_list.cu)
+  void *shortGammaState = nullptr; // short-range gamma values of the current list (n4_coulomb.cu)
+  unsigned long long listGeneration = 0;  // counts update_neighbour_list calls (values derived from a list name theirs)
   // device blocks of the per-geometry arrays, kept across set_geometry calls (poolAlloc / poolRelease):
   // a geometry step re-uploads ~20 arrays of nearly the same sizes, and cudaFree + cudaMalloc of each
   // cost more than everything else in set_geometry (each cudaFree synchronises the device)
@@ -496,6 +498,16 @@ int ensureSortedPairs(dftbp_b200_ctx *ctx, bool forLoad, const SortedPairs **out
 void freeSortedPairs(dftbp_b200_ctx *ctx);
 void solverDestroy(dftbp_b200_ctx *ctx);
 void freeNeighbourList(dftbp_b200_ctx *ctx);
+// the arrays of the device neighbour list of the last update_neighbour_list (n2_neighbour_list.cu), for the
+// kernels of other translation units that walk it (short-range gamma, n4_coulomb.cu)
+struct NeighbourListView {
+  bool valid = false;
+  int nAtom = 0, nAllAtom = 0, mNeigh = 0;
+  const double *coords = nullptr, *neighDist2 = nullptr;
+  const int *species = nullptr, *img2CentCell = nullptr, *nNeighbour = nullptr, *iNeighbour = nullptr;
+};
+NeighbourListView neighbourListView(dftbp_b200_ctx *ctx);
+void freeShortGamma(dftbp_b200_ctx *ctx);
 // give the arrays of the current geometry back to the block pool (context.cu)
 void releaseGeometry(dftbp_b200_ctx *ctx);
 

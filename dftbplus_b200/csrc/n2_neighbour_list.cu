@@ -88,6 +88,18 @@ int copyOut(dftbp_b200_ctx *ctx, T *dst, const T *src, size_t count) {
 }  // namespace
 
 namespace dftbp_b200 {
+NeighbourListView neighbourListView(dftbp_b200_ctx *ctx) {
+  NeighbourListView v;
+  if (!ctx->neighbourState) return v;
+  const nl::NeighbourList &L = static_cast<NeighbourState *>(ctx->neighbourState)->list;
+  if (!L.valid || L.symmetric) return v;
+  v.valid = true;
+  v.nAtom = L.nAtom; v.nAllAtom = L.nAllAtom; v.mNeigh = L.mNeigh;
+  v.coords = L.coords.p; v.neighDist2 = L.neighDist2.p; v.species = L.species.p; v.img2CentCell = L.img2CentCell.p;
+  v.nNeighbour = L.nNeighbour.p; v.iNeighbour = L.iNeighbour.p;
+  return v;
+}
+
 void freeNeighbourList(dftbp_b200_ctx *ctx) {
   if (!ctx->neighbourState) return;
   NeighbourState *st = static_cast<NeighbourState *>(ctx->neighbourState);
@@ -252,6 +264,7 @@ int dftbp_b200_update_neighbour_list(dftbp_b200_ctx *ctx, int nAtom, const doubl
       DFTBP_CHECK(ctx, sp[i] >= 1 && sp[i] <= ctx->nSpecies, "update_neighbour_list: species out of range");
   }
   NeighbourState *st = stateOf(ctx);
+  ctx->listGeneration++;
   CudaBackend be{ctx};
   be.scanTemp = st->scanTemp;
   ScopedTimer timer(ctx, kTimerNeighbourList);

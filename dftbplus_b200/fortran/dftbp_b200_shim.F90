@@ -19,6 +19,7 @@ module dftbp_b200_shim
   public :: b200_derivative_shift, b200_addShift_block, b200_addShift_atom, b200_getBlockStress
   public :: b200_hegv_real, b200_hegv_cmplx, b200_Efilling
   public :: b200_invRCluster, b200_invRPeriodic, b200_coulombShifts
+  public :: b200_shortGammaUpdateCoords, b200_shortGammaShifts
 
   integer, parameter :: dp = c_double
 
@@ -268,6 +269,21 @@ module dftbp_b200_shim
       integer(c_int), value :: nAtom, ld
       real(c_double), intent(in) :: invRMat(*), deltaQAtom(*)
       real(c_double), intent(out) :: shiftPerAtom(*)
+    end function
+    integer(c_int) function dftbp_b200_short_gamma_update(ctx, nSpecies, mHubbU, nHubbU, uniqHubbU, shortCutoffs)&
+        & bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nSpecies, mHubbU
+      integer(c_int), intent(in) :: nHubbU(*)
+      real(c_double), intent(in) :: uniqHubbU(*), shortCutoffs(*)
+    end function
+    integer(c_int) function dftbp_b200_short_gamma_shifts(ctx, iHubbU, deltaQShell, shiftShell) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), intent(in) :: iHubbU(*)
+      real(c_double), intent(in) :: deltaQShell(*)
+      real(c_double), intent(out) :: shiftShell(*)
     end function
     integer(c_int) function dftbp_b200_adopt_neighbour_list(ctx) bind(C)
       import :: c_ptr, c_int
@@ -582,6 +598,25 @@ contains
     call check(ctx, dftbp_b200_coulomb_shift(ctx%h, size(deltaQAtom), invRMat, size(invRMat, dim=1), deltaQAtom,&
         & shiftPerAtom))
   end subroutine b200_coulombShifts
+
+  !> TShortGamma%updateCoords, dftb/shortgamma.F90:177 (undamped, no H5), on the device neighbour list of the
+  !> last b200_updateNeighbourListAndSpecies: nHubbU / uniqHubbU = this%hubbU_, shortCutoffs = this%shortCutoffs_
+  subroutine b200_shortGammaUpdateCoords(ctx, nHubbU, uniqHubbU, shortCutoffs)
+    type(TB200Ctx), intent(in) :: ctx
+    integer, intent(in) :: nHubbU(:)
+    real(dp), intent(in) :: uniqHubbU(:,:), shortCutoffs(:,:,:,:)
+    call check(ctx, dftbp_b200_short_gamma_update(ctx%h, size(nHubbU), size(shortCutoffs, dim=1),&
+        & int(nHubbU, c_int), uniqHubbU(1:size(shortCutoffs, dim=1), :), shortCutoffs))
+  end subroutine b200_shortGammaUpdateCoords
+
+  !> TShortGamma%updateShifts, dftb/shortgamma.F90:220: shiftShell(mShell, nAtom) = buildShifts_(deltaQShell)
+  subroutine b200_shortGammaShifts(ctx, iHubbU, deltaQShell, shiftShell)
+    type(TB200Ctx), intent(in) :: ctx
+    integer, intent(in) :: iHubbU(:,:)
+    real(dp), intent(in) :: deltaQShell(:,:)
+    real(dp), intent(out) :: shiftShell(:,:)
+    call check(ctx, dftbp_b200_short_gamma_shifts(ctx%h, int(iHubbU, c_int), deltaQShell, shiftShell))
+  end subroutine b200_shortGammaShifts
 
   !> mullikenPerBlock, dftb/populations.F90:306 -- qq(mOrb, mOrb, nAtom) accumulates
   subroutine b200_mullikenPerBlock(ctx, qq, over, rho)

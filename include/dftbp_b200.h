@@ -321,6 +321,25 @@ int dftbp_b200_invr_periodic(dftbp_b200_ctx *ctx, int nAtom, const double *coord
 int dftbp_b200_coulomb_shift(dftbp_b200_ctx *ctx, int nAtom, const double *invRMat, int ld,
                              const double *deltaQAtom, double *shiftPerAtom);
 
+/* Short-range gamma of the SCC shifts (third piece), on the device neighbour list of the last
+ * dftbp_b200_update_neighbour_list (its cutoff must cover the largest short-range cutoff, as mCutOff does in
+ * the reference).  Arrays in the reference's layout, host or device pointers.
+ *
+ * short_gamma_update: TShortGamma%updateCoords, dftb/shortgamma.F90:177-196 = updateNrOfNeighbours_ (:779-801,
+ *   getNrOfNeighbours per (iU2, iU1, species, atom) with shortCutoffs(mHubbU, mHubbU, nSpecies, nSpecies) from
+ *   setupShortGammaCutoffs_) + updateShortGammaValues_ (:804-857, expGamma of shortgammafuncs.F90:97-148; no
+ *   damping, no H5 correction -- those stay with the Fortran routine).  nHubbU(nSpecies), uniqHubbU(mHubbU,
+ *   nSpecies): this%hubbU_ (TUniqueHubbard).  mHubbU <= 4.  Call it after every neighbour-list update.
+ * short_gamma_get: nNeigh_(mHubbU, mHubbU, nSpecies, nAtom), maxval over the first three dimensions per atom,
+ *   shortGamma_(mHubbU, mHubbU, 0:mNeigh, nAtom) of the last update (any pointer may be NULL).
+ * short_gamma_shifts: TShortGamma%updateShifts -> buildShifts_, dftb/shortgamma.F90:860-933: shiftShell(mShell,
+ *   nAtom) from deltaQShell(mShell, nAtom) and iHubbU(mShell, nSpecies) (overwrites shiftShell). */
+int dftbp_b200_short_gamma_update(dftbp_b200_ctx *ctx, int nSpecies, int mHubbU, const int *nHubbU,
+                                  const double *uniqHubbU, const double *shortCutoffs);
+int dftbp_b200_short_gamma_get(dftbp_b200_ctx *ctx, int *nNeighU, int *maxNeigh, double *shortGamma);
+int dftbp_b200_short_gamma_shifts(dftbp_b200_ctx *ctx, const int *iHubbU, const double *deltaQShell,
+                                  double *shiftShell);
+
 /* ---- not rewritten: dense generalized eigensolve via cuSOLVER ------------------------------- */
 
 /* diagDenseMtx, dftbplus/eigenvects.F90:85-100 (hegvd branch): H C = S C diag(eigen), lower

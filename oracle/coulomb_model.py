@@ -180,3 +180,84 @@ def coulomb_shift(invr, dq):
     y = np.zeros(n)
     _o.lib().orc_symv_lower(n, _o._d(invr), invr.shape[0], _o._d(dq), _o._d(y))
     return y
+
+
+# ---- short-range gamma (dftb/shortgamma.F90, dftb/shortgammafuncs.F90, dftb/uniquehubbard.F90) ----------------
+MIN_HUB_DIFF = 0.3125e-5
+
+
+def unique_hubbard(hubb_u, n_shell):
+    """TUniqueHubbard_init (dftb/uniquehubbard.F90:58-100): hubb_u[sp][shell] -> nHubbU[sp], uniqHubbU[sp][mU],
+    iHubbU[sp][mShell] (1-based, 0 = no such shell), mU."""
+    n_sp = len(n_shell)
+    m_shell = max(n_shell)
+    n_u = [1] * n_sp
+    uniq = np.zeros((n_sp, m_shell))
+    i_u = np.zeros((n_sp, m_shell), dtype=np.int32)
+    for sp in range(n_sp):
+        uniq[sp, 0] = hubb_u[sp][0]
+        i_u[sp, 0] = 1
+        for il in range(1, n_shell[sp]):
+            for iu in range(n_u[sp]):
+                if abs(hubb_u[sp][il] - uniq[sp, iu]) < MIN_HUB_DIFF:
+                    i_u[sp, il] = iu + 1
+                    break
+            else:
+                uniq[sp, n_u[sp]] = hubb_u[sp][il]
+                n_u[sp] += 1
+                i_u[sp, il] = n_u[sp]
+    m_u = max(n_u)
+    return dict(nHubbU=np.array(n_u, dtype=np.int32), uniqHubbU=np.ascontiguousarray(uniq[:, :m_u]), iHubbU=i_u, mU=m_u,
+                mShell=m_shell, nShell=np.array(n_shell, dtype=np.int32))
+
+
+def _gamma_lib():
+    lib = _o.lib()
+    lib.orc_exp_gamma.restype = ctypes.c_double
+    lib.orc_exp_gamma.argtypes = [ctypes.c_double] * 3
+    lib.orc_exp_gamma_cutoff.restype = ctypes.c_double
+    lib.orc_exp_gamma_cutoff.argtypes = [ctypes.c_double] * 2
+    return lib
+
+
+def exp_gamma(rab, ua, ub):
+    return _gamma_lib().orc_exp_gamma(rab, ua, ub)
+
+
+def short_gamma_cutoffs(hub):
+    """setupShortGammaCutoffs_: shortCutoffs[sp1][sp2][iU1][iU2] = Fortran (iU2, iU1, iSp2, iSp1)."""
+    lib = _gamma_lib()
+    n_sp, m_u = len(hub["nHubbU"]), hub["mU"]
+    c = np.zeros((n_sp, n_sp, m_u, m_u))
+    for s1 in range(n_sp):
+        for s2 in range(s1, n_sp):
+            for u1 in range(hub["nHubbU"][s1]):
+                for u2 in range(hub["nHubbU"][s2]):
+                    v = lib.orc_exp_gamma_cutoff(hub["uniqHubbU"][s2, u2], hub["uniqHubbU"][s1, u1])
+                    c[s1, s2, u1, u2] = v
+                    c[s2, s1, u2, u1] = v
+    return c
+
+
+def short_gamma_values(nl, hub, cutoffs):
+    """updateCoords of TShortGamma on the full neighbour list nl (oracle.neighbour_list_full)."""
+    n, m_n, m_u, n_sp = nl["nAtom"], nl["mNeigh"], hub["mU"], len(hub["nHubbU"])
+    n_neigh_u = np.zeros((n, n_sp, m_u, m_u), dtype=np.int32)
+    max_neigh = np.zeros(n, dtype=np.int32)
+    gam = np.zeros((n, m_n + 1, m_u, m_u))
+    _o.lib().orc_short_gamma_values(n, m_n, m_u, n_sp, _o._i(hub["nHubbU"]), _o._d(hub["uniqHubbU"]),
+                                    _o._d(np.ascontiguousarray(cutoffs)), _o._i(nl["species"]), _o._d(nl["coords"]),
+                                    _o._i(nl["nNeighbour"]), _o._i(nl["iNeighbour"]), _o._d(nl["neighDist2"]),
+                                    _o._i(n_neigh_u), _o._i(max_neigh), _o._d(gam))
+    return dict(nNeighU=n_neigh_u, maxNeigh=max_neigh, shortGamma=gam)
+
+
+def short_gamma_shifts(nl, hub, vals, dq_shell):
+    n, m_n, m_u, m_sh = nl["nAtom"], nl["mNeigh"], hub["mU"], hub["mShell"]
+    dq_shell = np.ascontiguousarray(dq_shell, dtype=np.float64)
+    out = np.zeros((n, m_sh))
+    _o.lib().orc_short_gamma_shifts(n, m_n, m_u, m_sh, len(hub["nHubbU"]), _o._i(hub["nShell"]),
+                                    _o._i(np.ascontiguousarray(hub["iHubbU"])), _o._i(nl["species"]), _o._i(nl["img2CentCell"]),
+                                    _o._i(nl["iNeighbour"]), _o._i(vals["maxNeigh"]), _o._d(vals["shortGamma"]),
+                                    _o._d(dq_shell), _o._d(out))
+    return out

@@ -1387,3 +1387,129 @@ void orc_symv_lower(int n, const double *A, int ld, const double *x, double *y)
     y[j] += t;
   }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Short-range gamma of the SCC shifts: expGamma / gammaSubExprn_ / expGammaCutoff
+ * (dftb/shortgammafuncs.F90:36-148, 470-500), setupShortGammaCutoffs_, updateNrOfNeighbours_,
+ * updateShortGammaValues_ (no damping, no H5) and buildShifts_ (dftb/shortgamma.F90:753-936).
+ * minHubDiff 0.3125e-5, minHubTol 1e-6, minShortGamma = tolShortGamma = 1e-10, tolSameDist 1e-5
+ * (common/accuracy.F90).  Arrays column-major with the reference's index order:
+ *   uniqHubbU(mU, nSpecies), shortCutoffs(mU, mU, nSpecies, nSpecies), nNeighU(mU, mU, nSpecies, nAtom),
+ *   shortGamma(mU, mU, 0:mNeigh, nAtom), iHubbU(mShell, nSpecies), deltaQShell / shiftShell(mShell, nAtom). */
+static const double minHubDiff = 0.3125e-5, tolSameDist = 1.0e-5, tolShortGamma = 1.0e-10, minShortGamma = 1.0e-10;
+
+static double gamma_sub_exprn(double rab, double tau1, double tau2)
+{
+  const double d2 = tau1 * tau1 - tau2 * tau2;
+  return exp(-tau1 * rab) * ((0.5 * tau2 * tau2 * tau2 * tau2 * tau1 / (d2 * d2))
+                             - (tau2 * tau2 * tau2 * tau2 * tau2 * tau2 - 3.0 * tau2 * tau2 * tau2 * tau2 * tau1 * tau1)
+                                   / (rab * (d2 * d2 * d2)));
+}
+
+double orc_exp_gamma(double rab, double Ua, double Ub)
+{
+  const double tauA = 3.2 * Ua, tauB = 3.2 * Ub;
+  if (rab < tolSameDist) {
+    if (fabs(Ua - Ub) < minHubDiff) return -0.5 * (Ua + Ub);
+    return -0.5 * ((tauA * tauB) / (tauA + tauB) + (tauA * tauB) * (tauA * tauB) / ((tauA + tauB) * (tauA + tauB) * (tauA + tauB)));
+  }
+  if (fabs(Ua - Ub) < minHubDiff) {
+    const double tauMean = 0.5 * (tauA + tauB);
+    return exp(-tauMean * rab) * (1.0 / rab + 0.6875 * tauMean + 0.1875 * rab * (tauMean * tauMean)
+                                  + 0.02083333333333333333 * (rab * rab) * (tauMean * tauMean * tauMean));
+  }
+  return gamma_sub_exprn(rab, tauA, tauB) + gamma_sub_exprn(rab, tauB, tauA);
+}
+
+double orc_exp_gamma_cutoff(double U2, double U1)
+{
+  const double cutValue = minShortGamma;
+  double rab = 1.0, minCutOff, maxCutOff, maxGamma, minGamma, lowerGamma, cut, gamma;
+  while (orc_exp_gamma(rab, U2, U1) > cutValue) rab = 2.0 * rab;
+  if (rab < 2.0) return -1.0; /* "requested tolerance too large" */
+  minCutOff = rab + 0.1;
+  maxCutOff = 0.5 * rab - 0.1;
+  maxGamma = orc_exp_gamma(maxCutOff, U2, U1);
+  minGamma = orc_exp_gamma(minCutOff, U2, U1);
+  lowerGamma = orc_exp_gamma(minCutOff, U2, U1);
+  cut = maxCutOff + 0.1;
+  gamma = orc_exp_gamma(cut, U2, U1);
+  while ((gamma - lowerGamma) > tolShortGamma) {
+    maxCutOff = 0.5 * (cut + minCutOff);
+    if ((maxGamma >= minGamma) == (cutValue >= orc_exp_gamma(maxCutOff, U2, U1))) {
+      minCutOff = maxCutOff;
+      lowerGamma = orc_exp_gamma(minCutOff, U2, U1);
+    } else {
+      cut = maxCutOff;
+      gamma = orc_exp_gamma(cut, U2, U1);
+    }
+  }
+  return minCutOff;
+}
+
+/* updateNrOfNeighbours_ + updateShortGammaValues_; maxNeighOut(nAtom) = maxval(nNeigh(:,:,:,iAt)) */
+void orc_short_gamma_values(int nAtom, int mNeigh, int mU, int nSpecies, const int *nHubbU, const double *uniqHubbU,
+                            const double *shortCutoffs, const int *species, const double *coords,
+                            const int *nNeighbour, const int *iNeighbour, const double *neighDist2,
+                            int *nNeighU, int *maxNeighOut, double *shortGamma)
+{
+  const int ld = mNeigh + 1;
+  int iAt, iSp, iU1, iU2, iNeigh;
+  for (iAt = 0; iAt < nAtom; ++iAt) {
+    const int sp1 = species[iAt] - 1;
+    int mx = 0;
+    for (iSp = 0; iSp < nSpecies; ++iSp)
+      for (iU1 = 0; iU1 < mU; ++iU1)
+        for (iU2 = 0; iU2 < mU; ++iU2) {
+          int v = 0;
+          if (iU1 < nHubbU[sp1] && iU2 < nHubbU[iSp]) {
+            const double c = shortCutoffs[iU2 + mU * (iU1 + mU * (iSp + nSpecies * sp1))];
+            v = orc_search_asc_real_geq(nNeighbour[iAt], neighDist2 + ld * iAt + 1, c * c, tolSameDist2);
+          }
+          nNeighU[iU2 + mU * (iU1 + mU * (iSp + nSpecies * iAt))] = v;
+          if (v > mx) mx = v;
+        }
+    maxNeighOut[iAt] = mx;
+    for (iNeigh = 0; iNeigh < ld * mU * mU; ++iNeigh) shortGamma[(size_t)ld * mU * mU * iAt + iNeigh] = 0.0;
+    for (iNeigh = 0; iNeigh <= mx; ++iNeigh) {
+      const int iAt2 = iNeighbour[iNeigh + ld * iAt] - 1, sp2 = species[iAt2] - 1;
+      const double dx = coords[3 * iAt] - coords[3 * iAt2], dy = coords[3 * iAt + 1] - coords[3 * iAt2 + 1],
+                   dz = coords[3 * iAt + 2] - coords[3 * iAt2 + 2];
+      const double rab = sqrt(dx * dx + dy * dy + dz * dz);
+      for (iU1 = 0; iU1 < nHubbU[sp1]; ++iU1)
+        for (iU2 = 0; iU2 < nHubbU[sp2]; ++iU2)
+          if (iNeigh <= nNeighU[iU2 + mU * (iU1 + mU * (sp2 + nSpecies * iAt))])
+            shortGamma[iU2 + mU * (iU1 + mU * (iNeigh + (size_t)ld * iAt))] =
+                orc_exp_gamma(rab, uniqHubbU[iU2 + mU * sp2], uniqHubbU[iU1 + mU * sp1]);
+    }
+  }
+}
+
+/* buildShifts_ (serial branch: all atoms in order) */
+void orc_short_gamma_shifts(int nAtom, int mNeigh, int mU, int mShell, int nSpecies, const int *nShell,
+                            const int *iHubbU, const int *species, const int *img2CentCell, const int *iNeighbour,
+                            const int *maxNeigh, const double *shortGamma, const double *deltaQShell,
+                            double *shiftShell)
+{
+  const int ld = mNeigh + 1;
+  int iAt1, iSh1, iSh2, iNeigh;
+  (void)nSpecies;
+  for (iAt1 = 0; iAt1 < mShell * nAtom; ++iAt1) shiftShell[iAt1] = 0.0;
+  for (iAt1 = 0; iAt1 < nAtom; ++iAt1) {
+    const int sp1 = species[iAt1] - 1;
+    for (iSh1 = 0; iSh1 < nShell[sp1]; ++iSh1) {
+      const int iU1 = iHubbU[iSh1 + mShell * sp1] - 1;
+      const double dq1 = deltaQShell[iSh1 + mShell * iAt1];
+      for (iNeigh = 0; iNeigh <= maxNeigh[iAt1]; ++iNeigh) {
+        const int iAt2f = img2CentCell[iNeighbour[iNeigh + ld * iAt1] - 1] - 1, sp2 = species[iAt2f] - 1;
+        for (iSh2 = 0; iSh2 < nShell[sp2]; ++iSh2) {
+          const int iU2 = iHubbU[iSh2 + mShell * sp2] - 1;
+          const double g = shortGamma[iU2 + mU * (iU1 + mU * (iNeigh + (size_t)ld * iAt1))];
+          shiftShell[iSh1 + mShell * iAt1] = shiftShell[iSh1 + mShell * iAt1] - g * deltaQShell[iSh2 + mShell * iAt2f];
+          if (iAt2f != iAt1)
+            shiftShell[iSh2 + mShell * iAt2f] = shiftShell[iSh2 + mShell * iAt2f] - g * dq1;
+        }
+      }
+    }
+  }
+}

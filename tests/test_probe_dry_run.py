@@ -54,6 +54,15 @@ class _FakeHotPath:
     def set_geometry(self, geo):
         self.geo = geo
 
+    # N4 stand-ins (flow only): the values come from the checker itself
+    def invRPeriodic(self, coord, r_lat, g_lat, alpha, volume, r_cutoff, invr=None):
+        from oracle import coulomb_model as cm
+        return cm.invr_periodic(coord, dict(rLat=r_lat, gLat=g_lat, alpha=alpha, volume=volume, maxR=r_cutoff))
+
+    def coulombShift(self, invr, dq, shift=None):
+        from oracle import coulomb_model as cm
+        return cm.coulomb_shift(invr, dq)
+
     def close(self):
         pass
 

@@ -92,3 +92,65 @@ def test_device_resident_chain(hp):
     assert np.all(invr.cpu().numpy()[n:, :] == 0.0)
     assert _rel(sh.cpu().numpy(), cm.coulomb_shift(ref, dq.cpu().numpy())) <= 1e-12
     hp.set_stream(None)
+
+
+# ---- short-range gamma (third piece) ------------------------------------------------------------------------
+def _hubbard_for(sk, resolved):
+    """Synthetic Hubbard U per shell: shell-resolved (distinct values, two shells of one species sharing one) or one
+    value per species (the reference's default, orbital-resolved SCC off)."""
+    n_shell = [len(a) for a in sk.ang_shells]
+    if resolved:
+        base = [[0.31, 0.27, 0.27, 0.22], [0.42, 0.36, 0.30, 0.25], [0.5, 0.45, 0.4, 0.35]]
+    else:
+        base = [[0.31] * 4, [0.42] * 4, [0.5] * 4]
+    return [base[i % 3][:n] for i, n in enumerate(n_shell)], n_shell
+
+
+@pytest.mark.parametrize("name,resolved", [("h2o", True), ("ce_o", True), ("fec128", True), ("fec128", False),
+                                           ("si512", False), ("water1002", True)])
+def test_short_gamma_on_the_device_list(name, resolved):
+    from dftbplus_b200.api import HotPath
+    w, sk, geo, model, selfegy = case(name)
+    hub_u, n_shell = _hubbard_for(sk, resolved)
+    hub = cm.unique_hubbard(hub_u, n_shell)
+    cut = cm.short_gamma_cutoffs(hub)
+    cutoff = max(sk.cutoff(), float(cut.max()))          # mCutOff: the list covers every short-range cutoff
+    rcell = np.zeros((1, 3)) if w["latvec"] is None else oracle.cell_translations(w["latvec"], cutoff)[1]
+    nl = oracle.neighbour_list_full(sk.n_orb_species, w["coord0"], w["species0"], rcell, cutoff, sk.cutoff())
+    ref = cm.short_gamma_values(nl, hub, cut)
+    hp = HotPath(0)
+    sk.upload(hp)
+    g = hp.updateNeighbourListAndSpecies(w["coord0"], w["species0"], cutoff, w["latvec"], sk_cutoff=sk.cutoff(), adopt=True)
+    assert g["mNeigh"] == nl["mNeigh"] and np.array_equal(g["iNeighbour"], nl["iNeighbour"])
+    got = hp.shortGammaUpdate(hub["nHubbU"], hub["uniqHubbU"], cut, fetch=True)
+    assert np.array_equal(got["nNeighU"], ref["nNeighU"]) and np.array_equal(got["maxNeigh"], ref["maxNeigh"])
+    scale = np.abs(ref["shortGamma"]).max()
+    assert np.abs(got["shortGamma"] - ref["shortGamma"]).max() <= 1e-13 * scale
+    assert int(ref["maxNeigh"].max()) > 0 or nl["nAtom"] == 1
+    rng = np.random.default_rng(11)
+    dq = rng.normal(size=(nl["nAtom"], hub["mShell"])) * 0.1
+    for a in range(nl["nAtom"]):                          # no charge on shells a species does not have
+        dq[a, n_shell[w["species0"][a] - 1]:] = 0.0
+    sh = hp.shortGammaShifts(hub["iHubbU"], dq)
+    sh_ref = cm.short_gamma_shifts(nl, hub, ref, dq)
+    assert np.abs(sh - sh_ref).max() <= 1e-12 * max(1.0, np.abs(sh_ref).max())
+    # a new list invalidates the values until updateCoords is repeated
+    from dftbplus_b200.api import DftbB200Error
+    hp.updateNeighbourListAndSpecies(w["coord0"][: max(1, nl["nAtom"] - 1)], w["species0"][: max(1, nl["nAtom"] - 1)],
+                                     cutoff, w["latvec"], sk_cutoff=sk.cutoff(), adopt=False, fetch=False)
+    if nl["nAtom"] > 1:
+        with pytest.raises(DftbB200Error):
+            hp.shortGammaShifts(hub["iHubbU"], dq)
+    hp.close()
+
+
+def test_gamma_limits_of_the_oracle():
+    """gamma = 1/R - expGamma -> the Hubbard U on site (equal U) and the closed form for different U;
+    continuity across the minHubDiff switch."""
+    for r in (1e-4, 1e-3):
+        assert abs(1.0 / r - cm.exp_gamma(r, 0.3, 0.3) - 0.3) < 1e-5
+    ta, tb = 3.2 * 0.3, 3.2 * 0.4
+    lim = 0.5 * (ta * tb / (ta + tb) + (ta * tb) ** 2 / (ta + tb) ** 3)
+    assert abs(1.0 / 1e-3 - cm.exp_gamma(1e-3, 0.3, 0.4) - lim) < 1e-5
+    assert abs(cm.exp_gamma(0.0, 0.3, 0.4) + lim) < 1e-15 and cm.exp_gamma(0.0, 0.3, 0.3) == -0.3
+    assert abs(cm.exp_gamma(3.0, 0.3, 0.3 + 2e-6) - cm.exp_gamma(3.0, 0.3, 0.3 + 4e-6)) < 1e-6
