@@ -85,3 +85,17 @@ def test_cluster_matrix_and_shift():
     q = rng.normal(size=17)
     full = ref + ref.T
     assert np.abs(cm.coulomb_shift(a, q) - full @ q).max() < 1e-13
+
+
+def test_gamma_limits_of_the_oracle():
+    """gamma = 1/R - expGamma -> the Hubbard U on site (equal U) and the closed form for different U;
+    continuity across the minHubDiff switch."""
+    for r in (1e-4, 1e-3):
+        assert abs(1.0 / r - cm.exp_gamma(r, 0.3, 0.3) - 0.3) < 1e-5
+    ta, tb = 3.2 * 0.3, 3.2 * 0.4
+    lim = 0.5 * (ta * tb / (ta + tb) + (ta * tb) ** 2 / (ta + tb) ** 3)
+    assert abs(1.0 / 1e-3 - cm.exp_gamma(1e-3, 0.3, 0.4) - lim) < 1e-5
+    assert abs(cm.exp_gamma(0.0, 0.3, 0.4) + lim) < 1e-15 and cm.exp_gamma(0.0, 0.3, 0.3) == -0.3
+    # the general formula joins the equal-U one (just above minHubDiff it cancels catastrophically -- in the
+    # reference too: 1.4e-3 off at U2 - U1 = 4e-6 -- so the join is checked at a separation of 1e-3)
+    assert abs(cm.exp_gamma(3.0, 0.3, 0.301) - 0.5 * (cm.exp_gamma(3.0, 0.3, 0.3) + cm.exp_gamma(3.0, 0.301, 0.301))) < 1e-6

@@ -142,15 +142,3 @@ def test_short_gamma_on_the_device_list(name, resolved):
         with pytest.raises(DftbB200Error):
             hp.shortGammaShifts(hub["iHubbU"], dq)
     hp.close()
-
-
-def test_gamma_limits_of_the_oracle():
-    """gamma = 1/R - expGamma -> the Hubbard U on site (equal U) and the closed form for different U;
-    continuity across the minHubDiff switch."""
-    for r in (1e-4, 1e-3):
-        assert abs(1.0 / r - cm.exp_gamma(r, 0.3, 0.3) - 0.3) < 1e-5
-    ta, tb = 3.2 * 0.3, 3.2 * 0.4
-    lim = 0.5 * (ta * tb / (ta + tb) + (ta * tb) ** 2 / (ta + tb) ** 3)
-    assert abs(1.0 / 1e-3 - cm.exp_gamma(1e-3, 0.3, 0.4) - lim) < 1e-5
-    assert abs(cm.exp_gamma(0.0, 0.3, 0.4) + lim) < 1e-15 and cm.exp_gamma(0.0, 0.3, 0.3) == -0.3
-    assert abs(cm.exp_gamma(3.0, 0.3, 0.3 + 2e-6) - cm.exp_gamma(3.0, 0.3, 0.3 + 4e-6)) < 1e-6
