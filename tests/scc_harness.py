@@ -65,6 +65,12 @@ class OracleArm:
         ham[0] += h0
         return ham[0]
 
+    def add_shift_block(self, h0, over, shift_block):
+        ham = self.o.add_shift(self.m, self.geo, np.zeros((1, self.geo["sparseSize"])), over, shift_block,
+                               is_input_zero=True)
+        ham[0] += h0
+        return ham[0]
+
     def solve(self, ham, over):
         H, S = self.o.unpack_hs_real(self.geo, ham), self.o.unpack_hs_real(self.geo, over)
         eig, C = scipy.linalg.eigh(H, S, lower=True)
@@ -95,6 +101,12 @@ class DeviceArm:
     def add_shift(self, h0, over, shift_atom):
         ham = np.zeros((1, self.geo["sparseSize"]))
         self.hp.addShift(ham, over, np.ascontiguousarray(shift_atom[None, :]), is_input_zero=True)
+        ham[0] += h0
+        return ham[0]
+
+    def add_shift_block(self, h0, over, shift_block):
+        ham = np.zeros((1, self.geo["sparseSize"]))
+        self.hp.addShift(ham, over, np.ascontiguousarray(shift_block), is_input_zero=True)
         ham[0] += h0
         return ham[0]
 
@@ -223,3 +235,117 @@ def velocity_verlet(make_arm, workload, sk, m_orb, n_steps, dt=20.670687, mix=0.
         steps.append(dict(n_iter=r["n_iter"], energy=r["energy"], sparseSize=geo["sparseSize"],
                           e_kin=0.5 * float((mass * v * v).sum())))
     return dict(steps=steps, x=x, v=v, q=r["q"], forces=r["forces"])
+
+
+# ---- the reference's own SCC potential: gamma = 1/R (cluster or Ewald) - short-range gamma ------
+class OracleGamma:
+    """TCoulomb + TShortGamma restated (oracle/coulomb_model.py, oracle/dftb_oracle.c): 1/R matrix once per
+    geometry, short-range gamma values on the full neighbour list, shifts per SCC iteration."""
+
+    def __init__(self, oracle, sk, workload, hub):
+        from oracle import coulomb_model as cm
+        self.cm, self.hub = cm, hub
+        coord0, species0, lat = np.asarray(workload["coord0"], dtype=float), workload["species0"], workload["latvec"]
+        cuts = cm.short_gamma_cutoffs(hub)
+        cutoff = max(sk.cutoff(), float(cuts.max()))
+        rcell = np.zeros((1, 3)) if lat is None else oracle.cell_translations(lat, cutoff)[1]
+        self.nl = oracle.neighbour_list_full(sk.n_orb_species, coord0, species0, rcell, cutoff, sk.cutoff())
+        self.vals = cm.short_gamma_values(self.nl, hub, cuts)
+        self.invr = cm.invr_cluster(coord0) if lat is None else cm.invr_periodic(coord0, cm.ewald_setup(lat))
+
+    def shifts(self, dq_shell):
+        return (self.cm.coulomb_shift(self.invr, dq_shell.sum(axis=1)),
+                self.cm.short_gamma_shifts(self.nl, self.hub, self.vals, dq_shell))
+
+
+class DeviceGamma:
+    """The same through the C ABI: dftbp_b200_update_neighbour_list (list cutoff = the largest of all cutoffs,
+    sparse structure from the SK cutoff, adopted as the geometry of the pair kernels), _invr_cluster /
+    _invr_periodic, _short_gamma_update once per geometry; _coulomb_shift + _short_gamma_shifts per iteration."""
+
+    def __init__(self, hp, sk, workload, hub):
+        from oracle import coulomb_model as cm          # input set-up only (Ewald parameters, cutoffs): host logic
+        self.hp, self.hub = hp, hub
+        coord0, species0, lat = np.asarray(workload["coord0"], dtype=float), workload["species0"], workload["latvec"]
+        cuts = cm.short_gamma_cutoffs(hub)
+        cutoff = max(sk.cutoff(), float(cuts.max()))
+        self.geo = hp.updateNeighbourListAndSpecies(coord0, species0, cutoff, lat, sk_cutoff=sk.cutoff(), adopt=True)
+        hp.shortGammaUpdate(hub["nHubbU"], hub["uniqHubbU"], cuts)
+        if lat is None:
+            self.invr = hp.invRCluster(coord0)
+        else:
+            ew = cm.ewald_setup(lat)
+            self.invr = hp.invRPeriodic(coord0, ew["rLat"], ew["gLat"], ew["alpha"], ew["volume"], ew["maxR"])
+
+    def shifts(self, dq_shell):
+        return (self.hp.coulombShift(self.invr, np.ascontiguousarray(dq_shell.sum(axis=1))),
+                self.hp.shortGammaShifts(self.hub["iHubbU"], np.ascontiguousarray(dq_shell)))
+
+
+def scc_reference_potential(arm, gam, workload, sk, geo, m_orb, tol=1e-8, max_iter=100):
+    """SCC single point with the reference's potential and defaults: shifts from `gam` (1/R - short-range
+    gamma, one Hubbard U per species as without OrbitalResolvedSCC), added as diagonal block shifts
+    (addShift_block), atom-reduced charges through the Broyden mixer, Efilling at minTemp.  Both arms run this
+    same host loop; the arm and gam objects decide whether a step is the CPU restatement or the CUDA library.
+    The gamma-derivative force terms (addGradientsDc, addInvRPrime) are outside the hot path and left out on
+    both sides: `forces` is the derivative_shift part."""
+    species0 = np.asarray(workload["species0"])
+    n_atom, m_shell = geo["nAtom"], max(len(a) for a in sk.ang_shells)
+    q0 = np.zeros((n_atom, m_orb))
+    shell_of = np.zeros((n_atom, m_orb), dtype=int)
+    n_orb_atom = np.zeros(n_atom, dtype=int)
+    for i, s in enumerate(species0):
+        k = 0
+        for ish, (l, occ) in enumerate(zip(sk.ang_shells[s - 1], sk.occ[s - 1])):
+            q0[i, k:k + 2 * l + 1] = occ / (2 * l + 1)
+            shell_of[i, k:k + 2 * l + 1] = ish
+            k += 2 * l + 1
+        n_orb_atom[i] = k
+    n_elec = q0.sum()
+
+    def shell_charges(dq_orb):
+        out = np.zeros((n_atom, m_shell))
+        for i in range(n_atom):
+            np.add.at(out[i], shell_of[i, :n_orb_atom[i]], dq_orb[i, :n_orb_atom[i]])
+        return out
+
+    def potential(q):
+        dq_shell = shell_charges(q - q0)
+        sh_atom, sh_shell = gam.shifts(dq_shell)
+        v = np.zeros((n_atom, m_orb))
+        for i in range(n_atom):
+            v[i, :n_orb_atom[i]] = sh_atom[i] + sh_shell[i, shell_of[i, :n_orb_atom[i]]]
+        e = 0.5 * float(sh_atom @ dq_shell.sum(axis=1)) + 0.5 * float((sh_shell * dq_shell).sum())
+        return v, e
+
+    def block(v):
+        b = np.zeros((1, n_atom, m_orb, m_orb))
+        idx = np.arange(m_orb)
+        b[0, :, idx, idx] = v.T
+        return b
+
+    mixer = scc_model.BroydenMixer(max_scc_iter=max(max_iter, 2))
+    mixer.reset(n_atom)
+    h0, over = arm.build()
+    q_in = q0.copy()
+    q_in_red = q_in.sum(axis=1)
+    for it in range(1, max_iter + 1):
+        v, _ = potential(q_in)
+        ham = arm.add_shift_block(h0, over, block(v))
+        eig, C = arm.solve(ham, over)
+        f = scc_model.fillings_and_band_energies(np.asarray(eig), n_elec, scc_model.MIN_TEMP)["filling"][:, 0, 0]
+        rho = arm.rho(C, f)
+        q_out = arm.mulliken(over, rho)
+        q_diff_red = q_out.sum(axis=1) - q_in_red
+        err = np.abs(q_diff_red).max()
+        if err < tol:
+            break
+        mixer.mix(q_in_red, q_diff_red)
+        q_in = np.zeros((n_atom, m_orb))
+        for i in range(n_atom):      # expandCharges, atom-wise equivalence
+            q_in[i, :n_orb_atom[i]] = q_in_red[i] / n_orb_atom[i]
+    v, e_scc = potential(q_out)
+    e_h0 = arm.mulliken(h0, rho).sum()
+    erho = arm.erho(C, f, np.asarray(eig))
+    forces = arm.forces(rho, erho, block(v))
+    return dict(n_iter=it, energy=e_h0 + e_scc, e_h0=e_h0, e_scc=e_scc, q=q_out, forces=forces, err=err)

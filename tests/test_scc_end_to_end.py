@@ -117,3 +117,58 @@ def test_oracle_md_steps_restart_and_momentum():
     mass = np.array([sk.mass[s - 1] for s in w["species0"]])[:, None]
     assert np.abs((mass * r["v"]).sum(axis=0)).max() < 1e-9 * mass.mean()
     assert np.abs(r["forces"].sum(axis=0)).max() < 1e-9
+
+
+# ---- the reference's SCC potential: 1/R (cluster / Ewald) - short-range gamma -------------------
+def _hub(sk):
+    """One Hubbard U per species (OrbitalResolvedSCC = No: every shell takes the U of the first, as the parser
+    sets hubbU(2:, :) = hubbU(1, :))."""
+    from oracle import coulomb_model as cm
+    return cm.unique_hubbard([[u[0]] * len(u) for u in sk.hubbU], [len(a) for a in sk.ang_shells])
+
+
+def test_oracle_scc_with_ewald_potential_converges():
+    """CPU: a periodic SCC single point (bcc Fe/C, 128 atoms) with the Ewald 1/R matrix and the short-range
+    gamma of the restatement: converges with the reference's mixer, conserves the electrons; a neutral charge
+    pattern feels no net potential from the uniform background term."""
+    w, sk, geo, model, selfegy = case("fec128")
+    gam = sh.OracleGamma(oracle, sk, w, _hub(sk))
+    r = sh.scc_reference_potential(sh.OracleArm(oracle, model, geo, selfegy), gam, w, sk, geo, model.mOrb, tol=1e-8,
+                                   max_iter=150)
+    assert r["err"] < 1e-8 and r["n_iter"] < 150          # a metal at minTemp: 69 iterations with the Broyden mixer
+    n_elec = sum(sum(sk.occ[s - 1]) for s in w["species0"])
+    assert abs(r["q"].sum() - n_elec) < 1e-8
+    # cluster case through the same driver
+    w, sk, geo, model, selfegy = case("h2o")
+    gam = sh.OracleGamma(oracle, sk, w, _hub(sk))
+    r2 = sh.scc_reference_potential(sh.OracleArm(oracle, model, geo, selfegy), gam, w, sk, geo, model.mOrb, tol=1e-9)
+    # one U per species and no periodic images: the potential equals the closed-form cluster gamma of round 1
+    r1 = sh.scc_single_point(sh.OracleArm(oracle, model, geo, selfegy), w, sk, geo, model.mOrb, reference_defaults=True,
+                             tol=1e-9)
+    assert r2["n_iter"] == r1["n_iter"] and abs(r2["energy"] - r1["energy"]) < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["h2o", "fec128", "watercluster24"])
+def test_scc_with_reference_potential_device_vs_oracle(name):
+    """Every SCC piece that has a device routine runs on the device: neighbour list (+ adopt), H0 / S, 1/R matrix
+    (cluster or Ewald), short-range gamma, shifts, addShift_block, eigensolve, density matrix, pack, Mulliken,
+    forces; against the oracle arm: identical iteration counts, energy 1e-8 Ha, charges 1e-9, forces 1e-7."""
+    from dftbplus_b200.api import HotPath
+    w, sk, geo, model, selfegy = _setup(name)
+    hub = _hub(sk)
+    ref = sh.scc_reference_potential(sh.OracleArm(oracle, model, geo, selfegy), sh.OracleGamma(oracle, sk, w, hub), w, sk,
+                                     geo, model.mOrb, tol=1e-9, max_iter=150)
+    hp = HotPath(0)
+    try:
+        sk.upload(hp)
+        gam = sh.DeviceGamma(hp, sk, w, hub)          # builds and adopts the list: geometry of the pair kernels
+        assert gam.geo["sparseSize"] == geo["sparseSize"]
+        got = sh.scc_reference_potential(sh.DeviceArm(hp, sk, geo), gam, w, sk, geo, model.mOrb, tol=1e-9, max_iter=150)
+    finally:
+        hp.close()
+    assert ref["err"] < 1e-9, "oracle arm did not converge"
+    assert got["n_iter"] == ref["n_iter"], (got["n_iter"], ref["n_iter"])
+    assert abs(got["energy"] - ref["energy"]) < TOL_ENERGY, (got["energy"], ref["energy"])
+    assert np.abs(got["q"] - ref["q"]).max() < 1e-9
+    assert np.abs(got["forces"] - ref["forces"]).max() < TOL_FORCE
