@@ -400,6 +400,16 @@ def section_md(dev, stream, n_steps):
     species0 = w["species0"]
     nAtom = len(species0)
     f64 = dict(dtype=torch.float64, device=dev)
+    potential = os.environ.get("DFTBP_B200_MD_POTENTIAL", "reference")
+    list_cutoff = cutoff
+    if potential == "reference":
+        from dftbplus_b200 import coulomb as pc
+        # one U per species (OrbitalResolvedSCC = No); Ewald parameters and gamma cutoffs: per-lattice host set-up
+        hubm = pc.unique_hubbard([[workloads.SPECIES[nm][2][0]] * len(sk.ang_shells[i]) for i, nm in enumerate(w["names"])],
+                                 [len(a) for a in sk.ang_shells])
+        gcuts = pc.short_gamma_cutoffs(hubm)
+        ew = pc.ewald_setup(lat)
+        list_cutoff = max(cutoff, float(gcuts.max()))      # mCutOff: the list covers every cutoff
     rng = np.random.default_rng(3)
     mass = np.array([workloads.SPECIES[w["names"][s - 1]][4] for s in species0]) * 1822.888486
     hub = np.array([workloads.SPECIES[w["names"][s - 1]][2][0] for s in species0])
@@ -420,21 +430,36 @@ def section_md(dev, stream, n_steps):
         hub_d = torch.from_numpy(hub).to(dev)
         q0_d = torch.from_numpy(q0).to(dev)
         didx = torch.arange(mo, device=dev)
+        if potential == "reference":
+            invr = new_dense(nAtom, device=dev)
+            rlat_d, glat_d = torch.from_numpy(ew["rLat"]).to(dev), torch.from_numpy(ew["gLat"]).to(dev)
+            dq_shell = torch.zeros((nAtom, hubm["mShell"]), **f64)
+            sh_shell = torch.zeros((nAtom, hubm["mShell"]), **f64)
+            sh_atom = torch.zeros(nAtom, **f64)
     dq = torch.zeros(nAtom, **f64)
     kT = 0.02        # the synthetic SK tables leave the box without a gap: Fermi smearing (hartree)
-    scc_iters, t_list, t_build, t_scc, t_force = [], 0.0, 0.0, 0.0, 0.0
+    scc_iters, t_list, t_build, t_scc, t_force, t_pot = [], 0.0, 0.0, 0.0, 0.0, 0.0
     mixer = None
     if os.environ.get("DFTBP_B200_MD_MIXER", "broyden") == "broyden":
         from dftbplus_b200.mixer import BroydenMixer
         mixer = BroydenMixer(max_scc_iter=64)
 
     def forces(x):
-        nonlocal dq, fill, t_list, t_build, t_scc, t_force
+        nonlocal dq, fill, t_list, t_build, t_scc, t_force, t_pot
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        g = hp.updateNeighbourListAndSpecies(x, species0, cutoff, lat, adopt=True, fetch=False)
+        g = hp.updateNeighbourListAndSpecies(x, species0, list_cutoff, lat, sk_cutoff=cutoff, adopt=True, fetch=False)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
+        if potential == "reference":
+            # TCoulomb%updateCoords + TShortGamma%updateCoords on the device
+            with torch.cuda.stream(stream):
+                x_d = torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+            hp.invRPeriodic(x_d, rlat_d, glat_d, ew["alpha"], ew["volume"], ew["maxR"], invr=invr)
+            hp.shortGammaUpdate(hubm["nHubbU"], hubm["uniqHubbU"], gcuts)
+            torch.cuda.synchronize()
+            t_pot += time.perf_counter() - t1
+            t1 = time.perf_counter()
         ss = g["sparseSize"]
         with torch.cuda.stream(stream):
             ham, over = torch.empty(ss, **f64), torch.empty(ss, **f64)
@@ -449,9 +474,20 @@ def section_md(dev, stream, n_steps):
         if mixer is not None:
             mixer.reset(nAtom)           # the reference resets its mixer for every geometry
         for it in range(1, 41):
-            with torch.cuda.stream(stream):
-                shift.zero_()
-                shift[0, :, didx, didx] = (hub_d * dq)[:, None]
+            if potential == "reference":
+                # TCoulomb%updateShifts + TShortGamma%updateShifts: V_A = (1/R dq)_A + shiftShell(1, A)
+                with torch.cuda.stream(stream):
+                    dq_shell.zero_()
+                    dq_shell[:, 0] = dq
+                hp.coulombShift(invr, dq, shift=sh_atom)
+                hp.shortGammaShifts(hubm["iHubbU"], dq_shell, shift_shell=sh_shell)
+                with torch.cuda.stream(stream):
+                    shift.zero_()
+                    shift[0, :, didx, didx] = (sh_atom + sh_shell[:, 0])[:, None]
+            else:
+                with torch.cuda.stream(stream):
+                    shift.zero_()
+                    shift[0, :, didx, didx] = (hub_d * dq)[:, None]
             hp.addShift(hscc, over, shift, is_input_zero=True)
             with torch.cuda.stream(stream):
                 hscc[0].add_(ham)
@@ -507,7 +543,7 @@ def section_md(dev, stream, n_steps):
 
     f = forces(x)                    # step 0 (SCC from neutral atoms), not timed
     scc_iters.clear()
-    t_list = t_build = t_scc = t_force = 0.0
+    t_list = t_build = t_scc = t_force = t_pot = 0.0
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(n_steps):
@@ -519,12 +555,16 @@ def section_md(dev, stream, n_steps):
     wall = time.perf_counter() - t0
     out = {"workload": "water2046", "nAtom": int(nAtom), "nOrb": n, "steps": n_steps, "steps_per_s": n_steps / wall,
            "ms_per_step": wall / n_steps * 1e3, "scc_iterations_per_step": float(np.mean(scc_iters)),
+           "scc_potential": ("reference: Ewald 1/R matrix + short-range gamma on the device (one U per species), list cutoff %.2f bohr"
+                             % list_cutoff) if potential == "reference" else "on-site part only (U_A dq_A)",
            "ms_per_step_breakdown": {"neighbour_list_update_adopt": t_list / n_steps * 1e3,
+                                     "ewald_matrix_and_gamma_values": t_pot / n_steps * 1e3,
                                      "buildH0S": t_build / n_steps * 1e3, "scc_loop": t_scc / n_steps * 1e3,
                                      "edm_pack_forces": t_force / n_steps * 1e3},
            "momentum_drift": float(np.abs((mass[:, None] * v).sum(axis=0)).max()),
            "timing": "host wall clock (the step contains cuSOLVER calls and small D2H reads)",
-           "note": "on-site SCC model of the harness (no gamma / Ewald), " + ("modified Broyden mixing with the reference's defaults (dftbplus_b200/mixer.py)" if mixer is not None else "Anderson mixing (5 vectors, 0.4)") +
+           "note": ("SCC potential of the reference on the device (dftbp_b200_invr_periodic, _short_gamma_update, _coulomb_shift, "
+                    "_short_gamma_shifts), " if potential == "reference" else "on-site SCC model of the harness (no gamma / Ewald), ") + ("modified Broyden mixing with the reference's defaults (dftbplus_b200/mixer.py)" if mixer is not None else "Anderson mixing (5 vectors, 0.4)") +
                    ", tolerance 1e-5, at most 40 iterations, Fermi smearing kT = 0.02 Ha (the synthetic tables leave no gap); "
                    "BASELINE asks for 100 steps: --md 100"}
     del H, S, D

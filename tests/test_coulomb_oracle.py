@@ -99,3 +99,25 @@ def test_gamma_limits_of_the_oracle():
     # the general formula joins the equal-U one (just above minHubDiff it cancels catastrophically -- in the
     # reference too: 1.4e-3 off at U2 - U1 = 4e-6 -- so the join is checked at a separation of 1e-3)
     assert abs(cm.exp_gamma(3.0, 0.3, 0.301) - 0.5 * (cm.exp_gamma(3.0, 0.3, 0.3) + cm.exp_gamma(3.0, 0.301, 0.301))) < 1e-6
+
+
+def test_product_host_mirror_equals_the_oracle_restatement():
+    """dftbplus_b200/coulomb.py (set-up used by bench.py and the harness' device arm) against oracle/coulomb_model.py:
+    Ewald parameters, lattice points (same points in the same order), unique Hubbard values, gamma cutoffs."""
+    from dftbplus_b200 import coulomb as pc
+    for lat in (np.eye(3) * 9.7, np.array([[9.0, 0.3, 0.0], [0.0, 11.0, 0.5], [0.2, 0.0, 13.0]]),
+                np.array([[0.0, 5.1, 5.1], [5.1, 0.0, 5.1], [5.1, 5.1, 0.0]])):
+        a, b = pc.ewald_setup(lat), cm.ewald_setup(lat)
+        for k in ("alpha", "volume", "maxR", "maxG"):
+            assert a[k] == b[k], k
+        assert a["rLat"].shape == b["rLat"].shape and a["gLat"].shape == b["gLat"].shape
+        assert np.abs(a["rLat"] - b["rLat"]).max() < 1e-12 and np.abs(a["gLat"] - b["gLat"]).max() < 1e-14
+    hub_u, n_shell = [[0.31, 0.27, 0.27 + 1e-6], [0.42, 0.36]], [3, 2]
+    a, b = pc.unique_hubbard(hub_u, n_shell), cm.unique_hubbard(hub_u, n_shell)
+    for k in ("nHubbU", "uniqHubbU", "iHubbU"):
+        assert np.array_equal(a[k], b[k]), k
+    ca, cb = pc.short_gamma_cutoffs(a), cm.short_gamma_cutoffs(b)
+    assert np.abs(ca - cb).max() < 1e-9
+    for r in (0.0, 0.7, 3.0, 11.0):
+        for ua, ub in ((0.3, 0.3), (0.3, 0.41)):
+            assert abs(pc.exp_gamma(r, ua, ub) - cm.exp_gamma(r, ua, ub)) <= 1e-15 * max(1.0, abs(cm.exp_gamma(r, ua, ub)))
