@@ -380,7 +380,7 @@ def fermi_fillings_device(eig, n_elec, kT):
     return 2.0 / (1.0 + torch.exp(torch.clamp((eig - 0.5 * (lo + hi)) / kT, -500.0, 500.0)))
 
 
-def section_md(dev, stream, n_steps):
+def section_md(dev, stream, n_steps, potential=None):
     """BASELINE config 5 pattern: 2046-atom water box, velocity-Verlet steps; per step the device neighbour
     list (update + adopt), buildH0 + buildS, an SCC loop restarted from the previous charges (addShift, unpack
     H and S, Dsygvd, density matrix, pack, Mulliken), energy-weighted density matrix and the SCC force
@@ -400,7 +400,8 @@ def section_md(dev, stream, n_steps):
     species0 = w["species0"]
     nAtom = len(species0)
     f64 = dict(dtype=torch.float64, device=dev)
-    potential = os.environ.get("DFTBP_B200_MD_POTENTIAL", "reference")
+    if potential is None:
+        potential = os.environ.get("DFTBP_B200_MD_POTENTIAL", "onsite")
     list_cutoff = cutoff
     if potential == "reference":
         from dftbplus_b200 import coulomb as pc
@@ -1107,7 +1108,7 @@ def main():
     barrier()
 
     # ---- BASELINE config 3 (k-points, all ranks) and config 5 (MD, rank 0 at N = 1) ---------------
-    kp_sec, md_sec = None, None
+    kp_sec, md_sec, md_ref_sec = None, None, None
     if not a.no_kpoints and not a.pair_only:
         try:
             kp_sec = section_kpoints(dev, stream, rank, world, dist, max_over_ranks, barrier)
@@ -1120,6 +1121,10 @@ def main():
             md_sec = section_md(dev, stream, a.md)
         except Exception as e:  # noqa: BLE001
             md_sec = {"error": repr(e)}
+        try:
+            md_ref_sec = section_md(dev, stream, min(a.md, 3), potential="reference")
+        except Exception as e:  # noqa: BLE001
+            md_ref_sec = {"error": repr(e)}
 
     # ---- CPU baseline (oracle port) on rank 0, N = 1 ----------------------------------------------
     cpu = None
@@ -1181,7 +1186,7 @@ def main():
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "roofline_k5": roofline_k5, "roofline_dm": roofline_dm, "kernels": kernels, "stream_mix_same_size": stream_mix,
                 "scc_step": scc,
-                "kpoints_si512": kp_sec, "md_water2046": md_sec, "multi_gpu": multi, "cpu_baseline": cpu,
+                "kpoints_si512": kp_sec, "md_water2046": md_sec, "md_water2046_reference_potential": md_ref_sec, "multi_gpu": multi, "cpu_baseline": cpu,
                 "neighbour_list": n2, "coulomb_ewald": coul}
         print(json.dumps(line), flush=True)
     hp.close()

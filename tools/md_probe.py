@@ -13,4 +13,4 @@ import bench  # noqa: E402
 
 dev = torch.device("cuda:0")
 stream = torch.cuda.Stream(device=dev)
-print(json.dumps(bench.section_md(dev, stream, int(sys.argv[1]) if len(sys.argv) > 1 else 4)))
+print(json.dumps(bench.section_md(dev, stream, int(sys.argv[1]) if len(sys.argv) > 1 else 4, potential=os.environ.get("DFTBP_B200_MD_POTENTIAL"))))
