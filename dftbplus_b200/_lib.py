@@ -73,6 +73,9 @@ SIGNATURES = {
     "dftbp_b200_short_gamma_update": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dftbp_b200_short_gamma_get": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "dftbp_b200_short_gamma_shifts": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dftbp_b200_mixer_init": (c_int, [c_void_p, c_int, c_double, c_double, c_double, c_double, c_double]),
+    "dftbp_b200_mixer_reset": (c_int, [c_void_p, c_int]),
+    "dftbp_b200_mixer_mix": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
 }
 
 _lib = None

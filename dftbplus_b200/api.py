@@ -481,6 +481,22 @@ class HotPath:
         self._ck(self._L.dftbp_b200_short_gamma_shifts(self._h, _ptr(_i32(i_hubb_u)), _ptr(dq), _ptr(shift_shell)))
         return shift_shell
 
+    # ---- N4: Broyden mixer with device-resident vectors ------------------------------------------------
+    def mixerInit(self, max_scc_iter=100, mix_param=0.2, omega0=0.01, min_weight=1.0, max_weight=1.0e5,
+                  weight_fac=1.0e-2):
+        """TBroydenMixerReal_init (mixer/broydenmixer.F90:110-139) with the parser's defaults."""
+        self._ck(self._L.dftbp_b200_mixer_init(self._h, int(max_scc_iter), float(mix_param), float(omega0),
+                                               float(min_weight), float(max_weight), float(weight_fac)))
+
+    def mixerReset(self, n_elem):
+        """TBroydenMixerReal_reset (:143-170): a new SCC cycle over vectors of n_elem charges."""
+        self._ck(self._L.dftbp_b200_mixer_reset(self._h, int(n_elem)))
+
+    def mixerMix(self, q_inp_result, q_diff):
+        """TBroydenMixerReal_mix (:180-342): q_inp_result is overwritten with the mixed charges (in place)."""
+        self._ck(self._L.dftbp_b200_mixer_mix(self._h, _ptr(q_inp_result), _ptr(_f64(q_diff)), int(q_inp_result.shape[0])))
+        return q_inp_result
+
     def diagDenseMtx(self, H, S, eigen=None, jobz="V"):
         """hegvd: H, S column-major, overwritten (H <- eigenvectors); returns eigenvalues."""
         n = H.shape[0]

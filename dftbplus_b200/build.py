@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libdftbp_b200.so")
 SOURCES = ["context.cu", "pair_sort.cu", "k1_pair_build.cu", "k2_sparse_dense.cu", "k3_density_matrix.cu",
-           "k4_mulliken.cu", "k5_forces.cu", "k6_add_shift.cu", "n2_neighbour_list.cu", "n4_efilling.cu", "n4_coulomb.cu", "solver.cu"]
+           "k4_mulliken.cu", "k5_forces.cu", "k6_add_shift.cu", "n2_neighbour_list.cu", "n4_efilling.cu", "n4_coulomb.cu", "n4_mixer.cu", "solver.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 CUDA_LIB = "/usr/local/cuda/lib64"

@@ -210,6 +210,7 @@ struct dftbp_b200_ctx {
   int *dInfo = nullptr;
   void *neighbourState = nullptr;  // device-built neighbour list (n2_neighbour_list.cu)
   void *shortGammaState = nullptr; // short-range gamma values of the current list (n4_coulomb.cu)
+  void *mixerState = nullptr;      // device Broyden mixer (n4_mixer.cu)
   unsigned long long listGeneration = 0;  // counts update_neighbour_list calls (values derived from a list name theirs)
   // device blocks of the per-geometry arrays, kept across set_geometry calls (poolAlloc / poolRelease):
   // a geometry step re-uploads ~20 arrays of nearly the same sizes, and cudaFree + cudaMalloc of each
@@ -508,6 +509,7 @@ struct NeighbourListView {
 };
 NeighbourListView neighbourListView(dftbp_b200_ctx *ctx);
 void freeShortGamma(dftbp_b200_ctx *ctx);
+void freeMixer(dftbp_b200_ctx *ctx);
 // give the arrays of the current geometry back to the block pool (context.cu)
 void releaseGeometry(dftbp_b200_ctx *ctx);
 

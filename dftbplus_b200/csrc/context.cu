@@ -91,6 +91,7 @@ int dftbp_b200_destroy(dftbp_b200_ctx *ctx) {
   freeSortedPairs(ctx);
   freeNeighbourList(ctx);
   freeShortGamma(ctx);
+  freeMixer(ctx);
   for (void *p : ctx->tableAllocs) cudaFree(p);
   for (Staging &s : ctx->staging) cudaFree(s.ptr);
   cudaFree(ctx->dNOrbSpecies); cudaFree(ctx->dOrbShell); cudaFree(ctx->dProgs);

@@ -20,6 +20,7 @@ module dftbp_b200_shim
   public :: b200_hegv_real, b200_hegv_cmplx, b200_Efilling
   public :: b200_invRCluster, b200_invRPeriodic, b200_coulombShifts
   public :: b200_shortGammaUpdateCoords, b200_shortGammaShifts
+  public :: b200_BroydenMixer_init, b200_BroydenMixer_reset, b200_BroydenMixer_mix
 
   integer, parameter :: dp = c_double
 
@@ -284,6 +285,25 @@ module dftbp_b200_shim
       integer(c_int), intent(in) :: iHubbU(*)
       real(c_double), intent(in) :: deltaQShell(*)
       real(c_double), intent(out) :: shiftShell(*)
+    end function
+    integer(c_int) function dftbp_b200_mixer_init(ctx, maxSccIter, mixParam, omega0, minWeight, maxWeight,&
+        & weightFac) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: maxSccIter
+      real(c_double), value :: mixParam, omega0, minWeight, maxWeight, weightFac
+    end function
+    integer(c_int) function dftbp_b200_mixer_reset(ctx, nElem) bind(C)
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nElem
+    end function
+    integer(c_int) function dftbp_b200_mixer_mix(ctx, qInpResult, qDiff, nElem) bind(C)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(inout) :: qInpResult(*)
+      real(c_double), intent(in) :: qDiff(*)
+      integer(c_int), value :: nElem
     end function
     integer(c_int) function dftbp_b200_adopt_neighbour_list(ctx) bind(C)
       import :: c_ptr, c_int
@@ -617,6 +637,29 @@ contains
     real(dp), intent(out) :: shiftShell(:,:)
     call check(ctx, dftbp_b200_short_gamma_shifts(ctx%h, int(iHubbU, c_int), deltaQShell, shiftShell))
   end subroutine b200_shortGammaShifts
+
+  !> TBroydenMixerReal_init, mixer/broydenmixer.F90:110 (same dummy arguments after the instance)
+  subroutine b200_BroydenMixer_init(ctx, mIter, mixParam, omega0, minWeight, maxWeight, weightFac)
+    type(TB200Ctx), intent(in) :: ctx
+    integer, intent(in) :: mIter
+    real(dp), intent(in) :: mixParam, omega0, minWeight, maxWeight, weightFac
+    call check(ctx, dftbp_b200_mixer_init(ctx%h, int(mIter, c_int), mixParam, omega0, minWeight, maxWeight, weightFac))
+  end subroutine b200_BroydenMixer_init
+
+  !> TBroydenMixerReal_reset, mixer/broydenmixer.F90:143
+  subroutine b200_BroydenMixer_reset(ctx, nElem)
+    type(TB200Ctx), intent(in) :: ctx
+    integer, intent(in) :: nElem
+    call check(ctx, dftbp_b200_mixer_reset(ctx%h, int(nElem, c_int)))
+  end subroutine b200_BroydenMixer_reset
+
+  !> TBroydenMixerReal_mix, mixer/broydenmixer.F90:180
+  subroutine b200_BroydenMixer_mix(ctx, qInpResult, qDiff)
+    type(TB200Ctx), intent(in) :: ctx
+    real(dp), intent(inout) :: qInpResult(:)
+    real(dp), intent(in) :: qDiff(:)
+    call check(ctx, dftbp_b200_mixer_mix(ctx%h, qInpResult, qDiff, size(qInpResult)))
+  end subroutine b200_BroydenMixer_mix
 
   !> mullikenPerBlock, dftb/populations.F90:306 -- qq(mOrb, mOrb, nAtom) accumulates
   subroutine b200_mullikenPerBlock(ctx, qq, over, rho)

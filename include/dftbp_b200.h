@@ -340,6 +340,19 @@ int dftbp_b200_short_gamma_get(dftbp_b200_ctx *ctx, int *nNeighU, int *maxNeigh,
 int dftbp_b200_short_gamma_shifts(dftbp_b200_ctx *ctx, const int *iHubbU, const double *deltaQShell,
                                   double *shiftShell);
 
+/* The charge mixer of the SCC loop with its vectors on the device: the modified Broyden mixer
+ * TBroydenMixerReal, mixer/broydenmixer.F90 -- init (:110-139; parser defaults mixParam 0.2, omega0 0.01,
+ * minWeight 1, maxWeight 1e5, weightFac 1e-2: dftbplus/parser.F90:5786-5790), reset (:143-170, once per SCC
+ * cycle), mix (:180-342): qInpResult(nElem) holds the input charges on entry and the mixed charges on exit,
+ * qDiff(nElem) = output - input charges.  Host or device pointers; with device pointers the charges go from the
+ * Mulliken kernel to the shift kernels without leaving the GPU (the call itself reads back 2 + 2 (iter - 2) + 1
+ * scalar products and solves the small system on the host, as the reference does with LAPACK).  More than
+ * maxSccIter calls after a reset fail with "Broyden mixer: Maximal nr. of steps exceeded". */
+int dftbp_b200_mixer_init(dftbp_b200_ctx *ctx, int maxSccIter, double mixParam, double omega0, double minWeight,
+                          double maxWeight, double weightFac);
+int dftbp_b200_mixer_reset(dftbp_b200_ctx *ctx, int nElem);
+int dftbp_b200_mixer_mix(dftbp_b200_ctx *ctx, double *qInpResult, const double *qDiff, int nElem);
+
 /* ---- not rewritten: dense generalized eigensolve via cuSOLVER ------------------------------- */
 
 /* diagDenseMtx, dftbplus/eigenvects.F90:85-100 (hegvd branch): H C = S C diag(eigen), lower

@@ -142,3 +142,72 @@ def test_short_gamma_on_the_device_list(name, resolved):
         with pytest.raises(DftbB200Error):
             hp.shortGammaShifts(hub["iHubbU"], dq)
     hp.close()
+
+
+# ---- Broyden mixer with device-resident vectors ------------------------------------------------------------
+def test_device_broyden_mixer_reference_known_answer(hp):
+    """test/src/dftbp/unit/mixer/broyden.F90 ("broyden_mixer_H20"): the reference's own vectors, atol 100 eps."""
+    expected = np.array([
+        [6.0000000000000018, 1.0000000000000002, 1.0000000000000002],
+        [6.1761632532030193, 0.91191837339849169, 0.91191837339849169],
+        [6.4798000093100434, 0.76009999534497941, 0.76009999534497941],
+        [6.4625859389302871, 0.76870703053485734, 0.76870703053485745],
+        [6.4635561795150211, 0.76822191024249031, 0.76822191024249042]])
+    difference = np.array([
+        [0.88081626601508667, -0.44040813300754278, -0.44040813300754278],
+        [0.55742893386488124, -0.27871446693244140, -0.27871446693244140],
+        [-3.2497351757903914E-002, 1.6248675878950958E-002, 1.6248675878951291E-002],
+        [1.9288771697691942E-003, -9.6443858488526324E-004, -9.6443858488515222E-004]])
+    hp.mixerInit(100, 0.2, 0.01, 1.0, 100000.0, 0.01)
+    hp.mixerReset(3)
+    q = expected[0].copy()
+    for ii in range(4):
+        hp.mixerMix(q, difference[ii])
+        assert np.abs(q - expected[ii + 1]).max() <= 100.0 * np.finfo(np.float64).eps, (ii, q, expected[ii + 1])
+
+
+@pytest.mark.parametrize("n", [7, 1000, 4096])
+def test_device_broyden_mixer_follows_the_oracle(n, hp):
+    """A linear fixed-point problem q_out = A q + b driven by the device mixer (device-resident vectors) and by the
+    oracle restatement side by side: the same iterates to 1e-11 of the charge scale, iteration by iteration, the
+    same number of iterations to convergence; too many calls after a reset are refused like in the reference."""
+    import torch
+    from oracle import scc_model
+    from dftbplus_b200.api import DftbB200Error
+    rng = np.random.default_rng(n)
+    d = rng.uniform(-0.5, 0.5, n)
+    lowrank = rng.normal(size=(n, 3)) / np.sqrt(n)
+    b = rng.normal(size=n)
+
+    def out(q):
+        return d * q + 0.3 * lowrank @ (lowrank.T @ q) + b
+
+    ref = scc_model.BroydenMixer(max_scc_iter=40)
+    ref.reset(n)
+    hp.use_torch_stream()
+    hp.mixerInit(40)
+    hp.mixerReset(n)
+    q_ref = np.zeros(n)
+    q_dev = torch.zeros(n, dtype=torch.float64, device="cuda")
+    its_ref = its_dev = None
+    for it in range(1, 41):
+        diff_ref = out(q_ref) - q_ref
+        q_host = q_dev.cpu().numpy()
+        diff_dev = out(q_host) - q_host
+        if its_ref is None and np.abs(diff_ref).max() < 1e-10:
+            its_ref = it
+        if its_dev is None and np.abs(diff_dev).max() < 1e-10:
+            its_dev = it
+        if its_ref is not None and its_dev is not None:
+            break
+        ref.mix(q_ref, diff_ref)
+        hp.mixerMix(q_dev, torch.from_numpy(diff_dev).cuda())
+        hp.synchronize()
+        assert np.abs(q_dev.cpu().numpy() - q_ref).max() <= 1e-11 * max(1.0, np.abs(q_ref).max()), it
+    assert its_ref is not None and its_ref == its_dev
+    hp.mixerReset(n)
+    for _ in range(40):
+        hp.mixerMix(q_dev, torch.zeros(n, dtype=torch.float64, device="cuda") + 1e-3)
+    with pytest.raises(DftbB200Error):
+        hp.mixerMix(q_dev, torch.zeros(n, dtype=torch.float64, device="cuda"))
+    hp.set_stream(None)
