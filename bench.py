@@ -441,7 +441,11 @@ def section_md(dev, stream, n_steps, potential=None):
     kT = 0.02        # the synthetic SK tables leave the box without a gap: Fermi smearing (hartree)
     scc_iters, t_list, t_build, t_scc, t_force, t_pot = [], 0.0, 0.0, 0.0, 0.0, 0.0
     mixer = None
-    if os.environ.get("DFTBP_B200_MD_MIXER", "broyden") == "broyden":
+    mixer_kind = os.environ.get("DFTBP_B200_MD_MIXER", "broyden")
+    if mixer_kind == "broyden":
+        hp.mixerInit(64)                 # modified Broyden with device-resident vectors (dftbp_b200_mixer_*)
+        mixer = "device"
+    elif mixer_kind == "broyden_host":
         from dftbplus_b200.mixer import BroydenMixer
         mixer = BroydenMixer(max_scc_iter=64)
 
@@ -472,8 +476,10 @@ def section_md(dev, stream, n_steps, potential=None):
         t2 = time.perf_counter()
         it = 0
         hist_x, hist_r = [], []
-        if mixer is not None:
-            mixer.reset(nAtom)           # the reference resets its mixer for every geometry
+        if mixer == "device":
+            hp.mixerReset(nAtom)         # the reference resets its mixer for every geometry
+        elif mixer is not None:
+            mixer.reset(nAtom)
         for it in range(1, 41):
             if potential == "reference":
                 # TCoulomb%updateShifts + TShortGamma%updateShifts: V_A = (1/R dq)_A + shiftShell(1, A)
@@ -515,8 +521,12 @@ def section_md(dev, stream, n_steps, potential=None):
                           float(eig[n_occ] - eig[n_occ - 1])), flush=True)
                 if err < 1e-5:
                     break
+                if mixer == "device":
+                    # modified Broyden mixing of the atomic charges, the reference's default; the vectors stay on the GPU
+                    dq = dq.clone()
+                    hp.mixerMix(dq, res.contiguous())
+                    continue
                 if mixer is not None:
-                    # modified Broyden mixing of the atomic charges, the reference's default (host side, O(nAtom))
                     dq = torch.from_numpy(mixer.mix(dq.cpu().numpy(), res.cpu().numpy())).to(dev)
                     continue
                 # Anderson mixing over the last five (input, residual) pairs of this geometry
@@ -565,7 +575,7 @@ def section_md(dev, stream, n_steps, potential=None):
            "momentum_drift": float(np.abs((mass[:, None] * v).sum(axis=0)).max()),
            "timing": "host wall clock (the step contains cuSOLVER calls and small D2H reads)",
            "note": ("SCC potential of the reference on the device (dftbp_b200_invr_periodic, _short_gamma_update, _coulomb_shift, "
-                    "_short_gamma_shifts), " if potential == "reference" else "on-site SCC model of the harness (no gamma / Ewald), ") + ("modified Broyden mixing with the reference's defaults (dftbplus_b200/mixer.py)" if mixer is not None else "Anderson mixing (5 vectors, 0.4)") +
+                    "_short_gamma_shifts), " if potential == "reference" else "on-site SCC model of the harness (no gamma / Ewald), ") + ("modified Broyden mixing with the reference's defaults, vectors on the device (dftbp_b200_mixer_*)" if mixer == "device" else "modified Broyden mixing with the reference's defaults (dftbplus_b200/mixer.py)" if mixer is not None else "Anderson mixing (5 vectors, 0.4)") +
                    ", tolerance 1e-5, at most 40 iterations, Fermi smearing kT = 0.02 Ha (the synthetic tables leave no gap); "
                    "BASELINE asks for 100 steps: --md 100"}
     del H, S, D
