@@ -132,6 +132,40 @@ int main(void) {
     fprintf(stderr, "gradients vanish or do not add up to zero\n");
     return 5;
   }
+  /* SCC pieces: 1/R matrix of the cluster, Coulomb shifts for the Mulliken charges, one step of
+   * the Broyden mixer -- TCoulomb%updateCoords / %updateShifts, TBroydenMixerReal%mix from plain C */
+  {
+    double invR[N_ATOM * N_ATOM], dq[N_ATOM], shiftAtom[N_ATOM], qIn[N_ATOM], qDiff[N_ATOM];
+    const double q0[N_ATOM] = {6.0, 1.0, 1.0};
+    CHECK(dftbp_b200_invr_cluster(ctx, N_ATOM, coords, invR, N_ATOM));
+    for (int j = 0; j < N_ATOM; ++j)
+      for (int i = 0; i < N_ATOM; ++i) {
+        const double dx = coords[3 * i] - coords[3 * j], dy = coords[3 * i + 1] - coords[3 * j + 1],
+                     dz = coords[3 * i + 2] - coords[3 * j + 2];
+        const double want = i > j ? 1.0 / sqrt(dx * dx + dy * dy + dz * dz) : 0.0;
+        if (fabs(invR[i + N_ATOM * j] - want) > 1e-15) { fprintf(stderr, "invRCluster differs\n"); return 6; }
+      }
+    double sumDq = 0.0;
+    for (int a = 0; a < N_ATOM; ++a) {
+      dq[a] = qq[4 * a] + qq[4 * a + 1] + qq[4 * a + 2] + qq[4 * a + 3] - q0[a];
+      sumDq += dq[a];
+    }
+    CHECK(dftbp_b200_coulomb_shift(ctx, N_ATOM, invR, N_ATOM, dq, shiftAtom));
+    for (int a = 0; a < N_ATOM; ++a) {
+      double want = 0.0;
+      for (int b = 0; b < N_ATOM; ++b)
+        if (b != a) want += invR[(a > b ? a : b) + N_ATOM * (a > b ? b : a)] * dq[b];
+      if (fabs(shiftAtom[a] - want) > 1e-14) { fprintf(stderr, "Coulomb shift differs\n"); return 7; }
+    }
+    printf("charge transfer %.6f %.6f %.6f (sum %.1e), Coulomb shifts %.6f %.6f %.6f\n", dq[0], dq[1], dq[2], sumDq,
+           shiftAtom[0], shiftAtom[1], shiftAtom[2]);
+    CHECK(dftbp_b200_mixer_init(ctx, 100, 0.2, 0.01, 1.0, 1.0e5, 1.0e-2));
+    CHECK(dftbp_b200_mixer_reset(ctx, N_ATOM));
+    for (int a = 0; a < N_ATOM; ++a) { qIn[a] = q0[a]; qDiff[a] = dq[a]; }
+    CHECK(dftbp_b200_mixer_mix(ctx, qIn, qDiff, N_ATOM));
+    for (int a = 0; a < N_ATOM; ++a)   /* first iteration: simple mixing with mixParam (broydenmixer.F90:268-273) */
+      if (fabs(qIn[a] - (q0[a] + 0.2 * dq[a])) > 1e-15) { fprintf(stderr, "first Broyden step is not simple mixing\n"); return 8; }
+  }
   printf("kernel launches %lld, pairs %lld\n", dftbp_b200_kernel_launches(ctx), dftbp_b200_num_pairs(ctx));
   CHECK(dftbp_b200_destroy(ctx));
   printf("chain.c: OK\n");
