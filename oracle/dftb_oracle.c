@@ -1398,12 +1398,16 @@ void orc_symv_lower(int n, const double *A, int ld, const double *x, double *y)
  *   shortGamma(mU, mU, 0:mNeigh, nAtom), iHubbU(mShell, nSpecies), deltaQShell / shiftShell(mShell, nAtom). */
 static const double minHubDiff = 0.3125e-5, tolSameDist = 1.0e-5, tolShortGamma = 1.0e-10, minShortGamma = 1.0e-10;
 
+/* integer powers as gfortran expands them (x**2 = x*x, x**3 = x*x*x, x**4 = (x*x)*(x*x), x**6 = (x*x*x)*(x*x*x)) */
+static double pw2(double x) { return x * x; }
+static double pw3(double x) { return x * x * x; }
+static double pw4(double x) { const double y = x * x; return y * y; }
+static double pw6(double x) { const double y = x * x * x; return y * y; }
+
 static double gamma_sub_exprn(double rab, double tau1, double tau2)
 {
-  const double d2 = tau1 * tau1 - tau2 * tau2;
-  return exp(-tau1 * rab) * ((0.5 * tau2 * tau2 * tau2 * tau2 * tau1 / (d2 * d2))
-                             - (tau2 * tau2 * tau2 * tau2 * tau2 * tau2 - 3.0 * tau2 * tau2 * tau2 * tau2 * tau1 * tau1)
-                                   / (rab * (d2 * d2 * d2)));
+  return exp(-tau1 * rab) * ((0.5 * pw4(tau2) * tau1 / pw2(pw2(tau1) - pw2(tau2)))
+                             - (pw6(tau2) - 3.0 * pw4(tau2) * pw2(tau1)) / (rab * pw3(pw2(tau1) - pw2(tau2))));
 }
 
 double orc_exp_gamma(double rab, double Ua, double Ub)
@@ -1411,12 +1415,12 @@ double orc_exp_gamma(double rab, double Ua, double Ub)
   const double tauA = 3.2 * Ua, tauB = 3.2 * Ub;
   if (rab < tolSameDist) {
     if (fabs(Ua - Ub) < minHubDiff) return -0.5 * (Ua + Ub);
-    return -0.5 * ((tauA * tauB) / (tauA + tauB) + (tauA * tauB) * (tauA * tauB) / ((tauA + tauB) * (tauA + tauB) * (tauA + tauB)));
+    return -0.5 * ((tauA * tauB) / (tauA + tauB) + pw2(tauA * tauB) / pw3(tauA + tauB));
   }
   if (fabs(Ua - Ub) < minHubDiff) {
     const double tauMean = 0.5 * (tauA + tauB);
-    return exp(-tauMean * rab) * (1.0 / rab + 0.6875 * tauMean + 0.1875 * rab * (tauMean * tauMean)
-                                  + 0.02083333333333333333 * (rab * rab) * (tauMean * tauMean * tauMean));
+    return exp(-tauMean * rab) * (1.0 / rab + 0.6875 * tauMean + 0.1875 * rab * pw2(tauMean)
+                                  + 0.02083333333333333333 * pw2(rab) * pw3(tauMean));
   }
   return gamma_sub_exprn(rab, tauA, tauB) + gamma_sub_exprn(rab, tauB, tauA);
 }
