@@ -120,4 +120,4 @@ def test_product_host_mirror_equals_the_oracle_restatement():
     assert np.abs(ca - cb).max() < 1e-9
     for r in (0.0, 0.7, 3.0, 11.0):
         for ua, ub in ((0.3, 0.3), (0.3, 0.41)):
-            assert abs(pc.exp_gamma(r, ua, ub) - cm.exp_gamma(r, ua, ub)) <= 1e-15 * max(1.0, abs(cm.exp_gamma(r, ua, ub)))
+            assert abs(pc.exp_gamma(r, ua, ub) - cm.exp_gamma(r, ua, ub)) <= 1e-13 * max(1.0, abs(cm.exp_gamma(r, ua, ub)))
