@@ -5,15 +5,22 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * build, load or call it.  Nothing under dftbplus_b200/ links or imports it.
  *
- * PARITY STATUS: "parity unpinned" against the real Fortran build -- this container has no
- * Fortran compiler and no .skf parameter files, so the reference itself cannot run here
- * (SURVEY.md section 8c).  What IS pinned: the shell-pair rotations are checked against a
- * machine translation of the reference's own closed forms (oracle/gen_ref_sk.py ->
- * oracle/_ref/, golden vectors in tests/golden/sk_rot_golden.npz); chunk-range logic is
- * checked against the expectations of the reference's own unit test
- * (test/src/dftbp/unit/common/schedule.F90); the bisection search_asc_real_geq against the known
- * answers of unit/math/binarysearch.F90; the neighbour list's proximity rule against
- * unit/dftb/periodic.F90 ("neighbourdistance").
+ * PARITY STATUS: not checked against a run of the Fortran BINARY -- this container has no Fortran compiler and no
+ * .skf parameter files -- but pinned to the reference's own SOURCE, executed here by other means:
+ *   - buildH0 / buildS / buildDiatomicBlocks / rotateH0, unpackHS / packHS (real and k-points), mullikenPerOrbital /
+ *     PerBlock, addShift_atom / _block, derivativeNonSccEuclidian / derivative_blockEuclidean with
+ *     getFirstDerivFiniteDiff: the reference's source text is transpiled statement by statement to NumPy with Fortran
+ *     index semantics and RUN (oracle/fortran_exec.py, oracle/gen_ref_sparse.py); its outputs are the golden vectors
+ *     tests/golden/sparse_ref_golden.npz, which this file reproduces (H0 / S to 5e-17, forces to 2e-12, the rest to
+ *     rounding; tests/test_oracle_sparse_ref.py);
+ *   - the shell-pair rotations ss ... ff, the interpolation routines, the tolerance heap sort and the scalar
+ *     SCC-potential functions: machine translations to C (oracle/gen_ref_sk.py, gen_ref_math.py, gen_ref_scc.py ->
+ *     oracle/_ref/, golden vectors under tests/golden/), bit for bit where the operation order is the reference's;
+ *   - chunk ranges, the bisection search_asc_real_geq, the neighbour list's proximity rule and the Broyden mixer: the
+ *     known answers of the reference's own unit tests (unit/common/schedule.F90, unit/math/binarysearch.F90,
+ *     unit/dftb/periodic.F90, unit/mixer/broyden.F90).
+ * Still restated only: updateNeighbourList (checked through the identities of tests/test_oracle_path.py), the dense
+ * steps (NumPy / SciPy), stress, the Ewald sums (pinned to Madelung constants), Efilling.
  *
  * Every routine cites the reference file:line (relative to /root/reference/src/dftbp/)
  * whose arithmetic and loop order it follows.  Arrays use the reference's layout:

@@ -1,0 +1,374 @@
+"""Run loop routines of the reference from their own source text: a Fortran-subset -> Python (NumPy) transpiler.
+
+TEST INFRASTRUCTURE ONLY (see oracle/README.md).  The reference is Fortran and this image has no Fortran compiler.
+The sparse-layout routines of the hot path (unpackHS / packHS / mullikenPerOrbital / addShift ...) are short loop
+nests over whole-array statements -- array sections, reshape, sum(dim=), matmul -- which plain C translation
+(gen_ref_math.py) does not cover.  This module reads such a routine where it lies under /root/reference, rewrites it
+statement by statement into Python that operates on NumPy arrays with Fortran index semantics (FArr: lower bounds,
+inclusive sections, column-major reshape) and executes it.  No reference source text is stored in the repository:
+the golden vectors made with it are (tests/golden/, gen_ref_sparse.py).
+
+Covered subset: do / do while / if blocks, scalar and array-section assignments, reshape, sum(.., dim=), matmul,
+size, dot_product, exp / cos / sin / sqrt / abs / real / cmplx / conjg / transpose, derived-type components (a%b),
+implied-do array constructors of the form [(i, i = a, b)], allocate of 1-D index arrays.  Calls are mapped by the
+caller (call_map); assertions and preprocessor lines are dropped."""
+import math
+import re
+
+import numpy as np
+
+
+class FArr:
+    """NumPy array with Fortran lower bounds.  a[i, j] -> scalar; any slice -> plain ndarray view/copy (sections are
+    1-based afterwards, as in Fortran); a[...] = value assigns with Fortran conformance (scalar broadcast or same shape)."""
+
+    def __init__(self, data, lower=None):
+        self.a = data
+        self.lb = tuple(lower) if lower is not None else (1,) * data.ndim
+
+    def _index(self, idx):
+        if not isinstance(idx, tuple):
+            idx = (idx,)
+        assert len(idx) == self.a.ndim, "rank mismatch"
+        out = []
+        for k, (i, lb) in enumerate(zip(idx, self.lb)):
+            if isinstance(i, slice):
+                lo = lb if i.start is None else int(i.start)
+                hi = lb + self.a.shape[k] - 1 if i.stop is None else int(i.stop)
+                assert i.step is None
+                assert lo >= lb and hi <= lb + self.a.shape[k] - 1 or hi < lo, "section out of bounds"
+                out.append(slice(lo - lb, max(hi - lb + 1, lo - lb)))
+            else:
+                j = int(i) - lb
+                assert 0 <= j < self.a.shape[k], "index out of bounds"
+                out.append(j)
+        return tuple(out)
+
+    def __getitem__(self, idx):
+        v = self.a[self._index(idx)]
+        return v.item() if np.ndim(v) == 0 else v
+
+    def __setitem__(self, idx, value):
+        ix = self._index(idx)
+        value = value.a if isinstance(value, FArr) else value
+        if np.ndim(value) == 0:
+            self.a[ix] = value
+        else:
+            tgt = self.a[ix]
+            assert tgt.shape == np.shape(value), "non-conforming assignment %s <- %s" % (tgt.shape, np.shape(value))
+            self.a[ix] = value
+
+
+def _whole(op):
+    return lambda self, other: op(self.a, other.a if isinstance(other, FArr) else other)
+
+
+# whole-array expressions (a bare array name): element-wise on the data, result a plain ndarray
+for _n, _f in (("__mul__", np.multiply), ("__add__", np.add), ("__sub__", np.subtract), ("__truediv__", np.divide)):
+    setattr(FArr, _n, _whole(_f))
+for _n, _f in (("__rmul__", np.multiply), ("__radd__", np.add)):
+    setattr(FArr, _n, _whole(_f))
+FArr.__rsub__ = lambda self, other: np.subtract(other, self.a)
+FArr.__neg__ = lambda self: -self.a
+FArr.__pow__ = lambda self, n: self.a ** n
+FArr.__array__ = lambda self, dtype=None, copy=None: self.a if dtype is None else self.a.astype(dtype)
+
+
+def f_reshape(x, shape):
+    x = x.a if isinstance(x, FArr) else np.asarray(x)
+    shape = tuple(int(s) for s in (shape if np.ndim(shape) else (shape,)))
+    return np.reshape(x, shape, order="F")
+
+
+def f_sum(x, dim=None):
+    x = x.a if isinstance(x, FArr) else np.asarray(x)
+    if dim is None:
+        return float(np.sum(x)) if not np.iscomplexobj(x) else complex(np.sum(x))
+    return np.sum(x, axis=int(dim) - 1)
+
+
+def f_size(x, dim=None):
+    x = x.a if isinstance(x, FArr) else np.asarray(x)
+    return int(x.size) if dim is None else int(x.shape[int(dim) - 1])
+
+
+def f_matmul(a, b):
+    a = a.a if isinstance(a, FArr) else a
+    b = b.a if isinstance(b, FArr) else b
+    return np.matmul(a, b)
+
+
+def f_dot(a, b):
+    a = a.a if isinstance(a, FArr) else a
+    b = b.a if isinstance(b, FArr) else b
+    s = 0.0
+    for x, y in zip(np.ravel(a), np.ravel(b)):   # serial sum like the intrinsic on short vectors
+        s = s + x * y
+    return s
+
+
+def f_cmplx(re_, im_=0.0, kind=None):
+    return complex(re_, im_)
+
+
+def f_real(x, kind=None):
+    return np.real(x) if np.ndim(x) else float(np.real(x))
+
+
+ENV = dict(np=np, math=math, FArr=FArr, f_reshape=f_reshape, f_sum=f_sum, f_size=f_size, f_matmul=f_matmul, f_dot=f_dot,
+           dp=None, f_cmplx=f_cmplx, f_real=f_real, f_exp=lambda x: np.exp(x) if np.ndim(x) else (complex(np.exp(x)) if isinstance(x, complex) else math.exp(x)),
+           f_conjg=np.conj, f_transpose=np.transpose, pi=3.14159265358979323846264338327950288, imag=1j)
+
+INTRINSICS = {"reshape": "f_reshape", "sum": "f_sum", "size": "f_size", "matmul": "f_matmul", "dot_product": "f_dot",
+              "cmplx": "f_cmplx", "real": "f_real", "exp": "f_exp", "cos": "math.cos", "sin": "math.sin", "sqrt": "math.sqrt",
+              "abs": "abs", "conjg": "f_conjg", "transpose": "f_transpose", "max": "max", "min": "min", "mod": "f_mod"}
+ENV["f_mod"] = lambda a, b: int(math.fmod(a, b)) if isinstance(a, int) and isinstance(b, int) else math.fmod(a, b)
+
+
+def _logical_lines(text):
+    out, cur = [], ""
+    for raw in text.splitlines():
+        line = raw.split("!")[0].rstrip()
+        if not line.strip() or line.strip().startswith("#:") or line.strip().startswith("@:"):
+            continue
+        s = line.strip()
+        if cur:
+            s = cur + " " + s.lstrip("&").strip()
+            cur = ""
+        if s.endswith("&"):
+            cur = s[:-1].rstrip()
+            continue
+        out.append(s)
+    return out
+
+
+def _match(s, i):
+    depth = 0
+    for j in range(i, len(s)):
+        if s[j] in "([":
+            depth += 1
+        elif s[j] in ")]":
+            depth -= 1
+            if depth == 0:
+                return j
+    raise ValueError("unbalanced: " + s)
+
+
+def _split_top(s):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    out.append(cur)
+    return out
+
+
+def _expr(s, arrays):
+    s = s.strip()
+    for a, b in ((r"\.gt\.", ">"), (r"\.lt\.", "<"), (r"\.ge\.", ">="), (r"\.le\.", "<="), (r"\.eq\.", "=="), (r"\.ne\.", "!="),
+                 (r"\.and\.", " and "), (r"\.or\.", " or "), (r"\.not\.", " not "), (r"\.true\.", "True"), (r"\.false\.", "False")):
+        s = re.sub(a, b, s, flags=re.I)
+    s = s.replace("/=", "!=").replace("(/", "[").replace("/)", "]")
+    s = re.sub(r"(\d+\.\d*(?:[eE][-+]?\d+)?|\d+)_dp", r"\1", s)
+    s = re.sub(r"\bdim\s*=\s*", "", s)
+    out, i = "", 0
+    while i < len(s):
+        m = re.match(r"[A-Za-z_]\w*(?:%[A-Za-z_]\w*)*", s[i:])
+        if not m:
+            out += s[i]
+            i += 1
+            continue
+        name = m.group(0)
+        j = i + len(name)
+        k = j
+        while k < len(s) and s[k] == " ":
+            k += 1
+        pyname = name.replace("%", ".")
+        base = name.split("%")[-1] if "%" in name else name
+        if k < len(s) and s[k] == "(":
+            e = _match(s, k)
+            inner = _expr(s[k + 1:e], arrays)
+            if name.lower() in INTRINSICS and "%" not in name:
+                out += "%s(%s)" % (INTRINSICS[name.lower()], inner)
+            elif name in arrays or base in arrays:
+                out += "%s[%s]" % (pyname, inner)
+            else:
+                out += "%s(%s)" % (pyname, inner)
+            i = e + 1
+            continue
+        out += pyname
+        i = j
+    return out
+
+
+def transpile(src, kind, name, call_map=None, extra_arrays=()):
+    """-> (python source of def <name>(args), argument list).  call_map: 'callee' -> python statement template using
+    {args} (list of translated arguments); unknown calls raise."""
+    m = re.search(r"\b%s\s+%s\s*\((.*?)\)\s*\n(.*?)\bend\s+%s\s+%s\b" % (kind, name, kind, name), src, re.S | re.I)
+    if not m:
+        raise RuntimeError("routine %s not found" % name)
+    args = [a.strip() for a in m.group(1).replace("&", " ").replace("\n", " ").split(",")]
+    lines = _logical_lines(m.group(2))
+    # Fortran is case-insensitive: every identifier takes its first spelling (dummy arguments first)
+    canon = {}
+    for tok in args + re.findall(r"[A-Za-z_]\w*", "\n".join(lines)):
+        canon.setdefault(tok.lower(), tok)
+    lines = [re.sub(r"[A-Za-z_]\w*", lambda t: canon[t.group(0).lower()], ln) for ln in lines]
+    arrays, local_alloc, body, lower = set(extra_arrays), [], [], {}
+    for ln in lines:
+        d = re.match(r"(real\(dp\)|integer|complex\(dp\)|logical|type\(\w+\)|class\(\w+\)|character\([^)]*\))\s*(,[^:]*)?::\s*(.*)$", ln, re.I)
+        if d:
+            typ, attrs, rest = d.group(1).lower(), (d.group(2) or "").lower(), d.group(3)
+            # split declared entities at top-level commas
+            ents, depth, cur = [], 0, ""
+            for ch in rest:
+                if ch == "(":
+                    depth += 1
+                elif ch == ")":
+                    depth -= 1
+                if ch == "," and depth == 0:
+                    ents.append(cur.strip())
+                    cur = ""
+                else:
+                    cur += ch
+            ents.append(cur.strip())
+            for e in ents:
+                em = re.match(r"(\w+)\s*\((.*)\)$", e)
+                if not em:
+                    continue
+                arrays.add(em.group(1))
+                lower[em.group(1)] = [int(x.split(":")[0]) if ":" in x and x.split(":")[0].strip() else 1
+                                      for x in _split_top(em.group(2))] if "intent" in attrs else None
+                if "intent" not in attrs and "allocatable" not in attrs and "pointer" not in attrs:
+                    dims = [_expr(x, arrays) for x in _split_top(em.group(2))]
+                    dt = "complex" if typ.startswith("complex") else ("int" if typ == "integer" else "float")
+                    local_alloc.append("%s = FArr(np.zeros((%s,), dtype=%s, order='F'))" % (em.group(1), ", ".join(dims), dt))
+            continue
+        body.append(ln)
+    py, ind, selects = ["def %s(%s):" % (name, ", ".join(args))], "    ", []
+    for a_ in args:
+        if lower.get(a_) is not None:
+            py.append("%s%s = %s if isinstance(%s, FArr) or not isinstance(%s, np.ndarray) else FArr(%s, %r)" % (ind, a_, a_, a_, a_, a_, tuple(lower[a_])))
+    py += [ind + x for x in local_alloc]
+    for s in body:
+        low = s.lower()
+        mm = re.match(r"if\s*\((.*)\)\s*then$", s, re.I)
+        if mm:
+            py.append("%sif %s:" % (ind, _expr(mm.group(1), arrays)))
+            ind += "    "
+            continue
+        mm = re.match(r"else\s*if\s*\((.*)\)\s*then$", s, re.I)
+        if mm:
+            ind = ind[:-4]
+            py.append("%selif %s:" % (ind, _expr(mm.group(1), arrays)))
+            ind += "    "
+            continue
+        if low == "else":
+            ind = ind[:-4]
+            py.append(ind + "else:")
+            ind += "    "
+            continue
+        if re.match(r"end\s*(if|do)$", low):
+            py.append(ind + "pass")
+            ind = ind[:-4]
+            continue
+        mm = re.match(r"select\s+case\s*\((.*)\)$", s, re.I)
+        if mm:
+            selects.append([_expr(mm.group(1), arrays), True])
+            continue
+        mm = re.match(r"case\s*\((.*)\)$", s, re.I)
+        if mm or low == "case default":
+            sel = selects[-1]
+            if not sel[1]:
+                ind = ind[:-4]
+            if mm:
+                py.append("%s%s %s == %s:" % (ind, "if" if sel[1] else "elif", sel[0], _expr(mm.group(1), arrays)))
+            else:
+                py.append(ind + ("if True:" if sel[1] else "else:"))
+            sel[1] = False
+            ind += "    "
+            continue
+        if re.match(r"end\s*select$", low):
+            sel = selects.pop()
+            if not sel[1]:
+                py.append(ind + "pass")
+                ind = ind[:-4]
+            continue
+        mm = re.match(r"(\w+)\s*=>\s*(.*)$", s)
+        if mm:   # pointer assignment: a view
+            py.append("%s%s = %s" % (ind, mm.group(1), _expr(mm.group(2), arrays)))
+            continue
+        mm = re.match(r"do\s+while\s*\((.*)\)$", s, re.I)
+        if mm:
+            py.append("%swhile %s:" % (ind, _expr(mm.group(1), arrays)))
+            ind += "    "
+            continue
+        mm = re.match(r"do\s+(\w+)\s*=\s*(.*)$", s, re.I)
+        if mm:
+            parts = [p for p in re.split(r",(?![^()]*\))", mm.group(2))]
+            lo, hi = _expr(parts[0], arrays), _expr(parts[1], arrays)
+            py.append("%sfor %s in range(%s, (%s) + 1):" % (ind, mm.group(1), lo, hi))
+            ind += "    "
+            continue
+        mm = re.match(r"call\s+(\w+(?:%\w+)*)\s*\((.*)\)$", s, re.I)
+        if mm:
+            callee = mm.group(1)
+            cargs = [_expr(p, arrays) for p in re.split(r",(?![^()]*\))", mm.group(2))]
+            if not call_map or callee not in call_map:
+                raise ValueError("unmapped call: " + s)
+            tmpl = call_map[callee]
+            py.append(ind + (tmpl(cargs) if callable(tmpl) else tmpl.format(args=cargs)))
+            continue
+        mm = re.match(r"allocate\s*\(\s*(\w+)\s*\((.*)\)\s*\)$", s, re.I)
+        if mm:
+            arrays.add(mm.group(1))
+            py.append("%s%s = FArr(np.zeros((%s,), dtype=int))" % (ind, mm.group(1), _expr(mm.group(2), arrays)))
+            continue
+        mm = re.match(r"(\w+)\s*\(\s*:\s*\)\s*=\s*\[\s*\(\s*(\w+)\s*,\s*\2\s*=\s*(.*?),\s*(.*?)\)\s*\]$", s)
+        if mm:   # implied do: a(:) = [(i, i = lo, hi)]
+            py.append("%s%s[:] = np.arange(%s, (%s) + 1)" % (ind, mm.group(1), _expr(mm.group(3), arrays), _expr(mm.group(4), arrays)))
+            continue
+        mm = re.match(r"if\s*(\(.*)$", s, re.I)
+        if mm:  # one-line if
+            e = _match(mm.group(1), 0)
+            cond, stmt = mm.group(1)[1:e], mm.group(1)[e + 1:].strip()
+            cm_ = re.match(r"call\s+(\w+)\s*\((.*)\)$", stmt, re.I)
+            if cm_:
+                cargs = [_expr(p, arrays) for p in re.split(r",(?![^()]*\))", cm_.group(2))]
+                if not call_map or cm_.group(1) not in call_map:
+                    raise ValueError("unmapped call: " + s)
+                py.append("%sif %s: %s" % (ind, _expr(cond, arrays), call_map[cm_.group(1)].format(args=cargs)))
+                continue
+            am = re.match(r"([^=]+?)=(?!=)(.*)$", stmt)
+            py.append("%sif %s: %s = %s" % (ind, _expr(cond, arrays), _expr(am.group(1), arrays), _expr(am.group(2), arrays)))
+            continue
+        mm = re.match(r"([^=]+?)=(?!=)(.*)$", s)
+        if mm:
+            py.append("%s%s = %s" % (ind, _expr(mm.group(1), arrays), _expr(mm.group(2), arrays)))
+            continue
+        raise ValueError("cannot translate: " + s)
+    transpile.last_lower = {k: v for k, v in lower.items() if v is not None}
+    return "\n".join(py) + "\n", args
+
+
+def compile_routine(src, kind, name, call_map=None, extra_env=None, extra_arrays=()):
+    code, args = transpile(src, kind, name, call_map, extra_arrays)
+    env = dict(ENV)
+    if extra_env:
+        env.update(extra_env)
+    exec(compile(code, "<%s from the reference>" % name, "exec"), env)
+    fn = env[name]
+    fn.lower = dict(transpile.last_lower)
+    return fn, args, code
+
+
+def wrap(fn, name, array):
+    """NumPy array (Fortran dimension order) -> FArr with the lower bounds the routine declares for dummy `name`."""
+    return FArr(array, fn.lower.get(name))
