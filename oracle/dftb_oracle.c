@@ -8,8 +8,8 @@
  * PARITY STATUS: not checked against a run of the Fortran BINARY -- this container has no Fortran compiler and no
  * .skf parameter files -- but pinned to the reference's own SOURCE, executed here by other means:
  *   - buildH0 / buildS / buildDiatomicBlocks / rotateH0, unpackHS / packHS (real and k-points), mullikenPerOrbital /
- *     PerBlock, addShift_atom / _block, derivativeNonSccEuclidian / derivative_blockEuclidean with
- *     getFirstDerivFiniteDiff: the reference's source text is transpiled statement by statement to NumPy with Fortran
+ *     PerBlock, addShift_atom / _block, derivativeNonSccEuclidian / derivative_blockEuclidean and getNonSCCStress /
+ *     getBlockStress with getFirstDerivFiniteDiff (and, for oracle.py, fullDensityMatrix_real / fullEnergyDensityMatrix_real): the reference's source text is transpiled statement by statement to NumPy with Fortran
  *     index semantics and RUN (oracle/fortran_exec.py, oracle/gen_ref_sparse.py); its outputs are the golden vectors
  *     tests/golden/sparse_ref_golden.npz, which this file reproduces (H0 / S to 5e-17, forces to 2e-12, the rest to
  *     rounding; tests/test_oracle_sparse_ref.py);
@@ -19,8 +19,8 @@
  *   - chunk ranges, the bisection search_asc_real_geq, the neighbour list's proximity rule and the Broyden mixer: the
  *     known answers of the reference's own unit tests (unit/common/schedule.F90, unit/math/binarysearch.F90,
  *     unit/dftb/periodic.F90, unit/mixer/broyden.F90).
- * Still restated only: updateNeighbourList (checked through the identities of tests/test_oracle_path.py), the dense
- * steps (NumPy / SciPy), stress, the Ewald sums (pinned to Madelung constants), Efilling.
+ * Still restated only: updateNeighbourList (checked through the identities of tests/test_oracle_path.py), the
+ * eigensolve (SciPy), the Ewald sums (pinned to Madelung constants), Efilling.
  *
  * Every routine cites the reference file:line (relative to /root/reference/src/dftbp/)
  * whose arithmetic and loop order it follows.  Arrays use the reference's layout:

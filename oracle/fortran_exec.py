@@ -121,7 +121,8 @@ ENV = dict(np=np, math=math, FArr=FArr, f_reshape=f_reshape, f_sum=f_sum, f_size
 
 INTRINSICS = {"reshape": "f_reshape", "sum": "f_sum", "size": "f_size", "matmul": "f_matmul", "dot_product": "f_dot",
               "cmplx": "f_cmplx", "real": "f_real", "exp": "f_exp", "cos": "math.cos", "sin": "math.sin", "sqrt": "math.sqrt",
-              "abs": "abs", "conjg": "f_conjg", "transpose": "f_transpose", "max": "max", "min": "min", "mod": "f_mod"}
+              "abs": "abs", "minval": "np.min", "maxval": "np.max", "epsilon": "f_epsilon", "sign": "math.copysign", "conjg": "f_conjg", "transpose": "f_transpose", "max": "max", "min": "min", "mod": "f_mod"}
+ENV["f_epsilon"] = lambda x: 2.220446049250313e-16
 ENV["f_mod"] = lambda a, b: int(math.fmod(a, b)) if isinstance(a, int) and isinstance(b, int) else math.fmod(a, b)
 
 
@@ -170,8 +171,41 @@ def _split_top(s):
     return out
 
 
+def _fix_eqv(s):
+    """a .eqv. b  ->  ((a)) == ((b)): the relational operators inside a and b bind tighter in Fortran, while Python would
+    chain the comparisons.  Operands end at the enclosing parenthesis or at a .and. / .or. of the same depth."""
+    while True:
+        m = re.search(r"\.eqv\.", s, re.I)
+        if not m:
+            return s
+        i, depth = m.start() - 1, 0
+        while i >= 0:
+            if s[i] == ")":
+                depth += 1
+            elif s[i] == "(":
+                if depth == 0:
+                    break
+                depth -= 1
+            elif depth == 0 and re.match(r"\.(and|or)\.", s[max(0, i - 4):i + 1][-5:], re.I):
+                break
+            i -= 1
+        left = i + 1
+        j, depth = m.end(), 0
+        while j < len(s):
+            if s[j] == "(":
+                depth += 1
+            elif s[j] == ")":
+                if depth == 0:
+                    break
+                depth -= 1
+            elif depth == 0 and re.match(r"\.(and|or)\.", s[j:j + 5], re.I):
+                break
+            j += 1
+        s = s[:left] + "((" + s[left:m.start()] + ")) == ((" + s[m.end():j] + "))" + s[j:]
+
+
 def _expr(s, arrays):
-    s = s.strip()
+    s = _fix_eqv(s.strip())
     for a, b in ((r"\.gt\.", ">"), (r"\.lt\.", "<"), (r"\.ge\.", ">="), (r"\.le\.", "<="), (r"\.eq\.", "=="), (r"\.ne\.", "!="),
                  (r"\.and\.", " and "), (r"\.or\.", " or "), (r"\.not\.", " not "), (r"\.true\.", "True"), (r"\.false\.", "False")):
         s = re.sub(a, b, s, flags=re.I)
@@ -312,15 +346,22 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
             continue
         mm = re.match(r"do\s+(\w+)\s*=\s*(.*)$", s, re.I)
         if mm:
-            parts = [p for p in re.split(r",(?![^()]*\))", mm.group(2))]
+            parts = _split_top(mm.group(2))
             lo, hi = _expr(parts[0], arrays), _expr(parts[1], arrays)
-            py.append("%sfor %s in range(%s, (%s) + 1):" % (ind, mm.group(1), lo, hi))
+            if len(parts) == 3:
+                st = _expr(parts[2], arrays)
+                py.append("%sfor %s in range(%s, (%s) + (1 if (%s) > 0 else -1), %s):" % (ind, mm.group(1), lo, hi, st, st))
+            else:
+                py.append("%sfor %s in range(%s, (%s) + 1):" % (ind, mm.group(1), lo, hi))
             ind += "    "
+            continue
+        if low in ("exit", "cycle"):
+            py.append(ind + ("break" if low == "exit" else "continue"))
             continue
         mm = re.match(r"call\s+(\w+(?:%\w+)*)\s*\((.*)\)$", s, re.I)
         if mm:
             callee = mm.group(1)
-            cargs = [_expr(p, arrays) for p in re.split(r",(?![^()]*\))", mm.group(2))]
+            cargs = [_expr(p, arrays) for p in _split_top(mm.group(2))]
             if not call_map or callee not in call_map:
                 raise ValueError("unmapped call: " + s)
             tmpl = call_map[callee]
@@ -341,7 +382,7 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
             cond, stmt = mm.group(1)[1:e], mm.group(1)[e + 1:].strip()
             cm_ = re.match(r"call\s+(\w+)\s*\((.*)\)$", stmt, re.I)
             if cm_:
-                cargs = [_expr(p, arrays) for p in re.split(r",(?![^()]*\))", cm_.group(2))]
+                cargs = [_expr(p, arrays) for p in _split_top(cm_.group(2))]
                 if not call_map or cm_.group(1) not in call_map:
                     raise ValueError("unmapped call: " + s)
                 py.append("%sif %s: %s" % (ind, _expr(cond, arrays), call_map[cm_.group(1)].format(args=cargs)))

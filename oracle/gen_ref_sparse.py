@@ -7,6 +7,9 @@ TEST INFRASTRUCTURE ONLY.  Routines, read where they lie under /root/reference:
     addShift_atom, addShift_block                                           dftb/shift.F90
     buildH0, buildS, buildDiatomicBlocks, getFirstDerivFiniteDiff           dftb/nonscc.F90
     derivativeNonSccEuclidian, derivative_blockEuclidean                    dftb/forces.F90
+    getNonSCCStress, getBlockStress                                         dftb/stress.F90
+    fullDensityMatrix_real, fullEnergyDensityMatrix_real                    dftb/densitymatrix.F90 (herk = the BLAS call
+                                                                            C := alpha A A^T + beta C, lower triangle)
     rotateH0                                                                dftb/sk.F90 (its ss ... ff callees are the
                                                                             machine translations of gen_ref_sk.py; the SK
                                                                             integrals come from the oracle's interpolation,
@@ -100,6 +103,18 @@ def routines():
     calls["derivator%getFirstDeriv"] = lambda a: "getFirstDerivFiniteDiff(%s, derivator)" % ", ".join(a)
     for name in ("derivativeNonSccEuclidian", "derivative_blockEuclidean"):
         r[name] = fx.compile_routine(frc, "subroutine", name, calls, extra_env=env, extra_arrays=orb_arrays)[0]
+    strs = open(REF + "stress.F90").read()
+    for name in ("getNonSCCStress", "getBlockStress"):
+        r[name] = fx.compile_routine(strs, "subroutine", name, calls, extra_env=env, extra_arrays=orb_arrays)[0]
+
+    def herk(c, a, alpha=1.0, beta=0.0):
+        a = a.a if isinstance(a, fx.FArr) else a
+        c.a[:, :] = np.tril(alpha * (a @ a.T) + beta * c.a) + np.triu(c.a, 1)
+
+    dms = open(REF + "densitymatrix.F90").read()
+    dcalls = {"herk": lambda a: "herk(%s)" % ", ".join(a)}
+    for name in ("fullDensityMatrix_real", "fullEnergyDensityMatrix_real"):
+        r[name] = fx.compile_routine(dms, "subroutine", name, dcalls, extra_env=dict(herk=herk, arbitraryConstant=0.1))[0]
     return r
 
 
@@ -227,6 +242,37 @@ def run_case(R, d):
       W(f, "species", species), W(f, "iNeighbour", iN), W(f, "nNeighbourSK", nN), W(f, "img2CentCell", img), W(f, "iPair", iP), orb,
       W(f, "shift", shb))
     out["deriv_block"] = der
+    # stress (periodic cases; the cluster cases run it too: a volume of 1000 bohr^3 is as good as any)
+    vol = 1000.0
+    f = R["getNonSCCStress"]
+    st = np.full((3, 3), 7.0, order="F")
+    f(None, W(f, "st", st), delta, W(f, "DM", d["rho"]), W(f, "EDM", d["over"]), contH, contS, W(f, "coords", coords), W(f, "species", species),
+      W(f, "iNeighbour", iN), W(f, "nNeighbourSK", nN), W(f, "img2CentCell", img), W(f, "iPair", iP), orb, vol)
+    out["stress_nonscc"] = st
+    f = R["getBlockStress"]
+    st = np.full((3, 3), 7.0, order="F")
+    f(None, W(f, "st", st), delta, W(f, "DM", dm2), W(f, "EDM", d["orig"]), contH, contS, W(f, "coords", coords), W(f, "species", species),
+      W(f, "iNeighbour", iN), W(f, "nNeighbourSK", nN), W(f, "img2CentCell", img), W(f, "iPair", iP), orb, W(f, "shift", shb), vol)
+    out["stress_block"] = st
+    # density matrices: both branches of both routines (positive fillings / zero and negative weights)
+    nd = min(n, 40)
+    rngd = np.random.default_rng(5 + nd)
+    C = F(rngd.normal(size=(nd, nd)))
+    eig = np.sort(rngd.normal(size=nd))
+    for tag, fill in (("pos", np.concatenate([np.full(nd // 2, 2.0), rngd.uniform(0.1, 1.9, 2), np.zeros(nd - nd // 2 - 2)])),
+                      ("mixed", np.concatenate([rngd.normal(size=nd // 2), np.zeros(nd - nd // 2)]))):
+        for key, fname in (("dm", "fullDensityMatrix_real"), ("edm", "fullEnergyDensityMatrix_real")):
+            f = R[fname]
+            dm = np.full((nd, nd), 7.0, order="F")
+            cc = C.copy(order="F")
+            if key == "dm":
+                f(W(f, "dm", dm), W(f, "eigenvecs", cc), W(f, "filling", fill))
+            else:
+                f(W(f, "dm", dm), W(f, "eigenvecs", cc), W(f, "filling", fill), W(f, "eigen", eig if tag == "mixed" else -np.abs(eig) - 0.1))
+            out["%s_%s" % (key, tag)] = dm
+            out["%s_%s_cback" % (key, tag)] = cc       # the eigenvectors are scaled and scaled back
+        out["dmin_%s_fill" % tag] = fill
+    out["dmin_C"], out["dmin_eig"] = C, eig
     for zero in (True, False):
         f = R["addShift_atom"]
         ham = F(d["ham0"].T.copy())                                    # (sparseSize, nSpin)

@@ -3,7 +3,8 @@ transpiles unpackHS_real / unpackHS_cmplx_kpts / packHS_real / packHS_cmplx_kpts
 mullikenPerBlock (dftb/populations.F90) and addShift_atom / addShift_block (dftb/shift.F90) statement by statement into
 NumPy with Fortran index semantics -- and buildH0 / buildS / buildDiatomicBlocks (dftb/nonscc.F90) with rotateH0
 (dftb/sk.F90), and the force contractions derivativeNonSccEuclidian / derivative_blockEuclidean (dftb/forces.F90) with the
-finite-difference derivator getFirstDerivFiniteDiff, the same way; oracle/gen_ref_sparse.py ran them on H2O, the Ce/O cluster (f shells), the 2-atom Si
+finite-difference derivator getFirstDerivFiniteDiff, getNonSCCStress / getBlockStress (dftb/stress.F90) and
+fullDensityMatrix_real / fullEnergyDensityMatrix_real (dftb/densitymatrix.F90) the same way; oracle/gen_ref_sparse.py ran them on H2O, the Ce/O cluster (f shells), the 2-atom Si
 cell (hundreds of images folding onto the same dense blocks) and bcc Fe/C 128 and wrote tests/golden/sparse_ref_golden.npz.
 This pins index order, transposition, the on-site symmetrisation, the Bloch phase convention and accumulate / overwrite
 semantics of the oracle (and through the GPU parity tests, of the kernels) to the reference's code."""
@@ -63,6 +64,21 @@ def test_oracle_equals_the_executed_reference_source(name, gold):
     dm2 = np.stack([d["rho"], 0.3 * d["over"]])
     g2 = oracle.derivative_shift(model, geo, dm2, d["orig"], shift=d["shift_block"])
     _cmp(gold, name, "deriv_block", np.asfortranarray(g2.T), 1e-11)
+    # stress: getNonSCCStress / getBlockStress (dftb/stress.F90); the oracle returns st[ii, jj] = reference st(jj, ii)
+    s1 = oracle.stress(model, geo, d["rho"], d["over"], 1000.0)
+    _cmp(gold, name, "stress_nonscc", np.asfortranarray(s1.T), 1e-11)
+    s2 = oracle.stress(model, geo, dm2, d["orig"], 1000.0, shift=d["shift_block"])
+    _cmp(gold, name, "stress_block", np.asfortranarray(s2.T), 1e-11)
+    # density matrices: fullDensityMatrix_real / fullEnergyDensityMatrix_real (dftb/densitymatrix.F90), both branches each
+    if name not in G.SAMPLED:
+        C, eig = gold[name + "__dmin_C"], gold[name + "__dmin_eig"]
+        for tag in ("pos", "mixed"):
+            fill = gold["%s__dmin_%s_fill" % (name, tag)]
+            _cmp(gold, name, "dm_" + tag, np.asfortranarray(oracle.density_matrix(C, fill)), 1e-14)
+            e = eig if tag == "mixed" else -np.abs(eig) - 0.1
+            _cmp(gold, name, "edm_" + tag, np.asfortranarray(oracle.energy_density_matrix(C, fill, e)), 1e-14)
+            # the reference scales the eigenvectors and scales them back: they return to rounding
+            assert np.abs(gold["%s__dm_%s_cback" % (name, tag)] - C).max() <= 1e-14 * np.abs(C).max()
     for zero in (True, False):
         ham = oracle.add_shift(model, geo, d["ham0"].copy(), d["over"], d["shift_atom"], is_input_zero=zero)
         _cmp(gold, name, "add_shift_atom_%d" % zero, np.asfortranarray(ham.T), 1e-15)
