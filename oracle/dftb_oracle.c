@@ -12,15 +12,16 @@
  *     getBlockStress with getFirstDerivFiniteDiff (and, for oracle.py, fullDensityMatrix_real / fullEnergyDensityMatrix_real): the reference's source text is transpiled statement by statement to NumPy with Fortran
  *     index semantics and RUN (oracle/fortran_exec.py, oracle/gen_ref_sparse.py); its outputs are the golden vectors
  *     tests/golden/sparse_ref_golden.npz, which this file reproduces (H0 / S to 5e-17, forces to 2e-12, the rest to
- *     rounding; tests/test_oracle_sparse_ref.py);
+ *     rounding; tests/test_oracle_sparse_ref.py); updateNeighbourList the same way (oracle/gen_ref_neigh.py,
+ *     tests/test_oracle_neigh_ref.py): every array bit for bit, ties and the "too close" pair included;
  *   - the shell-pair rotations ss ... ff, the interpolation routines, the tolerance heap sort and the scalar
  *     SCC-potential functions: machine translations to C (oracle/gen_ref_sk.py, gen_ref_math.py, gen_ref_scc.py ->
  *     oracle/_ref/, golden vectors under tests/golden/), bit for bit where the operation order is the reference's;
  *   - chunk ranges, the bisection search_asc_real_geq, the neighbour list's proximity rule and the Broyden mixer: the
  *     known answers of the reference's own unit tests (unit/common/schedule.F90, unit/math/binarysearch.F90,
  *     unit/dftb/periodic.F90, unit/mixer/broyden.F90).
- * Still restated only: updateNeighbourList (checked through the identities of tests/test_oracle_path.py), the
- * eigensolve (SciPy), the Ewald sums (pinned to Madelung constants), Efilling.
+ * Still restated only: the eigensolve (SciPy), the Ewald sums (pinned to Madelung constants), Efilling,
+ * getSparseDescriptor / getNrOfNeighbours (a prefix sum and the unit-tested bisection).
  *
  * Every routine cites the reference file:line (relative to /root/reference/src/dftbp/)
  * whose arithmetic and loop order it follows.  Arrays use the reference's layout:

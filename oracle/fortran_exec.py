@@ -18,6 +18,16 @@ import re
 import numpy as np
 
 
+class LoopExit(Exception):
+    def __init__(self, label):
+        self.label = label
+
+
+class LoopCycle(Exception):
+    def __init__(self, label):
+        self.label = label
+
+
 class FArr:
     """NumPy array with Fortran lower bounds.  a[i, j] -> scalar; any slice -> plain ndarray view/copy (sections are
     1-based afterwards, as in Fortran); a[...] = value assigns with Fortran conformance (scalar broadcast or same shape)."""
@@ -38,6 +48,10 @@ class FArr:
                 assert i.step is None
                 assert lo >= lb and hi <= lb + self.a.shape[k] - 1 or hi < lo, "section out of bounds"
                 out.append(slice(lo - lb, max(hi - lb + 1, lo - lb)))
+            elif isinstance(i, (np.ndarray, FArr, list)):          # vector subscript
+                v = np.asarray(i.a if isinstance(i, FArr) else i, dtype=np.int64) - lb
+                assert v.size == 0 or (v.min() >= 0 and v.max() < self.a.shape[k]), "vector subscript out of bounds"
+                out.append(v)
             else:
                 j = int(i) - lb
                 assert 0 <= j < self.a.shape[k], "index out of bounds"
@@ -121,15 +135,31 @@ ENV = dict(np=np, math=math, FArr=FArr, f_reshape=f_reshape, f_sum=f_sum, f_size
 
 INTRINSICS = {"reshape": "f_reshape", "sum": "f_sum", "size": "f_size", "matmul": "f_matmul", "dot_product": "f_dot",
               "cmplx": "f_cmplx", "real": "f_real", "exp": "f_exp", "cos": "math.cos", "sin": "math.sin", "sqrt": "math.sqrt",
-              "abs": "abs", "minval": "np.min", "maxval": "np.max", "epsilon": "f_epsilon", "sign": "math.copysign", "conjg": "f_conjg", "transpose": "f_transpose", "max": "max", "min": "min", "mod": "f_mod"}
+              "abs": "abs", "minval": "np.min", "maxval": "np.max", "epsilon": "f_epsilon", "sign": "math.copysign", "present": "f_present", "ubound": "f_ubound", "nint": "f_nint", "conjg": "f_conjg", "transpose": "f_transpose", "max": "max", "min": "min", "mod": "f_mod"}
 ENV["f_epsilon"] = lambda x: 2.220446049250313e-16
+ENV["f_present"] = lambda x: x is not None
+ENV["f_ubound"] = lambda x, dim: x.lb[int(dim) - 1] + x.a.shape[int(dim) - 1] - 1
+ENV["f_nint"] = lambda x: int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
+ENV["LoopExit"], ENV["LoopCycle"] = LoopExit, LoopCycle
 ENV["f_mod"] = lambda a, b: int(math.fmod(a, b)) if isinstance(a, int) and isinstance(b, int) else math.fmod(a, b)
 
 
 def _logical_lines(text):
-    out, cur = [], ""
+    out, cur, skip = [], "", []     # skip: stack of booleans (True = lines are dropped)
     for raw in text.splitlines():
         line = raw.split("!")[0].rstrip()
+        st = line.strip()
+        if st.startswith("#:if") or st.startswith("#:block"):
+            skip.append(True)        # every build option (WITH_MPI, EXP_TRAP, DEBUG_CODE ...) is off
+            continue
+        if st.startswith("#:else"):
+            skip[-1] = not skip[-1]
+            continue
+        if st.startswith("#:endif") or st.startswith("#:endblock"):
+            skip.pop()
+            continue
+        if any(skip):
+            continue
         if not line.strip() or line.strip().startswith("#:") or line.strip().startswith("@:"):
             continue
         s = line.strip()
@@ -255,7 +285,7 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
     for tok in args + re.findall(r"[A-Za-z_]\w*", "\n".join(lines)):
         canon.setdefault(tok.lower(), tok)
     lines = [re.sub(r"[A-Za-z_]\w*", lambda t: canon[t.group(0).lower()], ln) for ln in lines]
-    arrays, local_alloc, body, lower = set(extra_arrays), [], [], {}
+    arrays, local_alloc, body, lower, dtypes, int_scalars = set(extra_arrays), [], [], {}, {}, set()
     for ln in lines:
         d = re.match(r"(real\(dp\)|integer|complex\(dp\)|logical|type\(\w+\)|class\(\w+\)|character\([^)]*\))\s*(,[^:]*)?::\s*(.*)$", ln, re.I)
         if d:
@@ -276,8 +306,11 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
             for e in ents:
                 em = re.match(r"(\w+)\s*\((.*)\)$", e)
                 if not em:
+                    if typ == "integer" and re.match(r"\w+$", e):
+                        int_scalars.add(e)
                     continue
                 arrays.add(em.group(1))
+                dtypes[em.group(1)] = "complex" if typ.startswith("complex") else ("int" if typ == "integer" else "float")
                 lower[em.group(1)] = [int(x.split(":")[0]) if ":" in x and x.split(":")[0].strip() else 1
                                       for x in _split_top(em.group(2))] if "intent" in attrs else None
                 if "intent" not in attrs and "allocatable" not in attrs and "pointer" not in attrs:
@@ -286,7 +319,7 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
                     local_alloc.append("%s = FArr(np.zeros((%s,), dtype=%s, order='F'))" % (em.group(1), ", ".join(dims), dt))
             continue
         body.append(ln)
-    py, ind, selects = ["def %s(%s):" % (name, ", ".join(args))], "    ", []
+    py, ind, selects, loops = ["def %s(%s):" % (name, ", ".join(args))], "    ", [], []
     for a_ in args:
         if lower.get(a_) is not None:
             py.append("%s%s = %s if isinstance(%s, FArr) or not isinstance(%s, np.ndarray) else FArr(%s, %r)" % (ind, a_, a_, a_, a_, a_, tuple(lower[a_])))
@@ -309,7 +342,22 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
             py.append(ind + "else:")
             ind += "    "
             continue
-        if re.match(r"end\s*(if|do)$", low):
+        em_ = re.match(r"end\s*do(\s+\w+)?$", low)
+        if em_:
+            lab = loops.pop() if loops else None
+            py.append(ind + "pass")
+            if lab:
+                ind = ind[:-4]
+                py.append("%sexcept LoopCycle as e_:" % ind)
+                py.append("%s    if e_.label.lower() != %r: raise" % (ind, lab.lower()))
+                ind = ind[:-4]
+                ind = ind[:-4]
+                py.append("%sexcept LoopExit as e_:" % ind)
+                py.append("%s    if e_.label.lower() != %r: raise" % (ind, lab.lower()))
+            else:
+                ind = ind[:-4]
+            continue
+        if re.match(r"end\s*if$", low):
             py.append(ind + "pass")
             ind = ind[:-4]
             continue
@@ -341,11 +389,21 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
             continue
         mm = re.match(r"do\s+while\s*\((.*)\)$", s, re.I)
         if mm:
+            loops.append(None)
             py.append("%swhile %s:" % (ind, _expr(mm.group(1), arrays)))
             ind += "    "
             continue
+        label = None
+        lm = re.match(r"(\w+)\s*:\s*(do\b.*)$", s, re.I)
+        if lm:
+            label, s = lm.group(1), lm.group(2)
+            low = s.lower()
         mm = re.match(r"do\s+(\w+)\s*=\s*(.*)$", s, re.I)
         if mm:
+            if label:
+                py.append(ind + "try:")
+                ind += "    "
+            loops.append(label)
             parts = _split_top(mm.group(2))
             lo, hi = _expr(parts[0], arrays), _expr(parts[1], arrays)
             if len(parts) == 3:
@@ -354,9 +412,22 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
             else:
                 py.append("%sfor %s in range(%s, (%s) + 1):" % (ind, mm.group(1), lo, hi))
             ind += "    "
+            if label:
+                py.append(ind + "try:")
+                ind += "    "
+            continue
+        if low == "return":
+            py.append(ind + "return locals()")
             continue
         if low in ("exit", "cycle"):
             py.append(ind + ("break" if low == "exit" else "continue"))
+            continue
+        xm = re.match(r"(exit|cycle)\s+(\w+)$", s, re.I)
+        if xm:
+            py.append("%sraise %s(%r)" % (ind, "LoopExit" if xm.group(1).lower() == "exit" else "LoopCycle", xm.group(2)))
+            continue
+        if low.startswith("write(") or low.startswith("write ("):
+            py.append(ind + "pass")
             continue
         mm = re.match(r"call\s+(\w+(?:%\w+)*)\s*\((.*)\)$", s, re.I)
         if mm:
@@ -370,7 +441,17 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
         mm = re.match(r"allocate\s*\(\s*(\w+)\s*\((.*)\)\s*\)$", s, re.I)
         if mm:
             arrays.add(mm.group(1))
-            py.append("%s%s = FArr(np.zeros((%s,), dtype=int))" % (ind, mm.group(1), _expr(mm.group(2), arrays)))
+            los, shp = [], []
+            for dspec in _split_top(mm.group(2)):
+                if ":" in dspec:
+                    lo_, hi_ = dspec.split(":")
+                    los.append(_expr(lo_, arrays))
+                    shp.append("(%s) - (%s) + 1" % (_expr(hi_, arrays), _expr(lo_, arrays)))
+                else:
+                    los.append("1")
+                    shp.append(_expr(dspec, arrays))
+            py.append("%s%s = FArr(np.zeros((%s,), dtype=%s, order='F'), (%s,))" % (ind, mm.group(1), ", ".join(shp),
+                                                                                dtypes.get(mm.group(1), "int"), ", ".join(los)))
             continue
         mm = re.match(r"(\w+)\s*\(\s*:\s*\)\s*=\s*\[\s*\(\s*(\w+)\s*,\s*\2\s*=\s*(.*?),\s*(.*?)\)\s*\]$", s)
         if mm:   # implied do: a(:) = [(i, i = lo, hi)]
@@ -392,9 +473,13 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
             continue
         mm = re.match(r"([^=]+?)=(?!=)(.*)$", s)
         if mm:
-            py.append("%s%s = %s" % (ind, _expr(mm.group(1), arrays), _expr(mm.group(2), arrays)))
+            rhs = _expr(mm.group(2), arrays)
+            if mm.group(1).strip() in int_scalars and "/" in rhs:
+                rhs = "int(%s)" % rhs     # integer division / real -> integer conversion: truncation (non-negative operands)
+            py.append("%s%s = %s" % (ind, _expr(mm.group(1), arrays), rhs))
             continue
         raise ValueError("cannot translate: " + s)
+    py.append("    return locals()")
     transpile.last_lower = {k: v for k, v in lower.items() if v is not None}
     return "\n".join(py) + "\n", args
 
