@@ -416,6 +416,9 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
                 py.append(ind + "try:")
                 ind += "    "
             continue
+        if re.match(r"deallocate\s*\(", low):
+            py.append(ind + "pass")
+            continue
         if low == "return":
             py.append(ind + "return locals()")
             continue

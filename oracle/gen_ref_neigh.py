@@ -20,6 +20,7 @@ import fortran_exec as fx  # noqa: E402
 import gen_ref_math  # noqa: E402
 
 REF = "/root/reference/src/dftbp/dftb/periodic.F90"
+REF_S2D = "/root/reference/src/dftbp/dftb/sparse2dense.F90"
 
 
 class Neigh:
@@ -94,6 +95,19 @@ def run(f, coord0, rcell, cutoff, symmetric=False):
                 neighDist2=np.ascontiguousarray(neigh.neighDist2.a.T))
 
 
+def sparse_descriptor(r, n_orb_atom):
+    """getSparseDescriptor (dftb/sparse2dense.F90:3617-3662) executed from its source on the list r."""
+    f = fx.compile_routine(open(REF_S2D).read(), "subroutine", "getSparseDescriptor", {}, extra_arrays=("nOrbAtom",))[0]
+    n = len(n_orb_atom)
+    orb = Neigh()
+    orb.nOrbAtom = fx.FArr(np.asarray(n_orb_atom, dtype=np.int64))
+    ipair = fx.FArr(np.zeros((1, n), dtype=np.int64, order="F"), (0, 1))       # too small on purpose: the routine reallocates
+    loc = f(fx.wrap(f, "iNeighbour", np.asfortranarray(r["iNeighbour"].T.astype(np.int64))),
+            fx.wrap(f, "nNeighbour", r["nNeighbour"].astype(np.int64)), fx.wrap(f, "img2CentCell", r["img2CentCell"].astype(np.int64)),
+            orb, ipair, 0)
+    return np.ascontiguousarray(loc["iPair"].a.T).astype(np.int32), int(loc["sparseSize"])
+
+
 def cases():
     """name -> (coord0, rcell, cutoff, symmetric); inputs are regenerated by the test from the same code."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -120,6 +134,11 @@ def cases():
     return out
 
 
+def orbitals_of(n):
+    """orbitals per atom of the descriptor check: alternating s p d / s p / s atoms"""
+    return np.array([(9, 4, 1)[i % 3] for i in range(n)], dtype=np.int64)
+
+
 def main():
     if not os.path.exists(REF):
         print("reference not present; nothing to do", file=sys.stderr)
@@ -128,6 +147,8 @@ def main():
     g = {}
     for name, (c0, rcell, cutoff, sym) in cases().items():
         r = run(f, c0, rcell, cutoff, sym)
+        if "error" not in r and not sym:
+            r["iPair"], r["sparseSize"] = sparse_descriptor(r, orbitals_of(len(c0)))
         for k, v in r.items():
             g["%s__%s" % (name, k)] = np.asarray(v)
         print(name, {k: (v if np.ndim(v) == 0 or k == "error" else np.shape(v)) for k, v in r.items()})

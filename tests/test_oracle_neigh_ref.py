@@ -32,12 +32,17 @@ def cases():
 @pytest.mark.parametrize("name", ["h2o", "ce_o", "si2", "fec128", "crystal", "crystal_symmetric"])
 def test_oracle_list_equals_the_executed_reference_source(name, gold, cases):
     c0, rcell, cutoff, sym = cases[name]
-    got = oracle.neighbour_list_full([4], c0, np.ones(len(c0), dtype=np.int32), rcell, cutoff, cutoff, symmetric=sym)
+    species = np.array([1 + i % 3 for i in range(len(c0))], dtype=np.int32)      # 9 / 4 / 1 orbitals: gen_ref_neigh.orbitals_of
+    got = oracle.neighbour_list_full([9, 4, 1], c0, species, rcell, cutoff, cutoff, symmetric=sym)
     assert got["nAllAtom"] == int(gold[name + "__nAllAtom"]) and got["mNeigh"] == int(gold[name + "__mNeigh"])
     for k in KEYS:
         ref = gold["%s__%s" % (name, k)]
         assert got[k].shape == ref.shape, k
         assert np.array_equal(got[k], ref), k          # bit for bit, distances and coordinates included
+    if not sym:
+        # getSparseDescriptor (dftb/sparse2dense.F90:3617-3662), also executed from its source
+        assert got["sparseSize"] == int(gold[name + "__sparseSize"])
+        assert np.array_equal(got["iPair"], gold[name + "__iPair"])
     if name.startswith("crystal"):
         d = gold[name + "__neighDist2"][:, 1:]
         assert np.any((np.abs(np.diff(d, axis=1)) < 1e-10) & (d[:, 1:] > 0))      # shells of equal distance are present
