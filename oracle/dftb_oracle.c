@@ -20,8 +20,8 @@
  *   - chunk ranges, the bisection search_asc_real_geq, the neighbour list's proximity rule and the Broyden mixer: the
  *     known answers of the reference's own unit tests (unit/common/schedule.F90, unit/math/binarysearch.F90,
  *     unit/dftb/periodic.F90, unit/mixer/broyden.F90).
- * Still restated only: the eigensolve (SciPy), the Ewald sums (pinned to Madelung constants), Efilling,
- * getSparseDescriptor / getNrOfNeighbours (a prefix sum and the unit-tested bisection).
+ * (scc_model.py's Efilling: the same, oracle/gen_ref_filling.py.)  Still restated only: the eigensolve (SciPy) and the
+ * Ewald sums (pinned to Madelung constants).
  *
  * Every routine cites the reference file:line (relative to /root/reference/src/dftbp/)
  * whose arithmetic and loop order it follows.  Arrays use the reference's layout:

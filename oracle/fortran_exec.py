@@ -129,19 +129,27 @@ def f_real(x, kind=None):
     return np.real(x) if np.ndim(x) else float(np.real(x))
 
 
+def _exp(x):
+    """exp with IEEE overflow to +Inf (no trap), like the compiled reference"""
+    with np.errstate(over="ignore"):
+        v = np.exp(x)
+    return v if np.ndim(v) else (complex(v) if isinstance(x, complex) else float(v))
+
+
 ENV = dict(np=np, math=math, FArr=FArr, f_reshape=f_reshape, f_sum=f_sum, f_size=f_size, f_matmul=f_matmul, f_dot=f_dot,
-           dp=None, f_cmplx=f_cmplx, f_real=f_real, f_exp=lambda x: np.exp(x) if np.ndim(x) else (complex(np.exp(x)) if isinstance(x, complex) else math.exp(x)),
+           dp=None, f_cmplx=f_cmplx, f_real=f_real, f_exp=lambda x: _exp(x),
            f_conjg=np.conj, f_transpose=np.transpose, pi=3.14159265358979323846264338327950288, imag=1j)
 
 INTRINSICS = {"reshape": "f_reshape", "sum": "f_sum", "size": "f_size", "matmul": "f_matmul", "dot_product": "f_dot",
-              "cmplx": "f_cmplx", "real": "f_real", "exp": "f_exp", "cos": "math.cos", "sin": "math.sin", "sqrt": "math.sqrt",
+              "cmplx": "f_cmplx", "real": "f_real", "exp": "f_exp", "cos": "math.cos", "sin": "math.sin", "sqrt": "math.sqrt", "log": "math.log",
               "abs": "abs", "minval": "np.min", "maxval": "np.max", "epsilon": "f_epsilon", "sign": "math.copysign", "present": "f_present", "ubound": "f_ubound", "nint": "f_nint", "conjg": "f_conjg", "transpose": "f_transpose", "max": "max", "min": "min", "mod": "f_mod"}
 ENV["f_epsilon"] = lambda x: 2.220446049250313e-16
 ENV["f_present"] = lambda x: x is not None
 ENV["f_ubound"] = lambda x, dim: x.lb[int(dim) - 1] + x.a.shape[int(dim) - 1] - 1
 ENV["f_nint"] = lambda x: int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
 ENV["LoopExit"], ENV["LoopCycle"] = LoopExit, LoopCycle
-ENV["f_mod"] = lambda a, b: int(math.fmod(a, b)) if isinstance(a, int) and isinstance(b, int) else math.fmod(a, b)
+# integer mod: a first operand that came out of an integer division arrives as a float here -- truncate it like Fortran
+ENV["f_mod"] = lambda a, b: int(a) % int(b) if isinstance(b, (int, np.integer)) else math.fmod(a, b)
 
 
 def _logical_lines(text):
@@ -240,6 +248,7 @@ def _expr(s, arrays):
                  (r"\.and\.", " and "), (r"\.or\.", " or "), (r"\.not\.", " not "), (r"\.true\.", "True"), (r"\.false\.", "False")):
         s = re.sub(a, b, s, flags=re.I)
     s = s.replace("/=", "!=").replace("(/", "[").replace("/)", "]")
+    s = re.sub(r"epsilon\(1\.0_rsp\)", "1.1920928955078125e-07", s)
     s = re.sub(r"(\d+\.\d*(?:[eE][-+]?\d+)?|\d+)_dp", r"\1", s)
     s = re.sub(r"\bdim\s*=\s*", "", s)
     out, i = "", 0
@@ -288,6 +297,11 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
     arrays, local_alloc, body, lower, dtypes, int_scalars = set(extra_arrays), [], [], {}, {}, set()
     for ln in lines:
         d = re.match(r"(real\(dp\)|integer|complex\(dp\)|logical|type\(\w+\)|class\(\w+\)|character\([^)]*\))\s*(,[^:]*)?::\s*(.*)$", ln, re.I)
+        d0 = re.match(r"(integer|logical)\s+(\w+(?:\s*,\s*\w+)*)$", ln, re.I)
+        if d0 and not d:        # old-style declaration without '::' (scalars)
+            if d0.group(1).lower() == "integer":
+                int_scalars.update(x.strip() for x in d0.group(2).split(","))
+            continue
         if d:
             typ, attrs, rest = d.group(1).lower(), (d.group(2) or "").lower(), d.group(3)
             # split declared entities at top-level commas
@@ -470,6 +484,14 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
                 if not call_map or cm_.group(1) not in call_map:
                     raise ValueError("unmapped call: " + s)
                 py.append("%sif %s: %s" % (ind, _expr(cond, arrays), call_map[cm_.group(1)].format(args=cargs)))
+                continue
+            xm = re.match(r"(exit|cycle)(\s+\w+)?$", stmt, re.I)
+            if xm:
+                if xm.group(2):
+                    act = "raise %s(%r)" % ("LoopExit" if xm.group(1).lower() == "exit" else "LoopCycle", xm.group(2).strip())
+                else:
+                    act = "break" if xm.group(1).lower() == "exit" else "continue"
+                py.append("%sif %s: %s" % (ind, _expr(cond, arrays), act))
                 continue
             am = re.match(r"([^=]+?)=(?!=)(.*)$", stmt)
             py.append("%sif %s: %s = %s" % (ind, _expr(cond, arrays), _expr(am.group(1), arrays), _expr(am.group(2), arrays)))

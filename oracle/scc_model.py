@@ -200,7 +200,7 @@ def efilling(eigenvals, n_electrons, kT, k_weight):
     def done(ef, scale=None):
         eb, fill, ts, e0 = electron_fill(ef, eigenvals, kT, k_weight)
         if scale is not None:
-            fill = fill * scale
+            fill = fill * scale[0] / scale[1]        # filling(:,:,:) = filling * nElectrons / nElec (left to right)
         return dict(Ebs=eb, Ef=ef, TS=ts, E0=e0, filling=fill)
 
     if n_electrons < EPS:
@@ -238,7 +238,7 @@ def efilling(eigenvals, n_electrons, kT, k_weight):
         raise RuntimeError("Fermi level search did not converge.")
     scale = None
     if n_electrons > epsilon2 and abs(n_electrons - n_elec) > epsilon2:
-        scale = n_electrons / n_elec     # "Re-scale to give exact number of electrons"
+        scale = (n_electrons, n_elec)    # "Re-scale to give exact number of electrons"
     return done(ef, scale)
 
 
