@@ -125,7 +125,7 @@ def cases():
     c0 = (cc[:, None, :] + basis[None, :, :]).reshape(-1, 3) * a
     rcell = oracle.cell_translations(np.diag([2 * a, 2 * a, 2 * a]), 9.5)[1]
     out["crystal"] = (c0, rcell, 9.5, False)
-    out["crystal_symmetric"] = (c0, rcell, 7.0, True)
+    out["crystal_symmetric"] = (c0, oracle.cell_translations(np.diag([2 * a, 2 * a, 2 * a]), 7.0)[1], 7.0, True)
     w, sk, geo, model, selfegy = case("fec128")
     c1 = np.array(w["coord0"], dtype=np.float64)
     c1[77] = c1[12] + [0.003, 0.0, -0.002]
