@@ -13,7 +13,8 @@
  *     index semantics and RUN (oracle/fortran_exec.py, oracle/gen_ref_sparse.py); its outputs are the golden vectors
  *     tests/golden/sparse_ref_golden.npz, which this file reproduces (H0 / S to 5e-17, forces to 2e-12, the rest to
  *     rounding; tests/test_oracle_sparse_ref.py); updateNeighbourList the same way (oracle/gen_ref_neigh.py,
- *     tests/test_oracle_neigh_ref.py): every array bit for bit, ties and the "too close" pair included;
+ *     tests/test_oracle_neigh_ref.py): every array bit for bit, ties and the "too close" pair included; the SK-table
+ *     interpolation SlakoEqGrid_interNew_ / _interOld_ (oracle/gen_ref_interp.py): bit for bit in every branch;
  *   - the shell-pair rotations ss ... ff, the interpolation routines, the tolerance heap sort and the scalar
  *     SCC-potential functions: machine translations to C (oracle/gen_ref_sk.py, gen_ref_math.py, gen_ref_scc.py ->
  *     oracle/_ref/, golden vectors under tests/golden/), bit for bit where the operation order is the reference's;

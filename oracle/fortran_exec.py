@@ -73,6 +73,20 @@ class FArr:
             self.a[ix] = value
 
 
+def _assign_whole(self, value):
+    """whole-array assignment a = expr: element-wise into the existing storage (scalars broadcast); an array of another
+    shape replaces the storage (allocatable left-hand sides are reallocated by Fortran 2003 semantics)"""
+    value = value.a if isinstance(value, FArr) else value
+    if np.ndim(value) == 0 or np.shape(value) == self.a.shape:
+        self.a[...] = value
+    else:
+        self.a = np.array(value, order="F")
+        self.lb = (1,) * self.a.ndim
+
+
+FArr.assign = _assign_whole
+
+
 def _whole(op):
     return lambda self, other: op(self.a, other.a if isinstance(other, FArr) else other)
 
@@ -141,10 +155,11 @@ ENV = dict(np=np, math=math, FArr=FArr, f_reshape=f_reshape, f_sum=f_sum, f_size
            f_conjg=np.conj, f_transpose=np.transpose, pi=3.14159265358979323846264338327950288, imag=1j)
 
 INTRINSICS = {"reshape": "f_reshape", "sum": "f_sum", "size": "f_size", "matmul": "f_matmul", "dot_product": "f_dot",
-              "cmplx": "f_cmplx", "real": "f_real", "exp": "f_exp", "cos": "math.cos", "sin": "math.sin", "sqrt": "math.sqrt", "log": "math.log",
+              "cmplx": "f_cmplx", "real": "f_real", "exp": "f_exp", "cos": "math.cos", "sin": "math.sin", "sqrt": "math.sqrt", "log": "math.log", "floor": "f_floor",
               "abs": "abs", "minval": "np.min", "maxval": "np.max", "epsilon": "f_epsilon", "sign": "math.copysign", "present": "f_present", "ubound": "f_ubound", "nint": "f_nint", "conjg": "f_conjg", "transpose": "f_transpose", "max": "max", "min": "min", "mod": "f_mod"}
 ENV["f_epsilon"] = lambda x: 2.220446049250313e-16
 ENV["f_present"] = lambda x: x is not None
+ENV["f_floor"] = lambda x: int(math.floor(x))
 ENV["f_ubound"] = lambda x, dim: x.lb[int(dim) - 1] + x.a.shape[int(dim) - 1] - 1
 ENV["f_nint"] = lambda x: int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
 ENV["LoopExit"], ENV["LoopCycle"] = LoopExit, LoopCycle
@@ -154,8 +169,24 @@ ENV["f_mod"] = lambda a, b: int(a) % int(b) if isinstance(b, (int, np.integer)) 
 
 def _logical_lines(text):
     out, cur, skip = [], "", []     # skip: stack of booleans (True = lines are dropped)
+    state = {"q": None}     # quote character still open (a string literal continued over lines)
+
+    def strip_comment(raw):
+        q = state["q"]
+        for i, ch in enumerate(raw):
+            if q:
+                if ch == q:
+                    q = None
+            elif ch in "\"'":
+                q = ch
+            elif ch == "!":
+                state["q"] = None
+                return raw[:i]
+        state["q"] = q
+        return raw
+
     for raw in text.splitlines():
-        line = raw.split("!")[0].rstrip()
+        line = strip_comment(raw).rstrip()
         st = line.strip()
         if st.startswith("#:if") or st.startswith("#:block"):
             skip.append(True)        # every build option (WITH_MPI, EXP_TRAP, DEBUG_CODE ...) is off
@@ -294,7 +325,7 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
     for tok in args + re.findall(r"[A-Za-z_]\w*", "\n".join(lines)):
         canon.setdefault(tok.lower(), tok)
     lines = [re.sub(r"[A-Za-z_]\w*", lambda t: canon[t.group(0).lower()], ln) for ln in lines]
-    arrays, local_alloc, body, lower, dtypes, int_scalars = set(extra_arrays), [], [], {}, {}, set()
+    arrays, local_alloc, body, lower, dtypes, int_scalars, declared_arrays = set(extra_arrays), [], [], {}, {}, set(), set()
     for ln in lines:
         d = re.match(r"(real\(dp\)|integer|complex\(dp\)|logical|type\(\w+\)|class\(\w+\)|character\([^)]*\))\s*(,[^:]*)?::\s*(.*)$", ln, re.I)
         d0 = re.match(r"(integer|logical)\s+(\w+(?:\s*,\s*\w+)*)$", ln, re.I)
@@ -318,12 +349,18 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
                     cur += ch
             ents.append(cur.strip())
             for e in ents:
+                pm = re.match(r"(\w+)\s*=\s*(.*)$", e)
+                if pm and "parameter" in attrs:        # named constant with its value
+                    local_alloc.append("%s = %s" % (pm.group(1), _expr(pm.group(2), arrays)))
+                    continue
                 em = re.match(r"(\w+)\s*\((.*)\)$", e)
                 if not em:
                     if typ == "integer" and re.match(r"\w+$", e):
                         int_scalars.add(e)
                     continue
                 arrays.add(em.group(1))
+                if "allocatable" not in attrs or "intent" in attrs:
+                    declared_arrays.add(em.group(1))
                 dtypes[em.group(1)] = "complex" if typ.startswith("complex") else ("int" if typ == "integer" else "float")
                 lower[em.group(1)] = [int(x.split(":")[0]) if ":" in x and x.split(":")[0].strip() else 1
                                       for x in _split_top(em.group(2))] if "intent" in attrs else None
@@ -501,6 +538,9 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
             rhs = _expr(mm.group(2), arrays)
             if mm.group(1).strip() in int_scalars and "/" in rhs:
                 rhs = "int(%s)" % rhs     # integer division / real -> integer conversion: truncation (non-negative operands)
+            if mm.group(1).strip() in declared_arrays:
+                py.append("%s%s.assign(%s)" % (ind, mm.group(1).strip(), rhs))       # whole-array assignment
+                continue
             py.append("%s%s = %s" % (ind, _expr(mm.group(1), arrays), rhs))
             continue
         raise ValueError("cannot translate: " + s)
