@@ -156,9 +156,12 @@ ENV = dict(np=np, math=math, FArr=FArr, f_reshape=f_reshape, f_sum=f_sum, f_size
 
 INTRINSICS = {"reshape": "f_reshape", "sum": "f_sum", "size": "f_size", "matmul": "f_matmul", "dot_product": "f_dot",
               "cmplx": "f_cmplx", "real": "f_real", "exp": "f_exp", "cos": "math.cos", "sin": "math.sin", "sqrt": "math.sqrt", "log": "math.log", "floor": "f_floor",
-              "abs": "abs", "minval": "np.min", "maxval": "np.max", "epsilon": "f_epsilon", "sign": "math.copysign", "present": "f_present", "ubound": "f_ubound", "nint": "f_nint", "conjg": "f_conjg", "transpose": "f_transpose", "max": "max", "min": "min", "mod": "f_mod"}
+              "abs": "abs", "minval": "np.min", "maxval": "np.max", "epsilon": "f_epsilon", "sign": "math.copysign", "present": "f_present", "all": "f_all", "any": "f_any", "ubound": "f_ubound", "nint": "f_nint", "conjg": "f_conjg", "transpose": "f_transpose", "max": "max", "min": "min", "mod": "f_mod"}
 ENV["f_epsilon"] = lambda x: 2.220446049250313e-16
 ENV["f_present"] = lambda x: x is not None
+ENV["f_not"] = lambda x: np.logical_not(x.a if isinstance(x, FArr) else x) if isinstance(x, (FArr, np.ndarray)) else (not x)
+ENV["f_all"] = lambda x: bool(np.all(x.a if isinstance(x, FArr) else x))
+ENV["f_any"] = lambda x: bool(np.any(x.a if isinstance(x, FArr) else x))
 ENV["f_floor"] = lambda x: int(math.floor(x))
 ENV["f_ubound"] = lambda x, dim: x.lb[int(dim) - 1] + x.a.shape[int(dim) - 1] - 1
 ENV["f_nint"] = lambda x: int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
@@ -275,9 +278,13 @@ def _fix_eqv(s):
 
 def _expr(s, arrays):
     s = _fix_eqv(s.strip())
+    s = re.sub(r"\.not\.\s*(\w+\([^()]*\))", r"f_not(\1)", s, flags=re.I)
+    s = re.sub(r"\.not\.\s*(\w+)(?!\s*[\w(])", r"f_not(\1)", s, flags=re.I)
     for a, b in ((r"\.gt\.", ">"), (r"\.lt\.", "<"), (r"\.ge\.", ">="), (r"\.le\.", "<="), (r"\.eq\.", "=="), (r"\.ne\.", "!="),
                  (r"\.and\.", " and "), (r"\.or\.", " or "), (r"\.not\.", " not "), (r"\.true\.", "True"), (r"\.false\.", "False")):
         s = re.sub(a, b, s, flags=re.I)
+    s = re.sub(r"\.not\.\s*(\w+\([^()]*\))", r"f_not(\1)", s, flags=re.I)
+    s = re.sub(r"\.not\.\s*(\w+)(?!\s*\()", r"f_not(\1)", s, flags=re.I)
     s = s.replace("/=", "!=").replace("(/", "[").replace("/)", "]")
     s = re.sub(r"epsilon\(1\.0_rsp\)", "1.1920928955078125e-07", s)
     s = re.sub(r"(\d+\.\d*(?:[eE][-+]?\d+)?|\d+)_dp", r"\1", s)
@@ -365,12 +372,20 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
                 lower[em.group(1)] = [int(x.split(":")[0]) if ":" in x and x.split(":")[0].strip() else 1
                                       for x in _split_top(em.group(2))] if "intent" in attrs else None
                 if "intent" not in attrs and "allocatable" not in attrs and "pointer" not in attrs:
-                    dims = [_expr(x, arrays) for x in _split_top(em.group(2))]
-                    dt = "complex" if typ.startswith("complex") else ("int" if typ == "integer" else "float")
-                    local_alloc.append("%s = FArr(np.zeros((%s,), dtype=%s, order='F'))" % (em.group(1), ", ".join(dims), dt))
+                    shp, los = [], []
+                    for x in _split_top(em.group(2)):
+                        if ":" in x:
+                            lo_, hi_ = x.split(":")
+                            los.append(_expr(lo_, arrays))
+                            shp.append("(%s) - (%s) + 1" % (_expr(hi_, arrays), _expr(lo_, arrays)))
+                        else:
+                            los.append("1")
+                            shp.append(_expr(x, arrays))
+                    dt = "complex" if typ.startswith("complex") else ("int" if typ == "integer" else ("bool" if typ == "logical" else "float"))
+                    local_alloc.append("%s = FArr(np.zeros((%s,), dtype=%s, order='F'), (%s,))" % (em.group(1), ", ".join(shp), dt, ", ".join(los)))
             continue
         body.append(ln)
-    py, ind, selects, loops = ["def %s(%s):" % (name, ", ".join(args))], "    ", [], []
+    py, ind, selects, loops, wheres = ["def %s(%s):" % (name, ", ".join(args))], "    ", [], [], []
     for a_ in args:
         if lower.get(a_) is not None:
             py.append("%s%s = %s if isinstance(%s, FArr) or not isinstance(%s, np.ndarray) else FArr(%s, %r)" % (ind, a_, a_, a_, a_, a_, tuple(lower[a_])))
@@ -411,6 +426,18 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
         if re.match(r"end\s*if$", low):
             py.append(ind + "pass")
             ind = ind[:-4]
+            continue
+        mm = re.match(r"where\s*\((.*)\)$", s, re.I)
+        if mm:
+            wheres.append(_expr(mm.group(1), arrays))
+            continue
+        if re.match(r"end\s*where$", low):
+            wheres.pop()
+            continue
+        if wheres:
+            am = re.match(r"([^=]+?)=(?!=)(.*)$", s)
+            lhs_, rhs_ = _expr(am.group(1), arrays), _expr(am.group(2), arrays)
+            py.append("%snp.copyto(%s, %s, where=%s)" % (ind, lhs_, rhs_, wheres[-1]))      # masked assignment
             continue
         mm = re.match(r"select\s+case\s*\((.*)\)$", s, re.I)
         if mm:

@@ -103,6 +103,13 @@ def routines():
     calls["derivator%getFirstDeriv"] = lambda a: "getFirstDerivFiniteDiff(%s, derivator)" % ", ".join(a)
     for name in ("derivativeNonSccEuclidian", "derivative_blockEuclidean"):
         r[name] = fx.compile_routine(frc, "subroutine", name, calls, extra_env=env, extra_arrays=orb_arrays)[0]
+    # the Richardson derivator with the non-SCC force contraction
+    rich = fx.compile_routine(non, "subroutine", "getFirstDerivRichardson", calls, extra_env=env, extra_arrays=orb_arrays)[0]
+    env["getFirstDerivRichardson"] = rich
+    calls_r = dict(calls)
+    calls_r["derivator%getFirstDeriv"] = lambda a: "getFirstDerivRichardson(%s)" % ", ".join(a)
+    r["derivativeNonSccEuclidian_richardson"] = fx.compile_routine(frc, "subroutine", "derivativeNonSccEuclidian", calls_r,
+                                                                   extra_env=env, extra_arrays=orb_arrays)[0]
     strs = open(REF + "stress.F90").read()
     for name in ("getNonSCCStress", "getBlockStress"):
         r[name] = fx.compile_routine(strs, "subroutine", name, calls, extra_env=env, extra_arrays=orb_arrays)[0]
@@ -235,6 +242,12 @@ def run_case(R, d):
     f(None, W(f, "deriv", der), delta, W(f, "DM", d["rho"]), W(f, "EDM", d["over"]), contH, contS, W(f, "coords", coords),
       W(f, "species", species), W(f, "iNeighbour", iN), W(f, "nNeighbourSK", nN), W(f, "img2CentCell", img), W(f, "iPair", iP), orb)
     out["deriv_nonscc"] = der
+    if geo["nAtom"] <= 8:          # the Richardson tables are slow in the interpreter: the small cases only
+        f = R["derivativeNonSccEuclidian_richardson"]
+        der = np.full((3, nA), 7.0, order="F")
+        f(None, W(f, "deriv", der), None, W(f, "DM", d["rho"]), W(f, "EDM", d["over"]), contH, contS, W(f, "coords", coords),
+          W(f, "species", species), W(f, "iNeighbour", iN), W(f, "nNeighbourSK", nN), W(f, "img2CentCell", img), W(f, "iPair", iP), orb)
+        out["deriv_nonscc_richardson"] = der
     f = R["derivative_blockEuclidean"]
     der = np.full((3, nA), 7.0, order="F")
     shb = F(np.transpose(d["shift_block"], (3, 2, 1, 0)).copy())

@@ -64,6 +64,10 @@ def test_oracle_equals_the_executed_reference_source(name, gold):
     dm2 = np.stack([d["rho"], 0.3 * d["over"]])
     g2 = oracle.derivative_shift(model, geo, dm2, d["orig"], shift=d["shift_block"])
     _cmp(gold, name, "deriv_block", np.asfortranarray(g2.T), 1e-11)
+    if geo["nAtom"] <= 8:
+        # getFirstDerivRichardson (dftb/nonscc.F90:488-600): element-wise extrapolation tables, masked updates, frozen elements
+        g3 = oracle.derivative_shift(model, geo, d["rho"], d["over"], diff_type=2)
+        _cmp(gold, name, "deriv_nonscc_richardson", np.asfortranarray(g3.T), 1e-11)
     # stress: getNonSCCStress / getBlockStress (dftb/stress.F90); the oracle returns st[ii, jj] = reference st(jj, ii)
     s1 = oracle.stress(model, geo, d["rho"], d["over"], 1000.0)
     _cmp(gold, name, "stress_nonscc", np.asfortranarray(s1.T), 1e-11)

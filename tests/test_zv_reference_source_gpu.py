@@ -59,6 +59,9 @@ def test_kernels_equal_the_executed_reference_source(name):
         cmp("deriv_nonscc", np.asfortranarray(g1.T), 1e-9)
         g2 = hp.derivative_shift(np.stack([d["rho"], 0.3 * d["over"]]), d["orig"], shift=d["shift_block"])
         cmp("deriv_block", np.asfortranarray(g2.T), 1e-9)
+        if geo["nAtom"] <= 8:
+            g3 = hp.derivative_shift(d["rho"], d["over"], diff_type=2)           # Richardson derivator
+            cmp("deriv_nonscc_richardson", np.asfortranarray(g3.T), 1e-8)
         st = hp.stress(np.stack([d["rho"], 0.3 * d["over"]]), d["orig"], 1000.0, shift=d["shift_block"])
         cmp("stress_block", np.asfortranarray(np.asarray(st).T), 1e-9)
         if name not in GS.SAMPLED:
