@@ -13,6 +13,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import gen_ref_sparse as GS  # noqa: E402
 import gen_ref_neigh as GN  # noqa: E402
 import gen_ref_filling as GF  # noqa: E402
+import gen_ref_gamma as GG  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -113,5 +114,35 @@ def test_device_efilling_equals_the_executed_reference_source():
             assert abs(r["Ef"] - float(gold[name + "__Ef"])) <= 1e-12, name
             assert np.abs(fill - gold[name + "__filling"]).max() <= 1e-12, name
             assert np.abs(r["Ebs"] - gold[name + "__Ebs"]).max() <= 1e-12 * max(1.0, np.abs(gold[name + "__Ebs"]).max()), name
+    finally:
+        hp.close()
+
+
+@pytest.mark.parametrize("name", ["h2o", "ce_o", "fec128", "fec128r"])
+def test_device_short_gamma_equals_the_executed_reference_source(name):
+    """dftbp_b200_short_gamma_update / _shifts on the device neighbour list against updateNrOfNeighbours_ /
+    updateShortGammaValues_ / buildShifts_ executed from the reference's source."""
+    from dftbplus_b200.api import HotPath
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "gamma_ref_golden.npz"))
+    nl, hub, cuts, n_shell, dq = GG.cases()[name]
+    w, sk, geo, model, selfegy = case(name.rstrip("r"))
+    cutoff = max(sk.cutoff(), float(cuts.max()))
+    hp = HotPath(0)
+    try:
+        sk.upload(hp)
+        g = hp.updateNeighbourListAndSpecies(w["coord0"], w["species0"], cutoff, w["latvec"], sk_cutoff=sk.cutoff(), adopt=False)
+        assert np.array_equal(g["iNeighbour"], nl["iNeighbour"])
+        got = hp.shortGammaUpdate(hub["nHubbU"], hub["uniqHubbU"], cuts, fetch=True)
+        assert np.array_equal(got["nNeighU"], gold[name + "__nNeighU"])
+        gam = got["shortGamma"]
+        if name + "__shortGamma_shape" in gold:
+            shape = tuple(int(x) for x in gold[name + "__shortGamma_shape"])
+            dev = GG.sample(np.ascontiguousarray(gam[:, :shape[1]]))
+        else:
+            dev = gam[:, :gold[name + "__shortGamma"].shape[1]]
+        ref = gold[name + "__shortGamma"]
+        assert np.abs(dev - ref).max() <= 1e-13 * np.abs(ref).max()
+        sh = hp.shortGammaShifts(hub["iHubbU"], dq)
+        _close(sh, gold[name + "__shiftShell"], 1e-12, name + " shiftShell")
     finally:
         hp.close()
