@@ -21,8 +21,9 @@
  *   - chunk ranges, the bisection search_asc_real_geq, the neighbour list's proximity rule and the Broyden mixer: the
  *     known answers of the reference's own unit tests (unit/common/schedule.F90, unit/math/binarysearch.F90,
  *     unit/dftb/periodic.F90, unit/mixer/broyden.F90).
- * (scc_model.py's Efilling: the same, oracle/gen_ref_filling.py.)  Still restated only: the eigensolve (SciPy) and the
- * Ewald sums (pinned to Madelung constants).
+ * (scc_model.py's Efilling: the same, oracle/gen_ref_filling.py; the Ewald / cluster 1/R matrix with the dynamic neighbour
+ * list iterator: oracle/gen_ref_ewald.py; the short-range gamma: oracle/gen_ref_gamma.py.)  Still restated only: the
+ * eigensolve (SciPy).
  *
  * Every routine cites the reference file:line (relative to /root/reference/src/dftbp/)
  * whose arithmetic and loop order it follows.  Arrays use the reference's layout:

@@ -99,6 +99,9 @@ for _n, _f in (("__rmul__", np.multiply), ("__radd__", np.add)):
 FArr.__rsub__ = lambda self, other: np.subtract(other, self.a)
 FArr.__neg__ = lambda self: -self.a
 FArr.__pow__ = lambda self, n: self.a ** n
+FArr.__eq__ = lambda self, other: self.a == (other.a if isinstance(other, FArr) else other)
+FArr.__ne__ = lambda self, other: self.a != (other.a if isinstance(other, FArr) else other)
+FArr.__hash__ = lambda self: id(self)
 FArr.__array__ = lambda self, dtype=None, copy=None: self.a if dtype is None else self.a.astype(dtype)
 
 
@@ -111,7 +114,11 @@ def f_reshape(x, shape):
 def f_sum(x, dim=None):
     x = x.a if isinstance(x, FArr) else np.asarray(x)
     if dim is None:
-        return float(np.sum(x)) if not np.iscomplexobj(x) else complex(np.sum(x))
+        # the intrinsic is a serial loop in array-element (column-major) order
+        acc = 0.0 if not np.iscomplexobj(x) else 0j
+        for v in np.ravel(x, order="F").tolist():
+            acc = acc + v
+        return acc
     return np.sum(x, axis=int(dim) - 1)
 
 
@@ -156,9 +163,12 @@ ENV = dict(np=np, math=math, FArr=FArr, f_reshape=f_reshape, f_sum=f_sum, f_size
 
 INTRINSICS = {"reshape": "f_reshape", "sum": "f_sum", "size": "f_size", "matmul": "f_matmul", "dot_product": "f_dot",
               "cmplx": "f_cmplx", "real": "f_real", "exp": "f_exp", "cos": "math.cos", "sin": "math.sin", "sqrt": "math.sqrt", "log": "math.log", "floor": "f_floor",
-              "abs": "abs", "minval": "np.min", "maxval": "np.max", "epsilon": "f_epsilon", "sign": "math.copysign", "present": "f_present", "all": "f_all", "any": "f_any", "ubound": "f_ubound", "nint": "f_nint", "conjg": "f_conjg", "transpose": "f_transpose", "max": "max", "min": "min", "mod": "f_mod"}
+              "abs": "abs", "minval": "f_minval", "maxval": "f_maxval", "norm2": "f_norm2", "epsilon": "f_epsilon", "sign": "math.copysign", "present": "f_present", "all": "f_all", "any": "f_any", "ubound": "f_ubound", "nint": "f_nint", "conjg": "f_conjg", "transpose": "f_transpose", "max": "max", "min": "min", "mod": "f_mod"}
 ENV["f_epsilon"] = lambda x: 2.220446049250313e-16
 ENV["f_present"] = lambda x: x is not None
+ENV["f_minval"] = lambda x, dim=None: (np.min(x.a if isinstance(x, FArr) else x) if dim is None else np.min(x.a if isinstance(x, FArr) else x, axis=int(dim) - 1))
+ENV["f_maxval"] = lambda x, dim=None: (np.max(x.a if isinstance(x, FArr) else x) if dim is None else np.max(x.a if isinstance(x, FArr) else x, axis=int(dim) - 1))
+ENV["f_norm2"] = lambda x: math.sqrt(f_sum(np.asarray(x.a if isinstance(x, FArr) else x) ** 2))
 ENV["f_not"] = lambda x: np.logical_not(x.a if isinstance(x, FArr) else x) if isinstance(x, (FArr, np.ndarray)) else (not x)
 ENV["f_all"] = lambda x: bool(np.all(x.a if isinstance(x, FArr) else x))
 ENV["f_any"] = lambda x: bool(np.any(x.a if isinstance(x, FArr) else x))
@@ -322,7 +332,7 @@ def _expr(s, arrays):
 def transpile(src, kind, name, call_map=None, extra_arrays=()):
     """-> (python source of def <name>(args), argument list).  call_map: 'callee' -> python statement template using
     {args} (list of translated arguments); unknown calls raise."""
-    m = re.search(r"\b%s\s+%s\s*\((.*?)\)\s*\n(.*?)\bend\s+%s\s+%s\b" % (kind, name, kind, name), src, re.S | re.I)
+    m = re.search(r"\b%s\s+%s\s*\(([^)]*)\)[^\n]*\n(.*?)\bend\s+%s\s+%s\b" % (kind, name, kind, name), src, re.S | re.I)
     if not m:
         raise RuntimeError("routine %s not found" % name)
     args = [a.strip() for a in m.group(1).replace("&", " ").replace("\n", " ").split(",")]
@@ -385,7 +395,7 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
                     local_alloc.append("%s = FArr(np.zeros((%s,), dtype=%s, order='F'), (%s,))" % (em.group(1), ", ".join(shp), dt, ", ".join(los)))
             continue
         body.append(ln)
-    py, ind, selects, loops, wheres = ["def %s(%s):" % (name, ", ".join(args))], "    ", [], [], []
+    py, ind, selects, loops, wheres = ["def %s(%s):" % (name, ", ".join(a_ + "=None" for a_ in args))], "    ", [], [], []
     for a_ in args:
         if lower.get(a_) is not None:
             py.append("%s%s = %s if isinstance(%s, FArr) or not isinstance(%s, np.ndarray) else FArr(%s, %r)" % (ind, a_, a_, a_, a_, a_, tuple(lower[a_])))
@@ -461,9 +471,14 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
                 py.append(ind + "pass")
                 ind = ind[:-4]
             continue
-        mm = re.match(r"(\w+)\s*=>\s*(.*)$", s)
-        if mm:   # pointer assignment: a view
-            py.append("%s%s = %s" % (ind, mm.group(1), _expr(mm.group(2), arrays)))
+        mm = re.match(r"([\w%]+)\s*=>\s*(.*)$", s)
+        if mm:   # pointer assignment: a view / the same object
+            py.append("%s%s = %s" % (ind, mm.group(1).replace("%", "."), _expr(mm.group(2), arrays)))
+            continue
+        if low == "do":
+            loops.append(None)
+            py.append(ind + "while True:")
+            ind += "    "
             continue
         mm = re.match(r"do\s+while\s*\((.*)\)$", s, re.I)
         if mm:
@@ -519,6 +534,11 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
             tmpl = call_map[callee]
             py.append(ind + (tmpl(cargs) if callable(tmpl) else tmpl.format(args=cargs)))
             continue
+        mm = re.match(r"allocate\s*\(\s*([\w%]+)\s*\)$", s, re.I)
+        if mm:       # a derived-type scalar
+            py.append("%s%s = new_object(%r)" % (ind, mm.group(1).replace("%", "."), mm.group(1).split("%")[-1]))
+            continue
+        s = re.sub(r",\s*source\s*=\s*[^()]*\)$", ")", s)        # allocate(a(n), source=0.0_dp): arrays are zeroed anyway
         mm = re.match(r"allocate\s*\(\s*(\w+)\s*\((.*)\)\s*\)$", s, re.I)
         if mm:
             arrays.add(mm.group(1))

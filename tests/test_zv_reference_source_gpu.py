@@ -14,6 +14,7 @@ import gen_ref_sparse as GS  # noqa: E402
 import gen_ref_neigh as GN  # noqa: E402
 import gen_ref_filling as GF  # noqa: E402
 import gen_ref_gamma as GG  # noqa: E402
+import gen_ref_ewald as GE  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -144,5 +145,23 @@ def test_device_short_gamma_equals_the_executed_reference_source(name):
         assert np.abs(dev - ref).max() <= 1e-13 * np.abs(ref).max()
         sh = hp.shortGammaShifts(hub["iHubbU"], dq)
         _close(sh, gold[name + "__shiftShell"], 1e-12, name + " shiftShell")
+    finally:
+        hp.close()
+
+
+@pytest.mark.parametrize("name", ["nacl", "skew", "fec16"])
+def test_device_ewald_matrix_equals_the_executed_reference_source(name):
+    """dftbp_b200_invr_periodic / _invr_cluster against invRPeriodicSerial / invRClusterSerial executed from the reference's
+    source (with its dynamic neighbour list iterator)."""
+    from dftbplus_b200.api import HotPath
+    from dftbplus_b200 import coulomb as pc
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "ewald_ref_golden.npz"))
+    c0, lat = GE.cases()[name]
+    ew = pc.ewald_setup(lat)
+    hp = HotPath(0)
+    try:
+        got = hp.invRPeriodic(np.ascontiguousarray(c0), ew["rLat"], ew["gLat"], ew["alpha"], ew["volume"], ew["maxR"])
+        _close(got, gold[name + "__invr"], 1e-13, name + " invR")
+        _close(hp.invRCluster(np.ascontiguousarray(c0)), gold[name + "__invr_cluster"], 1e-15, name + " invR cluster")
     finally:
         hp.close()
