@@ -8,7 +8,7 @@ TEST INFRASTRUCTURE ONLY.  Routines, read where they lie under /root/reference:
     buildH0, buildS, buildDiatomicBlocks, getFirstDerivFiniteDiff           dftb/nonscc.F90
     derivativeNonSccEuclidian, derivative_blockEuclidean                    dftb/forces.F90
     getNonSCCStress, getBlockStress                                         dftb/stress.F90
-    fullDensityMatrix_real, fullEnergyDensityMatrix_real                    dftb/densitymatrix.F90 (herk = the BLAS call
+    fullDensityMatrix_real / _cmplx, fullEnergyDensityMatrix_real / _cmplx  dftb/densitymatrix.F90 (herk = the BLAS call
                                                                             C := alpha A A^T + beta C, lower triangle)
     rotateH0                                                                dftb/sk.F90 (its ss ... ff callees are the
                                                                             machine translations of gen_ref_sk.py; the SK
@@ -116,11 +116,11 @@ def routines():
 
     def herk(c, a, alpha=1.0, beta=0.0):
         a = a.a if isinstance(a, fx.FArr) else a
-        c.a[:, :] = np.tril(alpha * (a @ a.T) + beta * c.a) + np.triu(c.a, 1)
+        c.a[:, :] = np.tril(alpha * (a @ a.conj().T) + beta * c.a) + np.triu(c.a, 1)
 
     dms = open(REF + "densitymatrix.F90").read()
     dcalls = {"herk": lambda a: "herk(%s)" % ", ".join(a)}
-    for name in ("fullDensityMatrix_real", "fullEnergyDensityMatrix_real"):
+    for name in ("fullDensityMatrix_real", "fullEnergyDensityMatrix_real", "fullDensityMatrix_cmplx", "fullEnergyDensityMatrix_cmplx"):
         r[name] = fx.compile_routine(dms, "subroutine", name, dcalls, extra_env=dict(herk=herk, arbitraryConstant=0.1))[0]
     return r
 
@@ -284,6 +284,15 @@ def run_case(R, d):
                 f(W(f, "dm", dm), W(f, "eigenvecs", cc), W(f, "filling", fill), W(f, "eigen", eig if tag == "mixed" else -np.abs(eig) - 0.1))
             out["%s_%s" % (key, tag)] = dm
             out["%s_%s_cback" % (key, tag)] = cc       # the eigenvectors are scaled and scaled back
+        for key, fname in (("dmc", "fullDensityMatrix_cmplx"), ("edmc", "fullEnergyDensityMatrix_cmplx")):
+            f = R[fname]
+            dmc = np.full((nd, nd), 7.0 + 1j, order="F", dtype=np.complex128)
+            ccz = F(C + 1j * C[::-1, ::-1])
+            if key == "dmc":
+                f(W(f, "dm", dmc), W(f, "eigenvecs", ccz), W(f, "filling", fill))
+            else:
+                f(W(f, "dm", dmc), W(f, "eigenvecs", ccz), W(f, "filling", fill), W(f, "eigen", eig if tag == "mixed" else -np.abs(eig) - 0.1))
+            out["%s_%s" % (key, tag)] = dmc
         out["dmin_%s_fill" % tag] = fill
     out["dmin_C"], out["dmin_eig"] = C, eig
     for zero in (True, False):

@@ -81,6 +81,9 @@ def test_oracle_equals_the_executed_reference_source(name, gold):
             _cmp(gold, name, "dm_" + tag, np.asfortranarray(oracle.density_matrix(C, fill)), 1e-14)
             e = eig if tag == "mixed" else -np.abs(eig) - 0.1
             _cmp(gold, name, "edm_" + tag, np.asfortranarray(oracle.energy_density_matrix(C, fill, e)), 1e-14)
+            Cz = C + 1j * C[::-1, ::-1]
+            _cmp(gold, name, "dmc_" + tag, np.asfortranarray(oracle.density_matrix(Cz, fill)), 1e-14)
+            _cmp(gold, name, "edmc_" + tag, np.asfortranarray(oracle.energy_density_matrix(Cz, fill, e)), 1e-14)
             # the reference scales the eigenvectors and scales them back: they return to rounding
             assert np.abs(gold["%s__dm_%s_cback" % (name, tag)] - C).max() <= 1e-14 * np.abs(C).max()
     for zero in (True, False):

@@ -73,6 +73,9 @@ def test_kernels_equal_the_executed_reference_source(name):
                 cmp("dm_" + tag, np.asfortranarray(hp.getDensityMatrix(np.asfortranarray(C), fill)), 1e-13)
                 e = eig if tag == "mixed" else -np.abs(eig) - 0.1
                 cmp("edm_" + tag, np.asfortranarray(hp.getEDensityMatrix(np.asfortranarray(C), fill, e)), 1e-13)
+                Cz = np.asfortranarray(C + 1j * C[::-1, ::-1])
+                cmp("dmc_" + tag, np.asfortranarray(hp.getDensityMatrix(Cz, fill)), 1e-13)
+                cmp("edmc_" + tag, np.asfortranarray(hp.getEDensityMatrix(Cz, fill, e)), 1e-13)
     finally:
         hp.close()
 
