@@ -163,11 +163,12 @@ ENV = dict(np=np, math=math, FArr=FArr, f_reshape=f_reshape, f_sum=f_sum, f_size
 
 INTRINSICS = {"reshape": "f_reshape", "sum": "f_sum", "size": "f_size", "matmul": "f_matmul", "dot_product": "f_dot",
               "cmplx": "f_cmplx", "real": "f_real", "exp": "f_exp", "cos": "math.cos", "sin": "math.sin", "sqrt": "math.sqrt", "log": "math.log", "floor": "f_floor",
-              "abs": "abs", "minval": "f_minval", "maxval": "f_maxval", "norm2": "f_norm2", "epsilon": "f_epsilon", "sign": "math.copysign", "present": "f_present", "all": "f_all", "any": "f_any", "ubound": "f_ubound", "nint": "f_nint", "conjg": "f_conjg", "transpose": "f_transpose", "max": "max", "min": "min", "mod": "f_mod"}
+              "abs": "abs", "minval": "f_minval", "maxval": "f_maxval", "minloc": "f_minloc", "norm2": "f_norm2", "epsilon": "f_epsilon", "sign": "math.copysign", "present": "f_present", "all": "f_all", "any": "f_any", "ubound": "f_ubound", "nint": "f_nint", "conjg": "f_conjg", "transpose": "f_transpose", "max": "max", "min": "min", "mod": "f_mod"}
 ENV["f_epsilon"] = lambda x: 2.220446049250313e-16
 ENV["f_present"] = lambda x: x is not None
 ENV["f_minval"] = lambda x, dim=None: (np.min(x.a if isinstance(x, FArr) else x) if dim is None else np.min(x.a if isinstance(x, FArr) else x, axis=int(dim) - 1))
 ENV["f_maxval"] = lambda x, dim=None: (np.max(x.a if isinstance(x, FArr) else x) if dim is None else np.max(x.a if isinstance(x, FArr) else x, axis=int(dim) - 1))
+ENV["f_minloc"] = lambda x, dim=None: int(np.argmin(x.a if isinstance(x, FArr) else x)) + (x.lb[0] if isinstance(x, FArr) else 1)
 ENV["f_norm2"] = lambda x: math.sqrt(f_sum(np.asarray(x.a if isinstance(x, FArr) else x) ** 2))
 ENV["f_not"] = lambda x: np.logical_not(x.a if isinstance(x, FArr) else x) if isinstance(x, (FArr, np.ndarray)) else (not x)
 ENV["f_all"] = lambda x: bool(np.all(x.a if isinstance(x, FArr) else x))
