@@ -60,7 +60,7 @@ class FArr:
 
     def __getitem__(self, idx):
         v = self.a[self._index(idx)]
-        return v.item() if np.ndim(v) == 0 else v
+        return (v.item() if hasattr(v, "item") else v) if np.ndim(v) == 0 else v
 
     def __setitem__(self, idx, value):
         ix = self._index(idx)
@@ -163,7 +163,7 @@ ENV = dict(np=np, math=math, FArr=FArr, f_reshape=f_reshape, f_sum=f_sum, f_size
 
 INTRINSICS = {"reshape": "f_reshape", "sum": "f_sum", "size": "f_size", "matmul": "f_matmul", "dot_product": "f_dot",
               "cmplx": "f_cmplx", "real": "f_real", "exp": "f_exp", "cos": "math.cos", "sin": "math.sin", "sqrt": "math.sqrt", "log": "math.log", "floor": "f_floor",
-              "abs": "abs", "minval": "f_minval", "maxval": "f_maxval", "minloc": "f_minloc", "norm2": "f_norm2", "epsilon": "f_epsilon", "sign": "math.copysign", "present": "f_present", "all": "f_all", "any": "f_any", "ubound": "f_ubound", "nint": "f_nint", "conjg": "f_conjg", "transpose": "f_transpose", "max": "max", "min": "min", "mod": "f_mod"}
+              "abs": "abs", "minval": "f_minval", "maxval": "f_maxval", "minloc": "f_minloc", "norm2": "f_norm2", "epsilon": "f_epsilon", "sign": "math.copysign", "present": "f_present", "len": "len", "all": "f_all", "any": "f_any", "ubound": "f_ubound", "nint": "f_nint", "conjg": "f_conjg", "transpose": "f_transpose", "max": "max", "min": "min", "mod": "f_mod"}
 ENV["f_epsilon"] = lambda x: 2.220446049250313e-16
 ENV["f_present"] = lambda x: x is not None
 ENV["f_minval"] = lambda x, dim=None: (np.min(x.a if isinstance(x, FArr) else x) if dim is None else np.min(x.a if isinstance(x, FArr) else x, axis=int(dim) - 1))
@@ -327,7 +327,7 @@ def _expr(s, arrays):
             continue
         out += pyname
         i = j
-    return out
+    return out.replace("]%", "].").replace(")%", ").")        # component of an indexed element: a(i)%b
 
 
 def transpile(src, kind, name, call_map=None, extra_arrays=()):
@@ -370,6 +370,12 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
                 pm = re.match(r"(\w+)\s*=\s*(.*)$", e)
                 if pm and "parameter" in attrs:        # named constant with its value
                     local_alloc.append("%s = %s" % (pm.group(1), _expr(pm.group(2), arrays)))
+                    continue
+                pa = re.match(r"(\w+)\s*\(([^=]*)\)\s*=\s*(.*)$", e)
+                if pa and "parameter" in attrs:        # constant array: name(bounds) = reshape(...)
+                    arrays.add(pa.group(1))
+                    los = [_expr(x.split(":")[0], arrays) if ":" in x else "1" for x in _split_top(pa.group(2))]
+                    local_alloc.append("%s = FArr(np.array(%s, order='F'), (%s,))" % (pa.group(1), _expr(pa.group(3), arrays), ", ".join(los)))
                     continue
                 em = re.match(r"(\w+)\s*\((.*)\)$", e)
                 if not em:
