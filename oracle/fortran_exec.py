@@ -546,9 +546,9 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
             py.append("%s%s = new_object(%r)" % (ind, mm.group(1).replace("%", "."), mm.group(1).split("%")[-1]))
             continue
         s = re.sub(r",\s*source\s*=\s*[^()]*\)$", ")", s)        # allocate(a(n), source=0.0_dp): arrays are zeroed anyway
-        mm = re.match(r"allocate\s*\(\s*(\w+)\s*\((.*)\)\s*\)$", s, re.I)
+        mm = re.match(r"allocate\s*\(\s*([\w%]+)\s*\((.*)\)\s*\)$", s, re.I)
         if mm:
-            arrays.add(mm.group(1))
+            arrays.add(mm.group(1).split("%")[-1])
             los, shp = [], []
             for dspec in _split_top(mm.group(2)):
                 if ":" in dspec:
@@ -558,7 +558,7 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
                 else:
                     los.append("1")
                     shp.append(_expr(dspec, arrays))
-            py.append("%s%s = FArr(np.zeros((%s,), dtype=%s, order='F'), (%s,))" % (ind, mm.group(1), ", ".join(shp),
+            py.append("%s%s = FArr(np.zeros((%s,), dtype=%s, order='F'), (%s,))" % (ind, mm.group(1).replace("%", "."), ", ".join(shp),
                                                                                 dtypes.get(mm.group(1), "int"), ", ".join(los)))
             continue
         mm = re.match(r"(\w+)\s*\(\s*:\s*\)\s*=\s*\[\s*\(\s*(\w+)\s*,\s*\2\s*=\s*(.*?),\s*(.*?)\)\s*\]$", s)

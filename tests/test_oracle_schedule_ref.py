@@ -36,3 +36,20 @@ def test_partition_logic_equals_the_executed_reference_source():
             assert np.array_equal(idx, schedule.get_indices_with_workload(size, rank, 1, n, load))
             seen.extend(int(i) for i in idx)
         assert sorted(seen) == list(range(1, n + 1))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/dftbp/type/parallelks.F90"), reason="reference tree not present")
+def test_kpoint_spin_distribution_equals_the_executed_reference_source():
+    """TParallelKS_init (type/parallelks.F90:46-89): the (k-point, spin) pairs of every group, round-robin."""
+    import types
+    f = fx.compile_routine(open("/root/reference/src/dftbp/type/parallelks.F90").read(), "subroutine", "TParallelKS_init",
+                           extra_arrays=("nGroupKS", "groupKS", "localKS"))[0]
+    for n_group, n_k, n_s in ((1, 1, 1), (2, 1, 2), (8, 32, 1), (3, 5, 2), (8, 3, 2)):
+        seen = []
+        for my in range(n_group):
+            this = types.SimpleNamespace()
+            f(this, types.SimpleNamespace(nGroup=n_group, myGroup=my), n_k, n_s)
+            local = [tuple(int(v) for v in col) for col in np.asarray(this.localKS).T] if this.nLocalKS else []
+            assert local == schedule.parallel_ks(n_group, my, n_k, n_s)
+            seen += local
+        assert sorted(seen) == sorted((k, s) for s in range(1, n_s + 1) for k in range(1, n_k + 1))
