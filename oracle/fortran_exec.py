@@ -45,9 +45,8 @@ class FArr:
             if isinstance(i, slice):
                 lo = lb if i.start is None else int(i.start)
                 hi = lb + self.a.shape[k] - 1 if i.stop is None else int(i.stop)
-                assert i.step is None
                 assert lo >= lb and hi <= lb + self.a.shape[k] - 1 or hi < lo, "section out of bounds"
-                out.append(slice(lo - lb, max(hi - lb + 1, lo - lb)))
+                out.append(slice(lo - lb, max(hi - lb + 1, lo - lb), None if i.step is None else int(i.step)))
             elif isinstance(i, (np.ndarray, FArr, list)):          # vector subscript
                 v = np.asarray(i.a if isinstance(i, FArr) else i, dtype=np.int64) - lb
                 assert v.size == 0 or (v.min() >= 0 and v.max() < self.a.shape[k]), "vector subscript out of bounds"

@@ -3,7 +3,7 @@
 
 TEST INFRASTRUCTURE ONLY.  Routines, read where they lie under /root/reference:
     unpackHS_real, unpackHS_cmplx_kpts, packHS_real, packHS_cmplx_kpts      dftb/sparse2dense.F90
-    mullikenPerOrbital, mullikenPerBlock                                    dftb/populations.F90
+    mullikenPerOrbital, mullikenPerBlock, mullikenPerAtom, getOnsitePopulation  dftb/populations.F90
     addShift_atom, addShift_block                                           dftb/shift.F90
     buildH0, buildS, buildDiatomicBlocks, getFirstDerivFiniteDiff           dftb/nonscc.F90
     derivativeNonSccEuclidian, derivative_blockEuclidean                    dftb/forces.F90
@@ -55,6 +55,11 @@ def routines():
         r[name] = fx.compile_routine(s2d, "subroutine", name, CALLS)[0]
     for name in ("mullikenPerOrbital", "mullikenPerBlock"):
         r[name] = fx.compile_routine(pop, "subroutine", name, CALLS, extra_arrays=("nOrbAtom", "nOrbSpecies"))[0]
+    pcalls = dict(CALLS)
+    pcalls["mullikenPerOrbital"] = lambda a: "mullikenPerOrbital(%s)" % ", ".join(a)
+    for name in ("mullikenPerAtom", "getOnsitePopulation"):
+        r[name] = fx.compile_routine(pop, "subroutine", name, pcalls, extra_env=dict(mullikenPerOrbital=r["mullikenPerOrbital"]),
+                                     extra_arrays=("nOrbAtom", "nOrbSpecies"))[0]
     for name in ("addShift_atom", "addShift_block"):
         r[name] = fx.compile_routine(shf, "subroutine", name, CALLS, extra_arrays=("nOrbAtom", "nOrbSpecies"))[0]
     # buildH0 / buildS: the reference's loops, rotation driver and shell-pair routines; integrals from the oracle
@@ -206,6 +211,15 @@ def run_case(R, d):
     f(None, W(f, "qq", qb), W(f, "over", d["over"]), W(f, "rho", d["rho"]), orb, W(f, "iNeighbour", iN), W(f, "nNeighbourSK", nN),
       W(f, "img2CentCell", img), W(f, "iPair", iP))
     out["mulliken_block"] = qb
+    f = R["mullikenPerAtom"]
+    qa = np.linspace(-1.0, 1.0, nA)                                # accumulates into qq
+    f(None, W(f, "qq", qa), W(f, "over", d["over"]), W(f, "rho", d["rho"]), orb, W(f, "iNeighbour", iN), W(f, "nNeighbourSK", nN),
+      W(f, "img2CentCell", img), W(f, "iPair", iP))
+    out["mulliken_atom"] = qa
+    f = R["getOnsitePopulation"]
+    qo = np.full(nA, 7.0)
+    f(W(f, "rho", d["rho"]), orb, W(f, "iPair", iP), W(f, "qq", qo))
+    out["onsite_population"] = qo
     # buildH0 / buildS on the reference's TOrbitals view of the model
     model = d["model"]
     nSp, mShell = model.nSpecies, model.mShell

@@ -86,6 +86,8 @@ def test_oracle_equals_the_executed_reference_source(name, gold):
             _cmp(gold, name, "edmc_" + tag, np.asfortranarray(oracle.energy_density_matrix(Cz, fill, e)), 1e-14)
             # the reference scales the eigenvectors and scales them back: they return to rounding
             assert np.abs(gold["%s__dm_%s_cback" % (name, tag)] - C).max() <= 1e-14 * np.abs(C).max()
+    _cmp(gold, name, "mulliken_atom", oracle.mulliken_per_atom(model, geo, d["over"], d["rho"], qq=np.linspace(-1.0, 1.0, nA)), 1e-14)
+    _cmp(gold, name, "onsite_population", oracle.onsite_population(geo, d["rho"]), 1e-15)
     for zero in (True, False):
         ham = oracle.add_shift(model, geo, d["ham0"].copy(), d["over"], d["shift_atom"], is_input_zero=zero)
         _cmp(gold, name, "add_shift_atom_%d" % zero, np.asfortranarray(ham.T), 1e-15)

@@ -52,6 +52,8 @@ def test_kernels_equal_the_executed_reference_source(name):
         cmp("pack_cplx", hp.packHS(d["rho"].copy(), d["square_c"].copy(order="F"), kpoint=d["kpoint"], kweight=d["kweight"]), 1e-13)
         qq = hp.mulliken(d["over"], d["rho"])
         cmp("mulliken_orbital", np.asfortranarray(qq.T[:mOrb]), 1e-13)
+        cmp("mulliken_atom", hp.mullikenPerAtom(d["over"], d["rho"], qq=np.linspace(-1.0, 1.0, nA)), 1e-13)
+        cmp("onsite_population", hp.getOnsitePopulation(d["rho"]), 1e-15)
         for zero in (True, False):
             ham = hp.addShift(d["ham0"].copy(), d["over"], np.ascontiguousarray(d["shift_atom"]), is_input_zero=zero)
             cmp("add_shift_atom_%d" % zero, np.asfortranarray(ham.T), 1e-14)
