@@ -127,9 +127,26 @@ def f_size(x, dim=None):
 
 
 def f_matmul(a, b):
-    a = a.a if isinstance(a, FArr) else a
-    b = b.a if isinstance(b, FArr) else b
-    return np.matmul(a, b)
+    """small products as the compiler's inline loops: serial sum over the contracted index, a product and an addition
+    per term (no fused multiply-add -- x86-64 baseline); large ones through BLAS"""
+    a = np.asarray(a.a if isinstance(a, FArr) else a)
+    b = np.asarray(b.a if isinstance(b, FArr) else b)
+    if a.size * (b.shape[1] if b.ndim == 2 else 1) > 20000 or np.iscomplexobj(a) or np.iscomplexobj(b):
+        return np.matmul(a, b)
+    al, bl = a.tolist(), b.tolist()
+    if b.ndim == 1:
+        return np.array([_dot_serial(row, bl) for row in (al if a.ndim == 2 else [al])]) if a.ndim == 2 else _dot_serial(al, bl)
+    cols = list(zip(*bl))
+    if a.ndim == 1:
+        return np.array([_dot_serial(al, c) for c in cols])
+    return np.array([[_dot_serial(row, c) for c in cols] for row in al])
+
+
+def _dot_serial(x, y):
+    acc = 0.0
+    for u, v in zip(x, y):
+        acc = acc + u * v
+    return acc
 
 
 def f_dot(a, b):
@@ -161,10 +178,12 @@ ENV = dict(np=np, math=math, FArr=FArr, f_reshape=f_reshape, f_sum=f_sum, f_size
            f_conjg=np.conj, f_transpose=np.transpose, pi=3.14159265358979323846264338327950288, imag=1j)
 
 INTRINSICS = {"reshape": "f_reshape", "sum": "f_sum", "size": "f_size", "matmul": "f_matmul", "dot_product": "f_dot",
-              "cmplx": "f_cmplx", "real": "f_real", "exp": "f_exp", "cos": "math.cos", "sin": "math.sin", "sqrt": "math.sqrt", "log": "math.log", "floor": "f_floor",
-              "abs": "abs", "minval": "f_minval", "maxval": "f_maxval", "minloc": "f_minloc", "norm2": "f_norm2", "epsilon": "f_epsilon", "sign": "math.copysign", "present": "f_present", "len": "len", "all": "f_all", "any": "f_any", "ubound": "f_ubound", "nint": "f_nint", "conjg": "f_conjg", "transpose": "f_transpose", "max": "max", "min": "min", "mod": "f_mod"}
+              "cmplx": "f_cmplx", "real": "f_real", "exp": "f_exp", "cos": "math.cos", "sin": "math.sin", "sqrt": "f_sqrt", "log": "math.log", "floor": "f_floor",
+              "abs": "f_abs", "minval": "f_minval", "maxval": "f_maxval", "minloc": "f_minloc", "norm2": "f_norm2", "epsilon": "f_epsilon", "sign": "math.copysign", "present": "f_present", "len": "len", "all": "f_all", "any": "f_any", "ubound": "f_ubound", "nint": "f_nint", "conjg": "f_conjg", "transpose": "f_transpose", "max": "max", "min": "min", "mod": "f_mod"}
 ENV["f_epsilon"] = lambda x: 2.220446049250313e-16
 ENV["f_present"] = lambda x: x is not None
+ENV["f_sqrt"] = lambda x: np.sqrt(x.a if isinstance(x, FArr) else x) if isinstance(x, (FArr, np.ndarray)) else math.sqrt(x)
+ENV["f_abs"] = lambda x: np.abs(x.a if isinstance(x, FArr) else x) if isinstance(x, (FArr, np.ndarray)) else abs(x)
 ENV["f_minval"] = lambda x, dim=None: (np.min(x.a if isinstance(x, FArr) else x) if dim is None else np.min(x.a if isinstance(x, FArr) else x, axis=int(dim) - 1))
 ENV["f_maxval"] = lambda x, dim=None: (np.max(x.a if isinstance(x, FArr) else x) if dim is None else np.max(x.a if isinstance(x, FArr) else x, axis=int(dim) - 1))
 ENV["f_minloc"] = lambda x, dim=None: int(np.argmin(x.a if isinstance(x, FArr) else x)) + (x.lb[0] if isinstance(x, FArr) else 1)
@@ -172,7 +191,7 @@ ENV["f_norm2"] = lambda x: math.sqrt(f_sum(np.asarray(x.a if isinstance(x, FArr)
 ENV["f_not"] = lambda x: np.logical_not(x.a if isinstance(x, FArr) else x) if isinstance(x, (FArr, np.ndarray)) else (not x)
 ENV["f_all"] = lambda x: bool(np.all(x.a if isinstance(x, FArr) else x))
 ENV["f_any"] = lambda x: bool(np.any(x.a if isinstance(x, FArr) else x))
-ENV["f_floor"] = lambda x: int(math.floor(x))
+ENV["f_floor"] = lambda x: np.floor(x.a if isinstance(x, FArr) else x).astype(np.int64) if isinstance(x, (FArr, np.ndarray)) else int(math.floor(x))
 ENV["f_ubound"] = lambda x, dim: x.lb[int(dim) - 1] + x.a.shape[int(dim) - 1] - 1
 ENV["f_nint"] = lambda x: int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
 ENV["LoopExit"], ENV["LoopCycle"] = LoopExit, LoopCycle
@@ -443,9 +462,17 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
             py.append(ind + "pass")
             ind = ind[:-4]
             continue
-        mm = re.match(r"where\s*\((.*)\)$", s, re.I)
+        mm = re.match(r"where\s*(\(.*)$", s, re.I)
         if mm:
-            wheres.append(_expr(mm.group(1), arrays))
+            e_ = _match(mm.group(1), 0)
+            cond_, rest_ = mm.group(1)[1:e_], mm.group(1)[e_ + 1:].strip()
+            if rest_:       # one-line form: where (mask) a = b
+                am = re.match(r"([^=]+?)=(?!=)(.*)$", rest_)
+                tgt = am.group(1).strip()
+                tgt_e = "%s.a" % tgt if tgt in declared_arrays else _expr(tgt, arrays)
+                py.append("%snp.copyto(%s, %s, where=%s)" % (ind, tgt_e, _expr(am.group(2), arrays), _expr(cond_, arrays)))
+            else:
+                wheres.append(_expr(cond_, arrays))
             continue
         if re.match(r"end\s*where$", low):
             wheres.pop()
