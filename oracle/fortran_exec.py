@@ -179,9 +179,21 @@ ENV = dict(np=np, math=math, FArr=FArr, f_reshape=f_reshape, f_sum=f_sum, f_size
 
 INTRINSICS = {"reshape": "f_reshape", "sum": "f_sum", "size": "f_size", "matmul": "f_matmul", "dot_product": "f_dot",
               "cmplx": "f_cmplx", "real": "f_real", "exp": "f_exp", "cos": "math.cos", "sin": "math.sin", "sqrt": "f_sqrt", "log": "math.log", "floor": "f_floor",
-              "abs": "f_abs", "minval": "f_minval", "maxval": "f_maxval", "minloc": "f_minloc", "norm2": "f_norm2", "epsilon": "f_epsilon", "sign": "math.copysign", "present": "f_present", "len": "len", "all": "f_all", "any": "f_any", "ubound": "f_ubound", "nint": "f_nint", "conjg": "f_conjg", "transpose": "f_transpose", "max": "max", "min": "min", "mod": "f_mod"}
+              "abs": "f_abs", "minval": "f_minval", "maxval": "f_maxval", "minloc": "f_minloc", "norm2": "f_norm2", "epsilon": "f_epsilon", "sign": "math.copysign", "present": "f_present", "len": "len", "shape": "f_shape", "product": "f_product", "all": "f_all", "any": "f_any", "ubound": "f_ubound", "nint": "f_nint", "conjg": "f_conjg", "transpose": "f_transpose", "max": "max", "min": "min", "mod": "f_mod"}
 ENV["f_epsilon"] = lambda x: 2.220446049250313e-16
+def _f_assign(target, value):
+    """whole-array assignment; an unallocated allocatable (None) is allocated with the shape of the value"""
+    if isinstance(target, FArr):
+        target.assign(value)
+        return target
+    v = value.a if isinstance(value, FArr) else value
+    return FArr(np.array(v, order="F"))
+
+
+ENV["f_assign"] = _f_assign
 ENV["f_present"] = lambda x: x is not None
+ENV["f_product"] = lambda x: int(np.prod(x.a if isinstance(x, FArr) else x)) if np.asarray(x.a if isinstance(x, FArr) else x).dtype.kind in "iu" else float(np.prod(x.a if isinstance(x, FArr) else x))
+ENV["f_shape"] = lambda x: np.array((x.a if isinstance(x, FArr) else np.asarray(x)).shape)
 ENV["f_sqrt"] = lambda x: np.sqrt(x.a if isinstance(x, FArr) else x) if isinstance(x, (FArr, np.ndarray)) else math.sqrt(x)
 ENV["f_abs"] = lambda x: np.abs(x.a if isinstance(x, FArr) else x) if isinstance(x, (FArr, np.ndarray)) else abs(x)
 ENV["f_minval"] = lambda x, dim=None: (np.min(x.a if isinstance(x, FArr) else x) if dim is None else np.min(x.a if isinstance(x, FArr) else x, axis=int(dim) - 1))
@@ -619,7 +631,7 @@ def transpile(src, kind, name, call_map=None, extra_arrays=()):
             if mm.group(1).strip() in int_scalars and "/" in rhs:
                 rhs = "int(%s)" % rhs     # integer division / real -> integer conversion: truncation (non-negative operands)
             if mm.group(1).strip() in declared_arrays:
-                py.append("%s%s.assign(%s)" % (ind, mm.group(1).strip(), rhs))       # whole-array assignment
+                py.append("%s%s = f_assign(%s, %s)" % (ind, mm.group(1).strip(), mm.group(1).strip(), rhs))       # whole-array assignment
                 continue
             py.append("%s%s = %s" % (ind, _expr(mm.group(1), arrays), rhs))
             continue
